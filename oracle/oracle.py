@@ -1,0 +1,327 @@
+"""ctypes front-end of oracle.c + numpy compositions of the module-level forwards.
+
+TEST INFRASTRUCTURE ONLY -- imported by tests/, __graft_entry__.smoke() and
+bench.py's cpu_baseline / --impl reference leg.  The product (tg-pose_b200/)
+never imports this.  Pinned against the unmodified reference by
+tests/test_oracle_golden.py (fixtures: tests/golden/, made by make_golden.py).
+
+numpy in, numpy out; all float32 C-contiguous, indices int64 (chamfer: int32),
+mirroring the dtypes the reference produces.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "_build", "liboracle.so")
+
+
+def build(force=False):
+    """Compile oracle.c (gcc via oracle/Makefile). Building the checker is not using it."""
+    src = os.path.join(_HERE, "oracle.c")
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-s", "-C", _HERE], env={**os.environ, "CC": "gcc"})
+    return _SO
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = ctypes.CDLL(build())
+        _lib.orc_num_threads.restype = ctypes.c_int
+    return _lib
+
+
+def num_threads():
+    return int(lib().orc_num_threads())
+
+
+def set_num_threads(n):
+    lib().orc_set_num_threads(ctypes.c_int(int(n)))
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _i64(a):
+    return np.ascontiguousarray(a, dtype=np.int64)
+
+
+def _p(a):
+    return a.ctypes.data_as(ctypes.c_void_p) if a is not None else None
+
+
+# ----------------------------------------------------------------------------- primitive ops
+def knn_xyz(x, k, return_dist=False):
+    """gcn3d.py:14-23 for (B,N,3) inputs -> (B,N,k) int64 (bit-exact recipe, ties -> lower index)."""
+    x = _f32(x)
+    B, N, D = x.shape
+    assert D == 3
+    idx = np.empty((B, N, k), np.int64)
+    dist = np.empty((B, N, N), np.float32) if return_dist else None
+    lib().orc_knn_xyz(_p(x), B, N, k, _p(idx), _p(dist))
+    return (idx, dist) if return_dist else idx
+
+
+def knn_feat(x, k, return_dist=False):
+    """gcn3d.py:14-23 for (B,N,D) feature inputs (RF-F)."""
+    x = _f32(x)
+    B, N, D = x.shape
+    idx = np.empty((B, N, k), np.int64)
+    dist = np.empty((B, N, N), np.float32) if return_dist else None
+    lib().orc_knn_feat(_p(x), B, N, D, k, _p(idx), _p(dist))
+    return (idx, dist) if return_dist else idx
+
+
+def get_neighbor_index(x, k):
+    return knn_xyz(x, k) if x.shape[-1] == 3 else knn_feat(x, k)
+
+
+def get_nearest_index(target, source):
+    """gcn3d.py:26-35 -> (B,N,1) int64."""
+    t, s = _f32(target), _f32(source)
+    B, N, _ = t.shape
+    M = s.shape[1]
+    idx = np.empty((B, N, 1), np.int64)
+    lib().orc_nearest(_p(t), _p(s), B, N, M, _p(idx))
+    return idx
+
+
+def indexing_neighbor(tensor, index):
+    """gcn3d.py:38-46 -> (B,M,k,C)."""
+    t, index = _f32(tensor), _i64(index)
+    B, N, C = t.shape
+    _, M, k = index.shape
+    out = np.empty((B, M, k, C), np.float32)
+    lib().orc_gather(_p(t), _p(index), B, N, M, k, C, _p(out))
+    return out
+
+
+def direction_norm(xyz, idx):
+    """gcn3d.py:48-58 -> (B,N,k,3)."""
+    xyz, idx = _f32(xyz), _i64(idx)
+    B, N, k = idx.shape
+    out = np.empty((B, N, k, 3), np.float32)
+    lib().orc_dirnorm(_p(xyz), _p(idx), B, N, k, _p(out))
+    return out
+
+
+def surface_conv(xyz, idx, directions, S, C):
+    """gcn3d.py:91-106 -> (B,N,C)."""
+    xyz, idx, directions = _f32(xyz), _i64(idx), _f32(directions)
+    B, N, k = idx.shape
+    out = np.empty((B, N, C), np.float32)
+    lib().orc_surface_conv(_p(xyz), _p(idx), _p(directions), B, N, k, S, C, _p(out))
+    return out
+
+
+def layer_conv(xyz, idx, directions, P, S, C):
+    """gcn3d.py:157-180 given P = fm @ weights + bias, (B,N,(S+1)C) -> (B,N,C)."""
+    xyz, idx, directions, P = _f32(xyz), _i64(idx), _f32(directions), _f32(P)
+    B, N, k = idx.shape
+    out = np.empty((B, N, C), np.float32)
+    lib().orc_layer_conv(_p(xyz), _p(idx), _p(directions), _p(P), B, N, k, S, C, _p(out))
+    return out
+
+
+def gemm_bias(A, W, bias=None):
+    """A (..., K) @ W (K, Nout) + bias."""
+    A, W = _f32(A), _f32(W)
+    K, Nout = W.shape
+    M = A.size // K
+    b = _f32(bias) if bias is not None else None
+    out = np.empty(A.shape[:-1] + (Nout,), np.float32)
+    lib().orc_gemm_bias(_p(A), _p(W), _p(b), ctypes.c_long(M), K, Nout, _p(out))
+    return out
+
+
+def gather_max(f, idx, rows=None, return_arg=False):
+    """max over the k gathered rows; rows selects a subset of points (Pool, gcn3d.py:236-244)."""
+    f, idx = _f32(f), _i64(idx)
+    B, N, C = f.shape
+    k = idx.shape[2]
+    r = _i64(rows) if rows is not None else None
+    M = N if r is None else r.shape[0]
+    out = np.empty((B, M, C), np.float32)
+    arg = np.empty((B, M, C), np.uint8) if return_arg else None
+    lib().orc_gather_max(_p(f), _p(idx), _p(r), B, N, M, k, C, _p(out), _p(arg))
+    return (out, arg) if return_arg else out
+
+
+def orl_global(f, idx):
+    """gcn3d.py:210-217 before the .repeat -> (B,C)."""
+    f, idx = _f32(f), _i64(idx)
+    B, N, C = f.shape
+    g = np.empty((B, C), np.float32)
+    lib().orc_orl_global(_p(f), _p(idx), B, N, idx.shape[2], C, _p(g))
+    return g
+
+
+def chamfer_forward(xyz1, xyz2, contract=True):
+    """chamfer3D.cu:12-154 -> dist1 (B,n), dist2 (B,m) f32, idx1, idx2 int32."""
+    a, b = _f32(xyz1), _f32(xyz2)
+    B, n, _ = a.shape
+    m = b.shape[1]
+    d1, d2 = np.empty((B, n), np.float32), np.empty((B, m), np.float32)
+    i1, i2 = np.empty((B, n), np.int32), np.empty((B, m), np.int32)
+    c = 1 if contract else 0
+    lib().orc_chamfer_nn(_p(a), _p(b), B, n, m, c, _p(d1), _p(i1))
+    lib().orc_chamfer_nn(_p(b), _p(a), B, m, n, c, _p(d2), _p(i2))
+    return d1, d2, i1, i2
+
+
+def chamfer_backward(xyz1, xyz2, gd1, gd2, idx1, idx2):
+    """chamfer3D.cu:155-195 -> gradxyz1 (B,n,3), gradxyz2 (B,m,3)."""
+    a, b = _f32(xyz1), _f32(xyz2)
+    B, n, _ = a.shape
+    m = b.shape[1]
+    g1, g2 = np.zeros((B, n, 3), np.float32), np.zeros((B, m, 3), np.float32)
+    i1 = np.ascontiguousarray(idx1, np.int32)
+    i2 = np.ascontiguousarray(idx2, np.int32)
+    lib().orc_chamfer_bwd(_p(a), _p(b), _p(_f32(gd1)), _p(_f32(gd2)), _p(i1), _p(i2), B, n, m, _p(g1), _p(g2))
+    return g1, g2
+
+
+# ----------------------------------------------------------------------------- loss tail
+def calc_cd(d1, d2):
+    """TDA_loss_sym_recon.py:495-509: cd_p, cd_t from the two distance arrays."""
+    cd_p = (np.sqrt(d1).mean(1) + np.sqrt(d2).mean(1)) / 2
+    cd_t = d1.mean(1) + d2.mean(1)
+    return cd_p.astype(np.float32), cd_t.astype(np.float32)
+
+
+def calc_dcd(d1, d2, i1, i2, alpha=70.0, n_lambda=0.3):
+    """TDA_loss_sym_recon.py:411-450 (non_reg=False): per-cloud density-aware chamfer loss."""
+    B, n = d1.shape
+    m = d2.shape[1]
+    frac_12, frac_21 = n / m, m / n
+    out = np.empty(B, np.float32)
+    for b in range(B):
+        c1 = np.bincount(i1[b], minlength=m)
+        w1 = (c1[i1[b]].astype(np.float32) ** np.float32(n_lambda) + np.float32(1e-6)) ** -1 * np.float32(frac_21)
+        l1 = (-np.exp(-d1[b] * np.float32(alpha)) * w1 + 1.0).mean()
+        c2 = np.bincount(i2[b], minlength=n)
+        w2 = (c2[i2[b]].astype(np.float32) ** np.float32(n_lambda) + np.float32(1e-6)) ** -1 * np.float32(frac_12)
+        l2 = (-np.exp(-d2[b] * np.float32(alpha)) * w2 + 1.0).mean()
+        out[b] = l1 + 0.5 * l2
+    return out
+
+
+# ----------------------------------------------------------------------------- module forwards
+def conv1x1(x, weight):
+    """nn.Conv1d(kernel_size=1, bias=False) applied on the channel-last view: x (B,N,Cin), weight (Cout,Cin,1)."""
+    w = _f32(weight).reshape(weight.shape[0], weight.shape[1])
+    return gemm_bias(x, np.ascontiguousarray(w.T))
+
+
+def orl_forward(feature, xyz, k, conv2_weight, idx_xyz=None):
+    """gcn3d.py:108-112 / :182-186: conv2(cat[f, g.repeat]) + f."""
+    if idx_xyz is None:
+        idx_xyz = knn_xyz(xyz, k)
+    g = orl_global(feature, idx_xyz)
+    B, N, C = feature.shape
+    cat = np.concatenate([feature, np.broadcast_to(g[:, None, :], (B, N, C))], axis=-1)
+    return conv1x1(cat, conv2_weight) + feature
+
+
+def hs_surface_forward(p, xyz, k, idx=None, idx_orl=None):
+    """HSlayer_surface.forward, gcn3d.py:78-89.  p: dict of numpy params (state_dict names)."""
+    SC = p["directions"].shape[1]
+    C = p["STE_layer.weight"].shape[0]
+    S = SC // C
+    f_ste = conv1x1(xyz, p["STE_layer.weight"])
+    if idx is None:
+        idx = knn_xyz(xyz, k)
+    f = surface_conv(xyz, idx, p["directions"], S, C)
+    f = orl_forward(f, xyz, k, p["conv2.weight"], idx_orl if idx_orl is not None else idx)
+    return f + f_ste
+
+
+def hs_layer_forward(p, xyz, fm, k, idx=None, idx_orl=None):
+    """HS_layer.forward, gcn3d.py:142-155."""
+    C = p["STE_layer.weight"].shape[0]
+    S = p["directions"].shape[1] // C
+    f_ste = conv1x1(fm, p["STE_layer.weight"])
+    if idx is None:
+        idx = knn_feat(fm, k)
+    P = gemm_bias(fm, p["weights"], p["bias"])
+    f = layer_conv(xyz, idx, p["directions"], P, S, C)
+    f = orl_forward(f, xyz, k, p["conv2.weight"], idx_orl)
+    return f + f_ste
+
+
+def pool_forward(xyz, fm, sample_idx, k=4, idx=None):
+    """Pool_layer.forward, gcn3d.py:225-245; sample_idx = torch.randperm(N)[:N//rate] drawn by the caller."""
+    if idx is None:
+        idx = knn_xyz(xyz, k)
+    pooled = gather_max(fm, idx, rows=sample_idx)
+    return np.ascontiguousarray(xyz[:, sample_idx, :]), pooled
+
+
+def bn_eval_relu(x, p, prefix, relu=True, eps=1e-5):
+    """BatchNorm1d in eval mode on channel-last x, then ReLU (FaceRecon.py:58-65)."""
+    w, b = p[prefix + ".weight"], p[prefix + ".bias"]
+    mu, var = p[prefix + ".running_mean"], p[prefix + ".running_var"]
+    y = (x - mu) / np.sqrt(var + np.float32(eps)) * w + b
+    y = y.astype(np.float32)
+    return np.maximum(y, 0) if relu else y
+
+
+def _sub(p, prefix):
+    return {k[len(prefix) + 1:]: v for k, v in p.items() if k.startswith(prefix + ".")}
+
+
+def face_enc_forward(p, xyz, cat_id, perm1, perm2, k=20, obj_c=6, inject=None):
+    """Face_Enc.forward (eval), FaceRecon.py:39-86 -> feat (B,N0,1286).
+
+    perm1/perm2: the two torch.randperm draws Pool_layer makes (gcn3d.py:242).
+    inject: optional list of index arrays in reference call order (12 kNN + 2 nearest)
+    to replay instead of computing (parity tier T2, SURVEY 8c').
+    """
+    it = iter(inject) if inject is not None else None
+
+    def nxt(fn):
+        return _i64(next(it)) if it is not None else fn()
+
+    xyz = _f32(xyz)
+    B, N0, _ = xyz.shape
+    # conv_0: RF-P idx, ORL idx
+    i0 = nxt(lambda: knn_xyz(xyz, k))
+    i0o = nxt(lambda: knn_xyz(xyz, k))
+    fm0 = np.maximum(hs_surface_forward(_sub(p, "conv_0"), xyz, k, i0, i0o), 0)
+    # conv_1: RF-F idx, ORL idx
+    i1 = nxt(lambda: knn_feat(fm0, k))
+    i1o = nxt(lambda: knn_xyz(xyz, k))
+    fm1 = bn_eval_relu(hs_layer_forward(_sub(p, "conv_1"), xyz, fm0, k, i1, i1o), p, "bn1")
+    ip1 = nxt(lambda: knn_xyz(xyz, 4))
+    n1 = N0 // 4
+    v1, fp1 = pool_forward(xyz, fm1, _i64(perm1[:n1]), 4, ip1)
+    k1 = min(k, n1 // 8)
+    i2 = nxt(lambda: knn_feat(fp1, k1))
+    i2o = nxt(lambda: knn_xyz(v1, k1))
+    fm2 = bn_eval_relu(hs_layer_forward(_sub(p, "conv_2"), v1, fp1, k1, i2, i2o), p, "bn2")
+    i3 = nxt(lambda: knn_feat(fm2, k1))
+    i3o = nxt(lambda: knn_xyz(v1, k1))
+    fm3 = bn_eval_relu(hs_layer_forward(_sub(p, "conv_3"), v1, fm2, k1, i3, i3o), p, "bn3")
+    ip2 = nxt(lambda: knn_xyz(v1, 4))
+    n2 = n1 // 4
+    v2, fp2 = pool_forward(v1, fm3, _i64(perm2[:n2]), 4, ip2)
+    k2 = min(k, n2 // 8)
+    i4 = nxt(lambda: knn_feat(fp2, k2))
+    i4o = nxt(lambda: knn_xyz(v2, k2))
+    fm4 = hs_layer_forward(_sub(p, "conv_4"), v2, fp2, k2, i4, i4o)
+    nn1 = nxt(lambda: get_nearest_index(xyz, v1))
+    nn2 = nxt(lambda: get_nearest_index(xyz, v2))
+    up2 = indexing_neighbor(fm2, nn1)[:, :, 0]
+    up3 = indexing_neighbor(fm3, nn1)[:, :, 0]
+    up4 = indexing_neighbor(fm4, nn2)[:, :, 0]
+    one_hot = np.zeros((B, obj_c), np.float32)
+    one_hot[np.arange(B), np.asarray(cat_id).reshape(-1).astype(np.int64)] = 1
+    one_hot = np.broadcast_to(one_hot[:, None, :], (B, N0, obj_c))
+    return np.concatenate([fm0, fm1, up2, up3, up4, one_hot], axis=2).astype(np.float32)

@@ -1,0 +1,279 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference on CPU.
+
+Run here (the build container), where /root/reference exists:
+    python tests/golden/make_golden.py
+The GPU box has no /root/reference; tests only read the committed .npz files.
+
+Every array is produced by the reference's own code:
+  network/fs_net_repo/gcn3d.py   (get_neighbor_index :14, get_nearest_index :26,
+      indexing_neighbor_new :38, get_neighbor_direction_norm :48, HSlayer_surface :60,
+      HS_layer :115, get_ORL_global :210, Pool_layer :219)
+  network/fs_net_repo/FaceRecon.py (Face_Enc :12-86)
+  losses/metrics/CD/chamfer_python.py (distChamfer :18-39) -- the oracle the reference's
+      own unit test compares its CUDA kernel with (losses/metrics/CD/unit_test.py:14-35)
+Nothing is copied from the reference; it is imported and called.
+"""
+import hashlib
+import os
+import sys
+
+import numpy as np
+import torch
+
+REF = os.environ.get("TGPOSE_REFERENCE", "/root/reference")
+OUT = os.path.dirname(os.path.abspath(__file__))
+sys.dont_write_bytecode = True
+sys.path.insert(0, REF)
+
+import config.config  # noqa: E402,F401  (defines the absl flags the ctors read)
+from absl import flags  # noqa: E402
+
+flags.FLAGS(["make_golden"])
+import network.fs_net_repo.gcn3d as gcn3d  # noqa: E402
+from network.fs_net_repo.FaceRecon import Face_Enc  # noqa: E402
+
+sys.path.insert(0, os.path.join(REF, "losses", "metrics", "CD"))
+import chamfer_python  # noqa: E402
+
+torch.set_num_threads(max(1, os.cpu_count() or 1))
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def np_(t):
+    return t.detach().cpu().numpy()
+
+
+def save(name, **arrs):
+    path = os.path.join(OUT, name + ".npz")
+    np.savez_compressed(path, **arrs)
+    print(f"{name}: {os.path.getsize(path) / 1024:.1f} KiB")
+
+
+def ref_dist(x):
+    """the reference's distance matrix, gcn3d.py:18-20, for hashing."""
+    inner = torch.bmm(x, x.transpose(1, 2))
+    q = torch.sum(x ** 2, dim=2)
+    return inner * (-2) + q.unsqueeze(1) + q.unsqueeze(2)
+
+
+def nocs_cloud(g, B, N):
+    """object-sized cloud at camera range."""
+    pts = torch.rand(B, N, 3, generator=g)
+    t = torch.stack([torch.rand(B, generator=g) * 0.6 - 0.3,
+                     torch.rand(B, generator=g) * 0.6 - 0.3,
+                     torch.rand(B, generator=g) * 0.8 + 0.6], dim=1)
+    return (pts - 0.5) * 0.3 + t[:, None, :]
+
+
+@torch.no_grad()
+def knn_cases():
+    g = torch.Generator().manual_seed(1234)
+    out = {}
+    for tag, x, k in [
+        ("a", torch.rand(2, 257, 3, generator=g), 20),
+        ("b", torch.rand(1, 1028, 3, generator=g), 20),
+        ("c", nocs_cloud(g, 2, 257), 20),
+        ("d", torch.rand(3, 64, 3, generator=g), 8),
+        ("e", torch.rand(1, 300, 3, generator=g), 50),
+        ("f", torch.rand(2, 257, 3, generator=g) - 0.5, 4),
+    ]:
+        idx = gcn3d.get_neighbor_index(x, k)
+        out[f"{tag}_x"] = np_(x)
+        out[f"{tag}_k"] = np.int64(k)
+        out[f"{tag}_idx"] = np_(idx).astype(np.int16)
+        out[f"{tag}_dist_sha"] = np.array(sha(np_(ref_dist(x))))
+    # duplicates: half the cloud is a copy of point 0 (PcRandomDropout, data_augmentation.py:95-97)
+    x = torch.rand(1, 96, 3, generator=g)
+    x[:, 48:] = x[:, :1]
+    out["dup_x"] = np_(x)
+    out["dup_k"] = np.int64(8)
+    out["dup_idx"] = np_(gcn3d.get_neighbor_index(x, 8)).astype(np.int16)
+    out["dup_dist"] = np_(ref_dist(x))
+    save("knn_xyz", **out)
+
+    out = {}
+    for tag, B, N, D, k, scale in [("a", 2, 128, 32, 8, 1.0), ("b", 1, 257, 128, 20, 0.3), ("c", 1, 64, 256, 8, 0.2)]:
+        x = torch.randn(B, N, D, generator=g) * scale
+        out[f"{tag}_x"] = np_(x)
+        out[f"{tag}_k"] = np.int64(k)
+        out[f"{tag}_idx"] = np_(gcn3d.get_neighbor_index(x, k)).astype(np.int16)
+        out[f"{tag}_dist"] = np_(ref_dist(x))
+    save("knn_feat", **out)
+
+    out = {}
+    for tag, B, N, M in [("a", 2, 1028, 257), ("b", 2, 257, 64), ("c", 1, 100, 7)]:
+        t = torch.rand(B, N, 3, generator=g)
+        perm = torch.randperm(N, generator=g)[:M]
+        s = t[:, perm, :].contiguous()  # sources are a subset of the targets, as in FaceRecon.py:69-70
+        out[f"{tag}_t"], out[f"{tag}_s"] = np_(t), np_(s)
+        out[f"{tag}_idx"] = np_(gcn3d.get_nearest_index(t, s)).astype(np.int16)
+    t = torch.rand(1, 50, 3, generator=g)
+    s = torch.rand(1, 33, 3, generator=g)
+    out["d_t"], out["d_s"] = np_(t), np_(s)
+    out["d_idx"] = np_(gcn3d.get_nearest_index(t, s)).astype(np.int16)
+    save("nearest", **out)
+
+
+@torch.no_grad()
+def gather_dir_cases():
+    g = torch.Generator().manual_seed(77)
+    x = torch.rand(2, 128, 3, generator=g)
+    idx = gcn3d.get_neighbor_index(x, 8)
+    f = torch.randn(2, 128, 24, generator=g)
+    x2 = x.clone()
+    x2[:, 64:] = x2[:, :1]  # zero direction vectors must stay zero (F.normalize eps)
+    idx2 = gcn3d.get_neighbor_index(x2, 8)
+    save("gather_dir",
+         x=np_(x), idx=np_(idx).astype(np.int16), f=np_(f),
+         gathered_sha=np.array(sha(np_(gcn3d.indexing_neighbor_new(f, idx)))),
+         dirs=np_(gcn3d.get_neighbor_direction_norm(x, idx)),
+         x2=np_(x2), idx2=np_(idx2).astype(np.int16),
+         dirs2=np_(gcn3d.get_neighbor_direction_norm(x2, idx2)))
+
+
+def params_np(mod):
+    return {k: np_(v) for k, v in mod.state_dict().items()}
+
+
+@torch.no_grad()
+def conv_cases():
+    g = torch.Generator().manual_seed(99)
+    out = {}
+    # surface conv: kernel_num 16, S 7, N 128, k 8
+    torch.manual_seed(3)
+    surf = gcn3d.HSlayer_surface(kernel_num=16, support_num=7).eval()
+    x = torch.rand(2, 128, 3, generator=g)
+    k = 8
+    rf, idx = gcn3d.get_receptive_fields(k, x, mode='RF-P')
+    out["s_x"], out["s_k"] = np_(x), np.int64(k)
+    out["s_idx"] = np_(idx).astype(np.int16)
+    for n, v in params_np(surf).items():
+        out["s_p_" + n] = v
+    out["s_graph"] = np_(surf.graph_conv(rf, x, k))
+    out["s_fwd"] = np_(surf(x, k))
+
+    # layer conv: 16 -> 32, S 7, N 128, k 8 (idx from feature space)
+    torch.manual_seed(4)
+    lay = gcn3d.HS_layer(16, 32, support_num=7).eval()
+    fm = torch.randn(2, 128, 16, generator=g) * 0.5
+    rf, idx = gcn3d.get_receptive_fields(k, x, feature_map=fm, mode='RF-F')
+    out["l_fm"] = np_(fm)
+    out["l_idx"] = np_(idx).astype(np.int16)
+    out["l_idx_orl"] = np_(gcn3d.get_neighbor_index(x, k)).astype(np.int16)
+    for n, v in params_np(lay).items():
+        out["l_p_" + n] = v
+    out["l_proj"] = np_(fm @ lay.weights + lay.bias)
+    out["l_graph"] = np_(lay.graph_conv(rf, idx, fm, x, k))
+    out["l_orl_g"] = np_(gcn3d.get_ORL_global(lay.graph_conv(rf, idx, fm, x, k), x, k)[:, 0, :])
+    out["l_fwd"] = np_(lay(x, fm, k))
+
+    # second layer shape: 32 -> 16 with k 20, N 64 (k close to N/3), non-multiple-of-4 N
+    torch.manual_seed(5)
+    lay2 = gcn3d.HS_layer(32, 16, support_num=7).eval()
+    x3 = torch.rand(1, 61, 3, generator=g)
+    fm3 = torch.randn(1, 61, 32, generator=g)
+    k3 = 20
+    rf3, idx3 = gcn3d.get_receptive_fields(k3, x3, feature_map=fm3, mode='RF-F')
+    out["m_x"], out["m_fm"], out["m_k"] = np_(x3), np_(fm3), np.int64(k3)
+    out["m_idx"] = np_(idx3).astype(np.int16)
+    out["m_idx_orl"] = np_(gcn3d.get_neighbor_index(x3, k3)).astype(np.int16)
+    for n, v in params_np(lay2).items():
+        out["m_p_" + n] = v
+    out["m_graph"] = np_(lay2.graph_conv(rf3, idx3, fm3, x3, k3))
+    out["m_fwd"] = np_(lay2(x3, fm3, k3))
+
+    # pool
+    pool = gcn3d.Pool_layer(pooling_rate=4, neighbor_num=4)
+    torch.manual_seed(7)
+    vp, fp = pool(x, fm)
+    torch.manual_seed(7)
+    perm = torch.randperm(128)
+    out["p_perm"] = np_(perm).astype(np.int16)
+    out["p_v"], out["p_f"] = np_(vp), np_(fp)
+    save("convs", **out)
+
+
+@torch.no_grad()
+def chamfer_cases():
+    # losses/metrics/CD/unit_test.py:14-35: rand(4,100,3) vs rand(4,200,3), dist MSE < 1e-8, idx equal
+    g = torch.Generator().manual_seed(2024)
+    out = {}
+    for tag, B, n, m in [("a", 4, 100, 200), ("b", 2, 1028, 1024), ("c", 1, 7, 3)]:
+        p1 = torch.rand(B, n, 3, generator=g)
+        p2 = torch.rand(B, m, 3, generator=g)
+        d1, d2, i1, i2 = chamfer_python.distChamfer(p1, p2)
+        out[f"{tag}_p1"], out[f"{tag}_p2"] = np_(p1), np_(p2)
+        out[f"{tag}_d1"], out[f"{tag}_d2"] = np_(d1), np_(d2)
+        out[f"{tag}_i1"], out[f"{tag}_i2"] = np_(i1).astype(np.int16), np_(i2).astype(np.int16)
+    # backward: autograd through the pure-torch chamfer (unit_test.py:19-20 only runs it; we pin values)
+    p1 = out["a_p1"]
+    p2 = out["a_p2"]
+    gw = torch.Generator().manual_seed(5)
+    w1, w2 = torch.rand(4, 100, generator=gw), torch.rand(4, 200, generator=gw)
+    with torch.enable_grad():
+        t1 = torch.tensor(p1, requires_grad=True)
+        t2 = torch.tensor(p2, requires_grad=True)
+        x, y = t1.double(), t2.double()
+        P = (x.pow(2).sum(2)[:, :, None] + y.pow(2).sum(2)[:, None, :] - 2 * torch.bmm(x, y.transpose(2, 1)))
+        loss = (P.min(2)[0] * w1).sum() + (P.min(1)[0] * w2).sum()
+        loss.backward()
+    out["a_w1"], out["a_w2"] = np_(w1), np_(w2)
+    out["a_g1"], out["a_g2"] = np_(t1.grad), np_(t2.grad)
+    save("chamfer", **out)
+
+
+@torch.no_grad()
+def face_enc_case():
+    """Face_Enc (eval) at B=2, N=128; records every kNN / nearest index tensor in call order (T2)."""
+    torch.manual_seed(0)
+    enc = Face_Enc().eval()
+    sd = enc.state_dict()
+    g = torch.Generator().manual_seed(1234)
+    B, N = 2, 128
+    pts = torch.rand(B, N, 3, generator=g)
+    cat_id = torch.randint(0, 6, (B, 1), generator=g).float()
+    pts = pts - pts.mean(dim=1, keepdim=True)  # PoseNet9D.py:48
+
+    calls = []
+    orig_knn, orig_nn = gcn3d.get_neighbor_index, gcn3d.get_nearest_index
+
+    def rec_knn(v, k):
+        r = orig_knn(v, k)
+        calls.append(np_(r).astype(np.int16))
+        return r
+
+    def rec_nn(t, s):
+        r = orig_nn(t, s)
+        calls.append(np_(r).astype(np.int16))
+        return r
+
+    gcn3d.get_neighbor_index, gcn3d.get_nearest_index = rec_knn, rec_nn
+    try:
+        torch.manual_seed(7)
+        feat, _ = enc(pts, cat_id)
+    finally:
+        gcn3d.get_neighbor_index, gcn3d.get_nearest_index = orig_knn, orig_nn
+    torch.manual_seed(7)
+    perm1 = torch.randperm(N)
+    perm2 = torch.randperm(N // 4)
+    assert len(calls) == 14
+    out = {"pts": np_(pts), "cat_id": np_(cat_id), "feat": np_(feat),
+           "perm1": np_(perm1).astype(np.int16), "perm2": np_(perm2).astype(np.int16)}
+    for i, c in enumerate(calls):
+        out[f"idx_{i:02d}"] = c
+    names = sorted(sd.keys())
+    out["param_names"] = np.array(names)
+    out["param_sha"] = np.array([sha(np_(sd[n])) for n in names])
+    out["param_sum"] = np.array([float(np_(sd[n]).astype(np.float64).sum()) for n in names])
+    save("face_enc", **out)
+
+
+if __name__ == "__main__":
+    knn_cases()
+    gather_dir_cases()
+    conv_cases()
+    chamfer_cases()
+    face_enc_case()
