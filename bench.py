@@ -1,0 +1,331 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the 3D-GCN hot path (BASELINE.json metric: 3D-GCN fwd point clouds/sec @1028 pts).
+
+  python bench.py --gpus N --steps K --warmup W            # our arm (CUDA path)
+  python bench.py --impl reference --gpus N --steps K ...  # CPU arm: the oracle port on host cores
+
+One "step" = one full TG-Pose network forward (Face_Enc backbone on the sm_100a kernels + pose heads)
+over one batch of 32 synthetic NOCS-shaped clouds x 1028 points per GPU (BASELINE.json configs[1]).
+N > 1: one process per GPU (torchrun), the batch dimension is sharded, no data-path collective
+(inference), weak scaling.  Rank 0 prints ONE JSON line.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "3D-GCN fwd point clouds/sec @1028 pts"
+UNIT = "clouds/s"
+N_PTS = 1028
+PER_GPU_BATCH = 32
+FP32_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12   # CUDA-core FMA peak at sm_max_mhz: 74.4
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return {"hbm_gbs": float(p["hbm_gbs"]), "bf16_tflops": float(p["bf16_tflops"]),
+                "bf16_tflops_sustained": float(p.get("bf16_tflops_sustained", p["bf16_tflops"])), "source": "measured"}
+    except Exception:
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+def synth_inputs(batch, seed):
+    """object-sized clouds at camera range, 6 categories."""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    pts = torch.rand(batch, N_PTS, 3, generator=g)
+    t = torch.stack([torch.rand(batch, generator=g) * 0.6 - 0.3, torch.rand(batch, generator=g) * 0.6 - 0.3,
+                     torch.rand(batch, generator=g) * 0.8 + 0.6], dim=1)
+    pts = (pts - 0.5) * 0.3 + t[:, None, :]
+    cat = torch.randint(0, 6, (batch, 1), generator=g).float()
+    return pts, cat
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows = []
+        self.proc = None
+        self.gpu = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            parts = [p.strip() for p in r.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def cpu_port_run(batch, steps, warmup, seed=1234):
+    """The oracle port (C/OpenMP kernels + numpy/BLAS heads) of the same full-network forward on host cores."""
+    import torch
+    from oracle import oracle as orc
+    from tgpose_b200.posenet import PoseNet9D
+    torch.manual_seed(0)
+    net = PoseNet9D().eval()
+    sd = {k: v.detach().numpy() for k, v in net.state_dict().items()}
+    pts, cat = synth_inputs(batch, seed)
+    pts, cat = pts.numpy(), cat.numpy()
+    cores = os.cpu_count() or 1
+    orc.set_num_threads(cores)
+    times = []
+    for i in range(warmup + steps):
+        torch.manual_seed(7)
+        perm1, perm2 = torch.randperm(N_PTS).numpy(), torch.randperm(N_PTS // 4).numpy()
+        t0 = time.perf_counter()
+        orc.posenet_forward(sd, pts, cat, perm1, perm2)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    per = sum(times) / len(times)
+    return {"value": batch / per, "seconds_per_step": per, "cores": cores, "batch": batch}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    batch = 2   # BASELINE.json configs[0]: batch 2 x 1028 on CPU; a bounded sample of the 32-cloud step
+    r = cpu_port_run(batch, args.steps, args.warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["seconds_per_step"] * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "full TG-Pose network forward (Face_Enc 3D-GCN + heads), 32 x 1028 points per GPU",
+                   "points": N_PTS, "per_gpu_batch": PER_GPU_BATCH},
+        "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
+                         "sample": f"{batch} of the 32 clouds per step (same generator), C/OpenMP oracle + numpy heads"},
+        "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from tgpose_b200 import _lib, ops
+    from tgpose_b200.posenet import PoseNet9D
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.load()
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+
+    B = args.batch
+    torch.manual_seed(0)
+    net = PoseNet9D().to(dev).eval()
+    # several distinct input batches so no iteration re-reads the previous one's data
+    n_sets = 4
+    host_sets = []
+    for s in range(n_sets):
+        pts, cat = synth_inputs(B, 1234 + 17 * rank + s)
+        host_sets.append((pts.pin_memory(), cat.pin_memory()))
+    dev_sets = [(p.to(dev), c.to(dev)) for p, c in host_sets]
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)   # > 126 MB L2
+
+    def step(pts, cat):
+        torch.manual_seed(7)          # Pool_layer draws its permutation from the CPU generator (gcn3d.py:242)
+        with torch.no_grad():
+            return net(pts, cat)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        step(*dev_sets[i % n_sets])
+    barrier()
+
+    # ---- device-resident timing: K steps, CUDA events per step, L2 flushed between steps
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ops.EVENT_LOG = {} if rank == 0 else None
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    l0 = _lib.launch_count()
+    barrier()
+    wall0 = time.perf_counter()
+    for i in range(args.steps):
+        flush.zero_()
+        ev[i][0].record()
+        step(*dev_sets[i % n_sets])
+        ev[i][1].record()
+    barrier()
+    wall = time.perf_counter() - wall0
+    launches = _lib.launch_count() - l0
+    event_log, ops.EVENT_LOG = ops.EVENT_LOG, None
+    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+
+    # ---- end to end: pinned host inputs -> H2D -> forward -> D2H of the pose outputs, every step
+    barrier()
+    out_keys = ("p_green_R", "p_red_R", "f_green_R", "f_red_R", "Pred_T", "Pred_s")
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    h2d = d2h = 0
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        hp, hc = host_sets[i % n_sets]
+        p = hp.to(dev, non_blocking=True)
+        c = hc.to(dev, non_blocking=True)
+        out = step(p, c)
+        res = torch.cat([out[k].reshape(B, -1) for k in out_keys], dim=1).cpu()
+        if i == 0:
+            h2d = hp.numel() * 4 + hc.numel() * 4
+            d2h = res.numel() * 4
+    e1.record()
+    barrier()
+    e2e_ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+
+    t = torch.tensor([dev_ms, e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_ms = float(t[0]), float(t[1])
+
+    if rank == 0:
+        peaks = measured_peaks()
+        ms_per_step = dev_ms / args.steps
+        total = B * world
+        line = {
+            "metric": METRIC, "value": total / (ms_per_step / 1e3), "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "full TG-Pose network forward (Face_Enc 3D-GCN + heads), 32 x 1028 points per GPU",
+                       "points": N_PTS, "per_gpu_batch": B, "global_batch": total, "parallelism": f"dp{world}",
+                       "weights": "random-init (seed 0)", "l2": "256 MB flush write between timed steps"},
+            "e2e": {"value": total / (e2e_ms / args.steps / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "wall_s": wall,
+        }
+        line.update(kernel_report(event_log, args.steps, B, peaks))
+        if world == 1 and not args.no_cpu_baseline:
+            r = cpu_port_run(2, 2, 1)
+            line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
+                                    "sample": "2 of the 32 clouds per step, 2 timed passes after 1 warm-up; "
+                                              "C/OpenMP oracle + numpy heads"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def kernel_report(event_log, steps, B, peaks):
+    """Per-kernel device time inside the timed steps (CUDA events around each C-ABI call on the launching
+    stream) -> share of the step and roofline of the dominant kernel (algorithmic work: DESIGN.md / SURVEY 8d)."""
+    if not event_log:
+        return {}
+    agg = {}
+    for name, evs in event_log.items():
+        if name.startswith("__"):
+            continue
+        ms = [a.elapsed_time(b) for a, b in evs]
+        agg[name] = {"launches_per_step": len(ms) / steps, "ms_per_step": sum(ms) / steps}
+    total = sum(v["ms_per_step"] for v in agg.values())
+    for v in agg.values():
+        v["share"] = v["ms_per_step"] / total if total else 0.0
+    top = max(agg, key=lambda n: agg[n]["ms_per_step"])
+    out = {"kernels": {k: {kk: round(vv, 5) for kk, vv in v.items()} for k, v in sorted(agg.items())},
+           "dominant_kernel": top}
+    N0, k, S = N_PTS, 20, 7
+    if top == "layer_conv":
+        # conv_1..conv_4 launches: flops = N*k*S*C*9 + N*S*C ; compulsory bytes per SURVEY 8d
+        shapes = [(N0, 20, 128), (N0 // 4, 20, 256), (N0 // 4, 20, 256), (N0 // 16, 8, 512)]
+        flops = sum(n * kk * S * c * 9 + n * S * c for n, kk, c in shapes) * B
+        byts = sum(4 * (3 * n + S * c * n + c * n + c * n + 3 * S * c) + 4 * n * kk for n, kk, c in shapes) * B
+        t = agg[top]["ms_per_step"] / 1e3
+        out["roofline"] = {"bound": "fp32", "kernel": "layer_conv_kernel (4 launches/step)",
+                           "achieved": flops / t / 1e12, "peak": FP32_PEAK_TFLOPS, "unit": "TFLOP/s",
+                           "frac": flops / t / 1e12 / FP32_PEAK_TFLOPS, "traffic": None,
+                           "peak_source": "148 SM x 128 lanes x 2 flop x 1.965 GHz (SURVEY 8d); no measured fp32 peak",
+                           "hbm": {"achieved": byts / t / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                                   "frac": byts / t / 1e9 / peaks["hbm_gbs"], "peak_source": peaks["source"]}}
+    elif top == "gemm":
+        flops = 0.0
+        for m, kdim, n in event_log.get("__gemm_shapes__", []):
+            flops += 2.0 * m * kdim * n
+        t = agg[top]["ms_per_step"] / 1e3
+        flops /= steps
+        out["roofline"] = {"bound": "fp32", "kernel": "gemm_simt_kernel (all launches in the step)",
+                           "achieved": flops / t / 1e12, "peak": FP32_PEAK_TFLOPS, "unit": "TFLOP/s",
+                           "frac": flops / t / 1e12 / FP32_PEAK_TFLOPS, "traffic": None,
+                           "peak_source": "148 SM x 128 lanes x 2 flop x 1.965 GHz (SURVEY 8d)"}
+    out["kernels"].pop("__gemm_shapes__", None)
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=PER_GPU_BATCH, help="clouds per GPU per step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,160 @@
+/*
+ * tgpose_b200.h -- C-ABI of libtgpose_b200.so: the sm_100a implementation of TG-Pose's
+ * 3D-GCN + chamfer3D hot path.
+ *
+ * Conventions (SURVEY 8b "What a C-ABI replacement must export"):
+ *   - plain pointers + int sizes, no torch / ATen types; every pointer is DEVICE memory
+ *     unless the name ends in _host;
+ *   - `stream` is a cudaStream_t passed as void* (PyTorch's current stream);
+ *   - the callee never allocates, never synchronises, keeps no references, is re-entrant;
+ *   - returns 0 on success, a negative TGP_E* for an argument error, or a positive
+ *     cudaError_t from the launch; tgp_last_error() gives a thread-local message.
+ *     (The reference's chamfer extension returns 1/0 and printf()s -- chamfer_cuda.cpp:17-33,
+ *     chamfer3D.cu:145-151; the Python shim chamfer_3D.forward() maps 0 -> 1 to keep that contract.)
+ *   - all float tensors are fp32, C-contiguous; shapes are given in the comments;
+ *   - index tensors: `idx_bits` selects int64 (what torch.topk hands the reference's callers,
+ *     gcn3d.py:21) or int32 (what the fused encoder keeps internally).
+ *
+ * Each entry point cites the reference interface it replaces (paths relative to the
+ * reference checkout, network/fs_net_repo/ unless noted).
+ */
+#ifndef TGPOSE_B200_H
+#define TGPOSE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TGP_OK 0
+#define TGP_EINVAL (-1)   /* bad size / null pointer / unsupported combination */
+#define TGP_ENOSPACE (-2) /* workspace too small */
+
+typedef void* tgp_stream_t;
+
+/* library / build info */
+int tgp_version(void);
+const char* tgp_last_error(void);
+/* number of kernel launches issued by this library in this process (bench.py "gpu_launches") */
+unsigned long long tgp_launch_count(void);
+
+/* ------------------------------------------------------------------ kNN (gcn3d.py:14-35) */
+
+/* get_neighbor_index(vertices (B,N,3), k), gcn3d.py:14-23, xyz space.
+ * Bit-exact distance recipe, top-(k+1) by (distance, index) ascending, rank 0 dropped
+ * positionally.  idx64 (B,N,k) int64 and/or idx32 (B,N,k) int32; either may be NULL. */
+int tgp_knn_xyz(const float* xyz, int B, int N, int k, int64_t* idx64, int32_t* idx32, tgp_stream_t stream);
+
+/* get_neighbor_index(feature_map (B,N,D), k), gcn3d.py:14-23 as used by 'RF-F' (:201-206).
+ * workspace: tgp_knn_feat_workspace(B,N,D) bytes. */
+size_t tgp_knn_feat_workspace(int B, int N, int D);
+int tgp_knn_feat(const float* x, int B, int N, int D, int k, int64_t* idx64, int32_t* idx32,
+                 void* workspace, size_t workspace_bytes, tgp_stream_t stream);
+
+/* get_nearest_index(target (B,N,3), source (B,M,3)), gcn3d.py:26-35 -> (B,N,1). */
+int tgp_nearest(const float* target, const float* source, int B, int N, int M,
+                int64_t* idx64, int32_t* idx32, tgp_stream_t stream);
+
+/* ------------------------------------------------------------------ gathers (gcn3d.py:38-58) */
+
+/* indexing_neighbor_new(tensor (B,N,C), index (B,M,k)), gcn3d.py:38-46 -> out (B,M,k,C). */
+int tgp_gather_rows(const float* tensor, const void* index, int idx_bits, int B, int N, int M, int k, int C,
+                    float* out, tgp_stream_t stream);
+
+/* t[:, rows, :] with one row list shared by the whole batch (Pool_layer's vertices[:, sample_idx, :],
+ * gcn3d.py:243): t (B,N,C), rows (M) int64 -> out (B,M,C). */
+int tgp_select_rows(const float* t, const int64_t* rows, int B, int N, int M, int C, float* out, tgp_stream_t stream);
+
+/* get_neighbor_direction_norm(vertices (B,N,3), idx (B,N,k)), gcn3d.py:48-58 -> out (B,N,k,3). */
+int tgp_direction_norm(const float* xyz, const void* idx, int idx_bits, int B, int N, int k,
+                       float* out, tgp_stream_t stream);
+
+/* max over the k gathered rows: out[b,m,c] = max_j f[b, idx[b,rows[m],j], c].
+ * rows (M) int64 device pointer selects points (Pool_layer, gcn3d.py:236-244); NULL -> all N (M == N).
+ * arg (B,M,C) uint8, optional: winning neighbour slot (saved for backward). */
+int tgp_gather_max(const float* f, const void* idx, int idx_bits, const int64_t* rows, int B, int N, int M, int k,
+                   int C, float* out, uint8_t* arg, tgp_stream_t stream);
+
+/* get_ORL_global(feature (B,N,C), vertices, k), gcn3d.py:210-217, given the xyz kNN:
+ * g[b,c] = mean_n max_j f[b, idx[b,n,j], c]   (the (B,1,C) tensor before .repeat).
+ * arg (B,N,C) uint8 optional. */
+int tgp_orl_global(const float* f, const void* idx, int idx_bits, int B, int N, int k, int C,
+                   float* g, uint8_t* arg, tgp_stream_t stream);
+
+/* ------------------------------------------------------------------ graph convolutions */
+
+/* HSlayer_surface.graph_conv, gcn3d.py:91-106:
+ * out[b,n,c] = mean_s max_j relu(<dirnorm(b,n,j), normalize(directions,dim=0)[:, s*C+c]>).
+ * xyz (B,N,3), idx (B,N,k), directions (3,S*C) raw parameter, out (B,N,C),
+ * arg (B,N,S*C) uint8 optional (arg-max neighbour slot per (n,s,c)). */
+int tgp_surface_conv_fwd(const float* xyz, const void* idx, int idx_bits, const float* directions,
+                         int B, int N, int k, int S, int C, float* out, uint8_t* arg, tgp_stream_t stream);
+
+/* Edge records for the layer convolution: rec[b,n,j] = (dx,dy,dz, bitcast<float>(int idx[b,n,j]))
+ * with (dx,dy,dz) = get_neighbor_direction_norm (gcn3d.py:48-58).  rec: (B,N,k,4) fp32, 16-byte aligned. */
+int tgp_edge_records(const float* xyz, const void* idx, int idx_bits, int B, int N, int k,
+                     float* rec, tgp_stream_t stream);
+
+/* HS_layer.graph_conv after the projection, gcn3d.py:157-180:
+ * out[b,n,c] = centre[b,n,c] + mean_s max_j relu(theta[b,n,j,s,c]) * support[b, idx[b,n,j], s, c].
+ * edge_rec from tgp_edge_records (directions from xyz, indices from feature space, gcn3d.py:201-207);
+ * centre (B*N, C) row-major with leading dimension ld_centre;
+ * support in SLAB layout [C/4][B*N][S][4] as written by tgp_gemm (mode 1), C % 4 == 0, S*4 <= 32;
+ * arg_slab [C/4][B*N][S*4] uint8 optional: arg-max neighbour slot per (n,s,c), same layout. */
+int tgp_layer_conv_fwd(const float* edge_rec, const float* directions,
+                       const float* centre, long ld_centre, const float* support_slab,
+                       int B, int N, int k, int S, int C, float* out, uint8_t* arg_slab, tgp_stream_t stream);
+
+/* ------------------------------------------------------------------ dense contraction */
+
+/* One output column range of tgp_gemm.  mode 0: row-major, out[m*ld + (col - col_begin)].
+ * mode 1: SLAB, columns are ordered (cgroup, s, c4) and go to [cgroup][m][S*4]. */
+typedef struct {
+    int col_begin, col_end;
+    int mode;
+    int slab_width; /* S*4 for mode 1 */
+    long ld;        /* mode 0 leading dimension */
+    float* ptr;
+} tgp_out_seg;
+
+typedef struct {
+    /* C = A (M,K; lda) * Bmat + epilogue.  b_is_nk: Bmat given as (Ncols,K) K-contiguous
+     * (a Conv1d weight, gcn3d.py:70-71,130,132) instead of (K,Ncols) (HS_layer.weights, gcn3d.py:125). */
+    const float* A; long lda;
+    const float* Bmat; long ldb; int b_is_nk;
+    long M; int K; int Ncols;
+    const float* bias;            /* (Ncols) or NULL */
+    const float* group_bias;      /* (M / rows_per_group, Ncols) or NULL: per-cloud bias (ORL split) */
+    int rows_per_group;
+    const float* res1; long ld_res1;  /* optional residuals, (M, Ncols) */
+    const float* res2; long ld_res2;
+    const float* scale; const float* shift; /* optional per-column affine (eval BatchNorm) applied last */
+    int relu;
+    int nseg; tgp_out_seg seg[4];
+} tgp_gemm_args;
+
+/* feature_map @ weights + bias (gcn3d.py:170) and every 1x1 Conv1d on the path. */
+int tgp_gemm(const tgp_gemm_args* args_host, tgp_stream_t stream);
+
+/* ------------------------------------------------------------------ chamfer (losses/chamfer3D) */
+
+/* chamfer_3D.forward, chamfer_cuda.cpp:17-19 -> chamfer3D.cu:136-154 (NmDistanceKernel x2).
+ * xyz1 (B,n,3), xyz2 (B,m,3) -> dist1 (B,n), dist2 (B,m) fp32, idx1 (B,n), idx2 (B,m) int32.
+ * sums (B,4) optional: [sum dist1, sum dist2, sum sqrt(dist1), sum sqrt(dist2)] (calc_cd,
+ * losses/TDA_loss_sym_recon.py:495-509); must be zeroed by the caller. */
+int tgp_chamfer_fwd(const float* xyz1, const float* xyz2, int B, int n, int m,
+                    float* dist1, float* dist2, int32_t* idx1, int32_t* idx2, float* sums, tgp_stream_t stream);
+
+/* chamfer_3D.backward, chamfer_cuda.cpp:22-27 -> chamfer3D.cu:155-195.  gradxyz1/2 are
+ * OVERWRITTEN (no pre-zeroing needed): the direct terms are stored, the scattered terms are
+ * added with fp32 atomics like the reference, so the last bits depend on arrival order. */
+int tgp_chamfer_bwd(const float* xyz1, const float* xyz2, const float* graddist1, const float* graddist2,
+                    const int32_t* idx1, const int32_t* idx2, int B, int n, int m,
+                    float* gradxyz1, float* gradxyz2, tgp_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TGPOSE_B200_H */

@@ -325,3 +325,69 @@ def face_enc_forward(p, xyz, cat_id, perm1, perm2, k=20, obj_c=6, inject=None):
     one_hot[np.arange(B), np.asarray(cat_id).reshape(-1).astype(np.int64)] = 1
     one_hot = np.broadcast_to(one_hot[:, None, :], (B, N0, obj_c))
     return np.concatenate([fm0, fm1, up2, up3, up4, one_hot], axis=2).astype(np.float32)
+
+
+# ----------------------------------------------------------------------------- full network (heads)
+def _pw(x, p, conv, bn=None, act=None):
+    """1x1 Conv1d (+ eval BatchNorm + activation) on channel-last x (B,N,Cin)."""
+    w = p[conv + ".weight"]
+    y = gemm_bias(x, np.ascontiguousarray(w.reshape(w.shape[0], w.shape[1]).T), p.get(conv + ".bias"))
+    if bn is not None:
+        y = bn_eval_relu(y, p, bn, relu=False)
+    if act == "relu":
+        y = np.maximum(y, 0)
+    elif act == "leaky":
+        y = np.where(y > 0, y, np.float32(0.2) * y)
+    return y.astype(np.float32)
+
+
+def _lin(x, p, name):
+    w = p[name + ".weight"]
+    return gemm_bias(x, np.ascontiguousarray(w.T), p.get(name + ".bias"))
+
+
+def _point_head(x, p, pre):
+    """PoseR.py:26-39 / PoseTs.py:31-45 in eval mode: x (B,N,f) -> (B,k)."""
+    h = _pw(x, p, pre + ".conv1", pre + ".bn1", "relu")
+    h = _pw(h, p, pre + ".conv2", pre + ".bn2", "relu")
+    h = h.max(axis=1, keepdims=True)
+    h = _pw(h, p, pre + ".conv3", pre + ".bn3", "relu")
+    return _pw(h, p, pre + ".conv4")[:, 0, :]
+
+
+def posenet_forward(p, points, cat_id, perm1, perm2, inject=None):
+    """PoseNet9D.forward (eval mode, full output set), PoseNet9D.py:33-91 + FaceRecon.py:112-202."""
+    points = _f32(points)
+    mean = points.mean(axis=1, keepdims=True, dtype=np.float32)
+    xyz = points - mean
+    enc = {k[len("face_all.encoder."):]: v for k, v in p.items() if k.startswith("face_all.encoder.")}
+    feat = face_enc_forward(enc, xyz, cat_id, perm1, perm2, inject=inject)
+    # PH_Predictor (FaceRecon.py:139-167)
+    f5 = _pw(feat, p, "face_all.ph_pred.conv_5.0", "face_all.ph_pred.conv_5.1", "leaky")
+    pooled = f5.max(axis=1)
+    fa = _lin(np.concatenate([pooled, pooled], 1), p, "face_all.ph_pred.linear1")
+    fa = bn_eval_relu(fa, p, "face_all.ph_pred.bn5", relu=False)
+    fa = np.where(fa > 0, fa, np.float32(0.2) * fa).astype(np.float32)
+    pi1 = _lin(fa, p, "face_all.ph_pred.linear2")
+    pi2 = _lin(fa, p, "face_all.ph_pred.linear3")
+    h1 = 1.0 / (1.0 + np.exp(-pi1))
+    h2 = 1.0 / (1.0 + np.exp(-pi2))
+    feat_ph = feat + (_lin(pi1, p, "face_all.ph_pred.linear4") + _lin(pi2, p, "face_all.ph_pred.linear5"))[:, None, :]
+    # Face_Dec (FaceRecon.py:112-117)
+    d = "face_all.decoder."
+    h = _pw(feat_ph, p, d + "conv1d_block.0", d + "conv1d_block.1", "relu")
+    h = _pw(h, p, d + "conv1d_block.3", d + "conv1d_block.4", "relu")
+    h = _pw(h, p, d + "conv1d_block.6", d + "conv1d_block.7", "relu")
+    h = _pw(h, p, d + "recon_head.0", d + "recon_head.1", "relu")
+    recon = _pw(h, p, d + "recon_head.3")
+    green = _point_head(feat, p, "rot_green")
+    red = _point_head(feat, p, "rot_red")
+    ts = _point_head(np.concatenate([feat, xyz], axis=2), p, "ts")
+
+    def unit(v):
+        return v / (np.linalg.norm(v, axis=1, keepdims=True) + np.float32(1e-6))
+
+    return {"recon": recon + mean, "p_green_R": unit(green[:, 1:]), "p_red_R": unit(red[:, 1:]),
+            "f_green_R": 1.0 / (1.0 + np.exp(-green[:, 0])), "f_red_R": 1.0 / (1.0 + np.exp(-red[:, 0])),
+            "Pred_T": ts[:, 0:3] + mean[:, 0, :], "Pred_s": ts[:, 3:6], "h1": h1, "h2": h2, "feat": feat,
+            "feat_global": feat.max(axis=1)}

@@ -271,9 +271,54 @@ def face_enc_case():
     save("face_enc", **out)
 
 
+@torch.no_grad()
+def posenet_case():
+    """full PoseNet9D (eval mode, FLAGS.train=1 output set) at B=2, N=128 with recorded indices."""
+    from network.fs_net_repo.PoseNet9D import PoseNet9D
+    torch.manual_seed(0)
+    net = PoseNet9D().eval()
+    sd = net.state_dict()
+    g = torch.Generator().manual_seed(4321)
+    B, N = 2, 128
+    pts = nocs_cloud(g, B, N)
+    cat_id = torch.randint(0, 6, (B, 1), generator=g).float()
+    calls = []
+    orig_knn, orig_nn = gcn3d.get_neighbor_index, gcn3d.get_nearest_index
+
+    def rec_knn(v, k):
+        r = orig_knn(v, k)
+        calls.append(np_(r).astype(np.int16))
+        return r
+
+    def rec_nn(t, s_):
+        r = orig_nn(t, s_)
+        calls.append(np_(r).astype(np.int16))
+        return r
+
+    gcn3d.get_neighbor_index, gcn3d.get_nearest_index = rec_knn, rec_nn
+    try:
+        torch.manual_seed(7)
+        res = net(pts, cat_id)
+    finally:
+        gcn3d.get_neighbor_index, gcn3d.get_nearest_index = orig_knn, orig_nn
+    assert len(calls) == 14
+    out = {"pts": np_(pts), "cat_id": np_(cat_id)}
+    for k_, v in res.items():
+        if k_ == "feat":
+            continue  # covered by face_enc.npz; keep the file small
+        out["out_" + k_] = np_(v)
+    for i, c in enumerate(calls):
+        out[f"idx_{i:02d}"] = c
+    names = sorted(sd.keys())
+    out["param_names"] = np.array(names)
+    out["param_sha"] = np.array([sha(np_(sd[n])) for n in names])
+    save("posenet", **out)
+
+
 if __name__ == "__main__":
     knn_cases()
     gather_dir_cases()
     conv_cases()
     chamfer_cases()
     face_enc_case()
+    posenet_case()

@@ -153,3 +153,21 @@ def test_face_enc_injected_indices():
                                      g["perm2"].astype(np.int64))
     from util import frac_close
     assert frac_close(feat_free, g["feat"]) > 0.90
+
+
+def test_posenet_injected_indices():
+    """full network (heads included) through the oracle vs the reference's PoseNet9D outputs."""
+    torch = pytest.importorskip("torch")
+    from tgpose_b200.posenet import PoseNet9D
+    g = golden("posenet")
+    torch.manual_seed(0)
+    net = PoseNet9D(train_outputs=True).eval()
+    sd = {k: v.detach().numpy() for k, v in net.state_dict().items()}
+    for n, h in zip([str(n) for n in g["param_names"]], g["param_sha"]):
+        assert sha(sd[n]) == str(h), f"init of {n} differs from the reference under the same seed"
+    torch.manual_seed(7)
+    perm1, perm2 = torch.randperm(128).numpy(), torch.randperm(32).numpy()
+    inject = [g[f"idx_{i:02d}"].astype(np.int64) for i in range(14)]
+    out = orc.posenet_forward(sd, g["pts"], g["cat_id"], perm1, perm2, inject=inject)
+    for k in ("recon", "p_green_R", "p_red_R", "f_green_R", "f_red_R", "Pred_T", "Pred_s", "h1", "h2", "feat_global"):
+        assert_close(out[k], g["out_" + k], rel=2e-4, floor=2e-6, what=k)

@@ -1,0 +1,142 @@
+"""torch.autograd glue for the module-level forwards (kernels do the work, autograd only routes).
+
+Forward pipelines (each step one C-ABI launch):
+  HSSurfaceFn : gcn3d.py:78-112   STE gemm | xyz kNN | surface conv | ORL gather-max-mean | ORL gemm
+  HSLayerFn   : gcn3d.py:142-186  fused projection+STE gemm (centre | support slab | f_STE) |
+                                  feature kNN | edge records | layer conv | xyz kNN | ORL | ORL gemm
+  PoolFn      : gcn3d.py:225-245  xyz kNN | gather-max on the sampled rows | row select
+The backward contract is SURVEY 8(a'); see backward.py for the kernels' host side.
+"""
+import torch
+
+from . import ops
+
+_PACK_CACHE = {}
+
+
+def _pack_layer(weights, bias, ste_w, S, C):
+    """[centre | support in slab column order (cgroup, s, c4) | STE^T] as one (in, (S+2)*C) operand + bias.
+    Cached per parameter version (weights are constants in inference)."""
+    key = (weights.data_ptr(), weights._version, bias.data_ptr(), bias._version, ste_w.data_ptr(), ste_w._version)
+    hit = _PACK_CACHE.get(key)
+    if hit is not None:
+        return hit
+    cin = weights.shape[0]
+    with torch.no_grad():
+        w = weights.detach()
+        sup = w[:, C:].reshape(cin, S, C // 4, 4).permute(0, 2, 1, 3).reshape(cin, S * C)
+        wcat = torch.cat([w[:, :C], sup, ste_w.detach().reshape(C, cin).t()], dim=1).contiguous()
+        b = bias.detach()
+        bcat = torch.cat([b[:C], b[C:].reshape(S, C // 4, 4).permute(1, 0, 2).reshape(-1),
+                          torch.zeros(C, device=b.device, dtype=b.dtype)]).contiguous()
+    if len(_PACK_CACHE) > 64:
+        _PACK_CACHE.clear()
+    _PACK_CACHE[key] = (wcat, bcat)
+    return wcat, bcat
+
+
+def _orl_tail(feature, idx_xyz, conv2_w, f_ste, B, N, C, post, want_arg=False):
+    """ORL_forward (gcn3d.py:108-112,182-186) + the STE skip: conv2(cat[f, g]) + f + f_STE, where
+    conv2(cat[f, g.repeat]) = f @ W[:, :C]^T + (g @ W[:, C:]^T) broadcast over the cloud."""
+    M = B * N
+    w2 = conv2_w.reshape(C, 2 * C)
+    if want_arg:
+        g, arg = ops.orl_global(feature, idx_xyz, want_arg=True)
+    else:
+        g, arg = ops.orl_global(feature, idx_xyz), None
+    gb = ops.linear_nk(g, w2[:, C:])
+    out = torch.empty((B, N, C), dtype=torch.float32, device=feature.device)
+    scale, shift, relu = post if post is not None else (None, None, False)
+    f2 = feature.view(M, C)
+    ops.gemm(f2, w2[:, :C], True, [(0, C, out.view(M, C), 0, 0)], group_bias=gb, rows_per_group=N,
+             res1=f2, res2=f_ste, scale=scale, shift=shift, relu=relu)
+    return out, g, arg
+
+
+class HSSurfaceFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, xyz, directions, ste_w, conv2_w, k, S, C, idx_xyz, post):
+        xyz = xyz.contiguous().float()
+        B, N, _ = xyz.shape
+        M = B * N
+        train = any(ctx.needs_input_grad)
+        f_ste = ops.linear_nk(xyz.view(M, 3), ste_w.reshape(C, 3))
+        if idx_xyz is None:
+            idx_xyz = ops.knn_xyz(xyz, k, want64=False, want32=True)[1]
+        if train:
+            feature, arg = ops.surface_conv(xyz, idx_xyz, directions, S, C, want_arg=True)
+        else:
+            feature, arg = ops.surface_conv(xyz, idx_xyz, directions, S, C), None
+        out, g, arg_orl = _orl_tail(feature, idx_xyz, conv2_w, f_ste, B, N, C, post, want_arg=train)
+        if train:
+            ctx.save_for_backward(xyz, directions, ste_w, conv2_w, idx_xyz, arg, feature, g, arg_orl)
+            ctx.cfg = (k, S, C, post)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        from . import backward as bw
+        return bw.hs_surface_backward(ctx, grad_out)
+
+
+class HSLayerFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, xyz, fm, weights, bias, directions, ste_w, conv2_w, k, S, C, idx_feat, idx_xyz, post):
+        xyz = xyz.contiguous().float()
+        fm = fm.contiguous().float()
+        B, N, cin = fm.shape
+        M = B * N
+        train = any(ctx.needs_input_grad)
+        wcat, bcat = _pack_layer(weights, bias, ste_w, S, C)
+        dev = fm.device
+        centre = torch.empty((M, C), dtype=torch.float32, device=dev)
+        slab = torch.empty((C // 4, M, S * 4), dtype=torch.float32, device=dev)
+        f_ste = torch.empty((M, C), dtype=torch.float32, device=dev)
+        ops.gemm(fm.view(M, cin), wcat, False,
+                 [(0, C, centre, 0, 0), (C, C + S * C, slab, 1, S * 4), (C + S * C, (S + 2) * C, f_ste, 0, 0)],
+                 bias=bcat)
+        if idx_feat is None:
+            idx_feat = ops.knn_feat(fm, k, want64=False, want32=True)[1]
+        rec = ops.edge_records(xyz, idx_feat)
+        if train:
+            feature, arg = ops.layer_conv(rec, directions, centre, slab, B, N, S, C, want_arg=True)
+        else:
+            feature, arg = ops.layer_conv(rec, directions, centre, slab, B, N, S, C), None
+        if idx_xyz is None:
+            idx_xyz = ops.knn_xyz(xyz, k, want64=False, want32=True)[1]
+        out, g, arg_orl = _orl_tail(feature, idx_xyz, conv2_w, f_ste, B, N, C, post, want_arg=train)
+        if train:
+            ctx.save_for_backward(fm, weights, bias, directions, ste_w, conv2_w, rec, slab, arg, idx_xyz,
+                                  feature, g, arg_orl)
+            ctx.cfg = (k, S, C, post)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        from . import backward as bw
+        return bw.hs_layer_backward(ctx, grad_out)
+
+
+class PoolFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, xyz, fm, sample_idx, k, idx_xyz):
+        xyz = xyz.contiguous().float()
+        fm = fm.contiguous().float()
+        train = any(ctx.needs_input_grad)
+        if idx_xyz is None:
+            idx_xyz = ops.knn_xyz(xyz, k, want64=False, want32=True)[1]
+        rows = sample_idx.to(xyz.device, non_blocking=True)
+        if train:
+            pooled, arg = ops.gather_max(fm, idx_xyz, rows=rows, want_arg=True)
+            ctx.save_for_backward(idx_xyz, rows, arg)
+            ctx.shape = fm.shape
+        else:
+            pooled = ops.gather_max(fm, idx_xyz, rows=rows)
+        v_pool = ops.select_rows(xyz, rows)
+        ctx.mark_non_differentiable(v_pool)
+        return v_pool, pooled
+
+    @staticmethod
+    def backward(ctx, g_v, g_pooled):
+        from . import backward as bw
+        return bw.pool_backward(ctx, g_pooled)

@@ -1,0 +1,215 @@
+// gather.cu -- index-driven data movement of the 3D-GCN path (HBM/L2-bound kernels).
+//
+// Replaces indexing_neighbor_new (gcn3d.py:38-46), get_neighbor_direction_norm (:48-58),
+// the gather+max of get_ORL_global (:210-217) and Pool_layer (:225-245).  The reference
+// writes the k-fold expanded (B,M,k,C) tensor to memory and reduces it in a second pass;
+// the *_max kernels below reduce while gathering, so only (B,M,C) is ever written.
+#include "common.cuh"
+#include <float.h>
+
+namespace tgp {
+
+// out[r, :] = tensor[b*N + index[r], :]  for r over B*M*k rows; VEC = floats per thread access
+template <typename IdxT, int VEC>
+__global__ void gather_rows_kernel(const float* __restrict__ t, const IdxT* __restrict__ index, long rows,
+                                   long rows_per_cloud, int N, int C, float* __restrict__ out) {
+    const int cv = C / VEC;
+    const long total = rows * cv;
+    for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
+        const long r = e / cv;
+        const int c = (int)(e - r * cv) * VEC;
+        const long b = r / rows_per_cloud;
+        const float* src = t + (b * N + ld_idx(index, r)) * (long)C + c;
+        float* dst = out + r * (long)C + c;
+        if (VEC == 4) *reinterpret_cast<float4*>(dst) = __ldg(reinterpret_cast<const float4*>(src));
+        else *dst = __ldg(src);
+    }
+}
+
+// out[b,m,:] = t[b, rows[m], :]
+__global__ void select_rows_kernel(const float* __restrict__ t, const int64_t* __restrict__ rows, long total, int N,
+                                   int M, int C, float* __restrict__ out) {
+    const long e = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= total) return;
+    const long r = e / C;
+    const int c = (int)(e - r * C);
+    const long b = r / M;
+    out[e] = __ldg(t + (b * N + __ldg(rows + (r - b * M))) * C + c);
+}
+
+// (B,N,k) -> (B,N,k,3) unit direction from the centre point to each neighbour
+template <typename IdxT>
+__global__ void direction_norm_kernel(const float* __restrict__ xyz, const IdxT* __restrict__ idx, long total,
+                                      int N, int k, float* __restrict__ out) {
+    const long e = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= total) return;
+    const long pt = e / k;            // b*N + n
+    const long b = pt / N;
+    const long nb = b * N + ld_idx(idx, e);
+    float x = __ldg(xyz + nb * 3) - __ldg(xyz + pt * 3);
+    float y = __ldg(xyz + nb * 3 + 1) - __ldg(xyz + pt * 3 + 1);
+    float z = __ldg(xyz + nb * 3 + 2) - __ldg(xyz + pt * 3 + 2);
+    normalize3(x, y, z);
+    out[e * 3] = x; out[e * 3 + 1] = y; out[e * 3 + 2] = z;
+}
+
+// out[b,m,c] = max_j f[b, idx[b, rows[m], j], c]; one thread per VEC channels of one output row
+template <typename IdxT, int VEC, bool ARG>
+__global__ void gather_max_kernel(const float* __restrict__ f, const IdxT* __restrict__ idx,
+                                  const int64_t* __restrict__ rows, int N, int M, int k, int C, long total,
+                                  float* __restrict__ out, uint8_t* __restrict__ arg) {
+    const int cv = C / VEC;
+    const long e = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= total) return;
+    const long r = e / cv;            // b*M + m
+    const int c = (int)(e - r * cv) * VEC;
+    const long b = r / M;
+    const int m = (int)(r - b * M);
+    const long n = rows ? (long)__ldg(rows + m) : m;
+    const IdxT* id = idx + (b * N + n) * k;
+    float best[VEC];
+    int bj[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) { best[v] = -FLT_MAX; bj[v] = 0; }
+    for (int j = 0; j < k; ++j) {
+        const float* src = f + (b * N + ld_idx(id, j)) * (long)C + c;
+        float val[VEC];
+        if (VEC == 4) {
+            const float4 t4 = __ldg(reinterpret_cast<const float4*>(src));
+            val[0] = t4.x; val[1 % VEC] = t4.y; val[2 % VEC] = t4.z; val[3 % VEC] = t4.w;
+        } else val[0] = __ldg(src);
+#pragma unroll
+        for (int v = 0; v < VEC; ++v)
+            if (val[v] > best[v]) { best[v] = val[v]; bj[v] = j; }
+    }
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+        out[r * (long)C + c + v] = best[v];
+        if (ARG) arg[r * (long)C + c + v] = (uint8_t)bj[v];
+    }
+}
+
+// ORL global feature: g[b,c] += (1/N) * sum over this CTA's points of max_j f[b, idx[b,n,j], c].
+// CTA = (32-channel chunk, cloud, point split); lane = channel, warps stride over points.
+constexpr int ORL_THREADS = 256;
+template <typename IdxT, bool ARG>
+__global__ void __launch_bounds__(ORL_THREADS)
+orl_global_kernel(const float* __restrict__ f, const IdxT* __restrict__ idx, int N, int k, int C,
+                  float* __restrict__ g, uint8_t* __restrict__ arg) {
+    __shared__ float part[ORL_THREADS / 32][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + lane;
+    const long b = blockIdx.y;
+    const int nsplit = gridDim.z, sp = blockIdx.z;
+    const int per = (N + nsplit - 1) / nsplit;
+    const int n_beg = sp * per, n_end = min(N, n_beg + per);
+    float acc = 0.f;
+    for (int n = n_beg + warp; n < n_end; n += ORL_THREADS / 32) {
+        const IdxT* id = idx + (b * N + n) * k;
+        float best = -FLT_MAX;
+        int bj = 0;
+        if (c < C) {
+#pragma unroll 4
+            for (int j = 0; j < k; ++j) {
+                const float v = __ldg(f + (b * N + ld_idx(id, j)) * (long)C + c);
+                if (v > best) { best = v; bj = j; }
+            }
+            acc += best;
+            if (ARG) arg[(b * N + n) * (long)C + c] = (uint8_t)bj;
+        }
+    }
+    part[warp][lane] = acc;
+    __syncthreads();
+    if (warp == 0) {
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < ORL_THREADS / 32; ++w) s += part[w][lane];
+        if (c < C) atomicAdd(g + b * C + c, s / (float)N);
+    }
+}
+
+}  // namespace tgp
+
+using namespace tgp;
+
+extern "C" int tgp_gather_rows(const float* tensor, const void* index, int idx_bits, int B, int N, int M, int k,
+                               int C, float* out, tgp_stream_t stream) {
+    if (!tensor || !index || !out) return fail(TGP_EINVAL, "tgp_gather_rows: null pointer");
+    if (B <= 0 || N <= 0 || M <= 0 || k <= 0 || C <= 0) return fail(TGP_EINVAL, "tgp_gather_rows: sizes must be positive");
+    const long rows = (long)B * M * k;
+    const bool vec = (C % 4 == 0) && ((uintptr_t)tensor % 16 == 0) && ((uintptr_t)out % 16 == 0);
+    const long total = rows * (vec ? C / 4 : C);
+    const int threads = 256;
+    long nb = (total + threads - 1) / threads;
+    if (nb > (long)TGP_NUM_SMS * 32) nb = (long)TGP_NUM_SMS * 32;
+    const unsigned blocks = (unsigned)nb;
+    cudaStream_t st = as_stream(stream);
+    TGP_DISPATCH_IDX(idx_bits, {
+        if (vec) gather_rows_kernel<IdxT, 4><<<blocks, threads, 0, st>>>(tensor, (const IdxT*)index, rows, (long)M * k, N, C, out);
+        else gather_rows_kernel<IdxT, 1><<<blocks, threads, 0, st>>>(tensor, (const IdxT*)index, rows, (long)M * k, N, C, out);
+    });
+    return check_launch("gather_rows_kernel");
+}
+
+extern "C" int tgp_select_rows(const float* t, const int64_t* rows, int B, int N, int M, int C, float* out,
+                               tgp_stream_t stream) {
+    if (!t || !rows || !out) return fail(TGP_EINVAL, "tgp_select_rows: null pointer");
+    if (B <= 0 || N <= 0 || M <= 0 || C <= 0) return fail(TGP_EINVAL, "tgp_select_rows: sizes must be positive");
+    const long total = (long)B * M * C;
+    select_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(stream)>>>(t, rows, total, N, M, C, out);
+    return check_launch("select_rows_kernel");
+}
+
+extern "C" int tgp_direction_norm(const float* xyz, const void* idx, int idx_bits, int B, int N, int k, float* out,
+                                  tgp_stream_t stream) {
+    if (!xyz || !idx || !out) return fail(TGP_EINVAL, "tgp_direction_norm: null pointer");
+    if (B <= 0 || N <= 0 || k <= 0) return fail(TGP_EINVAL, "tgp_direction_norm: sizes must be positive");
+    const long total = (long)B * N * k;
+    const int threads = 256;
+    TGP_DISPATCH_IDX(idx_bits, {
+        direction_norm_kernel<IdxT><<<(unsigned)((total + threads - 1) / threads), threads, 0, as_stream(stream)>>>(
+            xyz, (const IdxT*)idx, total, N, k, out);
+    });
+    return check_launch("direction_norm_kernel");
+}
+
+extern "C" int tgp_gather_max(const float* f, const void* idx, int idx_bits, const int64_t* rows, int B, int N, int M,
+                              int k, int C, float* out, uint8_t* arg, tgp_stream_t stream) {
+    if (!f || !idx || !out) return fail(TGP_EINVAL, "tgp_gather_max: null pointer");
+    if (B <= 0 || N <= 0 || M <= 0 || k <= 0 || C <= 0) return fail(TGP_EINVAL, "tgp_gather_max: sizes must be positive");
+    if (!rows && M != N) return fail(TGP_EINVAL, "tgp_gather_max: rows == NULL requires M == N");
+    if (k > 255) return fail(TGP_EINVAL, "tgp_gather_max: k > 255");
+    const bool vec = (C % 4 == 0) && ((uintptr_t)f % 16 == 0);
+    const long total = (long)B * M * (vec ? C / 4 : C);
+    const int threads = 256;
+    const unsigned blocks = (unsigned)((total + threads - 1) / threads);
+    cudaStream_t st = as_stream(stream);
+    TGP_DISPATCH_IDX(idx_bits, {
+        const IdxT* ip = (const IdxT*)idx;
+        if (vec && arg) gather_max_kernel<IdxT, 4, true><<<blocks, threads, 0, st>>>(f, ip, rows, N, M, k, C, total, out, arg);
+        else if (vec) gather_max_kernel<IdxT, 4, false><<<blocks, threads, 0, st>>>(f, ip, rows, N, M, k, C, total, out, arg);
+        else if (arg) gather_max_kernel<IdxT, 1, true><<<blocks, threads, 0, st>>>(f, ip, rows, N, M, k, C, total, out, arg);
+        else gather_max_kernel<IdxT, 1, false><<<blocks, threads, 0, st>>>(f, ip, rows, N, M, k, C, total, out, arg);
+    });
+    return check_launch("gather_max_kernel");
+}
+
+extern "C" int tgp_orl_global(const float* f, const void* idx, int idx_bits, int B, int N, int k, int C, float* g,
+                              uint8_t* arg, tgp_stream_t stream) {
+    if (!f || !idx || !g) return fail(TGP_EINVAL, "tgp_orl_global: null pointer");
+    if (B <= 0 || N <= 0 || k <= 0 || C <= 0) return fail(TGP_EINVAL, "tgp_orl_global: sizes must be positive");
+    if (k > 255 || B > 65535) return fail(TGP_EINVAL, "tgp_orl_global: k > 255 or B > 65535");
+    cudaStream_t st = as_stream(stream);
+    cudaError_t e = cudaMemsetAsync(g, 0, (size_t)B * C * sizeof(float), st);
+    if (e != cudaSuccess) return fail((int)e, "tgp_orl_global: memset failed");
+    // split the points of a cloud over enough CTAs to fill the machine at small B
+    const int chunks = (C + 31) / 32;
+    int nsplit = (2 * TGP_NUM_SMS + B * chunks - 1) / (B * chunks);
+    nsplit = max(1, min(nsplit, (N + 63) / 64));
+    dim3 grid(chunks, B, nsplit);
+    TGP_DISPATCH_IDX(idx_bits, {
+        if (arg) orl_global_kernel<IdxT, true><<<grid, ORL_THREADS, 0, st>>>(f, (const IdxT*)idx, N, k, C, g, arg);
+        else orl_global_kernel<IdxT, false><<<grid, ORL_THREADS, 0, st>>>(f, (const IdxT*)idx, N, k, C, g, arg);
+    });
+    return check_launch("orl_global_kernel");
+}

@@ -1,0 +1,159 @@
+// gemm_simt.cu -- fp32 FMA-pipe contraction with the fused epilogue of the 3D-GCN path.
+//
+// Replaces `feature_map @ self.weights + self.bias` (gcn3d.py:170) and the 1x1 Conv1d layers
+// STE_layer / conv2 (gcn3d.py:70-71,130,132,148,185).  Exact-fp32 path: used for small or
+// oddly shaped problems (K = 3, tiny M) and as the numerical reference of the tcgen05 path
+// in gemm_tc.cu, which takes the large projections.
+//
+// Epilogue (all optional): + bias[col] + group_bias[row / rows_per_group, col] (the ORL
+// cloud-global term) + res1 + res2, per-column affine (eval BatchNorm), ReLU;
+// each column range goes to its own destination, either row-major or the channel-group
+// "slab" layout [cgroup][row][S*4] that layer_conv_kernel bulk-copies into shared memory.
+#include "common.cuh"
+
+namespace tgp {
+
+constexpr int GM_BM = 128, GM_BN = 128, GM_BK = 16, GM_THREADS = 256;
+constexpr int GM_LD = GM_BM + 4;
+
+struct GemmDev {
+    tgp_gemm_args a;
+};
+
+__device__ __forceinline__ float4 ld4_guard(const float* base, long row, long nrows, long ld, int k0, int K, bool vec) {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (row < nrows) {
+        const float* p = base + row * ld + k0;
+        if (vec && k0 + 3 < K) v = __ldg(reinterpret_cast<const float4*>(p));
+        else {
+            if (k0 + 0 < K) v.x = __ldg(p);
+            if (k0 + 1 < K) v.y = __ldg(p + 1);
+            if (k0 + 2 < K) v.z = __ldg(p + 2);
+            if (k0 + 3 < K) v.w = __ldg(p + 3);
+        }
+    }
+    return v;
+}
+
+__device__ __forceinline__ void epilogue_store(const tgp_gemm_args& g, long row, int col, float v) {
+    if (g.bias) v += __ldg(g.bias + col);
+    if (g.group_bias) v += __ldg(g.group_bias + (row / g.rows_per_group) * g.Ncols + col);
+    if (g.res1) v += __ldg(g.res1 + row * g.ld_res1 + col);
+    if (g.res2) v += __ldg(g.res2 + row * g.ld_res2 + col);
+    if (g.scale) v = fmaf(v, __ldg(g.scale + col), __ldg(g.shift + col));
+    if (g.relu) v = fmaxf(v, 0.f);
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+        if (s < g.nseg && col >= g.seg[s].col_begin && col < g.seg[s].col_end) {
+            const int rel = col - g.seg[s].col_begin;
+            if (g.seg[s].mode == 0) g.seg[s].ptr[row * g.seg[s].ld + rel] = v;
+            else {
+                const int w = g.seg[s].slab_width;
+                const int cg = rel / w, r = rel - cg * w;
+                g.seg[s].ptr[((long)cg * g.M + row) * w + r] = v;
+            }
+        }
+    }
+}
+
+template <bool B_NK>
+__global__ void __launch_bounds__(GM_THREADS)
+gemm_simt_kernel(const __grid_constant__ GemmDev P) {
+    __shared__ __align__(16) float As[GM_BK * GM_LD];
+    __shared__ __align__(16) float Bs[GM_BK * GM_LD];
+    const tgp_gemm_args& g = P.a;
+    const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+    const long m0 = (long)blockIdx.x * GM_BM;
+    const int n0 = blockIdx.y * GM_BN;
+    const bool vecA = (g.lda % 4 == 0) && ((uintptr_t)g.A % 16 == 0);
+    const bool vecB = (g.ldb % 4 == 0) && ((uintptr_t)g.Bmat % 16 == 0);
+
+    float acc[8][8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc[r][c] = 0.f;
+
+    for (int k0 = 0; k0 < g.K; k0 += GM_BK) {
+        __syncthreads();
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int row = (tid >> 2) + h * 64, kq = (tid & 3) * 4;
+            const float4 v = ld4_guard(g.A, m0 + row, g.M, g.lda, k0 + kq, g.K, vecA);
+            As[(kq + 0) * GM_LD + row] = v.x; As[(kq + 1) * GM_LD + row] = v.y;
+            As[(kq + 2) * GM_LD + row] = v.z; As[(kq + 3) * GM_LD + row] = v.w;
+        }
+        if (B_NK) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int row = (tid >> 2) + h * 64, kq = (tid & 3) * 4;
+                const float4 v = ld4_guard(g.Bmat, n0 + row, g.Ncols, g.ldb, k0 + kq, g.K, vecB);
+                Bs[(kq + 0) * GM_LD + row] = v.x; Bs[(kq + 1) * GM_LD + row] = v.y;
+                Bs[(kq + 2) * GM_LD + row] = v.z; Bs[(kq + 3) * GM_LD + row] = v.w;
+            }
+        } else {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int kr = (tid >> 5) + h * 8, c4 = (tid & 31) * 4;
+                // (K, Ncols) N-contiguous: row index is k, "K extent" is Ncols
+                const float4 v = ld4_guard(g.Bmat, k0 + kr, g.K, g.ldb, n0 + c4, g.Ncols, vecB);
+                *reinterpret_cast<float4*>(Bs + kr * GM_LD + c4) = v;
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < GM_BK; ++kk) {
+            const float4 a0 = *reinterpret_cast<const float4*>(As + kk * GM_LD + ty * 4);
+            const float4 a1 = *reinterpret_cast<const float4*>(As + kk * GM_LD + 64 + ty * 4);
+            const float4 b0 = *reinterpret_cast<const float4*>(Bs + kk * GM_LD + tx * 4);
+            const float4 b1 = *reinterpret_cast<const float4*>(Bs + kk * GM_LD + 64 + tx * 4);
+            const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+            for (int r = 0; r < 8; ++r)
+#pragma unroll
+                for (int c = 0; c < 8; ++c) acc[r][c] = fmaf(av[r], bv[c], acc[r][c]);
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        const long row = m0 + (r < 4 ? ty * 4 + r : 64 + ty * 4 + (r - 4));
+        if (row >= g.M) continue;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const int col = n0 + (c < 4 ? tx * 4 + c : 64 + tx * 4 + (c - 4));
+            if (col < g.Ncols) epilogue_store(g, row, col, acc[r][c]);
+        }
+    }
+}
+
+}  // namespace tgp
+
+using namespace tgp;
+
+int tgp_gemm_validate(const tgp_gemm_args* a) {
+    if (!a) return fail(TGP_EINVAL, "tgp_gemm: null args");
+    if (!a->A || !a->Bmat) return fail(TGP_EINVAL, "tgp_gemm: null operand");
+    if (a->M <= 0 || a->K <= 0 || a->Ncols <= 0) return fail(TGP_EINVAL, "tgp_gemm: sizes must be positive");
+    if (a->nseg < 1 || a->nseg > 4) return fail(TGP_EINVAL, "tgp_gemm: nseg must be 1..4");
+    if (a->group_bias && a->rows_per_group <= 0) return fail(TGP_EINVAL, "tgp_gemm: rows_per_group must be positive");
+    if ((a->scale == nullptr) != (a->shift == nullptr)) return fail(TGP_EINVAL, "tgp_gemm: scale and shift go together");
+    for (int s = 0; s < a->nseg; ++s) {
+        const tgp_out_seg& sg = a->seg[s];
+        if (!sg.ptr || sg.col_begin < 0 || sg.col_end > a->Ncols || sg.col_begin >= sg.col_end)
+            return fail(TGP_EINVAL, "tgp_gemm: bad output segment");
+        if (sg.mode == 1 && (sg.slab_width <= 0 || (sg.col_end - sg.col_begin) % sg.slab_width))
+            return fail(TGP_EINVAL, "tgp_gemm: slab segment must be a multiple of slab_width");
+        if (sg.mode != 0 && sg.mode != 1) return fail(TGP_EINVAL, "tgp_gemm: bad segment mode");
+    }
+    return TGP_OK;
+}
+
+int tgp_gemm_simt(const tgp_gemm_args* a, cudaStream_t st) {
+    GemmDev P;
+    P.a = *a;
+    dim3 grid((unsigned)((a->M + GM_BM - 1) / GM_BM), (a->Ncols + GM_BN - 1) / GM_BN);
+    if (a->b_is_nk) gemm_simt_kernel<true><<<grid, GM_THREADS, 0, st>>>(P);
+    else gemm_simt_kernel<false><<<grid, GM_THREADS, 0, st>>>(P);
+    return check_launch("gemm_simt_kernel");
+}

@@ -1,0 +1,418 @@
+// knn.cu -- k-nearest-neighbour index kernels for sm_100a.
+//
+// Replaces get_neighbor_index / get_nearest_index (reference network/fs_net_repo/gcn3d.py:14-35):
+// the reference materialises the (B,N,N) distance matrix with torch.bmm, two broadcast adds
+// and torch.topk; here distances are produced tile by tile in shared memory / registers and
+// the top-(k+1) list of a query lives in the registers of one warp (one or two ranks per
+// lane, kept sorted with shuffles).  Nothing of size N*N ever reaches HBM.
+//
+// Ordering contract: ascending by (distance, index); rank 0 is dropped
+// positionally (gcn3d.py:22), never by testing j == i.
+#include "common.cuh"
+#include <math_constants.h>
+
+namespace tgp {
+
+constexpr unsigned FULL = 0xffffffffu;
+
+// Sorted list of 32*SLOTS (distance, index) pairs spread over a warp: rank = lane + 32*s.
+template <int SLOTS>
+struct WarpTopList {
+    float d[SLOTS];
+    int i[SLOTS];
+
+    __device__ __forceinline__ void init() {
+#pragma unroll
+        for (int s = 0; s < SLOTS; ++s) { d[s] = CUDART_INF_F; i[s] = -1; }
+    }
+    // distance currently at rank K-1 (the admission threshold)
+    __device__ __forceinline__ float thresh(int K) const {
+        const int r = K - 1;
+        float v = 0.f;
+#pragma unroll
+        for (int s = 0; s < SLOTS; ++s)
+            if ((r >> 5) == s) v = __shfl_sync(FULL, d[s], r & 31);
+        return v;
+    }
+    // insert (cd, cj); candidates arrive in increasing cj, so equal distances go behind
+    __device__ __forceinline__ void insert(float cd, int cj, int lane) {
+        int pos = 0;
+#pragma unroll
+        for (int s = 0; s < SLOTS; ++s) pos += __popc(__ballot_sync(FULL, d[s] <= cd));
+#pragma unroll
+        for (int s = SLOTS - 1; s >= 0; --s) {
+            float up = __shfl_up_sync(FULL, d[s], 1);
+            int upi = __shfl_up_sync(FULL, i[s], 1);
+            if (s > 0) {
+                float cr = __shfl_sync(FULL, d[s - 1], 31);
+                int cri = __shfl_sync(FULL, i[s - 1], 31);
+                if (lane == 0) { up = cr; upi = cri; }
+            }
+            const int rank = lane + 32 * s;
+            if (rank > pos) { d[s] = up; i[s] = upi; }
+            else if (rank == pos) { d[s] = cd; i[s] = cj; }
+        }
+    }
+    // admit every lane's candidate (dd, base+lane) that beats the threshold, lowest lane first
+    __device__ __forceinline__ void admit(float dd, int base, int lane, float& th, int K) {
+        unsigned m = __ballot_sync(FULL, dd < th);
+        while (m) {
+            const int src = __ffs(m) - 1;
+            m &= m - 1;
+            const float cd = __shfl_sync(FULL, dd, src);
+            if (cd < th) {
+                insert(cd, base + src, lane);
+                th = thresh(K);
+            }
+        }
+    }
+    template <typename T>
+    __device__ __forceinline__ void store_ranks(T* out, int k, int lane) const {
+        // ranks 1..k -> out[0..k)
+#pragma unroll
+        for (int s = 0; s < SLOTS; ++s) {
+            const int rank = lane + 32 * s;
+            if (rank >= 1 && rank <= k) out[rank - 1] = (T)i[s];
+        }
+    }
+};
+
+// ------------------------------------------------------------------------------------------
+// xyz-space kNN.  Distance recipe reproduces CPU torch bit for bit:
+//   q = (x0*x0 + x1*x1) + x2*x2 ; inner = fma(a2,b2, fma(a1,b1, a0*b0)) ; d = ((inner*-2)+q_j)+q_i
+// Candidates of one cloud are staged once per CTA as (x,y,z,q) float4 in shared memory; each
+// warp owns a query and scans 32 candidates per step (conflict-free LDS.128).
+constexpr int KNN_QPC = 64;        // queries per CTA
+constexpr int KNN_THREADS = 256;
+constexpr int KNN_TILE_MAX = 4096; // candidates resident in shared memory at a time
+
+template <int SLOTS>
+__global__ void __launch_bounds__(KNN_THREADS)
+knn_xyz_kernel(const float* __restrict__ xyz, int N, int k, int tile, int64_t* __restrict__ idx64,
+               int32_t* __restrict__ idx32) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float4* pts = reinterpret_cast<float4*>(smem_raw);
+    float* st_d = reinterpret_cast<float*>(pts + tile);          // [KNN_QPC][32*SLOTS], only if multi-tile
+    int* st_i = reinterpret_cast<int*>(st_d + KNN_QPC * 32 * SLOTS);
+
+    const int b = blockIdx.y;
+    const int q0 = blockIdx.x * KNN_QPC;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const float* cloud = xyz + (size_t)b * N * 3;
+    const int K = k + 1;
+    const bool multi = N > tile;
+
+    for (int t0 = 0; t0 < N; t0 += tile) {
+        const int nt = min(tile, N - t0);
+        __syncthreads();
+        for (int j = threadIdx.x; j < nt; j += KNN_THREADS) {
+            const float x0 = cloud[(t0 + j) * 3], x1 = cloud[(t0 + j) * 3 + 1], x2 = cloud[(t0 + j) * 3 + 2];
+            const float q = __fadd_rn(__fadd_rn(__fmul_rn(x0, x0), __fmul_rn(x1, x1)), __fmul_rn(x2, x2));
+            pts[j] = make_float4(x0, x1, x2, q);
+        }
+        __syncthreads();
+        for (int ql = warp; ql < KNN_QPC; ql += KNN_THREADS / 32) {
+            const int qi = q0 + ql;
+            if (qi >= N) break;
+            const float a0 = __ldg(cloud + qi * 3), a1 = __ldg(cloud + qi * 3 + 1), a2 = __ldg(cloud + qi * 3 + 2);
+            const float qq = __fadd_rn(__fadd_rn(__fmul_rn(a0, a0), __fmul_rn(a1, a1)), __fmul_rn(a2, a2));
+            WarpTopList<SLOTS> top;
+            if (t0 == 0) top.init();
+            else {
+#pragma unroll
+                for (int s = 0; s < SLOTS; ++s) {
+                    top.d[s] = st_d[(ql * SLOTS + s) * 32 + lane];
+                    top.i[s] = st_i[(ql * SLOTS + s) * 32 + lane];
+                }
+            }
+            float th = top.thresh(K);
+            for (int j0 = 0; j0 < nt; j0 += 32) {
+                const int j = j0 + lane;
+                float dd = CUDART_INF_F;
+                if (j < nt) {
+                    const float4 p = pts[j];
+                    const float inner = __fmaf_rn(a2, p.z, __fmaf_rn(a1, p.y, __fmul_rn(a0, p.x)));
+                    dd = __fadd_rn(__fadd_rn(__fmul_rn(inner, -2.0f), p.w), qq);
+                }
+                top.admit(dd, t0 + j0, lane, th, K);
+            }
+            if (t0 + nt >= N) {
+                if (idx64) top.store_ranks(idx64 + ((size_t)b * N + qi) * k, k, lane);
+                if (idx32) top.store_ranks(idx32 + ((size_t)b * N + qi) * k, k, lane);
+            } else if (multi) {
+#pragma unroll
+                for (int s = 0; s < SLOTS; ++s) {
+                    st_d[(ql * SLOTS + s) * 32 + lane] = top.d[s];
+                    st_i[(ql * SLOTS + s) * 32 + lane] = top.i[s];
+                }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// nearest source point: d = (s_j + t_i) - 2*inner (gcn3d.py:33, a different op order from kNN),
+// strict '<' so the lowest index wins.  One thread per target, sources staged as (x,y,z,|s|^2).
+constexpr int NN_THREADS = 128;
+constexpr int NN_TILE = 2048;
+
+__global__ void __launch_bounds__(NN_THREADS)
+nearest_kernel(const float* __restrict__ tgt, const float* __restrict__ src, int N, int M,
+               int64_t* __restrict__ idx64, int32_t* __restrict__ idx32) {
+    __shared__ float4 sp[NN_TILE];
+    const int b = blockIdx.y;
+    const int i = blockIdx.x * NN_THREADS + threadIdx.x;
+    const float* sb = src + (size_t)b * M * 3;
+    float t0 = 0.f, t1 = 0.f, t2 = 0.f;
+    if (i < N) {
+        const float* t = tgt + ((size_t)b * N + i) * 3;
+        t0 = t[0]; t1 = t[1]; t2 = t[2];
+    }
+    const float tn = __fadd_rn(__fadd_rn(__fmul_rn(t0, t0), __fmul_rn(t1, t1)), __fmul_rn(t2, t2));
+    float best = CUDART_INF_F;
+    int bj = 0;
+    for (int m0 = 0; m0 < M; m0 += NN_TILE) {
+        const int nt = min(NN_TILE, M - m0);
+        __syncthreads();
+        for (int j = threadIdx.x; j < nt; j += NN_THREADS) {
+            const float x0 = sb[(m0 + j) * 3], x1 = sb[(m0 + j) * 3 + 1], x2 = sb[(m0 + j) * 3 + 2];
+            sp[j] = make_float4(x0, x1, x2,
+                                __fadd_rn(__fadd_rn(__fmul_rn(x0, x0), __fmul_rn(x1, x1)), __fmul_rn(x2, x2)));
+        }
+        __syncthreads();
+#pragma unroll 4
+        for (int j = 0; j < nt; ++j) {
+            const float4 p = sp[j];
+            const float inner = __fmaf_rn(t2, p.z, __fmaf_rn(t1, p.y, __fmul_rn(t0, p.x)));
+            const float d = __fsub_rn(__fadd_rn(p.w, tn), __fmul_rn(2.0f, inner));
+            if (d < best) { best = d; bj = m0 + j; }
+        }
+    }
+    if (i < N) {
+        if (idx64) idx64[(size_t)b * N + i] = bj;
+        if (idx32) idx32[(size_t)b * N + i] = bj;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// feature-space kNN (RF-F, gcn3d.py:201-206): same expanded formula with D = 128/256.
+// A CTA owns 64 queries; candidate tiles of 128 points are contracted against them with a
+// register-tiled fp32 FMA micro-kernel (4x8 per thread), the 64x128 distance tile is parked
+// in shared memory and the 8 warps run the same register top-list selection over its rows.
+constexpr int KF_BM = 64, KF_BN = 128, KF_BK = 16, KF_THREADS = 256;
+constexpr int KF_LDA = KF_BM + 4, KF_LDB = KF_BN + 4, KF_LDD = KF_BN + 4;
+
+__global__ void rownorm_kernel(const float* __restrict__ x, long rows, int D, float* __restrict__ q) {
+    const long r = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (r >= rows) return;
+    const float* p = x + r * D;
+    float s = 0.f;
+    for (int c = lane; c < D; c += 32) s = fmaf(p[c], p[c], s);
+    s = warp_sum(s);
+    if (lane == 0) q[r] = s;
+}
+
+template <int SLOTS>
+__global__ void __launch_bounds__(KF_THREADS)
+knn_feat_kernel(const float* __restrict__ x, const float* __restrict__ qn, int N, int D, int k,
+                int64_t* __restrict__ idx64, int32_t* __restrict__ idx32) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* As = reinterpret_cast<float*>(smem_raw);              // [KF_BK][KF_LDA]
+    float* Bs = As + KF_BK * KF_LDA;                             // [KF_BK][KF_LDB]
+    float* Ds = Bs + KF_BK * KF_LDB;                             // [KF_BM][KF_LDD]
+    float* st_d = Ds + KF_BM * KF_LDD;                           // [KF_BM][32*SLOTS]
+    int* st_i = reinterpret_cast<int*>(st_d + KF_BM * 32 * SLOTS);
+
+    const int b = blockIdx.y;
+    const int q0 = blockIdx.x * KF_BM;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int ty = tid >> 4, tx = tid & 15;
+    const float* xb = x + (size_t)b * N * D;
+    const float* qb = qn + (size_t)b * N;
+    const int K = k + 1;
+    const bool vec = (D & 3) == 0;
+
+    for (int c0 = 0; c0 < N; c0 += KF_BN) {
+        float acc[4][8];
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int c = 0; c < 8; ++c) acc[r][c] = 0.f;
+
+        for (int k0 = 0; k0 < D; k0 += KF_BK) {
+            __syncthreads();
+            // A chunk: 64 rows x 16 k  (one float4 per thread); B chunk: 128 rows x 16 k (two)
+            {
+                const int row = tid >> 2, kq = (tid & 3) * 4;
+                const int gr = q0 + row;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (gr < N) {
+                    const float* p = xb + (size_t)gr * D + k0 + kq;
+                    if (vec && k0 + kq + 3 < D) v = *reinterpret_cast<const float4*>(p);
+                    else {
+                        if (k0 + kq + 0 < D) v.x = p[0];
+                        if (k0 + kq + 1 < D) v.y = p[1];
+                        if (k0 + kq + 2 < D) v.z = p[2];
+                        if (k0 + kq + 3 < D) v.w = p[3];
+                    }
+                }
+                As[(kq + 0) * KF_LDA + row] = v.x; As[(kq + 1) * KF_LDA + row] = v.y;
+                As[(kq + 2) * KF_LDA + row] = v.z; As[(kq + 3) * KF_LDA + row] = v.w;
+            }
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int row = (tid >> 2) + h * 64, kq = (tid & 3) * 4;
+                const int gr = c0 + row;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (gr < N) {
+                    const float* p = xb + (size_t)gr * D + k0 + kq;
+                    if (vec && k0 + kq + 3 < D) v = *reinterpret_cast<const float4*>(p);
+                    else {
+                        if (k0 + kq + 0 < D) v.x = p[0];
+                        if (k0 + kq + 1 < D) v.y = p[1];
+                        if (k0 + kq + 2 < D) v.z = p[2];
+                        if (k0 + kq + 3 < D) v.w = p[3];
+                    }
+                }
+                Bs[(kq + 0) * KF_LDB + row] = v.x; Bs[(kq + 1) * KF_LDB + row] = v.y;
+                Bs[(kq + 2) * KF_LDB + row] = v.z; Bs[(kq + 3) * KF_LDB + row] = v.w;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int kk = 0; kk < KF_BK; ++kk) {
+                const float4 a = *reinterpret_cast<const float4*>(As + kk * KF_LDA + ty * 4);
+                const float4 b0 = *reinterpret_cast<const float4*>(Bs + kk * KF_LDB + tx * 4);
+                const float4 b1 = *reinterpret_cast<const float4*>(Bs + kk * KF_LDB + 64 + tx * 4);
+                const float av[4] = {a.x, a.y, a.z, a.w};
+                const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+                for (int r = 0; r < 4; ++r)
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) acc[r][c] = fmaf(av[r], bv[c], acc[r][c]);
+            }
+        }
+        // distance tile: d = ((inner*-2) + q_j) + q_i   (gcn3d.py:20)
+        {
+            float qj[8];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const int col = c0 + (c < 4 ? tx * 4 + c : 64 + tx * 4 + (c - 4));
+                qj[c] = col < N ? __ldg(qb + col) : 0.f;
+            }
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const int row = q0 + ty * 4 + r;
+                const float qi = row < N ? __ldg(qb + row) : 0.f;
+                float o[8];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) o[c] = __fadd_rn(__fadd_rn(__fmul_rn(acc[r][c], -2.0f), qj[c]), qi);
+                *reinterpret_cast<float4*>(Ds + (ty * 4 + r) * KF_LDD + tx * 4) = make_float4(o[0], o[1], o[2], o[3]);
+                *reinterpret_cast<float4*>(Ds + (ty * 4 + r) * KF_LDD + 64 + tx * 4) = make_float4(o[4], o[5], o[6], o[7]);
+            }
+        }
+        __syncthreads();
+        const int nt = min(KF_BN, N - c0);
+        const bool last = c0 + KF_BN >= N;
+        for (int ql = warp; ql < KF_BM; ql += KF_THREADS / 32) {
+            const int qi = q0 + ql;
+            if (qi >= N) break;
+            WarpTopList<SLOTS> top;
+            if (c0 == 0) top.init();
+            else {
+#pragma unroll
+                for (int s = 0; s < SLOTS; ++s) {
+                    top.d[s] = st_d[(ql * SLOTS + s) * 32 + lane];
+                    top.i[s] = st_i[(ql * SLOTS + s) * 32 + lane];
+                }
+            }
+            float th = top.thresh(K);
+            const float* drow = Ds + ql * KF_LDD;
+#pragma unroll
+            for (int j0 = 0; j0 < KF_BN; j0 += 32) {
+                const int j = j0 + lane;
+                const float dd = j < nt ? drow[j] : CUDART_INF_F;
+                top.admit(dd, c0 + j0, lane, th, K);
+            }
+            if (last) {
+                if (idx64) top.store_ranks(idx64 + ((size_t)b * N + qi) * k, k, lane);
+                if (idx32) top.store_ranks(idx32 + ((size_t)b * N + qi) * k, k, lane);
+            } else {
+#pragma unroll
+                for (int s = 0; s < SLOTS; ++s) {
+                    st_d[(ql * SLOTS + s) * 32 + lane] = top.d[s];
+                    st_i[(ql * SLOTS + s) * 32 + lane] = top.i[s];
+                }
+            }
+        }
+    }
+}
+
+}  // namespace tgp
+
+using namespace tgp;
+
+extern "C" int tgp_knn_xyz(const float* xyz, int B, int N, int k, int64_t* idx64, int32_t* idx32,
+                           tgp_stream_t stream) {
+    if (!xyz || (!idx64 && !idx32)) return fail(TGP_EINVAL, "tgp_knn_xyz: null pointer");
+    if (B <= 0 || N <= 0 || k <= 0) return fail(TGP_EINVAL, "tgp_knn_xyz: B, N, k must be positive");
+    if (k + 1 > N) return fail(TGP_EINVAL, "tgp_knn_xyz: k+1 > N (torch.topk would raise, gcn3d.py:21)");
+    if (k + 1 > 64) return fail(TGP_EINVAL, "tgp_knn_xyz: k > 63 unsupported");
+    if (B > 65535) return fail(TGP_EINVAL, "tgp_knn_xyz: B > 65535");
+    const int tile = N < KNN_TILE_MAX ? N : KNN_TILE_MAX;
+    const int slots = (k + 1 > 32) ? 2 : 1;
+    size_t smem = (size_t)tile * sizeof(float4);
+    if (N > tile) smem += (size_t)KNN_QPC * 32 * slots * 8;
+    dim3 grid((N + KNN_QPC - 1) / KNN_QPC, B);
+    cudaStream_t st = as_stream(stream);
+    if (slots == 1) {
+        cudaFuncSetAttribute(knn_xyz_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        knn_xyz_kernel<1><<<grid, KNN_THREADS, smem, st>>>(xyz, N, k, tile, idx64, idx32);
+    } else {
+        cudaFuncSetAttribute(knn_xyz_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        knn_xyz_kernel<2><<<grid, KNN_THREADS, smem, st>>>(xyz, N, k, tile, idx64, idx32);
+    }
+    return check_launch("knn_xyz_kernel");
+}
+
+extern "C" size_t tgp_knn_feat_workspace(int B, int N, int D) {
+    (void)D;
+    return (size_t)B * N * sizeof(float);
+}
+
+extern "C" int tgp_knn_feat(const float* x, int B, int N, int D, int k, int64_t* idx64, int32_t* idx32,
+                            void* workspace, size_t workspace_bytes, tgp_stream_t stream) {
+    if (!x || (!idx64 && !idx32) || !workspace) return fail(TGP_EINVAL, "tgp_knn_feat: null pointer");
+    if (B <= 0 || N <= 0 || k <= 0 || D <= 0) return fail(TGP_EINVAL, "tgp_knn_feat: sizes must be positive");
+    if (k + 1 > N) return fail(TGP_EINVAL, "tgp_knn_feat: k+1 > N (torch.topk would raise, gcn3d.py:21)");
+    if (k + 1 > 64) return fail(TGP_EINVAL, "tgp_knn_feat: k > 63 unsupported");
+    if (B > 65535) return fail(TGP_EINVAL, "tgp_knn_feat: B > 65535");
+    if (workspace_bytes < tgp_knn_feat_workspace(B, N, D)) return fail(TGP_ENOSPACE, "tgp_knn_feat: workspace too small");
+    cudaStream_t st = as_stream(stream);
+    float* qn = static_cast<float*>(workspace);
+    const long rows = (long)B * N;
+    rownorm_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(x, rows, D, qn);
+    int rc = check_launch("rownorm_kernel");
+    if (rc) return rc;
+    const int slots = (k + 1 > 32) ? 2 : 1;
+    const size_t smem = sizeof(float) * (KF_BK * KF_LDA + KF_BK * KF_LDB + KF_BM * KF_LDD) + (size_t)KF_BM * 32 * slots * 8;
+    dim3 grid((N + KF_BM - 1) / KF_BM, B);
+    if (slots == 1) {
+        cudaFuncSetAttribute(knn_feat_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        knn_feat_kernel<1><<<grid, KF_THREADS, smem, st>>>(x, qn, N, D, k, idx64, idx32);
+    } else {
+        cudaFuncSetAttribute(knn_feat_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        knn_feat_kernel<2><<<grid, KF_THREADS, smem, st>>>(x, qn, N, D, k, idx64, idx32);
+    }
+    return check_launch("knn_feat_kernel");
+}
+
+extern "C" int tgp_nearest(const float* target, const float* source, int B, int N, int M,
+                           int64_t* idx64, int32_t* idx32, tgp_stream_t stream) {
+    if (!target || !source || (!idx64 && !idx32)) return fail(TGP_EINVAL, "tgp_nearest: null pointer");
+    if (B <= 0 || N <= 0 || M <= 0) return fail(TGP_EINVAL, "tgp_nearest: sizes must be positive");
+    if (B > 65535) return fail(TGP_EINVAL, "tgp_nearest: B > 65535");
+    dim3 grid((N + NN_THREADS - 1) / NN_THREADS, B);
+    nearest_kernel<<<grid, NN_THREADS, 0, as_stream(stream)>>>(target, source, N, M, idx64, idx32);
+    return check_launch("nearest_kernel");
+}

@@ -1,0 +1,137 @@
+"""Face_Enc -- the 3D-GCN backbone of TG-Pose (reference network/fs_net_repo/FaceRecon.py:12-86)
+as one fused pipeline over the sm_100a kernels.
+
+Same attribute / parameter names and construction order as the reference class (state_dicts and
+seeds are interchangeable); the reference reads its hyper-parameters from absl FLAGS
+(FaceRecon.py:15-17,54), here they are constructor arguments with the flags' defaults
+(config/config.py:7,44-45,150).
+
+What the fused forward does differently from calling the five layers one by one:
+  * the xyz kNN is computed once per level and shared by conv RF-P / ORL / Pool (the reference
+    recomputes identical results 3+1 times at level 0 and 2+1 times at level 1);
+  * eval-mode BatchNorm + ReLU are folded into the last GEMM epilogue of each layer;
+  * Pool gathers only the sampled rows.
+"""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import gcn3d, ops
+
+
+class Face_Enc(nn.Module):
+    def __init__(self, neighbor_num=20, support_num=7, obj_c=6, output_channels=2500):
+        super().__init__()
+        self.neighbor_num = neighbor_num
+        self.support_num = support_num
+        self.output_channels = output_channels
+        self.obj_c = obj_c
+
+        self.conv_0 = gcn3d.HSlayer_surface(kernel_num=128, support_num=self.support_num)
+        self.conv_1 = gcn3d.HS_layer(128, 128, support_num=self.support_num)
+        self.pool_1 = gcn3d.Pool_layer(pooling_rate=4, neighbor_num=4)
+        self.conv_2 = gcn3d.HS_layer(128, 256, support_num=self.support_num)
+        self.conv_3 = gcn3d.HS_layer(256, 256, support_num=self.support_num)
+        self.pool_2 = gcn3d.Pool_layer(pooling_rate=4, neighbor_num=4)
+        self.conv_4 = gcn3d.HS_layer(256, 512, support_num=self.support_num)
+
+        self.bn1 = nn.BatchNorm1d(128)
+        self.bn2 = nn.BatchNorm1d(256)
+        self.bn3 = nn.BatchNorm1d(256)
+
+        feat_c = 128 + 128 + 256 + 256 + 512 + obj_c
+        self.proj_layer = nn.Sequential(nn.Conv1d(feat_c, feat_c, kernel_size=1, bias=False),
+                                        nn.BatchNorm1d(feat_c),
+                                        nn.LeakyReLU(negative_slope=0.2),
+                                        nn.Conv1d(feat_c, feat_c, kernel_size=1, bias=False))
+        # test hooks (parity tiers T1/T2, SURVEY 8c'): replay / record the 12 kNN + 2 nearest index tensors
+        self._inject = None
+        self._record = None
+
+    # -- helpers -------------------------------------------------------------------------
+    def _next_idx(self, compute):
+        """index tensors in the reference's call order; each slot is either injected or computed."""
+        if self._inject is not None:
+            t = self._inject[self._slot].to(dtype=torch.int32).contiguous()
+        else:
+            t = compute()
+        self._slot += 1
+        if self._record is not None:
+            self._record.append(t)
+        return t
+
+    def _bn_post(self, bn):
+        """eval BatchNorm folded to per-channel (scale, shift) + ReLU for the GEMM epilogue."""
+        scale = bn.weight.detach() * torch.rsqrt(bn.running_var + bn.eps)
+        shift = bn.bias.detach() - bn.running_mean * scale
+        return (scale.contiguous(), shift.contiguous(), True)
+
+    def _bn_relu(self, bn, x):
+        return F.relu(bn(x.transpose(1, 2)).transpose(1, 2))
+
+    # -- forward -------------------------------------------------------------------------
+    def forward(self, vertices, cat_id, enable_proj=False):
+        """vertices (B,N,3), cat_id (B,1) -> (feat (B,N,1286), feat_global (B,1286,N)); ref FaceRecon.py:39-86."""
+        bs, vertice_num, _ = vertices.size()
+        k = self.neighbor_num
+        fold = not self.training
+        self._slot = 0
+        share = self._inject is None
+
+        def xyz_knn(v, kk):
+            return ops.knn_xyz(v, kk, want64=False, want32=True)[1]
+
+        def feat_knn(f, kk):
+            return ops.knn_feat(f, kk, want64=False, want32=True)[1]
+
+        # level 0
+        i0 = self._next_idx(lambda: xyz_knn(vertices, k))
+        i0_orl = self._next_idx(lambda: i0 if share else xyz_knn(vertices, k))
+        # HSlayer_surface uses one xyz index for both RF-P and ORL; with injected indices they are the same tensor
+        fm_0 = self.conv_0(vertices, k, idx_xyz=i0, post=(None, None, True))
+        i1 = self._next_idx(lambda: feat_knn(fm_0, k))
+        i1_orl = self._next_idx(lambda: i0 if share else xyz_knn(vertices, k))
+        if fold:
+            fm_1 = self.conv_1(vertices, fm_0, k, idx_feat=i1, idx_xyz=i1_orl, post=self._bn_post(self.bn1))
+        else:
+            fm_1 = self._bn_relu(self.bn1, self.conv_1(vertices, fm_0, k, idx_feat=i1, idx_xyz=i1_orl))
+        ip1 = self._next_idx(lambda: i0[:, :, :4].contiguous() if share else xyz_knn(vertices, 4))
+        v_pool_1, fm_pool_1 = self.pool_1(vertices, fm_1, idx_xyz=ip1)
+
+        # level 1
+        k1 = min(k, v_pool_1.shape[1] // 8)
+        i2 = self._next_idx(lambda: feat_knn(fm_pool_1, k1))
+        i2_orl = self._next_idx(lambda: xyz_knn(v_pool_1, k1))
+        if fold:
+            fm_2 = self.conv_2(v_pool_1, fm_pool_1, k1, idx_feat=i2, idx_xyz=i2_orl, post=self._bn_post(self.bn2))
+        else:
+            fm_2 = self._bn_relu(self.bn2, self.conv_2(v_pool_1, fm_pool_1, k1, idx_feat=i2, idx_xyz=i2_orl))
+        i3 = self._next_idx(lambda: feat_knn(fm_2, k1))
+        i3_orl = self._next_idx(lambda: i2_orl if share else xyz_knn(v_pool_1, k1))
+        if fold:
+            fm_3 = self.conv_3(v_pool_1, fm_2, k1, idx_feat=i3, idx_xyz=i3_orl, post=self._bn_post(self.bn3))
+        else:
+            fm_3 = self._bn_relu(self.bn3, self.conv_3(v_pool_1, fm_2, k1, idx_feat=i3, idx_xyz=i3_orl))
+        ip2 = self._next_idx(lambda: (i2_orl[:, :, :4].contiguous() if (share and k1 >= 4) else xyz_knn(v_pool_1, 4)))
+        v_pool_2, fm_pool_2 = self.pool_2(v_pool_1, fm_3, idx_xyz=ip2)
+
+        # level 2
+        k2 = min(k, v_pool_2.shape[1] // 8)
+        i4 = self._next_idx(lambda: feat_knn(fm_pool_2, k2))
+        i4_orl = self._next_idx(lambda: xyz_knn(v_pool_2, k2))
+        fm_4 = self.conv_4(v_pool_2, fm_pool_2, k2, idx_feat=i4, idx_xyz=i4_orl)
+
+        # nearest-neighbour upsampling back to level 0 (FaceRecon.py:69-73)
+        nn1 = self._next_idx(lambda: ops.nearest(vertices, v_pool_1, want64=False, want32=True)[1])
+        nn2 = self._next_idx(lambda: ops.nearest(vertices, v_pool_2, want64=False, want32=True)[1])
+        fm_2u = gcn3d.indexing_neighbor_new(fm_2, nn1).squeeze(2)
+        fm_3u = gcn3d.indexing_neighbor_new(fm_3, nn1).squeeze(2)
+        fm_4u = gcn3d.indexing_neighbor_new(fm_4, nn2).squeeze(2)
+
+        obj_idh = cat_id.view(-1, 1)
+        one_hot = torch.zeros(bs, self.obj_c, device=vertices.device).scatter_(1, obj_idh.long(), 1)
+        one_hot = one_hot.unsqueeze(1).expand(-1, vertice_num, -1)
+        feat = torch.cat([fm_0, fm_1, fm_2u, fm_3u, fm_4u, one_hot], dim=2)
+        feat_global = feat.permute(0, 2, 1)
+        feat_global_prj = self.proj_layer(feat_global) if enable_proj else feat_global
+        return feat, feat_global_prj

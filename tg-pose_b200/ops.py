@@ -1,0 +1,246 @@
+"""Tensor-level wrappers over the C-ABI (torch supplies device memory and the current stream only).
+
+Every function takes/returns CUDA fp32 tensors in the reference's layouts; index tensors are
+int64 where the reference's callers see them (torch.topk output, gcn3d.py:21) and int32 inside
+the fused encoder.  No function here computes anything in PyTorch.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import GemmArgs, OutSeg
+
+
+# bench.py sets this to a dict to time every C-ABI call with CUDA events on the launching stream
+EVENT_LOG = None
+
+
+def _run(name, cfn, *args):
+    log = EVENT_LOG
+    if log is None:
+        _lib.check(cfn(*args), "tgp_" + name)
+        return
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    rc = cfn(*args)
+    b.record()
+    log.setdefault(name, []).append((a, b))
+    _lib.check(rc, "tgp_" + name)
+
+
+def _p(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _f32c(t, name):
+    if not t.is_cuda:
+        raise RuntimeError(f"{name}: expected a CUDA tensor (tg-pose_b200 has no CPU path)")
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def _idx(t, name):
+    if not t.is_cuda:
+        raise RuntimeError(f"{name}: expected a CUDA index tensor")
+    if t.dtype not in (torch.int64, torch.int32):
+        t = t.long()
+    t = t.contiguous()
+    return t, (64 if t.dtype == torch.int64 else 32)
+
+
+# --------------------------------------------------------------------------------------- kNN
+def knn_xyz(xyz, k, want64=True, want32=False):
+    """get_neighbor_index on (B,N,3), gcn3d.py:14-23.  Returns (idx64 or None, idx32 or None)."""
+    xyz = _f32c(xyz, "knn_xyz")
+    B, N, D = xyz.shape
+    assert D == 3
+    i64 = torch.empty((B, N, k), dtype=torch.int64, device=xyz.device) if want64 else None
+    i32 = torch.empty((B, N, k), dtype=torch.int32, device=xyz.device) if want32 else None
+    _run("knn_xyz", _lib.load().tgp_knn_xyz, _p(xyz), B, N, k, _p(i64), _p(i32), _stream())
+    return i64, i32
+
+
+def knn_feat(x, k, want64=True, want32=False):
+    """get_neighbor_index on (B,N,D) features (RF-F), gcn3d.py:14-23,201-206."""
+    x = _f32c(x, "knn_feat")
+    B, N, D = x.shape
+    lib = _lib.load()
+    ws_bytes = lib.tgp_knn_feat_workspace(B, N, D)
+    ws = torch.empty((ws_bytes + 3) // 4, dtype=torch.float32, device=x.device)
+    i64 = torch.empty((B, N, k), dtype=torch.int64, device=x.device) if want64 else None
+    i32 = torch.empty((B, N, k), dtype=torch.int32, device=x.device) if want32 else None
+    _run("knn_feat", lib.tgp_knn_feat, _p(x), B, N, D, k, _p(i64), _p(i32), _p(ws), ws_bytes, _stream())
+    return i64, i32
+
+
+def nearest(target, source, want64=True, want32=False):
+    """get_nearest_index, gcn3d.py:26-35 -> (B,N,1)."""
+    target, source = _f32c(target, "nearest"), _f32c(source, "nearest")
+    B, N, _ = target.shape
+    M = source.shape[1]
+    i64 = torch.empty((B, N, 1), dtype=torch.int64, device=target.device) if want64 else None
+    i32 = torch.empty((B, N, 1), dtype=torch.int32, device=target.device) if want32 else None
+    _run("nearest", _lib.load().tgp_nearest, _p(target), _p(source), B, N, M, _p(i64), _p(i32), _stream())
+    return i64, i32
+
+
+# --------------------------------------------------------------------------------------- gathers
+def gather_rows(tensor, index):
+    """indexing_neighbor_new, gcn3d.py:38-46: (B,N,C),(B,M,k) -> (B,M,k,C)."""
+    tensor = _f32c(tensor, "gather_rows")
+    index, bits = _idx(index, "gather_rows")
+    B, N = tensor.shape[0], tensor.shape[1]
+    C = tensor.numel() // (B * N)
+    _, M, k = index.shape
+    out = torch.empty((B, M, k, C), dtype=torch.float32, device=tensor.device)
+    _run("gather_rows", _lib.load().tgp_gather_rows, _p(tensor), _p(index), bits, B, N, M, k, C, _p(out), _stream())
+    return out
+
+
+def select_rows(tensor, rows):
+    """tensor[:, rows, :] with one row list for the whole batch (gcn3d.py:243-244)."""
+    tensor = _f32c(tensor, "select_rows")
+    rows = rows.to(device=tensor.device, dtype=torch.int64).contiguous()
+    B, N, C = tensor.shape
+    M = rows.numel()
+    out = torch.empty((B, M, C), dtype=torch.float32, device=tensor.device)
+    _run("select_rows", _lib.load().tgp_select_rows, _p(tensor), _p(rows), B, N, M, C, _p(out), _stream())
+    return out
+
+
+def direction_norm(xyz, idx):
+    """get_neighbor_direction_norm, gcn3d.py:48-58 -> (B,N,k,3)."""
+    xyz = _f32c(xyz, "direction_norm")
+    idx, bits = _idx(idx, "direction_norm")
+    B, N, k = idx.shape
+    out = torch.empty((B, N, k, 3), dtype=torch.float32, device=xyz.device)
+    _run("direction_norm", _lib.load().tgp_direction_norm, _p(xyz), _p(idx), bits, B, N, k, _p(out), _stream())
+    return out
+
+
+def gather_max(f, idx, rows=None, want_arg=False):
+    """max_j f[b, idx[b, rows[m], j], :] -> (B,M,C) (+ uint8 arg)."""
+    f = _f32c(f, "gather_max")
+    idx, bits = _idx(idx, "gather_max")
+    B, N, C = f.shape
+    k = idx.shape[2]
+    if rows is not None:
+        rows = rows.to(device=f.device, dtype=torch.int64).contiguous()
+        M = rows.numel()
+    else:
+        M = N
+    out = torch.empty((B, M, C), dtype=torch.float32, device=f.device)
+    arg = torch.empty((B, M, C), dtype=torch.uint8, device=f.device) if want_arg else None
+    _run("gather_max", _lib.load().tgp_gather_max, _p(f), _p(idx), bits, _p(rows), B, N, M, k, C, _p(out), _p(arg), _stream())
+    return (out, arg) if want_arg else out
+
+
+def orl_global(f, idx, want_arg=False):
+    """get_ORL_global before .repeat, gcn3d.py:210-217 -> (B,C)."""
+    f = _f32c(f, "orl_global")
+    idx, bits = _idx(idx, "orl_global")
+    B, N, C = f.shape
+    k = idx.shape[2]
+    g = torch.empty((B, C), dtype=torch.float32, device=f.device)
+    arg = torch.empty((B, N, C), dtype=torch.uint8, device=f.device) if want_arg else None
+    _run("orl_global", _lib.load().tgp_orl_global, _p(f), _p(idx), bits, B, N, k, C, _p(g), _p(arg), _stream())
+    return (g, arg) if want_arg else g
+
+
+# --------------------------------------------------------------------------------------- graph convs
+def surface_conv(xyz, idx, directions, S, C, want_arg=False):
+    """HSlayer_surface.graph_conv, gcn3d.py:91-106 -> (B,N,C)."""
+    xyz = _f32c(xyz, "surface_conv")
+    directions = _f32c(directions, "surface_conv")
+    idx, bits = _idx(idx, "surface_conv")
+    B, N, k = idx.shape
+    out = torch.empty((B, N, C), dtype=torch.float32, device=xyz.device)
+    arg = torch.empty((B, N, S * C), dtype=torch.uint8, device=xyz.device) if want_arg else None
+    _run("surface_conv_fwd", _lib.load().tgp_surface_conv_fwd, _p(xyz), _p(idx), bits, _p(directions), B, N, k, S, C, _p(out),
+                                                _p(arg), _stream())
+    return (out, arg) if want_arg else out
+
+
+def edge_records(xyz, idx):
+    xyz = _f32c(xyz, "edge_records")
+    idx, bits = _idx(idx, "edge_records")
+    B, N, k = idx.shape
+    rec = torch.empty((B, N, k, 4), dtype=torch.float32, device=xyz.device)
+    _run("edge_records", _lib.load().tgp_edge_records, _p(xyz), _p(idx), bits, B, N, k, _p(rec), _stream())
+    return rec
+
+
+def layer_conv(rec, directions, centre, support_slab, B, N, S, C, want_arg=False):
+    """HS_layer.graph_conv after the projection, gcn3d.py:157-180 -> (B,N,C).
+    centre: (B*N, C) view (any row stride); support_slab: [C/4][B*N][S*4]."""
+    k = rec.shape[2]
+    directions = _f32c(directions, "layer_conv")
+    out = torch.empty((B, N, C), dtype=torch.float32, device=rec.device)
+    arg = torch.empty((C // 4, B * N, S * 4), dtype=torch.uint8, device=rec.device) if want_arg else None
+    assert centre.stride(-1) == 1
+    _run("layer_conv_fwd", _lib.load().tgp_layer_conv_fwd, _p(rec), _p(directions), _p(centre), centre.stride(0), _p(support_slab),
+                                              B, N, k, S, C, _p(out), _p(arg), _stream())
+    return (out, arg) if want_arg else out
+
+
+# --------------------------------------------------------------------------------------- gemm
+def gemm(A, Bmat, b_is_nk, segs, bias=None, group_bias=None, rows_per_group=0, res1=None, res2=None,
+         scale=None, shift=None, relu=False, K=None, Ncols=None):
+    """C = A @ B (+ epilogue) written to `segs` = [(col_begin, col_end, tensor, mode, slab_width)].
+    A: (M,K) with unit column stride; Bmat: (K,Ncols) or, if b_is_nk, (Ncols,K); both may be row-strided views."""
+    assert A.stride(-1) == 1 and Bmat.stride(-1) == 1
+    M = A.shape[0]
+    if K is None:
+        K = A.shape[1]
+    if Ncols is None:
+        Ncols = Bmat.shape[0] if b_is_nk else Bmat.shape[1]
+    a = GemmArgs()
+    a.A, a.lda = A.data_ptr(), A.stride(0)
+    a.Bmat, a.ldb, a.b_is_nk = Bmat.data_ptr(), Bmat.stride(0), 1 if b_is_nk else 0
+    a.M, a.K, a.Ncols = M, K, Ncols
+    a.bias = bias.data_ptr() if bias is not None else None
+    a.group_bias = group_bias.data_ptr() if group_bias is not None else None
+    a.rows_per_group = rows_per_group
+    if res1 is not None:
+        assert res1.stride(-1) == 1
+        a.res1, a.ld_res1 = res1.data_ptr(), res1.stride(0)
+    if res2 is not None:
+        assert res2.stride(-1) == 1
+        a.res2, a.ld_res2 = res2.data_ptr(), res2.stride(0)
+    a.scale = scale.data_ptr() if scale is not None else None
+    a.shift = shift.data_ptr() if shift is not None else None
+    a.relu = 1 if relu else 0
+    a.nseg = len(segs)
+    for i, (c0, c1, t, mode, sw) in enumerate(segs):
+        a.seg[i] = OutSeg(c0, c1, mode, sw, t.stride(0) if mode == 0 else 0, t.data_ptr())
+    if EVENT_LOG is not None:
+        EVENT_LOG.setdefault("__gemm_shapes__", []).append((M, K, Ncols))
+    _run("gemm", _lib.load().tgp_gemm, ctypes.byref(a), _stream())
+
+
+def linear_nk(x2d, weight_nk, **kw):
+    """x (M,K) @ weight (Ncols,K)^T -> new (M,Ncols) tensor; epilogue options as in gemm()."""
+    out = torch.empty((x2d.shape[0], weight_nk.shape[0]), dtype=torch.float32, device=x2d.device)
+    gemm(x2d, weight_nk, True, [(0, weight_nk.shape[0], out, 0, 0)], **kw)
+    return out
+
+
+# --------------------------------------------------------------------------------------- chamfer
+def chamfer_forward(xyz1, xyz2, dist1, dist2, idx1, idx2, sums=None):
+    B, n, _ = xyz1.shape
+    m = xyz2.shape[1]
+    _run("chamfer_fwd", _lib.load().tgp_chamfer_fwd, _p(xyz1), _p(xyz2), B, n, m, _p(dist1), _p(dist2), _p(idx1), _p(idx2),
+                                           _p(sums), _stream())
+
+
+def chamfer_backward(xyz1, xyz2, gd1, gd2, idx1, idx2, g1, g2):
+    B, n, _ = xyz1.shape
+    m = xyz2.shape[1]
+    _run("chamfer_bwd", _lib.load().tgp_chamfer_bwd, _p(xyz1), _p(xyz2), _p(gd1), _p(gd2), _p(idx1), _p(idx2), B, n, m,
+                                           _p(g1), _p(g2), _stream())
