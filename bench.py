@@ -297,16 +297,28 @@ def kernel_report(event_log, steps, B, peaks):
                            "peak_source": "148 SM x 128 lanes x 2 flop x 1.965 GHz (SURVEY 8d); no measured fp32 peak",
                            "hbm": {"achieved": byts / t / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                                    "frac": byts / t / 1e9 / peaks["hbm_gbs"], "peak_source": peaks["source"]}}
-    elif top == "gemm":
-        flops = 0.0
-        for m, kdim, n in event_log.get("__gemm_shapes__", []):
-            flops += 2.0 * m * kdim * n
+    elif top == "gemm_tc":
+        # useful flops 2*M*K*N per launch ("a 3xTF32 GEMM's useful flops are the plain 2MNK");
+        # tensor roof = measured bf16 peak / 2 (TF32 runs at half the bf16 rate) / 3 passes
+        flops = sum(2.0 * m * kdim * n for nm, m, kdim, n in event_log.get("__gemm_shapes__", []) if nm == "gemm_tc") / steps
         t = agg[top]["ms_per_step"] / 1e3
-        flops /= steps
-        out["roofline"] = {"bound": "fp32", "kernel": "gemm_simt_kernel (all launches in the step)",
-                           "achieved": flops / t / 1e12, "peak": FP32_PEAK_TFLOPS, "unit": "TFLOP/s",
-                           "frac": flops / t / 1e12 / FP32_PEAK_TFLOPS, "traffic": None,
-                           "peak_source": "148 SM x 128 lanes x 2 flop x 1.965 GHz (SURVEY 8d)"}
+        peak = peaks["bf16_tflops_sustained"] / 2.0
+        out["roofline"] = {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 3xTF32, all launches in the step)",
+                           "achieved": 3.0 * flops / t / 1e12, "peak": peak, "unit": "TFLOP/s",
+                           "frac": 3.0 * flops / t / 1e12 / peak, "traffic": None,
+                           "useful_fp32_equiv_tflops": flops / t / 1e12,
+                           "peak_source": f"{peaks['source']} sustained bf16 dense / 2 (TF32 rate); achieved counts all 3 TF32 passes"}
+    if os.environ.get("TGP_BENCH_GEMM_TABLE"):
+        shapes = event_log.get("__gemm_shapes__", [])
+        evs = {"gemm": list(event_log.get("gemm", [])), "gemm_tc": list(event_log.get("gemm_tc", []))}
+        pos = {"gemm": 0, "gemm_tc": 0}
+        rows = {}
+        for nm, m, kdim, n in shapes:
+            a, b = evs[nm][pos[nm]]
+            pos[nm] += 1
+            rows.setdefault((nm, m, kdim, n), []).append(a.elapsed_time(b))
+        for key, v in sorted(rows.items(), key=lambda kv: -sum(kv[1])):
+            sys.stderr.write(f"GEMM {key}: {len(v) / steps:.1f}/step, {sum(v) / steps:.4f} ms/step\n")
     out["kernels"].pop("__gemm_shapes__", None)
     return out
 

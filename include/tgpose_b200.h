@@ -79,18 +79,24 @@ int tgp_gather_max(const float* f, const void* idx, int idx_bits, const int64_t*
 
 /* get_ORL_global(feature (B,N,C), vertices, k), gcn3d.py:210-217, given the xyz kNN:
  * g[b,c] = mean_n max_j f[b, idx[b,n,j], c]   (the (B,1,C) tensor before .repeat).
- * arg (B,N,C) uint8 optional. */
+ * arg (B,N,C) uint8 optional.  workspace: tgp_orl_workspace(B,N,C) bytes of scratch for the per-chunk
+ * partial sums; they are reduced in a fixed order, so the result is deterministic and does not depend
+ * on which batch a cloud sits in. */
+size_t tgp_orl_workspace(int B, int N, int C);
 int tgp_orl_global(const float* f, const void* idx, int idx_bits, int B, int N, int k, int C,
-                   float* g, uint8_t* arg, tgp_stream_t stream);
+                   float* g, uint8_t* arg, void* workspace, size_t workspace_bytes, tgp_stream_t stream);
 
 /* ------------------------------------------------------------------ graph convolutions */
 
 /* HSlayer_surface.graph_conv, gcn3d.py:91-106:
  * out[b,n,c] = mean_s max_j relu(<dirnorm(b,n,j), normalize(directions,dim=0)[:, s*C+c]>).
  * xyz (B,N,3), idx (B,N,k), directions (3,S*C) raw parameter, out (B,N,C),
- * arg (B,N,S*C) uint8 optional (arg-max neighbour slot per (n,s,c)). */
+ * arg (B,N,S*C) uint8 optional (arg-max neighbour slot per (n,s,c)).
+ * out_split (B*N, 2*Kp) optional, Kp = tgp_split_kpad(C): the same result as a tensor-core operand
+ * [tf32(v) | v - tf32(v)] for the contraction that follows (padding columns must be pre-zeroed). */
 int tgp_surface_conv_fwd(const float* xyz, const void* idx, int idx_bits, const float* directions,
-                         int B, int N, int k, int S, int C, float* out, uint8_t* arg, tgp_stream_t stream);
+                         int B, int N, int k, int S, int C, float* out, uint8_t* arg, float* out_split,
+                         tgp_stream_t stream);
 
 /* Edge records for the layer convolution: rec[b,n,j] = (dx,dy,dz, bitcast<float>(int idx[b,n,j]))
  * with (dx,dy,dz) = get_neighbor_direction_norm (gcn3d.py:48-58).  rec: (B,N,k,4) fp32, 16-byte aligned. */
@@ -102,15 +108,20 @@ int tgp_edge_records(const float* xyz, const void* idx, int idx_bits, int B, int
  * edge_rec from tgp_edge_records (directions from xyz, indices from feature space, gcn3d.py:201-207);
  * centre (B*N, C) row-major with leading dimension ld_centre;
  * support in SLAB layout [C/4][B*N][S][4] as written by tgp_gemm (mode 1), C % 4 == 0, S*4 <= 32;
- * arg_slab [C/4][B*N][S*4] uint8 optional: arg-max neighbour slot per (n,s,c), same layout. */
+ * arg_slab [C/4][B*N][S*4] uint8 optional: arg-max neighbour slot per (n,s,c), same layout;
+ * out_split (B*N, 2*Kp) optional: as in tgp_surface_conv_fwd. */
 int tgp_layer_conv_fwd(const float* edge_rec, const float* directions,
                        const float* centre, long ld_centre, const float* support_slab,
-                       int B, int N, int k, int S, int C, float* out, uint8_t* arg_slab, tgp_stream_t stream);
+                       int B, int N, int k, int S, int C, float* out, uint8_t* arg_slab, float* out_split,
+                       tgp_stream_t stream);
 
 /* ------------------------------------------------------------------ dense contraction */
 
-/* One output column range of tgp_gemm.  mode 0: row-major, out[m*ld + (col - col_begin)].
- * mode 1: SLAB, columns are ordered (cgroup, s, c4) and go to [cgroup][m][S*4]. */
+/* One output column range of tgp_gemm (ranges may overlap: every matching segment is written).
+ * mode 0: row-major, out[m*ld + (col - col_begin)].
+ * mode 1: SLAB, columns are ordered (cgroup, s, c4) and go to [cgroup][m][S*4] (slab_width = S*4).
+ * mode 2: SPLIT, the value is written as a tensor-core operand for the next contraction:
+ *         tf32(v) at out[m*ld + rel] and v - tf32(v) at out[m*ld + slab_width + rel] (slab_width = Kp). */
 typedef struct {
     int col_begin, col_end;
     int mode;
@@ -131,12 +142,25 @@ typedef struct {
     const float* res1; long ld_res1;  /* optional residuals, (M, Ncols) */
     const float* res2; long ld_res2;
     const float* scale; const float* shift; /* optional per-column affine (eval BatchNorm) applied last */
-    int relu;
+    int relu;                     /* 1: max(v, 0) after the affine */
+    const float* neg_slope;       /* optional per-column leaky slope: v > 0 ? v : v*neg_slope[col] (overrides relu) */
     int nseg; tgp_out_seg seg[4];
+    /* tensor-core path (tcgen05, 3xTF32): both operands pre-split by tgp_split_tf32 into
+     * [tf32(x) | x - tf32(x)], (rows, 2*Kp) with Kp = tgp_split_kpad(K).  A_split: (M, 2Kp),
+     * B_split: (Ncols, 2Kp).  When both are non-NULL they are used instead of A / Bmat;
+     * when NULL the exact-fp32 FMA path runs on A / Bmat. */
+    const float* A_split;
+    const float* B_split;
 } tgp_gemm_args;
 
 /* feature_map @ weights + bias (gcn3d.py:170) and every 1x1 Conv1d on the path. */
 int tgp_gemm(const tgp_gemm_args* args_host, tgp_stream_t stream);
+
+/* K rounded up to the tensor-core K block (32). */
+int tgp_split_kpad(int K);
+/* dst (rows, 2*Kp) = [tf32(src) | src - tf32(src)], zero padded.  src is (rows, K) with row stride ld,
+ * or, if src_is_kn, (K, rows) with row stride ld (transposed on the fly: HS_layer.weights, gcn3d.py:125). */
+int tgp_split_tf32(const float* src, long rows, int K, long ld, int src_is_kn, float* dst, tgp_stream_t stream);
 
 /* ------------------------------------------------------------------ chamfer (losses/chamfer3D) */
 

@@ -27,7 +27,8 @@ class GemmArgs(ctypes.Structure):
                 ("res1", c_void_p), ("ld_res1", c_long),
                 ("res2", c_void_p), ("ld_res2", c_long),
                 ("scale", c_void_p), ("shift", c_void_p),
-                ("relu", c_int), ("nseg", c_int), ("seg", OutSeg * 4)]
+                ("relu", c_int), ("neg_slope", c_void_p), ("nseg", c_int), ("seg", OutSeg * 4),
+                ("A_split", c_void_p), ("B_split", c_void_p)]
 
 
 # name -> (restype, argtypes); must list every symbol include/tgpose_b200.h declares
@@ -44,13 +45,17 @@ SIGNATURES = {
     "tgp_direction_norm": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "tgp_gather_max": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p,
                                c_void_p, c_void_p]),
-    "tgp_orl_global": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "tgp_orl_workspace": (c_size_t, [c_int, c_int, c_int]),
+    "tgp_orl_global": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                               c_size_t, c_void_p]),
     "tgp_surface_conv_fwd": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int,
-                                     c_void_p, c_void_p, c_void_p]),
+                                     c_void_p, c_void_p, c_void_p, c_void_p]),
     "tgp_edge_records": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "tgp_layer_conv_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_long, c_void_p, c_int, c_int, c_int, c_int, c_int,
-                                   c_void_p, c_void_p, c_void_p]),
+                                   c_void_p, c_void_p, c_void_p, c_void_p]),
     "tgp_gemm": (c_int, [ctypes.POINTER(GemmArgs), c_void_p]),
+    "tgp_split_kpad": (c_int, [c_int]),
+    "tgp_split_tf32": (c_int, [c_void_p, c_long, c_int, c_long, c_int, c_void_p, c_void_p]),
     "tgp_chamfer_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                 c_void_p, c_void_p]),
     "tgp_chamfer_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,

@@ -35,7 +35,8 @@ def _pack_layer(weights, bias, ste_w, S, C):
     return wcat, bcat
 
 
-def _orl_tail(feature, idx_xyz, conv2_w, f_ste, B, N, C, post, want_arg=False):
+def _orl_tail(feature, idx_xyz, conv2_w, f_ste, B, N, C, post, want_arg=False, feature_split=None,
+              want_split=False):
     """ORL_forward (gcn3d.py:108-112,182-186) + the STE skip: conv2(cat[f, g]) + f + f_STE, where
     conv2(cat[f, g.repeat]) = f @ W[:, :C]^T + (g @ W[:, C:]^T) broadcast over the cloud."""
     M = B * N
@@ -48,14 +49,19 @@ def _orl_tail(feature, idx_xyz, conv2_w, f_ste, B, N, C, post, want_arg=False):
     out = torch.empty((B, N, C), dtype=torch.float32, device=feature.device)
     scale, shift, relu = post if post is not None else (None, None, False)
     f2 = feature.view(M, C)
-    ops.gemm(f2, w2[:, :C], True, [(0, C, out.view(M, C), 0, 0)], group_bias=gb, rows_per_group=N,
-             res1=f2, res2=f_ste, scale=scale, shift=shift, relu=relu)
-    return out, g, arg
+    segs = [(0, C, out.view(M, C), 0, 0)]
+    out_split = None
+    if want_split:   # the next layer's projection reads this result as a tensor-core operand
+        out_split = ops._split_buf(M, C, feature.device)
+        segs.append((0, C, out_split, 2, ops.kpad(C)))
+    ops.gemm(f2, w2[:, :C], True, segs, group_bias=gb, rows_per_group=N,
+             res1=f2, res2=f_ste, scale=scale, shift=shift, relu=relu, A_split=feature_split)
+    return out, g, arg, out_split
 
 
 class HSSurfaceFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, xyz, directions, ste_w, conv2_w, k, S, C, idx_xyz, post):
+    def forward(ctx, xyz, directions, ste_w, conv2_w, k, S, C, idx_xyz, post, want_split):
         xyz = xyz.contiguous().float()
         B, N, _ = xyz.shape
         M = B * N
@@ -63,25 +69,29 @@ class HSSurfaceFn(torch.autograd.Function):
         f_ste = ops.linear_nk(xyz.view(M, 3), ste_w.reshape(C, 3))
         if idx_xyz is None:
             idx_xyz = ops.knn_xyz(xyz, k, want64=False, want32=True)[1]
-        if train:
-            feature, arg = ops.surface_conv(xyz, idx_xyz, directions, S, C, want_arg=True)
-        else:
-            feature, arg = ops.surface_conv(xyz, idx_xyz, directions, S, C), None
-        out, g, arg_orl = _orl_tail(feature, idx_xyz, conv2_w, f_ste, B, N, C, post, want_arg=train)
+        tc = ops.tc_eligible(M, C, C)
+        feature, arg, fsplit = ops.surface_conv(xyz, idx_xyz, directions, S, C, want_arg=train, want_split=tc,
+                                                full=True)
+        out, g, arg_orl, out_split = _orl_tail(feature, idx_xyz, conv2_w, f_ste, B, N, C, post, want_arg=train,
+                                               feature_split=fsplit, want_split=want_split and tc)
         if train:
             ctx.save_for_backward(xyz, directions, ste_w, conv2_w, idx_xyz, arg, feature, g, arg_orl)
             ctx.cfg = (k, S, C, post)
-        return out
+        if out_split is None:
+            out_split = out.new_empty(0)
+        ctx.mark_non_differentiable(out_split)
+        return out, out_split
 
     @staticmethod
-    def backward(ctx, grad_out):
+    def backward(ctx, grad_out, _g_split):
         from . import backward as bw
         return bw.hs_surface_backward(ctx, grad_out)
 
 
 class HSLayerFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, xyz, fm, weights, bias, directions, ste_w, conv2_w, k, S, C, idx_feat, idx_xyz, post):
+    def forward(ctx, xyz, fm, weights, bias, directions, ste_w, conv2_w, k, S, C, idx_feat, idx_xyz, post,
+                fm_split, want_split):
         xyz = xyz.contiguous().float()
         fm = fm.contiguous().float()
         B, N, cin = fm.shape
@@ -92,27 +102,30 @@ class HSLayerFn(torch.autograd.Function):
         centre = torch.empty((M, C), dtype=torch.float32, device=dev)
         slab = torch.empty((C // 4, M, S * 4), dtype=torch.float32, device=dev)
         f_ste = torch.empty((M, C), dtype=torch.float32, device=dev)
+        tc = ops.tc_eligible(M, C, C)
         ops.gemm(fm.view(M, cin), wcat, False,
                  [(0, C, centre, 0, 0), (C, C + S * C, slab, 1, S * 4), (C + S * C, (S + 2) * C, f_ste, 0, 0)],
-                 bias=bcat)
+                 bias=bcat, A_split=fm_split if (fm_split is not None and fm_split.numel()) else None)
         if idx_feat is None:
             idx_feat = ops.knn_feat(fm, k, want64=False, want32=True)[1]
         rec = ops.edge_records(xyz, idx_feat)
-        if train:
-            feature, arg = ops.layer_conv(rec, directions, centre, slab, B, N, S, C, want_arg=True)
-        else:
-            feature, arg = ops.layer_conv(rec, directions, centre, slab, B, N, S, C), None
+        feature, arg, fsplit = ops.layer_conv(rec, directions, centre, slab, B, N, S, C, want_arg=train,
+                                              want_split=tc, full=True)
         if idx_xyz is None:
             idx_xyz = ops.knn_xyz(xyz, k, want64=False, want32=True)[1]
-        out, g, arg_orl = _orl_tail(feature, idx_xyz, conv2_w, f_ste, B, N, C, post, want_arg=train)
+        out, g, arg_orl, out_split = _orl_tail(feature, idx_xyz, conv2_w, f_ste, B, N, C, post, want_arg=train,
+                                               feature_split=fsplit, want_split=want_split and tc)
         if train:
             ctx.save_for_backward(fm, weights, bias, directions, ste_w, conv2_w, rec, slab, arg, idx_xyz,
                                   feature, g, arg_orl)
             ctx.cfg = (k, S, C, post)
-        return out
+        if out_split is None:
+            out_split = out.new_empty(0)
+        ctx.mark_non_differentiable(out_split)
+        return out, out_split
 
     @staticmethod
-    def backward(ctx, grad_out):
+    def backward(ctx, grad_out, _g_split):
         from . import backward as bw
         return bw.hs_layer_backward(ctx, grad_out)
 

@@ -89,13 +89,14 @@ __global__ void gather_max_kernel(const float* __restrict__ f, const IdxT* __res
     }
 }
 
-// ORL global feature: g[b,c] += (1/N) * sum over this CTA's points of max_j f[b, idx[b,n,j], c].
+// ORL global feature: part[b,split,c] = sum over this CTA's points of max_j f[b, idx[b,n,j], c];
+// orl_finalize_kernel adds the splits in a fixed order and divides by N (deterministic).
 // CTA = (32-channel chunk, cloud, point split); lane = channel, warps stride over points.
 constexpr int ORL_THREADS = 256;
 template <typename IdxT, bool ARG>
 __global__ void __launch_bounds__(ORL_THREADS)
 orl_global_kernel(const float* __restrict__ f, const IdxT* __restrict__ idx, int N, int k, int C,
-                  float* __restrict__ g, uint8_t* __restrict__ arg) {
+                  float* __restrict__ partial, uint8_t* __restrict__ arg) {
     __shared__ float part[ORL_THREADS / 32][32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int c = blockIdx.x * 32 + lane;
@@ -124,8 +125,19 @@ orl_global_kernel(const float* __restrict__ f, const IdxT* __restrict__ idx, int
         float s = 0.f;
 #pragma unroll
         for (int w = 0; w < ORL_THREADS / 32; ++w) s += part[w][lane];
-        if (c < C) atomicAdd(g + b * C + c, s / (float)N);
+        if (c < C) partial[(b * nsplit + sp) * C + c] = s;
     }
+}
+
+__global__ void orl_finalize_kernel(const float* __restrict__ partial, int nsplit, int C, long total, int N,
+                                    float* __restrict__ g) {
+    const long e = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= total) return;
+    const long b = e / C;
+    const int c = (int)(e - b * C);
+    float s = 0.f;
+    for (int sp = 0; sp < nsplit; ++sp) s += partial[(b * nsplit + sp) * C + c];
+    g[e] = s / (float)N;
 }
 
 }  // namespace tgp
@@ -194,22 +206,31 @@ extern "C" int tgp_gather_max(const float* f, const void* idx, int idx_bits, con
     return check_launch("gather_max_kernel");
 }
 
+static int orl_nsplit(int N) {   // depends on N only, so a cloud's result is independent of the batch it is in
+    int s = (N + 63) / 64;
+    return s < 1 ? 1 : (s > 16 ? 16 : s);
+}
+
+extern "C" size_t tgp_orl_workspace(int B, int N, int C) { return (size_t)B * orl_nsplit(N) * C * sizeof(float); }
+
 extern "C" int tgp_orl_global(const float* f, const void* idx, int idx_bits, int B, int N, int k, int C, float* g,
-                              uint8_t* arg, tgp_stream_t stream) {
-    if (!f || !idx || !g) return fail(TGP_EINVAL, "tgp_orl_global: null pointer");
+                              uint8_t* arg, void* workspace, size_t workspace_bytes, tgp_stream_t stream) {
+    if (!f || !idx || !g || !workspace) return fail(TGP_EINVAL, "tgp_orl_global: null pointer");
+    if (workspace_bytes < tgp_orl_workspace(B, N, C)) return fail(TGP_ENOSPACE, "tgp_orl_global: workspace too small");
     if (B <= 0 || N <= 0 || k <= 0 || C <= 0) return fail(TGP_EINVAL, "tgp_orl_global: sizes must be positive");
     if (k > 255 || B > 65535) return fail(TGP_EINVAL, "tgp_orl_global: k > 255 or B > 65535");
     cudaStream_t st = as_stream(stream);
-    cudaError_t e = cudaMemsetAsync(g, 0, (size_t)B * C * sizeof(float), st);
-    if (e != cudaSuccess) return fail((int)e, "tgp_orl_global: memset failed");
-    // split the points of a cloud over enough CTAs to fill the machine at small B
     const int chunks = (C + 31) / 32;
-    int nsplit = (2 * TGP_NUM_SMS + B * chunks - 1) / (B * chunks);
-    nsplit = max(1, min(nsplit, (N + 63) / 64));
+    const int nsplit = orl_nsplit(N);
+    float* partial = static_cast<float*>(workspace);
     dim3 grid(chunks, B, nsplit);
     TGP_DISPATCH_IDX(idx_bits, {
-        if (arg) orl_global_kernel<IdxT, true><<<grid, ORL_THREADS, 0, st>>>(f, (const IdxT*)idx, N, k, C, g, arg);
-        else orl_global_kernel<IdxT, false><<<grid, ORL_THREADS, 0, st>>>(f, (const IdxT*)idx, N, k, C, g, arg);
+        if (arg) orl_global_kernel<IdxT, true><<<grid, ORL_THREADS, 0, st>>>(f, (const IdxT*)idx, N, k, C, partial, arg);
+        else orl_global_kernel<IdxT, false><<<grid, ORL_THREADS, 0, st>>>(f, (const IdxT*)idx, N, k, C, partial, arg);
     });
-    return check_launch("orl_global_kernel");
+    int rc = check_launch("orl_global_kernel");
+    if (rc) return rc;
+    const long total = (long)B * C;
+    orl_finalize_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(partial, nsplit, C, total, N, g);
+    return check_launch("orl_finalize_kernel");
 }

@@ -41,13 +41,20 @@ __device__ __forceinline__ void epilogue_store(const tgp_gemm_args& g, long row,
     if (g.res1) v += __ldg(g.res1 + row * g.ld_res1 + col);
     if (g.res2) v += __ldg(g.res2 + row * g.ld_res2 + col);
     if (g.scale) v = fmaf(v, __ldg(g.scale + col), __ldg(g.shift + col));
-    if (g.relu) v = fmaxf(v, 0.f);
+    if (g.neg_slope) v = v > 0.f ? v : v * __ldg(g.neg_slope + col);
+    else if (g.relu) v = fmaxf(v, 0.f);
 #pragma unroll
     for (int s = 0; s < 4; ++s) {
         if (s < g.nseg && col >= g.seg[s].col_begin && col < g.seg[s].col_end) {
             const int rel = col - g.seg[s].col_begin;
             if (g.seg[s].mode == 0) g.seg[s].ptr[row * g.seg[s].ld + rel] = v;
-            else {
+            else if (g.seg[s].mode == 2) {
+                uint32_t hb;
+                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v));
+                const float hi = __uint_as_float(hb);
+                g.seg[s].ptr[row * g.seg[s].ld + rel] = hi;
+                g.seg[s].ptr[row * g.seg[s].ld + g.seg[s].slab_width + rel] = v - hi;
+            } else {
                 const int w = g.seg[s].slab_width;
                 const int cg = rel / w, r = rel - cg * w;
                 g.seg[s].ptr[((long)cg * g.M + row) * w + r] = v;
@@ -133,7 +140,7 @@ using namespace tgp;
 
 int tgp_gemm_validate(const tgp_gemm_args* a) {
     if (!a) return fail(TGP_EINVAL, "tgp_gemm: null args");
-    if (!a->A || !a->Bmat) return fail(TGP_EINVAL, "tgp_gemm: null operand");
+    if ((!a->A || !a->Bmat) && (!a->A_split || !a->B_split)) return fail(TGP_EINVAL, "tgp_gemm: null operand");
     if (a->M <= 0 || a->K <= 0 || a->Ncols <= 0) return fail(TGP_EINVAL, "tgp_gemm: sizes must be positive");
     if (a->nseg < 1 || a->nseg > 4) return fail(TGP_EINVAL, "tgp_gemm: nseg must be 1..4");
     if (a->group_bias && a->rows_per_group <= 0) return fail(TGP_EINVAL, "tgp_gemm: rows_per_group must be positive");
@@ -144,7 +151,8 @@ int tgp_gemm_validate(const tgp_gemm_args* a) {
             return fail(TGP_EINVAL, "tgp_gemm: bad output segment");
         if (sg.mode == 1 && (sg.slab_width <= 0 || (sg.col_end - sg.col_begin) % sg.slab_width))
             return fail(TGP_EINVAL, "tgp_gemm: slab segment must be a multiple of slab_width");
-        if (sg.mode != 0 && sg.mode != 1) return fail(TGP_EINVAL, "tgp_gemm: bad segment mode");
+        if (sg.mode < 0 || sg.mode > 2) return fail(TGP_EINVAL, "tgp_gemm: bad segment mode");
+        if (sg.mode == 2 && sg.slab_width < sg.col_end - sg.col_begin) return fail(TGP_EINVAL, "tgp_gemm: split segment wider than Kp");
     }
     return TGP_OK;
 }

@@ -1,0 +1,387 @@
+// gemm_tc.cu -- the dense contractions of the path on the 5th-gen tensor cores (tcgen05 + TMEM + TMA).
+//
+// Replaces `feature_map @ self.weights + self.bias` (gcn3d.py:170), STE_layer / conv2 (gcn3d.py:70-71,
+// 130,132) and the 1x1 Conv1d head layers at fp32-equivalent accuracy: 3xTF32.
+//
+// Why 3xTF32: a single TF32 pass misses the rel-1e-4 tolerance on 41.7 % of the final features and flips
+// 5-9 % of the downstream feature-space kNN rows.  Each operand is split once into
+// hi = tf32(x) and lo = x - hi (both exactly representable), stored side by side as [hi | lo] (2*Kp
+// columns, Kp = K rounded up to 32), and the K loop runs three segments into ONE TMEM accumulator:
+//     lo(A).hi(B) + hi(A).lo(B) + hi(A).hi(B)          (small terms first)
+// so the 3xTF32 product is a plain TF32 GEMM over a 3x longer K -- no operand transform inside the
+// kernel, TMA feeds the tensor core directly.
+//
+// Kernel: persistent, one CTA per SM, 192 threads:
+//   warp 0    TMA producer   cp.async.bulk.tensor.2d (128B swizzle) -> 4-stage smem ring, mbarrier tx-count
+//   warp 1    MMA issuer     tcgen05.mma.cta_group::1.kind::tf32, M=128 x N=BN x K=8, fp32 accum in TMEM,
+//                            tcgen05.commit releases smem stages / publishes the accumulator
+//   warps 2-5 epilogue       tcgen05.ld 32x32b.x32 -> registers -> fused epilogue -> global
+// Two TMEM accumulator stages (2 x BN columns) let the epilogue of tile t overlap the mainloop of t+1.
+#include "common.cuh"
+#include <cuda.h>
+#include <stdlib.h>
+
+namespace tgp {
+
+constexpr int TC_BM = 128;
+constexpr int TC_BK = 32;                 // 32 fp32 = one 128-byte swizzle span
+constexpr int TC_STAGES = 4;
+constexpr int TC_THREADS = 192;
+constexpr int TC_A_BYTES = TC_BM * TC_BK * 4;   // 16 KB
+
+struct GemmDev {
+    tgp_gemm_args a;
+};
+
+__device__ __forceinline__ uint32_t s_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void tc_mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void tc_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tc_mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done = 0;
+    unsigned spins = 0;
+    while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.b32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(s_u32(bar)), "r"(parity) : "memory");
+        if (!done && ++spins > (1u << 27)) __trap();   // a broken pipeline must fault, never hang the GPU
+    }
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tm, int c0, int c1, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(s_u32(dst)), "l"(tm), "r"(c0), "r"(c1), "r"(s_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// K-major, 128B-swizzled operand tile: rows of 128 B, 8-row groups 1024 B apart (SBO), LBO unused (=1),
+// descriptor version 1 (sm_100), layout type 2 (SWIZZLE_128B).
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;                  // leading byte offset (ignored for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;        // stride byte offset
+    d |= (uint64_t)1 << 46;                  // version
+    d |= (uint64_t)2 << 61;                  // SWIZZLE_128B
+    return d;
+}
+
+#define TMEM_LD_32x32(taddr, r)                                                                         \
+    asm volatile(                                                                                       \
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                       \
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "                       \
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"       \
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),   \
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]),          \
+          "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]),        \
+          "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]),        \
+          "=r"(r[29]), "=r"(r[30]), "=r"(r[31])                                                             \
+        : "r"(taddr))
+
+template <int BN>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ GemmDev P, int Kp, int num_m_tiles, int num_tiles, int dbg) {
+    extern __shared__ __align__(1024) unsigned char tc_smem[];
+    constexpr int B_BYTES = BN * TC_BK * 4;
+    constexpr int STAGE_BYTES = TC_A_BYTES + B_BYTES;
+    // carve: [stages x (A | B)] [barriers] [tmem ptr]
+    unsigned char* base = reinterpret_cast<unsigned char*>(((uintptr_t)tc_smem + 1023) & ~(uintptr_t)1023);
+    uint64_t* full = reinterpret_cast<uint64_t*>(base + TC_STAGES * STAGE_BYTES);
+    uint64_t* empty = full + TC_STAGES;
+    uint64_t* tmem_full = empty + TC_STAGES;
+    uint64_t* tmem_empty = tmem_full + 2;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+    float* stage_all = reinterpret_cast<float*>(base + TC_STAGES * STAGE_BYTES + 256);   // [4 warps][32][33]
+
+    const tgp_gemm_args& g = P.a;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int kblocks = Kp / TC_BK;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < TC_STAGES; ++s) { tc_mbar_init(full + s, 1); tc_mbar_init(empty + s, 1); }
+        for (int s = 0; s < 2; ++s) { tc_mbar_init(tmem_full + s, 1); tc_mbar_init(tmem_empty + s, 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {   // one full warp allocates all 512 TMEM columns (1 CTA per SM)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(tmem_ptr)), "n"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+                const int m0 = (t % num_m_tiles) * TC_BM, n0 = (t / num_m_tiles) * BN;
+                for (int seg = 0; seg < 3; ++seg) {
+                    // segment order: lo.hi, hi.lo, hi.hi
+                    const int a_off = (seg == 0) ? Kp : 0, b_off = (seg == 1) ? Kp : 0;
+                    for (int kb = 0; kb < kblocks; ++kb) {
+                        tc_mbar_wait(empty + stage, phase ^ 1);
+                        unsigned char* sa = base + stage * STAGE_BYTES;
+                        if (dbg & 4) { tc_mbar_arrive(full + stage); }
+                        else {
+                            tc_mbar_expect_tx(full + stage, STAGE_BYTES);
+                            tma_load_2d(sa, &tmA, a_off + kb * TC_BK, m0, full + stage);
+                            tma_load_2d(sa + TC_A_BYTES, &tmB, b_off + kb * TC_BK, n0, full + stage);
+                        }
+                        if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+            int stage = 0;
+            uint32_t phase = 0;
+            int it = 0;
+            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+                const int acc = it & 1;
+                const uint32_t acc_phase = (it >> 1) & 1;
+                tc_mbar_wait(tmem_empty + acc, acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BN;
+                uint32_t accum = 0;
+                for (int kb = 0; kb < 3 * kblocks; ++kb) {
+                    tc_mbar_wait(full + stage, phase);
+                    tc_fence_after();
+                    const uint32_t sa = s_u32(base + stage * STAGE_BYTES);
+                    const uint64_t adesc = make_sw128_desc(sa), bdesc = make_sw128_desc(sa + TC_A_BYTES);
+#pragma unroll
+                    for (int k = 0; k < ((dbg & 2) ? 0 : TC_BK / 8); ++k) {
+                        // +32 B along K inside the swizzle span = +2 in the descriptor's 16-byte address units
+                        umma_tf32(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, accum);
+                        accum = 1;
+                    }
+                    umma_commit(empty + stage);
+                    if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(tmem_full + acc);
+            }
+        }
+    } else {
+        // ===================== epilogue (warps 2..5 -> TMEM lane quarters 2,3,0,1) =====================
+        const int quarter = warp & 3;
+        int it = 0;
+        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+            const int acc = it & 1;
+            const uint32_t acc_phase = (it >> 1) & 1;
+            const int m0 = (t % num_m_tiles) * TC_BM, n0 = (t / num_m_tiles) * BN;
+            tc_mbar_wait(tmem_full + acc, acc_phase);
+            tc_fence_after();
+            // TMEM gives each thread one ROW (32 consecutive columns per load); a padded shared-memory
+            // transpose turns that into lane = COLUMN so that every global access of the epilogue
+            // (residual loads, output stores) is a full, coalesced 128-byte row segment.
+            float* stg = stage_all + (warp - 2) * (32 * 33);
+            const long row0 = (long)m0 + quarter * 32;
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                uint32_t r[32];
+                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + c0);
+                TMEM_LD_32x32(taddr, r);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                __syncwarp();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = __uint_as_float(r[j]);
+                __syncwarp();
+                const int col = n0 + c0 + lane;
+                if (col < g.Ncols && !(dbg & 1)) {
+                    // per-column constants of this lane
+                    const float bias = g.bias ? __ldg(g.bias + col) : 0.f;
+                    const float sc = g.scale ? __ldg(g.scale + col) : 1.f;
+                    const float sh = g.scale ? __ldg(g.shift + col) : 0.f;
+                    const float slope = g.neg_slope ? __ldg(g.neg_slope + col) : (g.relu ? 0.f : 1.f);
+                    float* cp[4];
+                    long rs[4];
+                    int lo_off[4];
+#pragma unroll
+                    for (int s = 0; s < 4; ++s) {
+                        cp[s] = nullptr; rs[s] = 0; lo_off[s] = 0;
+                        if (s < g.nseg && col >= g.seg[s].col_begin && col < g.seg[s].col_end) {
+                            const int rel = col - g.seg[s].col_begin;
+                            if (g.seg[s].mode == 1) {
+                                const int w = g.seg[s].slab_width;
+                                const int cg = rel / w, rr = rel - cg * w;
+                                cp[s] = g.seg[s].ptr + (long)cg * g.M * w + rr;
+                                rs[s] = w;
+                            } else {
+                                cp[s] = g.seg[s].ptr + rel;
+                                rs[s] = g.seg[s].ld;
+                                if (g.seg[s].mode == 2) lo_off[s] = g.seg[s].slab_width;
+                            }
+                        }
+                    }
+                    const int nrows = (int)min((long)32, g.M - row0);
+                    const float* gbp = g.group_bias ? g.group_bias + col : nullptr;
+                    const float* r1p = g.res1 ? g.res1 + col : nullptr;
+                    const float* r2p = g.res2 ? g.res2 + col : nullptr;
+#pragma unroll 4
+                    for (int rr = 0; rr < nrows; ++rr) {
+                        const long row = row0 + rr;
+                        float v = stg[rr * 33 + lane] + bias;
+                        if (gbp) v += __ldg(gbp + (row / g.rows_per_group) * g.Ncols);
+                        if (r1p) v += __ldg(r1p + row * g.ld_res1);
+                        if (r2p) v += __ldg(r2p + row * g.ld_res2);
+                        v = fmaf(v, sc, sh);
+                        v = v > 0.f ? v : v * slope;
+#pragma unroll
+                        for (int s = 0; s < 4; ++s) {
+                            if (cp[s]) {
+                                if (lo_off[s]) {
+                                    uint32_t hb;
+                                    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v));
+                                    const float hi = __uint_as_float(hb);
+                                    cp[s][row * rs[s]] = hi;
+                                    cp[s][row * rs[s] + lo_off[s]] = v - hi;
+                                } else cp[s][row * rs[s]] = v;
+                            }
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) tc_mbar_arrive(tmem_empty + acc);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
+    }
+}
+
+// operand split: dst[r, 0:Kp) = tf32(src[r,:]) ; dst[r, Kp:2Kp) = src - hi ; zero padding beyond K.
+// src_is_kn: src is stored (K, rows) (HS_layer.weights, gcn3d.py:125) and is transposed on the fly.
+__global__ void split_tf32_kernel(const float* __restrict__ src, long rows, int K, long ld, int src_is_kn, int Kp,
+                                  float* __restrict__ dst) {
+    // one CTA per row chunk: no per-element division, coalesced along K
+    for (long r = blockIdx.x; r < rows; r += gridDim.x) {
+        float* d = dst + r * 2 * Kp;
+        for (int k = threadIdx.x; k < Kp; k += blockDim.x) {
+            float v = 0.f;
+            if (k < K) v = src_is_kn ? __ldg(src + (long)k * ld + r) : __ldg(src + r * ld + k);
+            uint32_t hb;
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v));
+            const float hi = __uint_as_float(hb);
+            d[k] = hi;
+            d[Kp + k] = v - hi;
+        }
+    }
+}
+
+}  // namespace tgp
+
+using namespace tgp;
+
+typedef CUresult (*tgp_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static tgp_encode_fn get_encode() {
+    static tgp_encode_fn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<tgp_encode_fn>(p);
+    }
+    return fn;
+}
+
+static int make_map(CUtensorMap* tm, const float* ptr, long rows, int Kp, int box_rows) {
+    tgp_encode_fn enc = get_encode();
+    if (!enc) return fail(TGP_EINVAL, "tgp_gemm: cuTensorMapEncodeTiled unavailable");
+    cuuint64_t gdim[2] = {(cuuint64_t)(2 * Kp), (cuuint64_t)rows};
+    cuuint64_t gstride[1] = {(cuuint64_t)(2 * Kp) * sizeof(float)};
+    cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), gdim, gstride, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(TGP_EINVAL, "tgp_gemm: cuTensorMapEncodeTiled failed");
+    return TGP_OK;
+}
+
+extern "C" int tgp_split_kpad(int K) { return (K + TC_BK - 1) / TC_BK * TC_BK; }
+
+extern "C" int tgp_split_tf32(const float* src, long rows, int K, long ld, int src_is_kn, float* dst,
+                              tgp_stream_t stream) {
+    if (!src || !dst) return fail(TGP_EINVAL, "tgp_split_tf32: null pointer");
+    if (rows <= 0 || K <= 0) return fail(TGP_EINVAL, "tgp_split_tf32: sizes must be positive");
+    if ((uintptr_t)dst % 16) return fail(TGP_EINVAL, "tgp_split_tf32: dst must be 16-byte aligned");
+    const int Kp = tgp_split_kpad(K);
+    const int threads = Kp >= 256 ? 256 : (Kp >= 128 ? 128 : 64);
+    long nb = rows < (long)TGP_NUM_SMS * 64 ? rows : (long)TGP_NUM_SMS * 64;
+    split_tf32_kernel<<<(unsigned)nb, threads, 0, as_stream(stream)>>>(src, rows, K, ld, src_is_kn, Kp, dst);
+    return check_launch("split_tf32_kernel");
+}
+
+template <int BN>
+static int launch_tc(const tgp_gemm_args* a, cudaStream_t st) {
+    const int Kp = tgp_split_kpad(a->K);
+    CUtensorMap tmA, tmB;
+    int rc = make_map(&tmA, a->A_split, a->M, Kp, TC_BM);
+    if (rc) return rc;
+    rc = make_map(&tmB, a->B_split, a->Ncols, Kp, BN);
+    if (rc) return rc;
+    GemmDev P;
+    P.a = *a;
+    const int num_m_tiles = (int)((a->M + TC_BM - 1) / TC_BM);
+    const int num_n_tiles = (a->Ncols + BN - 1) / BN;
+    const int num_tiles = num_m_tiles * num_n_tiles;
+    const size_t smem = (size_t)TC_STAGES * (TC_A_BYTES + BN * TC_BK * 4) + 1024 + 256 + 4 * 32 * 33 * sizeof(float);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr_set = true;
+    }
+    const int grid = num_tiles < TGP_NUM_SMS ? num_tiles : TGP_NUM_SMS;
+    static int dbg = -1;
+    if (dbg < 0) { const char* e = getenv("TGP_TC_DEBUG"); dbg = e ? atoi(e) : 0; }
+    gemm_tc_kernel<BN><<<grid, TC_THREADS, smem, st>>>(tmA, tmB, P, Kp, num_m_tiles, num_tiles, dbg);
+    return check_launch("gemm_tc_kernel");
+}
+
+// tensor-core path: both operands pre-split ([hi | lo], tgp_split_tf32)
+int tgp_gemm_tc(const tgp_gemm_args* a, cudaStream_t st) {
+    if ((uintptr_t)a->A_split % 16 || (uintptr_t)a->B_split % 16)
+        return fail(TGP_EINVAL, "tgp_gemm: split operands must be 16-byte aligned");
+    if (a->Ncols > 128) return launch_tc<256>(a, st);
+    if (a->Ncols > 64) return launch_tc<128>(a, st);
+    return launch_tc<64>(a, st);
+}

@@ -50,6 +50,19 @@ __device__ __forceinline__ void load_sd(const float* __restrict__ directions, in
     normalize3(x, y, z);
 }
 
+// result store: raw row-major and, optionally, the [tf32 | residual] operand of the next contraction
+__device__ __forceinline__ void store_out(float* __restrict__ out, float* __restrict__ out_split, int kp, long pt,
+                                          int C, int c, float v) {
+    out[pt * C + c] = v;
+    if (out_split) {
+        uint32_t hb;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v));
+        const float hi = __uint_as_float(hb);
+        out_split[pt * 2 * kp + c] = hi;
+        out_split[pt * 2 * kp + kp + c] = v - hi;
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // edge records: (dx,dy,dz, idx) per (b,n,j)
 template <typename IdxT>
@@ -78,7 +91,8 @@ constexpr int SURF_PTS = 32;
 template <typename IdxT, int S_T, bool ARG>
 __global__ void __launch_bounds__(SURF_THREADS)
 surface_conv_kernel(const float* __restrict__ xyz, const IdxT* __restrict__ idx, const float* __restrict__ directions,
-                    int N, int k, int S_rt, int C, float* __restrict__ out, uint8_t* __restrict__ arg) {
+                    int N, int k, int S_rt, int C, float* __restrict__ out, uint8_t* __restrict__ arg,
+                    float* __restrict__ out_split, int kp) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int S = S_T > 0 ? S_T : S_rt;
     const int SC = S * C;
@@ -132,7 +146,7 @@ surface_conv_kernel(const float* __restrict__ xyz, const IdxT* __restrict__ idx,
                     acc += m[s];
                     if (ARG) arg[pt * SC + s * C + c] = (uint8_t)a[s];
                 }
-                out[pt * C + c] = acc * inv_s;
+                store_out(out, out_split, kp, pt, C, c, acc * inv_s);
             } else {
                 float acc = 0.f;
                 for (int s = 0; s < S; ++s) {
@@ -147,7 +161,7 @@ surface_conv_kernel(const float* __restrict__ xyz, const IdxT* __restrict__ idx,
                     acc += m;
                     if (ARG) arg[pt * SC + s * C + c] = (uint8_t)a;
                 }
-                out[pt * C + c] = acc * inv_s;
+                store_out(out, out_split, kp, pt, C, c, acc * inv_s);
             }
         }
     }
@@ -159,7 +173,8 @@ template <bool ARG>
 __global__ void __launch_bounds__(1024)
 layer_conv_kernel(const float4* __restrict__ rec, const float* __restrict__ directions,
                   const float* __restrict__ centre, long ld_centre, const float* __restrict__ slab,
-                  long M, int N, int k, int S, int C, float* __restrict__ out, uint8_t* __restrict__ arg_slab) {
+                  long M, int N, int k, int S, int C, float* __restrict__ out, uint8_t* __restrict__ arg_slab,
+                  float* __restrict__ out_split, int kp) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int W = S * 4;                                   // slab row width in floats
     float* tab = reinterpret_cast<float*>(smem_raw);       // [N][W]
@@ -218,7 +233,8 @@ layer_conv_kernel(const float4* __restrict__ rec, const float* __restrict__ dire
         m += __shfl_down_sync(0xffffffffu, m, 16);
         m += __shfl_down_sync(0xffffffffu, m, 8);
         m += __shfl_down_sync(0xffffffffu, m, 4);
-        if (lane < 4) out[pt * C + cg * 4 + lane] = __ldg(centre + pt * ld_centre + cg * 4 + lane) + m * inv_s;
+        if (lane < 4)
+            store_out(out, out_split, kp, pt, C, cg * 4 + lane, __ldg(centre + pt * ld_centre + cg * 4 + lane) + m * inv_s);
     }
 }
 
@@ -242,37 +258,39 @@ extern "C" int tgp_edge_records(const float* xyz, const void* idx, int idx_bits,
 
 template <typename IdxT, int S_T>
 static int launch_surface(const float* xyz, const IdxT* idx, const float* directions, int B, int N, int k, int S, int C,
-                          float* out, uint8_t* arg, cudaStream_t st) {
+                          float* out, uint8_t* arg, float* out_split, cudaStream_t st) {
+    const int kp = (C + 31) / 32 * 32;
     const int SC = S * C;
     const size_t smem = sizeof(float) * (3 * SC + 4) + sizeof(float4) * (SURF_THREADS / 32) * k;
     if (smem > 227 * 1024) return fail(TGP_EINVAL, "tgp_surface_conv_fwd: S*C too large for shared memory");
     dim3 grid((N + SURF_PTS - 1) / SURF_PTS, B);
     if (arg) {
         cudaFuncSetAttribute(surface_conv_kernel<IdxT, S_T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        surface_conv_kernel<IdxT, S_T, true><<<grid, SURF_THREADS, smem, st>>>(xyz, idx, directions, N, k, S, C, out, arg);
+        surface_conv_kernel<IdxT, S_T, true><<<grid, SURF_THREADS, smem, st>>>(xyz, idx, directions, N, k, S, C, out, arg, out_split, kp);
     } else {
         cudaFuncSetAttribute(surface_conv_kernel<IdxT, S_T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        surface_conv_kernel<IdxT, S_T, false><<<grid, SURF_THREADS, smem, st>>>(xyz, idx, directions, N, k, S, C, out, arg);
+        surface_conv_kernel<IdxT, S_T, false><<<grid, SURF_THREADS, smem, st>>>(xyz, idx, directions, N, k, S, C, out, arg, out_split, kp);
     }
     return check_launch("surface_conv_kernel");
 }
 
 extern "C" int tgp_surface_conv_fwd(const float* xyz, const void* idx, int idx_bits, const float* directions, int B,
-                                    int N, int k, int S, int C, float* out, uint8_t* arg, tgp_stream_t stream) {
+                                    int N, int k, int S, int C, float* out, uint8_t* arg, float* out_split,
+                                    tgp_stream_t stream) {
     if (!xyz || !idx || !directions || !out) return fail(TGP_EINVAL, "tgp_surface_conv_fwd: null pointer");
     if (B <= 0 || N <= 0 || k <= 0 || S <= 0 || C <= 0) return fail(TGP_EINVAL, "tgp_surface_conv_fwd: sizes must be positive");
     if (k > 255 || B > 65535) return fail(TGP_EINVAL, "tgp_surface_conv_fwd: k > 255 or B > 65535");
     cudaStream_t st = as_stream(stream);
     TGP_DISPATCH_IDX(idx_bits, {
-        if (S == 7) return launch_surface<IdxT, 7>(xyz, (const IdxT*)idx, directions, B, N, k, S, C, out, arg, st);
-        return launch_surface<IdxT, 0>(xyz, (const IdxT*)idx, directions, B, N, k, S, C, out, arg, st);
+        if (S == 7) return launch_surface<IdxT, 7>(xyz, (const IdxT*)idx, directions, B, N, k, S, C, out, arg, out_split, st);
+        return launch_surface<IdxT, 0>(xyz, (const IdxT*)idx, directions, B, N, k, S, C, out, arg, out_split, st);
     });
     return TGP_OK;
 }
 
 extern "C" int tgp_layer_conv_fwd(const float* edge_rec, const float* directions, const float* centre, long ld_centre,
                                   const float* support_slab, int B, int N, int k, int S, int C, float* out,
-                                  uint8_t* arg_slab, tgp_stream_t stream) {
+                                  uint8_t* arg_slab, float* out_split, tgp_stream_t stream) {
     if (!edge_rec || !directions || !centre || !support_slab || !out) return fail(TGP_EINVAL, "tgp_layer_conv_fwd: null pointer");
     if (B <= 0 || N <= 0 || k <= 0 || S <= 0 || C <= 0) return fail(TGP_EINVAL, "tgp_layer_conv_fwd: sizes must be positive");
     if (C % 4) return fail(TGP_EINVAL, "tgp_layer_conv_fwd: C must be a multiple of 4 (slab layout)");
@@ -288,14 +306,15 @@ extern "C" int tgp_layer_conv_fwd(const float* edge_rec, const float* directions
     dim3 grid(C / 4, B);
     cudaStream_t st = as_stream(stream);
     const long M = (long)B * N;
+    const int kp = (C + 31) / 32 * 32;
     if (arg_slab) {
         cudaFuncSetAttribute(layer_conv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         layer_conv_kernel<true><<<grid, threads, smem, st>>>(reinterpret_cast<const float4*>(edge_rec), directions, centre,
-                                                           ld_centre, support_slab, M, N, k, S, C, out, arg_slab);
+                                                           ld_centre, support_slab, M, N, k, S, C, out, arg_slab, out_split, kp);
     } else {
         cudaFuncSetAttribute(layer_conv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         layer_conv_kernel<false><<<grid, threads, smem, st>>>(reinterpret_cast<const float4*>(edge_rec), directions, centre,
-                                                            ld_centre, support_slab, M, N, k, S, C, out, arg_slab);
+                                                            ld_centre, support_slab, M, N, k, S, C, out, arg_slab, out_split, kp);
     }
     return check_launch("layer_conv_kernel");
 }

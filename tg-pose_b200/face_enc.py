@@ -88,13 +88,14 @@ class Face_Enc(nn.Module):
         i0 = self._next_idx(lambda: xyz_knn(vertices, k))
         i0_orl = self._next_idx(lambda: i0 if share else xyz_knn(vertices, k))
         # HSlayer_surface uses one xyz index for both RF-P and ORL; with injected indices they are the same tensor
-        fm_0 = self.conv_0(vertices, k, idx_xyz=i0, post=(None, None, True))
+        fm_0, fm_0s = self.conv_0(vertices, k, idx_xyz=i0, post=(None, None, True), want_split=True)
         i1 = self._next_idx(lambda: feat_knn(fm_0, k))
         i1_orl = self._next_idx(lambda: i0 if share else xyz_knn(vertices, k))
         if fold:
-            fm_1 = self.conv_1(vertices, fm_0, k, idx_feat=i1, idx_xyz=i1_orl, post=self._bn_post(self.bn1))
+            fm_1 = self.conv_1(vertices, fm_0, k, idx_feat=i1, idx_xyz=i1_orl, post=self._bn_post(self.bn1),
+                               fm_split=fm_0s)
         else:
-            fm_1 = self._bn_relu(self.bn1, self.conv_1(vertices, fm_0, k, idx_feat=i1, idx_xyz=i1_orl))
+            fm_1 = self._bn_relu(self.bn1, self.conv_1(vertices, fm_0, k, idx_feat=i1, idx_xyz=i1_orl, fm_split=fm_0s))
         ip1 = self._next_idx(lambda: i0[:, :, :4].contiguous() if share else xyz_knn(vertices, 4))
         v_pool_1, fm_pool_1 = self.pool_1(vertices, fm_1, idx_xyz=ip1)
 
@@ -103,13 +104,16 @@ class Face_Enc(nn.Module):
         i2 = self._next_idx(lambda: feat_knn(fm_pool_1, k1))
         i2_orl = self._next_idx(lambda: xyz_knn(v_pool_1, k1))
         if fold:
-            fm_2 = self.conv_2(v_pool_1, fm_pool_1, k1, idx_feat=i2, idx_xyz=i2_orl, post=self._bn_post(self.bn2))
+            fm_2, fm_2s = self.conv_2(v_pool_1, fm_pool_1, k1, idx_feat=i2, idx_xyz=i2_orl,
+                                      post=self._bn_post(self.bn2), want_split=True)
         else:
+            fm_2s = None
             fm_2 = self._bn_relu(self.bn2, self.conv_2(v_pool_1, fm_pool_1, k1, idx_feat=i2, idx_xyz=i2_orl))
         i3 = self._next_idx(lambda: feat_knn(fm_2, k1))
         i3_orl = self._next_idx(lambda: i2_orl if share else xyz_knn(v_pool_1, k1))
         if fold:
-            fm_3 = self.conv_3(v_pool_1, fm_2, k1, idx_feat=i3, idx_xyz=i3_orl, post=self._bn_post(self.bn3))
+            fm_3 = self.conv_3(v_pool_1, fm_2, k1, idx_feat=i3, idx_xyz=i3_orl, post=self._bn_post(self.bn3),
+                               fm_split=fm_2s)
         else:
             fm_3 = self._bn_relu(self.bn3, self.conv_3(v_pool_1, fm_2, k1, idx_feat=i3, idx_xyz=i3_orl))
         ip2 = self._next_idx(lambda: (i2_orl[:, :, :4].contiguous() if (share and k1 >= 4) else xyz_knn(v_pool_1, 4)))

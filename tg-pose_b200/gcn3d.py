@@ -83,11 +83,13 @@ class HSlayer_surface(nn.Module):
         stdv = 1. / math.sqrt(self.support_num * self.kernel_num)
         self.directions.data.uniform_(-stdv, stdv)
 
-    def forward(self, vertices: "(bs, vertice_num, 3)", neighbor_num: int, idx_xyz=None, post=None):
-        """-> (bs, vertice_num, kernel_num).  idx_xyz / post are extensions used by the fused encoder:
-        a precomputed int32 xyz kNN, and (scale, shift, relu) folded into the last epilogue."""
-        return HSSurfaceFn.apply(vertices, self.directions, self.STE_layer.weight, self.conv2.weight,
-                                 neighbor_num, self.support_num, self.kernel_num, idx_xyz, post)
+    def forward(self, vertices: "(bs, vertice_num, 3)", neighbor_num: int, idx_xyz=None, post=None, want_split=False):
+        """-> (bs, vertice_num, kernel_num).  idx_xyz / post / want_split are extensions used by the fused
+        encoder: a precomputed int32 xyz kNN, (scale, shift, relu) folded into the last epilogue, and the
+        result also returned as the next projection's tensor-core operand (-> (out, out_split))."""
+        out, out_split = HSSurfaceFn.apply(vertices, self.directions, self.STE_layer.weight, self.conv2.weight,
+                                           neighbor_num, self.support_num, self.kernel_num, idx_xyz, post, want_split)
+        return (out, out_split) if want_split else out
 
     def graph_conv(self, receptive_fields_norm, vertices, neighbor_num):
         """ref gcn3d.py:91-106 (kept for API parity; recomputes the xyz kNN like get_receptive_fields)."""
@@ -119,11 +121,13 @@ class HS_layer(nn.Module):
         self.directions.data.uniform_(-stdv, stdv)
 
     def forward(self, vertices: "(bs, vertice_num, 3)", feature_map: "(bs, vertice_num, in_channel)",
-                neighbor_num: int, idx_feat=None, idx_xyz=None, post=None):
-        """-> (bs, vertice_num, out_channel).  idx_feat / idx_xyz (int32) and post are fused-encoder extensions."""
-        return HSLayerFn.apply(vertices, feature_map, self.weights, self.bias, self.directions,
-                               self.STE_layer.weight, self.conv2.weight, neighbor_num, self.support_num,
-                               self.out_channel, idx_feat, idx_xyz, post)
+                neighbor_num: int, idx_feat=None, idx_xyz=None, post=None, fm_split=None, want_split=False):
+        """-> (bs, vertice_num, out_channel).  idx_feat / idx_xyz (int32), post, fm_split (feature_map already
+        split for the tensor cores) and want_split (-> (out, out_split)) are fused-encoder extensions."""
+        out, out_split = HSLayerFn.apply(vertices, feature_map, self.weights, self.bias, self.directions,
+                                         self.STE_layer.weight, self.conv2.weight, neighbor_num, self.support_num,
+                                         self.out_channel, idx_feat, idx_xyz, post, fm_split, want_split)
+        return (out, out_split) if want_split else out
 
 
 class Pool_layer(nn.Module):

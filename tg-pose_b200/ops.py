@@ -12,6 +12,9 @@ from . import _lib
 from ._lib import GemmArgs, OutSeg
 
 
+# large contractions go to the tcgen05 3xTF32 kernel; small / odd ones (K = 3, M = batch) to the fp32 FMA kernel
+TC_ENABLED = True
+
 # bench.py sets this to a dict to time every C-ABI call with CUDA events on the launching stream
 EVENT_LOG = None
 
@@ -149,21 +152,32 @@ def orl_global(f, idx, want_arg=False):
     k = idx.shape[2]
     g = torch.empty((B, C), dtype=torch.float32, device=f.device)
     arg = torch.empty((B, N, C), dtype=torch.uint8, device=f.device) if want_arg else None
-    _run("orl_global", _lib.load().tgp_orl_global, _p(f), _p(idx), bits, B, N, k, C, _p(g), _p(arg), _stream())
+    lib = _lib.load()
+    ws_bytes = lib.tgp_orl_workspace(B, N, C)
+    ws = torch.empty((ws_bytes + 3) // 4, dtype=torch.float32, device=f.device)
+    _run("orl_global", lib.tgp_orl_global, _p(f), _p(idx), bits, B, N, k, C, _p(g), _p(arg), _p(ws), ws_bytes, _stream())
     return (g, arg) if want_arg else g
 
 
 # --------------------------------------------------------------------------------------- graph convs
-def surface_conv(xyz, idx, directions, S, C, want_arg=False):
-    """HSlayer_surface.graph_conv, gcn3d.py:91-106 -> (B,N,C)."""
+def _split_buf(M, C, device):
+    kp = kpad(C)
+    return (torch.zeros if kp != C else torch.empty)((M, 2 * kp), dtype=torch.float32, device=device)
+
+
+def surface_conv(xyz, idx, directions, S, C, want_arg=False, want_split=False, full=False):
+    """HSlayer_surface.graph_conv, gcn3d.py:91-106 -> (B,N,C) [, arg][, split operand (B*N, 2*Kp)]."""
     xyz = _f32c(xyz, "surface_conv")
     directions = _f32c(directions, "surface_conv")
     idx, bits = _idx(idx, "surface_conv")
     B, N, k = idx.shape
     out = torch.empty((B, N, C), dtype=torch.float32, device=xyz.device)
     arg = torch.empty((B, N, S * C), dtype=torch.uint8, device=xyz.device) if want_arg else None
-    _run("surface_conv_fwd", _lib.load().tgp_surface_conv_fwd, _p(xyz), _p(idx), bits, _p(directions), B, N, k, S, C, _p(out),
-                                                _p(arg), _stream())
+    spl = _split_buf(B * N, C, xyz.device) if want_split else None
+    _run("surface_conv_fwd", _lib.load().tgp_surface_conv_fwd, _p(xyz), _p(idx), bits, _p(directions), B, N, k, S, C,
+         _p(out), _p(arg), _p(spl), _stream())
+    if full or want_split:
+        return out, arg, spl
     return (out, arg) if want_arg else out
 
 
@@ -176,7 +190,7 @@ def edge_records(xyz, idx):
     return rec
 
 
-def layer_conv(rec, directions, centre, support_slab, B, N, S, C, want_arg=False):
+def layer_conv(rec, directions, centre, support_slab, B, N, S, C, want_arg=False, want_split=False, full=False):
     """HS_layer.graph_conv after the projection, gcn3d.py:157-180 -> (B,N,C).
     centre: (B*N, C) view (any row stride); support_slab: [C/4][B*N][S*4]."""
     k = rec.shape[2]
@@ -184,25 +198,77 @@ def layer_conv(rec, directions, centre, support_slab, B, N, S, C, want_arg=False
     out = torch.empty((B, N, C), dtype=torch.float32, device=rec.device)
     arg = torch.empty((C // 4, B * N, S * 4), dtype=torch.uint8, device=rec.device) if want_arg else None
     assert centre.stride(-1) == 1
-    _run("layer_conv_fwd", _lib.load().tgp_layer_conv_fwd, _p(rec), _p(directions), _p(centre), centre.stride(0), _p(support_slab),
-                                              B, N, k, S, C, _p(out), _p(arg), _stream())
+    spl = _split_buf(B * N, C, rec.device) if want_split else None
+    _run("layer_conv_fwd", _lib.load().tgp_layer_conv_fwd, _p(rec), _p(directions), _p(centre), centre.stride(0),
+         _p(support_slab), B, N, k, S, C, _p(out), _p(arg), _p(spl), _stream())
+    if full or want_split:
+        return out, arg, spl
     return (out, arg) if want_arg else out
 
 
 # --------------------------------------------------------------------------------------- gemm
+def tc_eligible(M, K, Ncols):
+    return TC_ENABLED and M >= 256 and K >= 16 and Ncols >= 16
+
+
+def split_tf32(x2d, src_is_kn=False):
+    """[tf32(x) | x - tf32(x)] operand for the tensor-core GEMM: (rows, 2*Kp).  x2d: (rows,K) (row-strided
+    views allowed) or, with src_is_kn, (K, rows)."""
+    assert x2d.stride(-1) == 1
+    rows, K = (x2d.shape[1], x2d.shape[0]) if src_is_kn else (x2d.shape[0], x2d.shape[1])
+    lib = _lib.load()
+    Kp = lib.tgp_split_kpad(K)
+    dst = torch.empty((rows, 2 * Kp), dtype=torch.float32, device=x2d.device)
+    _run("split_tf32", lib.tgp_split_tf32, _p(x2d), rows, K, x2d.stride(0), 1 if src_is_kn else 0, _p(dst), _stream())
+    return dst
+
+
+_WSPLIT_CACHE = {}
+
+
+def split_weight(w2d, src_is_kn=False):
+    """split_tf32 of a parameter, cached per (storage, version): weights are constants in inference."""
+    key = (w2d.data_ptr(), w2d._version, tuple(w2d.shape), tuple(w2d.stride()), src_is_kn)
+    hit = _WSPLIT_CACHE.get(key)
+    if hit is None:
+        if len(_WSPLIT_CACHE) > 256:
+            _WSPLIT_CACHE.clear()
+        hit = split_tf32(w2d.detach(), src_is_kn)
+        _WSPLIT_CACHE[key] = hit
+    return hit
+
+
 def gemm(A, Bmat, b_is_nk, segs, bias=None, group_bias=None, rows_per_group=0, res1=None, res2=None,
-         scale=None, shift=None, relu=False, K=None, Ncols=None):
+         scale=None, shift=None, relu=False, K=None, Ncols=None, A_split=None, B_split=None, neg_slope=None, tc=None):
     """C = A @ B (+ epilogue) written to `segs` = [(col_begin, col_end, tensor, mode, slab_width)].
     A: (M,K) with unit column stride; Bmat: (K,Ncols) or, if b_is_nk, (Ncols,K); both may be row-strided views."""
-    assert A.stride(-1) == 1 and Bmat.stride(-1) == 1
-    M = A.shape[0]
+    assert Bmat.stride(-1) == 1
+    if A is None:
+        assert A_split is not None and K is not None, "gemm: A=None needs A_split and K"
+        M = A_split.shape[0]
+        tc = True
+    else:
+        assert A.stride(-1) == 1
+        M = A.shape[0]
     if K is None:
         K = A.shape[1]
     if Ncols is None:
         Ncols = Bmat.shape[0] if b_is_nk else Bmat.shape[1]
+    if tc is None:
+        tc = tc_eligible(M, K, Ncols)
+    if tc:
+        if A_split is None:
+            A_split = split_tf32(A[:, :K] if A.shape[1] != K else A)
+        if B_split is None:
+            B_split = split_weight(Bmat, src_is_kn=not b_is_nk)
+    else:
+        A_split = B_split = None
     a = GemmArgs()
-    a.A, a.lda = A.data_ptr(), A.stride(0)
+    if A is not None:
+        a.A, a.lda = A.data_ptr(), A.stride(0)
     a.Bmat, a.ldb, a.b_is_nk = Bmat.data_ptr(), Bmat.stride(0), 1 if b_is_nk else 0
+    if A_split is not None and B_split is not None:
+        a.A_split, a.B_split = A_split.data_ptr(), B_split.data_ptr()
     a.M, a.K, a.Ncols = M, K, Ncols
     a.bias = bias.data_ptr() if bias is not None else None
     a.group_bias = group_bias.data_ptr() if group_bias is not None else None
@@ -216,12 +282,35 @@ def gemm(A, Bmat, b_is_nk, segs, bias=None, group_bias=None, rows_per_group=0, r
     a.scale = scale.data_ptr() if scale is not None else None
     a.shift = shift.data_ptr() if shift is not None else None
     a.relu = 1 if relu else 0
+    a.neg_slope = neg_slope.data_ptr() if neg_slope is not None else None
     a.nseg = len(segs)
     for i, (c0, c1, t, mode, sw) in enumerate(segs):
-        a.seg[i] = OutSeg(c0, c1, mode, sw, t.stride(0) if mode == 0 else 0, t.data_ptr())
+        a.seg[i] = OutSeg(c0, c1, mode, sw, t.stride(0) if mode != 1 else 0, t.data_ptr())
+    name = "gemm_tc" if A_split is not None and B_split is not None else "gemm"
     if EVENT_LOG is not None:
-        EVENT_LOG.setdefault("__gemm_shapes__", []).append((M, K, Ncols))
-    _run("gemm", _lib.load().tgp_gemm, ctypes.byref(a), _stream())
+        EVENT_LOG.setdefault("__gemm_shapes__", []).append((name, M, K, Ncols))
+    _run(name, _lib.load().tgp_gemm, ctypes.byref(a), _stream())
+
+
+def kpad(K):
+    return _lib.load().tgp_split_kpad(K)
+
+
+def linear_fused(x2d, weight_nk, want_raw=True, want_split=False, x_split=None, w_split=None, **kw):
+    """x (M,K) @ weight (Ncols,K)^T with the fused epilogue; returns (raw (M,Ncols) or None, split (M,2*Kp) or None).
+    The split form is the next contraction's tensor-core operand, written by this one's epilogue."""
+    M, Ncols = x2d.shape[0], weight_nk.shape[0]
+    segs, raw, spl = [], None, None
+    if want_raw:
+        raw = torch.empty((M, Ncols), dtype=torch.float32, device=x2d.device)
+        segs.append((0, Ncols, raw, 0, 0))
+    if want_split:
+        kp = kpad(Ncols)
+        # padding columns of the operand must be zero: allocate zeroed only when there is padding
+        spl = (torch.zeros if kp != Ncols else torch.empty)((M, 2 * kp), dtype=torch.float32, device=x2d.device)
+        segs.append((0, Ncols, spl, 2, kp))
+    gemm(x2d, weight_nk, True, segs, A_split=x_split, B_split=w_split, **kw)
+    return raw, spl
 
 
 def linear_nk(x2d, weight_nk, **kw):

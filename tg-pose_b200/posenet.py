@@ -21,25 +21,50 @@ from .face_enc import Face_Enc
 FEAT_C = 1286  # 128 + 128 + 256 + 256 + 512 + obj_c(6), FLAGS.feat_c_R
 
 
+def _fold(conv, bn):
+    """(scale, shift) of conv-bias + eval BatchNorm as one per-channel affine applied to W.x."""
+    cout = conv.out_channels
+    dev = conv.weight.device
+    if bn is None:
+        scale = torch.ones(cout, device=dev)
+        shift = conv.bias.detach().clone() if conv.bias is not None else torch.zeros(cout, device=dev)
+        return scale, shift
+    scale = bn.weight.detach() * torch.rsqrt(bn.running_var + bn.eps)
+    shift = bn.bias.detach() - bn.running_mean * scale
+    if conv.bias is not None:
+        shift = shift + conv.bias.detach() * scale
+    return scale, shift
+
+
+class _Packed:
+    """weights of one fused 1x1-conv stage: (Ncols, K) matrix, its tensor-core split, affine and activation."""
+
+    def __init__(self, mats, folds, slopes, k_pad_to=None):
+        ws = []
+        for w in mats:
+            w = w.detach().reshape(w.shape[0], w.shape[1])
+            if k_pad_to is not None and w.shape[1] < k_pad_to:
+                w = torch.cat([w, w.new_zeros(w.shape[0], k_pad_to - w.shape[1])], 1)
+            ws.append(w)
+        self.w = torch.cat(ws, 0).contiguous()
+        self.scale = torch.cat([f[0] for f in folds]).contiguous()
+        self.shift = torch.cat([f[1] for f in folds]).contiguous()
+        self.slope = torch.cat([torch.full((m.shape[0],), float(sl), device=self.w.device)
+                                for m, sl in zip(mats, slopes)]).contiguous()
+        self.w_split = ops.split_tf32(self.w)
+
+
 def pointwise(x_cl, conv, bn=None, act=None, slope=0.2):
-    """1x1 Conv1d (+ eval BatchNorm + activation) on a channel-last (B,N,Cin) tensor -> (B,N,Cout),
-    one GEMM launch with the affine/ReLU folded into the epilogue.  LeakyReLU is applied afterwards."""
+    """1x1 Conv1d (+ eval BatchNorm + activation) on a channel-last (B,N,Cin) tensor -> (B,N,Cout): one GEMM
+    launch with the affine and the activation folded into the epilogue."""
     B, N, cin = x_cl.shape
-    w = conv.weight.reshape(conv.out_channels, cin)
-    scale = shift = None
-    if bn is not None:
-        scale = bn.weight * torch.rsqrt(bn.running_var + bn.eps)
-        shift = bn.bias - bn.running_mean * scale
-        if conv.bias is not None:
-            shift = shift + conv.bias * scale
-        bias = None
-    else:
-        bias = conv.bias
-    out = ops.linear_nk(x_cl.reshape(B * N, cin), w, bias=bias, scale=scale, shift=shift, relu=(act == "relu"))
-    out = out.view(B, N, conv.out_channels)
+    scale, shift = _fold(conv, bn)
+    ns = None
     if act == "leaky":
-        out = F.leaky_relu(out, slope, inplace=True)
-    return out
+        ns = torch.full((conv.out_channels,), slope, device=x_cl.device)
+    out = ops.linear_nk(x_cl.reshape(B * N, cin), conv.weight.reshape(conv.out_channels, cin), scale=scale,
+                        shift=shift, relu=(act == "relu"), neg_slope=ns)
+    return out.view(B, N, conv.out_channels)
 
 
 class Face_Dec(nn.Module):
@@ -207,7 +232,110 @@ class PoseNet9D(nn.Module):
         else:
             self.face_enc = FaceNet(**enc_kwargs)
 
+    # ---- inference: every per-point 1x1 convolution of the heads as fused tensor-core GEMMs ------------
+    def _head_packs(self):
+        """packed / BN-folded / tf32-split head weights, rebuilt only when a parameter or BN buffer changes."""
+        fa, g, r, t = self.face_all, self.rot_green, self.rot_red, self.ts
+        d, ph = fa.decoder, fa.ph_pred
+        mods = [g.conv1, g.bn1, g.conv2, g.bn2, r.conv1, r.bn1, r.conv2, r.bn2, t.conv1, t.bn1, t.conv2, t.bn2,
+                ph.conv_5[0], ph.conv_5[1], d.conv1d_block[0], d.conv1d_block[1], d.conv1d_block[3], d.conv1d_block[4],
+                d.conv1d_block[6], d.conv1d_block[7], d.recon_head[0], d.recon_head[1]]
+        key = tuple(x._version for m in mods for x in list(m.parameters()) + list(m.buffers())) + (
+            str(g.conv1.weight.device),)
+        if getattr(self, "_packs_key", None) != key:
+            kin = FEAT_C + 3
+            c = d.conv1d_block
+            self._packs = {
+                # [rot_green.conv1 | rot_red.conv1 | ph_pred.conv_5 | ts.conv1] on [feat | xyz] (K = 1289)
+                "stage1": _Packed([g.conv1.weight, r.conv1.weight, ph.conv_5[0].weight, t.conv1.weight],
+                                  [_fold(g.conv1, g.bn1), _fold(r.conv1, r.bn1), _fold(ph.conv_5[0], ph.conv_5[1]),
+                                   _fold(t.conv1, t.bn1)], [0.0, 0.0, 0.2, 0.0], k_pad_to=kin),
+                "green2": _Packed([g.conv2.weight], [_fold(g.conv2, g.bn2)], [0.0]),
+                "red2": _Packed([r.conv2.weight], [_fold(r.conv2, r.bn2)], [0.0]),
+                "ts2": _Packed([t.conv2.weight], [_fold(t.conv2, t.bn2)], [0.0]),
+                "dec1": _Packed([c[0].weight], [_fold(c[0], c[1])], [0.0], k_pad_to=kin),
+                "dec2": _Packed([c[3].weight], [_fold(c[3], c[4])], [0.0]),
+                "dec3": _Packed([c[6].weight], [_fold(c[6], c[7])], [0.0]),
+                "dec4": _Packed([d.recon_head[0].weight], [_fold(d.recon_head[0], d.recon_head[1])], [0.0]),
+            }
+            self._packs_key = key
+        return self._packs
+
+    @staticmethod
+    def _stage(pk, x_split, K, outs, M, **kw):
+        """one fused GEMM: column blocks of pk.w go to `outs` = [(n_cols, 'raw'|'split')]; returns the tensors."""
+        segs, res, c0 = [], [], 0
+        dev = x_split.device
+        for n, kind in outs:
+            if kind == "raw":
+                t_ = torch.empty((M, n), dtype=torch.float32, device=dev)
+                segs.append((c0, c0 + n, t_, 0, 0))
+            else:
+                t_ = ops._split_buf(M, n, dev)
+                segs.append((c0, c0 + n, t_, 2, ops.kpad(n)))
+            res.append(t_)
+            c0 += n
+        ops.gemm(None, pk.w, True, segs, scale=pk.scale, shift=pk.shift, neg_slope=pk.slope, K=K,
+                 A_split=x_split, B_split=pk.w_split, **kw)
+        return res
+
+    def _forward_fused_eval(self, points, obj_id, enable_proj=False):
+        mean = points.mean(dim=1, keepdim=True)
+        centred = points - mean
+        fa, g, r, t = self.face_all, self.rot_green, self.rot_red, self.ts
+        feat, feat_global = fa.encoder(centred, obj_id, enable_proj)
+        B, N, _ = feat.shape
+        M = B * N
+        pk = self._head_packs()
+        kin = FEAT_C + 3
+        x = torch.cat([feat, centred], dim=2).view(M, kin)        # [feat | xyz]: Pose_Ts input (PoseNet9D.py:63)
+        xs = ops.split_tf32(x)
+        # stage 1: four 1286/1289 -> 1024 convolutions as one contraction over the shared operand
+        hg, hr, f5, ht = self._stage(pk["stage1"], xs, kin, [(1024, "split"), (1024, "split"), (1024, "raw"),
+                                                              (1024, "split")], M)
+        # PH_Predictor tail (FaceRecon.py:145-165); per-cloud, tiny
+        ph = fa.ph_pred
+        pooled = f5.view(B, N, 1024).max(dim=1)[0]
+        feat_all = F.leaky_relu(ph.bn5(ph.linear1(torch.cat((pooled, pooled), 1))), negative_slope=0.2)
+        pi1 = ph.linear2(feat_all)
+        pi2 = ph.linear3(feat_all)
+        h1, h2 = ph.ac2(pi1), ph.ac3(pi2)
+        cvec = ph.linear4(pi1) + ph.linear5(pi2)                  # (B,1286): added to every point's feature
+        # Face_Dec on feat + cvec: W.(feat + c) = W.feat + W.c  -> per-cloud bias in the epilogue
+        dec = fa.decoder
+        w1 = dec.conv1d_block[0].weight.reshape(512, FEAT_C)
+        gb = ops.linear_nk(cvec.contiguous(), w1)
+        (d1,) = self._stage(pk["dec1"], xs, kin, [(512, "split")], M, group_bias=gb, rows_per_group=N)
+        (d2,) = self._stage(pk["dec2"], d1, 512, [(512, "split")], M)
+        (d3,) = self._stage(pk["dec3"], d2, 512, [(256, "split")], M)
+        (d4,) = self._stage(pk["dec4"], d3, 256, [(128, "raw")], M)
+        last = dec.recon_head[3]
+        recon = ops.linear_nk(d4, last.weight.reshape(3, 128), bias=last.bias).view(B, N, 3)
+
+        def tail(head, hidden_split, pack):
+            (h,) = self._stage(pack, hidden_split, 1024, [(256, "raw")], M)
+            v = h.view(B, N, 256).max(dim=1)[0].unsqueeze(2)
+            v = F.relu(head.bn3(head.conv3(v)))
+            return head.conv4(head.drop1(v)).squeeze(2).contiguous()
+
+        green_R_vec = tail(g, hg, pk["green2"])
+        red_R_vec = tail(r, hr, pk["red2"])
+        ts_vec = tail(t, ht, pk["ts2"])
+        return self._assemble(green_R_vec, red_R_vec, ts_vec[:, 0:3], ts_vec[:, 3:6], mean, recon, h1, h2, feat,
+                              feat_global.max(2)[0])
+
+    def _assemble(self, green_R_vec, red_R_vec, T, s, mean, recon, h1, h2, feat, feat_global):
+        p_green_R = green_R_vec[:, 1:] / (torch.norm(green_R_vec[:, 1:], dim=1, keepdim=True) + 1e-6)
+        p_red_R = red_R_vec[:, 1:] / (torch.norm(red_R_vec[:, 1:], dim=1, keepdim=True) + 1e-6)
+        out = {'p_green_R': p_green_R, 'p_red_R': p_red_R, 'f_green_R': torch.sigmoid(green_R_vec[:, 0]),
+               'f_red_R': torch.sigmoid(red_R_vec[:, 0]), 'Pred_T': T + mean.squeeze(1), 'Pred_s': s}
+        if self.train_outputs:
+            out.update({'recon': recon + mean, 'h1': h1, 'h2': h2, 'feat': feat, 'feat_global': feat_global})
+        return out
+
     def forward(self, points, obj_id, enable_proj=False):
+        if not self.training and not self.only_encoder and points.is_cuda:
+            return self._forward_fused_eval(points, obj_id, enable_proj)
         mean = points.mean(dim=1, keepdim=True)
         centred = points - mean
         if self.only_encoder:
