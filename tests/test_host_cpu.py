@@ -72,7 +72,7 @@ def test_pack_layer_column_order():
     w = torch.arange(cin * (S + 1) * C, dtype=torch.float32).reshape(cin, (S + 1) * C)
     b = torch.arange((S + 1) * C, dtype=torch.float32)
     ste = torch.arange(C * cin, dtype=torch.float32).reshape(C, cin, 1) + 1000
-    wcat, bcat = _pack_layer(w, b, ste, S, C)
+    wcat, bcat, _ = _pack_layer(w, b, ste, S, C)
     assert wcat.shape == (cin, (S + 2) * C) and bcat.shape == ((S + 2) * C,)
     assert torch.equal(wcat[:, :C], w[:, :C])
     for cg in range(C // 4):

@@ -11,28 +11,23 @@ import torch
 
 from . import ops
 
-_PACK_CACHE = {}
-
-
 def _pack_layer(weights, bias, ste_w, S, C):
-    """[centre | support in slab column order (cgroup, s, c4) | STE^T] as one (in, (S+2)*C) operand + bias.
-    Cached per parameter version (weights are constants in inference)."""
-    key = (weights.data_ptr(), weights._version, bias.data_ptr(), bias._version, ste_w.data_ptr(), ste_w._version)
-    hit = _PACK_CACHE.get(key)
-    if hit is not None:
-        return hit
-    cin = weights.shape[0]
-    with torch.no_grad():
-        w = weights.detach()
-        sup = w[:, C:].reshape(cin, S, C // 4, 4).permute(0, 2, 1, 3).reshape(cin, S * C)
-        wcat = torch.cat([w[:, :C], sup, ste_w.detach().reshape(C, cin).t()], dim=1).contiguous()
-        b = bias.detach()
-        bcat = torch.cat([b[:C], b[C:].reshape(S, C // 4, 4).permute(1, 0, 2).reshape(-1),
-                          torch.zeros(C, device=b.device, dtype=b.dtype)]).contiguous()
-    if len(_PACK_CACHE) > 64:
-        _PACK_CACHE.clear()
-    _PACK_CACHE[key] = (wcat, bcat)
-    return wcat, bcat
+    """[centre | support in slab column order (cgroup, s, c4) | STE^T] as one (in, (S+2)*C) operand, its bias and
+    its tensor-core split.  Cached per parameter object/version (weights are constants in inference)."""
+
+    def build():
+        cin = weights.shape[0]
+        with torch.no_grad():
+            w = weights.detach()
+            sup = w[:, C:].reshape(cin, S, C // 4, 4).permute(0, 2, 1, 3).reshape(cin, S * C)
+            wcat = torch.cat([w[:, :C], sup, ste_w.detach().reshape(C, cin).t()], dim=1).contiguous()
+            b = bias.detach()
+            bcat = torch.cat([b[:C], b[C:].reshape(S, C // 4, 4).permute(1, 0, 2).reshape(-1),
+                              torch.zeros(C, device=b.device, dtype=b.dtype)]).contiguous()
+            wsplit = ops.split_tf32(wcat, src_is_kn=True) if wcat.is_cuda else None
+        return wcat, bcat, wsplit
+
+    return ops.PARAM_CACHE.get((weights, bias, ste_w), ("pack_layer", S, C), build)
 
 
 def _orl_tail(feature, idx_xyz, conv2_w, f_ste, B, N, C, post, want_arg=False, feature_split=None,
@@ -54,8 +49,11 @@ def _orl_tail(feature, idx_xyz, conv2_w, f_ste, B, N, C, post, want_arg=False, f
     if want_split:   # the next layer's projection reads this result as a tensor-core operand
         out_split = ops._split_buf(M, C, feature.device)
         segs.append((0, C, out_split, 2, ops.kpad(C)))
+    w2a_split = None
+    if feature_split is not None:
+        w2a_split = ops.PARAM_CACHE.get((conv2_w,), "orl_w2a", lambda: ops.split_tf32(w2[:, :C].detach()))
     ops.gemm(f2, w2[:, :C], True, segs, group_bias=gb, rows_per_group=N,
-             res1=f2, res2=f_ste, scale=scale, shift=shift, relu=relu, A_split=feature_split)
+             res1=f2, res2=f_ste, scale=scale, shift=shift, relu=relu, A_split=feature_split, B_split=w2a_split)
     return out, g, arg, out_split
 
 
@@ -97,7 +95,7 @@ class HSLayerFn(torch.autograd.Function):
         B, N, cin = fm.shape
         M = B * N
         train = any(ctx.needs_input_grad)
-        wcat, bcat = _pack_layer(weights, bias, ste_w, S, C)
+        wcat, bcat, wcat_split = _pack_layer(weights, bias, ste_w, S, C)
         dev = fm.device
         centre = torch.empty((M, C), dtype=torch.float32, device=dev)
         slab = torch.empty((C // 4, M, S * 4), dtype=torch.float32, device=dev)
@@ -105,7 +103,8 @@ class HSLayerFn(torch.autograd.Function):
         tc = ops.tc_eligible(M, C, C)
         ops.gemm(fm.view(M, cin), wcat, False,
                  [(0, C, centre, 0, 0), (C, C + S * C, slab, 1, S * 4), (C + S * C, (S + 2) * C, f_ste, 0, 0)],
-                 bias=bcat, A_split=fm_split if (fm_split is not None and fm_split.numel()) else None)
+                 bias=bcat, A_split=fm_split if (fm_split is not None and fm_split.numel()) else None,
+                 B_split=wcat_split)
         if idx_feat is None:
             idx_feat = ops.knn_feat(fm, k, want64=False, want32=True)[1]
         rec = ops.edge_records(xyz, idx_feat)

@@ -134,6 +134,51 @@ gemm_simt_kernel(const __grid_constant__ GemmDev P) {
     }
 }
 
+// skinny contraction (M <= 64, e.g. one row per cloud: the ORL cloud-global term g @ W2b^T):
+// a warp owns one output column n (one K-contiguous weight row), lanes stride over K, 4 rows of A at a time.
+__global__ void __launch_bounds__(256)
+gemm_skinny_kernel(const __grid_constant__ GemmDev P) {
+    const tgp_gemm_args& g = P.a;
+    const int lane = threadIdx.x & 31;
+    const int n = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (n >= g.Ncols) return;
+    const float* w = g.Bmat + (long)n * g.ldb;
+    for (long m0 = 0; m0 < g.M; m0 += 4) {
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int k = lane; k < g.K; k += 32) {
+            const float wv = __ldg(w + k);
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+                if (m0 + r < g.M) acc[r] = fmaf(__ldg(g.A + (m0 + r) * g.lda + k), wv, acc[r]);
+        }
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const float v = warp_sum(acc[r]);
+            if (lane == 0 && m0 + r < g.M) epilogue_store(g, m0 + r, n, v);
+        }
+    }
+}
+
+// tiny-K / tiny-N contraction (K = 3: STE of the surface layer, gcn3d.py:70,84; N = 3: recon head): one thread
+// per output element.
+template <bool B_NK>
+__global__ void gemm_naive_kernel(const __grid_constant__ GemmDev P, long total) {
+    const tgp_gemm_args& g = P.a;
+    const long e = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= total) return;
+    const long m = e / g.Ncols;
+    const int n = (int)(e - m * g.Ncols);
+    const float* a = g.A + m * g.lda;
+    float acc = 0.f;
+    if (B_NK) {
+        const float* w = g.Bmat + (long)n * g.ldb;
+        for (int k = 0; k < g.K; ++k) acc = fmaf(__ldg(a + k), __ldg(w + k), acc);
+    } else {
+        for (int k = 0; k < g.K; ++k) acc = fmaf(__ldg(a + k), __ldg(g.Bmat + (long)k * g.ldb + n), acc);
+    }
+    epilogue_store(g, m, n, acc);
+}
+
 }  // namespace tgp
 
 using namespace tgp;
@@ -160,6 +205,17 @@ int tgp_gemm_validate(const tgp_gemm_args* a) {
 int tgp_gemm_simt(const tgp_gemm_args* a, cudaStream_t st) {
     GemmDev P;
     P.a = *a;
+    if (a->M <= 64 && a->b_is_nk && a->K >= 32) {
+        gemm_skinny_kernel<<<(a->Ncols + 7) / 8, 256, 0, st>>>(P);
+        return check_launch("gemm_skinny_kernel");
+    }
+    if (a->K <= 8 || a->Ncols <= 8) {
+        const long total = a->M * a->Ncols;
+        const unsigned blocks = (unsigned)((total + 255) / 256);
+        if (a->b_is_nk) gemm_naive_kernel<true><<<blocks, 256, 0, st>>>(P, total);
+        else gemm_naive_kernel<false><<<blocks, 256, 0, st>>>(P, total);
+        return check_launch("gemm_naive_kernel");
+    }
     dim3 grid((unsigned)((a->M + GM_BM - 1) / GM_BM), (a->Ncols + GM_BN - 1) / GM_BN);
     if (a->b_is_nk) gemm_simt_kernel<true><<<grid, GM_THREADS, 0, st>>>(P);
     else gemm_simt_kernel<false><<<grid, GM_THREADS, 0, st>>>(P);

@@ -15,7 +15,8 @@
 //   warp 0    TMA producer   cp.async.bulk.tensor.2d (128B swizzle) -> 4-stage smem ring, mbarrier tx-count
 //   warp 1    MMA issuer     tcgen05.mma.cta_group::1.kind::tf32, M=128 x N=BN x K=8, fp32 accum in TMEM,
 //                            tcgen05.commit releases smem stages / publishes the accumulator
-//   warps 2-5 epilogue       tcgen05.ld 32x32b.x32 -> registers -> fused epilogue -> global
+//   warps 2-9 epilogue       tcgen05.ld 32x32b.x32 -> registers -> smem transpose -> fused epilogue -> coalesced global
+//                            (two warps per TMEM lane quarter, interleaved 32-column chunks)
 // Two TMEM accumulator stages (2 x BN columns) let the epilogue of tile t overlap the mainloop of t+1.
 #include "common.cuh"
 #include <cuda.h>
@@ -26,7 +27,8 @@ namespace tgp {
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 32;                 // 32 fp32 = one 128-byte swizzle span
 constexpr int TC_STAGES = 4;
-constexpr int TC_THREADS = 192;
+constexpr int TC_EPI_WARPS = 8;
+constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;   // TMA warp + MMA warp + epilogue warps
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 4;   // 16 KB
 
 struct GemmDev {
@@ -112,7 +114,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint64_t* tmem_full = empty + TC_STAGES;
     uint64_t* tmem_empty = tmem_full + 2;
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-    float* stage_all = reinterpret_cast<float*>(base + TC_STAGES * STAGE_BYTES + 256);   // [4 warps][32][33]
+    float* stage_all = reinterpret_cast<float*>(base + TC_STAGES * STAGE_BYTES + 256);   // [epi warps][32][33]
 
     const tgp_gemm_args& g = P.a;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -120,7 +122,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < TC_STAGES; ++s) { tc_mbar_init(full + s, 1); tc_mbar_init(empty + s, 1); }
-        for (int s = 0; s < 2; ++s) { tc_mbar_init(tmem_full + s, 1); tc_mbar_init(tmem_empty + s, 4); }
+        for (int s = 0; s < 2; ++s) { tc_mbar_init(tmem_full + s, 1); tc_mbar_init(tmem_empty + s, TC_EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {   // one full warp allocates all 512 TMEM columns (1 CTA per SM)
@@ -190,8 +192,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
         }
     } else {
-        // ===================== epilogue (warps 2..5 -> TMEM lane quarters 2,3,0,1) =====================
+        // ===================== epilogue (warps 2..9 -> TMEM lane quarters 2,3,0,1,2,3,0,1) =====================
         const int quarter = warp & 3;
+        const int half = (warp - 2) >> 2;            // which interleaved set of 32-column chunks
+        float* stg = stage_all + (warp - 2) * (32 * 33);
         int it = 0;
         for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
             const int acc = it & 1;
@@ -202,10 +206,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             // TMEM gives each thread one ROW (32 consecutive columns per load); a padded shared-memory
             // transpose turns that into lane = COLUMN so that every global access of the epilogue
             // (residual loads, output stores) is a full, coalesced 128-byte row segment.
-            float* stg = stage_all + (warp - 2) * (32 * 33);
             const long row0 = (long)m0 + quarter * 32;
+            const int nrows = (int)max((long)0, min((long)32, g.M - row0));
+            long grp0 = 0, grp_end = 0;
+            if (g.group_bias) { grp0 = row0 / g.rows_per_group; grp_end = (grp0 + 1) * g.rows_per_group; }
 #pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 32) {
+            for (int c0 = half * 32; c0 < BN; c0 += 64) {
                 uint32_t r[32];
                 const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + c0);
                 TMEM_LD_32x32(taddr, r);
@@ -221,49 +227,53 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     const float sc = g.scale ? __ldg(g.scale + col) : 1.f;
                     const float sh = g.scale ? __ldg(g.shift + col) : 0.f;
                     const float slope = g.neg_slope ? __ldg(g.neg_slope + col) : (g.relu ? 0.f : 1.f);
-                    float* cp[4];
+                    float* dp[4];
                     long rs[4];
                     int lo_off[4];
 #pragma unroll
                     for (int s = 0; s < 4; ++s) {
-                        cp[s] = nullptr; rs[s] = 0; lo_off[s] = 0;
+                        dp[s] = nullptr; rs[s] = 0; lo_off[s] = 0;
                         if (s < g.nseg && col >= g.seg[s].col_begin && col < g.seg[s].col_end) {
                             const int rel = col - g.seg[s].col_begin;
                             if (g.seg[s].mode == 1) {
                                 const int w = g.seg[s].slab_width;
                                 const int cg = rel / w, rr = rel - cg * w;
-                                cp[s] = g.seg[s].ptr + (long)cg * g.M * w + rr;
                                 rs[s] = w;
+                                dp[s] = g.seg[s].ptr + ((long)cg * g.M + row0) * w + rr;
                             } else {
-                                cp[s] = g.seg[s].ptr + rel;
                                 rs[s] = g.seg[s].ld;
+                                dp[s] = g.seg[s].ptr + row0 * rs[s] + rel;
                                 if (g.seg[s].mode == 2) lo_off[s] = g.seg[s].slab_width;
                             }
                         }
                     }
-                    const int nrows = (int)min((long)32, g.M - row0);
-                    const float* gbp = g.group_bias ? g.group_bias + col : nullptr;
-                    const float* r1p = g.res1 ? g.res1 + col : nullptr;
-                    const float* r2p = g.res2 ? g.res2 + col : nullptr;
+                    const float* gbp = g.group_bias ? g.group_bias + grp0 * g.Ncols + col : nullptr;
+                    float gbv = gbp ? __ldg(gbp) : 0.f;
+                    long gb_next = grp_end;
+                    const float* r1p = g.res1 ? g.res1 + row0 * g.ld_res1 + col : nullptr;
+                    const float* r2p = g.res2 ? g.res2 + row0 * g.ld_res2 + col : nullptr;
 #pragma unroll 4
                     for (int rr = 0; rr < nrows; ++rr) {
-                        const long row = row0 + rr;
                         float v = stg[rr * 33 + lane] + bias;
-                        if (gbp) v += __ldg(gbp + (row / g.rows_per_group) * g.Ncols);
-                        if (r1p) v += __ldg(r1p + row * g.ld_res1);
-                        if (r2p) v += __ldg(r2p + row * g.ld_res2);
+                        if (gbp) {
+                            if (row0 + rr >= gb_next) { gbp += g.Ncols; gbv = __ldg(gbp); gb_next += g.rows_per_group; }
+                            v += gbv;
+                        }
+                        if (r1p) { v += __ldg(r1p); r1p += g.ld_res1; }
+                        if (r2p) { v += __ldg(r2p); r2p += g.ld_res2; }
                         v = fmaf(v, sc, sh);
                         v = v > 0.f ? v : v * slope;
 #pragma unroll
                         for (int s = 0; s < 4; ++s) {
-                            if (cp[s]) {
+                            if (dp[s]) {
                                 if (lo_off[s]) {
                                     uint32_t hb;
                                     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v));
                                     const float hi = __uint_as_float(hb);
-                                    cp[s][row * rs[s]] = hi;
-                                    cp[s][row * rs[s] + lo_off[s]] = v - hi;
-                                } else cp[s][row * rs[s]] = v;
+                                    dp[s][0] = hi;
+                                    dp[s][lo_off[s]] = v - hi;
+                                } else dp[s][0] = v;
+                                dp[s] += rs[s];
                             }
                         }
                     }
@@ -364,7 +374,7 @@ static int launch_tc(const tgp_gemm_args* a, cudaStream_t st) {
     const int num_m_tiles = (int)((a->M + TC_BM - 1) / TC_BM);
     const int num_n_tiles = (a->Ncols + BN - 1) / BN;
     const int num_tiles = num_m_tiles * num_n_tiles;
-    const size_t smem = (size_t)TC_STAGES * (TC_A_BYTES + BN * TC_BK * 4) + 1024 + 256 + 4 * 32 * 33 * sizeof(float);
+    const size_t smem = (size_t)TC_STAGES * (TC_A_BYTES + BN * TC_BK * 4) + 1024 + 256 + TC_EPI_WARPS * 32 * 33 * sizeof(float);
     static bool attr_set = false;
     if (!attr_set) {
         cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -223,19 +223,29 @@ def split_tf32(x2d, src_is_kn=False):
     return dst
 
 
-_WSPLIT_CACHE = {}
+class ParamCache:
+    """Derived weight tensors (packed / tf32-split) cached per parameter OBJECT and version.
+    Keys use id() guarded by weak references: a data_ptr-only key goes stale when a freed parameter's
+    storage is reused by a new module."""
+
+    def __init__(self):
+        self._d = {}
+
+    def get(self, params, tag, build):
+        import weakref
+        key = (tag,) + tuple(id(p) for p in params)
+        ver = tuple((p._version, p.data_ptr()) for p in params)
+        ent = self._d.get(key)
+        if ent is not None and ent[0] == ver and all(r() is p for r, p in zip(ent[1], params)):
+            return ent[2]
+        if len(self._d) > 512:
+            self._d = {k: v for k, v in self._d.items() if all(r() is not None for r in v[1])}
+        val = build()
+        self._d[key] = (ver, tuple(weakref.ref(p) for p in params), val)
+        return val
 
 
-def split_weight(w2d, src_is_kn=False):
-    """split_tf32 of a parameter, cached per (storage, version): weights are constants in inference."""
-    key = (w2d.data_ptr(), w2d._version, tuple(w2d.shape), tuple(w2d.stride()), src_is_kn)
-    hit = _WSPLIT_CACHE.get(key)
-    if hit is None:
-        if len(_WSPLIT_CACHE) > 256:
-            _WSPLIT_CACHE.clear()
-        hit = split_tf32(w2d.detach(), src_is_kn)
-        _WSPLIT_CACHE[key] = hit
-    return hit
+PARAM_CACHE = ParamCache()
 
 
 def gemm(A, Bmat, b_is_nk, segs, bias=None, group_bias=None, rows_per_group=0, res1=None, res2=None,
@@ -260,7 +270,7 @@ def gemm(A, Bmat, b_is_nk, segs, bias=None, group_bias=None, rows_per_group=0, r
         if A_split is None:
             A_split = split_tf32(A[:, :K] if A.shape[1] != K else A)
         if B_split is None:
-            B_split = split_weight(Bmat, src_is_kn=not b_is_nk)
+            B_split = split_tf32(Bmat.detach(), src_is_kn=not b_is_nk)   # callers with persistent weights pass a cached split
     else:
         A_split = B_split = None
     a = GemmArgs()

@@ -240,8 +240,7 @@ class PoseNet9D(nn.Module):
         mods = [g.conv1, g.bn1, g.conv2, g.bn2, r.conv1, r.bn1, r.conv2, r.bn2, t.conv1, t.bn1, t.conv2, t.bn2,
                 ph.conv_5[0], ph.conv_5[1], d.conv1d_block[0], d.conv1d_block[1], d.conv1d_block[3], d.conv1d_block[4],
                 d.conv1d_block[6], d.conv1d_block[7], d.recon_head[0], d.recon_head[1]]
-        key = tuple(x._version for m in mods for x in list(m.parameters()) + list(m.buffers())) + (
-            str(g.conv1.weight.device),)
+        key = tuple((x._version, x.data_ptr()) for m in mods for x in list(m.parameters()) + list(m.buffers()))
         if getattr(self, "_packs_key", None) != key:
             kin = FEAT_C + 3
             c = d.conv1d_block
