@@ -63,7 +63,7 @@ class HSSurfaceFn(torch.autograd.Function):
         xyz = xyz.contiguous().float()
         B, N, _ = xyz.shape
         M = B * N
-        train = any(ctx.needs_input_grad)
+        train = torch.is_grad_enabled() and any(ctx.needs_input_grad)
         f_ste = ops.linear_nk(xyz.view(M, 3), ste_w.reshape(C, 3))
         if idx_xyz is None:
             idx_xyz = ops.knn_xyz(xyz, k, want64=False, want32=True)[1]
@@ -94,7 +94,7 @@ class HSLayerFn(torch.autograd.Function):
         fm = fm.contiguous().float()
         B, N, cin = fm.shape
         M = B * N
-        train = any(ctx.needs_input_grad)
+        train = torch.is_grad_enabled() and any(ctx.needs_input_grad)
         wcat, bcat, wcat_split = _pack_layer(weights, bias, ste_w, S, C)
         dev = fm.device
         centre = torch.empty((M, C), dtype=torch.float32, device=dev)
@@ -134,7 +134,7 @@ class PoolFn(torch.autograd.Function):
     def forward(ctx, xyz, fm, sample_idx, k, idx_xyz):
         xyz = xyz.contiguous().float()
         fm = fm.contiguous().float()
-        train = any(ctx.needs_input_grad)
+        train = torch.is_grad_enabled() and any(ctx.needs_input_grad)
         if idx_xyz is None:
             idx_xyz = ops.knn_xyz(xyz, k, want64=False, want32=True)[1]
         rows = sample_idx.to(xyz.device, non_blocking=True)

@@ -135,27 +135,35 @@ gemm_simt_kernel(const __grid_constant__ GemmDev P) {
 }
 
 // skinny contraction (M <= 64, e.g. one row per cloud: the ORL cloud-global term g @ W2b^T):
-// a warp owns one output column n (one K-contiguous weight row), lanes stride over K, 4 rows of A at a time.
+// a warp owns one output column n (one K-contiguous weight row) and 4 rows of A; lanes stride over K with
+// 4 independent loads in flight per operand.
 __global__ void __launch_bounds__(256)
 gemm_skinny_kernel(const __grid_constant__ GemmDev P) {
     const tgp_gemm_args& g = P.a;
     const int lane = threadIdx.x & 31;
     const int n = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const long m0 = (long)blockIdx.y * 4;
     if (n >= g.Ncols) return;
     const float* w = g.Bmat + (long)n * g.ldb;
-    for (long m0 = 0; m0 < g.M; m0 += 4) {
-        float acc[4] = {0.f, 0.f, 0.f, 0.f};
-        for (int k = lane; k < g.K; k += 32) {
-            const float wv = __ldg(w + k);
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int k0 = 0; k0 < g.K; k0 += 128) {
+        float wv[4], av[4][4];
 #pragma unroll
-            for (int r = 0; r < 4; ++r)
-                if (m0 + r < g.M) acc[r] = fmaf(__ldg(g.A + (m0 + r) * g.lda + k), wv, acc[r]);
+        for (int u = 0; u < 4; ++u) {
+            const int k = k0 + u * 32 + lane;
+            wv[u] = k < g.K ? __ldg(w + k) : 0.f;
+#pragma unroll
+            for (int r = 0; r < 4; ++r) av[r][u] = (k < g.K && m0 + r < g.M) ? __ldg(g.A + (m0 + r) * g.lda + k) : 0.f;
         }
 #pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            const float v = warp_sum(acc[r]);
-            if (lane == 0 && m0 + r < g.M) epilogue_store(g, m0 + r, n, v);
-        }
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int r = 0; r < 4; ++r) acc[r] = fmaf(av[r][u], wv[u], acc[r]);
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const float v = warp_sum(acc[r]);
+        if (lane == 0 && m0 + r < g.M) epilogue_store(g, m0 + r, n, v);
     }
 }
 
@@ -206,7 +214,7 @@ int tgp_gemm_simt(const tgp_gemm_args* a, cudaStream_t st) {
     GemmDev P;
     P.a = *a;
     if (a->M <= 64 && a->b_is_nk && a->K >= 32) {
-        gemm_skinny_kernel<<<(a->Ncols + 7) / 8, 256, 0, st>>>(P);
+        gemm_skinny_kernel<<<dim3((a->Ncols + 7) / 8, (unsigned)((a->M + 3) / 4)), 256, 0, st>>>(P);
         return check_launch("gemm_skinny_kernel");
     }
     if (a->K <= 8 || a->Ncols <= 8) {

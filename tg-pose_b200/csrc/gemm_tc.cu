@@ -18,6 +18,9 @@
 //   warps 2-9 epilogue       tcgen05.ld 32x32b.x32 -> registers -> smem transpose -> fused epilogue -> coalesced global
 //                            (two warps per TMEM lane quarter, interleaved 32-column chunks)
 // Two TMEM accumulator stages (2 x BN columns) let the epilogue of tile t overlap the mainloop of t+1.
+// Tile order is n-fastest: the ~148 tiles in flight cover a band of a few m-tiles x all n-tiles, so each A tile
+// is fetched from HBM once and re-read from L2 by the CTAs working on its other column blocks (ncu, round 1:
+// m-fastest order streamed the A operand from DRAM once per column block -- 8.2 GB for the 4096-wide head GEMM).
 #include "common.cuh"
 #include <cuda.h>
 #include <stdlib.h>
@@ -103,7 +106,7 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
 template <int BN>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const __grid_constant__ GemmDev P, int Kp, int num_m_tiles, int num_tiles, int dbg) {
+               const __grid_constant__ GemmDev P, int Kp, int num_n_tiles, int num_tiles, int dbg) {
     extern __shared__ __align__(1024) unsigned char tc_smem[];
     constexpr int B_BYTES = BN * TC_BK * 4;
     constexpr int STAGE_BYTES = TC_A_BYTES + B_BYTES;
@@ -142,7 +145,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             int stage = 0;
             uint32_t phase = 0;
             for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-                const int m0 = (t % num_m_tiles) * TC_BM, n0 = (t / num_m_tiles) * BN;
+                const int m0 = (t / num_n_tiles) * TC_BM, n0 = (t % num_n_tiles) * BN;
                 for (int seg = 0; seg < 3; ++seg) {
                     // segment order: lo.hi, hi.lo, hi.hi
                     const int a_off = (seg == 0) ? Kp : 0, b_off = (seg == 1) ? Kp : 0;
@@ -200,7 +203,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
-            const int m0 = (t % num_m_tiles) * TC_BM, n0 = (t / num_m_tiles) * BN;
+            const int m0 = (t / num_n_tiles) * TC_BM, n0 = (t % num_n_tiles) * BN;
             tc_mbar_wait(tmem_full + acc, acc_phase);
             tc_fence_after();
             // TMEM gives each thread one ROW (32 consecutive columns per load); a padded shared-memory
@@ -383,7 +386,7 @@ static int launch_tc(const tgp_gemm_args* a, cudaStream_t st) {
     const int grid = num_tiles < TGP_NUM_SMS ? num_tiles : TGP_NUM_SMS;
     static int dbg = -1;
     if (dbg < 0) { const char* e = getenv("TGP_TC_DEBUG"); dbg = e ? atoi(e) : 0; }
-    gemm_tc_kernel<BN><<<grid, TC_THREADS, smem, st>>>(tmA, tmB, P, Kp, num_m_tiles, num_tiles, dbg);
+    gemm_tc_kernel<BN><<<grid, TC_THREADS, smem, st>>>(tmA, tmB, P, Kp, num_n_tiles, num_tiles, dbg);
     return check_launch("gemm_tc_kernel");
 }
 
@@ -391,7 +394,11 @@ static int launch_tc(const tgp_gemm_args* a, cudaStream_t st) {
 int tgp_gemm_tc(const tgp_gemm_args* a, cudaStream_t st) {
     if ((uintptr_t)a->A_split % 16 || (uintptr_t)a->B_split % 16)
         return fail(TGP_EINVAL, "tgp_gemm: split operands must be 16-byte aligned");
-    if (a->Ncols > 128) return launch_tc<256>(a, st);
-    if (a->Ncols > 64) return launch_tc<128>(a, st);
+    // widest column block that still gives every SM a tile (small problems: more, narrower tiles)
+    const long mt = (a->M + TC_BM - 1) / TC_BM;
+    int bn = a->Ncols > 128 ? 256 : (a->Ncols > 64 ? 128 : 64);
+    while (bn > 64 && mt * ((a->Ncols + bn - 1) / bn) < TGP_NUM_SMS) bn >>= 1;
+    if (bn == 256) return launch_tc<256>(a, st);
+    if (bn == 128) return launch_tc<128>(a, st);
     return launch_tc<64>(a, st);
 }

@@ -82,7 +82,7 @@ struct WarpTopList {
 //   q = (x0*x0 + x1*x1) + x2*x2 ; inner = fma(a2,b2, fma(a1,b1, a0*b0)) ; d = ((inner*-2)+q_j)+q_i
 // Candidates of one cloud are staged once per CTA as (x,y,z,q) float4 in shared memory; each
 // warp owns a query and scans 32 candidates per step (conflict-free LDS.128).
-constexpr int KNN_QPC = 64;        // queries per CTA
+constexpr int KNN_QPC = 32;        // queries per CTA (4 per warp): enough CTAs to fill 148 SMs at small batch
 constexpr int KNN_THREADS = 256;
 constexpr int KNN_TILE_MAX = 4096; // candidates resident in shared memory at a time
 
