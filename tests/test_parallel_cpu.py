@@ -1,0 +1,64 @@
+"""world_size-2 gloo tests of the host-side N>1 logic (no GPU): shard bounds, identical Pool permutation on
+every rank, gradient all-reduce."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from tgpose_b200 import parallel
+    lo, hi = parallel.shard_bounds(33, rank, world)
+    parallel.seed_for_forward(7)
+    perm = torch.randperm(1028)[:257]
+    lin = torch.nn.Linear(4, 3)
+    with torch.no_grad():
+        lin.weight.fill_(1.0)
+        lin.bias.fill_(0.0)
+    x = torch.full((2, 4), float(rank + 1))
+    lin(x).sum().backward()
+    nb = parallel.allreduce_gradients(lin.parameters(), world)
+    q.put((rank, lo, hi, perm[:8].tolist(), lin.weight.grad.clone(), lin.bias.grad.clone(), nb))
+    dist.destroy_process_group()
+
+
+def test_two_rank_sharding_and_grad_allreduce():
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in range(world)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (r0, lo0, hi0, perm0, gw0, gb0, nb0), (r1, lo1, hi1, perm1, gw1, gb1, nb1) = res
+    assert (lo0, hi0, lo1, hi1) == (0, 17, 17, 33)           # contiguous, disjoint, covering
+    assert perm0 == perm1                                     # same Pool permutation on every rank
+    # rank r: d/dW sum(lin(x)) = 2*(r+1) per entry; average over ranks = 3
+    assert torch.allclose(gw0, torch.full((3, 4), 3.0)) and torch.equal(gw0, gw1)
+    assert torch.allclose(gb0, torch.full((3,), 2.0)) and torch.equal(gb0, gb1)
+    assert nb0 == 1
+
+
+def test_shard_bounds_cover_everything():
+    from tgpose_b200.parallel import shard_bounds
+    for n in (1, 7, 32, 8192):
+        for w in (1, 2, 4, 8):
+            spans = [shard_bounds(n, r, w) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))

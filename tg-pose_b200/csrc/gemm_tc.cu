@@ -91,6 +91,70 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
     return d;
 }
 
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts_f32(uint32_t addr, float v) {
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+
+// one output destination of a column: pointer to (row0, col), row stride, and (split mode) the lo-half offset
+struct EpiDst {
+    float* p;
+    long rs;
+    int lo;
+};
+
+__device__ __forceinline__ void epi_store(EpiDst& d, float v) {
+    if (d.p) {
+        if (d.lo) {
+            uint32_t hb;
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v));
+            const float hi = __uint_as_float(hb);
+            d.p[0] = hi;
+            d.p[d.lo] = v - hi;
+        } else d.p[0] = v;
+        d.p += d.rs;
+    }
+}
+
+// rows of one 32-column chunk: lane = column.  Loads (shared-memory staging + residuals) for 8 rows are issued
+// before any of their stores so that the global loads overlap (ncu round 1: the row-at-a-time loop stalled on
+// long_scoreboard for every residual load).
+template <bool D1>
+__device__ __forceinline__ void epi_rows(uint32_t stg_addr, int lane, int nrows, float bias, float sc, float sh,
+                                         float slope, float gbv0, float gbv1, int gb_switch, const float* r1p,
+                                         long ld1, const float* r2p, long ld2, EpiDst d0, EpiDst d1) {
+#pragma unroll 1
+    for (int rr0 = 0; rr0 < nrows; rr0 += 8) {
+        float a[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) a[u] = lds_f32(stg_addr + (uint32_t)(((rr0 + u) * 33 + lane) * 4)) + bias;
+        if (r1p) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                if (rr0 + u < nrows) a[u] += __ldg(r1p + (long)(rr0 + u) * ld1);
+        }
+        if (r2p) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                if (rr0 + u < nrows) a[u] += __ldg(r2p + (long)(rr0 + u) * ld2);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            if (rr0 + u < nrows) {
+                float v = a[u] + ((rr0 + u) >= gb_switch ? gbv1 : gbv0);
+                v = fmaf(v, sc, sh);
+                v = v > 0.f ? v : v * slope;
+                epi_store(d0, v);
+                if (D1) epi_store(d1, v);
+            }
+        }
+    }
+}
+
 #define TMEM_LD_32x32(taddr, r)                                                                         \
     asm volatile(                                                                                       \
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                       \
@@ -211,8 +275,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             // (residual loads, output stores) is a full, coalesced 128-byte row segment.
             const long row0 = (long)m0 + quarter * 32;
             const int nrows = (int)max((long)0, min((long)32, g.M - row0));
-            long grp0 = 0, grp_end = 0;
-            if (g.group_bias) { grp0 = row0 / g.rows_per_group; grp_end = (grp0 + 1) * g.rows_per_group; }
+            // per-cloud bias: at most one group boundary inside these 32 rows when rows_per_group >= 32
+            long grp0 = 0;
+            int gb_switch = 64;
+            bool gb_slow = false;
+            if (g.group_bias) {
+                grp0 = row0 / g.rows_per_group;
+                const long nxt = (grp0 + 1) * g.rows_per_group - row0;
+                gb_switch = nxt < 64 ? (int)nxt : 64;
+                gb_slow = g.rows_per_group < 32;
+            }
+            const uint32_t stg_addr = s_u32(stg);
 #pragma unroll 1
             for (int c0 = half * 32; c0 < BN; c0 += 64) {
                 uint32_t r[32];
@@ -221,66 +294,59 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                 __syncwarp();
 #pragma unroll
-                for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = __uint_as_float(r[j]);
+                for (int j = 0; j < 32; ++j) sts_f32(stg_addr + (uint32_t)((lane * 33 + j) * 4), __uint_as_float(r[j]));
                 __syncwarp();
                 const int col = n0 + c0 + lane;
-                if (col < g.Ncols && !(dbg & 1)) {
-                    // per-column constants of this lane
-                    const float bias = g.bias ? __ldg(g.bias + col) : 0.f;
-                    const float sc = g.scale ? __ldg(g.scale + col) : 1.f;
-                    const float sh = g.scale ? __ldg(g.shift + col) : 0.f;
-                    const float slope = g.neg_slope ? __ldg(g.neg_slope + col) : (g.relu ? 0.f : 1.f);
-                    float* dp[4];
-                    long rs[4];
-                    int lo_off[4];
+                const bool live = col < g.Ncols && !(dbg & 1);
+                // per-column constants of this lane
+                float bias = 0.f, sc = 1.f, sh = 0.f, slope = g.relu ? 0.f : 1.f, gbv0 = 0.f, gbv1 = 0.f;
+                EpiDst d0 = {nullptr, 0, 0}, d1 = {nullptr, 0, 0};
+                const float* r1p = nullptr;
+                const float* r2p = nullptr;
+                if (live) {
+                    if (g.bias) bias = __ldg(g.bias + col);
+                    if (g.scale) { sc = __ldg(g.scale + col); sh = __ldg(g.shift + col); }
+                    if (g.neg_slope) slope = __ldg(g.neg_slope + col);
 #pragma unroll
                     for (int s = 0; s < 4; ++s) {
-                        dp[s] = nullptr; rs[s] = 0; lo_off[s] = 0;
                         if (s < g.nseg && col >= g.seg[s].col_begin && col < g.seg[s].col_end) {
                             const int rel = col - g.seg[s].col_begin;
+                            EpiDst d;
                             if (g.seg[s].mode == 1) {
                                 const int w = g.seg[s].slab_width;
                                 const int cg = rel / w, rr = rel - cg * w;
-                                rs[s] = w;
-                                dp[s] = g.seg[s].ptr + ((long)cg * g.M + row0) * w + rr;
+                                d.rs = w; d.lo = 0;
+                                d.p = g.seg[s].ptr + ((long)cg * g.M + row0) * w + rr;
                             } else {
-                                rs[s] = g.seg[s].ld;
-                                dp[s] = g.seg[s].ptr + row0 * rs[s] + rel;
-                                if (g.seg[s].mode == 2) lo_off[s] = g.seg[s].slab_width;
+                                d.rs = g.seg[s].ld;
+                                d.p = g.seg[s].ptr + row0 * d.rs + rel;
+                                d.lo = g.seg[s].mode == 2 ? g.seg[s].slab_width : 0;
                             }
+                            if (!d0.p) d0 = d; else d1 = d;     // at most two destinations per column (raw + split)
                         }
                     }
-                    const float* gbp = g.group_bias ? g.group_bias + grp0 * g.Ncols + col : nullptr;
-                    float gbv = gbp ? __ldg(gbp) : 0.f;
-                    long gb_next = grp_end;
-                    const float* r1p = g.res1 ? g.res1 + row0 * g.ld_res1 + col : nullptr;
-                    const float* r2p = g.res2 ? g.res2 + row0 * g.ld_res2 + col : nullptr;
-#pragma unroll 4
-                    for (int rr = 0; rr < nrows; ++rr) {
-                        float v = stg[rr * 33 + lane] + bias;
-                        if (gbp) {
-                            if (row0 + rr >= gb_next) { gbp += g.Ncols; gbv = __ldg(gbp); gb_next += g.rows_per_group; }
-                            v += gbv;
-                        }
-                        if (r1p) { v += __ldg(r1p); r1p += g.ld_res1; }
-                        if (r2p) { v += __ldg(r2p); r2p += g.ld_res2; }
-                        v = fmaf(v, sc, sh);
-                        v = v > 0.f ? v : v * slope;
-#pragma unroll
-                        for (int s = 0; s < 4; ++s) {
-                            if (dp[s]) {
-                                if (lo_off[s]) {
-                                    uint32_t hb;
-                                    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v));
-                                    const float hi = __uint_as_float(hb);
-                                    dp[s][0] = hi;
-                                    dp[s][lo_off[s]] = v - hi;
-                                } else dp[s][0] = v;
-                                dp[s] += rs[s];
-                            }
-                        }
+                    if (g.group_bias && !gb_slow) {
+                        gbv0 = __ldg(g.group_bias + grp0 * g.Ncols + col);
+                        if (gb_switch < nrows) gbv1 = __ldg(g.group_bias + (grp0 + 1) * g.Ncols + col);
                     }
+                    if (g.res1) r1p = g.res1 + row0 * g.ld_res1 + col;
+                    if (g.res2) r2p = g.res2 + row0 * g.ld_res2 + col;
                 }
+                if (gb_slow) {
+                    // tiny groups (< 32 rows per cloud): fold the per-row group bias into the staged values first
+                    if (live)
+                        for (int rr = 0; rr < nrows; ++rr) {
+                            const uint32_t ad = stg_addr + (uint32_t)((rr * 33 + lane) * 4);
+                            sts_f32(ad, lds_f32(ad) + __ldg(g.group_bias + ((row0 + rr) / g.rows_per_group) * g.Ncols + col));
+                        }
+                }
+                const int nr = live ? nrows : 0;
+                if (__any_sync(0xffffffffu, d1.p != nullptr))
+                    epi_rows<true>(stg_addr, lane, nr, bias, sc, sh, slope, gbv0, gbv1, gb_switch, r1p, g.ld_res1, r2p,
+                                   g.ld_res2, d0, d1);
+                else
+                    epi_rows<false>(stg_addr, lane, nr, bias, sc, sh, slope, gbv0, gbv1, gb_switch, r1p, g.ld_res1, r2p,
+                                    g.ld_res2, d0, d1);
             }
             tc_fence_before();
             __syncwarp();
