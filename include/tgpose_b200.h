@@ -178,6 +178,66 @@ int tgp_chamfer_bwd(const float* xyz1, const float* xyz2, const float* graddist1
                     const int32_t* idx1, const int32_t* idx2, int B, int n, int m,
                     float* gradxyz1, float* gradxyz2, tgp_stream_t stream);
 
+/* ------------------------------------------------------------------ backward (SURVEY 8a', north_star item 5)
+ * The reference has no hand-written backward for gcn3d: torch autograd differentiates the graph built by
+ * gcn3d.py:78-112 (HSlayer_surface), :142-186 (HS_layer), :210-217 (ORL), :225-245 (Pool_layer) and
+ * FaceRecon.py:69-73 (nearest upsampling).  These entry points are what the torch.autograd.Function
+ * wrappers of the drop-in module call instead.  Indices carry no gradient and vertices never require one
+ * (trainer/RL_TDA.py:111).  Scatter-adds use fp32 atomics (as ATen's index backward does); reductions across
+ * clouds go through fixed-order partial sums in the caller-provided workspace. */
+
+/* backward of a fused epilogue activation: gz = grad * [y > 0 (if relu)] * scale[col] (scale may be NULL).
+ * grad, y, gz: (M, C) with row strides ld_*. */
+int tgp_act_bwd(const float* grad, long ld_grad, const float* y, long ld_y, const float* scale, int relu,
+                long M, int C, float* gz, long ld_gz, tgp_stream_t stream);
+
+/* per-group column sums: out[g, c] = sum of x[r, c] over the rows_per_group rows of group g (bias gradients,
+ * the per-cloud ORL bias gradient).  x (M, C) row stride ld, out (M / rows_per_group, C). */
+size_t tgp_colsum_workspace(long M, int C, long rows_per_group);
+int tgp_colsum(const float* x, long ld, long M, int C, long rows_per_group, float* out,
+               void* workspace, size_t workspace_bytes, tgp_stream_t stream);
+
+/* backward of tgp_gather_max / tgp_orl_global (torch.max over the gathered neighbours, gcn3d.py:215,239):
+ * dfeat[b, idx[b, rows[m], arg[b,m,c]], c] += scale * grad[b,m,c]; dfeat (B,N,C) is ACCUMULATED into.
+ * grad_is_per_cloud: grad is (B,C), broadcast over m (the mean over N of the ORL, scale = 1/N). */
+int tgp_gather_max_bwd(const float* grad, int grad_is_per_cloud, float scale, const void* idx, int idx_bits,
+                       const int64_t* rows, const uint8_t* arg, int B, int N, int M, int k, int C,
+                       float* dfeat, tgp_stream_t stream);
+
+/* backward of tgp_gather_rows (indexing_neighbor_new, gcn3d.py:38-46; the nearest upsampling FaceRecon.py:71-73):
+ * dtensor[b, index[b,m,j], :] += grad[b,m,j,:]; dtensor (B,N,C) is ACCUMULATED into. */
+int tgp_scatter_add_rows(const float* grad, const void* index, int idx_bits, int B, int N, int M, int k, int C,
+                         float* dtensor, tgp_stream_t stream);
+
+/* backward of tgp_layer_conv_fwd w.r.t. the support features and the support directions
+ * (the centre term's gradient is grad itself).  grad (B*N, C) row stride ld_grad;
+ * d_support: row-major (B*N, S*C) block with row stride ld_ds whose columns are in SLAB order (cgroup, s, c4),
+ *            i.e. the column order of the packed projection weight -- fully overwritten;
+ * d_directions (3, S*C): gradient of the raw `directions` parameter (through F.normalize(dim=0)) -- overwritten. */
+size_t tgp_layer_conv_bwd_workspace(int B, int S, int C);
+int tgp_layer_conv_bwd(const float* edge_rec, const float* directions, const float* support_slab,
+                       const uint8_t* arg_slab, const float* grad, long ld_grad, int B, int N, int k, int S, int C,
+                       float* d_support, long ld_ds, float* d_directions,
+                       void* workspace, size_t workspace_bytes, tgp_stream_t stream);
+
+/* backward of tgp_surface_conv_fwd: only `directions` receives a gradient. arg (B,N,S*C) from the forward. */
+size_t tgp_surface_conv_bwd_workspace(int B, int N, int S, int C);
+int tgp_surface_conv_bwd(const float* xyz, const void* idx, int idx_bits, const float* directions,
+                         const uint8_t* arg, const float* grad, long ld_grad, int B, int N, int k, int S, int C,
+                         float* d_directions, void* workspace, size_t workspace_bytes, tgp_stream_t stream);
+
+/* weight-gradient contraction out (K1,K2; row stride ldo) = A^T B with A (M,K1), B (M,K2) row-major
+ * (dW = x^T dY of `feature_map @ weights`, gcn3d.py:170, and of every 1x1 Conv1d on the path).
+ * tgp_gemm_tn: exact fp32 FMA path on the raw operands (small / odd shapes).
+ * tgp_gemm_tn_tc: tcgen05 3xTF32 path; operands are the TRANSPOSED splits from tgp_split_tf32(src_is_kn=1):
+ *                 At_split (K1, 2*Mp), Bt_split (K2, 2*Mp), Mp = tgp_split_kpad(M); split-K over M. */
+size_t tgp_gemm_tn_workspace(long M, int K1, int K2);
+int tgp_gemm_tn(const float* A, long lda, const float* Bm, long ldb, long M, int K1, int K2, float* out, long ldo,
+                void* workspace, size_t workspace_bytes, tgp_stream_t stream);
+size_t tgp_gemm_tn_tc_workspace(long M, int K1, int K2);
+int tgp_gemm_tn_tc(const float* At_split, const float* Bt_split, long M, int K1, int K2, float* out, long ldo,
+                   void* workspace, size_t workspace_bytes, tgp_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -391,3 +391,127 @@ def posenet_forward(p, points, cat_id, perm1, perm2, inject=None):
             "f_green_R": 1.0 / (1.0 + np.exp(-green[:, 0])), "f_red_R": 1.0 / (1.0 + np.exp(-red[:, 0])),
             "Pred_T": ts[:, 0:3] + mean[:, 0, :], "Pred_s": ts[:, 3:6], "h1": h1, "h2": h2, "feat": feat,
             "feat_global": feat.max(axis=1)}
+
+
+# ----------------------------------------------------------------------------- backward (SURVEY 8a')
+# What torch autograd computes through the reference graph (gcn3d.py:78-112, :142-186, :210-217, :225-245),
+# restated in closed form with float64 accumulation.  Pinned against the reference's own autograd by
+# tests/golden/backward.npz (make_golden.py: backward_cases).  Small cases only (pure numpy).
+def _unit_dirs(directions, S, C):
+    """F.normalize(directions, dim=0) -> (u (3,S*C) float64, norm (S*C,))."""
+    v = np.asarray(directions, np.float64)
+    nrm = np.maximum(np.sqrt((v * v).sum(0)), 1e-12)
+    return v / nrm, nrm
+
+
+def _normalize_bwd(directions, du):
+    """backward of F.normalize(dim=0): dv = (du - u (u.du)) / ||v||."""
+    u, nrm = _unit_dirs(directions, 0, 0)
+    return ((du - u * (u * du).sum(0)) / nrm).astype(np.float32)
+
+
+def _theta(xyz, idx, directions, S, C):
+    d = direction_norm(xyz, idx).astype(np.float64)                  # (B,N,k,3)
+    u, _ = _unit_dirs(directions, S, C)
+    th = np.maximum(d @ u, 0.0)                                      # (B,N,k,S*C)
+    return d, th
+
+
+def surface_conv_backward(xyz, idx, directions, S, C, G):
+    """d directions of gcn3d.py:91-106 for upstream G (B,N,C)."""
+    d, th = _theta(xyz, idx, directions, S, C)
+    B, N, k, _ = th.shape
+    th5 = th.reshape(B, N, k, S, C)
+    jstar = th5.argmax(2)                                            # (B,N,S,C)
+    a = np.asarray(G, np.float64)[:, :, None, :] / S                 # (B,N,1,C)
+    thmax = np.take_along_axis(th5, jstar[:, :, None], 2)[:, :, 0]   # (B,N,S,C)
+    dth = np.where(thmax > 0, a, 0.0)                                # (B,N,S,C)
+    dsel = np.take_along_axis(d[:, :, :, None, None, :], jstar[:, :, None, :, :, None], 2)[:, :, 0]  # (B,N,S,C,3)
+    du = (dth[..., None] * dsel).sum((0, 1)).reshape(S * C, 3).T     # (3, S*C)
+    return _normalize_bwd(directions, du)
+
+
+def layer_conv_backward(xyz, idx, directions, P, S, C, G):
+    """(dP (B,N,(S+1)C), d directions) of gcn3d.py:157-180 for upstream G (B,N,C)."""
+    idx = _i64(idx)
+    d, th = _theta(xyz, idx, directions, S, C)
+    B, N, k, _ = th.shape
+    P64 = np.asarray(P, np.float64)
+    sup = P64[..., C:]                                               # (B,N,S*C)
+    gathered = np.stack([sup[b][idx[b]] for b in range(B)])          # (B,N,k,S*C)
+    v5 = (th * gathered).reshape(B, N, k, S, C)
+    jstar = v5.argmax(2)
+    a = np.asarray(G, np.float64)[:, :, None, :] / S
+    th_s = np.take_along_axis(th.reshape(B, N, k, S, C), jstar[:, :, None], 2)[:, :, 0]
+    sup_s = np.take_along_axis(gathered.reshape(B, N, k, S, C), jstar[:, :, None], 2)[:, :, 0]
+    dP = np.zeros_like(P64)
+    dP[..., :C] = G
+    nb = np.take_along_axis(idx[:, :, :, None, None], jstar[:, :, None], 2)[:, :, 0]   # (B,N,S,C) neighbour row
+    contrib = a * th_s                                               # (B,N,S,C)
+    cols = C + (np.arange(S)[:, None] * C + np.arange(C)[None, :])   # (S,C)
+    for b in range(B):
+        np.add.at(dP[b], (nb[b].reshape(-1), np.broadcast_to(cols, (N, S, C)).reshape(-1)), contrib[b].reshape(-1))
+    dth = np.where(th_s > 0, a * sup_s, 0.0)
+    dsel = np.take_along_axis(d[:, :, :, None, None, :], jstar[:, :, None, :, :, None], 2)[:, :, 0]
+    du = (dth[..., None] * dsel).sum((0, 1)).reshape(S * C, 3).T
+    return dP.astype(np.float32), _normalize_bwd(directions, du)
+
+
+def gather_max_backward(f, idx, G, rows=None):
+    """df of max_j f[b, idx[b, rows[m], j], c] for upstream G (B,M,C)."""
+    f, idx = np.asarray(f, np.float64), _i64(idx)
+    B, N, C = f.shape
+    r = np.arange(N) if rows is None else _i64(rows)
+    df = np.zeros_like(f)
+    for b in range(B):
+        gath = f[b][idx[b][r]]                                       # (M,k,C)
+        j = gath.argmax(1)                                           # (M,C)
+        nb = np.take_along_axis(idx[b][r][:, :, None], j[:, None, :], 1)[:, 0]   # (M,C)
+        np.add.at(df[b], (nb.reshape(-1), np.broadcast_to(np.arange(C), nb.shape).reshape(-1)),
+                  np.asarray(G[b], np.float64).reshape(-1))
+    return df.astype(np.float32)
+
+
+def _orl_backward(f, idx_xyz, conv2_weight, gz):
+    """backward of conv2(cat[f, g.repeat]) + f with g = mean_n max_j f[idx_xyz] -> (d_f, d_conv2_weight)."""
+    B, N, C = f.shape
+    w2 = np.asarray(conv2_weight, np.float64).reshape(C, 2 * C)
+    g = orl_global(f, idx_xyz).astype(np.float64)
+    gz64 = np.asarray(gz, np.float64)
+    d_gb = gz64.sum(1)                                               # (B,C)
+    dW2a = np.einsum("bno,bni->oi", gz64, np.asarray(f, np.float64))
+    dW2b = d_gb.T @ g
+    dg = d_gb @ w2[:, C:]
+    d_f = gz64 @ w2[:, :C] + gz64
+    d_f += gather_max_backward(f, idx_xyz, np.broadcast_to((dg / N)[:, None, :], (B, N, C)))
+    return d_f.astype(np.float32), np.concatenate([dW2a, dW2b], 1).reshape(C, 2 * C, 1).astype(np.float32)
+
+
+def hs_surface_backward(p, xyz, k, idx, idx_orl, G):
+    """parameter gradients of HSlayer_surface.forward (gcn3d.py:78-89) for upstream G."""
+    C = p["STE_layer.weight"].shape[0]
+    S = p["directions"].shape[1] // C
+    f = surface_conv(xyz, idx, p["directions"], S, C)
+    d_f, d_conv2 = _orl_backward(f, idx_orl, p["conv2.weight"], G)
+    d_ste = np.einsum("bno,bni->oi", np.asarray(G, np.float64), np.asarray(xyz, np.float64))
+    return {"directions": surface_conv_backward(xyz, idx, p["directions"], S, C, d_f),
+            "STE_layer.weight": d_ste.reshape(C, 3, 1).astype(np.float32), "conv2.weight": d_conv2}
+
+
+def hs_layer_backward(p, xyz, fm, k, idx, idx_orl, G):
+    """(d_fm, parameter gradients) of HS_layer.forward (gcn3d.py:142-155) for upstream G."""
+    C = p["STE_layer.weight"].shape[0]
+    S = p["directions"].shape[1] // C
+    cin = fm.shape[-1]
+    P = gemm_bias(fm, p["weights"], p["bias"])
+    f = layer_conv(xyz, idx, p["directions"], P, S, C)
+    d_f, d_conv2 = _orl_backward(f, idx_orl, p["conv2.weight"], G)
+    dP, d_dir = layer_conv_backward(xyz, idx, p["directions"], P, S, C, d_f)
+    fm64, dP64, G64 = np.asarray(fm, np.float64), dP.astype(np.float64), np.asarray(G, np.float64)
+    wste = np.asarray(p["STE_layer.weight"], np.float64).reshape(C, cin)
+    d_fm = dP64 @ np.asarray(p["weights"], np.float64).T + G64 @ wste
+    grads = {"weights": np.einsum("bni,bno->io", fm64, dP64).astype(np.float32),
+             "bias": dP64.sum((0, 1)).astype(np.float32), "directions": d_dir,
+             "STE_layer.weight": np.einsum("bno,bni->oi", G64, fm64).reshape(C, cin, 1).astype(np.float32),
+             "conv2.weight": d_conv2}
+    return d_fm.astype(np.float32), grads

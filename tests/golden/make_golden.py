@@ -315,6 +315,112 @@ def posenet_case():
     save("posenet", **out)
 
 
+def _patched(knn_list):
+    """replay recorded index tensors into the reference (it resolves get_neighbor_index through module globals)."""
+    it = iter(knn_list)
+    return lambda v, k: next(it)
+
+
+def backward_cases():
+    """Gradients from the reference's own autograd (SURVEY 8a'): op level (surface / layer / pool) and the whole
+    Face_Enc in train mode (BatchNorm batch statistics) with the index tensors recorded for replay."""
+    g = torch.Generator().manual_seed(4242)
+    out = {}
+    k = 8
+    x = torch.rand(2, 128, 3, generator=g)
+    orig_knn, orig_nn = gcn3d.get_neighbor_index, gcn3d.get_nearest_index
+    idx_xyz = orig_knn(x, k)
+    out["x"], out["k"] = np_(x), np.int64(k)
+    out["idx_xyz"] = np_(idx_xyz).astype(np.int16)
+
+    # HSlayer_surface, kernel_num 16
+    torch.manual_seed(3)
+    surf = gcn3d.HSlayer_surface(kernel_num=16, support_num=7)
+    o = surf(x, k)
+    G = torch.randn(o.shape, generator=g)
+    (o * G).sum().backward()
+    out["s_G"], out["s_out"] = np_(G), np_(o)
+    for n, v in params_np(surf).items():
+        out["s_p_" + n] = v
+    for n, prm in surf.named_parameters():
+        out["s_g_" + n] = np_(prm.grad)
+
+    # HS_layer 16 -> 32 (feature-space neighbours), gradient also w.r.t. the input feature map
+    torch.manual_seed(4)
+    lay = gcn3d.HS_layer(16, 32, support_num=7)
+    fm = (torch.randn(2, 128, 16, generator=g) * 0.5).requires_grad_(True)
+    idx_f = orig_knn(fm.detach(), k)
+    gcn3d.get_neighbor_index = _patched([idx_f, idx_xyz])
+    try:
+        o = lay(x, fm, k)
+    finally:
+        gcn3d.get_neighbor_index = orig_knn
+    G = torch.randn(o.shape, generator=g)
+    (o * G).sum().backward()
+    out["l_fm"], out["l_idx"], out["l_G"], out["l_out"] = np_(fm), np_(idx_f).astype(np.int16), np_(G), np_(o)
+    out["l_dfm"] = np_(fm.grad)
+    for n, v in params_np(lay).items():
+        out["l_p_" + n] = v
+    for n, prm in lay.named_parameters():
+        out["l_g_" + n] = np_(prm.grad)
+
+    # Pool_layer
+    pool = gcn3d.Pool_layer(pooling_rate=4, neighbor_num=4)
+    f2 = torch.randn(2, 128, 24, generator=g).requires_grad_(True)
+    torch.manual_seed(7)
+    vp, fp = pool(x, f2)
+    torch.manual_seed(7)
+    out["p_perm"] = np_(torch.randperm(128)).astype(np.int16)
+    G = torch.randn(fp.shape, generator=g)
+    (fp * G).sum().backward()
+    out["p_f"], out["p_G"], out["p_df"] = np_(f2), np_(G), np_(f2.grad)
+    save("backward", **out)
+
+    # Face_Enc, train mode, B=2 N=128: parameter gradients of sum(feat * W) with recorded indices
+    torch.manual_seed(0)
+    enc = Face_Enc().train()
+    g = torch.Generator().manual_seed(1234)
+    B, N = 2, 128
+    pts = torch.rand(B, N, 3, generator=g)
+    cat_id = torch.randint(0, 6, (B, 1), generator=g).float()
+    pts = pts - pts.mean(dim=1, keepdim=True)
+    calls = []
+
+    def rec_knn(v, kk):
+        r = orig_knn(v, kk)
+        calls.append(np_(r).astype(np.int16))
+        return r
+
+    def rec_nn(t, s_):
+        r = orig_nn(t, s_)
+        calls.append(np_(r).astype(np.int16))
+        return r
+
+    gcn3d.get_neighbor_index, gcn3d.get_nearest_index = rec_knn, rec_nn
+    try:
+        torch.manual_seed(7)
+        feat, _ = enc(pts, cat_id)
+    finally:
+        gcn3d.get_neighbor_index, gcn3d.get_nearest_index = orig_knn, orig_nn
+    assert len(calls) == 14
+    W = torch.randn(feat.shape, generator=g) * 0.1
+    (feat * W).sum().backward()
+    # W is regenerated by the test from the same generator state (seed 1234 -> rand pts, randint cat_id, randn W);
+    # large gradients are stored as a seeded sample of 4096 entries plus their float64 sum / abs-sum.
+    o2 = {"pts": np_(pts), "cat_id": np_(cat_id), "feat_sample": np_(feat).reshape(-1)[::97].copy()}
+    for i, c in enumerate(calls):
+        o2[f"idx_{i:02d}"] = c
+    rs = np.random.RandomState(5)
+    for n, prm in enc.named_parameters():
+        if prm.grad is not None and not n.startswith("proj_layer"):
+            gnp = np_(prm.grad).reshape(-1)
+            sel = np.sort(rs.choice(gnp.size, size=min(4096, gnp.size), replace=False))
+            o2["gsel_" + n] = sel.astype(np.int32)
+            o2["gval_" + n] = gnp[sel]
+            o2["gsum_" + n] = np.array([gnp.astype(np.float64).sum(), np.abs(gnp.astype(np.float64)).sum()])
+    save("face_enc_bwd", **o2)
+
+
 if __name__ == "__main__":
     knn_cases()
     gather_dir_cases()
@@ -322,3 +428,4 @@ if __name__ == "__main__":
     chamfer_cases()
     face_enc_case()
     posenet_case()
+    backward_cases()

@@ -171,3 +171,28 @@ def test_posenet_injected_indices():
     out = orc.posenet_forward(sd, g["pts"], g["cat_id"], perm1, perm2, inject=inject)
     for k in ("recon", "p_green_R", "p_red_R", "f_green_R", "f_red_R", "Pred_T", "Pred_s", "h1", "h2", "feat_global"):
         assert_close(out[k], g["out_" + k], rel=2e-4, floor=2e-6, what=k)
+
+
+# ----------------------------------------------------------------------------------------- backward oracle
+def _bparams(g, prefix):
+    return {k[len(prefix):]: g[k] for k in g.files if k.startswith(prefix)}
+
+
+def test_backward_oracle_vs_reference_autograd():
+    """oracle.hs_*_backward / gather_max_backward (SURVEY 8a' closed forms) against gradients produced by the
+    unmodified reference's autograd (make_golden.py: backward_cases)."""
+    from util import assert_grad_close
+    g = golden("backward")
+    x, k = g["x"], int(g["k"])
+    idx_xyz = g["idx_xyz"].astype(np.int64)
+    sg = orc.hs_surface_backward(_bparams(g, "s_p_"), x, k, idx_xyz, idx_xyz, g["s_G"])
+    for n, v in sg.items():
+        assert_grad_close(v, g["s_g_" + n], what=f"surface {n}")
+    dfm, lg = orc.hs_layer_backward(_bparams(g, "l_p_"), x, g["l_fm"], k, g["l_idx"].astype(np.int64), idx_xyz, g["l_G"])
+    assert_grad_close(dfm, g["l_dfm"], what="layer d_fm")
+    for n, v in lg.items():
+        assert_grad_close(v, g["l_g_" + n], what=f"layer {n}")
+    perm = g["p_perm"].astype(np.int64)
+    idx4 = orc.knn_xyz(x, 4)
+    df = orc.gather_max_backward(g["p_f"], idx4, g["p_G"], rows=perm[:32])
+    assert_grad_close(df, g["p_df"], what="pool d_f")

@@ -78,3 +78,20 @@ def knn_feat_mismatch(idx, ref_idx, ref_dist, D, q=None):
             if (np.abs(d_mine - d_ref) > bound).any():
                 viol += 1
     return rows_any, rows_set, viol
+
+
+def assert_grad_close(a, b, rel=REL_TOL, scale_floor=2e-5, what=""):
+    """Gradient comparator: |a-b| <= rel*max(|a|,|b|) + scale_floor*max|b|.  Gradients are long signed sums
+    (over B*N*S rows) whose small entries are cancellation residues of O(max|b|) terms, so the absolute floor is
+    tied to the tensor's scale instead of the fixed 1e-6 used for activations."""
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    assert a.shape == b.shape, f"{what}: shape {a.shape} vs {b.shape}"
+    assert np.isfinite(a).all(), f"{what}: non-finite gradient"
+    err = np.abs(a - b)
+    tol = rel * np.maximum(np.abs(a), np.abs(b)) + scale_floor * max(float(np.abs(b).max()), 1e-30)
+    bad = err > tol
+    if bad.any():
+        i = np.unravel_index(np.argmax(err - tol), a.shape)
+        raise AssertionError(f"{what}: {bad.sum()}/{bad.size} outside tolerance; worst at {i}: {a[i]} vs {b[i]} "
+                             f"(scale {np.abs(b).max():.3e})")

@@ -60,6 +60,25 @@ SIGNATURES = {
                                 c_void_p, c_void_p]),
     "tgp_chamfer_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                 c_void_p, c_void_p, c_void_p]),
+    "tgp_act_bwd": (c_int, [c_void_p, c_long, c_void_p, c_long, c_void_p, c_int, c_long, c_int, c_void_p, c_long,
+                            c_void_p]),
+    "tgp_colsum_workspace": (c_size_t, [c_long, c_int, c_long]),
+    "tgp_colsum": (c_int, [c_void_p, c_long, c_long, c_int, c_long, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "tgp_gather_max_bwd": (c_int, [c_void_p, c_int, ctypes.c_float, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int,
+                                   c_int, c_int, c_int, c_void_p, c_void_p]),
+    "tgp_scatter_add_rows": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "tgp_layer_conv_bwd_workspace": (c_size_t, [c_int, c_int, c_int]),
+    "tgp_layer_conv_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_long, c_int, c_int, c_int, c_int,
+                                   c_int, c_void_p, c_long, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "tgp_surface_conv_bwd_workspace": (c_size_t, [c_int, c_int, c_int, c_int]),
+    "tgp_surface_conv_bwd": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_long, c_int, c_int,
+                                     c_int, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "tgp_gemm_tn_workspace": (c_size_t, [c_long, c_int, c_int]),
+    "tgp_gemm_tn": (c_int, [c_void_p, c_long, c_void_p, c_long, c_long, c_int, c_int, c_void_p, c_long, c_void_p,
+                            c_size_t, c_void_p]),
+    "tgp_gemm_tn_tc_workspace": (c_size_t, [c_long, c_int, c_int]),
+    "tgp_gemm_tn_tc": (c_int, [c_void_p, c_void_p, c_long, c_int, c_int, c_void_p, c_long, c_void_p, c_size_t,
+                               c_void_p]),
 }
 
 _lib = None

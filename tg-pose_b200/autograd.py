@@ -63,7 +63,7 @@ class HSSurfaceFn(torch.autograd.Function):
         xyz = xyz.contiguous().float()
         B, N, _ = xyz.shape
         M = B * N
-        train = torch.is_grad_enabled() and any(ctx.needs_input_grad)
+        train = any(ctx.needs_input_grad)   # grad mode is off inside Function.forward
         f_ste = ops.linear_nk(xyz.view(M, 3), ste_w.reshape(C, 3))
         if idx_xyz is None:
             idx_xyz = ops.knn_xyz(xyz, k, want64=False, want32=True)[1]
@@ -73,7 +73,7 @@ class HSSurfaceFn(torch.autograd.Function):
         out, g, arg_orl, out_split = _orl_tail(feature, idx_xyz, conv2_w, f_ste, B, N, C, post, want_arg=train,
                                                feature_split=fsplit, want_split=want_split and tc)
         if train:
-            ctx.save_for_backward(xyz, directions, ste_w, conv2_w, idx_xyz, arg, feature, g, arg_orl)
+            ctx.save_for_backward(xyz, directions, ste_w, conv2_w, idx_xyz, arg, feature, g, arg_orl, out)
             ctx.cfg = (k, S, C, post)
         if out_split is None:
             out_split = out.new_empty(0)
@@ -94,7 +94,7 @@ class HSLayerFn(torch.autograd.Function):
         fm = fm.contiguous().float()
         B, N, cin = fm.shape
         M = B * N
-        train = torch.is_grad_enabled() and any(ctx.needs_input_grad)
+        train = any(ctx.needs_input_grad)   # grad mode is off inside Function.forward
         wcat, bcat, wcat_split = _pack_layer(weights, bias, ste_w, S, C)
         dev = fm.device
         centre = torch.empty((M, C), dtype=torch.float32, device=dev)
@@ -116,7 +116,7 @@ class HSLayerFn(torch.autograd.Function):
                                                feature_split=fsplit, want_split=want_split and tc)
         if train:
             ctx.save_for_backward(fm, weights, bias, directions, ste_w, conv2_w, rec, slab, arg, idx_xyz,
-                                  feature, g, arg_orl)
+                                  feature, g, arg_orl, out)
             ctx.cfg = (k, S, C, post)
         if out_split is None:
             out_split = out.new_empty(0)
@@ -134,7 +134,7 @@ class PoolFn(torch.autograd.Function):
     def forward(ctx, xyz, fm, sample_idx, k, idx_xyz):
         xyz = xyz.contiguous().float()
         fm = fm.contiguous().float()
-        train = torch.is_grad_enabled() and any(ctx.needs_input_grad)
+        train = any(ctx.needs_input_grad)   # grad mode is off inside Function.forward
         if idx_xyz is None:
             idx_xyz = ops.knn_xyz(xyz, k, want64=False, want32=True)[1]
         rows = sample_idx.to(xyz.device, non_blocking=True)
@@ -152,3 +152,20 @@ class PoolFn(torch.autograd.Function):
     def backward(ctx, g_v, g_pooled):
         from . import backward as bw
         return bw.pool_backward(ctx, g_pooled)
+
+
+class GatherRowsFn(torch.autograd.Function):
+    """indexing_neighbor_new (gcn3d.py:38-46) with its scatter-add backward (the nearest upsampling of
+    FaceRecon.py:71-73 in training)."""
+
+    @staticmethod
+    def forward(ctx, tensor, index):
+        ctx.save_for_backward(index)
+        ctx.n = tensor.shape[1]
+        ctx.tshape = tensor.shape
+        return ops.gather_rows(tensor, index)
+
+    @staticmethod
+    def backward(ctx, grad):
+        (index,) = ctx.saved_tensors
+        return ops.scatter_add_rows(grad, index, ctx.n).view(ctx.tshape), None

@@ -170,7 +170,8 @@ __device__ __forceinline__ void epi_rows(uint32_t stg_addr, int lane, int nrows,
 template <int BN>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const __grid_constant__ GemmDev P, int Kp, int num_n_tiles, int num_tiles, int dbg) {
+               const __grid_constant__ GemmDev P, int Kp, int num_n_tiles, int num_tiles, int dbg,
+               int tiles_mn, int kb_per, long zstride) {
     extern __shared__ __align__(1024) unsigned char tc_smem[];
     constexpr int B_BYTES = BN * TC_BK * 4;
     constexpr int STAGE_BYTES = TC_A_BYTES + B_BYTES;
@@ -209,11 +210,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             int stage = 0;
             uint32_t phase = 0;
             for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-                const int m0 = (t / num_n_tiles) * TC_BM, n0 = (t % num_n_tiles) * BN;
+                const int z = t / tiles_mn, tt = t - z * tiles_mn;       // split-K slice z (weight-gradient shapes)
+                const int m0 = (tt / num_n_tiles) * TC_BM, n0 = (tt % num_n_tiles) * BN;
+                const int kb0 = z * kb_per, kb1 = min(kblocks, kb0 + kb_per);
                 for (int seg = 0; seg < 3; ++seg) {
                     // segment order: lo.hi, hi.lo, hi.hi
                     const int a_off = (seg == 0) ? Kp : 0, b_off = (seg == 1) ? Kp : 0;
-                    for (int kb = 0; kb < kblocks; ++kb) {
+                    for (int kb = kb0; kb < kb1; ++kb) {
                         tc_mbar_wait(empty + stage, phase ^ 1);
                         unsigned char* sa = base + stage * STAGE_BYTES;
                         if (dbg & 4) { tc_mbar_arrive(full + stage); }
@@ -241,7 +244,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * BN;
                 uint32_t accum = 0;
-                for (int kb = 0; kb < 3 * kblocks; ++kb) {
+                const int zz = t / tiles_mn;
+                const int nkb = 3 * (min(kblocks, zz * kb_per + kb_per) - zz * kb_per);
+                for (int kb = 0; kb < nkb; ++kb) {
                     tc_mbar_wait(full + stage, phase);
                     tc_fence_after();
                     const uint32_t sa = s_u32(base + stage * STAGE_BYTES);
@@ -267,7 +272,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
-            const int m0 = (t / num_n_tiles) * TC_BM, n0 = (t % num_n_tiles) * BN;
+            const int z = t / tiles_mn, tt = t - z * tiles_mn;
+            const int m0 = (tt / num_n_tiles) * TC_BM, n0 = (tt % num_n_tiles) * BN;
             tc_mbar_wait(tmem_full + acc, acc_phase);
             tc_fence_after();
             // TMEM gives each thread one ROW (32 consecutive columns per load); a padded shared-memory
@@ -319,7 +325,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                 d.p = g.seg[s].ptr + ((long)cg * g.M + row0) * w + rr;
                             } else {
                                 d.rs = g.seg[s].ld;
-                                d.p = g.seg[s].ptr + row0 * d.rs + rel;
+                                d.p = g.seg[s].ptr + z * zstride + row0 * d.rs + rel;
                                 d.lo = g.seg[s].mode == 2 ? g.seg[s].slab_width : 0;
                             }
                             if (!d0.p) d0 = d; else d1 = d;     // at most two destinations per column (raw + split)
@@ -380,6 +386,45 @@ __global__ void split_tf32_kernel(const float* __restrict__ src, long rows, int 
     }
 }
 
+// transposing split for large (K, rows) sources (activations as weight-gradient operands): 32x32 tiles through
+// shared memory, reads coalesced along rows, writes coalesced along K.
+__global__ void __launch_bounds__(256)
+split_tf32_transpose_kernel(const float* __restrict__ src, long rows, long K, long ld, long Kp, float* __restrict__ dst) {
+    __shared__ float tile[32][33];
+    const long k0 = (long)blockIdx.x * 32, r0 = (long)blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = ty; i < 32; i += 8) {
+        const long k = k0 + i, r = r0 + tx;
+        tile[i][tx] = (k < K && r < rows) ? __ldg(src + k * ld + r) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = ty; i < 32; i += 8) {
+        const long r = r0 + i, k = k0 + tx;
+        if (r < rows && k < Kp) {
+            const float v = tile[tx][i];
+            uint32_t hb;
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v));
+            const float hi = __uint_as_float(hb);
+            dst[r * 2 * Kp + k] = hi;
+            dst[r * 2 * Kp + Kp + k] = v - hi;
+        }
+    }
+}
+
+// out[r, c] = sum_z partial[z][r][c]  (fixed order: deterministic)
+__global__ void tc_splitk_reduce_kernel(const float* __restrict__ partial, int nsplit, long rows, int cols,
+                                        float* __restrict__ out, long ldo) {
+    const long total = rows * cols;
+    for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
+        float s = 0.f;
+        for (int sp = 0; sp < nsplit; ++sp) s += partial[(long)sp * total + e];
+        const long r = e / cols;
+        out[r * ldo + (e - r * cols)] = s;
+    }
+}
+
 }  // namespace tgp
 
 using namespace tgp;
@@ -402,7 +447,7 @@ static tgp_encode_fn get_encode() {
     return fn;
 }
 
-static int make_map(CUtensorMap* tm, const float* ptr, long rows, int Kp, int box_rows) {
+static int make_map(CUtensorMap* tm, const float* ptr, long rows, long Kp, int box_rows) {
     tgp_encode_fn enc = get_encode();
     if (!enc) return fail(TGP_EINVAL, "tgp_gemm: cuTensorMapEncodeTiled unavailable");
     cuuint64_t gdim[2] = {(cuuint64_t)(2 * Kp), (cuuint64_t)rows};
@@ -424,6 +469,12 @@ extern "C" int tgp_split_tf32(const float* src, long rows, int K, long ld, int s
     if (rows <= 0 || K <= 0) return fail(TGP_EINVAL, "tgp_split_tf32: sizes must be positive");
     if ((uintptr_t)dst % 16) return fail(TGP_EINVAL, "tgp_split_tf32: dst must be 16-byte aligned");
     const int Kp = tgp_split_kpad(K);
+    if (src_is_kn && (long)rows * K >= 4096) {
+        dim3 grid((unsigned)(Kp / 32), (unsigned)((rows + 31) / 32));
+        if (grid.y > 65535) return fail(TGP_EINVAL, "tgp_split_tf32: too many rows for the transposing split");
+        split_tf32_transpose_kernel<<<grid, 256, 0, as_stream(stream)>>>(src, rows, K, ld, Kp, dst);
+        return check_launch("split_tf32_transpose_kernel");
+    }
     const int threads = Kp >= 256 ? 256 : (Kp >= 128 ? 128 : 64);
     long nb = rows < (long)TGP_NUM_SMS * 64 ? rows : (long)TGP_NUM_SMS * 64;
     split_tf32_kernel<<<(unsigned)nb, threads, 0, as_stream(stream)>>>(src, rows, K, ld, src_is_kn, Kp, dst);
@@ -431,7 +482,7 @@ extern "C" int tgp_split_tf32(const float* src, long rows, int K, long ld, int s
 }
 
 template <int BN>
-static int launch_tc(const tgp_gemm_args* a, cudaStream_t st) {
+static int launch_tc(const tgp_gemm_args* a, cudaStream_t st, int ksplit = 1) {
     const int Kp = tgp_split_kpad(a->K);
     CUtensorMap tmA, tmB;
     int rc = make_map(&tmA, a->A_split, a->M, Kp, TC_BM);
@@ -442,7 +493,12 @@ static int launch_tc(const tgp_gemm_args* a, cudaStream_t st) {
     P.a = *a;
     const int num_m_tiles = (int)((a->M + TC_BM - 1) / TC_BM);
     const int num_n_tiles = (a->Ncols + BN - 1) / BN;
-    const int num_tiles = num_m_tiles * num_n_tiles;
+    const int tiles_mn = num_m_tiles * num_n_tiles;
+    const int kblocks = Kp / TC_BK;
+    const int kb_per = (kblocks + ksplit - 1) / ksplit;
+    ksplit = (kblocks + kb_per - 1) / kb_per;          // no empty slices
+    const int num_tiles = tiles_mn * ksplit;
+    const long zstride = ksplit > 1 ? a->M * (long)a->seg[0].ld : 0;
     const size_t smem = (size_t)TC_STAGES * (TC_A_BYTES + BN * TC_BK * 4) + 1024 + 256 + TC_EPI_WARPS * 32 * 33 * sizeof(float);
     static bool attr_set = false;
     if (!attr_set) {
@@ -452,7 +508,7 @@ static int launch_tc(const tgp_gemm_args* a, cudaStream_t st) {
     const int grid = num_tiles < TGP_NUM_SMS ? num_tiles : TGP_NUM_SMS;
     static int dbg = -1;
     if (dbg < 0) { const char* e = getenv("TGP_TC_DEBUG"); dbg = e ? atoi(e) : 0; }
-    gemm_tc_kernel<BN><<<grid, TC_THREADS, smem, st>>>(tmA, tmB, P, Kp, num_n_tiles, num_tiles, dbg);
+    gemm_tc_kernel<BN><<<grid, TC_THREADS, smem, st>>>(tmA, tmB, P, Kp, num_n_tiles, num_tiles, dbg, tiles_mn, kb_per, zstride);
     return check_launch("gemm_tc_kernel");
 }
 
@@ -467,4 +523,65 @@ int tgp_gemm_tc(const tgp_gemm_args* a, cudaStream_t st) {
     if (bn == 256) return launch_tc<256>(a, st);
     if (bn == 128) return launch_tc<128>(a, st);
     return launch_tc<64>(a, st);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// weight-gradient contraction out (K1,K2) = A^T B over M rows on the tensor cores: both operands arrive as
+// TRANSPOSED splits (tgp_split_tf32 with src_is_kn): At_split (K1, 2*Mp), Bt_split (K2, 2*Mp).  The long
+// contraction is cut into split-K slices (one TMEM accumulator each, partials in `workspace`) that a second
+// kernel adds in a fixed order.
+static int tn_plan(long M, int K1, int K2, int* bn_out) {
+    const long mt = (K1 + TC_BM - 1) / TC_BM;
+    int bn = K2 > 128 ? 256 : (K2 > 64 ? 128 : 64);
+    const long tiles = mt * ((K2 + bn - 1) / bn);
+    const int kblocks = tgp_split_kpad((int)M) / TC_BK;
+    long ks = (2L * TGP_NUM_SMS + tiles - 1) / tiles;
+    const long cap = kblocks / 16 > 0 ? kblocks / 16 : 1;     // at least 16 K blocks (x3 passes) per slice
+    if (ks > cap) ks = cap;
+    if (ks < 1) ks = 1;
+    if (ks > 512) ks = 512;
+    const int kb_per = (int)((kblocks + ks - 1) / ks);
+    ks = (kblocks + kb_per - 1) / kb_per;
+    *bn_out = bn;
+    return (int)ks;
+}
+
+extern "C" size_t tgp_gemm_tn_tc_workspace(long M, int K1, int K2) {
+    if (M <= 0 || K1 <= 0 || K2 <= 0) return 0;
+    int bn;
+    const int ks = tn_plan(M, K1, K2, &bn);
+    return (size_t)ks * K1 * K2 * sizeof(float);
+}
+
+extern "C" int tgp_gemm_tn_tc(const float* At_split, const float* Bt_split, long M, int K1, int K2, float* out,
+                              long ldo, void* workspace, size_t workspace_bytes, tgp_stream_t stream) {
+    if (!At_split || !Bt_split || !out || !workspace) return fail(TGP_EINVAL, "tgp_gemm_tn_tc: null pointer");
+    if (M <= 0 || M > 0x7fffffffL - 64 || K1 <= 0 || K2 <= 0) return fail(TGP_EINVAL, "tgp_gemm_tn_tc: bad sizes");
+    if ((uintptr_t)At_split % 16 || (uintptr_t)Bt_split % 16) return fail(TGP_EINVAL, "tgp_gemm_tn_tc: operands must be 16-byte aligned");
+    if (workspace_bytes < tgp_gemm_tn_tc_workspace(M, K1, K2)) return fail(TGP_ENOSPACE, "tgp_gemm_tn_tc: workspace too small");
+    int bn;
+    const int ks = tn_plan(M, K1, K2, &bn);
+    tgp_gemm_args a = {};
+    a.A_split = At_split;
+    a.B_split = Bt_split;
+    a.M = K1;
+    a.K = (int)M;
+    a.Ncols = K2;
+    a.nseg = 1;
+    a.seg[0].col_begin = 0;
+    a.seg[0].col_end = K2;
+    a.seg[0].mode = 0;
+    a.seg[0].ld = ks > 1 ? K2 : ldo;
+    a.seg[0].ptr = ks > 1 ? static_cast<float*>(workspace) : out;
+    cudaStream_t st = as_stream(stream);
+    int rc;
+    if (bn == 256) rc = launch_tc<256>(&a, st, ks);
+    else if (bn == 128) rc = launch_tc<128>(&a, st, ks);
+    else rc = launch_tc<64>(&a, st, ks);
+    if (rc || ks == 1) return rc;
+    const long total = (long)K1 * K2;
+    long nb = (total + 255) / 256;
+    if (nb > TGP_NUM_SMS * 8) nb = TGP_NUM_SMS * 8;
+    tc_splitk_reduce_kernel<<<(unsigned)nb, 256, 0, st>>>(static_cast<const float*>(workspace), ks, K1, K2, out, ldo);
+    return check_launch("tc_splitk_reduce_kernel");
 }

@@ -16,7 +16,7 @@ import torch
 import torch.nn as nn
 
 from . import ops
-from .autograd import HSLayerFn, HSSurfaceFn, PoolFn
+from .autograd import GatherRowsFn, HSLayerFn, HSSurfaceFn, PoolFn
 
 
 # ----------------------------------------------------------------------------- free functions
@@ -34,6 +34,8 @@ def get_nearest_index(target: "(bs, v1, 3)", source: "(bs, v2, 3)"):
 
 def indexing_neighbor_new(tensor: "(bs, vertice_num, dim)", index: "(bs, vertice_num, neighbor_num)"):
     """ref gcn3d.py:38-46 -> (bs, vertice_num, neighbor_num, dim)."""
+    if torch.is_grad_enabled() and tensor.requires_grad:
+        return GatherRowsFn.apply(tensor, index)
     return ops.gather_rows(tensor, index)
 
 

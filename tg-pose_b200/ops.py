@@ -343,3 +343,122 @@ def chamfer_backward(xyz1, xyz2, gd1, gd2, idx1, idx2, g1, g2):
     m = xyz2.shape[1]
     _run("chamfer_bwd", _lib.load().tgp_chamfer_bwd, _p(xyz1), _p(xyz2), _p(gd1), _p(gd2), _p(idx1), _p(idx2), B, n, m,
                                            _p(g1), _p(g2), _stream())
+
+
+# --------------------------------------------------------------------------------------- backward (SURVEY 8a')
+def _ws(nbytes, device):
+    return torch.empty((max(int(nbytes), 4) + 3) // 4, dtype=torch.float32, device=device)
+
+
+def act_bwd(grad2d, y2d=None, scale=None, relu=False, out=None):
+    """gz = grad * [y > 0] * scale: backward of a fused (affine, ReLU) epilogue.  2-D row-strided views allowed."""
+    M, C = grad2d.shape
+    assert grad2d.stride(1) == 1 and (y2d is None or y2d.stride(1) == 1)
+    if out is None:
+        out = torch.empty((M, C), dtype=torch.float32, device=grad2d.device)
+    assert out.stride(1) == 1
+    _run("act_bwd", _lib.load().tgp_act_bwd, _p(grad2d), grad2d.stride(0), _p(y2d), y2d.stride(0) if y2d is not None else 0,
+         _p(scale), 1 if relu else 0, M, C, _p(out), out.stride(0), _stream())
+    return out
+
+
+def colsum(x2d, rows_per_group=None):
+    """column sums per group of rows_per_group consecutive rows -> (M / rows_per_group, C)."""
+    M, C = x2d.shape
+    assert x2d.stride(1) == 1
+    rpg = M if rows_per_group is None else rows_per_group
+    lib = _lib.load()
+    nb = lib.tgp_colsum_workspace(M, C, rpg)
+    ws = _ws(nb, x2d.device)
+    out = torch.empty((M // rpg, C), dtype=torch.float32, device=x2d.device)
+    _run("colsum", lib.tgp_colsum, _p(x2d), x2d.stride(0), M, C, rpg, _p(out), _p(ws), nb, _stream())
+    return out
+
+
+def gather_max_bwd(grad, idx, arg, N, dfeat, rows=None, per_cloud=False, scale=1.0):
+    """dfeat[b, idx[b, rows[m], arg[b,m,c]], c] += scale * grad[b,m,c]   (grad (B,C) if per_cloud)."""
+    idx, bits = _idx(idx, "gather_max_bwd")
+    grad = _f32c(grad, "gather_max_bwd")
+    B, M, C = arg.shape
+    k = idx.shape[2]
+    if rows is not None:
+        rows = rows.to(device=grad.device, dtype=torch.int64).contiguous()
+    assert dfeat.is_contiguous() and dfeat.shape == (B, N, C)
+    _run("gather_max_bwd", _lib.load().tgp_gather_max_bwd, _p(grad), 1 if per_cloud else 0, float(scale), _p(idx), bits,
+         _p(rows), _p(arg), B, N, M, k, C, _p(dfeat), _stream())
+    return dfeat
+
+
+def scatter_add_rows(grad, index, N):
+    """backward of gather_rows: (B,M,k,C) scattered into a new zero (B,N,C)."""
+    grad = _f32c(grad, "scatter_add_rows")
+    index, bits = _idx(index, "scatter_add_rows")
+    B, M, k = index.shape
+    C = grad.numel() // (B * M * k)
+    out = torch.zeros((B, N, C), dtype=torch.float32, device=grad.device)
+    _run("scatter_add_rows", _lib.load().tgp_scatter_add_rows, _p(grad), _p(index), bits, B, N, M, k, C, _p(out), _stream())
+    return out
+
+
+def layer_conv_bwd(rec, directions, support_slab, arg_slab, grad2d, B, N, S, C, d_support):
+    """-> d_directions (3,S*C); d_support: a (B*N, S*C) row-strided view that is overwritten (slab column order)."""
+    k = rec.shape[2]
+    directions = _f32c(directions, "layer_conv_bwd")
+    lib = _lib.load()
+    nb = lib.tgp_layer_conv_bwd_workspace(B, S, C)
+    ws = _ws(nb, rec.device)
+    dd = torch.empty((3, S * C), dtype=torch.float32, device=rec.device)
+    assert grad2d.stride(1) == 1 and d_support.stride(1) == 1
+    _run("layer_conv_bwd", lib.tgp_layer_conv_bwd, _p(rec), _p(directions), _p(support_slab), _p(arg_slab), _p(grad2d),
+         grad2d.stride(0), B, N, k, S, C, _p(d_support), d_support.stride(0), _p(dd), _p(ws), nb, _stream())
+    return dd
+
+
+def surface_conv_bwd(xyz, idx, directions, arg, grad2d, S, C):
+    """-> d_directions (3,S*C)."""
+    xyz = _f32c(xyz, "surface_conv_bwd")
+    directions = _f32c(directions, "surface_conv_bwd")
+    idx, bits = _idx(idx, "surface_conv_bwd")
+    B, N, k = idx.shape
+    lib = _lib.load()
+    nb = lib.tgp_surface_conv_bwd_workspace(B, N, S, C)
+    ws = _ws(nb, xyz.device)
+    dd = torch.empty((3, S * C), dtype=torch.float32, device=xyz.device)
+    assert grad2d.stride(1) == 1
+    _run("surface_conv_bwd", lib.tgp_surface_conv_bwd, _p(xyz), _p(idx), bits, _p(directions), _p(arg), _p(grad2d),
+         grad2d.stride(0), B, N, k, S, C, _p(dd), _p(ws), nb, _stream())
+    return dd
+
+
+def gemm_tn(A2d, B2d, out=None, tc=None):
+    """A^T B: (M,K1),(M,K2) -> (K1,K2), the weight-gradient contraction.  Large shapes run on the tensor cores
+    (transposed tf32 splits + split-K), small / skinny ones on the exact fp32 FMA kernel."""
+    M, K1 = A2d.shape
+    K2 = B2d.shape[1]
+    assert B2d.shape[0] == M and A2d.stride(1) == 1 and B2d.stride(1) == 1
+    if out is None:
+        out = torch.empty((K1, K2), dtype=torch.float32, device=A2d.device)
+    assert out.stride(1) == 1
+    lib = _lib.load()
+    if tc is None:
+        tc = TC_ENABLED and M >= 512 and K1 >= 16 and K2 >= 16
+    if tc:
+        At = split_tf32(A2d, src_is_kn=True)
+        Bt = At if (B2d.data_ptr() == A2d.data_ptr() and B2d.shape == A2d.shape and B2d.stride() == A2d.stride()) \
+            else split_tf32(B2d, src_is_kn=True)
+        nb = lib.tgp_gemm_tn_tc_workspace(M, K1, K2)
+        ws = _ws(nb, A2d.device)
+        _run("gemm_tn_tc", lib.tgp_gemm_tn_tc, _p(At), _p(Bt), M, K1, K2, _p(out), out.stride(0), _p(ws), nb, _stream())
+    else:
+        nb = lib.tgp_gemm_tn_workspace(M, K1, K2)
+        ws = _ws(nb, A2d.device)
+        _run("gemm_tn", lib.tgp_gemm_tn, _p(A2d), A2d.stride(0), _p(B2d), B2d.stride(0), M, K1, K2, _p(out),
+             out.stride(0), _p(ws), nb, _stream())
+    return out
+
+
+def matmul_kn(x2d, w_kn, **kw):
+    """x (M,K) @ w (K,Ncols) -> new (M,Ncols) (w row-major, e.g. dY @ W for a Conv1d weight W (out,in))."""
+    out = torch.empty((x2d.shape[0], w_kn.shape[1]), dtype=torch.float32, device=x2d.device)
+    gemm(x2d, w_kn, False, [(0, w_kn.shape[1], out, 0, 0)], **kw)
+    return out
