@@ -267,6 +267,94 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------------------------------------ training step
+def run_train(args):
+    """BASELINE.json configs[2]: RL_TDA training step (fwd + bwd + chamfer/DCD loss + gradient all-reduce + optimizer)
+    at a GLOBAL batch of 256 x 1028 points, sharded over the ranks (strong scaling).  Secondary bench line."""
+    import torch
+    import torch.distributed as dist
+    from tgpose_b200 import _lib, ops
+    from tgpose_b200.posenet import PoseNet9D
+    from tgpose_b200.train_step import TrainStep, synthetic_targets
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.load()
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    gb = args.train_batch
+    B = gb // world
+    torch.manual_seed(0)
+    net = PoseNet9D(train_outputs=True).to(dev)
+    step = TrainStep(net)
+    sets = []
+    for s_ in range(2):
+        pts, cat = synth_inputs(B, 4321 + 17 * rank + s_)
+        sets.append((pts.pin_memory(), cat.pin_memory(), synthetic_targets(B, 99 + rank + s_, dev)))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        hp, hc, tgt = sets[i % 2]
+        step(hp.to(dev, non_blocking=True), hc.to(dev, non_blocking=True), tgt)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ops.EVENT_LOG = {} if rank == 0 else None
+    l0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    loss = None
+    for i in range(args.steps):
+        hp, hc, tgt = sets[i % 2]
+        loss = step(hp.to(dev, non_blocking=True), hc.to(dev, non_blocking=True), tgt)   # H2D inside the timed region
+        loss_host = float(loss)                                                           # D2H of the step's loss
+    e1.record()
+    barrier()
+    launches = _lib.launch_count() - l0
+    event_log, ops.EVENT_LOG = ops.EVENT_LOG, None
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t[0]) / args.steps
+    if rank == 0:
+        kern = {}
+        tot = 0.0
+        for name, evs in (event_log or {}).items():
+            if name.startswith("__"):
+                continue
+            v = sum(a.elapsed_time(b) for a, b in evs) / args.steps
+            kern[name] = round(v, 4)
+            tot += v
+        val = gb / (ms / 1e3)
+        line = {"metric": "RL_TDA train step clouds/sec @1028 pts", "value": val, "unit": UNIT, "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": "RL_TDA training step: PoseNet9D fwd+bwd, chamfer3D/DCD recon loss, gradient "
+                                       "all-reduce, clip, Adam; global batch 256 x 1028 points",
+                           "points": N_PTS, "global_batch": gb, "per_gpu_batch": B, "parallelism": f"dp{world}",
+                           "l2": "per-step working set (> 1 GB of activations) exceeds the 126 MB L2"},
+                "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": B * (N_PTS * 3 + 1) * 4, "d2h_bytes_per_step": 4},
+                "gpu_launches": int(launches), "allreduce_buckets": step.buckets, "loss": loss_host, "clocks": clocks,
+                "tgpose_kernel_ms_per_step": round(tot, 3), "kernels_ms_per_step": dict(sorted(kern.items()))}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def kernel_report(event_log, steps, B, peaks):
     """Per-kernel device time inside the timed steps (CUDA events around each C-ABI call on the launching
     stream) -> share of the step and roofline of the dominant kernel (algorithmic work: DESIGN.md / SURVEY 8d)."""
@@ -331,10 +419,15 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=PER_GPU_BATCH, help="clouds per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mode", default="infer", choices=["infer", "train"],
+                    help="infer: BASELINE.json configs[1] (the headline); train: configs[2], a secondary line")
+    ap.add_argument("--train-batch", type=int, default=256, help="global batch of the training step")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         run_reference(args)
+    elif args.mode == "train":
+        run_train(args)
     else:
         run_ours(args)
 

@@ -178,6 +178,13 @@ int tgp_chamfer_bwd(const float* xyz1, const float* xyz2, const float* graddist1
                     const int32_t* idx1, const int32_t* idx2, int B, int n, int m,
                     float* gradxyz1, float* gradxyz2, tgp_stream_t stream);
 
+/* calc_dcd, losses/TDA_loss_sym_recon.py:411-450 (non_reg=False), on the outputs of tgp_chamfer_fwd:
+ * loss (B) = mean_i(1 - exp(-alpha d1_i) w1_i) + 0.5 mean_j(1 - exp(-alpha d2_j) w2_j) with the bincount weights
+ * w = (count[idx]^n_lambda + 1e-6)^-1 * frac built in shared memory (replaces the reference's Python loop over
+ * the batch with torch.bincount).  coef1 (B,n) / coef2 (B,m), optional: d loss[b] / d dist (weights detached). */
+int tgp_dcd(const float* dist1, const float* dist2, const int32_t* idx1, const int32_t* idx2, int B, int n, int m,
+            float alpha, float n_lambda, float* loss, float* coef1, float* coef2, tgp_stream_t stream);
+
 /* ------------------------------------------------------------------ backward (SURVEY 8a', north_star item 5)
  * The reference has no hand-written backward for gcn3d: torch autograd differentiates the graph built by
  * gcn3d.py:78-112 (HSlayer_surface), :142-186 (HS_layer), :210-217 (ORL), :225-245 (Pool_layer) and

@@ -250,7 +250,7 @@ def test_face_enc_backward_golden():
         assert abs(np.abs(gnp.astype(np.float64)).sum() - ref_sum[1]) <= 1e-3 * ref_sum[1], n
         checked += 1
     print(f"Face_Enc backward: {checked} parameter tensors checked, worst out-of-tolerance fraction {worst:.2e}")
-    assert checked >= 30
+    assert checked == 29    # conv_0: 3, conv_1..4: 5 each, bn1..3: 2 each
 
 
 def test_full_size_backward_properties():
@@ -279,3 +279,54 @@ def test_full_size_backward_properties():
         s = a[n] + b[n]
         scale = float(full[n].abs().max())
         assert float((full[n] - s).abs().max()) <= 2e-3 * scale + 1e-7, (n, float((full[n] - s).abs().max()), scale)
+
+
+# ----------------------------------------------------------------------------------------- loss tail + training step
+@pytest.mark.parametrize("B,n,m", [(4, 1028, 1024), (2, 100, 200), (1, 7, 3)])
+def test_dcd_vs_oracle(B, n, m):
+    from tgpose_b200.dist_chamfer_3D import calc_dcd
+    g = torch.Generator().manual_seed(n + m)
+    a = (torch.rand(B, n, 3, generator=g) * 0.3).cuda().requires_grad_(True)
+    b = (torch.rand(B, m, 3, generator=g) * 0.3).cuda()
+    loss, d1, d2, i1, i2 = calc_dcd(a, b, alpha=70, n_lambda=0.3, return_raw=True)
+    ref = orc.calc_dcd(nump(d1), nump(d2), nump(i1), nump(i2), alpha=70.0, n_lambda=0.3)
+    assert_close(nump(loss), ref, what="calc_dcd")
+    # gradient: finite differences of the oracle loss are discontinuous in idx, so compare with torch autograd
+    # through the reference's own formula evaluated on our dist/idx (weights detached, TDA_loss_sym_recon.py:433)
+    loss.sum().backward()
+    d1r = d1.detach().clone().requires_grad_(True)
+    l1 = []
+    for bb in range(B):
+        c1 = torch.bincount(i1[bb].long(), minlength=m)
+        w1 = (c1[i1[bb].long()].float() ** 0.3 + 1e-6) ** (-1) * (m / n)
+        l1.append((-torch.exp(-d1r[bb] * 70) * w1 + 1.).mean())
+    torch.stack(l1).sum().backward()
+    # chain through chamfer backward on both sides: compare d loss / d dist1 via the saved coefficients instead
+    from tgpose_b200 import ops
+    _, c1, _ = ops.dcd(d1.detach(), d2.detach(), i1, i2, 70.0, 0.3)
+    assert_close(nump(c1), nump(d1r.grad), rel=1e-4, floor=1e-7, what="d dcd / d dist1")
+    assert torch.isfinite(a.grad).all()
+
+
+def test_train_step_runs_and_learns():
+    """the synthetic RL_TDA step (train_step.py): finite loss, every trainable parameter that is on the path gets a
+    finite gradient, and a few steps on one fixed batch reduce the loss."""
+    from tgpose_b200.posenet import PoseNet9D
+    from tgpose_b200.train_step import TrainStep, synthetic_targets
+    torch.manual_seed(0)
+    net = PoseNet9D(train_outputs=True).cuda()
+    step = TrainStep(net, lr=2e-4)
+    gen = torch.Generator().manual_seed(3)
+    pts = (torch.rand(4, 256, 3, generator=gen) - 0.5) * 0.3 + torch.tensor([0.1, -0.1, 1.0])
+    cat = torch.randint(0, 6, (4, 1), generator=gen).float()
+    tgt = synthetic_targets(4, 5, "cuda")
+    first = float(step(pts.cuda(), cat.cuda(), tgt))
+    for n, p in net.named_parameters():
+        if "proj_layer" in n:
+            continue
+        assert p.grad is not None and torch.isfinite(p.grad).all(), n
+    last = first
+    for _ in range(8):
+        last = float(step(pts.cuda(), cat.cuda(), tgt))
+    assert np.isfinite(first) and np.isfinite(last)
+    assert last < first, (first, last)

@@ -60,6 +60,8 @@ SIGNATURES = {
                                 c_void_p, c_void_p]),
     "tgp_chamfer_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                 c_void_p, c_void_p, c_void_p]),
+    "tgp_dcd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, ctypes.c_float, ctypes.c_float,
+                        c_void_p, c_void_p, c_void_p, c_void_p]),
     "tgp_act_bwd": (c_int, [c_void_p, c_long, c_void_p, c_long, c_void_p, c_int, c_long, c_int, c_void_p, c_long,
                             c_void_p]),
     "tgp_colsum_workspace": (c_size_t, [c_long, c_int, c_long]),

@@ -119,6 +119,54 @@ __global__ void chamfer_bwd_scatter_kernel(const float* __restrict__ xyz1, const
     }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// density-aware chamfer tail (calc_dcd, losses/TDA_loss_sym_recon.py:411-450, non_reg=False).
+// The reference loops over the batch in Python and calls torch.bincount per cloud (B host syncs);
+// here one CTA per cloud builds both histograms in shared memory, evaluates
+//   loss[b] = mean_i(1 - exp(-a d1_i) w1_i) + 0.5 mean_j(1 - exp(-a d2_j) w2_j),
+//   w1_i = (count1[idx1_i]^lambda + 1e-6)^-1 * (m/n),  w2_j = (count2[idx2_j]^lambda + 1e-6)^-1 * (n/m)
+// and the coefficients d loss / d dist (the weights are detached in the reference, :433,438).
+constexpr int DCD_THREADS = 256;
+__global__ void __launch_bounds__(DCD_THREADS)
+dcd_kernel(const float* __restrict__ dist1, const float* __restrict__ dist2, const int32_t* __restrict__ idx1,
+           const int32_t* __restrict__ idx2, int n, int m, float alpha, float lambda, float* __restrict__ loss,
+           float* __restrict__ coef1, float* __restrict__ coef2) {
+    extern __shared__ int hist[];            // [m] counts of idx1 values, then [n] counts of idx2 values
+    __shared__ float red[2][DCD_THREADS / 32];
+    int* c1 = hist;
+    int* c2 = hist + m;
+    const long b = blockIdx.x;
+    for (int i = threadIdx.x; i < n + m; i += DCD_THREADS) hist[i] = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += DCD_THREADS) atomicAdd(c1 + __ldg(idx1 + b * n + i), 1);
+    for (int j = threadIdx.x; j < m; j += DCD_THREADS) atomicAdd(c2 + __ldg(idx2 + b * m + j), 1);
+    __syncthreads();
+    const float frac_12 = (float)n / (float)m, frac_21 = (float)m / (float)n;
+    float s1 = 0.f, s2 = 0.f;
+    for (int i = threadIdx.x; i < n; i += DCD_THREADS) {
+        const float w = frac_21 / (powf((float)c1[__ldg(idx1 + b * n + i)], lambda) + 1e-6f);
+        const float e = expf(-__ldg(dist1 + b * n + i) * alpha);
+        s1 += 1.f - e * w;
+        if (coef1) coef1[b * n + i] = alpha * e * w / (float)n;
+    }
+    for (int j = threadIdx.x; j < m; j += DCD_THREADS) {
+        const float w = frac_12 / (powf((float)c2[__ldg(idx2 + b * m + j)], lambda) + 1e-6f);
+        const float e = expf(-__ldg(dist2 + b * m + j) * alpha);
+        s2 += 1.f - e * w;
+        if (coef2) coef2[b * m + j] = 0.5f * alpha * e * w / (float)m;
+    }
+    s1 = warp_sum(s1);
+    s2 = warp_sum(s2);
+    if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = s1; red[1][threadIdx.x >> 5] = s2; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float a = 0.f, c = 0.f;
+        for (int w = 0; w < DCD_THREADS / 32; ++w) { a += red[0][w]; c += red[1][w]; }
+        loss[b] = a / (float)n + 0.5f * (c / (float)m);
+    }
+}
+
 }  // namespace tgp
 
 using namespace tgp;
@@ -149,4 +197,20 @@ extern "C" int tgp_chamfer_bwd(const float* xyz1, const float* xyz2, const float
     if (rc) return rc;
     chamfer_bwd_scatter_kernel<<<blocks, threads, 0, st>>>(xyz1, xyz2, graddist1, graddist2, idx1, idx2, B, n, m, gradxyz1, gradxyz2);
     return check_launch("chamfer_bwd_scatter_kernel");
+}
+
+extern "C" int tgp_dcd(const float* dist1, const float* dist2, const int32_t* idx1, const int32_t* idx2, int B, int n,
+                       int m, float alpha, float n_lambda, float* loss, float* coef1, float* coef2,
+                       tgp_stream_t stream) {
+    if (!dist1 || !dist2 || !idx1 || !idx2 || !loss) return fail(TGP_EINVAL, "tgp_dcd: null pointer");
+    if (B <= 0 || n <= 0 || m <= 0) return fail(TGP_EINVAL, "tgp_dcd: sizes must be positive");
+    const size_t smem = (size_t)(n + m) * sizeof(int);
+    if (smem > 200 * 1024) return fail(TGP_EINVAL, "tgp_dcd: n + m too large for the shared-memory histograms");
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(dcd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        attr = true;
+    }
+    dcd_kernel<<<B, DCD_THREADS, smem, as_stream(stream)>>>(dist1, dist2, idx1, idx2, n, m, alpha, n_lambda, loss, coef1, coef2);
+    return check_launch("dcd_kernel");
 }
