@@ -48,9 +48,13 @@ unsigned long long tgp_launch_count(void);
 int tgp_knn_xyz(const float* xyz, int B, int N, int k, int64_t* idx64, int32_t* idx32, tgp_stream_t stream);
 
 /* get_neighbor_index(feature_map (B,N,D), k), gcn3d.py:14-23 as used by 'RF-F' (:201-206).
- * workspace: tgp_knn_feat_workspace(B,N,D) bytes. */
-size_t tgp_knn_feat_workspace(int B, int N, int D);
-int tgp_knn_feat(const float* x, int B, int N, int D, int k, int64_t* idx64, int32_t* idx32,
+ * The pairwise inner products (the reference's torch.bmm, gcn3d.py:18) run on the tensor cores (tcgen05, 3xTF32)
+ * fused with the warp-shuffle top-(k+1) selection; shapes the tensor-core kernel does not cover (k > 31,
+ * N > 4096, tiny problems) run on an fp32 FMA tile kernel with the same selection.
+ * x_split, optional: x already split as a tensor-core operand (B*N, 2*Kp) by tgp_split_tf32 / a mode-2 epilogue;
+ * workspace: tgp_knn_feat_workspace(B,N,D, x_split != NULL) bytes (row norms + the split when not supplied). */
+size_t tgp_knn_feat_workspace(int B, int N, int D, int have_split);
+int tgp_knn_feat(const float* x, const float* x_split, int B, int N, int D, int k, int64_t* idx64, int32_t* idx32,
                  void* workspace, size_t workspace_bytes, tgp_stream_t stream);
 
 /* get_nearest_index(target (B,N,3), source (B,M,3)), gcn3d.py:26-35 -> (B,N,1). */

@@ -37,8 +37,9 @@ SIGNATURES = {
     "tgp_last_error": (ctypes.c_char_p, []),
     "tgp_launch_count": (ctypes.c_ulonglong, []),
     "tgp_knn_xyz": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
-    "tgp_knn_feat_workspace": (c_size_t, [c_int, c_int, c_int]),
-    "tgp_knn_feat": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "tgp_knn_feat_workspace": (c_size_t, [c_int, c_int, c_int, c_int]),
+    "tgp_knn_feat": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t,
+                             c_void_p]),
     "tgp_nearest": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "tgp_gather_rows": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "tgp_select_rows": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),

@@ -21,84 +21,18 @@
 // Tile order is n-fastest: the ~148 tiles in flight cover a band of a few m-tiles x all n-tiles, so each A tile
 // is fetched from HBM once and re-read from L2 by the CTAs working on its other column blocks (ncu, round 1:
 // m-fastest order streamed the A operand from DRAM once per column block -- 8.2 GB for the 4096-wide head GEMM).
-#include "common.cuh"
-#include <cuda.h>
+#include "tc_common.cuh"
 #include <stdlib.h>
 
 namespace tgp {
 
-constexpr int TC_BM = 128;
-constexpr int TC_BK = 32;                 // 32 fp32 = one 128-byte swizzle span
 constexpr int TC_STAGES = 4;
 constexpr int TC_EPI_WARPS = 8;
 constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;   // TMA warp + MMA warp + epilogue warps
-constexpr int TC_A_BYTES = TC_BM * TC_BK * 4;   // 16 KB
 
 struct GemmDev {
     tgp_gemm_args a;
 };
-
-__device__ __forceinline__ uint32_t s_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void tc_mbar_init(uint64_t* bar, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void tc_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void tc_mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tc_mbar_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t done = 0;
-    unsigned spins = 0;
-    while (!done) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.b32 %0, 1, 0, p;\n\t}"
-            : "=r"(done) : "r"(s_u32(bar)), "r"(parity) : "memory");
-        if (!done && ++spins > (1u << 27)) __trap();   // a broken pipeline must fault, never hang the GPU
-    }
-}
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tm, int c0, int c1, uint64_t* bar) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-        ::"r"(s_u32(dst)), "l"(tm), "r"(c0), "r"(c1), "r"(s_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-// K-major, 128B-swizzled operand tile: rows of 128 B, 8-row groups 1024 B apart (SBO), LBO unused (=1),
-// descriptor version 1 (sm_100), layout type 2 (SWIZZLE_128B).
-__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
-    d |= (uint64_t)1 << 16;                  // leading byte offset (ignored for swizzled K-major)
-    d |= (uint64_t)(1024 >> 4) << 32;        // stride byte offset
-    d |= (uint64_t)1 << 46;                  // version
-    d |= (uint64_t)2 << 61;                  // SWIZZLE_128B
-    return d;
-}
-
-__device__ __forceinline__ float lds_f32(uint32_t addr) {
-    float v;
-    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
-    return v;
-}
-__device__ __forceinline__ void sts_f32(uint32_t addr, float v) {
-    asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
-}
 
 // one output destination of a column: pointer to (row0, col), row stride, and (split mode) the lo-half offset
 struct EpiDst {
@@ -154,18 +88,6 @@ __device__ __forceinline__ void epi_rows(uint32_t stg_addr, int lane, int nrows,
         }
     }
 }
-
-#define TMEM_LD_32x32(taddr, r)                                                                         \
-    asm volatile(                                                                                       \
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                       \
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "                       \
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"       \
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),   \
-          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]),          \
-          "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]),        \
-          "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]),        \
-          "=r"(r[29]), "=r"(r[30]), "=r"(r[31])                                                             \
-        : "r"(taddr))
 
 template <int BN>
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -429,38 +351,6 @@ __global__ void tc_splitk_reduce_kernel(const float* __restrict__ partial, int n
 
 using namespace tgp;
 
-typedef CUresult (*tgp_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static tgp_encode_fn get_encode() {
-    static tgp_encode_fn fn = nullptr;
-    static bool tried = false;
-    if (!tried) {
-        tried = true;
-        void* p = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-            q == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<tgp_encode_fn>(p);
-    }
-    return fn;
-}
-
-static int make_map(CUtensorMap* tm, const float* ptr, long rows, long Kp, int box_rows) {
-    tgp_encode_fn enc = get_encode();
-    if (!enc) return fail(TGP_EINVAL, "tgp_gemm: cuTensorMapEncodeTiled unavailable");
-    cuuint64_t gdim[2] = {(cuuint64_t)(2 * Kp), (cuuint64_t)rows};
-    cuuint64_t gstride[1] = {(cuuint64_t)(2 * Kp) * sizeof(float)};
-    cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
-    cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), gdim, gstride, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return fail(TGP_EINVAL, "tgp_gemm: cuTensorMapEncodeTiled failed");
-    return TGP_OK;
-}
-
 extern "C" int tgp_split_kpad(int K) { return (K + TC_BK - 1) / TC_BK * TC_BK; }
 
 extern "C" int tgp_split_tf32(const float* src, long rows, int K, long ld, int src_is_kn, float* dst,
@@ -485,9 +375,9 @@ template <int BN>
 static int launch_tc(const tgp_gemm_args* a, cudaStream_t st, int ksplit = 1) {
     const int Kp = tgp_split_kpad(a->K);
     CUtensorMap tmA, tmB;
-    int rc = make_map(&tmA, a->A_split, a->M, Kp, TC_BM);
+    int rc = tgp_make_map(&tmA, a->A_split, a->M, Kp, TC_BM);
     if (rc) return rc;
-    rc = make_map(&tmB, a->B_split, a->Ncols, Kp, BN);
+    rc = tgp_make_map(&tmB, a->B_split, a->Ncols, Kp, BN);
     if (rc) return rc;
     GemmDev P;
     P.a = *a;

@@ -8,74 +8,10 @@
 //
 // Ordering contract: ascending by (distance, index); rank 0 is dropped
 // positionally (gcn3d.py:22), never by testing j == i.
-#include "common.cuh"
-#include <math_constants.h>
+#include "knn_select.cuh"
+#include <stdlib.h>
 
 namespace tgp {
-
-constexpr unsigned FULL = 0xffffffffu;
-
-// Sorted list of 32*SLOTS (distance, index) pairs spread over a warp: rank = lane + 32*s.
-template <int SLOTS>
-struct WarpTopList {
-    float d[SLOTS];
-    int i[SLOTS];
-
-    __device__ __forceinline__ void init() {
-#pragma unroll
-        for (int s = 0; s < SLOTS; ++s) { d[s] = CUDART_INF_F; i[s] = -1; }
-    }
-    // distance currently at rank K-1 (the admission threshold)
-    __device__ __forceinline__ float thresh(int K) const {
-        const int r = K - 1;
-        float v = 0.f;
-#pragma unroll
-        for (int s = 0; s < SLOTS; ++s)
-            if ((r >> 5) == s) v = __shfl_sync(FULL, d[s], r & 31);
-        return v;
-    }
-    // insert (cd, cj); candidates arrive in increasing cj, so equal distances go behind
-    __device__ __forceinline__ void insert(float cd, int cj, int lane) {
-        int pos = 0;
-#pragma unroll
-        for (int s = 0; s < SLOTS; ++s) pos += __popc(__ballot_sync(FULL, d[s] <= cd));
-#pragma unroll
-        for (int s = SLOTS - 1; s >= 0; --s) {
-            float up = __shfl_up_sync(FULL, d[s], 1);
-            int upi = __shfl_up_sync(FULL, i[s], 1);
-            if (s > 0) {
-                float cr = __shfl_sync(FULL, d[s - 1], 31);
-                int cri = __shfl_sync(FULL, i[s - 1], 31);
-                if (lane == 0) { up = cr; upi = cri; }
-            }
-            const int rank = lane + 32 * s;
-            if (rank > pos) { d[s] = up; i[s] = upi; }
-            else if (rank == pos) { d[s] = cd; i[s] = cj; }
-        }
-    }
-    // admit every lane's candidate (dd, base+lane) that beats the threshold, lowest lane first
-    __device__ __forceinline__ void admit(float dd, int base, int lane, float& th, int K) {
-        unsigned m = __ballot_sync(FULL, dd < th);
-        while (m) {
-            const int src = __ffs(m) - 1;
-            m &= m - 1;
-            const float cd = __shfl_sync(FULL, dd, src);
-            if (cd < th) {
-                insert(cd, base + src, lane);
-                th = thresh(K);
-            }
-        }
-    }
-    template <typename T>
-    __device__ __forceinline__ void store_ranks(T* out, int k, int lane) const {
-        // ranks 1..k -> out[0..k)
-#pragma unroll
-        for (int s = 0; s < SLOTS; ++s) {
-            const int rank = lane + 32 * s;
-            if (rank >= 1 && rank <= k) out[rank - 1] = (T)i[s];
-        }
-    }
-};
 
 // ------------------------------------------------------------------------------------------
 // xyz-space kNN.  Distance recipe reproduces CPU torch bit for bit:
@@ -375,25 +311,44 @@ extern "C" int tgp_knn_xyz(const float* xyz, int B, int N, int k, int64_t* idx64
     return check_launch("knn_xyz_kernel");
 }
 
-extern "C" size_t tgp_knn_feat_workspace(int B, int N, int D) {
-    (void)D;
-    return (size_t)B * N * sizeof(float);
+bool tgp_knn_tc_eligible(int B, int N, int D, int k);
+int tgp_knn_tc(const float* x_split, const float* qn, int B, int N, int D, int k, int64_t* idx64, int32_t* idx32,
+               cudaStream_t st);
+
+static size_t knn_qn_bytes(int B, int N) { return (((size_t)B * N * sizeof(float)) + 255) & ~(size_t)255; }
+
+extern "C" size_t tgp_knn_feat_workspace(int B, int N, int D, int have_split) {
+    size_t s = knn_qn_bytes(B, N);
+    if (!have_split) s += (size_t)B * N * 2 * tgp_split_kpad(D) * sizeof(float);
+    return s;
 }
 
-extern "C" int tgp_knn_feat(const float* x, int B, int N, int D, int k, int64_t* idx64, int32_t* idx32,
-                            void* workspace, size_t workspace_bytes, tgp_stream_t stream) {
+extern "C" int tgp_knn_feat(const float* x, const float* x_split, int B, int N, int D, int k, int64_t* idx64,
+                            int32_t* idx32, void* workspace, size_t workspace_bytes, tgp_stream_t stream) {
     if (!x || (!idx64 && !idx32) || !workspace) return fail(TGP_EINVAL, "tgp_knn_feat: null pointer");
     if (B <= 0 || N <= 0 || k <= 0 || D <= 0) return fail(TGP_EINVAL, "tgp_knn_feat: sizes must be positive");
     if (k + 1 > N) return fail(TGP_EINVAL, "tgp_knn_feat: k+1 > N (torch.topk would raise, gcn3d.py:21)");
     if (k + 1 > 64) return fail(TGP_EINVAL, "tgp_knn_feat: k > 63 unsupported");
     if (B > 65535) return fail(TGP_EINVAL, "tgp_knn_feat: B > 65535");
-    if (workspace_bytes < tgp_knn_feat_workspace(B, N, D)) return fail(TGP_ENOSPACE, "tgp_knn_feat: workspace too small");
+    if (workspace_bytes < tgp_knn_feat_workspace(B, N, D, x_split != nullptr)) return fail(TGP_ENOSPACE, "tgp_knn_feat: workspace too small");
     cudaStream_t st = as_stream(stream);
     float* qn = static_cast<float*>(workspace);
     const long rows = (long)B * N;
     rownorm_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(x, rows, D, qn);
     int rc = check_launch("rownorm_kernel");
     if (rc) return rc;
+    static int force_fp32 = -1;
+    if (force_fp32 < 0) { const char* e = getenv("TGP_KNN_FP32"); force_fp32 = (e && e[0] == '1') ? 1 : 0; }
+    if (!force_fp32 && tgp_knn_tc_eligible(B, N, D, k)) {
+        // inner products on the tensor cores (knn_tc.cu); the split operand is built here unless the caller has it
+        if (!x_split) {
+            float* spl = reinterpret_cast<float*>(static_cast<unsigned char*>(workspace) + knn_qn_bytes(B, N));
+            rc = tgp_split_tf32(x, rows, D, D, 0, spl, stream);
+            if (rc) return rc;
+            x_split = spl;
+        }
+        return tgp_knn_tc(x_split, qn, B, N, D, k, idx64, idx32, st);
+    }
     const int slots = (k + 1 > 32) ? 2 : 1;
     const size_t smem = sizeof(float) * (KF_BK * KF_LDA + KF_BK * KF_LDB + KF_BM * KF_LDD) + (size_t)KF_BM * 32 * slots * 8;
     dim3 grid((N + KF_BM - 1) / KF_BM, B);

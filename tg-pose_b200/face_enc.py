@@ -81,15 +81,15 @@ class Face_Enc(nn.Module):
         def xyz_knn(v, kk):
             return ops.knn_xyz(v, kk, want64=False, want32=True)[1]
 
-        def feat_knn(f, kk):
-            return ops.knn_feat(f, kk, want64=False, want32=True)[1]
+        def feat_knn(f, kk, f_split=None):
+            return ops.knn_feat(f, kk, want64=False, want32=True, x_split=f_split)[1]
 
         # level 0
         i0 = self._next_idx(lambda: xyz_knn(vertices, k))
         i0_orl = self._next_idx(lambda: i0 if share else xyz_knn(vertices, k))
         # HSlayer_surface uses one xyz index for both RF-P and ORL; with injected indices they are the same tensor
         fm_0, fm_0s = self.conv_0(vertices, k, idx_xyz=i0, post=(None, None, True), want_split=True)
-        i1 = self._next_idx(lambda: feat_knn(fm_0, k))
+        i1 = self._next_idx(lambda: feat_knn(fm_0, k, fm_0s))
         i1_orl = self._next_idx(lambda: i0 if share else xyz_knn(vertices, k))
         if fold:
             fm_1 = self.conv_1(vertices, fm_0, k, idx_feat=i1, idx_xyz=i1_orl, post=self._bn_post(self.bn1),
@@ -109,7 +109,7 @@ class Face_Enc(nn.Module):
         else:
             fm_2s = None
             fm_2 = self._bn_relu(self.bn2, self.conv_2(v_pool_1, fm_pool_1, k1, idx_feat=i2, idx_xyz=i2_orl))
-        i3 = self._next_idx(lambda: feat_knn(fm_2, k1))
+        i3 = self._next_idx(lambda: feat_knn(fm_2, k1, fm_2s))
         i3_orl = self._next_idx(lambda: i2_orl if share else xyz_knn(v_pool_1, k1))
         if fold:
             fm_3 = self.conv_3(v_pool_1, fm_2, k1, idx_feat=i3, idx_xyz=i3_orl, post=self._bn_post(self.bn3),

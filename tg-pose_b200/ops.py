@@ -69,16 +69,19 @@ def knn_xyz(xyz, k, want64=True, want32=False):
     return i64, i32
 
 
-def knn_feat(x, k, want64=True, want32=False):
-    """get_neighbor_index on (B,N,D) features (RF-F), gcn3d.py:14-23,201-206."""
+def knn_feat(x, k, want64=True, want32=False, x_split=None):
+    """get_neighbor_index on (B,N,D) features (RF-F), gcn3d.py:14-23,201-206.  x_split: the same features already
+    split as a tensor-core operand (B*N, 2*kpad(D)), if a producer's epilogue wrote it."""
     x = _f32c(x, "knn_feat")
     B, N, D = x.shape
     lib = _lib.load()
-    ws_bytes = lib.tgp_knn_feat_workspace(B, N, D)
+    if x_split is not None and (x_split.numel() == 0 or x_split.shape != (B * N, 2 * kpad(D))):
+        x_split = None
+    ws_bytes = lib.tgp_knn_feat_workspace(B, N, D, 1 if x_split is not None else 0)
     ws = torch.empty((ws_bytes + 3) // 4, dtype=torch.float32, device=x.device)
     i64 = torch.empty((B, N, k), dtype=torch.int64, device=x.device) if want64 else None
     i32 = torch.empty((B, N, k), dtype=torch.int32, device=x.device) if want32 else None
-    _run("knn_feat", lib.tgp_knn_feat, _p(x), B, N, D, k, _p(i64), _p(i32), _p(ws), ws_bytes, _stream())
+    _run("knn_feat", lib.tgp_knn_feat, _p(x), _p(x_split), B, N, D, k, _p(i64), _p(i32), _p(ws), ws_bytes, _stream())
     return i64, i32
 
 
