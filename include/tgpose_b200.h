@@ -90,6 +90,25 @@ size_t tgp_orl_workspace(int B, int N, int C);
 int tgp_orl_global(const float* f, const void* idx, int idx_bits, int B, int N, int k, int C,
                    float* g, uint8_t* arg, void* workspace, size_t workspace_bytes, tgp_stream_t stream);
 
+/* One source of tgp_concat_rows: (rows, C) fp32 with row stride ld.
+ * idx == NULL, n_src > 0 : row r of the output takes row r of the source (n_src is ignored);
+ * idx != NULL            : int32 (B,N): output row (b,n) takes source row b*n_src + idx[b,n]
+ *                          (the nearest upsampling indexing_neighbor_new(fm, nearest).squeeze(2), FaceRecon.py:71-73);
+ * n_src == 0             : one source row per cloud, broadcast to its N points (the one-hot category, FaceRecon.py:75-79). */
+typedef struct {
+    const float* ptr;
+    int C;
+    long ld;
+    const int32_t* idx;
+    int n_src;
+} tgp_concat_src;
+
+/* torch.cat([...], dim=2) of FaceRecon.py:81 (+ the cat with the points, PoseNet9D.py:63) fused with the gathers that
+ * feed it: out[(b,n), :] = [src_0 row | src_1 row | ...].  out_raw (B*N, ld_raw) and/or out_split (B*N, 2*Kp): the
+ * same row as a tensor-core operand [tf32 | residual], zero padded to Kp.  Either may be NULL. */
+int tgp_concat_rows(const tgp_concat_src* srcs_host, int nsrc, int B, int N, float* out_raw, long ld_raw,
+                    float* out_split, int Kp, tgp_stream_t stream);
+
 /* ------------------------------------------------------------------ graph convolutions */
 
 /* HSlayer_surface.graph_conv, gcn3d.py:91-106:
@@ -125,7 +144,11 @@ int tgp_layer_conv_fwd(const float* edge_rec, const float* directions,
  * mode 0: row-major, out[m*ld + (col - col_begin)].
  * mode 1: SLAB, columns are ordered (cgroup, s, c4) and go to [cgroup][m][S*4] (slab_width = S*4).
  * mode 2: SPLIT, the value is written as a tensor-core operand for the next contraction:
- *         tf32(v) at out[m*ld + rel] and v - tf32(v) at out[m*ld + slab_width + rel] (slab_width = Kp). */
+ *         tf32(v) at out[m*ld + rel] and v - tf32(v) at out[m*ld + slab_width + rel] (slab_width = Kp).
+ * mode 3: COLUMN MAX per group of rows_per_group rows (torch.max over the points of a cloud, PoseR.py:33,
+ *         FaceRecon.py:146): ptr is an int32 (M / rows_per_group, col_end - col_begin) buffer pre-filled with
+ *         INT_MIN that receives atomicMax of the order-preserving encoding e(v) = bits(v) >= 0 ? bits(v) :
+ *         bits(v) ^ 0x7fffffff (decode with the same map); the (M, cols) tensor itself is never written. */
 typedef struct {
     int col_begin, col_end;
     int mode;

@@ -18,6 +18,11 @@ class OutSeg(ctypes.Structure):
                 ("ld", c_long), ("ptr", c_void_p)]
 
 
+class ConcatSrc(ctypes.Structure):
+    """tgp_concat_src"""
+    _fields_ = [("ptr", c_void_p), ("C", c_int), ("ld", c_long), ("idx", c_void_p), ("n_src", c_int)]
+
+
 class GemmArgs(ctypes.Structure):
     """tgp_gemm_args"""
     _fields_ = [("A", c_void_p), ("lda", c_long),
@@ -61,6 +66,8 @@ SIGNATURES = {
                                 c_void_p, c_void_p]),
     "tgp_chamfer_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                 c_void_p, c_void_p, c_void_p]),
+    "tgp_concat_rows": (c_int, [ctypes.POINTER(ConcatSrc), c_int, c_int, c_int, c_void_p, c_long, c_void_p, c_int,
+                                c_void_p]),
     "tgp_dcd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, ctypes.c_float, ctypes.c_float,
                         c_void_p, c_void_p, c_void_p, c_void_p]),
     "tgp_act_bwd": (c_int, [c_void_p, c_long, c_void_p, c_long, c_void_p, c_int, c_long, c_int, c_void_p, c_long,

@@ -59,11 +59,11 @@ def _orl_tail(feature, idx_xyz, conv2_w, f_ste, B, N, C, post, want_arg=False, f
 
 class HSSurfaceFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, xyz, directions, ste_w, conv2_w, k, S, C, idx_xyz, post, want_split):
+    def forward(ctx, xyz, directions, ste_w, conv2_w, k, S, C, idx_xyz, post, want_split, grad_on):
         xyz = xyz.contiguous().float()
         B, N, _ = xyz.shape
         M = B * N
-        train = any(ctx.needs_input_grad)   # grad mode is off inside Function.forward
+        train = grad_on and any(ctx.needs_input_grad)   # grad_on: torch.is_grad_enabled() at the call site (it is off in here)
         f_ste = ops.linear_nk(xyz.view(M, 3), ste_w.reshape(C, 3))
         if idx_xyz is None:
             idx_xyz = ops.knn_xyz(xyz, k, want64=False, want32=True)[1]
@@ -89,12 +89,12 @@ class HSSurfaceFn(torch.autograd.Function):
 class HSLayerFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, xyz, fm, weights, bias, directions, ste_w, conv2_w, k, S, C, idx_feat, idx_xyz, post,
-                fm_split, want_split):
+                fm_split, want_split, grad_on):
         xyz = xyz.contiguous().float()
         fm = fm.contiguous().float()
         B, N, cin = fm.shape
         M = B * N
-        train = any(ctx.needs_input_grad)   # grad mode is off inside Function.forward
+        train = grad_on and any(ctx.needs_input_grad)   # grad_on: torch.is_grad_enabled() at the call site (it is off in here)
         wcat, bcat, wcat_split = _pack_layer(weights, bias, ste_w, S, C)
         dev = fm.device
         centre = torch.empty((M, C), dtype=torch.float32, device=dev)
@@ -131,10 +131,10 @@ class HSLayerFn(torch.autograd.Function):
 
 class PoolFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, xyz, fm, sample_idx, k, idx_xyz):
+    def forward(ctx, xyz, fm, sample_idx, k, idx_xyz, grad_on):
         xyz = xyz.contiguous().float()
         fm = fm.contiguous().float()
-        train = any(ctx.needs_input_grad)   # grad mode is off inside Function.forward
+        train = grad_on and any(ctx.needs_input_grad)   # grad_on: torch.is_grad_enabled() at the call site (it is off in here)
         if idx_xyz is None:
             idx_xyz = ops.knn_xyz(xyz, k, want64=False, want32=True)[1]
         rows = sample_idx.to(xyz.device, non_blocking=True)

@@ -52,7 +52,7 @@ def hs_surface_backward(ctx, grad_out):
     gz, d_f, d_conv2 = _orl_tail_bwd(grad_out, out, post, feature, g, idx_xyz, arg_orl, conv2_w, B, N, C)
     d_ste = ops.gemm_tn(gz, xyz.view(M, 3)).view(C, 3, 1)         # f_STE = xyz @ W_STE^T
     d_dir = ops.surface_conv_bwd(xyz, idx_xyz, directions, arg, d_f, S, C)
-    return None, d_dir, d_ste, d_conv2, None, None, None, None, None, None
+    return None, d_dir, d_ste, d_conv2, None, None, None, None, None, None, None
 
 
 def hs_layer_backward(ctx, grad_out):
@@ -76,7 +76,7 @@ def hs_layer_backward(ctx, grad_out):
     d_bias = torch.cat([d_bcat[:C], d_bcat[C:].reshape(C // 4, S, 4).permute(1, 0, 2).reshape(SC)])
     d_ste = d_wcat[:, C + SC:].t().reshape(C, cin, 1)
     return (None, d_fm.view(B, N, cin), d_weights, d_bias, d_dir, d_ste, d_conv2,
-            None, None, None, None, None, None, None, None)
+            None, None, None, None, None, None, None, None, None)
 
 
 def pool_backward(ctx, g_pooled):
@@ -84,4 +84,4 @@ def pool_backward(ctx, g_pooled):
     B, N, C = ctx.shape
     d_fm = torch.zeros((B, N, C), dtype=torch.float32, device=g_pooled.device)
     ops.gather_max_bwd(g_pooled, idx_xyz, arg, N, d_fm, rows=rows)
-    return None, d_fm, None, None, None
+    return None, d_fm, None, None, None, None

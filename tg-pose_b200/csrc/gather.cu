@@ -140,6 +140,50 @@ __global__ void orl_finalize_kernel(const float* __restrict__ partial, int nspli
     g[e] = s / (float)N;
 }
 
+
+// ------------------------------------------------------------------------------------------
+// gather-concatenate: out[r, off_s + c] = src_s[row_s(r), c] for up to 8 sources side by side.
+// Replaces the chain indexing_neighbor_new(...).squeeze(2) x3 + one_hot expand + torch.cat (FaceRecon.py:69-81)
+// and the second cat with the centred points (PoseNet9D.py:63): one pass that reads every source row once and
+// writes the concatenated row as raw fp32 and/or directly as the [tf32 | residual] operand of the head GEMMs.
+struct ConcatDev {
+    tgp_concat_src s[8];
+    int nsrc;
+};
+
+__global__ void __launch_bounds__(256)
+concat_rows_kernel(const __grid_constant__ ConcatDev P, int N, float* __restrict__ out_raw, long ld_raw,
+                   float* __restrict__ out_split, int Kp) {
+    const long r = blockIdx.x;
+    const long b = r / N;
+    int off = 0;
+    for (int si = 0; si < P.nsrc; ++si) {
+        const tgp_concat_src& s = P.s[si];
+        long row;
+        if (s.n_src == 0) row = b;                                         // one row per cloud, broadcast
+        else if (s.idx) row = b * s.n_src + __ldg(s.idx + r);              // nearest-upsampling gather
+        else row = r;
+        const float* src = s.ptr + row * s.ld;
+        for (int c = threadIdx.x; c < s.C; c += blockDim.x) {
+            const float v = __ldg(src + c);
+            if (out_raw) out_raw[r * ld_raw + off + c] = v;
+            if (out_split) {
+                uint32_t hb;
+                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v));
+                const float hi = __uint_as_float(hb);
+                out_split[r * 2 * Kp + off + c] = hi;
+                out_split[r * 2 * Kp + Kp + off + c] = v - hi;
+            }
+        }
+        off += s.C;
+    }
+    if (out_split)
+        for (int c = off + threadIdx.x; c < Kp; c += blockDim.x) {
+            out_split[r * 2 * Kp + c] = 0.f;
+            out_split[r * 2 * Kp + Kp + c] = 0.f;
+        }
+}
+
 }  // namespace tgp
 
 using namespace tgp;
@@ -233,4 +277,22 @@ extern "C" int tgp_orl_global(const float* f, const void* idx, int idx_bits, int
     const long total = (long)B * C;
     orl_finalize_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(partial, nsplit, C, total, N, g);
     return check_launch("orl_finalize_kernel");
+}
+
+extern "C" int tgp_concat_rows(const tgp_concat_src* srcs_host, int nsrc, int B, int N, float* out_raw, long ld_raw,
+                               float* out_split, int Kp, tgp_stream_t stream) {
+    if (!srcs_host || (!out_raw && !out_split)) return fail(TGP_EINVAL, "tgp_concat_rows: null pointer");
+    if (nsrc < 1 || nsrc > 8 || B <= 0 || N <= 0) return fail(TGP_EINVAL, "tgp_concat_rows: bad sizes");
+    ConcatDev P;
+    P.nsrc = nsrc;
+    int total = 0;
+    for (int i = 0; i < nsrc; ++i) {
+        if (!srcs_host[i].ptr || srcs_host[i].C <= 0 || srcs_host[i].n_src < 0) return fail(TGP_EINVAL, "tgp_concat_rows: bad source");
+        P.s[i] = srcs_host[i];
+        total += srcs_host[i].C;
+    }
+    if (out_split && (Kp < total || Kp % 4)) return fail(TGP_EINVAL, "tgp_concat_rows: Kp smaller than the concatenated width");
+    if (out_raw && ld_raw < total) return fail(TGP_EINVAL, "tgp_concat_rows: ld_raw smaller than the concatenated width");
+    concat_rows_kernel<<<(unsigned)((long)B * N), 256, 0, as_stream(stream)>>>(P, N, out_raw, ld_raw, out_split, Kp);
+    return check_launch("concat_rows_kernel");
 }

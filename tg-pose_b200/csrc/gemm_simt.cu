@@ -47,7 +47,11 @@ __device__ __forceinline__ void epilogue_store(const tgp_gemm_args& g, long row,
     for (int s = 0; s < 4; ++s) {
         if (s < g.nseg && col >= g.seg[s].col_begin && col < g.seg[s].col_end) {
             const int rel = col - g.seg[s].col_begin;
-            if (g.seg[s].mode == 0) g.seg[s].ptr[row * g.seg[s].ld + rel] = v;
+            if (g.seg[s].mode == 3) {
+                const int i = __float_as_int(v);
+                atomicMax(reinterpret_cast<int*>(g.seg[s].ptr) + (row / g.rows_per_group) * (g.seg[s].col_end - g.seg[s].col_begin) + rel,
+                          i >= 0 ? i : i ^ 0x7fffffff);
+            } else if (g.seg[s].mode == 0) g.seg[s].ptr[row * g.seg[s].ld + rel] = v;
             else if (g.seg[s].mode == 2) {
                 uint32_t hb;
                 asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v));
@@ -196,6 +200,7 @@ int tgp_gemm_validate(const tgp_gemm_args* a) {
     if ((!a->A || !a->Bmat) && (!a->A_split || !a->B_split)) return fail(TGP_EINVAL, "tgp_gemm: null operand");
     if (a->M <= 0 || a->K <= 0 || a->Ncols <= 0) return fail(TGP_EINVAL, "tgp_gemm: sizes must be positive");
     if (a->nseg < 1 || a->nseg > 4) return fail(TGP_EINVAL, "tgp_gemm: nseg must be 1..4");
+    if (a->rows_per_group < 0) return fail(TGP_EINVAL, "tgp_gemm: rows_per_group must be >= 0");
     if (a->group_bias && a->rows_per_group <= 0) return fail(TGP_EINVAL, "tgp_gemm: rows_per_group must be positive");
     if ((a->scale == nullptr) != (a->shift == nullptr)) return fail(TGP_EINVAL, "tgp_gemm: scale and shift go together");
     for (int s = 0; s < a->nseg; ++s) {
@@ -204,7 +209,8 @@ int tgp_gemm_validate(const tgp_gemm_args* a) {
             return fail(TGP_EINVAL, "tgp_gemm: bad output segment");
         if (sg.mode == 1 && (sg.slab_width <= 0 || (sg.col_end - sg.col_begin) % sg.slab_width))
             return fail(TGP_EINVAL, "tgp_gemm: slab segment must be a multiple of slab_width");
-        if (sg.mode < 0 || sg.mode > 2) return fail(TGP_EINVAL, "tgp_gemm: bad segment mode");
+        if (sg.mode < 0 || sg.mode > 3) return fail(TGP_EINVAL, "tgp_gemm: bad segment mode");
+        if (sg.mode == 3 && a->rows_per_group < 32) return fail(TGP_EINVAL, "tgp_gemm: column-max segment needs rows_per_group >= 32");
         if (sg.mode == 2 && sg.slab_width < sg.col_end - sg.col_begin) return fail(TGP_EINVAL, "tgp_gemm: split segment wider than Kp");
     }
     return TGP_OK;

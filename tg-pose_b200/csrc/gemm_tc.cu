@@ -22,6 +22,7 @@
 // is fetched from HBM once and re-read from L2 by the CTAs working on its other column blocks (ncu, round 1:
 // m-fastest order streamed the A operand from DRAM once per column block -- 8.2 GB for the 4096-wide head GEMM).
 #include "tc_common.cuh"
+#include <math_constants.h>
 #include <stdlib.h>
 
 namespace tgp {
@@ -38,8 +39,14 @@ struct GemmDev {
 struct EpiDst {
     float* p;
     long rs;
-    int lo;
+    int lo;      // > 0: split mode, offset of the residual half;  -1: per-group column max (p -> encoded int cell of group 0)
 };
+
+// order-preserving float -> int map for atomicMax (mode 3): signed-int order == float order
+__device__ __forceinline__ int enc_ordered(float v) {
+    const int i = __float_as_int(v);
+    return i >= 0 ? i : i ^ 0x7fffffff;
+}
 
 __device__ __forceinline__ void epi_store(EpiDst& d, float v) {
     if (d.p) {
@@ -57,10 +64,12 @@ __device__ __forceinline__ void epi_store(EpiDst& d, float v) {
 // rows of one 32-column chunk: lane = column.  Loads (shared-memory staging + residuals) for 8 rows are issued
 // before any of their stores so that the global loads overlap (ncu round 1: the row-at-a-time loop stalled on
 // long_scoreboard for every residual load).
-template <bool D1>
+template <bool D1, bool MX>
 __device__ __forceinline__ void epi_rows(uint32_t stg_addr, int lane, int nrows, float bias, float sc, float sh,
                                          float slope, float gbv0, float gbv1, int gb_switch, const float* r1p,
                                          long ld1, const float* r2p, long ld2, EpiDst d0, EpiDst d1) {
+    float mx0 = -CUDART_INF_F, mx1 = -CUDART_INF_F;
+    const bool is_max = MX && d0.lo < 0;
 #pragma unroll 1
     for (int rr0 = 0; rr0 < nrows; rr0 += 8) {
         float a[8];
@@ -82,10 +91,19 @@ __device__ __forceinline__ void epi_rows(uint32_t stg_addr, int lane, int nrows,
                 float v = a[u] + ((rr0 + u) >= gb_switch ? gbv1 : gbv0);
                 v = fmaf(v, sc, sh);
                 v = v > 0.f ? v : v * slope;
-                epi_store(d0, v);
-                if (D1) epi_store(d1, v);
+                if (MX && is_max) {
+                    if ((rr0 + u) >= gb_switch) mx1 = fmaxf(mx1, v); else mx0 = fmaxf(mx0, v);
+                } else {
+                    epi_store(d0, v);
+                    if (D1) epi_store(d1, v);
+                }
             }
         }
+    }
+    if (MX && is_max && nrows > 0) {
+        int* cell = reinterpret_cast<int*>(d0.p);
+        if (gb_switch > 0) atomicMax(cell, enc_ordered(mx0));
+        if (gb_switch < nrows) atomicMax(cell + d0.rs, enc_ordered(mx1));
     }
 }
 
@@ -207,11 +225,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             long grp0 = 0;
             int gb_switch = 64;
             bool gb_slow = false;
-            if (g.group_bias) {
+            if (g.group_bias || g.rows_per_group > 0) {
                 grp0 = row0 / g.rows_per_group;
                 const long nxt = (grp0 + 1) * g.rows_per_group - row0;
                 gb_switch = nxt < 64 ? (int)nxt : 64;
-                gb_slow = g.rows_per_group < 32;
+                gb_slow = g.group_bias && g.rows_per_group < 32;
             }
             const uint32_t stg_addr = s_u32(stg);
 #pragma unroll 1
@@ -240,7 +258,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         if (s < g.nseg && col >= g.seg[s].col_begin && col < g.seg[s].col_end) {
                             const int rel = col - g.seg[s].col_begin;
                             EpiDst d;
-                            if (g.seg[s].mode == 1) {
+                            if (g.seg[s].mode == 3) {
+                                // per-group column max: rows_per_group >= 32, so a 32-row block touches <= 2 groups
+                                d.rs = g.seg[s].col_end - g.seg[s].col_begin;
+                                d.lo = -1;
+                                d.p = g.seg[s].ptr + grp0 * d.rs + rel;
+                            } else if (g.seg[s].mode == 1) {
                                 const int w = g.seg[s].slab_width;
                                 const int cg = rel / w, rr = rel - cg * w;
                                 d.rs = w; d.lo = 0;
@@ -269,11 +292,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         }
                 }
                 const int nr = live ? nrows : 0;
-                if (__any_sync(0xffffffffu, d1.p != nullptr))
-                    epi_rows<true>(stg_addr, lane, nr, bias, sc, sh, slope, gbv0, gbv1, gb_switch, r1p, g.ld_res1, r2p,
+                if (__any_sync(0xffffffffu, d0.p != nullptr && d0.lo < 0))
+                    epi_rows<true, true>(stg_addr, lane, nr, bias, sc, sh, slope, gbv0, gbv1, gb_switch, r1p, g.ld_res1, r2p,
+                                         g.ld_res2, d0, d1);
+                else if (__any_sync(0xffffffffu, d1.p != nullptr))
+                    epi_rows<true, false>(stg_addr, lane, nr, bias, sc, sh, slope, gbv0, gbv1, gb_switch, r1p, g.ld_res1, r2p,
                                    g.ld_res2, d0, d1);
                 else
-                    epi_rows<false>(stg_addr, lane, nr, bias, sc, sh, slope, gbv0, gbv1, gb_switch, r1p, g.ld_res1, r2p,
+                    epi_rows<false, false>(stg_addr, lane, nr, bias, sc, sh, slope, gbv0, gbv1, gb_switch, r1p, g.ld_res1, r2p,
                                     g.ld_res2, d0, d1);
             }
             tc_fence_before();

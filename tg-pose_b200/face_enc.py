@@ -70,9 +70,9 @@ class Face_Enc(nn.Module):
         return F.relu(bn(x.transpose(1, 2)).transpose(1, 2))
 
     # -- forward -------------------------------------------------------------------------
-    def forward(self, vertices, cat_id, enable_proj=False):
-        """vertices (B,N,3), cat_id (B,1) -> (feat (B,N,1286), feat_global (B,1286,N)); ref FaceRecon.py:39-86."""
-        bs, vertice_num, _ = vertices.size()
+    def encode(self, vertices):
+        """the five graph-conv feature maps and the two nearest-upsampling index tensors (FaceRecon.py:55-70):
+        -> dict(fm_0 (B,N0,128), fm_1 (B,N0,128), fm_2, fm_3 (B,N1,256), fm_4 (B,N2,512), nn1, nn2 (B,N0,1) int32)."""
         k = self.neighbor_num
         fold = not self.training
         self._slot = 0
@@ -125,17 +125,40 @@ class Face_Enc(nn.Module):
         i4_orl = self._next_idx(lambda: xyz_knn(v_pool_2, k2))
         fm_4 = self.conv_4(v_pool_2, fm_pool_2, k2, idx_feat=i4, idx_xyz=i4_orl)
 
-        # nearest-neighbour upsampling back to level 0 (FaceRecon.py:69-73)
+        # nearest-neighbour upsampling indices back to level 0 (FaceRecon.py:69-70)
         nn1 = self._next_idx(lambda: ops.nearest(vertices, v_pool_1, want64=False, want32=True)[1])
         nn2 = self._next_idx(lambda: ops.nearest(vertices, v_pool_2, want64=False, want32=True)[1])
-        fm_2u = gcn3d.indexing_neighbor_new(fm_2, nn1).squeeze(2)
-        fm_3u = gcn3d.indexing_neighbor_new(fm_3, nn1).squeeze(2)
-        fm_4u = gcn3d.indexing_neighbor_new(fm_4, nn2).squeeze(2)
+        return {"fm_0": fm_0, "fm_1": fm_1, "fm_2": fm_2, "fm_3": fm_3, "fm_4": fm_4, "nn1": nn1, "nn2": nn2}
 
+    def one_hot(self, cat_id, bs):
         obj_idh = cat_id.view(-1, 1)
-        one_hot = torch.zeros(bs, self.obj_c, device=vertices.device).scatter_(1, obj_idh.long(), 1)
-        one_hot = one_hot.unsqueeze(1).expand(-1, vertice_num, -1)
-        feat = torch.cat([fm_0, fm_1, fm_2u, fm_3u, fm_4u, one_hot], dim=2)
+        return torch.zeros(bs, self.obj_c, device=cat_id.device).scatter_(1, obj_idh.long(), 1)
+
+    @staticmethod
+    def concat_sources(parts, one_hot, extra=()):
+        """the column blocks of `feat` (FaceRecon.py:81) as tgp_concat_rows sources (+ optional extra blocks)."""
+        f = parts
+        n1, n2 = f["fm_2"].shape[1], f["fm_4"].shape[1]
+        flat = lambda t: t.reshape(-1, t.shape[-1])
+        nn1, nn2 = f["nn1"].reshape(f["nn1"].shape[0], -1), f["nn2"].reshape(f["nn2"].shape[0], -1)
+        return [(flat(f["fm_0"]), None, 1), (flat(f["fm_1"]), None, 1), (flat(f["fm_2"]), nn1, n1),
+                (flat(f["fm_3"]), nn1, n1), (flat(f["fm_4"]), nn2, n2), (one_hot, None, 0)] + list(extra)
+
+    def forward(self, vertices, cat_id, enable_proj=False):
+        """vertices (B,N,3), cat_id (B,1) -> (feat (B,N,1286), feat_global (B,1286,N)); ref FaceRecon.py:39-86."""
+        bs, vertice_num, _ = vertices.size()
+        parts = self.encode(vertices)
+        one_hot = self.one_hot(cat_id, bs)
+        if torch.is_grad_enabled() and any(parts[k].requires_grad for k in ("fm_0", "fm_1", "fm_2", "fm_3", "fm_4")):
+            # autograd path: the gathers scatter-add in backward (GatherRowsFn), the concatenation is torch's
+            fm_2u = gcn3d.indexing_neighbor_new(parts["fm_2"], parts["nn1"]).squeeze(2)
+            fm_3u = gcn3d.indexing_neighbor_new(parts["fm_3"], parts["nn1"]).squeeze(2)
+            fm_4u = gcn3d.indexing_neighbor_new(parts["fm_4"], parts["nn2"]).squeeze(2)
+            feat = torch.cat([parts["fm_0"], parts["fm_1"], fm_2u, fm_3u, fm_4u,
+                              one_hot.unsqueeze(1).expand(-1, vertice_num, -1)], dim=2)
+        else:
+            # one launch: upsampling gathers + one-hot broadcast + concatenation
+            feat = ops.concat_rows(self.concat_sources(parts, one_hot), bs, vertice_num)[0].view(bs, vertice_num, -1)
         feat_global = feat.permute(0, 2, 1)
         feat_global_prj = self.proj_layer(feat_global) if enable_proj else feat_global
         return feat, feat_global_prj

@@ -90,7 +90,8 @@ class HSlayer_surface(nn.Module):
         encoder: a precomputed int32 xyz kNN, (scale, shift, relu) folded into the last epilogue, and the
         result also returned as the next projection's tensor-core operand (-> (out, out_split))."""
         out, out_split = HSSurfaceFn.apply(vertices, self.directions, self.STE_layer.weight, self.conv2.weight,
-                                           neighbor_num, self.support_num, self.kernel_num, idx_xyz, post, want_split)
+                                           neighbor_num, self.support_num, self.kernel_num, idx_xyz, post, want_split,
+                                           torch.is_grad_enabled())
         return (out, out_split) if want_split else out
 
     def graph_conv(self, receptive_fields_norm, vertices, neighbor_num):
@@ -128,7 +129,8 @@ class HS_layer(nn.Module):
         split for the tensor cores) and want_split (-> (out, out_split)) are fused-encoder extensions."""
         out, out_split = HSLayerFn.apply(vertices, feature_map, self.weights, self.bias, self.directions,
                                          self.STE_layer.weight, self.conv2.weight, neighbor_num, self.support_num,
-                                         self.out_channel, idx_feat, idx_xyz, post, fm_split, want_split)
+                                         self.out_channel, idx_feat, idx_xyz, post, fm_split, want_split,
+                                         torch.is_grad_enabled())
         return (out, out_split) if want_split else out
 
 
@@ -146,4 +148,4 @@ class Pool_layer(nn.Module):
         vertice_num = vertices.size(1)
         pool_num = int(vertice_num / self.pooling_rate)
         sample_idx = torch.randperm(vertice_num)[:pool_num]
-        return PoolFn.apply(vertices, feature_map, sample_idx, self.neighbor_num, idx_xyz)
+        return PoolFn.apply(vertices, feature_map, sample_idx, self.neighbor_num, idx_xyz, torch.is_grad_enabled())

@@ -162,6 +162,29 @@ def orl_global(f, idx, want_arg=False):
     return (g, arg) if want_arg else g
 
 
+def concat_rows(sources, B, N, want_raw=True, want_split=False):
+    """[src_0 | src_1 | ...] per point.  sources: list of (tensor2d (rows, C), idx or None, n_src):
+    idx None & n_src > 0: identity rows; idx (B,N) int32: gather from a cloud of n_src rows; n_src == 0: per-cloud row.
+    Returns (raw (B*N, total) or None, split (B*N, 2*kpad(total)) or None)."""
+    dev = sources[0][0].device
+    arr = (_lib.ConcatSrc * len(sources))()
+    total = 0
+    keep = []
+    for i, (t, idx, n_src) in enumerate(sources):
+        assert t.stride(-1) == 1 and t.dim() == 2
+        if idx is not None:
+            idx = idx.to(torch.int32).contiguous()
+            keep.append(idx)
+        arr[i] = _lib.ConcatSrc(t.data_ptr(), t.shape[1], t.stride(0), idx.data_ptr() if idx is not None else None, n_src)
+        total += t.shape[1]
+    M = B * N
+    raw = torch.empty((M, total), dtype=torch.float32, device=dev) if want_raw else None
+    kp = kpad(total)
+    spl = torch.empty((M, 2 * kp), dtype=torch.float32, device=dev) if want_split else None
+    _run("concat_rows", _lib.load().tgp_concat_rows, arr, len(sources), B, N, _p(raw), total, _p(spl), kp, _stream())
+    return raw, spl
+
+
 # --------------------------------------------------------------------------------------- graph convs
 def _split_buf(M, C, device):
     kp = kpad(C)
@@ -298,11 +321,16 @@ def gemm(A, Bmat, b_is_nk, segs, bias=None, group_bias=None, rows_per_group=0, r
     a.neg_slope = neg_slope.data_ptr() if neg_slope is not None else None
     a.nseg = len(segs)
     for i, (c0, c1, t, mode, sw) in enumerate(segs):
-        a.seg[i] = OutSeg(c0, c1, mode, sw, t.stride(0) if mode != 1 else 0, t.data_ptr())
+        a.seg[i] = OutSeg(c0, c1, mode, sw, t.stride(0) if mode in (0, 2) else 0, t.data_ptr())
     name = "gemm_tc" if A_split is not None and B_split is not None else "gemm"
     if EVENT_LOG is not None:
         EVENT_LOG.setdefault("__gemm_shapes__", []).append((name, M, K, Ncols))
     _run(name, _lib.load().tgp_gemm, ctypes.byref(a), _stream())
+
+
+def decode_max(enc_i32):
+    """inverse of the order-preserving int encoding written by a column-max GEMM segment (mode 3) -> fp32."""
+    return torch.where(enc_i32 >= 0, enc_i32, enc_i32 ^ 0x7fffffff).view(torch.float32)
 
 
 def kpad(K):

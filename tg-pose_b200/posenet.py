@@ -237,73 +237,102 @@ class PoseNet9D(nn.Module):
         """packed / BN-folded / tf32-split head weights, rebuilt only when a parameter or BN buffer changes."""
         fa, g, r, t = self.face_all, self.rot_green, self.rot_red, self.ts
         d, ph = fa.decoder, fa.ph_pred
-        mods = [g.conv1, g.bn1, g.conv2, g.bn2, r.conv1, r.bn1, r.conv2, r.bn2, t.conv1, t.bn1, t.conv2, t.bn2,
-                ph.conv_5[0], ph.conv_5[1], d.conv1d_block[0], d.conv1d_block[1], d.conv1d_block[3], d.conv1d_block[4],
-                d.conv1d_block[6], d.conv1d_block[7], d.recon_head[0], d.recon_head[1]]
+        mods = [g, r, t, d, ph]
         key = tuple((x._version, x.data_ptr()) for m in mods for x in list(m.parameters()) + list(m.buffers()))
         if getattr(self, "_packs_key", None) != key:
             kin = FEAT_C + 3
             c = d.conv1d_block
-            self._packs = {
-                # [rot_green.conv1 | rot_red.conv1 | ph_pred.conv_5 | ts.conv1] on [feat | xyz] (K = 1289)
-                "stage1": _Packed([g.conv1.weight, r.conv1.weight, ph.conv_5[0].weight, t.conv1.weight],
-                                  [_fold(g.conv1, g.bn1), _fold(r.conv1, r.bn1), _fold(ph.conv_5[0], ph.conv_5[1]),
-                                   _fold(t.conv1, t.bn1)], [0.0, 0.0, 0.2, 0.0], k_pad_to=kin),
-                "green2": _Packed([g.conv2.weight], [_fold(g.conv2, g.bn2)], [0.0]),
-                "red2": _Packed([r.conv2.weight], [_fold(r.conv2, r.bn2)], [0.0]),
-                "ts2": _Packed([t.conv2.weight], [_fold(t.conv2, t.bn2)], [0.0]),
-                "dec1": _Packed([c[0].weight], [_fold(c[0], c[1])], [0.0], k_pad_to=kin),
-                "dec2": _Packed([c[3].weight], [_fold(c[3], c[4])], [0.0]),
-                "dec3": _Packed([c[6].weight], [_fold(c[6], c[7])], [0.0]),
-                "dec4": _Packed([d.recon_head[0].weight], [_fold(d.recon_head[0], d.recon_head[1])], [0.0]),
-            }
+            dev = g.conv1.weight.device
+            with torch.no_grad():
+                ones = lambda n: torch.ones(n, device=dev)
+                zeros = lambda n: torch.zeros(n, device=dev)
+                w_l1 = ph.linear1.weight.detach()
+                bn5_scale = ph.bn5.weight.detach() * torch.rsqrt(ph.bn5.running_var + ph.bn5.eps)
+                self._packs = {
+                    # [rot_green.conv1 | rot_red.conv1 | ph_pred.conv_5 | ts.conv1] on [feat | xyz] (K = 1289)
+                    "stage1": _Packed([g.conv1.weight, r.conv1.weight, ph.conv_5[0].weight, t.conv1.weight],
+                                      [_fold(g.conv1, g.bn1), _fold(r.conv1, r.bn1), _fold(ph.conv_5[0], ph.conv_5[1]),
+                                       _fold(t.conv1, t.bn1)], [0.0, 0.0, 0.2, 0.0], k_pad_to=kin),
+                    "green2": _Packed([g.conv2.weight], [_fold(g.conv2, g.bn2)], [0.0]),
+                    "red2": _Packed([r.conv2.weight], [_fold(r.conv2, r.bn2)], [0.0]),
+                    "ts2": _Packed([t.conv2.weight], [_fold(t.conv2, t.bn2)], [0.0]),
+                    "dec1": _Packed([c[0].weight], [_fold(c[0], c[1])], [0.0], k_pad_to=kin),
+                    "dec2": _Packed([c[3].weight], [_fold(c[3], c[4])], [0.0]),
+                    "dec3": _Packed([c[6].weight], [_fold(c[6], c[7])], [0.0]),
+                    "dec4": _Packed([d.recon_head[0].weight], [_fold(d.recon_head[0], d.recon_head[1])], [0.0]),
+                    # per-cloud tails (M = batch): plain fp32 matrices for the skinny kernel
+                    # linear1 sees cat(pooled, pooled) (FaceRecon.py:146-149) = pooled @ (W[:, :1024] + W[:, 1024:])^T
+                    "ph_l1": ((w_l1[:, :1024] + w_l1[:, 1024:]).contiguous(), bn5_scale.contiguous(),
+                              (ph.bn5.bias.detach() - ph.bn5.running_mean * bn5_scale).contiguous(),
+                              torch.full((1024,), 0.2, device=dev)),
+                    "ph_l23": (torch.cat([ph.linear2.weight.detach(), ph.linear3.weight.detach()], 0).contiguous(),
+                               torch.cat([ph.linear2.bias.detach(), ph.linear3.bias.detach()]).contiguous()),
+                    "ph_l45": (torch.cat([ph.linear4.weight.detach(), ph.linear5.weight.detach()], 1).contiguous(),
+                               (ph.linear4.bias.detach() + ph.linear5.bias.detach()).contiguous()),
+                    "dec1_w": c[0].weight.detach().reshape(512, FEAT_C),
+                }
+                for name, head in (("green", g), ("red", r), ("ts", t)):
+                    sc, sh = _fold(head.conv3, head.bn3)
+                    self._packs[name + "3"] = (head.conv3.weight.detach().reshape(256, 256), sc.contiguous(), sh.contiguous())
+                    self._packs[name + "4"] = (head.conv4.weight.detach().reshape(head.k, 256), head.conv4.bias.detach())
             self._packs_key = key
         return self._packs
 
     @staticmethod
-    def _stage(pk, x_split, K, outs, M, **kw):
-        """one fused GEMM: column blocks of pk.w go to `outs` = [(n_cols, 'raw'|'split')]; returns the tensors."""
+    def _stage(pk, x_split, K, outs, M, rows_per_group=0, **kw):
+        """one fused GEMM: column blocks of pk.w go to `outs` = [(n_cols, 'raw'|'split'|'max')]; returns the tensors.
+        'max': per-cloud column max (torch.max over the points) taken in the epilogue, nothing else is written."""
         segs, res, c0 = [], [], 0
         dev = x_split.device
         for n, kind in outs:
             if kind == "raw":
                 t_ = torch.empty((M, n), dtype=torch.float32, device=dev)
                 segs.append((c0, c0 + n, t_, 0, 0))
+            elif kind == "max":
+                t_ = torch.full((M // rows_per_group, n), -2 ** 31, dtype=torch.int32, device=dev)
+                segs.append((c0, c0 + n, t_, 3, 0))
             else:
                 t_ = ops._split_buf(M, n, dev)
                 segs.append((c0, c0 + n, t_, 2, ops.kpad(n)))
             res.append(t_)
             c0 += n
         ops.gemm(None, pk.w, True, segs, scale=pk.scale, shift=pk.shift, neg_slope=pk.slope, K=K,
-                 A_split=x_split, B_split=pk.w_split, **kw)
+                 A_split=x_split, B_split=pk.w_split, rows_per_group=rows_per_group, **kw)
         return res
 
     def _forward_fused_eval(self, points, obj_id, enable_proj=False):
         mean = points.mean(dim=1, keepdim=True)
         centred = points - mean
         fa, g, r, t = self.face_all, self.rot_green, self.rot_red, self.ts
-        feat, feat_global = fa.encoder(centred, obj_id, enable_proj)
-        B, N, _ = feat.shape
+        enc = fa.encoder
+        B, N, _ = centred.shape
         M = B * N
+        parts = enc.encode(centred)
         pk = self._head_packs()
         kin = FEAT_C + 3
-        x = torch.cat([feat, centred], dim=2).view(M, kin)        # [feat | xyz]: Pose_Ts input (PoseNet9D.py:63)
-        xs = ops.split_tf32(x)
-        # stage 1: four 1286/1289 -> 1024 convolutions as one contraction over the shared operand
-        hg, hr, f5, ht = self._stage(pk["stage1"], xs, kin, [(1024, "split"), (1024, "split"), (1024, "raw"),
-                                                              (1024, "split")], M)
-        # PH_Predictor tail (FaceRecon.py:145-165); per-cloud, tiny
-        ph = fa.ph_pred
-        pooled = f5.view(B, N, 1024).max(dim=1)[0]
-        feat_all = F.leaky_relu(ph.bn5(ph.linear1(torch.cat((pooled, pooled), 1))), negative_slope=0.2)
-        pi1 = ph.linear2(feat_all)
-        pi2 = ph.linear3(feat_all)
-        h1, h2 = ph.ac2(pi1), ph.ac3(pi2)
-        cvec = ph.linear4(pi1) + ph.linear5(pi2)                  # (B,1286): added to every point's feature
+        # [feat | xyz] (Pose_Ts input, PoseNet9D.py:63) assembled straight into the tensor-core operand: upsampling
+        # gathers, one-hot broadcast and both torch.cat of the reference in one launch
+        src = enc.concat_sources(parts, enc.one_hot(obj_id, B), extra=[(centred.reshape(M, 3), None, 1)])
+        raw, xs = ops.concat_rows(src, B, N, want_raw=self.train_outputs, want_split=True)
+        # stage 1: four 1286/1289 -> 1024 convolutions as one contraction over the shared operand; conv_5's output is
+        # only ever max-pooled over the cloud (FaceRecon.py:145-146), so that pooling happens in the epilogue
+        hg, hr, f5max, ht = self._stage(pk["stage1"], xs, kin, [(1024, "split"), (1024, "split"), (1024, "max"),
+                                                                 (1024, "split")], M, rows_per_group=N)
+        pooled = ops.decode_max(f5max)
+        # PH_Predictor tail (FaceRecon.py:147-165): per-cloud (M = batch) contractions on the skinny kernel
+        w1, sc5, sh5, sl5 = pk["ph_l1"]
+        feat_all = ops.linear_nk(pooled, w1, scale=sc5, shift=sh5, neg_slope=sl5)      # linear1 + bn5 + leaky; dropout = id
+        w23, b23 = pk["ph_l23"]
+        pi12 = ops.linear_nk(feat_all, w23, bias=b23)                                   # [pi1 | pi2]
+        w45, b45 = pk["ph_l45"]
+        cvec = ops.linear_nk(pi12, w45, bias=b45)                                       # linear4(pi1) + linear5(pi2): (B,1286)
+        h1 = h2 = None
+        if self.train_outputs:
+            oc = fa.ph_pred.output_channels
+            h1, h2 = torch.sigmoid(pi12[:, :oc]), torch.sigmoid(pi12[:, oc:])
         # Face_Dec on feat + cvec: W.(feat + c) = W.feat + W.c  -> per-cloud bias in the epilogue
         dec = fa.decoder
-        w1 = dec.conv1d_block[0].weight.reshape(512, FEAT_C)
-        gb = ops.linear_nk(cvec.contiguous(), w1)
+        gb = ops.linear_nk(cvec, pk["dec1_w"])
         (d1,) = self._stage(pk["dec1"], xs, kin, [(512, "split")], M, group_bias=gb, rows_per_group=N)
         (d2,) = self._stage(pk["dec2"], d1, 512, [(512, "split")], M)
         (d3,) = self._stage(pk["dec3"], d2, 512, [(256, "split")], M)
@@ -311,17 +340,22 @@ class PoseNet9D(nn.Module):
         last = dec.recon_head[3]
         recon = ops.linear_nk(d4, last.weight.reshape(3, 128), bias=last.bias).view(B, N, 3)
 
-        def tail(head, hidden_split, pack):
-            (h,) = self._stage(pack, hidden_split, 1024, [(256, "raw")], M)
-            v = h.view(B, N, 256).max(dim=1)[0].unsqueeze(2)
-            v = F.relu(head.bn3(head.conv3(v)))
-            return head.conv4(head.drop1(v)).squeeze(2).contiguous()
+        def tail(name, hidden_split):
+            # conv2 + bn2 + relu, max over the points in the epilogue (PoseR.py:32-33); conv3 + bn3 + relu; conv4
+            (hm,) = self._stage(pk[name + "2"], hidden_split, 1024, [(256, "max")], M, rows_per_group=N)
+            w3, sc3, sh3 = pk[name + "3"]
+            v = ops.linear_nk(ops.decode_max(hm), w3, scale=sc3, shift=sh3, relu=True)
+            w4, b4 = pk[name + "4"]
+            return ops.linear_nk(v, w4, bias=b4)
 
-        green_R_vec = tail(g, hg, pk["green2"])
-        red_R_vec = tail(r, hr, pk["red2"])
-        ts_vec = tail(t, ht, pk["ts2"])
-        return self._assemble(green_R_vec, red_R_vec, ts_vec[:, 0:3], ts_vec[:, 3:6], mean, recon, h1, h2, feat,
-                              feat_global.max(2)[0])
+        green_R_vec = tail("green", hg)
+        red_R_vec = tail("red", hr)
+        ts_vec = tail("ts", ht)
+        feat = feat_global = None
+        if self.train_outputs:
+            feat = raw.view(B, N, kin)[:, :, :FEAT_C]
+            feat_global = feat.max(dim=1)[0]
+        return self._assemble(green_R_vec, red_R_vec, ts_vec[:, 0:3], ts_vec[:, 3:6], mean, recon, h1, h2, feat, feat_global)
 
     def _assemble(self, green_R_vec, red_R_vec, T, s, mean, recon, h1, h2, feat, feat_global):
         p_green_R = green_R_vec[:, 1:] / (torch.norm(green_R_vec[:, 1:], dim=1, keepdim=True) + 1e-6)
