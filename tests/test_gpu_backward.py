@@ -260,9 +260,11 @@ def test_full_size_backward_properties():
     torch.manual_seed(0)
     enc = Face_Enc().cuda().eval()
     gen = torch.Generator().manual_seed(9)
-    pts = torch.rand(4, 1028, 3, generator=gen).cuda()
-    cat = torch.randint(0, 6, (4, 1), generator=gen).float().cuda()
-    W = torch.randn(4, 1028, 1286, generator=gen).cuda() * 0.01
+    # 8 clouds, shards of 4: every level keeps >= 256 rows per call, so the same (tensor-core) kernels run in all
+    # three calls and a cloud's forward is bit-identical in each (DESIGN.md "Determinism")
+    pts = torch.rand(8, 1028, 3, generator=gen).cuda()
+    cat = torch.randint(0, 6, (8, 1), generator=gen).float().cuda()
+    W = torch.randn(8, 1028, 1286, generator=gen).cuda() * 0.01
     names = [n for n, _ in enc.named_parameters() if not n.startswith("proj_layer") and not n.startswith("bn")]
 
     def grads(lo, hi):
@@ -272,13 +274,13 @@ def test_full_size_backward_properties():
         (feat * W[lo:hi]).sum().backward()
         return {n: p.grad.detach().clone() for n, p in enc.named_parameters() if n in names}
 
-    full = grads(0, 4)
-    a, b = grads(0, 2), grads(2, 4)
+    full = grads(0, 8)
+    a, b = grads(0, 4), grads(4, 8)
     for n in names:
         assert torch.isfinite(full[n]).all(), n
         s = a[n] + b[n]
         scale = float(full[n].abs().max())
-        assert float((full[n] - s).abs().max()) <= 2e-3 * scale + 1e-7, (n, float((full[n] - s).abs().max()), scale)
+        assert float((full[n] - s).abs().max()) <= 1e-4 * scale + 1e-7, (n, float((full[n] - s).abs().max()), scale)
 
 
 # ----------------------------------------------------------------------------------------- loss tail + training step
@@ -325,8 +327,9 @@ def test_train_step_runs_and_learns():
         if "proj_layer" in n:
             continue
         assert p.grad is not None and torch.isfinite(p.grad).all(), n
-    last = first
-    for _ in range(8):
-        last = float(step(pts.cuda(), cat.cuda(), tgt))
-    assert np.isfinite(first) and np.isfinite(last)
-    assert last < first, (first, last)
+    hist = [first]
+    for _ in range(12):
+        hist.append(float(step(pts.cuda(), cat.cuda(), tgt)))
+    print("train-step losses:", " ".join(f"{v:.4f}" for v in hist))
+    assert all(np.isfinite(v) for v in hist)
+    assert min(hist[-4:]) < first, hist

@@ -40,7 +40,7 @@ def _orl_tail(feature, idx_xyz, conv2_w, f_ste, B, N, C, post, want_arg=False, f
         g, arg = ops.orl_global(feature, idx_xyz, want_arg=True)
     else:
         g, arg = ops.orl_global(feature, idx_xyz), None
-    gb = ops.linear_nk(g, w2[:, C:])
+    gb = ops.linear_nk(g, w2[:, C:], tc=False)      # one row per cloud: always the exact-fp32 kernel, whatever B
     out = torch.empty((B, N, C), dtype=torch.float32, device=feature.device)
     scale, shift, relu = post if post is not None else (None, None, False)
     f2 = feature.view(M, C)

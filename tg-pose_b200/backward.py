@@ -32,9 +32,9 @@ def _orl_tail_bwd(grad_out, out, post, feature, g, idx_xyz, arg_orl, conv2_w, B,
         gz = go
     w2 = conv2_w.detach().reshape(C, 2 * C)
     d_gb = ops.colsum(gz, rows_per_group=N)                       # (B, C): gradient of the per-cloud bias
-    dg = ops.matmul_kn(d_gb, w2[:, C:])                           # (B, C)
+    dg = ops.matmul_kn(d_gb, w2[:, C:], tc=False)                           # (B, C)
     d_w2 = torch.empty((C, 2 * C), dtype=torch.float32, device=dev)
-    ops.gemm_tn(d_gb, g, out=d_w2[:, C:])
+    ops.gemm_tn(d_gb, g, out=d_w2[:, C:], tc=False)
     ops.gemm_tn(gz, feature.view(M, C), out=d_w2[:, :C])
     d_sc = torch.zeros((B, N, C), dtype=torch.float32, device=dev)
     ops.gather_max_bwd(dg, idx_xyz, arg_orl, N, d_sc, per_cloud=True, scale=1.0 / N)

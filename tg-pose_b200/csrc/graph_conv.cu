@@ -169,13 +169,14 @@ surface_conv_kernel(const float* __restrict__ xyz, const IdxT* __restrict__ idx,
 
 // ------------------------------------------------------------------------------------------
 // layer conv.  CTA = (4-channel group cg, cloud b).  lane = s*4 + c4 (< S*4 <= 32).
-template <bool ARG>
+template <bool ARG, int KT>
 __global__ void __launch_bounds__(1024)
 layer_conv_kernel(const float4* __restrict__ rec, const float* __restrict__ directions,
                   const float* __restrict__ centre, long ld_centre, const float* __restrict__ slab,
-                  long M, int N, int k, int S, int C, float* __restrict__ out, uint8_t* __restrict__ arg_slab,
+                  long M, int N, int k_rt, int S, int C, float* __restrict__ out, uint8_t* __restrict__ arg_slab,
                   float* __restrict__ out_split, int kp) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int k = KT > 0 ? KT : k_rt;                      // neighbour count: compile-time for the encoder's 20 / 8
     const int W = S * 4;                                   // slab row width in floats
     float* tab = reinterpret_cast<float*>(smem_raw);       // [N][W]
     const size_t tab_bytes = (size_t)N * W * sizeof(float);
@@ -210,18 +211,30 @@ layer_conv_kernel(const float4* __restrict__ rec, const float* __restrict__ dire
 
     float4* my = recs + warp * k;
     const float inv_s = 1.0f / (float)S;
+    // byte address of this lane's column in table row 0; a neighbour's row is one integer add away
+    const uint32_t tab_lane = smem_u32(tab) + (uint32_t)(lane < W ? lane : 0) * 4u;
+    const uint32_t row_bytes = (uint32_t)W * 4u;
+    // the k edge records of the warp's next point are fetched while the current point is being reduced
+    const float4* rp = rec + (b * N + warp) * (long)k;
+    const long rstep = (long)nwarps * k;
+    float4 nxt = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (warp < N && lane < k) nxt = __ldg(rp + lane);
     for (int n = warp; n < N; n += nwarps) {
         const long pt = b * N + n;
         __syncwarp();
-        for (int j = lane; j < k; j += 32) my[j] = __ldg(rec + pt * k + j);
+        if (lane < k) my[lane] = nxt;
+        for (int j = lane + 32; j < k; j += 32) my[j] = __ldg(rp + j);
         __syncwarp();
+        rp += rstep;
+        if (n + nwarps < N && lane < k) nxt = __ldg(rp + lane);
         float m = -FLT_MAX;
         int a = 0;
         if (lane < W) {
-#pragma unroll 4
+#pragma unroll (KT > 0 ? KT : 4)
             for (int j = 0; j < k; ++j) {
                 const float4 d = my[j];
-                const float sup = tab[__float_as_int(d.w) * W + lane];
+                float sup;
+                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(sup) : "r"(tab_lane + (uint32_t)__float_as_int(d.w) * row_bytes));
                 const float th = fmaxf(fmaf(d.z, sz, fmaf(d.y, sy, d.x * sx)), 0.f);
                 const float v = th * sup;
                 if (ARG) { if (v > m) { m = v; a = j; } }
@@ -307,14 +320,18 @@ extern "C" int tgp_layer_conv_fwd(const float* edge_rec, const float* directions
     cudaStream_t st = as_stream(stream);
     const long M = (long)B * N;
     const int kp = (C + 31) / 32 * 32;
+#define TGP_LAUNCH_LC(ARGV, KTV)                                                                                        \
+    do {                                                                                                                \
+        cudaFuncSetAttribute(layer_conv_kernel<ARGV, KTV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);       \
+        layer_conv_kernel<ARGV, KTV><<<grid, threads, smem, st>>>(reinterpret_cast<const float4*>(edge_rec), directions, \
+                                                                  centre, ld_centre, support_slab, M, N, k, S, C, out,   \
+                                                                  arg_slab, out_split, kp);                              \
+    } while (0)
     if (arg_slab) {
-        cudaFuncSetAttribute(layer_conv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        layer_conv_kernel<true><<<grid, threads, smem, st>>>(reinterpret_cast<const float4*>(edge_rec), directions, centre,
-                                                           ld_centre, support_slab, M, N, k, S, C, out, arg_slab, out_split, kp);
+        if (k == 20) TGP_LAUNCH_LC(true, 20); else if (k == 8) TGP_LAUNCH_LC(true, 8); else TGP_LAUNCH_LC(true, 0);
     } else {
-        cudaFuncSetAttribute(layer_conv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        layer_conv_kernel<false><<<grid, threads, smem, st>>>(reinterpret_cast<const float4*>(edge_rec), directions, centre,
-                                                            ld_centre, support_slab, M, N, k, S, C, out, arg_slab, out_split, kp);
+        if (k == 20) TGP_LAUNCH_LC(false, 20); else if (k == 8) TGP_LAUNCH_LC(false, 8); else TGP_LAUNCH_LC(false, 0);
     }
+#undef TGP_LAUNCH_LC
     return check_launch("layer_conv_kernel");
 }

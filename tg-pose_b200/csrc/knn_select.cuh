@@ -74,4 +74,32 @@ struct WarpTopList {
 };
 
 
+// Two independent 32-entry lists advanced in lock step: the (shuffle-latency-bound) insertion chains of the two
+// queries are interleaved in one basic block, which doubles the instruction-level parallelism of the selection.
+// All control flow is warp-uniform; an exhausted side keeps executing with pos = 33 (no lane changes).
+struct WarpTopPair {
+    float dA, dB;
+    int iA, iB;
+    float thA, thB;
+
+    __device__ __forceinline__ void admit2(float ddA, float ddB, int base, int lane, int K) {
+        unsigned mA = __ballot_sync(FULL, ddA < thA), mB = __ballot_sync(FULL, ddB < thB);
+        while (mA | mB) {
+            const int sA = mA ? __ffs(mA) - 1 : 0, sB = mB ? __ffs(mB) - 1 : 0;
+            const float cdA = __shfl_sync(FULL, ddA, sA), cdB = __shfl_sync(FULL, ddB, sB);
+            const bool vA = mA != 0 && cdA < thA, vB = mB != 0 && cdB < thB;
+            mA &= mA - 1;
+            mB &= mB - 1;
+            const unsigned leA = __ballot_sync(FULL, dA <= cdA), leB = __ballot_sync(FULL, dB <= cdB);
+            const int posA = vA ? __popc(leA) : 33, posB = vB ? __popc(leB) : 33;
+            const float upA = __shfl_up_sync(FULL, dA, 1), upB = __shfl_up_sync(FULL, dB, 1);
+            const int upiA = __shfl_up_sync(FULL, iA, 1), upiB = __shfl_up_sync(FULL, iB, 1);
+            if (lane > posA) { dA = upA; iA = upiA; } else if (lane == posA) { dA = cdA; iA = base + sA; }
+            if (lane > posB) { dB = upB; iB = upiB; } else if (lane == posB) { dB = cdB; iB = base + sB; }
+            thA = __shfl_sync(FULL, dA, K - 1);
+            thB = __shfl_sync(FULL, dB, K - 1);
+        }
+    }
+};
+
 }  // namespace tgp

@@ -10,8 +10,8 @@
 //   warp 1      tcgen05.mma kind::tf32 128x128x8, three passes lo.hi + hi.lo + hi.hi (3xTF32: fp32-level inner
 //               products, error << the reference formula's own rounding bound, SURVEY 8c rule 3) into a
 //               double-buffered TMEM accumulator: the MMA of candidate tile t+1 overlaps the selection of tile t
-//   warps 2-9   tcgen05.ld -> d = ((inner * -2) + q_j) + q_i (gcn3d.py:20, same rounding order) -> 128x128 distance
-//               tile in shared memory -> each warp owns 16 queries whose sorted (distance, index) lists live in
+//   warps 2-17  tcgen05.ld -> d = ((inner * -2) + q_j) + q_i (gcn3d.py:20, same rounding order) -> 128x128 distance
+//               tile in shared memory -> each warp owns 8 queries (two at a time, interleaved) whose sorted (distance, index) lists live in
 //               registers across all candidate tiles (knn_select.cuh), ascending (distance, index).
 // Padding: rows of a tile that belong to the next cloud / lie past the end are masked through q_j = +inf.
 #include "knn_select.cuh"
@@ -21,7 +21,7 @@ namespace tgp {
 
 constexpr int KT_STAGES = 4;
 constexpr int KT_BN = 128;
-constexpr int KT_EPI_WARPS = 8;
+constexpr int KT_EPI_WARPS = 16;
 constexpr int KT_THREADS = 64 + 32 * KT_EPI_WARPS;
 constexpr int KT_QPW = TC_BM / KT_EPI_WARPS;            // queries per selection warp (16)
 constexpr int KT_LDD = KT_BN + 4;                       // distance tile pitch (floats)
@@ -125,7 +125,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
         // ===================== distance tile + selection (warps 2..9) =====================
         const int e = warp - 2;                    // selection warp 0..7: queries e, e+8, ...
         const int quarter = warp & 3;              // TMEM lane quarter this warp may read
-        const int half = e >> 2;                   // which 64-column half of the accumulator it converts
+        const int chunk = e >> 2;                  // which 32-column chunk of the accumulator it converts (4 warps / quarter)
         const int et = threadIdx.x - 64;           // 0..255
         const int my_row = quarter * 32 + lane;    // query row of this thread in the TMEM layout
         int it = 0;
@@ -150,9 +150,8 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
                 const int c0 = ct * KT_BN;
                 tc_mbar_wait(tmem_full + acc, acc_phase);
                 tc_fence_after();
-#pragma unroll 1
-                for (int ch = 0; ch < 2; ++ch) {
-                    const int cc = half * 64 + ch * 32;
+                {
+                    const int cc = chunk * 32;
                     uint32_t r[32];
                     const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * KT_BN + cc);
                     TMEM_LD_32x32(taddr, r);
@@ -175,16 +174,19 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
                 if (lane == 0) tc_mbar_arrive(tmem_empty + acc);
                 epi_bar_sync();                    // distance tile complete
 #pragma unroll
-                for (int i = 0; i < KT_QPW; ++i) {
-                    const int ql = e + KT_EPI_WARPS * i;
-                    if (ql < nq) {
-                        WarpTopList<1> top;
-                        top.d[0] = td[i]; top.i[0] = ti[i];
-                        float t = th[i];
-                        const float* drow = Ds + ql * KT_LDD;
+                for (int i = 0; i < KT_QPW; i += 2) {
+                    const int qa = e + KT_EPI_WARPS * i, qb2 = qa + KT_EPI_WARPS;
+                    if (qa < nq) {
+                        // rows past nq hold other clouds' queries: harmless, their lists are never stored
+                        WarpTopPair pr;
+                        pr.dA = td[i]; pr.iA = ti[i]; pr.thA = th[i];
+                        pr.dB = td[i + 1]; pr.iB = ti[i + 1]; pr.thB = th[i + 1];
+                        const float* ra = Ds + qa * KT_LDD;
+                        const float* rb = Ds + qb2 * KT_LDD;
 #pragma unroll
-                        for (int j0 = 0; j0 < KT_BN; j0 += 32) top.admit(drow[j0 + lane], c0 + j0, lane, t, K);
-                        td[i] = top.d[0]; ti[i] = top.i[0]; th[i] = t;
+                        for (int j0 = 0; j0 < KT_BN; j0 += 32) pr.admit2(ra[j0 + lane], rb[j0 + lane], c0 + j0, lane, K);
+                        td[i] = pr.dA; ti[i] = pr.iA; th[i] = pr.thA;
+                        td[i + 1] = pr.dB; ti[i + 1] = pr.iB; th[i + 1] = pr.thB;
                     }
                 }
                 epi_bar_sync();                    // selection done: Ds may be overwritten

@@ -321,18 +321,18 @@ class PoseNet9D(nn.Module):
         pooled = ops.decode_max(f5max)
         # PH_Predictor tail (FaceRecon.py:147-165): per-cloud (M = batch) contractions on the skinny kernel
         w1, sc5, sh5, sl5 = pk["ph_l1"]
-        feat_all = ops.linear_nk(pooled, w1, scale=sc5, shift=sh5, neg_slope=sl5)      # linear1 + bn5 + leaky; dropout = id
+        feat_all = ops.linear_nk(pooled, w1, scale=sc5, shift=sh5, neg_slope=sl5, tc=False)      # linear1 + bn5 + leaky; dropout = id
         w23, b23 = pk["ph_l23"]
-        pi12 = ops.linear_nk(feat_all, w23, bias=b23)                                   # [pi1 | pi2]
+        pi12 = ops.linear_nk(feat_all, w23, bias=b23, tc=False)                                   # [pi1 | pi2]
         w45, b45 = pk["ph_l45"]
-        cvec = ops.linear_nk(pi12, w45, bias=b45)                                       # linear4(pi1) + linear5(pi2): (B,1286)
+        cvec = ops.linear_nk(pi12, w45, bias=b45, tc=False)                                       # linear4(pi1) + linear5(pi2): (B,1286)
         h1 = h2 = None
         if self.train_outputs:
             oc = fa.ph_pred.output_channels
             h1, h2 = torch.sigmoid(pi12[:, :oc]), torch.sigmoid(pi12[:, oc:])
         # Face_Dec on feat + cvec: W.(feat + c) = W.feat + W.c  -> per-cloud bias in the epilogue
         dec = fa.decoder
-        gb = ops.linear_nk(cvec, pk["dec1_w"])
+        gb = ops.linear_nk(cvec, pk["dec1_w"], tc=False)
         (d1,) = self._stage(pk["dec1"], xs, kin, [(512, "split")], M, group_bias=gb, rows_per_group=N)
         (d2,) = self._stage(pk["dec2"], d1, 512, [(512, "split")], M)
         (d3,) = self._stage(pk["dec3"], d2, 512, [(256, "split")], M)
@@ -344,9 +344,9 @@ class PoseNet9D(nn.Module):
             # conv2 + bn2 + relu, max over the points in the epilogue (PoseR.py:32-33); conv3 + bn3 + relu; conv4
             (hm,) = self._stage(pk[name + "2"], hidden_split, 1024, [(256, "max")], M, rows_per_group=N)
             w3, sc3, sh3 = pk[name + "3"]
-            v = ops.linear_nk(ops.decode_max(hm), w3, scale=sc3, shift=sh3, relu=True)
+            v = ops.linear_nk(ops.decode_max(hm), w3, scale=sc3, shift=sh3, relu=True, tc=False)
             w4, b4 = pk[name + "4"]
-            return ops.linear_nk(v, w4, bias=b4)
+            return ops.linear_nk(v, w4, bias=b4, tc=False)
 
         green_R_vec = tail("green", hg)
         red_R_vec = tail("red", hr)
