@@ -27,7 +27,9 @@
 
 namespace tgp {
 
-constexpr int TC_STAGES = 4;
+// operand ring depth: as many stages as fit in ~192 KB, so that narrow tiles (short, latency-bound mainloops) keep
+// as many bytes in flight as wide ones: BN 256 -> 4 x 48 KB, BN 128 -> 6 x 32 KB, BN 64 -> 8 x 24 KB
+template <int BN> struct TcStages { static constexpr int value = (192 * 1024) / (TC_BM * TC_BK * 4 + BN * TC_BK * 4); };
 constexpr int TC_EPI_WARPS = 8;
 constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;   // TMA warp + MMA warp + epilogue warps
 
@@ -61,7 +63,7 @@ __device__ __forceinline__ void epi_store(EpiDst& d, float v) {
     }
 }
 
-// rows of one 32-column chunk: lane = column.  Loads (shared-memory staging + residuals) for 8 rows are issued
+// rows of one 32-column chunk: lane = column.  Loads (shared-memory staging + residuals) for 16 rows are issued
 // before any of their stores so that the global loads overlap (ncu round 1: the row-at-a-time loop stalled on
 // long_scoreboard for every residual load).
 template <bool D1, bool MX>
@@ -71,22 +73,22 @@ __device__ __forceinline__ void epi_rows(uint32_t stg_addr, int lane, int nrows,
     float mx0 = -CUDART_INF_F, mx1 = -CUDART_INF_F;
     const bool is_max = MX && d0.lo < 0;
 #pragma unroll 1
-    for (int rr0 = 0; rr0 < nrows; rr0 += 8) {
-        float a[8];
+    for (int rr0 = 0; rr0 < nrows; rr0 += 16) {
+        float a[16];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) a[u] = lds_f32(stg_addr + (uint32_t)(((rr0 + u) * 33 + lane) * 4)) + bias;
+        for (int u = 0; u < 16; ++u) a[u] = lds_f32(stg_addr + (uint32_t)(((rr0 + u) * 33 + lane) * 4)) + bias;
         if (r1p) {
 #pragma unroll
-            for (int u = 0; u < 8; ++u)
+            for (int u = 0; u < 16; ++u)
                 if (rr0 + u < nrows) a[u] += __ldg(r1p + (long)(rr0 + u) * ld1);
         }
         if (r2p) {
 #pragma unroll
-            for (int u = 0; u < 8; ++u)
+            for (int u = 0; u < 16; ++u)
                 if (rr0 + u < nrows) a[u] += __ldg(r2p + (long)(rr0 + u) * ld2);
         }
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
+        for (int u = 0; u < 16; ++u) {
             if (rr0 + u < nrows) {
                 float v = a[u] + ((rr0 + u) >= gb_switch ? gbv1 : gbv0);
                 v = fmaf(v, sc, sh);
@@ -107,13 +109,170 @@ __device__ __forceinline__ void epi_rows(uint32_t stg_addr, int lane, int nrows,
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// vectorised epilogue of one 32-row x 32-column chunk (the common case: every column count, segment boundary and
+// leading dimension a multiple of 4 and every pointer 16-byte aligned -- checked on the host, `vec_ok`).
+// ncu, round 1: the scalar epilogue (lane = column, one row per instruction) ran ~3000 latency-bound instructions per
+// chunk and warp -- 35-40 us per output tile with only 8 epilogue warps resident, which bounded every small GEMM.
+// Here the chunk is staged with an XOR swizzle (conflict-free 128-bit writes by row and reads by (row, 4 columns)),
+// a lane owns 4 consecutive columns, a warp instruction covers 4 rows, and all global traffic is 128-bit.
+struct VDst {
+    float* p;      // (row0, first column of this lane)
+    long rs;       // row stride
+    int kind;      // 0 none, 1 raw, 2 split, 3 column max
+    int lo;        // split: offset of the residual half
+};
+
+__device__ __forceinline__ float4 ldg4s(const float* p) {   // 4 scalar loads: parameter vectors may be unaligned views
+    return make_float4(__ldg(p), __ldg(p + 1), __ldg(p + 2), __ldg(p + 3));
+}
+__device__ __forceinline__ float4 f4add(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+__device__ __forceinline__ float act1(float v, float sc, float sh, float sl) {
+    v = fmaf(v, sc, sh);
+    return v > 0.f ? v : v * sl;
+}
+__device__ __forceinline__ void vstore(const VDst& d, int row, float4 v) {
+    if (d.kind == 1) {
+        *reinterpret_cast<float4*>(d.p + row * d.rs) = v;
+    } else if (d.kind == 2) {
+        float4 hi, lo;
+        uint32_t hb;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v.x)); hi.x = __uint_as_float(hb); lo.x = v.x - hi.x;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v.y)); hi.y = __uint_as_float(hb); lo.y = v.y - hi.y;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v.z)); hi.z = __uint_as_float(hb); lo.z = v.z - hi.z;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v.w)); hi.w = __uint_as_float(hb); lo.w = v.w - hi.w;
+        float* q = d.p + row * d.rs;
+        *reinterpret_cast<float4*>(q) = hi;
+        *reinterpret_cast<float4*>(q + d.lo) = lo;
+    }
+}
+
+__device__ __forceinline__ void epi_chunk_vec(const tgp_gemm_args& g, uint32_t stg_addr, const uint32_t (&r)[32], int lane,
+                                              long row0, int nrows, int colbase, long grp0, int gb_switch, long zoff) {
+    // stage: thread = row writes its 32 columns as 8 float4, slot j ^ (row & 7) of its 128-byte line
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const uint32_t ad = stg_addr + (uint32_t)(lane * 128 + ((j ^ (lane & 7)) << 4));
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(ad), "r"(r[4 * j]), "r"(r[4 * j + 1]),
+                     "r"(r[4 * j + 2]), "r"(r[4 * j + 3]) : "memory");
+    }
+    __syncwarp();
+    const int c4i = lane & 7, rsub = lane >> 3;
+    const int col = colbase + c4i * 4;
+    const bool live = col < g.Ncols;
+    float4 bias = make_float4(0.f, 0.f, 0.f, 0.f), sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = bias, gb0 = bias, gb1 = bias;
+    const float s0 = g.relu ? 0.f : 1.f;
+    float4 sl = make_float4(s0, s0, s0, s0);
+    VDst d0 = {nullptr, 0, 0, 0}, d1 = {nullptr, 0, 0, 0};
+    const float* r1p = nullptr;
+    const float* r2p = nullptr;
+    if (live) {
+        if (g.bias) bias = ldg4s(g.bias + col);
+        if (g.scale) { sc = ldg4s(g.scale + col); sh = ldg4s(g.shift + col); }
+        if (g.neg_slope) sl = ldg4s(g.neg_slope + col);
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+            if (s < g.nseg && col >= g.seg[s].col_begin && col < g.seg[s].col_end) {
+                const int rel = col - g.seg[s].col_begin;
+                VDst d;
+                d.lo = 0;
+                if (g.seg[s].mode == 3) {
+                    d.kind = 3;
+                    d.rs = g.seg[s].col_end - g.seg[s].col_begin;
+                    d.p = g.seg[s].ptr + grp0 * d.rs + rel;
+                } else if (g.seg[s].mode == 1) {
+                    const int w = g.seg[s].slab_width;
+                    const int cg = rel / w, rr = rel - cg * w;
+                    d.kind = 1;
+                    d.rs = w;
+                    d.p = g.seg[s].ptr + ((long)cg * g.M + row0) * w + rr;
+                } else {
+                    d.kind = g.seg[s].mode == 2 ? 2 : 1;
+                    d.rs = g.seg[s].ld;
+                    d.p = g.seg[s].ptr + zoff + row0 * d.rs + rel;
+                    d.lo = g.seg[s].slab_width;
+                }
+                if (!d0.kind) d0 = d; else d1 = d;
+            }
+        }
+        if (g.group_bias) {
+            gb0 = ldg4s(g.group_bias + grp0 * g.Ncols + col);
+            if (gb_switch < nrows) gb1 = ldg4s(g.group_bias + (grp0 + 1) * g.Ncols + col);
+        }
+        if (g.res1) r1p = g.res1 + row0 * g.ld_res1 + col;
+        if (g.res2) r2p = g.res2 + row0 * g.ld_res2 + col;
+    }
+    float4 mx0 = make_float4(-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F), mx1 = mx0;
+    const bool any_max = d0.kind == 3 || d1.kind == 3;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        float4 a[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int row = (half * 4 + u) * 4 + rsub;
+            const uint32_t ad = stg_addr + (uint32_t)(row * 128 + ((c4i ^ (row & 7)) << 4));
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a[u].x), "=f"(a[u].y), "=f"(a[u].z), "=f"(a[u].w) : "r"(ad));
+        }
+        float4 q1[4], q2[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int row = (half * 4 + u) * 4 + rsub;
+            q1[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            q2[u] = q1[u];
+            if (row < nrows) {
+                if (r1p) q1[u] = __ldg(reinterpret_cast<const float4*>(r1p + (long)row * g.ld_res1));
+                if (r2p) q2[u] = __ldg(reinterpret_cast<const float4*>(r2p + (long)row * g.ld_res2));
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int row = (half * 4 + u) * 4 + rsub;
+            if (live && row < nrows) {
+                const bool second = row >= gb_switch;
+                float4 v = f4add(f4add(f4add(a[u], bias), f4add(q1[u], q2[u])), second ? gb1 : gb0);
+                v.x = act1(v.x, sc.x, sh.x, sl.x); v.y = act1(v.y, sc.y, sh.y, sl.y);
+                v.z = act1(v.z, sc.z, sh.z, sl.z); v.w = act1(v.w, sc.w, sh.w, sl.w);
+                vstore(d0, row, v);
+                vstore(d1, row, v);
+                if (any_max) {
+                    float4& m = second ? mx1 : mx0;
+                    m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
+                }
+            }
+        }
+    }
+    if (__any_sync(0xffffffffu, any_max)) {
+        // combine the 4 row sub-groups (lanes differing in bits 3, 4), then one atomicMax per column and group
+#pragma unroll
+        for (int o = 8; o <= 16; o <<= 1) {
+            mx0.x = fmaxf(mx0.x, __shfl_xor_sync(0xffffffffu, mx0.x, o)); mx0.y = fmaxf(mx0.y, __shfl_xor_sync(0xffffffffu, mx0.y, o));
+            mx0.z = fmaxf(mx0.z, __shfl_xor_sync(0xffffffffu, mx0.z, o)); mx0.w = fmaxf(mx0.w, __shfl_xor_sync(0xffffffffu, mx0.w, o));
+            mx1.x = fmaxf(mx1.x, __shfl_xor_sync(0xffffffffu, mx1.x, o)); mx1.y = fmaxf(mx1.y, __shfl_xor_sync(0xffffffffu, mx1.y, o));
+            mx1.z = fmaxf(mx1.z, __shfl_xor_sync(0xffffffffu, mx1.z, o)); mx1.w = fmaxf(mx1.w, __shfl_xor_sync(0xffffffffu, mx1.w, o));
+        }
+        if (any_max && live && rsub == 0 && nrows > 0) {
+            const VDst& dm = d0.kind == 3 ? d0 : d1;
+            int* cell = reinterpret_cast<int*>(dm.p);
+            atomicMax(cell, enc_ordered(mx0.x)); atomicMax(cell + 1, enc_ordered(mx0.y));
+            atomicMax(cell + 2, enc_ordered(mx0.z)); atomicMax(cell + 3, enc_ordered(mx0.w));
+            if (gb_switch < nrows) {
+                cell += dm.rs;
+                atomicMax(cell, enc_ordered(mx1.x)); atomicMax(cell + 1, enc_ordered(mx1.y));
+                atomicMax(cell + 2, enc_ordered(mx1.z)); atomicMax(cell + 3, enc_ordered(mx1.w));
+            }
+        }
+    }
+    __syncwarp();
+}
+
 template <int BN>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ GemmDev P, int Kp, int num_n_tiles, int num_tiles, int dbg,
-               int tiles_mn, int kb_per, long zstride) {
+               int tiles_mn, int kb_per, long zstride, int vec_ok) {
     extern __shared__ __align__(1024) unsigned char tc_smem[];
     constexpr int B_BYTES = BN * TC_BK * 4;
+    constexpr int TC_STAGES = TcStages<BN>::value;
     constexpr int STAGE_BYTES = TC_A_BYTES + B_BYTES;
     // carve: [stages x (A | B)] [barriers] [tmem ptr]
     unsigned char* base = reinterpret_cast<unsigned char*>(((uintptr_t)tc_smem + 1023) & ~(uintptr_t)1023);
@@ -239,6 +398,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 TMEM_LD_32x32(taddr, r);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                 __syncwarp();
+                if (vec_ok && !gb_slow && !(dbg & 1)) {
+                    epi_chunk_vec(g, stg_addr, r, lane, row0, nrows, n0 + c0, grp0, gb_switch, z * zstride);
+                    continue;
+                }
 #pragma unroll
                 for (int j = 0; j < 32; ++j) sts_f32(stg_addr + (uint32_t)((lane * 33 + j) * 4), __uint_as_float(r[j]));
                 __syncwarp();
@@ -415,16 +578,30 @@ static int launch_tc(const tgp_gemm_args* a, cudaStream_t st, int ksplit = 1) {
     ksplit = (kblocks + kb_per - 1) / kb_per;          // no empty slices
     const int num_tiles = tiles_mn * ksplit;
     const long zstride = ksplit > 1 ? a->M * (long)a->seg[0].ld : 0;
-    const size_t smem = (size_t)TC_STAGES * (TC_A_BYTES + BN * TC_BK * 4) + 1024 + 256 + TC_EPI_WARPS * 32 * 33 * sizeof(float);
+    const size_t smem = (size_t)TcStages<BN>::value * (TC_A_BYTES + BN * TC_BK * 4) + 1024 + 256 + TC_EPI_WARPS * 32 * 33 * sizeof(float);
     static bool attr_set = false;
     if (!attr_set) {
         cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         attr_set = true;
     }
     const int grid = num_tiles < TGP_NUM_SMS ? num_tiles : TGP_NUM_SMS;
+    // 128-bit epilogue: every width / boundary / leading dimension a multiple of 4 floats, every pointer 16-byte aligned
+    auto al16 = [](const void* q) { return ((uintptr_t)q & 15) == 0; };
+    int vec_ok = (a->Ncols % 4 == 0);
+    if (a->res1) vec_ok = vec_ok && al16(a->res1) && a->ld_res1 % 4 == 0;
+    if (a->res2) vec_ok = vec_ok && al16(a->res2) && a->ld_res2 % 4 == 0;
+    for (int s = 0; s < a->nseg; ++s) {
+        const tgp_out_seg& sg = a->seg[s];
+        vec_ok = vec_ok && sg.col_begin % 4 == 0 && sg.col_end % 4 == 0;
+        if (sg.mode == 3) continue;
+        vec_ok = vec_ok && al16(sg.ptr);
+        if (sg.mode == 1) vec_ok = vec_ok && sg.slab_width % 4 == 0;
+        else vec_ok = vec_ok && sg.ld % 4 == 0 && (sg.mode != 2 || sg.slab_width % 4 == 0);
+    }
+    { const char* e = getenv("TGP_TC_SCALAR_EPI"); if (e && e[0] == '1') vec_ok = 0; }
     static int dbg = -1;
     if (dbg < 0) { const char* e = getenv("TGP_TC_DEBUG"); dbg = e ? atoi(e) : 0; }
-    gemm_tc_kernel<BN><<<grid, TC_THREADS, smem, st>>>(tmA, tmB, P, Kp, num_n_tiles, num_tiles, dbg, tiles_mn, kb_per, zstride);
+    gemm_tc_kernel<BN><<<grid, TC_THREADS, smem, st>>>(tmA, tmB, P, Kp, num_n_tiles, num_tiles, dbg, tiles_mn, kb_per, zstride, vec_ok);
     return check_launch("gemm_tc_kernel");
 }
 

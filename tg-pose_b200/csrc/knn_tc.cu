@@ -196,8 +196,10 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
                 const int ql = e + KT_EPI_WARPS * i;
                 if (ql < nq && lane >= 1 && lane <= k) {
                     const size_t o = ((size_t)b * N + q0 + ql) * k + lane - 1;
-                    if (idx64) idx64[o] = ti[i];
-                    if (idx32) idx32[o] = ti[i];
+                    // (a rank can only stay unfilled if a distance was NaN; never hand -1 to the gathers)
+                    const int v = ti[i] < 0 ? 0 : ti[i];
+                    if (idx64) idx64[o] = v;
+                    if (idx32) idx32[o] = v;
                 }
             }
         }
