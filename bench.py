@@ -179,10 +179,21 @@ def run_ours(args):
     dev_sets = [(p.to(dev), c.to(dev)) for p, c in host_sets]
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)   # > 126 MB L2
 
-    def step(pts, cat):
+    def eager_step(pts, cat):
         torch.manual_seed(7)          # Pool_layer draws its permutation from the CPU generator (gcn3d.py:242)
         with torch.no_grad():
             return net(pts, cat)
+
+    graphed = None
+    if not args.no_graph:
+        from tgpose_b200.graph import GraphedPoseNet
+        graphed = GraphedPoseNet(net, B, N_PTS)
+
+    def step(pts, cat):
+        if graphed is None:
+            return eager_step(pts, cat)
+        torch.manual_seed(7)
+        return graphed(pts, cat)      # copies the inputs into the graph's static buffers, draws the perms, replays
 
     def barrier():
         if world > 1:
@@ -194,12 +205,24 @@ def run_ours(args):
     barrier()
 
     # ---- device-resident timing: K steps, CUDA events per step, L2 flushed between steps
+    # ---- per-kernel table: an EAGER pass of the same steps with CUDA events around every C-ABI call (a graph replay
+    # cannot be instrumented per call); the launches counted here are the ones each graph replay re-issues
+    event_log = None
+    kt_steps = min(args.steps, 5)
+    l0 = _lib.launch_count()
+    if rank == 0:
+        ops.EVENT_LOG = {}
+    for i in range(kt_steps):
+        flush.zero_()
+        eager_step(*dev_sets[i % n_sets])
+    barrier()
+    event_log, ops.EVENT_LOG = ops.EVENT_LOG, None
+    launches_per_step = (_lib.launch_count() - l0) // kt_steps
+
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    ops.EVENT_LOG = {} if rank == 0 else None
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    l0 = _lib.launch_count()
     barrier()
     wall0 = time.perf_counter()
     for i in range(args.steps):
@@ -209,8 +232,7 @@ def run_ours(args):
         ev[i][1].record()
     barrier()
     wall = time.perf_counter() - wall0
-    launches = _lib.launch_count() - l0
-    event_log, ops.EVENT_LOG = ops.EVENT_LOG, None
+    launches = launches_per_step * args.steps
     dev_ms = sum(a.elapsed_time(b) for a, b in ev)
 
     # ---- end to end: pinned host inputs -> H2D -> forward -> D2H of the pose outputs, every step
@@ -222,9 +244,10 @@ def run_ours(args):
     e0.record()
     for i in range(args.steps):
         hp, hc = host_sets[i % n_sets]
-        p = hp.to(dev, non_blocking=True)
-        c = hc.to(dev, non_blocking=True)
-        out = step(p, c)
+        if graphed is None:
+            out = step(hp.to(dev, non_blocking=True), hc.to(dev, non_blocking=True))
+        else:
+            out = step(hp, hc)        # pinned host -> the graph's static input buffers (H2D inside the timed region)
         res = torch.cat([out[k].reshape(B, -1) for k in out_keys], dim=1).cpu()
         if i == 0:
             h2d = hp.numel() * 4 + hc.numel() * 4
@@ -249,14 +272,15 @@ def run_ours(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "full TG-Pose network forward (Face_Enc 3D-GCN + heads), 32 x 1028 points per GPU",
                        "points": N_PTS, "per_gpu_batch": B, "global_batch": total, "parallelism": f"dp{world}",
-                       "weights": "random-init (seed 0)", "l2": "256 MB flush write between timed steps"},
+                       "weights": "random-init (seed 0)", "l2": "256 MB flush write between timed steps",
+                       "launch": "CUDA graph replay of the whole forward" if graphed is not None else "eager launches"},
             "e2e": {"value": total / (e2e_ms / args.steps / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "wall_s": wall,
         }
-        line.update(kernel_report(event_log, args.steps, B, peaks))
+        line.update(kernel_report(event_log, kt_steps, B, peaks))
         if world == 1 and not args.no_cpu_baseline:
             r = cpu_port_run(2, 2, 1)
             line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
@@ -355,6 +379,72 @@ def run_train(args):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------------------------------------ microbench sweep
+def run_micro(args):
+    """BASELINE.json configs[3]: kNN + Conv_surface / Conv_layer sweep, N = 1028..16384, k = 10..50, S = 7, C = 128,
+    D in {3, 128}; CUDA events, L2 flushed between iterations; per-kernel roofline fractions (SURVEY 8d work counts)."""
+    import torch
+    from tgpose_b200 import _lib, ops
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    _lib.load()
+    dev = torch.device("cuda", 0)
+    peaks = measured_peaks()
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
+    S, C, D = 7, 128, 128
+    rows = []
+
+    def timed(fn, iters):
+        fn()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(iters):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        ts.sort()
+        return ts[len(ts) // 2] / 1e3
+
+    g = torch.Generator().manual_seed(1234)
+    for N in (1028, 2048, 4096, 8192, 16384):
+        B = max(1, (32 * 1028) // N)
+        xyz = torch.rand(B, N, 3, generator=g).to(dev)
+        feat = (torch.randn(B, N, D, generator=g) * 0.3).to(dev)
+        dirs = ((torch.rand(3, S * C, generator=g) - 0.5) * 0.07).to(dev)
+        M = B * N
+        slab = torch.randn(C // 4, M, S * 4, generator=g).to(dev)
+        centre = torch.randn(M, C, generator=g).to(dev)
+        for k in (10, 20, 30, 40, 50):
+            it = 5 if N >= 8192 else 10
+            t_xyz = timed(lambda: ops.knn_xyz(xyz, k, want64=False, want32=True), it)
+            t_feat = timed(lambda: ops.knn_feat(feat, k, want64=False, want32=True), it)
+            idx = ops.knn_xyz(xyz, k, want64=False, want32=True)[1]
+            t_surf = timed(lambda: ops.surface_conv(xyz, idx, dirs, S, C), it)
+            rec = ops.edge_records(xyz, idx)
+            t_lay = timed(lambda: ops.layer_conv(rec, dirs, centre, slab, B, N, S, C), it)
+            f_xyz = B * (N * N * (2 * 3 + 3) + N * N)
+            f_feat = B * (N * N * (2 * D + 3) + N * N)
+            f_surf = B * (N * k * S * C * 8 + N * S * C)
+            f_lay = B * (N * k * S * C * 9 + N * S * C)
+            b_lay = B * (4 * (3 * N + S * C * N + C * N + C * N + 3 * S * C) + 4 * N * k)
+            rows.append({"N": N, "B": B, "k": k,
+                         "knn_xyz": {"ms": t_xyz * 1e3, "gpairs_s": B * N * N / t_xyz / 1e9, "fp32_frac": f_xyz / t_xyz / 1e12 / FP32_PEAK_TFLOPS},
+                         "knn_feat_D128": {"ms": t_feat * 1e3, "gpairs_s": B * N * N / t_feat / 1e9, "tflops": f_feat / t_feat / 1e12,
+                                           "fp32_frac": f_feat / t_feat / 1e12 / FP32_PEAK_TFLOPS,
+                                           "path": "tcgen05 3xTF32 + warp select" if k <= 31 else "fp32 FMA tile + warp select"},
+                         "surface_conv": {"ms": t_surf * 1e3, "tflops": f_surf / t_surf / 1e12, "fp32_frac": f_surf / t_surf / 1e12 / FP32_PEAK_TFLOPS},
+                         "layer_conv": {"ms": t_lay * 1e3, "tflops": f_lay / t_lay / 1e12, "fp32_frac": f_lay / t_lay / 1e12 / FP32_PEAK_TFLOPS,
+                                        "hbm_gbs": b_lay / t_lay / 1e9, "hbm_frac": b_lay / t_lay / 1e9 / peaks["hbm_gbs"],
+                                        "table": "smem" if N * S * 16 <= 215 * 1024 else "L2 gather"}})
+    print(json.dumps({"metric": "kNN + Conv_surface/Conv_layer microbench sweep", "S": S, "C": C, "D": D,
+                      "fp32_peak_tflops": FP32_PEAK_TFLOPS, "hbm_peak_gbs": peaks["hbm_gbs"], "peak_source": peaks["source"],
+                      "timing": "median of CUDA-event times, 256 MB L2 flush before each iteration", "rows": rows}), flush=True)
+
+
 def kernel_report(event_log, steps, B, peaks):
     """Per-kernel device time inside the timed steps (CUDA events around each C-ABI call on the launching
     stream) -> share of the step and roofline of the dominant kernel (algorithmic work: DESIGN.md / SURVEY 8d)."""
@@ -419,7 +509,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=PER_GPU_BATCH, help="clouds per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--mode", default="infer", choices=["infer", "train"],
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--mode", default="infer", choices=["infer", "train", "micro"],
                     help="infer: BASELINE.json configs[1] (the headline); train: configs[2], a secondary line")
     ap.add_argument("--train-batch", type=int, default=256, help="global batch of the training step")
     args = ap.parse_args()
@@ -428,6 +519,8 @@ def main():
         run_reference(args)
     elif args.mode == "train":
         run_train(args)
+    elif args.mode == "micro":
+        run_micro(args)
     else:
         run_ours(args)
 

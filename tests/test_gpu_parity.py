@@ -90,7 +90,7 @@ def test_knn_feat_golden(ops, tag, D):
     assert any_ <= 0.03 * mine.shape[0] * mine.shape[1]
 
 
-@pytest.mark.parametrize("B,N,D,k", [(4, 1028, 128, 20), (4, 257, 256, 20), (8, 64, 256, 8), (2, 130, 20, 5),
+@pytest.mark.parametrize("B,N,D,k", [(4, 1028, 128, 20), (4, 257, 256, 20), (8, 64, 256, 8), (2, 130, 20, 5), (1, 4500, 64, 30),
                                      (1, 300, 64, 40), (2, 257, 128, 20)])
 def test_knn_feat_vs_oracle(ops, B, N, D, k):
     g = torch.Generator().manual_seed(N + D)
@@ -263,7 +263,8 @@ def test_layer_conv_golden(ops, tag, xk, cout):
     assert_close(nump(out), g[f"{tag}_graph"], what="layer graph_conv vs reference")
 
 
-@pytest.mark.parametrize("S,C,N,k,B", [(7, 128, 1028, 20, 2), (7, 256, 257, 20, 3), (7, 512, 64, 8, 2), (4, 8, 50, 33, 1)])
+@pytest.mark.parametrize("S,C,N,k,B", [(7, 128, 1028, 20, 2), (7, 256, 257, 20, 3), (7, 512, 64, 8, 2), (4, 8, 50, 33, 1),
+                                       (7, 16, 2500, 12, 1)])     # last: N*S*16 B > shared memory -> L2-gather variant
 def test_layer_conv_vs_oracle(ops, S, C, N, k, B):
     rng = np.random.default_rng(C + N)
     x = rng.random((B, N, 3), dtype=np.float32)
@@ -464,3 +465,26 @@ def test_posenet_golden():
         assert np.degrees(np.arccos(cosang)).max() < 0.25, k
     for k in ("Pred_T", "Pred_s"):
         assert np.abs(nump(out[k]) - g["out_" + k]).max() < 1e-4, k
+
+
+def test_cuda_graph_replay_equals_eager():
+    """graph.GraphedPoseNet: the replayed forward (static buffers, Pool draws made on the host in the reference's
+    order) is bit-identical to the eager forward for the same CPU seed, for two different inputs."""
+    from tgpose_b200.graph import GraphedPoseNet
+    from tgpose_b200.posenet import PoseNet9D
+    torch.manual_seed(0)
+    net = PoseNet9D().cuda().eval()
+    B, N = 4, 1028
+    gr = GraphedPoseNet(net, B, N)
+    gen = torch.Generator().manual_seed(21)
+    for trial in range(2):
+        pts = (torch.rand(B, N, 3, generator=gen) - 0.5) * 0.3 + torch.tensor([0.0, 0.1, 1.0])
+        cat = torch.randint(0, 6, (B, 1), generator=gen).float()
+        torch.manual_seed(100 + trial)
+        with torch.no_grad():
+            eager = {k: v.clone() for k, v in net(pts.cuda(), cat.cuda()).items()}
+        torch.manual_seed(100 + trial)
+        out = gr(pts.pin_memory(), cat.pin_memory())
+        torch.cuda.synchronize()
+        for k in eager:
+            assert torch.equal(eager[k], out[k]), (trial, k)

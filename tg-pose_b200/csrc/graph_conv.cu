@@ -169,7 +169,9 @@ surface_conv_kernel(const float* __restrict__ xyz, const IdxT* __restrict__ idx,
 
 // ------------------------------------------------------------------------------------------
 // layer conv.  CTA = (4-channel group cg, cloud b).  lane = s*4 + c4 (< S*4 <= 32).
-template <bool ARG, int KT>
+// TAB: the (cloud, channel-group) support table is staged in shared memory (N*S*16 B <= ~215 KB, i.e. N <= ~1960 at
+// S = 7); otherwise (the N = 2048..16384 microbenchmark clouds) the 112-byte rows are gathered through L2.
+template <bool ARG, int KT, bool TAB>
 __global__ void __launch_bounds__(1024)
 layer_conv_kernel(const float4* __restrict__ rec, const float* __restrict__ directions,
                   const float* __restrict__ centre, long ld_centre, const float* __restrict__ slab,
@@ -179,7 +181,7 @@ layer_conv_kernel(const float4* __restrict__ rec, const float* __restrict__ dire
     const int k = KT > 0 ? KT : k_rt;                      // neighbour count: compile-time for the encoder's 20 / 8
     const int W = S * 4;                                   // slab row width in floats
     float* tab = reinterpret_cast<float*>(smem_raw);       // [N][W]
-    const size_t tab_bytes = (size_t)N * W * sizeof(float);
+    const size_t tab_bytes = TAB ? (size_t)N * W * sizeof(float) : 0;
     float4* recs = reinterpret_cast<float4*>(smem_raw + ((tab_bytes + 15) & ~(size_t)15));  // [warps][k]
     __shared__ __align__(8) uint64_t bar;
 
@@ -190,12 +192,12 @@ layer_conv_kernel(const float4* __restrict__ rec, const float* __restrict__ dire
 
     // one elected thread arms the barrier and issues the bulk copies (<= 32 KB pieces)
     const float* src = slab + ((long)cg * M + b * N) * W;
-    if (threadIdx.x == 0) {
+    if (TAB && threadIdx.x == 0) {
         mbar_init(&bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
+    if (TAB && threadIdx.x == 0) {
         mbar_expect_tx(&bar, (uint32_t)tab_bytes);
         const uint32_t piece = 32768;
         for (uint32_t off = 0; off < tab_bytes; off += piece) {
@@ -207,7 +209,7 @@ layer_conv_kernel(const float4* __restrict__ rec, const float* __restrict__ dire
     float sx = 0.f, sy = 0.f, sz = 0.f;
     const int s_l = lane >> 2, c4 = lane & 3;
     if (lane < W) load_sd(directions, SC, s_l * C + cg * 4 + c4, sx, sy, sz);
-    mbar_wait(&bar, 0);
+    if (TAB) mbar_wait(&bar, 0);
 
     float4* my = recs + warp * k;
     const float inv_s = 1.0f / (float)S;
@@ -215,18 +217,21 @@ layer_conv_kernel(const float4* __restrict__ rec, const float* __restrict__ dire
     const uint32_t tab_lane = smem_u32(tab) + (uint32_t)(lane < W ? lane : 0) * 4u;
     const uint32_t row_bytes = (uint32_t)W * 4u;
     // the k edge records of the warp's next point are fetched while the current point is being reduced
-    const float4* rp = rec + (b * N + warp) * (long)k;
+    // gridDim.z splits the points of the cloud when (clouds x channel groups) alone cannot fill the machine
+    const int per = (N + gridDim.z - 1) / gridDim.z;
+    const int n_beg = blockIdx.z * per, n_end = min(N, n_beg + per);
+    const float4* rp = rec + (b * N + n_beg + warp) * (long)k;
     const long rstep = (long)nwarps * k;
     float4 nxt = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (warp < N && lane < k) nxt = __ldg(rp + lane);
-    for (int n = warp; n < N; n += nwarps) {
+    if (n_beg + warp < n_end && lane < k) nxt = __ldg(rp + lane);
+    for (int n = n_beg + warp; n < n_end; n += nwarps) {
         const long pt = b * N + n;
         __syncwarp();
         if (lane < k) my[lane] = nxt;
         for (int j = lane + 32; j < k; j += 32) my[j] = __ldg(rp + j);
         __syncwarp();
         rp += rstep;
-        if (n + nwarps < N && lane < k) nxt = __ldg(rp + lane);
+        if (n + nwarps < n_end && lane < k) nxt = __ldg(rp + lane);
         float m = -FLT_MAX;
         int a = 0;
         if (lane < W) {
@@ -234,7 +239,8 @@ layer_conv_kernel(const float4* __restrict__ rec, const float* __restrict__ dire
             for (int j = 0; j < k; ++j) {
                 const float4 d = my[j];
                 float sup;
-                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(sup) : "r"(tab_lane + (uint32_t)__float_as_int(d.w) * row_bytes));
+                if (TAB) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(sup) : "r"(tab_lane + (uint32_t)__float_as_int(d.w) * row_bytes));
+                else sup = __ldg(src + (long)__float_as_int(d.w) * W + (lane < W ? lane : 0));
                 const float th = fmaxf(fmaf(d.z, sz, fmaf(d.y, sy, d.x * sx)), 0.f);
                 const float v = th * sup;
                 if (ARG) { if (v > m) { m = v; a = j; } }
@@ -314,23 +320,33 @@ extern "C" int tgp_layer_conv_fwd(const float* edge_rec, const float* directions
     const size_t tab_bytes = (size_t)N * W * sizeof(float);
     // enough warps to hide the gather latency, few enough that several CTAs share an SM when the table is small
     int threads = N >= 512 ? 1024 : (N >= 128 ? 256 : 128);
-    const size_t smem = ((tab_bytes + 15) & ~(size_t)15) + sizeof(float4) * (threads / 32) * k;
-    if (smem > 227 * 1024) return fail(TGP_EINVAL, "tgp_layer_conv_fwd: N*S too large for one shared-memory table (N*S*16 B <= ~220 KB)");
-    dim3 grid(C / 4, B);
+    size_t smem = ((tab_bytes + 15) & ~(size_t)15) + sizeof(float4) * (threads / 32) * k;
+    const bool tab = smem <= 227 * 1024;        // else: gather the support rows through L2 instead of a shared-memory table
+    if (!tab) smem = sizeof(float4) * (threads / 32) * k;
+    if (smem > 227 * 1024) return fail(TGP_EINVAL, "tgp_layer_conv_fwd: k too large");
+    // point splits: aim at >= 2 CTAs per SM; depends on the shapes only.  (Each split re-stages the table when TAB.)
+    int zs = (2 * TGP_NUM_SMS + (C / 4) * B - 1) / ((C / 4) * B);
+    const int zcap = (N + 255) / 256;
+    if (zs > zcap) zs = zcap;
+    if (zs < 1) zs = 1;
+    if (zs > 64) zs = 64;
+    dim3 grid(C / 4, B, zs);
     cudaStream_t st = as_stream(stream);
     const long M = (long)B * N;
     const int kp = (C + 31) / 32 * 32;
-#define TGP_LAUNCH_LC(ARGV, KTV)                                                                                        \
+#define TGP_LAUNCH_LC(ARGV, KTV, TABV)                                                                                   \
     do {                                                                                                                \
-        cudaFuncSetAttribute(layer_conv_kernel<ARGV, KTV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);       \
-        layer_conv_kernel<ARGV, KTV><<<grid, threads, smem, st>>>(reinterpret_cast<const float4*>(edge_rec), directions, \
-                                                                  centre, ld_centre, support_slab, M, N, k, S, C, out,   \
-                                                                  arg_slab, out_split, kp);                              \
+        cudaFuncSetAttribute(layer_conv_kernel<ARGV, KTV, TABV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        layer_conv_kernel<ARGV, KTV, TABV><<<grid, threads, smem, st>>>(reinterpret_cast<const float4*>(edge_rec),       \
+                                                                        directions, centre, ld_centre, support_slab, M,  \
+                                                                        N, k, S, C, out, arg_slab, out_split, kp);       \
     } while (0)
-    if (arg_slab) {
-        if (k == 20) TGP_LAUNCH_LC(true, 20); else if (k == 8) TGP_LAUNCH_LC(true, 8); else TGP_LAUNCH_LC(true, 0);
+    if (!tab) {
+        if (arg_slab) TGP_LAUNCH_LC(true, 0, false); else TGP_LAUNCH_LC(false, 0, false);
+    } else if (arg_slab) {
+        if (k == 20) TGP_LAUNCH_LC(true, 20, true); else if (k == 8) TGP_LAUNCH_LC(true, 8, true); else TGP_LAUNCH_LC(true, 0, true);
     } else {
-        if (k == 20) TGP_LAUNCH_LC(false, 20); else if (k == 8) TGP_LAUNCH_LC(false, 8); else TGP_LAUNCH_LC(false, 0);
+        if (k == 20) TGP_LAUNCH_LC(false, 20, true); else if (k == 8) TGP_LAUNCH_LC(false, 8, true); else TGP_LAUNCH_LC(false, 0, true);
     }
 #undef TGP_LAUNCH_LC
     return check_launch("layer_conv_kernel");

@@ -26,7 +26,6 @@ constexpr int KT_THREADS = 64 + 32 * KT_EPI_WARPS;
 constexpr int KT_QPW = TC_BM / KT_EPI_WARPS;            // queries per selection warp (16)
 constexpr int KT_LDD = KT_BN + 4;                       // distance tile pitch (floats)
 constexpr int KT_STAGE_BYTES = TC_A_BYTES + KT_BN * TC_BK * 4;
-constexpr int KT_MAX_N = 4096;                          // candidate norms of one cloud staged in shared memory
 
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(32 * KT_EPI_WARPS) : "memory"); }
 
@@ -42,7 +41,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     uint64_t* tmem_empty = tmem_full + 2;
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
     float* Ds = reinterpret_cast<float*>(base + KT_STAGES * KT_STAGE_BYTES + 256);        // [128][KT_LDD]
-    float* qns = Ds + TC_BM * KT_LDD;                                                       // [n_cand_tiles * 128]
+    float* qns = Ds + TC_BM * KT_LDD;                                                       // [2][128] candidate norms, per tile
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int kblocks = Kp / TC_BK;
@@ -134,9 +133,10 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
             const int q0 = qt * q_step;
             const int nq = min(q_step, N - q0);    // valid queries of this unit
             const float* qb = qn + (size_t)b * N;
-            // candidate norms of the cloud, +inf beyond N (masks the padding columns of the last tile)
+            // candidate norms of tile 0, +inf beyond N (masks the padding columns of the last tile); the norms of
+            // tile t+1 are fetched into the other buffer before tile t's closing barrier
             // (every warp passed the last tile's closing barrier, so nobody still reads the previous unit's norms)
-            for (int j = et; j < c_tiles * KT_BN; j += 32 * KT_EPI_WARPS) qns[j] = j < N ? __ldg(qb + j) : CUDART_INF_F;
+            if (et < KT_BN) qns[(it & 1) * KT_BN + et] = et < N ? __ldg(qb + et) : CUDART_INF_F;
             const float qi = my_row < nq ? __ldg(qb + q0 + my_row) : 0.f;
             float td[KT_QPW];
             int ti[KT_QPW];
@@ -157,7 +157,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
                     TMEM_LD_32x32(taddr, r);
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                     float* drow = Ds + my_row * KT_LDD + cc;
-                    const float4* qj4 = reinterpret_cast<const float4*>(qns + c0 + cc);
+                    const float4* qj4 = reinterpret_cast<const float4*>(qns + (it & 1) * KT_BN + cc);
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {
                         const float4 qj = qj4[j >> 2];
@@ -188,6 +188,10 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
                         td[i] = pr.dA; ti[i] = pr.iA; th[i] = pr.thA;
                         td[i + 1] = pr.dB; ti[i + 1] = pr.iB; th[i + 1] = pr.thB;
                     }
+                }
+                if (et < KT_BN && ct + 1 < c_tiles) {
+                    const int j = c0 + KT_BN + et;
+                    qns[((it + 1) & 1) * KT_BN + et] = j < N ? __ldg(qb + j) : CUDART_INF_F;
                 }
                 epi_bar_sync();                    // selection done: Ds may be overwritten
             }
@@ -220,7 +224,7 @@ using namespace tgp;
 // (must not depend on B: a cloud's result may not change with the batch it sits in)
 bool tgp_knn_tc_eligible(int B, int N, int D, int k) {
     (void)B;
-    return k + 1 <= 32 && N >= 64 && N <= KT_MAX_N && D >= 16;
+    return k + 1 <= 32 && N >= 64 && D >= 16;
 }
 
 int tgp_knn_tc(const float* x_split, const float* qn, int B, int N, int D, int k, int64_t* idx64, int32_t* idx32,
@@ -234,8 +238,7 @@ int tgp_knn_tc(const float* x_split, const float* qn, int B, int N, int D, int k
     const int q_tiles = (N + TC_BM - 1) / TC_BM;
     const int q_step = (N + q_tiles - 1) / q_tiles;          // balanced query tiles (1028 -> 9 x 115, not 8 x 128 + 4)
     const int num_units = B * q_tiles;
-    const int c_tiles = (N + KT_BN - 1) / KT_BN;
-    const size_t smem = (size_t)KT_STAGES * KT_STAGE_BYTES + 1024 + 256 + sizeof(float) * (TC_BM * KT_LDD + (size_t)c_tiles * KT_BN);
+    const size_t smem = (size_t)KT_STAGES * KT_STAGE_BYTES + 1024 + 256 + sizeof(float) * (TC_BM * KT_LDD + 2 * KT_BN);
     static bool attr_set = false;
     if (!attr_set) {
         cudaFuncSetAttribute(knn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);

@@ -47,6 +47,8 @@ class Face_Enc(nn.Module):
         # test hooks (parity tiers T1/T2, SURVEY 8c'): replay / record the 12 kNN + 2 nearest index tensors
         self._inject = None
         self._record = None
+        # CUDA-graph replay (graph.py): device tensors holding the two Pool_layer draws of this forward
+        self._static_perms = None
 
     # -- helpers -------------------------------------------------------------------------
     def _next_idx(self, compute):
@@ -97,7 +99,8 @@ class Face_Enc(nn.Module):
         else:
             fm_1 = self._bn_relu(self.bn1, self.conv_1(vertices, fm_0, k, idx_feat=i1, idx_xyz=i1_orl, fm_split=fm_0s))
         ip1 = self._next_idx(lambda: i0[:, :, :4].contiguous() if share else xyz_knn(vertices, 4))
-        v_pool_1, fm_pool_1 = self.pool_1(vertices, fm_1, idx_xyz=ip1)
+        sp = self._static_perms
+        v_pool_1, fm_pool_1 = self.pool_1(vertices, fm_1, idx_xyz=ip1, sample_idx=sp[0] if sp else None)
 
         # level 1
         k1 = min(k, v_pool_1.shape[1] // 8)
@@ -117,7 +120,7 @@ class Face_Enc(nn.Module):
         else:
             fm_3 = self._bn_relu(self.bn3, self.conv_3(v_pool_1, fm_2, k1, idx_feat=i3, idx_xyz=i3_orl))
         ip2 = self._next_idx(lambda: (i2_orl[:, :, :4].contiguous() if (share and k1 >= 4) else xyz_knn(v_pool_1, 4)))
-        v_pool_2, fm_pool_2 = self.pool_2(v_pool_1, fm_3, idx_xyz=ip2)
+        v_pool_2, fm_pool_2 = self.pool_2(v_pool_1, fm_3, idx_xyz=ip2, sample_idx=sp[1] if sp else None)
 
         # level 2
         k2 = min(k, v_pool_2.shape[1] // 8)

@@ -142,10 +142,13 @@ class Pool_layer(nn.Module):
         self.pooling_rate = pooling_rate
         self.neighbor_num = neighbor_num
 
-    def forward(self, vertices: "(bs, vertice_num, 3)", feature_map: "(bs, vertice_num, channel_num)", idx_xyz=None):
+    def forward(self, vertices: "(bs, vertice_num, 3)", feature_map: "(bs, vertice_num, channel_num)", idx_xyz=None,
+                sample_idx=None):
         """-> (vertices_pool (bs, n/rate, 3), feature_map_pool (bs, n/rate, channel)).
-        The sample is one torch.randperm on the global CPU generator shared by the batch (gcn3d.py:241-244)."""
+        The sample is one torch.randperm on the global CPU generator shared by the batch (gcn3d.py:241-244).
+        sample_idx (extension): a device tensor that already holds that draw (CUDA-graph replay, graph.py)."""
         vertice_num = vertices.size(1)
         pool_num = int(vertice_num / self.pooling_rate)
-        sample_idx = torch.randperm(vertice_num)[:pool_num]
+        if sample_idx is None:
+            sample_idx = torch.randperm(vertice_num)[:pool_num]
         return PoolFn.apply(vertices, feature_map, sample_idx, self.neighbor_num, idx_xyz, torch.is_grad_enabled())

@@ -1,0 +1,64 @@
+"""CUDA-graph replay of the inference forward ("CUDA-graph the whole encoder").
+
+One forward of the full network is ~75 kernel launches of 5-1400 us each; replaying them as one graph removes the
+per-launch host work and the gaps between the small kernels.  Everything the reference draws on the host stays on
+the host: Pool_layer's two torch.randperm draws (gcn3d.py:242) are made from the CPU generator in the reference's
+order before every replay and copied into static device buffers, so a replay equals the eager forward bit for bit.
+"""
+import torch
+
+from . import ops
+
+
+class GraphedPoseNet:
+    """net: a PoseNet9D in eval mode on a CUDA device; fixed (batch, n_points)."""
+
+    def __init__(self, net, batch, n_points, warmup=2):
+        assert not net.training, "graph replay is for inference"
+        self.net = net
+        dev = next(net.parameters()).device
+        self.enc = net.face_all.encoder if not net.only_encoder else net.face_enc.encoder
+        self.n0 = n_points
+        self.n1 = int(n_points / self.enc.pool_1.pooling_rate)
+        self.p1 = int(n_points / self.enc.pool_1.pooling_rate)
+        self.p2 = int(self.n1 / self.enc.pool_2.pooling_rate)
+        self.pts = torch.zeros(batch, n_points, 3, device=dev)
+        self.cat = torch.zeros(batch, 1, device=dev)
+        self.perm1 = torch.zeros(self.p1, dtype=torch.int64, device=dev)
+        self.perm2 = torch.zeros(self.p2, dtype=torch.int64, device=dev)
+        self.h_perm1 = torch.zeros(self.p1, dtype=torch.int64).pin_memory()
+        self.h_perm2 = torch.zeros(self.p2, dtype=torch.int64).pin_memory()
+        self._draw()
+        # a valid input for the warm-up / capture passes (the values are overwritten before every replay)
+        self.pts.copy_(torch.rand(batch, n_points, 3, device=dev) - 0.5)
+        self.enc._static_perms = (self.perm1, self.perm2)
+        try:
+            assert ops.EVENT_LOG is None, "per-call event timing cannot run inside a graph capture"
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side), torch.no_grad():
+                for _ in range(warmup):           # weight packs / split caches are built here, outside the capture
+                    net(self.pts, self.cat)
+            torch.cuda.current_stream(dev).wait_stream(side)
+            torch.cuda.synchronize(dev)
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph), torch.no_grad():
+                self.out = net(self.pts, self.cat)
+        finally:
+            self.enc._static_perms = None
+
+    def _draw(self):
+        """the two CPU-generator draws of Pool_layer.forward, in the reference's order (gcn3d.py:241-243)."""
+        self.h_perm1.copy_(torch.randperm(self.n0)[:self.p1])
+        self.h_perm2.copy_(torch.randperm(self.n1)[:self.p2])
+        self.perm1.copy_(self.h_perm1, non_blocking=True)
+        self.perm2.copy_(self.h_perm2, non_blocking=True)
+
+    def __call__(self, points, obj_id):
+        """points (B,N,3), obj_id (B,1): host (pinned) or device tensors.  Returns the static output dict (valid
+        until the next call)."""
+        self.pts.copy_(points, non_blocking=True)
+        self.cat.copy_(obj_id, non_blocking=True)
+        self._draw()
+        self.graph.replay()
+        return self.out
