@@ -129,6 +129,54 @@ orl_global_kernel(const float* __restrict__ f, const IdxT* __restrict__ idx, int
     }
 }
 
+
+// ORL global feature with the cloud's 32-channel slice staged in shared memory: CTA = (32-channel chunk, cloud).
+// The k-fold gather (20 x the feature map through L2 in the kernel above) becomes conflict-free shared-memory reads
+// (lane = channel = bank); HBM/L2 traffic drops to the compulsory one read of the feature map.  The per-point maxima
+// are summed per warp and the warps are added in a fixed order: deterministic, and independent of the batch.
+constexpr int ORLS_THREADS = 512;
+template <typename IdxT, bool ARG>
+__global__ void __launch_bounds__(ORLS_THREADS)
+orl_smem_kernel(const float* __restrict__ f, const IdxT* __restrict__ idx, int N, int k, int C,
+                float* __restrict__ g, uint8_t* __restrict__ arg) {
+    extern __shared__ __align__(16) float orl_tab[];       // [N][32]
+    __shared__ float part[ORLS_THREADS / 32][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int c0 = blockIdx.x * 32, c = c0 + lane;
+    const long b = blockIdx.y;
+    const float* fb = f + b * N * (long)C;
+    for (int n = warp; n < N; n += ORLS_THREADS / 32) orl_tab[n * 32 + lane] = c < C ? __ldg(fb + (long)n * C + c) : 0.f;
+    __syncthreads();
+    float acc = 0.f;
+    for (int n = warp; n < N; n += ORLS_THREADS / 32) {
+        const IdxT* id = idx + (b * N + n) * k;
+        int nb = lane < k ? ld_idx(id, lane) : 0;            // k <= 32: one coalesced index load per point
+        float best = -FLT_MAX;
+        int bj = 0;
+        const int kk = k < 32 ? k : 32;
+#pragma unroll 4
+        for (int j = 0; j < kk; ++j) {
+            const float v = orl_tab[__shfl_sync(0xffffffffu, nb, j) * 32 + lane];
+            if (ARG) { if (v > best) { best = v; bj = j; } }
+            else best = fmaxf(best, v);
+        }
+        for (int j = 32; j < k; ++j) {                       // k > 32 (not used by the network)
+            const float v = orl_tab[ld_idx(id, j) * 32 + lane];
+            if (v > best) { best = v; bj = j; }
+        }
+        acc += best;
+        if (ARG && c < C) arg[(b * N + n) * (long)C + c] = (uint8_t)bj;
+    }
+    part[warp][lane] = acc;
+    __syncthreads();
+    if (warp == 0 && c < C) {
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < ORLS_THREADS / 32; ++w) s += part[w][lane];
+        g[b * C + c] = s / (float)N;
+    }
+}
+
 __global__ void orl_finalize_kernel(const float* __restrict__ partial, int nsplit, int C, long total, int N,
                                     float* __restrict__ g) {
     const long e = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -265,6 +313,21 @@ extern "C" int tgp_orl_global(const float* f, const void* idx, int idx_bits, int
     if (k > 255 || B > 65535) return fail(TGP_EINVAL, "tgp_orl_global: k > 255 or B > 65535");
     cudaStream_t st = as_stream(stream);
     const int chunks = (C + 31) / 32;
+    const size_t tab_bytes = (size_t)N * 32 * sizeof(float);
+    if (tab_bytes <= 200 * 1024) {
+        // the cloud's channel slice fits in shared memory (N <= 1600): one pass, no partial sums
+        dim3 grid(chunks, B);
+        TGP_DISPATCH_IDX(idx_bits, {
+            if (arg) {
+                cudaFuncSetAttribute(orl_smem_kernel<IdxT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+                orl_smem_kernel<IdxT, true><<<grid, ORLS_THREADS, tab_bytes, st>>>(f, (const IdxT*)idx, N, k, C, g, arg);
+            } else {
+                cudaFuncSetAttribute(orl_smem_kernel<IdxT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+                orl_smem_kernel<IdxT, false><<<grid, ORLS_THREADS, tab_bytes, st>>>(f, (const IdxT*)idx, N, k, C, g, arg);
+            }
+        });
+        return check_launch("orl_smem_kernel");
+    }
     const int nsplit = orl_nsplit(N);
     float* partial = static_cast<float*>(workspace);
     dim3 grid(chunks, B, nsplit);
