@@ -272,6 +272,28 @@ size_t tgp_gemm_tn_tc_workspace(long M, int K1, int K2);
 int tgp_gemm_tn_tc(const float* At_split, const float* Bt_split, long M, int K1, int K2, float* out, long ldo,
                    void* workspace, size_t workspace_bytes, tgp_stream_t stream);
 
+/* ------------------------------------------------------------------ heads in training
+ * Train-mode Conv1d(k=1) + BatchNorm1d + ReLU/LeakyReLU stacks of the heads (PoseR.py:26-33, PoseTs.py:31-38,
+ * FaceRecon.py:95-117,139-141) on channel-last rows; the contraction itself is tgp_gemm / tgp_gemm_tn_tc.
+ * All matrices (M, C) fp32 with the given row strides; per-channel vectors (C). */
+
+/* out[c] = sum_r (x[r,c] - mu[c])^2   (second pass of the batch variance).  workspace: tgp_bn_workspace(M, C). */
+size_t tgp_bn_workspace(long M, int C);
+int tgp_colsumsq_dev(const float* x, long ld, long M, int C, const float* mu, float* out,
+                     void* workspace, size_t workspace_bytes, tgp_stream_t stream);
+
+/* y = act(z * scale[c] + shift[c]), act(v) = v > 0 ? v : v * slope.  out (M,C) and/or out_split (M, 2*Kp) as the
+ * next contraction's tensor-core operand (padding columns must be pre-zeroed). */
+int tgp_affine_act(const float* z, long ld_z, const float* scale, const float* shift, float slope, long M, int C,
+                   float* out, long ld_out, float* out_split, int Kp, tgp_stream_t stream);
+
+/* backward of y = act(BN_train(z)): dbeta[c] = sum g, dgamma[c] = sum g * zhat, g = dy * act'(y),
+ * dz = gamma * invstd * (g - dbeta / M - zhat * dgamma / M).  workspace: tgp_bn_workspace(M, C). */
+int tgp_bn_bwd(const float* dy, long ld_dy, const float* y, long ld_y, const float* z, long ld_z,
+               const float* mean, const float* invstd, const float* gamma, float slope, long M, int C,
+               float* dz, long ld_dz, float* dbeta, float* dgamma,
+               void* workspace, size_t workspace_bytes, tgp_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -333,3 +333,38 @@ def test_train_step_runs_and_learns():
     print("train-step losses:", " ".join(f"{v:.4f}" for v in hist))
     assert all(np.isfinite(v) for v in hist)
     assert min(hist[-4:]) < first, hist
+
+
+@pytest.mark.parametrize("M,cin,cout,slope", [(4112, 1286, 1024, 0.0), (2056, 1024, 256, 0.0), (1000, 70, 64, 0.2)])
+def test_conv_bn_act_train_vs_torch(M, cin, cout, slope):
+    """heads_train.conv_bn_act_train (train-mode Conv1d(k=1) + BatchNorm1d + ReLU/LeakyReLU on the library's kernels)
+    against the same torch layers in fp32 (TF32 off): output, running statistics, and every gradient."""
+    from tgpose_b200.heads_train import conv_bn_act_train
+    import torch.nn as nn
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.manual_seed(M + cin)
+    conv_a, bn_a = nn.Conv1d(cin, cout, 1).cuda(), nn.BatchNorm1d(cout).cuda()
+    with torch.no_grad():
+        bn_a.weight.uniform_(0.5, 1.5)
+        bn_a.bias.uniform_(-0.5, 0.5)
+    import copy
+    conv_b, bn_b = copy.deepcopy(conv_a), copy.deepcopy(bn_a)
+    x = torch.randn(M, cin).cuda()
+    xa, xb = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    G = torch.randn(M, cout).cuda()
+    ya = conv_bn_act_train(xa, conv_a, bn_a, slope)
+    (ya * G).sum().backward()
+    zb = bn_b(conv_b(xb.t().unsqueeze(0)))               # (1, cin, M) -> (1, cout, M)
+    yb = (torch.relu(zb) if slope == 0.0 else torch.nn.functional.leaky_relu(zb, slope))[0].t()
+    (yb * G).sum().backward()
+    assert_close(nump(ya), nump(yb), rel=1e-4, floor=2e-5, what="conv+bn+act forward")
+    assert_close(nump(bn_a.running_mean), nump(bn_b.running_mean), what="running_mean")
+    assert_close(nump(bn_a.running_var), nump(bn_b.running_var), what="running_var")
+    assert int(bn_a.num_batches_tracked) == 1
+    assert_grad_close(nump(xa.grad), nump(xb.grad), what="dx")
+    assert_grad_close(nump(conv_a.weight.grad), nump(conv_b.weight.grad), what="dW")
+    assert_grad_close(nump(bn_a.weight.grad), nump(bn_b.weight.grad), what="dgamma")
+    assert_grad_close(nump(bn_a.bias.grad), nump(bn_b.bias.grad), what="dbeta")
+    # the conv bias gradient is a sum of terms that cancel exactly in theory (BatchNorm removes the mean)
+    assert float(conv_a.bias.grad.abs().max()) <= 1e-3 * float(G.abs().sum(0).max())

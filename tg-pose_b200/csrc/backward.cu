@@ -308,6 +308,124 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ partial, int nspl
     }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// train-mode BatchNorm1d + activation around a 1x1 convolution (the heads' Conv1d-BN-ReLU stacks, PoseR.py:26-33,
+// PoseTs.py:31-38, FaceRecon.py:95-117,139-141), channel-last rows: statistics over the M = B*N rows per channel.
+//   forward : z = x W^T + b (tgp_gemm) ; mean, var (tgp_colsum, tgp_colsumsq_dev) ; y = act(z * scale + shift)
+//   backward: g = dy * act'(y) ; dbeta = sum g ; dgamma = sum g * zhat ; dz = gamma*invstd * (g - dbeta/M - zhat*dgamma/M)
+// sum over rows of (x - mu[c])^2 (two-pass variance: no cancellation)
+__global__ void __launch_bounds__(CS_THREADS)
+colsumsq_partial_kernel(const float* __restrict__ x, long ld, long M, int C, const float* __restrict__ mu,
+                        float* __restrict__ partial) {
+    __shared__ float part[CS_THREADS / 32][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + lane;
+    const int nsplit = gridDim.z, sp = blockIdx.z;
+    const long per = (M + nsplit - 1) / nsplit;
+    const long r_beg = sp * per, r_end = min(M, r_beg + per);
+    float acc0 = 0.f, acc1 = 0.f;
+    if (c < C) {
+        const float m = __ldg(mu + c);
+        long r = r_beg + warp;
+        for (; r + CS_THREADS / 32 < r_end; r += 2 * (CS_THREADS / 32)) {
+            const float a = __ldg(x + r * ld + c) - m, b2 = __ldg(x + (r + CS_THREADS / 32) * ld + c) - m;
+            acc0 = fmaf(a, a, acc0);
+            acc1 = fmaf(b2, b2, acc1);
+        }
+        if (r < r_end) { const float a = __ldg(x + r * ld + c) - m; acc0 = fmaf(a, a, acc0); }
+    }
+    part[warp][lane] = acc0 + acc1;
+    __syncthreads();
+    if (warp == 0 && c < C) {
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < CS_THREADS / 32; ++w) s += part[w][lane];
+        partial[(long)sp * C + c] = s;
+    }
+}
+
+// y = act(z * scale[c] + shift[c]), act = leaky with `slope` (0: ReLU, 1: identity); raw and/or split destination
+__global__ void affine_act_kernel(const float* __restrict__ z, long ld_z, const float* __restrict__ scale,
+                                  const float* __restrict__ shift, float slope, long M, int C, float* __restrict__ out,
+                                  long ld_out, float* __restrict__ out_split, int kp) {
+    const long total = M * C;
+    for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
+        const long r = e / C;
+        const int c = (int)(e - r * C);
+        float v = fmaf(__ldg(z + r * ld_z + c), __ldg(scale + c), __ldg(shift + c));
+        v = v > 0.f ? v : v * slope;
+        if (out) out[r * ld_out + c] = v;
+        if (out_split) {
+            uint32_t hb;
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v));
+            const float hi = __uint_as_float(hb);
+            out_split[r * 2 * kp + c] = hi;
+            out_split[r * 2 * kp + kp + c] = v - hi;
+        }
+    }
+}
+
+// partial[sp][0][c] = sum g, partial[sp][1][c] = sum g * zhat over this split's rows
+__global__ void __launch_bounds__(CS_THREADS)
+bn_bwd_reduce_kernel(const float* __restrict__ dy, long ld_dy, const float* __restrict__ y, long ld_y,
+                     const float* __restrict__ z, long ld_z, const float* __restrict__ mean,
+                     const float* __restrict__ invstd, float slope, long M, int C, float* __restrict__ partial) {
+    __shared__ float part[2][CS_THREADS / 32][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + lane;
+    const int nsplit = gridDim.z, sp = blockIdx.z;
+    const long per = (M + nsplit - 1) / nsplit;
+    const long r_beg = sp * per, r_end = min(M, r_beg + per);
+    float s0 = 0.f, s1 = 0.f;
+    if (c < C) {
+        const float m = __ldg(mean + c), is = __ldg(invstd + c);
+        for (long r = r_beg + warp; r < r_end; r += CS_THREADS / 32) {
+            float g = __ldg(dy + r * ld_dy + c);
+            if (!(__ldg(y + r * ld_y + c) > 0.f)) g *= slope;
+            s0 += g;
+            s1 = fmaf(g, (__ldg(z + r * ld_z + c) - m) * is, s1);
+        }
+    }
+    part[0][warp][lane] = s0;
+    part[1][warp][lane] = s1;
+    __syncthreads();
+    if (warp < 2 && c < C) {
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < CS_THREADS / 32; ++w) s += part[warp][w][lane];
+        partial[((long)sp * 2 + warp) * C + c] = s;
+    }
+}
+
+__global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int nsplit, int C, float* __restrict__ dbeta,
+                                       float* __restrict__ dgamma) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    float a = 0.f, b2 = 0.f;
+    for (int sp = 0; sp < nsplit; ++sp) { a += partial[((long)sp * 2) * C + c]; b2 += partial[((long)sp * 2 + 1) * C + c]; }
+    dbeta[c] = a;
+    dgamma[c] = b2;
+}
+
+__global__ void bn_bwd_apply_kernel(const float* __restrict__ dy, long ld_dy, const float* __restrict__ y, long ld_y,
+                                    const float* __restrict__ z, long ld_z, const float* __restrict__ mean,
+                                    const float* __restrict__ invstd, const float* __restrict__ gamma,
+                                    const float* __restrict__ dbeta, const float* __restrict__ dgamma, float slope,
+                                    long M, int C, float* __restrict__ dz, long ld_dz) {
+    const long total = M * C;
+    const float inv_m = 1.0f / (float)M;
+    for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
+        const long r = e / C;
+        const int c = (int)(e - r * C);
+        float g = __ldg(dy + r * ld_dy + c);
+        if (!(__ldg(y + r * ld_y + c) > 0.f)) g *= slope;
+        const float is = __ldg(invstd + c);
+        const float zh = (__ldg(z + r * ld_z + c) - __ldg(mean + c)) * is;
+        dz[r * ld_dz + c] = __ldg(gamma + c) * is * (g - __ldg(dbeta + c) * inv_m - zh * __ldg(dgamma + c) * inv_m);
+    }
+}
+
 }  // namespace tgp
 
 using namespace tgp;
@@ -478,4 +596,59 @@ extern "C" int tgp_gemm_tn(const float* A, long lda, const float* Bm, long ldb, 
     if (rc) return rc;
     splitk_reduce_kernel<<<grid_for((long)K1 * K2, 256), 256, 0, st>>>(part, nsplit, K1, K2, out, ldo);
     return check_launch("splitk_reduce_kernel");
+}
+
+static int rowsplit(long M, int C, int per_row_min) {
+    const long chunks = (C + 31) / 32;
+    long want = ((long)TGP_NUM_SMS * 4 + chunks - 1) / chunks;
+    long cap = (M + per_row_min - 1) / per_row_min;
+    long s = want < cap ? want : cap;
+    return (int)(s < 1 ? 1 : (s > 256 ? 256 : s));
+}
+
+extern "C" size_t tgp_bn_workspace(long M, int C) { return (size_t)rowsplit(M, C, 64) * 2 * C * sizeof(float); }
+
+extern "C" int tgp_colsumsq_dev(const float* x, long ld, long M, int C, const float* mu, float* out, void* workspace,
+                                size_t workspace_bytes, tgp_stream_t stream) {
+    if (!x || !mu || !out || !workspace) return fail(TGP_EINVAL, "tgp_colsumsq_dev: null pointer");
+    if (M <= 0 || C <= 0) return fail(TGP_EINVAL, "tgp_colsumsq_dev: sizes must be positive");
+    if (workspace_bytes < tgp_bn_workspace(M, C)) return fail(TGP_ENOSPACE, "tgp_colsumsq_dev: workspace too small");
+    const int nsplit = rowsplit(M, C, 64);
+    cudaStream_t st = as_stream(stream);
+    dim3 grid((C + 31) / 32, 1, nsplit);
+    colsumsq_partial_kernel<<<grid, CS_THREADS, 0, st>>>(x, ld, M, C, mu, static_cast<float*>(workspace));
+    int rc = check_launch("colsumsq_partial_kernel");
+    if (rc) return rc;
+    colsum_finalize_kernel<<<(unsigned)((C + 255) / 256), 256, 0, st>>>(static_cast<const float*>(workspace), nsplit, C, C, out);
+    return check_launch("colsum_finalize_kernel");
+}
+
+extern "C" int tgp_affine_act(const float* z, long ld_z, const float* scale, const float* shift, float slope, long M,
+                              int C, float* out, long ld_out, float* out_split, int Kp, tgp_stream_t stream) {
+    if (!z || !scale || !shift || (!out && !out_split)) return fail(TGP_EINVAL, "tgp_affine_act: null pointer");
+    if (M <= 0 || C <= 0 || (out_split && Kp < C)) return fail(TGP_EINVAL, "tgp_affine_act: bad sizes");
+    affine_act_kernel<<<grid_for(M * C, 256), 256, 0, as_stream(stream)>>>(z, ld_z, scale, shift, slope, M, C, out, ld_out, out_split, Kp);
+    return check_launch("affine_act_kernel");
+}
+
+extern "C" int tgp_bn_bwd(const float* dy, long ld_dy, const float* y, long ld_y, const float* z, long ld_z,
+                          const float* mean, const float* invstd, const float* gamma, float slope, long M, int C,
+                          float* dz, long ld_dz, float* dbeta, float* dgamma, void* workspace, size_t workspace_bytes,
+                          tgp_stream_t stream) {
+    if (!dy || !y || !z || !mean || !invstd || !gamma || !dz || !dbeta || !dgamma || !workspace)
+        return fail(TGP_EINVAL, "tgp_bn_bwd: null pointer");
+    if (M <= 0 || C <= 0) return fail(TGP_EINVAL, "tgp_bn_bwd: sizes must be positive");
+    if (workspace_bytes < tgp_bn_workspace(M, C)) return fail(TGP_ENOSPACE, "tgp_bn_bwd: workspace too small");
+    const int nsplit = rowsplit(M, C, 64);
+    cudaStream_t st = as_stream(stream);
+    dim3 grid((C + 31) / 32, 1, nsplit);
+    float* part = static_cast<float*>(workspace);
+    bn_bwd_reduce_kernel<<<grid, CS_THREADS, 0, st>>>(dy, ld_dy, y, ld_y, z, ld_z, mean, invstd, slope, M, C, part);
+    int rc = check_launch("bn_bwd_reduce_kernel");
+    if (rc) return rc;
+    bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(part, nsplit, C, dbeta, dgamma);
+    rc = check_launch("bn_bwd_finalize_kernel");
+    if (rc) return rc;
+    bn_bwd_apply_kernel<<<grid_for(M * C, 256), 256, 0, st>>>(dy, ld_dy, y, ld_y, z, ld_z, mean, invstd, gamma, dbeta, dgamma, slope, M, C, dz, ld_dz);
+    return check_launch("bn_bwd_apply_kernel");
 }

@@ -1,0 +1,65 @@
+"""Train-mode Conv1d(k=1) + BatchNorm1d + ReLU / LeakyReLU blocks of the heads on the library's kernels.
+
+The reference runs these as nn.Conv1d / nn.BatchNorm1d on (B, C, N) tensors (PoseR.py:26-33, PoseTs.py:31-38,
+FaceRecon.py:95-117,139-141); 14.7 GFLOP per cloud forward, the dominant cost of the training step.  Here the rows
+are channel-last (B*N, C):
+    forward   z = x W^T + b                 tgp_gemm (tcgen05 3xTF32)
+              mean, var over the rows       tgp_colsum, tgp_colsumsq_dev (two-pass)
+              y = act((z - mean) * invstd * gamma + beta)   tgp_affine_act (also emits the next GEMM's split operand)
+    backward  dz, dgamma, dbeta             tgp_bn_bwd
+              dW = dz^T x, db = colsum(dz)  tgp_gemm_tn_tc, tgp_colsum
+              dx = dz W                     tgp_gemm
+BatchNorm's running statistics are updated exactly like torch's (momentum, unbiased variance, num_batches_tracked).
+"""
+import torch
+
+from . import ops
+
+
+class _ConvBNActFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x2d, weight, bias, gamma, beta, eps, slope, x_split, want_split):
+        M = x2d.shape[0]
+        cout, cin = weight.shape[0], weight.shape[1]
+        w2 = weight.reshape(cout, cin)
+        z = torch.empty((M, cout), dtype=torch.float32, device=x2d.device)
+        xs = x_split if (x_split is not None and x_split.numel()) else None
+        ops.gemm(x2d, w2, True, [(0, cout, z, 0, 0)], bias=bias, A_split=xs)
+        mean = ops.colsum(z).view(-1) / M
+        var = ops.colsumsq_dev(z, mean) / M                      # biased, as used for normalisation
+        invstd = torch.rsqrt(var + eps)
+        scale = gamma * invstd
+        shift = beta - mean * scale
+        y, y_split = ops.affine_act(z, scale, shift, slope, want_raw=True, want_split=want_split)
+        ctx.save_for_backward(x2d, w2, z, y, mean, invstd, gamma)
+        ctx.slope = slope
+        ctx.has_bias = bias is not None
+        ctx.wshape = weight.shape
+        if y_split is None:
+            y_split = y.new_empty(0)
+        ctx.mark_non_differentiable(y_split, mean, var)
+        return y, y_split, mean, var
+
+    @staticmethod
+    def backward(ctx, dy, _ds, _dm, _dv):
+        x2d, w2, z, y, mean, invstd, gamma = ctx.saved_tensors
+        dz, dbeta, dgamma = ops.bn_bwd(dy, y, z, mean, invstd, gamma, ctx.slope)
+        dw = ops.gemm_tn(dz, x2d).view(ctx.wshape)
+        db = ops.colsum(dz).view(-1) if ctx.has_bias else None
+        dx = ops.matmul_kn(dz, w2) if ctx.needs_input_grad[0] else None
+        return dx, dw, db, dgamma, dbeta, None, None, None, None
+
+
+def conv_bn_act_train(x2d, conv, bn, slope, x_split=None, want_split=False):
+    """(M, Cin) channel-last rows -> act(BN_train(conv(x))) as (M, Cout) [+ its tensor-core split]; updates bn's running
+    statistics like torch.nn.BatchNorm1d in train mode.  slope: 0 ReLU, 0.2 LeakyReLU(0.2), 1 no activation."""
+    M = x2d.shape[0]
+    y, y_split, mean, var = _ConvBNActFn.apply(x2d, conv.weight, conv.bias, bn.weight, bn.bias, bn.eps, float(slope),
+                                               x_split, want_split)
+    if bn.track_running_stats:
+        with torch.no_grad():
+            bn.num_batches_tracked += 1
+            mom = bn.momentum if bn.momentum is not None else 1.0 / float(bn.num_batches_tracked)
+            bn.running_mean.mul_(1 - mom).add_(mean, alpha=mom)
+            bn.running_var.mul_(1 - mom).add_(var * (M / max(M - 1, 1)), alpha=mom)
+    return (y, y_split) if want_split else y

@@ -505,3 +505,42 @@ def matmul_kn(x2d, w_kn, **kw):
     out = torch.empty((x2d.shape[0], w_kn.shape[1]), dtype=torch.float32, device=x2d.device)
     gemm(x2d, w_kn, False, [(0, w_kn.shape[1], out, 0, 0)], **kw)
     return out
+
+
+# --------------------------------------------------------------------------------------- heads in training
+def colsumsq_dev(x2d, mu):
+    """sum over rows of (x - mu)^2 -> (C,)."""
+    M, C = x2d.shape
+    assert x2d.stride(1) == 1
+    lib = _lib.load()
+    nb = lib.tgp_bn_workspace(M, C)
+    ws = _ws(nb, x2d.device)
+    out = torch.empty(C, dtype=torch.float32, device=x2d.device)
+    _run("colsumsq_dev", lib.tgp_colsumsq_dev, _p(x2d), x2d.stride(0), M, C, _p(mu), _p(out), _p(ws), nb, _stream())
+    return out
+
+
+def affine_act(z2d, scale, shift, slope, want_raw=True, want_split=False):
+    """act(z * scale + shift) -> (raw (M,C) or None, split (M, 2*kpad(C)) or None)."""
+    M, C = z2d.shape
+    assert z2d.stride(1) == 1
+    raw = torch.empty((M, C), dtype=torch.float32, device=z2d.device) if want_raw else None
+    spl = _split_buf(M, C, z2d.device) if want_split else None
+    _run("affine_act", _lib.load().tgp_affine_act, _p(z2d), z2d.stride(0), _p(scale), _p(shift), float(slope), M, C,
+         _p(raw), C, _p(spl), kpad(C), _stream())
+    return raw, spl
+
+
+def bn_bwd(dy2d, y2d, z2d, mean, invstd, gamma, slope):
+    """-> (dz (M,C), dbeta (C,), dgamma (C,)) of y = act(BN_train(z))."""
+    M, C = z2d.shape
+    dy2d = dy2d if dy2d.stride(1) == 1 else dy2d.contiguous()
+    lib = _lib.load()
+    nb = lib.tgp_bn_workspace(M, C)
+    ws = _ws(nb, z2d.device)
+    dz = torch.empty((M, C), dtype=torch.float32, device=z2d.device)
+    dbeta = torch.empty(C, dtype=torch.float32, device=z2d.device)
+    dgamma = torch.empty(C, dtype=torch.float32, device=z2d.device)
+    _run("bn_bwd", lib.tgp_bn_bwd, _p(dy2d), dy2d.stride(0), _p(y2d), y2d.stride(0), _p(z2d), z2d.stride(0), _p(mean),
+         _p(invstd), _p(gamma), float(slope), M, C, _p(dz), C, _p(dbeta), _p(dgamma), _p(ws), nb, _stream())
+    return dz, dbeta, dgamma

@@ -83,6 +83,8 @@ class Face_Dec(nn.Module):
 
     def forward(self, x):
         """x (B, C, N) -> recon (B, N, 3)."""
+        if self.training and x.is_cuda:
+            return self.forward_rows(x.permute(0, 2, 1).contiguous())
         if self.training:
             return self.recon_head(self.conv1d_block(x)).permute(0, 2, 1)
         h = x.permute(0, 2, 1).contiguous()
@@ -93,6 +95,29 @@ class Face_Dec(nn.Module):
         r = self.recon_head
         h = pointwise(h, r[0], r[1], "relu")
         return pointwise(h, r[3])
+
+    def forward_rows(self, x_cl, x_split=None):
+        """train mode on channel-last input (B, N, C) -> recon (B, N, 3): the four Conv1d-BN-ReLU blocks on the library's
+        kernels (heads_train.py), the final 128 -> 3 projection as a torch linear."""
+        B, N, C = x_cl.shape
+        b, r = self.conv1d_block, self.recon_head
+        h = _train_chain(x_cl.reshape(B * N, C), [(b[0], b[1], 0.0), (b[3], b[4], 0.0), (b[6], b[7], 0.0), (r[0], r[1], 0.0)],
+                         x_split)
+        last = r[3]
+        return F.linear(h, last.weight.reshape(last.out_channels, -1), last.bias).view(B, N, -1)
+
+
+def _train_chain(x2d, layers, x_split=None):
+    """Conv1d-BN-ReLU blocks in train mode on channel-last rows; every block hands the next one its split operand."""
+    from .heads_train import conv_bn_act_train
+    h, hs = x2d, x_split
+    for i, (conv, bn, slope) in enumerate(layers):
+        last = i == len(layers) - 1
+        if last:
+            h = conv_bn_act_train(h, conv, bn, slope, x_split=hs)
+        else:
+            h, hs = conv_bn_act_train(h, conv, bn, slope, x_split=hs, want_split=True)
+    return h
 
 
 class PH_Predictor(nn.Module):
@@ -117,7 +142,10 @@ class PH_Predictor(nn.Module):
     def forward(self, feat):
         """feat (B,N,1286) -> (feat + pi1 + pi2 as (B,1286,N), h1, h2)."""
         bs = feat.shape[0]
-        if self.training:
+        if self.training and feat.is_cuda:
+            f = _train_chain(feat.reshape(-1, feat.shape[2]), [(self.conv_5[0], self.conv_5[1], 0.2)])
+            pooled = f.view(bs, feat.shape[1], -1).max(dim=1)[0]
+        elif self.training:
             f = self.conv_5(feat.permute(0, 2, 1))
             pooled = F.adaptive_max_pool1d(f, 1).view(bs, -1)
         else:
@@ -175,7 +203,11 @@ class _PointHead(nn.Module):
 
     def trunk(self, x):
         """x (B, f, N) -> (B, k)."""
-        if self.training:
+        if self.training and x.is_cuda:
+            B, C, N = x.shape
+            h = _train_chain(x.permute(0, 2, 1).reshape(B * N, C), [(self.conv1, self.bn1, 0.0), (self.conv2, self.bn2, 0.0)])
+            x = h.view(B, N, -1).max(dim=1)[0].unsqueeze(2)
+        elif self.training:
             x = F.relu(self.bn1(self.conv1(x)))
             x = F.relu(self.bn2(self.conv2(x)))
             x = torch.max(x, 2, keepdim=True)[0]
