@@ -362,9 +362,16 @@ def test_conv_bn_act_train_vs_torch(M, cin, cout, slope):
     assert_close(nump(bn_a.running_mean), nump(bn_b.running_mean), what="running_mean")
     assert_close(nump(bn_a.running_var), nump(bn_b.running_var), what="running_var")
     assert int(bn_a.num_batches_tracked) == 1
-    assert_grad_close(nump(xa.grad), nump(xb.grad), what="dx")
-    assert_grad_close(nump(conv_a.weight.grad), nump(conv_b.weight.grad), what="dW")
-    assert_grad_close(nump(bn_a.weight.grad), nump(bn_b.weight.grad), what="dgamma")
-    assert_grad_close(nump(bn_a.bias.grad), nump(bn_b.bias.grad), what="dbeta")
+    # the activation is discontinuous in its derivative at 0: an output within rounding distance of 0 may take the other
+    # branch in one of the two implementations, which changes that ROW of dx and that COLUMN of dW/dgamma/dbeta by O(1)
+    # terms.  Such elements (|BN output| < 1e-5, a handful out of millions) are excluded by row / column.
+    near0 = (zb[0].t().abs() < 1e-5)
+    good_rows = nump(~near0.any(dim=1))
+    good_cols = nump(~near0.any(dim=0))
+    assert good_rows.mean() > 0.99 and good_cols.mean() > 0.9
+    assert_grad_close(nump(xa.grad)[good_rows], nump(xb.grad)[good_rows], what="dx")
+    assert_grad_close(nump(conv_a.weight.grad)[good_cols, :, 0], nump(conv_b.weight.grad)[good_cols, :, 0], what="dW")
+    assert_grad_close(nump(bn_a.weight.grad)[good_cols], nump(bn_b.weight.grad)[good_cols], what="dgamma")
+    assert_grad_close(nump(bn_a.bias.grad)[good_cols], nump(bn_b.bias.grad)[good_cols], what="dbeta")
     # the conv bias gradient is a sum of terms that cancel exactly in theory (BatchNorm removes the mean)
     assert float(conv_a.bias.grad.abs().max()) <= 1e-3 * float(G.abs().sum(0).max())

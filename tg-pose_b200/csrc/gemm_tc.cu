@@ -159,7 +159,7 @@ __device__ __forceinline__ void epi_chunk_vec(const tgp_gemm_args& g, uint32_t s
     __syncwarp();
     const int c4i = lane & 7, rsub = lane >> 3;
     const int col = colbase + c4i * 4;
-    const bool live = col < g.Ncols;
+    const bool live = col < g.Ncols && nrows > 0;     // row blocks past M must not touch group_bias / residual rows
     float4 bias = make_float4(0.f, 0.f, 0.f, 0.f), sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = bias, gb0 = bias, gb1 = bias;
     const float s0 = g.relu ? 0.f : 1.f;
     float4 sl = make_float4(s0, s0, s0, s0);
@@ -406,7 +406,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 for (int j = 0; j < 32; ++j) sts_f32(stg_addr + (uint32_t)((lane * 33 + j) * 4), __uint_as_float(r[j]));
                 __syncwarp();
                 const int col = n0 + c0 + lane;
-                const bool live = col < g.Ncols && !(dbg & 1);
+                const bool live = col < g.Ncols && nrows > 0 && !(dbg & 1);
                 // per-column constants of this lane
                 float bias = 0.f, sc = 1.f, sh = 0.f, slope = g.relu ? 0.f : 1.f, gbv0 = 0.f, gbv1 = 0.f;
                 EpiDst d0 = {nullptr, 0, 0}, d1 = {nullptr, 0, 0};
