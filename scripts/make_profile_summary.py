@@ -76,11 +76,15 @@ TO_US = {"ns": 1e-3, "us": 1, "ms": 1e3, "s": 1e6, "nsecond": 1e-3, "usecond": 1
 
 
 def forward():
+    raw = os.path.join(GO, f"{R}_forward_raw.csv")
     rep = os.path.join(GO, f"{R}_forward.ncu-rep")
-    if not os.path.exists(rep):
+    if os.path.exists(raw):
+        out = open(raw).read()
+    elif os.path.exists(rep):
+        out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    else:
         return
-    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-    rows = list(csv.reader(out.splitlines()))
+    rows = list(csv.reader([l for l in out.splitlines() if l.startswith('"')]))
     hdr, units = rows[0], rows[1]
     cols = {b: hdr.index(a) for a, b in WANT.items() if a in hdr}
     i_name = hdr.index("Kernel Name")
@@ -113,7 +117,7 @@ def forward():
                "per_kernel": per, "launches": launches_}, open(os.path.join(PR, f"{R}_kernels.json"), "w"), indent=1)
     with open(os.path.join(PR, f"{R}_kernels.md"), "w") as f:
         f.write(f"# {R} -- `ncu --set full` of every library kernel in one forward (32 x 1028 clouds, eval, eager launches)\n\n"
-                "Command: `scripts/profile_round.sh` step 2 (`-k regex:tgp:: -s <launches of the two warm-up forwards> -c <launches of "
+                "Command: `scripts/profile_round.sh` step 2 (`-k regex:<library kernel names> -s <launches of the two warm-up forwards> -c <launches of "
                 "one forward>`, i.e. the third forward of `scripts/profile_forward.py`).  Times are under the profiler (cold caches, serialised) -- use them for "
                 "shares and per-kernel diagnosis, never as benchmark values.  dram = `dram__bytes_read.sum + dram__bytes_write.sum`.\n\n"
                 "## Per kernel (summed over its launches in the forward)\n\n"

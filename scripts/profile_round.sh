@@ -5,13 +5,26 @@ set -u
 R=${1:-r01}
 O=gpurun_out
 mkdir -p $O
+if [ "${2:-all}" != "forward" ]; then
 # 1. launch list of the benchmark command (eager launches: one row per kernel; cold-cache, serialised)
 python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-graph > $O/${R}_plain_bench.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file $O/${R}_launches.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-graph > $O/${R}_ncu_launches.log 2>&1
-# 2. full-set capture of every library kernel of ONE forward (second forward of the script: warm caches / packs)
+fi
+# (ncu matches the base name, without the tgp:: namespace)
+KERNELS="^(concat_rows|edge_record|gather_max|gather_rows|gemm_naive|gemm_skinny|gemm_simt|gemm_tc|knn_tc|knn_xyz|knn_feat|layer_conv|nearest|orl_|rownorm|select_rows|split_tf32|surface_conv|direction_norm)"
+# 2. every library kernel of ONE forward (third forward of the script: warm caches / packs) with the sections the
+#    roofline needs; the report stays on the box (it exceeds the 64 MiB return limit), only its raw CSV page comes back
 python scripts/profile_forward.py > $O/${R}_plain_fwd.log 2>&1 &&
 SKIP=$(grep -o "skip=[0-9]*" $O/${R}_plain_fwd.log | cut -d= -f2) && COUNT=$(grep -o "count=[0-9]*" $O/${R}_plain_fwd.log | cut -d= -f2) &&
-ncu --set full --clock-control none --import-source on -k regex:"tgp::" -s $SKIP -c $COUNT -o $O/${R}_forward -f \
-    python scripts/profile_forward.py > $O/${R}_ncu_forward.log 2>&1
+ncu --section SpeedOfLight --section MemoryWorkloadAnalysis --section ComputeWorkloadAnalysis --section WarpStateStats \
+    --section LaunchStats --section Occupancy --section SchedulerStats --metrics dram__bytes_read.sum,dram__bytes_write.sum \
+    --clock-control none -k regex:"$KERNELS" -s $SKIP -c $COUNT -o /tmp/${R}_forward -f \
+    python scripts/profile_forward.py > $O/${R}_ncu_forward.log 2>&1 &&
+ncu -i /tmp/${R}_forward.ncu-rep --page raw --csv > $O/${R}_forward_raw.csv
 tail -2 $O/${R}_ncu_forward.log
+# 3. the dominant kernel (tcgen05 GEMM), full set with source correlation: the 17 launches of one forward
+python scripts/profile_forward.py > $O/${R}_plain_fwd2.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:"^gemm_tc" -s 34 -c 17 -o $O/${R}_gemm_tc -f \
+    python scripts/profile_forward.py > $O/${R}_ncu_gemm.log 2>&1
+tail -2 $O/${R}_ncu_gemm.log
