@@ -492,29 +492,34 @@ def kernel_report(event_log, steps, B, peaks):
                                    "frac": byts / t / 1e9 / peaks["hbm_gbs"], "peak_source": peaks["source"]}}
     elif top == "gemm_tc":
         # algorithmic flops 2*M*K*N per launch ("a 3xTF32 GEMM's useful flops are the plain 2MNK").
-        # Roof: the path must deliver fp32-level accuracy (rel 1e-4 parity); the tensor cores have no fp32 mode, so
-        # the ceiling for this contraction is the TF32 rate (measured bf16 dense / 2) divided by the 3 passes of 3xTF32.
-        flops = sum(2.0 * m * kdim * n for nm, m, kdim, n in event_log.get("__gemm_shapes__", []) if nm == "gemm_tc") / steps
-        t = agg[top]["ms_per_step"] / 1e3
+        # Roof: the path must deliver fp32-level accuracy (rel 1e-4 parity) and the tensor cores have no fp32 mode, so the
+        # ceiling of a contraction is the TF32 rate (measured bf16 dense / 2) divided by the TF32-pass equivalents it has
+        # to execute: 3 for the 3xTF32 operands of the encoder, 2 for the heads' mixed operands (TF32 hi.hi + two bf16
+        # cross terms at twice the TF32 rate).  `peak` is the flop-weighted roof of the launches in one step.
+        shapes = [x for x in event_log.get("__gemm_shapes__", []) if x[0] == "gemm_tc"]
+        flops = sum(2.0 * m * kdim * n for _, m, kdim, n, *_ in shapes) / steps
         tf32_peak = peaks["bf16_tflops_sustained"] / 2.0
-        peak = tf32_peak / 3.0
-        out["roofline"] = {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 3xTF32, all launches in the step)",
+        roof_t = sum(2.0 * m * kdim * n * (2.0 if (rest and rest[0]) else 3.0) for _, m, kdim, n, *rest in shapes) / steps / (tf32_peak * 1e12)
+        t = agg[top]["ms_per_step"] / 1e3
+        peak = flops / roof_t / 1e12
+        out["roofline"] = {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05; all launches in the step)",
                            "achieved": flops / t / 1e12, "peak": peak, "unit": "TFLOP/s",
-                           "frac": flops / t / 1e12 / peak, "traffic": profile_traffic("gemm_tc_kernel"),
-                           "executed_tf32_tflops": 3.0 * flops / t / 1e12, "tf32_peak": tf32_peak,
-                           "peak_source": f"{peaks['source']} sustained bf16 dense / 2 (TF32 rate) / 3 (3xTF32 passes for "
-                                          "fp32-equivalent results); achieved = algorithmic 2MNK flops",
+                           "frac": roof_t / t, "traffic": profile_traffic("gemm_tc_kernel"),
+                           "executed_tf32_equiv_tflops": roof_t * tf32_peak / t, "tf32_peak": tf32_peak,
+                           "peak_source": f"{peaks['source']} sustained bf16 dense / 2 (TF32 rate) / TF32-pass equivalents "
+                                          "(3: 3xTF32 encoder operands, 2: mixed TF32+bf16 head operands), flop-weighted; "
+                                          "achieved = algorithmic 2MNK flops",
                            "traffic_source": "sum of dram__bytes_read+write over the gemm_tc launches of one forward, "
-                                             "profiles/*_kernels.json (ncu --set full); bytes per step"}
+                                             "profiles/*_kernels.json (ncu); bytes per step"}
     if os.environ.get("TGP_BENCH_GEMM_TABLE"):
         shapes = event_log.get("__gemm_shapes__", [])
         evs = {"gemm": list(event_log.get("gemm", [])), "gemm_tc": list(event_log.get("gemm_tc", []))}
         pos = {"gemm": 0, "gemm_tc": 0}
         rows = {}
-        for nm, m, kdim, n in shapes:
+        for nm, m, kdim, n, *rest in shapes:
             a, b = evs[nm][pos[nm]]
             pos[nm] += 1
-            rows.setdefault((nm, m, kdim, n), []).append(a.elapsed_time(b))
+            rows.setdefault((nm, m, kdim, n) + tuple(rest), []).append(a.elapsed_time(b))
         for key, v in sorted(rows.items(), key=lambda kv: -sum(kv[1])):
             sys.stderr.write(f"GEMM {key}: {len(v) / steps:.1f}/step, {sum(v) / steps:.4f} ms/step\n")
     out["kernels"].pop("__gemm_shapes__", None)

@@ -105,9 +105,10 @@ typedef struct {
 
 /* torch.cat([...], dim=2) of FaceRecon.py:81 (+ the cat with the points, PoseNet9D.py:63) fused with the gathers that
  * feed it: out[(b,n), :] = [src_0 row | src_1 row | ...].  out_raw (B*N, ld_raw) and/or out_split (B*N, 2*Kp): the
- * same row as a tensor-core operand [tf32 | residual], zero padded to Kp.  Either may be NULL. */
+ * same row as a tensor-core operand [tf32 | residual] (mixed = 0) or as a MIXED operand (mixed = 1, see
+ * tgp_gemm_args.mixed), zero padded to Kp.  Either may be NULL. */
 int tgp_concat_rows(const tgp_concat_src* srcs_host, int nsrc, int B, int N, float* out_raw, long ld_raw,
-                    float* out_split, int Kp, tgp_stream_t stream);
+                    float* out_split, int Kp, int mixed, tgp_stream_t stream);
 
 /* ------------------------------------------------------------------ graph convolutions */
 
@@ -145,6 +146,8 @@ int tgp_layer_conv_fwd(const float* edge_rec, const float* directions,
  * mode 1: SLAB, columns are ordered (cgroup, s, c4) and go to [cgroup][m][S*4] (slab_width = S*4).
  * mode 2: SPLIT, the value is written as a tensor-core operand for the next contraction:
  *         tf32(v) at out[m*ld + rel] and v - tf32(v) at out[m*ld + slab_width + rel] (slab_width = Kp).
+ * mode 4: MIXED, the value is written as a mixed tensor-core operand (see tgp_gemm_args.mixed): ptr = operand base,
+ *         ld = 2*Kp (fp32 slots per row), slab_width = Kp = tgp_mixed_kpad(width); col_begin maps to operand column 0.
  * mode 3: COLUMN MAX per group of rows_per_group rows (torch.max over the points of a cloud, PoseR.py:33,
  *         FaceRecon.py:146): ptr is an int32 (M / rows_per_group, col_end - col_begin) buffer pre-filled with
  *         INT_MIN that receives atomicMax of the order-preserving encoding e(v) = bits(v) >= 0 ? bits(v) :
@@ -178,6 +181,13 @@ typedef struct {
      * when NULL the exact-fp32 FMA path runs on A / Bmat. */
     const float* A_split;
     const float* B_split;
+    /* mixed = 1: A_split / B_split are MIXED operands (tgp_split_mixed, output mode 4): rows of 8*Kp bytes,
+     * Kp = tgp_mixed_kpad(K): [tf32(x) as fp32 x Kp | bf16(x) x Kp | bf16(x - tf32(x)) x Kp].  The product runs as
+     * tf32(a).tf32(b) on the TF32 pipe plus the two cross terms lo(a).b + a.lo(b) in bf16 (twice the TF32 rate): two
+     * TF32-pass equivalents instead of three, relative error ~2^-19 per product (fp32-summation-noise level at the
+     * heads' K ~ 1e3).  Used for the heads' 1x1 convolutions (PoseR.py, PoseTs.py, FaceRecon.py:89-167), whose outputs
+     * feed no neighbour search; the encoder and the kNN keep the 3xTF32 operands. */
+    int mixed;
 } tgp_gemm_args;
 
 /* feature_map @ weights + bias (gcn3d.py:170) and every 1x1 Conv1d on the path. */
@@ -188,6 +198,10 @@ int tgp_split_kpad(int K);
 /* dst (rows, 2*Kp) = [tf32(src) | src - tf32(src)], zero padded.  src is (rows, K) with row stride ld,
  * or, if src_is_kn, (K, rows) with row stride ld (transposed on the fly: HS_layer.weights, gcn3d.py:125). */
 int tgp_split_tf32(const float* src, long rows, int K, long ld, int src_is_kn, float* dst, tgp_stream_t stream);
+
+/* mixed operand (tgp_gemm_args.mixed): K rounded up to 64, and the split of a row-major (rows, K) matrix (zero padded). */
+int tgp_mixed_kpad(int K);
+int tgp_split_mixed(const float* src, long rows, int K, long ld, float* dst, tgp_stream_t stream);
 
 /* ------------------------------------------------------------------ chamfer (losses/chamfer3D) */
 

@@ -488,3 +488,29 @@ def test_cuda_graph_replay_equals_eager():
         torch.cuda.synchronize()
         for k in eager:
             assert torch.equal(eager[k], out[k]), (trial, k)
+
+
+@pytest.mark.parametrize("M,K,N", [(1028, 1289, 512), (300, 64, 128), (4112, 1024, 256), (257, 200, 96)])
+def test_gemm_mixed_operands(ops, M, K, N):
+    """tgp_gemm with MIXED operands (TF32 hi.hi + bf16 cross terms, the heads' contraction): error vs an fp64 product
+    stays at fp32-summation-noise level, and the mode-4 epilogue writes an operand that a second contraction accepts."""
+    g = torch.Generator().manual_seed(M + K + N)
+    A = torch.randn(M, K, generator=g).cuda()
+    W = (torch.randn(N, K, generator=g) * 0.05).cuda()
+    bias = torch.randn(N, generator=g).cuda()
+    ref = A.double() @ W.double().t() + bias.double()
+    out = torch.empty(M, N, device="cuda")
+    mix = ops.mixed_buf(M, N, "cuda")
+    ops.gemm(None, W, True, [(0, N, out, 0, 0), (0, N, mix, 4, ops.mixed_kpad(N))], bias=bias, K=K,
+             A_split=ops.split_mixed(A), B_split=ops.split_mixed(W), mixed=True)
+    scale = float(ref.abs().max())
+    err = float((out.double() - ref).abs().max())
+    # measured ~1e-6 * scale; the bound below is 2^-16 of the output scale (the fp32 FMA kernel sits at ~2^-20)
+    assert err <= 1.6e-5 * scale, (err, scale)
+    # the mode-4 operand equals the split of the raw output (bit for bit), so the next layer can consume it
+    assert torch.equal(mix, ops.split_mixed(out))
+    W2 = (torch.randn(64, N, generator=g) * 0.1).cuda()
+    out2 = torch.empty(M, 64, device="cuda")
+    ops.gemm(None, W2, True, [(0, 64, out2, 0, 0)], K=N, A_split=mix, B_split=ops.split_mixed(W2), mixed=True)
+    ref2 = out.double() @ W2.double().t()
+    assert float((out2.double() - ref2).abs().max()) <= 1.6e-5 * float(ref2.abs().max())

@@ -33,7 +33,7 @@ class GemmArgs(ctypes.Structure):
                 ("res2", c_void_p), ("ld_res2", c_long),
                 ("scale", c_void_p), ("shift", c_void_p),
                 ("relu", c_int), ("neg_slope", c_void_p), ("nseg", c_int), ("seg", OutSeg * 4),
-                ("A_split", c_void_p), ("B_split", c_void_p)]
+                ("A_split", c_void_p), ("B_split", c_void_p), ("mixed", c_int)]
 
 
 # name -> (restype, argtypes); must list every symbol include/tgpose_b200.h declares
@@ -67,7 +67,9 @@ SIGNATURES = {
     "tgp_chamfer_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                 c_void_p, c_void_p, c_void_p]),
     "tgp_concat_rows": (c_int, [ctypes.POINTER(ConcatSrc), c_int, c_int, c_int, c_void_p, c_long, c_void_p, c_int,
-                                c_void_p]),
+                                c_int, c_void_p]),
+    "tgp_mixed_kpad": (c_int, [c_int]),
+    "tgp_split_mixed": (c_int, [c_void_p, c_long, c_int, c_long, c_void_p, c_void_p]),
     "tgp_dcd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, ctypes.c_float, ctypes.c_float,
                         c_void_p, c_void_p, c_void_p, c_void_p]),
     "tgp_act_bwd": (c_int, [c_void_p, c_long, c_void_p, c_long, c_void_p, c_int, c_long, c_int, c_void_p, c_long,

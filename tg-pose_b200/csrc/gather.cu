@@ -5,6 +5,7 @@
 // writes the k-fold expanded (B,M,k,C) tensor to memory and reduces it in a second pass;
 // the *_max kernels below reduce while gathering, so only (B,M,C) is ever written.
 #include "common.cuh"
+#include <cuda_bf16.h>
 #include <float.h>
 
 namespace tgp {
@@ -201,7 +202,7 @@ struct ConcatDev {
 
 __global__ void __launch_bounds__(256)
 concat_rows_kernel(const __grid_constant__ ConcatDev P, int N, float* __restrict__ out_raw, long ld_raw,
-                   float* __restrict__ out_split, int Kp) {
+                   float* __restrict__ out_split, int Kp, int mixed) {
     const long r = blockIdx.x;
     const long b = r / N;
     int off = 0;
@@ -220,7 +221,11 @@ concat_rows_kernel(const __grid_constant__ ConcatDev P, int N, float* __restrict
                 asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v));
                 const float hi = __uint_as_float(hb);
                 out_split[r * 2 * Kp + off + c] = hi;
-                out_split[r * 2 * Kp + Kp + off + c] = v - hi;
+                if (mixed) {     // [tf32 | bf16(x) | bf16(x - tf32(x))], see tgp_gemm_args.mixed
+                    __nv_bfloat16* h16 = reinterpret_cast<__nv_bfloat16*>(out_split + r * 2 * Kp + Kp);
+                    h16[off + c] = __float2bfloat16_rn(v);
+                    h16[Kp + off + c] = __float2bfloat16_rn(v - hi);
+                } else out_split[r * 2 * Kp + Kp + off + c] = v - hi;
             }
         }
         off += s.C;
@@ -228,7 +233,11 @@ concat_rows_kernel(const __grid_constant__ ConcatDev P, int N, float* __restrict
     if (out_split)
         for (int c = off + threadIdx.x; c < Kp; c += blockDim.x) {
             out_split[r * 2 * Kp + c] = 0.f;
-            out_split[r * 2 * Kp + Kp + c] = 0.f;
+            if (mixed) {
+                __nv_bfloat16* h16 = reinterpret_cast<__nv_bfloat16*>(out_split + r * 2 * Kp + Kp);
+                h16[c] = __float2bfloat16_rn(0.f);
+                h16[Kp + c] = __float2bfloat16_rn(0.f);
+            } else out_split[r * 2 * Kp + Kp + c] = 0.f;
         }
 }
 
@@ -343,8 +352,9 @@ extern "C" int tgp_orl_global(const float* f, const void* idx, int idx_bits, int
 }
 
 extern "C" int tgp_concat_rows(const tgp_concat_src* srcs_host, int nsrc, int B, int N, float* out_raw, long ld_raw,
-                               float* out_split, int Kp, tgp_stream_t stream) {
+                               float* out_split, int Kp, int mixed, tgp_stream_t stream) {
     if (!srcs_host || (!out_raw && !out_split)) return fail(TGP_EINVAL, "tgp_concat_rows: null pointer");
+    if (out_split && mixed && Kp % 64) return fail(TGP_EINVAL, "tgp_concat_rows: a mixed operand needs Kp % 64 == 0");
     if (nsrc < 1 || nsrc > 8 || B <= 0 || N <= 0) return fail(TGP_EINVAL, "tgp_concat_rows: bad sizes");
     ConcatDev P;
     P.nsrc = nsrc;
@@ -356,6 +366,6 @@ extern "C" int tgp_concat_rows(const tgp_concat_src* srcs_host, int nsrc, int B,
     }
     if (out_split && (Kp < total || Kp % 4)) return fail(TGP_EINVAL, "tgp_concat_rows: Kp smaller than the concatenated width");
     if (out_raw && ld_raw < total) return fail(TGP_EINVAL, "tgp_concat_rows: ld_raw smaller than the concatenated width");
-    concat_rows_kernel<<<(unsigned)((long)B * N), 256, 0, as_stream(stream)>>>(P, N, out_raw, ld_raw, out_split, Kp);
+    concat_rows_kernel<<<(unsigned)((long)B * N), 256, 0, as_stream(stream)>>>(P, N, out_raw, ld_raw, out_split, Kp, mixed);
     return check_launch("concat_rows_kernel");
 }

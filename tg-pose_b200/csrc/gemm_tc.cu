@@ -22,6 +22,7 @@
 // is fetched from HBM once and re-read from L2 by the CTAs working on its other column blocks (ncu, round 1:
 // m-fastest order streamed the A operand from DRAM once per column block -- 8.2 GB for the 4096-wide head GEMM).
 #include "tc_common.cuh"
+#include <cuda_bf16.h>
 #include <math_constants.h>
 #include <stdlib.h>
 
@@ -42,7 +43,20 @@ struct EpiDst {
     float* p;
     long rs;
     int lo;      // > 0: split mode, offset of the residual half;  -1: per-group column max (p -> encoded int cell of group 0)
+    int mix;     // > 0: MIXED operand, mix = Kp and `rel` = column inside the operand (p points at the fp32 slot)
+    int rel;
 };
+
+// MIXED operand row: [tf32(x) fp32 x Kp | bf16(x) x Kp | bf16(x - tf32(x)) x Kp]; p = address of the fp32 slot of column rel
+__device__ __forceinline__ void store_mixed(float* p, int Kp, int rel, float v) {
+    uint32_t hb;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v));
+    const float hi = __uint_as_float(hb);
+    p[0] = hi;
+    __nv_bfloat16* h16 = reinterpret_cast<__nv_bfloat16*>(p - rel + Kp) + rel;
+    h16[0] = __float2bfloat16_rn(v);
+    h16[Kp] = __float2bfloat16_rn(v - hi);
+}
 
 // order-preserving float -> int map for atomicMax (mode 3): signed-int order == float order
 __device__ __forceinline__ int enc_ordered(float v) {
@@ -52,7 +66,9 @@ __device__ __forceinline__ int enc_ordered(float v) {
 
 __device__ __forceinline__ void epi_store(EpiDst& d, float v) {
     if (d.p) {
-        if (d.lo) {
+        if (d.mix) {
+            store_mixed(d.p, d.mix, d.rel, v);
+        } else if (d.lo) {
             uint32_t hb;
             asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v));
             const float hi = __uint_as_float(hb);
@@ -119,8 +135,9 @@ __device__ __forceinline__ void epi_rows(uint32_t stg_addr, int lane, int nrows,
 struct VDst {
     float* p;      // (row0, first column of this lane)
     long rs;       // row stride
-    int kind;      // 0 none, 1 raw, 2 split, 3 column max
-    int lo;        // split: offset of the residual half
+    int kind;      // 0 none, 1 raw, 2 split, 3 column max, 4 mixed operand
+    int lo;        // split: offset of the residual half; mixed: Kp
+    int rel;       // mixed: column inside the operand
 };
 
 __device__ __forceinline__ float4 ldg4s(const float* p) {   // 4 scalar loads: parameter vectors may be unaligned views
@@ -144,6 +161,23 @@ __device__ __forceinline__ void vstore(const VDst& d, int row, float4 v) {
         float* q = d.p + row * d.rs;
         *reinterpret_cast<float4*>(q) = hi;
         *reinterpret_cast<float4*>(q + d.lo) = lo;
+    } else if (d.kind == 4) {
+        float4 hi;
+        uint32_t hb;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v.x)); hi.x = __uint_as_float(hb);
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v.y)); hi.y = __uint_as_float(hb);
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v.z)); hi.z = __uint_as_float(hb);
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v.w)); hi.w = __uint_as_float(hb);
+        float* q = d.p + row * d.rs;
+        *reinterpret_cast<float4*>(q) = hi;
+        __nv_bfloat162 a0 = __floats2bfloat162_rn(v.x, v.y), a1 = __floats2bfloat162_rn(v.z, v.w);
+        __nv_bfloat162 l0 = __floats2bfloat162_rn(v.x - hi.x, v.y - hi.y), l1 = __floats2bfloat162_rn(v.z - hi.z, v.w - hi.w);
+        __nv_bfloat16* h16 = reinterpret_cast<__nv_bfloat16*>(q - d.rel + d.lo) + d.rel;      // 8-byte aligned: rel % 4 == 0
+        uint2 pa, pl;
+        pa.x = *reinterpret_cast<uint32_t*>(&a0); pa.y = *reinterpret_cast<uint32_t*>(&a1);
+        pl.x = *reinterpret_cast<uint32_t*>(&l0); pl.y = *reinterpret_cast<uint32_t*>(&l1);
+        *reinterpret_cast<uint2*>(h16) = pa;
+        *reinterpret_cast<uint2*>(h16 + d.lo) = pl;
     }
 }
 
@@ -163,7 +197,7 @@ __device__ __forceinline__ void epi_chunk_vec(const tgp_gemm_args& g, uint32_t s
     float4 bias = make_float4(0.f, 0.f, 0.f, 0.f), sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = bias, gb0 = bias, gb1 = bias;
     const float s0 = g.relu ? 0.f : 1.f;
     float4 sl = make_float4(s0, s0, s0, s0);
-    VDst d0 = {nullptr, 0, 0, 0}, d1 = {nullptr, 0, 0, 0};
+    VDst d0 = {nullptr, 0, 0, 0, 0}, d1 = {nullptr, 0, 0, 0, 0};
     const float* r1p = nullptr;
     const float* r2p = nullptr;
     if (live) {
@@ -176,6 +210,7 @@ __device__ __forceinline__ void epi_chunk_vec(const tgp_gemm_args& g, uint32_t s
                 const int rel = col - g.seg[s].col_begin;
                 VDst d;
                 d.lo = 0;
+                d.rel = rel;
                 if (g.seg[s].mode == 3) {
                     d.kind = 3;
                     d.rs = g.seg[s].col_end - g.seg[s].col_begin;
@@ -187,7 +222,7 @@ __device__ __forceinline__ void epi_chunk_vec(const tgp_gemm_args& g, uint32_t s
                     d.rs = w;
                     d.p = g.seg[s].ptr + ((long)cg * g.M + row0) * w + rr;
                 } else {
-                    d.kind = g.seg[s].mode == 2 ? 2 : 1;
+                    d.kind = g.seg[s].mode == 2 ? 2 : (g.seg[s].mode == 4 ? 4 : 1);
                     d.rs = g.seg[s].ld;
                     d.p = g.seg[s].ptr + zoff + row0 * d.rs + rel;
                     d.lo = g.seg[s].slab_width;
@@ -268,6 +303,7 @@ __device__ __forceinline__ void epi_chunk_vec(const tgp_gemm_args& g, uint32_t s
 template <int BN>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmA16, const __grid_constant__ CUtensorMap tmB16,
                const __grid_constant__ GemmDev P, int Kp, int num_n_tiles, int num_tiles, int dbg,
                int tiles_mn, int kb_per, long zstride, int vec_ok) {
     extern __shared__ __align__(1024) unsigned char tc_smem[];
@@ -312,6 +348,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const int z = t / tiles_mn, tt = t - z * tiles_mn;       // split-K slice z (weight-gradient shapes)
                 const int m0 = (tt / num_n_tiles) * TC_BM, n0 = (tt % num_n_tiles) * BN;
                 const int kb0 = z * kb_per, kb1 = min(kblocks, kb0 + kb_per);
+                if (g.mixed) {
+                    // per 64 columns of K: two TF32 stages (hi.hi, 32 columns each) and two bf16 stages (lo.b, a.lo; 64
+                    // columns = one 128-byte swizzle span each).  Every stage is the same 16 KB + BN*128 B.
+                    for (int k64 = 0; k64 < Kp / 64; ++k64) {
+                        for (int u = 0; u < 4; ++u) {
+                            tc_mbar_wait(empty + stage, phase ^ 1);
+                            unsigned char* sa = base + stage * STAGE_BYTES;
+                            tc_mbar_expect_tx(full + stage, STAGE_BYTES);
+                            if (u < 2) {
+                                tma_load_2d(sa, &tmA, k64 * 64 + u * 32, m0, full + stage);
+                                tma_load_2d(sa + TC_A_BYTES, &tmB, k64 * 64 + u * 32, n0, full + stage);
+                            } else {
+                                // u == 2: lo16(A) . hi16(B);  u == 3: hi16(A) . lo16(B)
+                                tma_load_2d(sa, &tmA16, (u == 2 ? 3 : 2) * Kp + k64 * 64, m0, full + stage);
+                                tma_load_2d(sa + TC_A_BYTES, &tmB16, (u == 2 ? 2 : 3) * Kp + k64 * 64, n0, full + stage);
+                            }
+                            if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+                        }
+                    }
+                    continue;
+                }
                 for (int seg = 0; seg < 3; ++seg) {
                     // segment order: lo.hi, hi.lo, hi.hi
                     const int a_off = (seg == 0) ? Kp : 0, b_off = (seg == 1) ? Kp : 0;
@@ -333,6 +390,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // ===================== MMA issuer =====================
         if (lane == 0) {
             constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+            // kind::f16 with bf16 operands (format 1), fp32 accumulate
+            constexpr uint32_t idesc16 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
@@ -344,17 +403,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const uint32_t d_tmem = tmem_base + acc * BN;
                 uint32_t accum = 0;
                 const int zz = t / tiles_mn;
-                const int nkb = 3 * (min(kblocks, zz * kb_per + kb_per) - zz * kb_per);
+                const int nkb = g.mixed ? 4 * (Kp / 64) : 3 * (min(kblocks, zz * kb_per + kb_per) - zz * kb_per);
                 for (int kb = 0; kb < nkb; ++kb) {
                     tc_mbar_wait(full + stage, phase);
                     tc_fence_after();
                     const uint32_t sa = s_u32(base + stage * STAGE_BYTES);
                     const uint64_t adesc = make_sw128_desc(sa), bdesc = make_sw128_desc(sa + TC_A_BYTES);
+                    if (g.mixed && (kb & 2)) {
+                        // bf16 stage: 64 columns of K, 16 per instruction = the same +32 B descriptor step
 #pragma unroll
-                    for (int k = 0; k < ((dbg & 2) ? 0 : TC_BK / 8); ++k) {
-                        // +32 B along K inside the swizzle span = +2 in the descriptor's 16-byte address units
-                        umma_tf32(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, accum);
-                        accum = 1;
+                        for (int k = 0; k < 4; ++k) {
+                            umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc16, accum);
+                            accum = 1;
+                        }
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < ((dbg & 2) ? 0 : TC_BK / 8); ++k) {
+                            // +32 B along K inside the swizzle span = +2 in the descriptor's 16-byte address units
+                            umma_tf32(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, accum);
+                            accum = 1;
+                        }
                     }
                     umma_commit(empty + stage);
                     if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
@@ -409,7 +477,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const bool live = col < g.Ncols && nrows > 0 && !(dbg & 1);
                 // per-column constants of this lane
                 float bias = 0.f, sc = 1.f, sh = 0.f, slope = g.relu ? 0.f : 1.f, gbv0 = 0.f, gbv1 = 0.f;
-                EpiDst d0 = {nullptr, 0, 0}, d1 = {nullptr, 0, 0};
+                EpiDst d0 = {nullptr, 0, 0, 0, 0}, d1 = {nullptr, 0, 0, 0, 0};
                 const float* r1p = nullptr;
                 const float* r2p = nullptr;
                 if (live) {
@@ -421,6 +489,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         if (s < g.nseg && col >= g.seg[s].col_begin && col < g.seg[s].col_end) {
                             const int rel = col - g.seg[s].col_begin;
                             EpiDst d;
+                            d.mix = 0; d.rel = 0;
                             if (g.seg[s].mode == 3) {
                                 // per-group column max: rows_per_group >= 32, so a 32-row block touches <= 2 groups
                                 d.rs = g.seg[s].col_end - g.seg[s].col_begin;
@@ -435,6 +504,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                 d.rs = g.seg[s].ld;
                                 d.p = g.seg[s].ptr + z * zstride + row0 * d.rs + rel;
                                 d.lo = g.seg[s].mode == 2 ? g.seg[s].slab_width : 0;
+                                if (g.seg[s].mode == 4) { d.mix = g.seg[s].slab_width; d.rel = rel; }
                             }
                             if (!d0.p) d0 = d; else d1 = d;     // at most two destinations per column (raw + split)
                         }
@@ -497,6 +567,14 @@ __global__ void split_tf32_kernel(const float* __restrict__ src, long rows, int 
     }
 }
 
+// MIXED operand of a row-major (rows, K) matrix: [tf32(x) | bf16(x) | bf16(x - tf32(x))], zero padded to Kp (multiple of 64)
+__global__ void split_mixed_kernel(const float* __restrict__ src, long rows, int K, long ld, int Kp, float* __restrict__ dst) {
+    for (long r = blockIdx.x; r < rows; r += gridDim.x) {
+        float* d = dst + r * 2 * Kp;
+        for (int k = threadIdx.x; k < Kp; k += blockDim.x) store_mixed(d + k, Kp, k, k < K ? __ldg(src + r * ld + k) : 0.f);
+    }
+}
+
 // transposing split for large (K, rows) sources (activations as weight-gradient operands): 32x32 tiles through
 // shared memory, reads coalesced along rows, writes coalesced along K.
 __global__ void __launch_bounds__(256)
@@ -542,6 +620,18 @@ using namespace tgp;
 
 extern "C" int tgp_split_kpad(int K) { return (K + TC_BK - 1) / TC_BK * TC_BK; }
 
+extern "C" int tgp_mixed_kpad(int K) { return (K + 63) / 64 * 64; }
+
+extern "C" int tgp_split_mixed(const float* src, long rows, int K, long ld, float* dst, tgp_stream_t stream) {
+    if (!src || !dst) return fail(TGP_EINVAL, "tgp_split_mixed: null pointer");
+    if (rows <= 0 || K <= 0) return fail(TGP_EINVAL, "tgp_split_mixed: sizes must be positive");
+    if ((uintptr_t)dst % 16) return fail(TGP_EINVAL, "tgp_split_mixed: dst must be 16-byte aligned");
+    const int Kp = tgp_mixed_kpad(K);
+    long nb = rows < (long)TGP_NUM_SMS * 64 ? rows : (long)TGP_NUM_SMS * 64;
+    split_mixed_kernel<<<(unsigned)nb, 256, 0, as_stream(stream)>>>(src, rows, K, ld, Kp, dst);
+    return check_launch("split_mixed_kernel");
+}
+
 extern "C" int tgp_split_tf32(const float* src, long rows, int K, long ld, int src_is_kn, float* dst,
                               tgp_stream_t stream) {
     if (!src || !dst) return fail(TGP_EINVAL, "tgp_split_tf32: null pointer");
@@ -562,12 +652,22 @@ extern "C" int tgp_split_tf32(const float* src, long rows, int K, long ld, int s
 
 template <int BN>
 static int launch_tc(const tgp_gemm_args* a, cudaStream_t st, int ksplit = 1) {
-    const int Kp = tgp_split_kpad(a->K);
-    CUtensorMap tmA, tmB;
+    const int Kp = a->mixed ? tgp_mixed_kpad(a->K) : tgp_split_kpad(a->K);
+    CUtensorMap tmA, tmB, tmA16, tmB16;
     int rc = tgp_make_map(&tmA, a->A_split, a->M, Kp, TC_BM);
     if (rc) return rc;
     rc = tgp_make_map(&tmB, a->B_split, a->Ncols, Kp, BN);
     if (rc) return rc;
+    if (a->mixed) {
+        if (ksplit != 1) return fail(TGP_EINVAL, "tgp_gemm: split-K is not available for mixed operands");
+        rc = tgp_make_map_bf16(&tmA16, a->A_split, a->M, Kp, TC_BM);
+        if (rc) return rc;
+        rc = tgp_make_map_bf16(&tmB16, a->B_split, a->Ncols, Kp, BN);
+        if (rc) return rc;
+    } else {
+        tmA16 = tmA;
+        tmB16 = tmB;
+    }
     GemmDev P;
     P.a = *a;
     const int num_m_tiles = (int)((a->M + TC_BM - 1) / TC_BM);
@@ -596,12 +696,12 @@ static int launch_tc(const tgp_gemm_args* a, cudaStream_t st, int ksplit = 1) {
         if (sg.mode == 3) continue;
         vec_ok = vec_ok && al16(sg.ptr);
         if (sg.mode == 1) vec_ok = vec_ok && sg.slab_width % 4 == 0;
-        else vec_ok = vec_ok && sg.ld % 4 == 0 && (sg.mode != 2 || sg.slab_width % 4 == 0);
+        else vec_ok = vec_ok && sg.ld % 4 == 0 && ((sg.mode != 2 && sg.mode != 4) || sg.slab_width % 4 == 0);
     }
     { const char* e = getenv("TGP_TC_SCALAR_EPI"); if (e && e[0] == '1') vec_ok = 0; }
     static int dbg = -1;
     if (dbg < 0) { const char* e = getenv("TGP_TC_DEBUG"); dbg = e ? atoi(e) : 0; }
-    gemm_tc_kernel<BN><<<grid, TC_THREADS, smem, st>>>(tmA, tmB, P, Kp, num_n_tiles, num_tiles, dbg, tiles_mn, kb_per, zstride, vec_ok);
+    gemm_tc_kernel<BN><<<grid, TC_THREADS, smem, st>>>(tmA, tmB, tmA16, tmB16, P, Kp, num_n_tiles, num_tiles, dbg, tiles_mn, kb_per, zstride, vec_ok);
     return check_launch("gemm_tc_kernel");
 }
 

@@ -44,6 +44,13 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s_u32(bar)) : "memory");
 }
@@ -119,3 +126,19 @@ static inline int tgp_make_map(CUtensorMap* tm, const float* ptr, long rows, lon
     return TGP_OK;
 }
 
+
+// bf16 view of a MIXED operand (rows, 8*Kp bytes per row): box = (64 bf16 = 128 bytes, box_rows rows), 128B swizzle.
+// Columns [2Kp, 3Kp) hold bf16(x), [3Kp, 4Kp) hold bf16(x - tf32(x)).
+static inline int tgp_make_map_bf16(CUtensorMap* tm, const float* ptr, long rows, long Kp, int box_rows) {
+    tgp_encode_fn enc = tgp_get_encode();
+    if (!enc) return tgp::fail(TGP_EINVAL, "tgp_gemm: cuTensorMapEncodeTiled unavailable");
+    cuuint64_t gdim[2] = {(cuuint64_t)(4 * Kp), (cuuint64_t)rows};
+    cuuint64_t gstride[1] = {(cuuint64_t)(8 * Kp)};
+    cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<float*>(ptr), gdim, gstride, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return tgp::fail(TGP_EINVAL, "tgp_gemm: cuTensorMapEncodeTiled (bf16) failed");
+    return TGP_OK;
+}

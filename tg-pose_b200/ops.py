@@ -162,7 +162,7 @@ def orl_global(f, idx, want_arg=False):
     return (g, arg) if want_arg else g
 
 
-def concat_rows(sources, B, N, want_raw=True, want_split=False):
+def concat_rows(sources, B, N, want_raw=True, want_split=False, mixed=False):
     """[src_0 | src_1 | ...] per point.  sources: list of (tensor2d (rows, C), idx or None, n_src):
     idx None & n_src > 0: identity rows; idx (B,N) int32: gather from a cloud of n_src rows; n_src == 0: per-cloud row.
     Returns (raw (B*N, total) or None, split (B*N, 2*kpad(total)) or None)."""
@@ -179,9 +179,10 @@ def concat_rows(sources, B, N, want_raw=True, want_split=False):
         total += t.shape[1]
     M = B * N
     raw = torch.empty((M, total), dtype=torch.float32, device=dev) if want_raw else None
-    kp = kpad(total)
+    kp = mixed_kpad(total) if mixed else kpad(total)
     spl = torch.empty((M, 2 * kp), dtype=torch.float32, device=dev) if want_split else None
-    _run("concat_rows", _lib.load().tgp_concat_rows, arr, len(sources), B, N, _p(raw), total, _p(spl), kp, _stream())
+    _run("concat_rows", _lib.load().tgp_concat_rows, arr, len(sources), B, N, _p(raw), total, _p(spl), kp,
+         1 if mixed else 0, _stream())
     return raw, spl
 
 
@@ -275,7 +276,8 @@ PARAM_CACHE = ParamCache()
 
 
 def gemm(A, Bmat, b_is_nk, segs, bias=None, group_bias=None, rows_per_group=0, res1=None, res2=None,
-         scale=None, shift=None, relu=False, K=None, Ncols=None, A_split=None, B_split=None, neg_slope=None, tc=None):
+         scale=None, shift=None, relu=False, K=None, Ncols=None, A_split=None, B_split=None, neg_slope=None, tc=None,
+         mixed=False):
     """C = A @ B (+ epilogue) written to `segs` = [(col_begin, col_end, tensor, mode, slab_width)].
     A: (M,K) with unit column stride; Bmat: (K,Ncols) or, if b_is_nk, (Ncols,K); both may be row-strided views."""
     assert Bmat.stride(-1) == 1
@@ -305,6 +307,9 @@ def gemm(A, Bmat, b_is_nk, segs, bias=None, group_bias=None, rows_per_group=0, r
     a.Bmat, a.ldb, a.b_is_nk = Bmat.data_ptr(), Bmat.stride(0), 1 if b_is_nk else 0
     if A_split is not None and B_split is not None:
         a.A_split, a.B_split = A_split.data_ptr(), B_split.data_ptr()
+    a.mixed = 1 if mixed else 0
+    if mixed:
+        assert A_split is not None and B_split is not None, "mixed operands must be supplied (split_mixed / mode-4 epilogue)"
     a.M, a.K, a.Ncols = M, K, Ncols
     a.bias = bias.data_ptr() if bias is not None else None
     a.group_bias = group_bias.data_ptr() if group_bias is not None else None
@@ -321,10 +326,10 @@ def gemm(A, Bmat, b_is_nk, segs, bias=None, group_bias=None, rows_per_group=0, r
     a.neg_slope = neg_slope.data_ptr() if neg_slope is not None else None
     a.nseg = len(segs)
     for i, (c0, c1, t, mode, sw) in enumerate(segs):
-        a.seg[i] = OutSeg(c0, c1, mode, sw, t.stride(0) if mode in (0, 2) else 0, t.data_ptr())
+        a.seg[i] = OutSeg(c0, c1, mode, sw, t.stride(0) if mode in (0, 2, 4) else 0, t.data_ptr())
     name = "gemm_tc" if A_split is not None and B_split is not None else "gemm"
     if EVENT_LOG is not None:
-        EVENT_LOG.setdefault("__gemm_shapes__", []).append((name, M, K, Ncols))
+        EVENT_LOG.setdefault("__gemm_shapes__", []).append((name, M, K, Ncols, bool(mixed)))
     _run(name, _lib.load().tgp_gemm, ctypes.byref(a), _stream())
 
 
@@ -335,6 +340,25 @@ def decode_max(enc_i32):
 
 def kpad(K):
     return _lib.load().tgp_split_kpad(K)
+
+
+def mixed_kpad(K):
+    return _lib.load().tgp_mixed_kpad(K)
+
+
+def split_mixed(x2d):
+    """MIXED tensor-core operand of a row-major (rows, K) matrix (include/tgpose_b200.h, tgp_gemm_args.mixed):
+    (rows, 2*mixed_kpad(K)) fp32 slots = [tf32(x) | bf16(x), bf16(x - tf32(x))]."""
+    assert x2d.stride(-1) == 1
+    rows, K = x2d.shape
+    dst = torch.empty((rows, 2 * mixed_kpad(K)), dtype=torch.float32, device=x2d.device)
+    _run("split_mixed", _lib.load().tgp_split_mixed, _p(x2d), rows, K, x2d.stride(0), _p(dst), _stream())
+    return dst
+
+
+def mixed_buf(M, C, device):
+    kp = mixed_kpad(C)
+    return (torch.zeros if kp != C else torch.empty)((M, 2 * kp), dtype=torch.float32, device=device)
 
 
 def linear_fused(x2d, weight_nk, want_raw=True, want_split=False, x_split=None, w_split=None, **kw):

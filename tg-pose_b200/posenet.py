@@ -51,7 +51,9 @@ class _Packed:
         self.shift = torch.cat([f[1] for f in folds]).contiguous()
         self.slope = torch.cat([torch.full((m.shape[0],), float(sl), device=self.w.device)
                                 for m, sl in zip(mats, slopes)]).contiguous()
-        self.w_split = ops.split_tf32(self.w)
+        # the heads' contractions run on MIXED operands (TF32 + bf16 cross terms): two TF32-pass equivalents instead of
+        # three at ~2^-19 relative error per product; nothing downstream of the heads is a neighbour search
+        self.w_split = ops.split_mixed(self.w)
 
 
 def pointwise(x_cl, conv, bn=None, act=None, slope=0.2):
@@ -324,12 +326,12 @@ class PoseNet9D(nn.Module):
                 t_ = torch.full((M // rows_per_group, n), -2 ** 31, dtype=torch.int32, device=dev)
                 segs.append((c0, c0 + n, t_, 3, 0))
             else:
-                t_ = ops._split_buf(M, n, dev)
-                segs.append((c0, c0 + n, t_, 2, ops.kpad(n)))
+                t_ = ops.mixed_buf(M, n, dev)
+                segs.append((c0, c0 + n, t_, 4, ops.mixed_kpad(n)))
             res.append(t_)
             c0 += n
         ops.gemm(None, pk.w, True, segs, scale=pk.scale, shift=pk.shift, neg_slope=pk.slope, K=K,
-                 A_split=x_split, B_split=pk.w_split, rows_per_group=rows_per_group, **kw)
+                 A_split=x_split, B_split=pk.w_split, rows_per_group=rows_per_group, mixed=True, **kw)
         return res
 
     def _forward_fused_eval(self, points, obj_id, enable_proj=False):
@@ -345,7 +347,7 @@ class PoseNet9D(nn.Module):
         # [feat | xyz] (Pose_Ts input, PoseNet9D.py:63) assembled straight into the tensor-core operand: upsampling
         # gathers, one-hot broadcast and both torch.cat of the reference in one launch
         src = enc.concat_sources(parts, enc.one_hot(obj_id, B), extra=[(centred.reshape(M, 3), None, 1)])
-        raw, xs = ops.concat_rows(src, B, N, want_raw=self.train_outputs, want_split=True)
+        raw, xs = ops.concat_rows(src, B, N, want_raw=self.train_outputs, want_split=True, mixed=True)
         # stage 1: four 1286/1289 -> 1024 convolutions as one contraction over the shared operand; conv_5's output is
         # only ever max-pooled over the cloud (FaceRecon.py:145-146), so that pooling happens in the epilogue
         hg, hr, f5max, ht = self._stage(pk["stage1"], xs, kin, [(1024, "split"), (1024, "split"), (1024, "max"),
