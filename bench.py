@@ -240,6 +240,9 @@ def run_ours(args):
     out_keys = ("p_green_R", "p_red_R", "f_green_R", "f_red_R", "Pred_T", "Pred_s")
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     h2d = d2h = 0
+    # every step's pose outputs are read back into pinned host memory (one buffer per step); the copies are queued on the
+    # stream behind the step that produced them and the host waits once, after the last step, inside the timed region
+    res_host = [torch.empty((B, 18), dtype=torch.float32).pin_memory() for _ in range(args.steps)]
     barrier()
     e0.record()
     for i in range(args.steps):
@@ -248,11 +251,14 @@ def run_ours(args):
             out = step(hp.to(dev, non_blocking=True), hc.to(dev, non_blocking=True))
         else:
             out = step(hp, hc)        # pinned host -> the graph's static input buffers (H2D inside the timed region)
-        res = torch.cat([out[k].reshape(B, -1) for k in out_keys], dim=1).cpu()
+        res = torch.cat([out[k].reshape(B, -1) for k in out_keys], dim=1)
+        res_host[i].copy_(res, non_blocking=True)
         if i == 0:
             h2d = hp.numel() * 4 + hc.numel() * 4
             d2h = res.numel() * 4
     e1.record()
+    e1.synchronize()
+    assert all(bool(torch.isfinite(r).all()) for r in res_host)
     barrier()
     e2e_ms = e0.elapsed_time(e1)
     clocks = sampler.stop() if rank == 0 else None
