@@ -242,7 +242,7 @@ def run_ours(args):
     h2d = d2h = 0
     # every step's pose outputs are read back into pinned host memory (one buffer per step); the copies are queued on the
     # stream behind the step that produced them and the host waits once, after the last step, inside the timed region
-    res_host = [torch.empty((B, 18), dtype=torch.float32).pin_memory() for _ in range(args.steps)]
+    res_host = [torch.empty((B, 14), dtype=torch.float32).pin_memory() for _ in range(args.steps)]   # 3+3+1+1+3+3 pose values
     barrier()
     e0.record()
     for i in range(args.steps):
