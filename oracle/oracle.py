@@ -130,9 +130,19 @@ def layer_conv(xyz, idx, directions, P, S, C):
     return out
 
 
+# bench.py's CPU baseline sets this: the dense contractions then go through numpy's BLAS sgemm (what the reference's
+# torch CPU path uses, MKL/OpenBLAS) instead of the plain C loop nest, so that the timed port is not handicapped.
+USE_BLAS = False
+
+
 def gemm_bias(A, W, bias=None):
     """A (..., K) @ W (K, Nout) + bias."""
     A, W = _f32(A), _f32(W)
+    if USE_BLAS:
+        out = A.reshape(-1, W.shape[0]) @ W
+        if bias is not None:
+            out += _f32(bias)
+        return out.reshape(A.shape[:-1] + (W.shape[1],))
     K, Nout = W.shape
     M = A.size // K
     b = _f32(bias) if bias is not None else None
