@@ -213,6 +213,39 @@ concat_rows_kernel(const __grid_constant__ ConcatDev P, int N, float* __restrict
         else if (s.idx) row = b * s.n_src + __ldg(s.idx + r);              // nearest-upsampling gather
         else row = r;
         const float* src = s.ptr + row * s.ld;
+        // 128-bit path: source block and its destination offset are multiples of 4 floats and 16-byte aligned
+        const bool v4 = (s.C % 4 == 0) && (off % 4 == 0) && (s.ld % 4 == 0) && (((uintptr_t)s.ptr & 15) == 0) &&
+                        (!out_raw || (ld_raw % 4 == 0 && ((uintptr_t)out_raw & 15) == 0));
+        if (v4) {
+            for (int c = threadIdx.x * 4; c < s.C; c += blockDim.x * 4) {
+                const float4 v = __ldg(reinterpret_cast<const float4*>(src + c));
+                if (out_raw) *reinterpret_cast<float4*>(out_raw + r * ld_raw + off + c) = v;
+                if (out_split) {
+                    float4 hi;
+                    uint32_t hb;
+                    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v.x)); hi.x = __uint_as_float(hb);
+                    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v.y)); hi.y = __uint_as_float(hb);
+                    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v.z)); hi.z = __uint_as_float(hb);
+                    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v.w)); hi.w = __uint_as_float(hb);
+                    float* q = out_split + r * 2 * Kp + off + c;
+                    *reinterpret_cast<float4*>(q) = hi;
+                    if (mixed) {
+                        __nv_bfloat162 a0 = __floats2bfloat162_rn(v.x, v.y), a1 = __floats2bfloat162_rn(v.z, v.w);
+                        __nv_bfloat162 l0 = __floats2bfloat162_rn(v.x - hi.x, v.y - hi.y), l1 = __floats2bfloat162_rn(v.z - hi.z, v.w - hi.w);
+                        __nv_bfloat16* h16 = reinterpret_cast<__nv_bfloat16*>(out_split + r * 2 * Kp + Kp) + off + c;
+                        uint2 pa, pl;
+                        pa.x = *reinterpret_cast<uint32_t*>(&a0); pa.y = *reinterpret_cast<uint32_t*>(&a1);
+                        pl.x = *reinterpret_cast<uint32_t*>(&l0); pl.y = *reinterpret_cast<uint32_t*>(&l1);
+                        *reinterpret_cast<uint2*>(h16) = pa;
+                        *reinterpret_cast<uint2*>(h16 + Kp) = pl;
+                    } else {
+                        *reinterpret_cast<float4*>(q + Kp) = make_float4(v.x - hi.x, v.y - hi.y, v.z - hi.z, v.w - hi.w);
+                    }
+                }
+            }
+            off += s.C;
+            continue;
+        }
         for (int c = threadIdx.x; c < s.C; c += blockDim.x) {
             const float v = __ldg(src + c);
             if (out_raw) out_raw[r * ld_raw + off + c] = v;
