@@ -5,14 +5,14 @@ set -u
 R=${1:-r01}
 O=gpurun_out
 mkdir -p $O
-if [ "${2:-all}" != "forward" ]; then
+if [ "${2:-all}" = "all" ]; then
 # 1. launch list of the benchmark command (eager launches: one row per kernel; cold-cache, serialised)
 python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-graph > $O/${R}_plain_bench.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file $O/${R}_launches.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-graph > $O/${R}_ncu_launches.log 2>&1
 fi
 # (ncu matches the base name, without the tgp:: namespace)
-KERNELS="^(concat_rows|edge_record|gather_max|gather_rows|gemm_naive|gemm_skinny|gemm_simt|gemm_tc|knn_tc|knn_xyz|knn_feat|layer_conv|nearest|orl_|rownorm|select_rows|split_tf32|surface_conv|direction_norm)"
+KERNELS="^(concat_rows|edge_record|gather_max|gather_rows|gemm_naive|gemm_skinny|gemm_simt|gemm_tc|knn_tc|knn_xyz|knn_feat|layer_conv|nearest|orl_|rownorm|select_rows|split_tf32|split_mixed|surface_conv|direction_norm)"
 # 2. every library kernel of ONE forward (third forward of the script: warm caches / packs) with the sections the
 #    roofline needs; the report stays on the box (it exceeds the 64 MiB return limit), only its raw CSV page comes back
 python scripts/profile_forward.py > $O/${R}_plain_fwd.log 2>&1 &&
@@ -23,6 +23,7 @@ ncu --section SpeedOfLight --section MemoryWorkloadAnalysis --section ComputeWor
     python scripts/profile_forward.py > $O/${R}_ncu_forward.log 2>&1 &&
 ncu -i /tmp/${R}_forward.ncu-rep --page raw --csv > $O/${R}_forward_raw.csv
 tail -2 $O/${R}_ncu_forward.log
+if [ "${2:-all}" = "fwdonly" ]; then exit 0; fi
 # 3. the dominant kernel (tcgen05 GEMM), full set with source correlation: the 17 launches of one forward
 python scripts/profile_forward.py > $O/${R}_plain_fwd2.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:"^gemm_tc" -s 34 -c 17 -o $O/${R}_gemm_tc -f \
