@@ -520,6 +520,43 @@ def kernel_report(event_log, steps, B, peaks):
                                           "achieved = algorithmic 2MNK flops",
                            "traffic_source": "sum of dram__bytes_read+write over the gemm_tc launches of one forward, "
                                              "profiles/*_kernels.json (ncu); bytes per step"}
+    # the other kernels of the step against their roofs (algorithmic work per SURVEY 8d at this step's shapes; times are
+    # the per-call CUDA-event sums of the eager pass, which include a few us of event overhead per launch)
+    N1, N2 = N0 // 4, N0 // 16
+    k2 = min(k, N2 // 8)
+    def ms(name):
+        return agg[name]["ms_per_step"] / 1e3 if name in agg else None
+    kr = {}
+    if ms("knn_feat"):
+        fl = B * sum(n * n * (2 * d + 3) + n * n for n, d in ((N0, 128), (N1, 128), (N1, 256), (N2, 256)))
+        kr["knn_feat"] = {"bound": "fp32 roof (inner products run on the tensor pipe)", "achieved_tflops": fl / ms("knn_feat") / 1e12,
+                          "frac_fp32": fl / ms("knn_feat") / 1e12 / FP32_PEAK_TFLOPS}
+    if ms("knn_xyz"):
+        fl = B * sum(n * n * 9 + n * n for n in (N0, N1, N2))
+        kr["knn_xyz"] = {"bound": "fp32 / selection", "achieved_tflops": fl / ms("knn_xyz") / 1e12,
+                         "frac_fp32": fl / ms("knn_xyz") / 1e12 / FP32_PEAK_TFLOPS,
+                         "gpairs_s": B * (N0 * N0 + N1 * N1 + N2 * N2) / ms("knn_xyz") / 1e9}
+    if ms("layer_conv_fwd"):
+        shp = [(N0, k, 128), (N1, k, 256), (N1, k, 256), (N2, k2, 512)]
+        fl = B * sum(n * kk * S * c * 9 + n * S * c for n, kk, c in shp)
+        by = B * sum(4 * (3 * n + S * c * n + c * n + c * n + 3 * S * c) + 4 * n * kk for n, kk, c in shp)
+        kr["layer_conv_fwd"] = {"bound": "fp32 issue", "achieved_tflops": fl / ms("layer_conv_fwd") / 1e12,
+                                "frac_fp32": fl / ms("layer_conv_fwd") / 1e12 / FP32_PEAK_TFLOPS,
+                                "compulsory_gbs": by / ms("layer_conv_fwd") / 1e9,
+                                "frac_hbm": by / ms("layer_conv_fwd") / 1e9 / peaks["hbm_gbs"]}
+    if ms("surface_conv_fwd"):
+        fl = B * (N0 * k * S * 128 * 8 + N0 * S * 128)
+        kr["surface_conv_fwd"] = {"bound": "fp32", "achieved_tflops": fl / ms("surface_conv_fwd") / 1e12,
+                                  "frac_fp32": fl / ms("surface_conv_fwd") / 1e12 / FP32_PEAK_TFLOPS}
+    if ms("orl_global"):
+        by = B * sum(4 * n * c + 4 * n * kk + 4 * c for n, c, kk in ((N0, 128, k), (N0, 128, k), (N1, 256, k), (N1, 256, k), (N2, 512, k2)))
+        kr["orl_global"] = {"bound": "hbm", "achieved_gbs": by / ms("orl_global") / 1e9,
+                            "frac_hbm": by / ms("orl_global") / 1e9 / peaks["hbm_gbs"]}
+    if ms("concat_rows"):
+        by = B * N0 * (4 * 1289 + 8 * 1344)
+        kr["concat_rows"] = {"bound": "hbm", "achieved_gbs": by / ms("concat_rows") / 1e9,
+                             "frac_hbm": by / ms("concat_rows") / 1e9 / peaks["hbm_gbs"]}
+    out["kernel_rooflines"] = {kk_: {a: (round(b, 4) if isinstance(b, float) else b) for a, b in v.items()} for kk_, v in kr.items()}
     if os.environ.get("TGP_BENCH_GEMM_TABLE"):
         shapes = event_log.get("__gemm_shapes__", [])
         evs = {"gemm": list(event_log.get("gemm", [])), "gemm_tc": list(event_log.get("gemm_tc", []))}
