@@ -193,6 +193,9 @@ typedef struct {
 /* feature_map @ weights + bias (gcn3d.py:170) and every 1x1 Conv1d on the path. */
 int tgp_gemm(const tgp_gemm_args* args_host, tgp_stream_t stream);
 
+/* decode the int32 cells of a mode-3 (column max) segment back to fp32: out[i] = float(e^-1(enc[i])). */
+int tgp_decode_max(const int32_t* enc, long n, float* out, tgp_stream_t stream);
+
 /* K rounded up to the tensor-core K block (32). */
 int tgp_split_kpad(int K);
 /* dst (rows, 2*Kp) = [tf32(src) | src - tf32(src)], zero padded.  src is (rows, K) with row stride ld,

@@ -514,3 +514,26 @@ def test_gemm_mixed_operands(ops, M, K, N):
     ops.gemm(None, W2, True, [(0, 64, out2, 0, 0)], K=N, A_split=mix, B_split=ops.split_mixed(W2), mixed=True)
     ref2 = out.double() @ W2.double().t()
     assert float((out2.double() - ref2).abs().max()) <= 1.6e-5 * float(ref2.abs().max())
+
+
+def test_posenet_inference_output_set_and_folded_ph_tail():
+    """train_outputs=False (FLAGS.train = 0, PoseNet9D.py:68): only the six pose outputs are returned, they equal the
+    train_outputs=True run bit for bit, and the internally computed recon (PH tail folded into one matrix) agrees with
+    the unfolded chain."""
+    from tgpose_b200.posenet import PoseNet9D
+    g = golden("posenet")
+    torch.manual_seed(0)
+    net = PoseNet9D(train_outputs=True).cuda().eval()
+    pts, cat = cu(g["pts"]), cu(g["cat_id"])
+    with torch.no_grad():
+        torch.manual_seed(7)
+        full = net(pts, cat)
+        recon_full = net._last_recon.clone()
+        net.train_outputs = False
+        torch.manual_seed(7)
+        lean = net(pts, cat)
+        recon_lean = net._last_recon.clone()
+    assert set(lean) == {"p_green_R", "p_red_R", "f_green_R", "f_red_R", "Pred_T", "Pred_s"}
+    for k in lean:
+        assert torch.equal(lean[k], full[k]), k
+    assert_close(nump(recon_lean), nump(recon_full), rel=1e-4, floor=2e-6, what="recon with the folded PH tail")

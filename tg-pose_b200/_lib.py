@@ -68,6 +68,7 @@ SIGNATURES = {
                                 c_void_p, c_void_p, c_void_p]),
     "tgp_concat_rows": (c_int, [ctypes.POINTER(ConcatSrc), c_int, c_int, c_int, c_void_p, c_long, c_void_p, c_int,
                                 c_int, c_void_p]),
+    "tgp_decode_max": (c_int, [c_void_p, c_long, c_void_p, c_void_p]),
     "tgp_mixed_kpad": (c_int, [c_int]),
     "tgp_split_mixed": (c_int, [c_void_p, c_long, c_int, c_long, c_void_p, c_void_p]),
     "tgp_dcd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, ctypes.c_float, ctypes.c_float,

@@ -191,9 +191,23 @@ __global__ void gemm_naive_kernel(const __grid_constant__ GemmDev P, long total)
     epilogue_store(g, m, n, acc);
 }
 
+__global__ void decode_max_kernel(const int* __restrict__ enc, long n, float* __restrict__ out) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        const int e = enc[i];
+        out[i] = __int_as_float(e >= 0 ? e : e ^ 0x7fffffff);
+    }
+}
+
 }  // namespace tgp
 
 using namespace tgp;
+
+extern "C" int tgp_decode_max(const int32_t* enc, long n, float* out, tgp_stream_t stream) {
+    if (!enc || !out || n <= 0) return fail(TGP_EINVAL, "tgp_decode_max: bad arguments");
+    decode_max_kernel<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(enc, n, out);
+    return check_launch("decode_max_kernel");
+}
 
 int tgp_gemm_validate(const tgp_gemm_args* a) {
     if (!a) return fail(TGP_EINVAL, "tgp_gemm: null args");

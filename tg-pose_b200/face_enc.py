@@ -63,10 +63,13 @@ class Face_Enc(nn.Module):
         return t
 
     def _bn_post(self, bn):
-        """eval BatchNorm folded to per-channel (scale, shift) + ReLU for the GEMM epilogue."""
-        scale = bn.weight.detach() * torch.rsqrt(bn.running_var + bn.eps)
-        shift = bn.bias.detach() - bn.running_mean * scale
-        return (scale.contiguous(), shift.contiguous(), True)
+        """eval BatchNorm folded to per-channel (scale, shift) + ReLU for the GEMM epilogue; recomputed only when a
+        parameter or running statistic of the layer changes."""
+        def build():
+            scale = bn.weight.detach() * torch.rsqrt(bn.running_var + bn.eps)
+            shift = bn.bias.detach() - bn.running_mean * scale
+            return (scale.contiguous(), shift.contiguous(), True)
+        return ops.PARAM_CACHE.get((bn.weight, bn.bias, bn.running_mean, bn.running_var), ("bn_post", bn.eps), build)
 
     def _bn_relu(self, bn, x):
         return F.relu(bn(x.transpose(1, 2)).transpose(1, 2))

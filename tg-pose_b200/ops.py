@@ -334,8 +334,10 @@ def gemm(A, Bmat, b_is_nk, segs, bias=None, group_bias=None, rows_per_group=0, r
 
 
 def decode_max(enc_i32):
-    """inverse of the order-preserving int encoding written by a column-max GEMM segment (mode 3) -> fp32."""
-    return torch.where(enc_i32 >= 0, enc_i32, enc_i32 ^ 0x7fffffff).view(torch.float32)
+    """inverse of the order-preserving int encoding written by a column-max GEMM segment (mode 3) -> fp32 (new tensor)."""
+    out = torch.empty(enc_i32.shape, dtype=torch.float32, device=enc_i32.device)
+    _run("decode_max", _lib.load().tgp_decode_max, _p(enc_i32), enc_i32.numel(), _p(out), _stream())
+    return out
 
 
 def kpad(K):

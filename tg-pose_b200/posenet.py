@@ -305,6 +305,13 @@ class PoseNet9D(nn.Module):
                                (ph.linear4.bias.detach() + ph.linear5.bias.detach()).contiguous()),
                     "dec1_w": c[0].weight.detach().reshape(512, FEAT_C),
                 }
+                # inference without the h1 / h2 outputs: linear2|3 -> linear4+5 -> decoder conv1 are three consecutive
+                # linear maps (no activation in between, FaceRecon.py:151-165) and collapse into one (512, 1024) matrix
+                w1d = c[0].weight.detach().reshape(512, FEAT_C).double()
+                w45d, w23d = self._packs["ph_l45"][0].double(), self._packs["ph_l23"][0].double()
+                b45d, b23d = self._packs["ph_l45"][1].double(), self._packs["ph_l23"][1].double()
+                wf = w1d @ w45d
+                self._packs["ph_fold"] = ((wf @ w23d).float().contiguous(), (wf @ b23d + w1d @ b45d).float().contiguous())
                 for name, head in (("green", g), ("red", r), ("ts", t)):
                     sc, sh = _fold(head.conv3, head.bn3)
                     self._packs[name + "3"] = (head.conv3.weight.detach().reshape(256, 256), sc.contiguous(), sh.contiguous())
@@ -356,17 +363,20 @@ class PoseNet9D(nn.Module):
         # PH_Predictor tail (FaceRecon.py:147-165): per-cloud (M = batch) contractions on the skinny kernel
         w1, sc5, sh5, sl5 = pk["ph_l1"]
         feat_all = ops.linear_nk(pooled, w1, scale=sc5, shift=sh5, neg_slope=sl5, tc=False)      # linear1 + bn5 + leaky; dropout = id
-        w23, b23 = pk["ph_l23"]
-        pi12 = ops.linear_nk(feat_all, w23, bias=b23, tc=False)                                   # [pi1 | pi2]
-        w45, b45 = pk["ph_l45"]
-        cvec = ops.linear_nk(pi12, w45, bias=b45, tc=False)                                       # linear4(pi1) + linear5(pi2): (B,1286)
         h1 = h2 = None
+        dec = fa.decoder
+        # Face_Dec on feat + cvec: W.(feat + c) = W.feat + W.c  -> per-cloud bias `gb` in the epilogue
         if self.train_outputs:
+            w23, b23 = pk["ph_l23"]
+            pi12 = ops.linear_nk(feat_all, w23, bias=b23, tc=False)                               # [pi1 | pi2]
+            w45, b45 = pk["ph_l45"]
+            cvec = ops.linear_nk(pi12, w45, bias=b45, tc=False)                                   # linear4(pi1) + linear5(pi2): (B,1286)
             oc = fa.ph_pred.output_channels
             h1, h2 = torch.sigmoid(pi12[:, :oc]), torch.sigmoid(pi12[:, oc:])
-        # Face_Dec on feat + cvec: W.(feat + c) = W.feat + W.c  -> per-cloud bias in the epilogue
-        dec = fa.decoder
-        gb = ops.linear_nk(cvec, pk["dec1_w"], tc=False)
+            gb = ops.linear_nk(cvec, pk["dec1_w"], tc=False)
+        else:
+            wfold, bfold = pk["ph_fold"]
+            gb = ops.linear_nk(feat_all, wfold, bias=bfold, tc=False)
         (d1,) = self._stage(pk["dec1"], xs, kin, [(512, "split")], M, group_bias=gb, rows_per_group=N)
         (d2,) = self._stage(pk["dec2"], d1, 512, [(512, "split")], M)
         (d3,) = self._stage(pk["dec3"], d2, 512, [(256, "split")], M)
@@ -382,6 +392,7 @@ class PoseNet9D(nn.Module):
             w4, b4 = pk[name + "4"]
             return ops.linear_nk(v, w4, bias=b4, tc=False)
 
+        self._last_recon = recon          # (tests) the reference computes recon in inference too but only returns it with FLAGS.train
         green_R_vec = tail("green", hg)
         red_R_vec = tail("red", hr)
         ts_vec = tail("ts", ht)
