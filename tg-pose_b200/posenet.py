@@ -258,6 +258,8 @@ class PoseNet9D(nn.Module):
         super().__init__()
         self.only_encoder = only_encoder
         self.train_outputs = train_outputs
+        self.overlap_heads = True      # inference: pose tails on forked streams next to the decoder chain
+        self._side = None
         if not only_encoder:
             self.face_all = FaceNet(**enc_kwargs)
             self.rot_green = Rot_green()
@@ -359,6 +361,17 @@ class PoseNet9D(nn.Module):
         # only ever max-pooled over the cloud (FaceRecon.py:145-146), so that pooling happens in the epilogue
         hg, hr, f5max, ht = self._stage(pk["stage1"], xs, kin, [(1024, "split"), (1024, "split"), (1024, "max"),
                                                                  (1024, "split")], M, rows_per_group=N)
+        # The three pose tails and the decoder chain are independent after stage 1.  Each of their GEMMs has 257 row tiles
+        # for 148 SMs (a 1.7-wave tail), so they are issued on forked streams: the persistent CTAs of one kernel that finish
+        # early free their SMs for the next kernel's CTAs.  Under CUDA-graph capture the forks become parallel branches.
+        main = torch.cuda.current_stream()
+        side = None
+        if self.overlap_heads:
+            if self._side is None:
+                self._side = [torch.cuda.Stream(device=points.device) for _ in range(3)]
+            side = self._side
+            for st in side:
+                st.wait_stream(main)
         pooled = ops.decode_max(f5max)
         # PH_Predictor tail (FaceRecon.py:147-165): per-cloud (M = batch) contractions on the skinny kernel
         w1, sc5, sh5, sl5 = pk["ph_l1"]
@@ -393,9 +406,19 @@ class PoseNet9D(nn.Module):
             return ops.linear_nk(v, w4, bias=b4, tc=False)
 
         self._last_recon = recon          # (tests) the reference computes recon in inference too but only returns it with FLAGS.train
-        green_R_vec = tail("green", hg)
-        red_R_vec = tail("red", hr)
-        ts_vec = tail("ts", ht)
+        if side is not None:
+            with torch.cuda.stream(side[0]):
+                green_R_vec = tail("green", hg)
+            with torch.cuda.stream(side[1]):
+                red_R_vec = tail("red", hr)
+            with torch.cuda.stream(side[2]):
+                ts_vec = tail("ts", ht)
+            for st in side:
+                main.wait_stream(st)
+        else:
+            green_R_vec = tail("green", hg)
+            red_R_vec = tail("red", hr)
+            ts_vec = tail("ts", ht)
         feat = feat_global = None
         if self.train_outputs:
             feat = raw.view(B, N, kin)[:, :, :FEAT_C]
