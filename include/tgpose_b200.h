@@ -300,9 +300,10 @@ int tgp_colsumsq_dev(const float* x, long ld, long M, int C, const float* mu, fl
                      void* workspace, size_t workspace_bytes, tgp_stream_t stream);
 
 /* y = act(z * scale[c] + shift[c]), act(v) = v > 0 ? v : v * slope.  out (M,C) and/or out_split (M, 2*Kp) as the
- * next contraction's tensor-core operand (padding columns must be pre-zeroed). */
+ * next contraction's tensor-core operand ([tf32 | residual], or the MIXED layout when mixed = 1; padding columns must
+ * be pre-zeroed). */
 int tgp_affine_act(const float* z, long ld_z, const float* scale, const float* shift, float slope, long M, int C,
-                   float* out, long ld_out, float* out_split, int Kp, tgp_stream_t stream);
+                   float* out, long ld_out, float* out_split, int Kp, int mixed, tgp_stream_t stream);
 
 /* backward of y = act(BN_train(z)): dbeta[c] = sum g, dgamma[c] = sum g * zhat, g = dy * act'(y),
  * dz = gamma * invstd * (g - dbeta / M - zhat * dgamma / M).  workspace: tgp_bn_workspace(M, C). */

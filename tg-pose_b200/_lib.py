@@ -89,7 +89,7 @@ SIGNATURES = {
     "tgp_bn_workspace": (c_size_t, [c_long, c_int]),
     "tgp_colsumsq_dev": (c_int, [c_void_p, c_long, c_long, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "tgp_affine_act": (c_int, [c_void_p, c_long, c_void_p, c_void_p, ctypes.c_float, c_long, c_int, c_void_p, c_long,
-                               c_void_p, c_int, c_void_p]),
+                               c_void_p, c_int, c_int, c_void_p]),
     "tgp_bn_bwd": (c_int, [c_void_p, c_long, c_void_p, c_long, c_void_p, c_long, c_void_p, c_void_p, c_void_p,
                            ctypes.c_float, c_long, c_int, c_void_p, c_long, c_void_p, c_void_p, c_void_p, c_size_t,
                            c_void_p]),

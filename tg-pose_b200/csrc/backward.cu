@@ -11,6 +11,7 @@
 // runs), so the last bits depend on arrival order; every cross-cloud reduction (directions,
 // column sums) goes through fixed-order partial sums and is deterministic.
 #include "common.cuh"
+#include <cuda_bf16.h>
 #include <float.h>
 
 namespace tgp {
@@ -348,7 +349,7 @@ colsumsq_partial_kernel(const float* __restrict__ x, long ld, long M, int C, con
 // y = act(z * scale[c] + shift[c]), act = leaky with `slope` (0: ReLU, 1: identity); raw and/or split destination
 __global__ void affine_act_kernel(const float* __restrict__ z, long ld_z, const float* __restrict__ scale,
                                   const float* __restrict__ shift, float slope, long M, int C, float* __restrict__ out,
-                                  long ld_out, float* __restrict__ out_split, int kp) {
+                                  long ld_out, float* __restrict__ out_split, int kp, int mixed) {
     const long total = M * C;
     for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
         const long r = e / C;
@@ -361,7 +362,11 @@ __global__ void affine_act_kernel(const float* __restrict__ z, long ld_z, const 
             asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v));
             const float hi = __uint_as_float(hb);
             out_split[r * 2 * kp + c] = hi;
-            out_split[r * 2 * kp + kp + c] = v - hi;
+            if (mixed) {     // [tf32 | bf16(x) | bf16(x - tf32(x))], tgp_gemm_args.mixed
+                __nv_bfloat16* h16 = reinterpret_cast<__nv_bfloat16*>(out_split + r * 2 * kp + kp);
+                h16[c] = __float2bfloat16_rn(v);
+                h16[kp + c] = __float2bfloat16_rn(v - hi);
+            } else out_split[r * 2 * kp + kp + c] = v - hi;
         }
     }
 }
@@ -624,10 +629,10 @@ extern "C" int tgp_colsumsq_dev(const float* x, long ld, long M, int C, const fl
 }
 
 extern "C" int tgp_affine_act(const float* z, long ld_z, const float* scale, const float* shift, float slope, long M,
-                              int C, float* out, long ld_out, float* out_split, int Kp, tgp_stream_t stream) {
+                              int C, float* out, long ld_out, float* out_split, int Kp, int mixed, tgp_stream_t stream) {
     if (!z || !scale || !shift || (!out && !out_split)) return fail(TGP_EINVAL, "tgp_affine_act: null pointer");
-    if (M <= 0 || C <= 0 || (out_split && Kp < C)) return fail(TGP_EINVAL, "tgp_affine_act: bad sizes");
-    affine_act_kernel<<<grid_for(M * C, 256), 256, 0, as_stream(stream)>>>(z, ld_z, scale, shift, slope, M, C, out, ld_out, out_split, Kp);
+    if (M <= 0 || C <= 0 || (out_split && Kp < C) || (out_split && mixed && Kp % 64)) return fail(TGP_EINVAL, "tgp_affine_act: bad sizes");
+    affine_act_kernel<<<grid_for(M * C, 256), 256, 0, as_stream(stream)>>>(z, ld_z, scale, shift, slope, M, C, out, ld_out, out_split, Kp, mixed);
     return check_launch("affine_act_kernel");
 }
 

@@ -23,14 +23,17 @@ class _ConvBNActFn(torch.autograd.Function):
         cout, cin = weight.shape[0], weight.shape[1]
         w2 = weight.reshape(cout, cin)
         z = torch.empty((M, cout), dtype=torch.float32, device=x2d.device)
-        xs = x_split if (x_split is not None and x_split.numel()) else None
-        ops.gemm(x2d, w2, True, [(0, cout, z, 0, 0)], bias=bias, A_split=xs)
+        # forward and dx contractions on MIXED operands (TF32 + bf16 cross terms, see tgp_gemm_args.mixed); the weight
+        # gradient keeps the transposed 3xTF32 operands
+        xs = x_split if (x_split is not None and x_split.numel()) else ops.split_mixed(x2d)
+        ops.gemm(None, w2, True, [(0, cout, z, 0, 0)], bias=bias, K=cin, A_split=xs, B_split=ops.split_mixed(w2.detach()),
+                 mixed=True)
         mean = ops.colsum(z).view(-1) / M
         var = ops.colsumsq_dev(z, mean) / M                      # biased, as used for normalisation
         invstd = torch.rsqrt(var + eps)
         scale = gamma * invstd
         shift = beta - mean * scale
-        y, y_split = ops.affine_act(z, scale, shift, slope, want_raw=True, want_split=want_split)
+        y, y_split = ops.affine_act(z, scale, shift, slope, want_raw=True, want_split=want_split, mixed=True)
         ctx.save_for_backward(x2d, w2, z, y, mean, invstd, gamma)
         ctx.slope = slope
         ctx.has_bias = bias is not None
@@ -46,7 +49,12 @@ class _ConvBNActFn(torch.autograd.Function):
         dz, dbeta, dgamma = ops.bn_bwd(dy, y, z, mean, invstd, gamma, ctx.slope)
         dw = ops.gemm_tn(dz, x2d).view(ctx.wshape)
         db = ops.colsum(dz).view(-1) if ctx.has_bias else None
-        dx = ops.matmul_kn(dz, w2) if ctx.needs_input_grad[0] else None
+        dx = None
+        if ctx.needs_input_grad[0]:
+            cout, cin = w2.shape
+            dx = torch.empty((dz.shape[0], cin), dtype=torch.float32, device=dz.device)
+            ops.gemm(None, w2, False, [(0, cin, dx, 0, 0)], K=cout, Ncols=cin, A_split=ops.split_mixed(dz),
+                     B_split=ops.split_mixed(w2.t().contiguous()), mixed=True)
         return dx, dw, db, dgamma, dbeta, None, None, None, None
 
 

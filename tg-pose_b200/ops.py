@@ -546,14 +546,17 @@ def colsumsq_dev(x2d, mu):
     return out
 
 
-def affine_act(z2d, scale, shift, slope, want_raw=True, want_split=False):
-    """act(z * scale + shift) -> (raw (M,C) or None, split (M, 2*kpad(C)) or None)."""
+def affine_act(z2d, scale, shift, slope, want_raw=True, want_split=False, mixed=False):
+    """act(z * scale + shift) -> (raw (M,C) or None, split operand or None): (M, 2*kpad(C)) [tf32 | residual], or the
+    MIXED layout (M, 2*mixed_kpad(C)) when mixed."""
     M, C = z2d.shape
     assert z2d.stride(1) == 1
     raw = torch.empty((M, C), dtype=torch.float32, device=z2d.device) if want_raw else None
-    spl = _split_buf(M, C, z2d.device) if want_split else None
+    spl = None
+    if want_split:
+        spl = mixed_buf(M, C, z2d.device) if mixed else _split_buf(M, C, z2d.device)
     _run("affine_act", _lib.load().tgp_affine_act, _p(z2d), z2d.stride(0), _p(scale), _p(shift), float(slope), M, C,
-         _p(raw), C, _p(spl), kpad(C), _stream())
+         _p(raw), C, _p(spl), mixed_kpad(C) if mixed else kpad(C), 1 if mixed else 0, _stream())
     return raw, spl
 
 
