@@ -51,7 +51,8 @@ def test_knn_xyz_duplicates(ops):
 
 
 @pytest.mark.parametrize("B,N,k", [(8, 1028, 20), (3, 257, 20), (5, 64, 8), (2, 1028, 4), (2, 333, 50), (1, 5000, 10),
-                                   (2, 40, 39), (1, 2, 1)])
+                                   (2, 40, 39), (1, 2, 1), (3, 1028, 31), (2, 40, 31), (1, 33, 31), (1, 9000, 20),
+                                   (1, 16500, 31), (2, 1028, 1), (2, 65, 30)])
 def test_knn_xyz_vs_oracle(ops, B, N, k):
     g = torch.Generator().manual_seed(B * 1000 + N + k)
     x = torch.rand(B, N, 3, generator=g)
@@ -69,6 +70,17 @@ def test_knn_xyz_half_cloud_one_point(ops):
     d = nump(ops.direction_norm(x.cuda(), torch.as_tensor(mine).cuda()))
     assert np.isfinite(d).all()
     assert_close(d, orc.direction_norm(x.numpy(), mine), what="dirs with duplicates")
+
+
+def test_knn_xyz_multi_tile_with_duplicates(ops):
+    """N > 8192 (both selection passes walk shared-memory tiles) with tie groups larger than the survivor buffer
+    (slow path inside the threshold-selection kernel), plus a cloud of identical points."""
+    g = torch.Generator().manual_seed(11)
+    x = torch.rand(2, 9000, 3, generator=g)
+    x[0, 4000:4400] = x[0, 17]
+    x[1, :] = x[1, 0]
+    mine = nump(ops.knn_xyz(x.cuda(), 20)[0])
+    assert np.array_equal(mine, orc.knn_xyz(x.numpy(), 20))
 
 
 def test_knn_errors(ops):

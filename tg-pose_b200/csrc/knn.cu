@@ -87,6 +87,181 @@ knn_xyz_kernel(const float* __restrict__ xyz, int N, int k, int tile, int64_t* _
 }
 
 // ------------------------------------------------------------------------------------------
+// xyz-space kNN by threshold selection (knn_select.cuh), k + 1 <= 32: each warp owns 4 queries and advances them
+// together, so one LDS.128 of a candidate feeds four distance evaluations.  Pass 1 keeps two strided minima per
+// lane and query (64 groups), pass 2 recomputes the (bit-identical) distances and compacts the ~K + 4 survivors
+// with warp ballots, then every survivor ranks itself.  ~6x fewer instructions per query than the insertion list.
+constexpr int KS_QPW = 4;                                  // queries per warp
+#ifndef KS_THREADS
+#define KS_THREADS 128
+#endif
+constexpr int KS_QPC = KS_QPW * (KS_THREADS / 32);         // queries per CTA
+constexpr int KS_SLOTS_MAX = 8;                            // survivor slots per lane and query (lane-private lists):
+constexpr int KS_CAP = 128;                                //   6 for k <= 21, 8 above; compacted survivors per query
+constexpr int KS_TILE_MAX = 8192;                          // candidates resident in shared memory at a time
+static inline int ks_slots(int k) { return k + 1 <= 22 ? 6 : KS_SLOTS_MAX; }
+static inline int ks_warp_smem(int k) { return (KS_QPW * ks_slots(k) * 32 + KS_CAP) * 8; }
+
+__device__ __forceinline__ float xyz_dist(float a0, float a1, float a2, float qq, const float4& p) {
+    const float inner = __fmaf_rn(a2, p.z, __fmaf_rn(a1, p.y, __fmul_rn(a0, p.x)));
+    return __fadd_rn(__fadd_rn(__fmul_rn(inner, -2.0f), p.w), qq);
+}
+
+__device__ __forceinline__ void stage_xyz_tile(float4* pts, const float* cloud, int t0, int nt, int ntp) {
+    for (int j = threadIdx.x; j < ntp; j += KS_THREADS) {
+        float4 v = make_float4(0.f, 0.f, 0.f, CUDART_INF_F);          // padding: distance +inf
+        if (j < nt) {
+            const float x0 = cloud[(t0 + j) * 3], x1 = cloud[(t0 + j) * 3 + 1], x2 = cloud[(t0 + j) * 3 + 2];
+            v = make_float4(x0, x1, x2, __fadd_rn(__fadd_rn(__fmul_rn(x0, x0), __fmul_rn(x1, x1)), __fmul_rn(x2, x2)));
+        }
+        pts[j] = v;
+    }
+}
+
+__global__ void __launch_bounds__(KS_THREADS)
+knn_xyz_sel_kernel(const float* __restrict__ xyz, int N, int k, int tile, int slots, int64_t* __restrict__ idx64,
+                   int32_t* __restrict__ idx32) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float4* pts = reinterpret_cast<float4*>(smem_raw);                                  // [tile] (tile % 32 == 0)
+    const int qstride = slots * 256;                                                    // bytes of one query's lists
+    unsigned char* wsm = reinterpret_cast<unsigned char*>(pts + tile) + (size_t)(threadIdx.x >> 5) * (KS_QPW * qstride + KS_CAP * 8);
+    uint2* compact = reinterpret_cast<uint2*>(wsm + KS_QPW * qstride);                  // [KS_CAP] (key, index)
+
+    const int b = blockIdx.y;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const float* cloud = xyz + (size_t)b * N * 3;
+    const int K = k + 1;
+    const int qbase = blockIdx.x * KS_QPC + warp * KS_QPW;
+    const bool single = N <= tile;
+
+    float a0[KS_QPW], a1[KS_QPW], a2[KS_QPW], qq[KS_QPW], m0[KS_QPW], m1[KS_QPW];
+#pragma unroll
+    for (int q = 0; q < KS_QPW; ++q) {
+        const int qi = min(qbase + q, N - 1);              // clamped: idle warps still walk the barriers
+        a0[q] = __ldg(cloud + qi * 3); a1[q] = __ldg(cloud + qi * 3 + 1); a2[q] = __ldg(cloud + qi * 3 + 2);
+        qq[q] = __fadd_rn(__fadd_rn(__fmul_rn(a0[q], a0[q]), __fmul_rn(a1[q], a1[q])), __fmul_rn(a2[q], a2[q]));
+        m0[q] = CUDART_INF_F; m1[q] = CUDART_INF_F;
+    }
+    // ---- pass 1: 64 strided group minima per query
+    for (int t0 = 0; t0 < N; t0 += tile) {
+        const int nt = min(tile, N - t0), ntp = (nt + 63) & ~63;
+        if (t0) __syncthreads();
+        stage_xyz_tile(pts, cloud, t0, nt, ntp);
+        __syncthreads();
+#pragma unroll 2
+        for (int j0 = 0; j0 < ntp; j0 += 64) {
+            const float4 p = pts[j0 + lane], r = pts[j0 + 32 + lane];
+#pragma unroll
+            for (int q = 0; q < KS_QPW; ++q) {
+                m0[q] = fminf(m0[q], xyz_dist(a0[q], a1[q], a2[q], qq[q], p));
+                m1[q] = fminf(m1[q], xyz_dist(a0[q], a1[q], a2[q], qq[q], r));
+            }
+        }
+    }
+    float T[KS_QPW];
+#pragma unroll
+    for (int q = 0; q < KS_QPW; ++q) T[q] = fminf(warp_kth_of_64(m0[q], m1[q], K, lane), 3.0e38f);
+    // ---- pass 2: every lane appends its survivors (d <= T) to a private list: no ballots in the scan
+    // (the write cursor of each list is a byte offset that advances by one 256-byte row per survivor; predicated, no branch)
+    uint32_t cur[KS_QPW];
+#pragma unroll
+    const uint32_t wsm_s = (uint32_t)__cvta_generic_to_shared(wsm);
+#pragma unroll
+    for (int q = 0; q < KS_QPW; ++q) cur[q] = wsm_s + (uint32_t)(q * qstride + lane * 8);
+    for (int t0 = 0; t0 < N; t0 += tile) {
+        const int nt = min(tile, N - t0), ntp = (nt + 63) & ~63;
+        if (!single) {
+            __syncthreads();
+            stage_xyz_tile(pts, cloud, t0, nt, ntp);
+            __syncthreads();
+        }
+#pragma unroll 2
+        for (int j0 = 0; j0 < ntp; j0 += 32) {
+            const float4 p = pts[j0 + lane];
+            const float jf = __int_as_float(t0 + j0 + lane);
+#pragma unroll
+            for (int q = 0; q < KS_QPW; ++q) {
+                const float d = xyz_dist(a0[q], a1[q], a2[q], qq[q], p);
+                const bool pass = d <= T[q];
+                const uint32_t lim = wsm_s + (uint32_t)((q + 1) * qstride);
+                const uint32_t st = (pass && cur[q] < lim) ? 1u : 0u;
+                asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %0, 0;\n\t@p st.shared.v2.f32 [%1], {%2, %3};\n\t}"
+                             :: "r"(st), "r"(cur[q]), "f"(d), "f"(jf) : "memory");
+                cur[q] += pass ? 256u : 0u;
+            }
+        }
+    }
+    int cnt[KS_QPW];
+#pragma unroll
+    for (int q = 0; q < KS_QPW; ++q) cnt[q] = (int)((cur[q] - wsm_s - (uint32_t)(q * qstride + lane * 8)) >> 8);
+    // ---- compaction + ranks, one query at a time
+    bool slow = false;
+    bool redo[KS_QPW];
+#pragma unroll
+    for (int q = 0; q < KS_QPW; ++q) {
+        const int qi = qbase + q;
+        int incl = cnt[q];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(FULL, incl, o);
+            if (lane >= o) incl += v;
+        }
+        const int total = __shfl_sync(FULL, incl, 31);
+        const bool over = __any_sync(FULL, cnt[q] > slots);
+        redo[q] = qi < N && (over || total < K || total > KS_CAP);
+        slow |= redo[q];
+        if (qi >= N || redo[q]) continue;
+        const int off = incl - cnt[q];
+        __syncwarp();
+#pragma unroll
+        for (int s = 0; s < KS_SLOTS_MAX; ++s)
+            if (s < cnt[q]) {
+                const float2 e = *reinterpret_cast<const float2*>(wsm + q * qstride + s * 256 + lane * 8);
+                compact[off + s] = make_uint2(ordered_key(e.x), (uint32_t)__float_as_int(e.y));
+            }
+        __syncwarp();
+        const size_t o = ((size_t)b * N + qi) * k;
+        warp_rank_store<KS_CAP / 32>(compact, total, k, lane, idx64 ? idx64 + o : nullptr, idx32 ? idx32 + o : nullptr);
+    }
+    // ---- slow path (massive distance ties, e.g. padded / duplicated points, or non-finite input): insertion list
+    if (!single) slow = __syncthreads_or(slow);            // tiles must be restaged by the whole CTA
+    if (slow) {
+        for (int t0 = 0; t0 < N; t0 += tile) {
+            const int nt = min(tile, N - t0), ntp = (nt + 63) & ~63;
+            if (!single) {
+                __syncthreads();
+                stage_xyz_tile(pts, cloud, t0, nt, ntp);
+                __syncthreads();
+            }
+#pragma unroll
+            for (int q = 0; q < KS_QPW; ++q) {
+                const int qi = qbase + q;
+                if (!redo[q]) continue;
+                WarpTopList<1> top;
+                float* sd = reinterpret_cast<float*>(wsm + q * qstride);            // list parked between tiles
+                int* si = reinterpret_cast<int*>(sd + 32);
+                if (t0 == 0) top.init();
+                else { top.d[0] = sd[lane]; top.i[0] = si[lane]; }
+                // nothing above T can be among the K nearest: admission is capped just above it from the start
+                const float cap = T[q] < 3.0e38f ? nextafterf(T[q], CUDART_INF_F) : CUDART_INF_F;
+                float th = fminf(top.thresh(K), cap);
+                for (int j0 = 0; j0 < ntp; j0 += 32)
+                    top.admit(xyz_dist(a0[q], a1[q], a2[q], qq[q], pts[j0 + lane]), t0 + j0, lane, th, K, cap);
+                if (t0 + nt >= N) {
+                    if (lane >= 1 && lane <= k) {
+                        const size_t o = ((size_t)b * N + qi) * k + lane - 1;
+                        const int v = top.i[0] < 0 ? 0 : top.i[0];            // unfilled rank (NaN input): a valid index
+                        if (idx64) idx64[o] = v;
+                        if (idx32) idx32[o] = v;
+                    }
+                } else { sd[lane] = top.d[0]; si[lane] = top.i[0]; }
+                __syncwarp();
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // nearest source point: d = (s_j + t_i) - 2*inner (gcn3d.py:33, a different op order from kNN),
 // strict '<' so the lowest index wins.  One thread per target, sources staged as (x,y,z,|s|^2).
 constexpr int NN_THREADS = 128;
@@ -295,12 +470,28 @@ extern "C" int tgp_knn_xyz(const float* xyz, int B, int N, int k, int64_t* idx64
     if (k + 1 > N) return fail(TGP_EINVAL, "tgp_knn_xyz: k+1 > N (torch.topk would raise, gcn3d.py:21)");
     if (k + 1 > 64) return fail(TGP_EINVAL, "tgp_knn_xyz: k > 63 unsupported");
     if (B > 65535) return fail(TGP_EINVAL, "tgp_knn_xyz: B > 65535");
+    cudaStream_t st = as_stream(stream);
+    static int legacy = -1;
+    if (legacy < 0) { const char* e = getenv("TGP_KNN_LEGACY"); legacy = (e && e[0] == '1') ? 1 : 0; }
+    if (k + 1 <= 32 && !legacy) {
+        // threshold selection; the whole cloud stays resident when it fits, otherwise both passes walk 8192-point tiles
+        const int tile = N <= KS_TILE_MAX ? ((N + 63) & ~63) : KS_TILE_MAX;
+        const size_t smem = (size_t)tile * sizeof(float4) + (size_t)(KS_THREADS / 32) * ks_warp_smem(k);
+        static bool attr_set = false;
+        if (!attr_set) {
+            cudaFuncSetAttribute(knn_xyz_sel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)(KS_TILE_MAX * sizeof(float4) + (KS_THREADS / 32) * ks_warp_smem(63)));
+            attr_set = true;
+        }
+        dim3 grid((N + KS_QPC - 1) / KS_QPC, B);
+        knn_xyz_sel_kernel<<<grid, KS_THREADS, smem, st>>>(xyz, N, k, tile, ks_slots(k), idx64, idx32);
+        return check_launch("knn_xyz_sel_kernel");
+    }
     const int tile = N < KNN_TILE_MAX ? N : KNN_TILE_MAX;
     const int slots = (k + 1 > 32) ? 2 : 1;
     size_t smem = (size_t)tile * sizeof(float4);
     if (N > tile) smem += (size_t)KNN_QPC * 32 * slots * 8;
     dim3 grid((N + KNN_QPC - 1) / KNN_QPC, B);
-    cudaStream_t st = as_stream(stream);
     if (slots == 1) {
         cudaFuncSetAttribute(knn_xyz_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         knn_xyz_kernel<1><<<grid, KNN_THREADS, smem, st>>>(xyz, N, k, tile, idx64, idx32);
