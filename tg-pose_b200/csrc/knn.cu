@@ -503,13 +503,15 @@ extern "C" int tgp_knn_xyz(const float* xyz, int B, int N, int k, int64_t* idx64
 }
 
 bool tgp_knn_tc_eligible(int B, int N, int D, int k);
+size_t tgp_knn_tc_fix_bytes(int B, int N);
 int tgp_knn_tc(const float* x_split, const float* qn, int B, int N, int D, int k, int64_t* idx64, int32_t* idx32,
-               cudaStream_t st);
+               int* fix_list, cudaStream_t st);
 
 static size_t knn_qn_bytes(int B, int N) { return (((size_t)B * N * sizeof(float)) + 255) & ~(size_t)255; }
 
+// workspace layout: [row norms | fix-up unit list | split operand (unless the caller passes one)]
 extern "C" size_t tgp_knn_feat_workspace(int B, int N, int D, int have_split) {
-    size_t s = knn_qn_bytes(B, N);
+    size_t s = knn_qn_bytes(B, N) + tgp_knn_tc_fix_bytes(B, N);
     if (!have_split) s += (size_t)B * N * 2 * tgp_split_kpad(D) * sizeof(float);
     return s;
 }
@@ -532,13 +534,17 @@ extern "C" int tgp_knn_feat(const float* x, const float* x_split, int B, int N, 
     if (force_fp32 < 0) { const char* e = getenv("TGP_KNN_FP32"); force_fp32 = (e && e[0] == '1') ? 1 : 0; }
     if (!force_fp32 && tgp_knn_tc_eligible(B, N, D, k)) {
         // inner products on the tensor cores (knn_tc.cu); the split operand is built here unless the caller has it
+        unsigned char* ws = static_cast<unsigned char*>(workspace);
         if (!x_split) {
-            float* spl = reinterpret_cast<float*>(static_cast<unsigned char*>(workspace) + knn_qn_bytes(B, N));
+            float* spl = reinterpret_cast<float*>(ws + knn_qn_bytes(B, N) + tgp_knn_tc_fix_bytes(B, N));
             rc = tgp_split_tf32(x, rows, D, D, 0, spl, stream);
             if (rc) return rc;
             x_split = spl;
         }
-        return tgp_knn_tc(x_split, qn, B, N, D, k, idx64, idx32, st);
+        static int legacy = -1;
+        if (legacy < 0) { const char* e = getenv("TGP_KNN_LEGACY"); legacy = (e && e[0] == '1') ? 1 : 0; }
+        return tgp_knn_tc(x_split, qn, B, N, D, k, idx64, idx32,
+                          legacy ? nullptr : reinterpret_cast<int*>(ws + knn_qn_bytes(B, N)), st);
     }
     const int slots = (k + 1 > 32) ? 2 : 1;
     const size_t smem = sizeof(float) * (KF_BK * KF_LDA + KF_BK * KF_LDB + KF_BM * KF_LDD) + (size_t)KF_BM * 32 * slots * 8;

@@ -51,7 +51,7 @@ struct WarpTopList {
     }
     // admit every lane's candidate (dd, base+lane) that beats the threshold, lowest lane first
     // (cap: an upper bound the caller knows for the admission threshold, e.g. from a previous pass)
-    __device__ __forceinline__ void admit(float dd, int base, int lane, float& th, int K, float cap = CUDART_INF_F) {
+    __device__ __forceinline__ void admit(float dd, int base, int lane, float& th, int K, float cap = 3.402823466e+38f) {
         unsigned m = __ballot_sync(FULL, dd < th);
         while (m) {
             const int src = __ffs(m) - 1;
