@@ -171,10 +171,14 @@ def test_gather_max_and_orl(ops, C):
 @pytest.mark.parametrize("M,K,N,nk", [(300, 128, 1024, False), (257, 3, 128, True), (1000, 256, 256, True),
                                       (64, 128, 130, False), (5, 16, 7, True), (129, 20, 36, False),
                                       (4112, 1289, 520, True), (700, 100, 72, False), (32, 1286, 512, True),
-                                      (3, 256, 40, True), (2000, 128, 3, True), (2000, 3, 128, False)])
+                                      (3, 256, 40, True), (2000, 128, 3, True), (2000, 3, 128, False),
+                                      (32, 5000, 1286, True), (40, 1024, 5000, True), (64, 200, 33, True),
+                                      (17, 129, 19, True), (1, 33, 1, True)])
 def test_gemm_plain(ops, M, K, N, nk, tc):
     """both contraction kernels (fp32 FMA and tcgen05 3xTF32) against the fp64-accumulated oracle.
     Tolerance: rel 1e-4 with an absolute floor of 1e-5 (sums of K unit-scale products)."""
+    if tc and K > 4096:
+        pytest.skip("K = 5000 only occurs in per-cloud (M = batch) contractions, which are pinned to the fp32 kernel")
     rng = np.random.default_rng(M + K + N)
     A = rng.standard_normal((M, K)).astype(np.float32)
     W = rng.standard_normal((K, N)).astype(np.float32) * 0.1

@@ -138,36 +138,169 @@ gemm_simt_kernel(const __grid_constant__ GemmDev P) {
     }
 }
 
-// skinny contraction (M <= 64, e.g. one row per cloud: the ORL cloud-global term g @ W2b^T):
-// a warp owns one output column n (one K-contiguous weight row) and 4 rows of A; lanes stride over K with
-// 4 independent loads in flight per operand.
+// skinny contraction (M <= 64, one row per cloud: the ORL cloud-global term g @ W2b^T, SURVEY 8a a8, and the per-cloud
+// head tails).  HBM/L2-bound on the weights: every weight row is streamed exactly once, 512 B per warp load.
+//   CTA  = 32 rows of A x 16 output columns; warp = 16 rows x 4 columns (64 accumulators), lanes split K (4 consecutive k
+//          each per 128-wide chunk); the A chunk (32 x 128) is staged in shared memory once per CTA and read back as
+//          conflict-free LDS.128; weights and the next A chunk are prefetched one chunk ahead in registers;
+//   end  = butterfly transpose-reduction of the 64 lane-partials (62 shuffles), fused epilogue.
+// A row's result never depends on the other rows or on M (fixed k partition), so a cloud's output is batch-independent.
+constexpr int SK_KC = 128;
+
 __global__ void __launch_bounds__(256)
 gemm_skinny_kernel(const __grid_constant__ GemmDev P) {
+    __shared__ __align__(16) float As[2][32 * SK_KC];
     const tgp_gemm_args& g = P.a;
-    const int lane = threadIdx.x & 31;
-    const int n = blockIdx.x * 8 + (threadIdx.x >> 5);
-    const long m0 = (long)blockIdx.y * 4;
-    if (n >= g.Ncols) return;
-    const float* w = g.Bmat + (long)n * g.ldb;
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int k0 = 0; k0 < g.K; k0 += 128) {
-        float wv[4], av[4][4];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int rh = warp & 1, cgp = warp >> 1;
+    const long m0 = (long)blockIdx.y * 32;
+    const int n0 = blockIdx.x * 16 + cgp * 4;
+    const bool vecA = (g.lda % 4 == 0) && ((uintptr_t)g.A % 16 == 0);
+    const bool vecB = (g.ldb % 4 == 0) && ((uintptr_t)g.Bmat % 16 == 0);
+    const int arow = tid >> 3, akq = (tid & 7) * 16;       // staging role: 8 threads per A row, 16 floats each
+
+    float acc[64];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int k = k0 + u * 32 + lane;
-            wv[u] = k < g.K ? __ldg(w + k) : 0.f;
+    for (int i = 0; i < 64; ++i) acc[i] = 0.f;
+    float4 wn[4], an[4];
 #pragma unroll
-            for (int r = 0; r < 4; ++r) av[r][u] = (k < g.K && m0 + r < g.M) ? __ldg(g.A + (m0 + r) * g.lda + k) : 0.f;
+    for (int c = 0; c < 4; ++c) wn[c] = ld4_guard(g.Bmat, n0 + c, g.Ncols, g.ldb, lane * 4, g.K, vecB);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) an[j] = ld4_guard(g.A, m0 + arow, g.M, g.lda, akq + j * 4, g.K, vecA);
+    int buf = 0;
+    for (int k0 = 0; k0 < g.K; k0 += SK_KC, buf ^= 1) {
+        float* as = As[buf];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) *reinterpret_cast<float4*>(as + arow * SK_KC + akq + j * 4) = an[j];
+        float4 w[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) w[c] = wn[c];
+        __syncthreads();                                    // chunk visible; the other buffer is free again
+        if (k0 + SK_KC < g.K) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) wn[c] = ld4_guard(g.Bmat, n0 + c, g.Ncols, g.ldb, k0 + SK_KC + lane * 4, g.K, vecB);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) an[j] = ld4_guard(g.A, m0 + arow, g.M, g.lda, k0 + SK_KC + akq + j * 4, g.K, vecA);
+        }
+        const float* ar = as + rh * 16 * SK_KC + lane * 4;
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+            const float4 a = *reinterpret_cast<const float4*>(ar + r * SK_KC);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                float v = acc[r * 4 + c];
+                v = fmaf(a.x, w[c].x, v); v = fmaf(a.y, w[c].y, v); v = fmaf(a.z, w[c].z, v); v = fmaf(a.w, w[c].w, v);
+                acc[r * 4 + c] = v;
+            }
+        }
+    }
+    // transpose-reduce: after the step with offset `off` a lane keeps the upper half of its values iff (lane & off)
+#pragma unroll
+    for (int off = 16, cnt = 32; off >= 1; off >>= 1, cnt >>= 1) {
+        const bool up = (lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < cnt; ++i) {
+            const float send = up ? acc[i] : acc[i + cnt];
+            const float keep = up ? acc[i + cnt] : acc[i];
+            acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+    }
+    const int base = ((lane >> 4) & 1) * 32 + ((lane >> 3) & 1) * 16 + ((lane >> 2) & 1) * 8 + ((lane >> 1) & 1) * 4 + (lane & 1) * 2;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const int idx = base + i;
+        const long row = m0 + rh * 16 + (idx >> 2);
+        const int col = n0 + (idx & 3);
+        if (row < g.M && col < g.Ncols) epilogue_store(g, row, col, acc[i]);
+    }
+}
+
+// Same tiling with a 4-deep cp.async ring for both operands (16-byte aligned rows only): one chunk of register prefetch
+// (~0.3 us of work) does not cover the DRAM latency of the weight stream, three chunks in flight do.
+constexpr int SKP_STAGES = 4;
+constexpr int SKP_STAGE_FLOATS = (32 + 16) * SK_KC;      // A chunk 32 x 128, W chunk 16 x 128
+
+__device__ __forceinline__ void cp_async16(float* dst, const float* src, int src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src), "r"(src_bytes) : "memory");
+}
+
+__global__ void __launch_bounds__(256)
+gemm_skinny_pipe_kernel(const __grid_constant__ GemmDev P) {
+    extern __shared__ __align__(16) float sk_smem[];
+    const tgp_gemm_args& g = P.a;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int rh = warp & 1, cgp = warp >> 1;
+    const long m0 = (long)blockIdx.y * 32;
+    const int nb = blockIdx.x * 16;
+    const int nchunks = (g.K + SK_KC - 1) / SK_KC;
+
+    // staging roles: A piece j of thread t -> row t/8, floats (t%8)*16 + 4j; W piece j -> column (t + 256 j)/32, floats ((t + 256 j)%32)*4
+    auto issue = [&](int chunk) {
+        float* st = sk_smem + (chunk % SKP_STAGES) * SKP_STAGE_FLOATS;
+        const int k0 = chunk * SK_KC;
+        const int arow = tid >> 3;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int kq = (tid & 7) * 16 + j * 4, k = k0 + kq;
+            const bool ok = m0 + arow < g.M && k < g.K;
+            const int bytes = ok ? min(16, (g.K - k) * 4) : 0;
+            cp_async16(st + arow * SK_KC + kq, ok ? g.A + (m0 + arow) * g.lda + k : g.A, bytes);
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
+        for (int j = 0; j < 2; ++j) {
+            const int p = tid + 256 * j, col = p >> 5, kq = (p & 31) * 4, k = k0 + kq;
+            const bool ok = nb + col < g.Ncols && k < g.K;
+            const int bytes = ok ? min(16, (g.K - k) * 4) : 0;
+            cp_async16(st + 32 * SK_KC + col * SK_KC + kq, ok ? g.Bmat + (long)(nb + col) * g.ldb + k : g.Bmat, bytes);
+        }
+    };
+
+    float acc[64];
 #pragma unroll
-            for (int r = 0; r < 4; ++r) acc[r] = fmaf(av[r][u], wv[u], acc[r]);
+    for (int i = 0; i < 64; ++i) acc[i] = 0.f;
+#pragma unroll
+    for (int c = 0; c < SKP_STAGES - 1; ++c) {
+        if (c < nchunks) issue(c);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    for (int c = 0; c < nchunks; ++c) {
+        asm volatile("cp.async.wait_group %0;" ::"n"(SKP_STAGES - 2) : "memory");
+        __syncthreads();                                    // chunk c has landed for everyone; the stage of chunk c-1 is free
+        if (c + SKP_STAGES - 1 < nchunks) issue(c + SKP_STAGES - 1);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        const float* st = sk_smem + (c % SKP_STAGES) * SKP_STAGE_FLOATS;
+        float4 w[4];
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) w[cc] = *reinterpret_cast<const float4*>(st + 32 * SK_KC + (cgp * 4 + cc) * SK_KC + lane * 4);
+        const float* ar = st + rh * 16 * SK_KC + lane * 4;
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+            const float4 a = *reinterpret_cast<const float4*>(ar + r * SK_KC);
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc) {
+                float v = acc[r * 4 + cc];
+                v = fmaf(a.x, w[cc].x, v); v = fmaf(a.y, w[cc].y, v); v = fmaf(a.z, w[cc].z, v); v = fmaf(a.w, w[cc].w, v);
+                acc[r * 4 + cc] = v;
+            }
+        }
     }
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-        const float v = warp_sum(acc[r]);
-        if (lane == 0 && m0 + r < g.M) epilogue_store(g, m0 + r, n, v);
+    for (int off = 16, cnt = 32; off >= 1; off >>= 1, cnt >>= 1) {
+        const bool up = (lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < cnt; ++i) {
+            const float send = up ? acc[i] : acc[i + cnt];
+            const float keep = up ? acc[i + cnt] : acc[i];
+            acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+    }
+    const int base = ((lane >> 4) & 1) * 32 + ((lane >> 3) & 1) * 16 + ((lane >> 2) & 1) * 8 + ((lane >> 1) & 1) * 4 + (lane & 1) * 2;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const int idx = base + i;
+        const long row = m0 + rh * 16 + (idx >> 2);
+        const int col = nb + cgp * 4 + (idx & 3);
+        if (row < g.M && col < g.Ncols) epilogue_store(g, row, col, acc[i]);
     }
 }
 
@@ -237,7 +370,19 @@ int tgp_gemm_simt(const tgp_gemm_args* a, cudaStream_t st) {
     GemmDev P;
     P.a = *a;
     if (a->M <= 64 && a->b_is_nk && a->K >= 32) {
-        gemm_skinny_kernel<<<dim3((a->Ncols + 7) / 8, (unsigned)((a->M + 3) / 4)), 256, 0, st>>>(P);
+        const dim3 grid((a->Ncols + 15) / 16, (unsigned)((a->M + 31) / 32));
+        // (the summation order over k is the same in both kernels: the choice only depends on operand alignment)
+        if (a->lda % 4 == 0 && a->ldb % 4 == 0 && (uintptr_t)a->A % 16 == 0 && (uintptr_t)a->Bmat % 16 == 0) {
+            const size_t smem = (size_t)SKP_STAGES * SKP_STAGE_FLOATS * sizeof(float);
+            static bool attr_set = false;
+            if (!attr_set) {
+                cudaFuncSetAttribute(gemm_skinny_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                attr_set = true;
+            }
+            gemm_skinny_pipe_kernel<<<grid, 256, smem, st>>>(P);
+            return check_launch("gemm_skinny_pipe_kernel");
+        }
+        gemm_skinny_kernel<<<grid, 256, 0, st>>>(P);
         return check_launch("gemm_skinny_kernel");
     }
     if (a->K <= 8 || a->Ncols <= 8) {
