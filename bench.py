@@ -501,14 +501,14 @@ def kernel_report(event_log, steps, B, peaks):
         # algorithmic flops 2*M*K*N per launch ("a 3xTF32 GEMM's useful flops are the plain 2MNK").
         # Roof: the path must deliver fp32-level accuracy (rel 1e-4 parity) and the tensor cores have no fp32 mode, so the
         # ceiling of a contraction is the TF32 rate (measured bf16 dense / 2) divided by the TF32-pass equivalents it has
-        # to execute: 3 for the 3xTF32 operands of the encoder, 2 for the heads' mixed operands (TF32 hi.hi + two bf16
-        # cross terms at twice the TF32 rate).  `peak` is the flop-weighted roof of the launches in one step.
+        # to execute: 3 for the 3xTF32 operands of the encoder, 1.5 for the heads' mixed operands (fp16 hi.hi + two bf16
+        # cross terms, all three at twice the TF32 rate).  `peak` is the flop-weighted roof of the launches in one step.
         shapes = [x for x in event_log.get("__gemm_shapes__", []) if x[0] == "gemm_tc"]
         flops = sum(2.0 * m * kdim * n for _, m, kdim, n, *_ in shapes) / steps
         # the step runs at full SM clocks (1965 MHz sampled, no power capping even over 1000 steps), so the BURST bf16
         # figure is the applicable denominator, not the power-capped sustained one
         tf32_peak = peaks["bf16_tflops"] / 2.0
-        roof_t = sum(2.0 * m * kdim * n * (2.0 if (rest and rest[0]) else 3.0) for _, m, kdim, n, *rest in shapes) / steps / (tf32_peak * 1e12)
+        roof_t = sum(2.0 * m * kdim * n * (1.5 if (rest and rest[0]) else 3.0) for _, m, kdim, n, *rest in shapes) / steps / (tf32_peak * 1e12)
         t = agg[top]["ms_per_step"] / 1e3
         peak = flops / roof_t / 1e12
         out["roofline"] = {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05; all launches in the step)",
@@ -516,7 +516,7 @@ def kernel_report(event_log, steps, B, peaks):
                            "frac": roof_t / t, "traffic": profile_traffic("gemm_tc_kernel"),
                            "executed_tf32_equiv_tflops": roof_t * tf32_peak / t, "tf32_peak": tf32_peak,
                            "peak_source": f"{peaks['source']} burst bf16 dense / 2 (TF32 rate; SM clocks stay at max during the step) / TF32-pass equivalents "
-                                          "(3: 3xTF32 encoder operands, 2: mixed TF32+bf16 head operands), flop-weighted; "
+                                          "(3: 3xTF32 encoder operands, 1.5: mixed fp16+bf16 head operands), flop-weighted; "
                                           "achieved = algorithmic 2MNK flops",
                            "traffic_source": "sum of dram__bytes_read+write over the gemm_tc launches of one forward, "
                                              "profiles/*_kernels.json (ncu); bytes per step"}
@@ -553,7 +553,7 @@ def kernel_report(event_log, steps, B, peaks):
         kr["orl_global"] = {"bound": "hbm", "achieved_gbs": by / ms("orl_global") / 1e9,
                             "frac_hbm": by / ms("orl_global") / 1e9 / peaks["hbm_gbs"]}
     if ms("concat_rows"):
-        by = B * N0 * (4 * 1289 + 8 * 1344)
+        by = B * N0 * (4 * 1289 + 6 * 1344)
         kr["concat_rows"] = {"bound": "hbm", "achieved_gbs": by / ms("concat_rows") / 1e9,
                              "frac_hbm": by / ms("concat_rows") / 1e9 / peaks["hbm_gbs"]}
     out["kernel_rooflines"] = {kk_: {a: (round(b, 4) if isinstance(b, float) else b) for a, b in v.items()} for kk_, v in kr.items()}

@@ -182,11 +182,12 @@ typedef struct {
     const float* A_split;
     const float* B_split;
     /* mixed = 1: A_split / B_split are MIXED operands (tgp_split_mixed, output mode 4): rows of 8*Kp bytes,
-     * Kp = tgp_mixed_kpad(K): [tf32(x) as fp32 x Kp | bf16(x) x Kp | bf16(x - tf32(x)) x Kp].  The product runs as
-     * tf32(a).tf32(b) on the TF32 pipe plus the two cross terms lo(a).b + a.lo(b) in bf16 (twice the TF32 rate): two
-     * TF32-pass equivalents instead of three, relative error ~2^-19 per product (fp32-summation-noise level at the
-     * heads' K ~ 1e3).  Used for the heads' 1x1 convolutions (PoseR.py, PoseTs.py, FaceRecon.py:89-167), whose outputs
-     * feed no neighbour search; the encoder and the kNN keep the 3xTF32 operands. */
+     * Kp = tgp_mixed_kpad(K), holding 16-bit slots [fp16(x) x Kp | bf16(x) x Kp | bf16(x - fp16(x)) x Kp | unused x Kp]
+     * (fp16 saturating at +-65504; the residual then carries the remainder).  The product runs as
+     * fp16(a).fp16(b) + lo(a).bf16(b) + bf16(a).lo(b), three 16-bit tensor-core passes at twice the TF32 rate into one
+     * fp32 accumulator = 1.5 TF32-pass equivalents instead of the three of 3xTF32, relative error ~2^-19 per product
+     * (fp32-summation-noise level at the heads' K ~ 1e3).  Used for the heads' 1x1 convolutions (PoseR.py, PoseTs.py,
+     * FaceRecon.py:89-167), whose outputs feed no neighbour search; the encoder and the kNN keep the 3xTF32 operands. */
     int mixed;
 } tgp_gemm_args;
 

@@ -508,7 +508,7 @@ def test_cuda_graph_replay_equals_eager():
 
 @pytest.mark.parametrize("M,K,N", [(1028, 1289, 512), (300, 64, 128), (4112, 1024, 256), (257, 200, 96)])
 def test_gemm_mixed_operands(ops, M, K, N):
-    """tgp_gemm with MIXED operands (TF32 hi.hi + bf16 cross terms, the heads' contraction): error vs an fp64 product
+    """tgp_gemm with MIXED operands (fp16 hi.hi + bf16 cross terms, the heads' contraction): error vs an fp64 product
     stays at fp32-summation-noise level, and the mode-4 epilogue writes an operand that a second contraction accepts."""
     g = torch.Generator().manual_seed(M + K + N)
     A = torch.randn(M, K, generator=g).cuda()
@@ -524,12 +524,38 @@ def test_gemm_mixed_operands(ops, M, K, N):
     # measured ~1e-6 * scale; the bound below is 2^-16 of the output scale (the fp32 FMA kernel sits at ~2^-20)
     assert err <= 1.6e-5 * scale, (err, scale)
     # the mode-4 operand equals the split of the raw output (bit for bit), so the next layer can consume it
-    assert torch.equal(mix, ops.split_mixed(out))
+    kp3 = 3 * ops.mixed_kpad(N)            # 16-bit slots in use: [fp16(x) | bf16(x) | bf16(x - fp16(x))]; the last quarter is unused
+    assert torch.equal(mix.view(torch.int16)[:, :kp3], ops.split_mixed(out).view(torch.int16)[:, :kp3])
     W2 = (torch.randn(64, N, generator=g) * 0.1).cuda()
     out2 = torch.empty(M, 64, device="cuda")
     ops.gemm(None, W2, True, [(0, 64, out2, 0, 0)], K=N, A_split=mix, B_split=ops.split_mixed(W2), mixed=True)
     ref2 = out.double() @ W2.double().t()
     assert float((out2.double() - ref2).abs().max()) <= 1.6e-5 * float(ref2.abs().max())
+
+
+def test_gemm_mixed_operands_range(ops):
+    """fp16(x) saturates instead of overflowing (the bf16 residual carries the remainder) and tiny values keep their relative
+    accuracy through the residual: rows scaled by 1e5 / 1e-6 stay finite and accurate."""
+    g = torch.Generator().manual_seed(3)
+    M, K, N = 256, 320, 128
+    A = torch.randn(M, K, generator=g)
+    A[:64] *= 1e5          # beyond the fp16 range
+    A[64:128] *= 1e-6      # fp16 subnormals / underflow
+    W = torch.randn(N, K, generator=g) * 0.05
+    W[:16] *= 1e-5
+    A, W = A.cuda(), W.cuda()
+    out = torch.empty(M, N, device="cuda")
+    ops.gemm(None, W, True, [(0, N, out, 0, 0)], K=K, A_split=ops.split_mixed(A), B_split=ops.split_mixed(W), mixed=True)
+    ref = A.double() @ W.double().t()
+    assert bool(torch.isfinite(out).all())
+    rowscale = ref.abs().amax(dim=1, keepdim=True)
+    rel = ((out.double() - ref).abs() / rowscale)
+    assert float(rel[128:].max()) <= 1.6e-5                     # in-range rows: full accuracy
+    assert float(rel[64:128].max()) <= 2e-4                     # rows entirely below the fp16 normal range: |err| <= 2^-34 per element,
+                                                                # i.e. 2^-14 relative at 1e-6 (irrelevant next to in-range terms of a sum)
+    assert float(rel[:64].max()) <= 5e-3                        # saturated rows: bf16-residual accuracy, never inf
+    colscale = ref[128:].abs().amax(dim=0)
+    assert float(((out.double() - ref)[128:].abs() / colscale).max()) <= 2e-4   # tiny weight rows likewise
 
 
 def test_posenet_inference_output_set_and_folded_ph_tail():

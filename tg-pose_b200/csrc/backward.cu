@@ -357,16 +357,14 @@ __global__ void affine_act_kernel(const float* __restrict__ z, long ld_z, const 
         float v = fmaf(__ldg(z + r * ld_z + c), __ldg(scale + c), __ldg(shift + c));
         v = v > 0.f ? v : v * slope;
         if (out) out[r * ld_out + c] = v;
-        if (out_split) {
+        if (out_split && mixed) {
+            mixed_store1(reinterpret_cast<uint16_t*>(out_split + r * 2 * kp), kp, c, v);      // tgp_gemm_args.mixed
+        } else if (out_split) {
             uint32_t hb;
             asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v));
             const float hi = __uint_as_float(hb);
             out_split[r * 2 * kp + c] = hi;
-            if (mixed) {     // [tf32 | bf16(x) | bf16(x - tf32(x))], tgp_gemm_args.mixed
-                __nv_bfloat16* h16 = reinterpret_cast<__nv_bfloat16*>(out_split + r * 2 * kp + kp);
-                h16[c] = __float2bfloat16_rn(v);
-                h16[kp + c] = __float2bfloat16_rn(v - hi);
-            } else out_split[r * 2 * kp + kp + c] = v - hi;
+            out_split[r * 2 * kp + kp + c] = v - hi;
         }
     }
 }

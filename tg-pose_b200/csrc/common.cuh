@@ -57,6 +57,40 @@ __device__ __forceinline__ void normalize3(float& x, float& y, float& z) {
     x *= inv; y *= inv; z *= inv;
 }
 
+// MIXED tensor-core operand (tgp_gemm_args.mixed): a row is 4*Kp 16-bit slots,
+//   [fp16(x) x Kp | bf16(x) x Kp | bf16(x - fp16(x)) x Kp | unused x Kp].
+// fp16(x) saturates to +-65504 instead of overflowing, the residual then carries the rest (reduced precision, never inf);
+// below the fp16 normal range the residual keeps the relative accuracy.
+__device__ __forceinline__ uint16_t mixed_hi16(float v, float& hi) {
+    uint16_t h;
+    asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(h) : "f"(v));
+    asm("cvt.f32.f16 %0, %1;" : "=f"(hi) : "h"(h));
+    return h;
+}
+__device__ __forceinline__ uint16_t bf16_bits(float v) {
+    uint16_t h;
+    asm("cvt.rn.bf16.f32 %0, %1;" : "=h"(h) : "f"(v));
+    return h;
+}
+// one value -> slot `col` of the row starting at `row16`
+__device__ __forceinline__ void mixed_store1(uint16_t* row16, int Kp, int col, float v) {
+    float hi;
+    row16[col] = mixed_hi16(v, hi);
+    row16[Kp + col] = bf16_bits(v);
+    row16[2 * Kp + col] = bf16_bits(v - hi);
+}
+// four consecutive values (col % 4 == 0, row 16-byte aligned): three 8-byte stores
+__device__ __forceinline__ void mixed_store4(uint16_t* row16, int Kp, int col, float4 v) {
+    float h0, h1, h2, h3;
+    const uint32_t a0 = mixed_hi16(v.x, h0), a1 = mixed_hi16(v.y, h1), a2 = mixed_hi16(v.z, h2), a3 = mixed_hi16(v.w, h3);
+    *reinterpret_cast<uint2*>(row16 + col) = make_uint2(a0 | (a1 << 16), a2 | (a3 << 16));
+    *reinterpret_cast<uint2*>(row16 + Kp + col) =
+        make_uint2((uint32_t)bf16_bits(v.x) | ((uint32_t)bf16_bits(v.y) << 16), (uint32_t)bf16_bits(v.z) | ((uint32_t)bf16_bits(v.w) << 16));
+    *reinterpret_cast<uint2*>(row16 + 2 * Kp + col) =
+        make_uint2((uint32_t)bf16_bits(v.x - h0) | ((uint32_t)bf16_bits(v.y - h1) << 16),
+                   (uint32_t)bf16_bits(v.z - h2) | ((uint32_t)bf16_bits(v.w - h3) << 16));
+}
+
 #define TGP_DISPATCH_IDX(bits, ...)                                   \
     do {                                                              \
         if ((bits) == 64) { using IdxT = int64_t; __VA_ARGS__; }      \

@@ -220,7 +220,9 @@ concat_rows_kernel(const __grid_constant__ ConcatDev P, int N, float* __restrict
             for (int c = threadIdx.x * 4; c < s.C; c += blockDim.x * 4) {
                 const float4 v = __ldg(reinterpret_cast<const float4*>(src + c));
                 if (out_raw) *reinterpret_cast<float4*>(out_raw + r * ld_raw + off + c) = v;
-                if (out_split) {
+                if (out_split && mixed) {
+                    mixed_store4(reinterpret_cast<uint16_t*>(out_split + r * 2 * Kp), Kp, off + c, v);
+                } else if (out_split) {
                     float4 hi;
                     uint32_t hb;
                     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v.x)); hi.x = __uint_as_float(hb);
@@ -229,18 +231,7 @@ concat_rows_kernel(const __grid_constant__ ConcatDev P, int N, float* __restrict
                     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v.w)); hi.w = __uint_as_float(hb);
                     float* q = out_split + r * 2 * Kp + off + c;
                     *reinterpret_cast<float4*>(q) = hi;
-                    if (mixed) {
-                        __nv_bfloat162 a0 = __floats2bfloat162_rn(v.x, v.y), a1 = __floats2bfloat162_rn(v.z, v.w);
-                        __nv_bfloat162 l0 = __floats2bfloat162_rn(v.x - hi.x, v.y - hi.y), l1 = __floats2bfloat162_rn(v.z - hi.z, v.w - hi.w);
-                        __nv_bfloat16* h16 = reinterpret_cast<__nv_bfloat16*>(out_split + r * 2 * Kp + Kp) + off + c;
-                        uint2 pa, pl;
-                        pa.x = *reinterpret_cast<uint32_t*>(&a0); pa.y = *reinterpret_cast<uint32_t*>(&a1);
-                        pl.x = *reinterpret_cast<uint32_t*>(&l0); pl.y = *reinterpret_cast<uint32_t*>(&l1);
-                        *reinterpret_cast<uint2*>(h16) = pa;
-                        *reinterpret_cast<uint2*>(h16 + Kp) = pl;
-                    } else {
-                        *reinterpret_cast<float4*>(q + Kp) = make_float4(v.x - hi.x, v.y - hi.y, v.z - hi.z, v.w - hi.w);
-                    }
+                    *reinterpret_cast<float4*>(q + Kp) = make_float4(v.x - hi.x, v.y - hi.y, v.z - hi.z, v.w - hi.w);
                 }
             }
             off += s.C;
@@ -249,28 +240,25 @@ concat_rows_kernel(const __grid_constant__ ConcatDev P, int N, float* __restrict
         for (int c = threadIdx.x; c < s.C; c += blockDim.x) {
             const float v = __ldg(src + c);
             if (out_raw) out_raw[r * ld_raw + off + c] = v;
-            if (out_split) {
+            if (out_split && mixed) {
+                mixed_store1(reinterpret_cast<uint16_t*>(out_split + r * 2 * Kp), Kp, off + c, v);
+            } else if (out_split) {
                 uint32_t hb;
                 asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v));
                 const float hi = __uint_as_float(hb);
                 out_split[r * 2 * Kp + off + c] = hi;
-                if (mixed) {     // [tf32 | bf16(x) | bf16(x - tf32(x))], see tgp_gemm_args.mixed
-                    __nv_bfloat16* h16 = reinterpret_cast<__nv_bfloat16*>(out_split + r * 2 * Kp + Kp);
-                    h16[off + c] = __float2bfloat16_rn(v);
-                    h16[Kp + off + c] = __float2bfloat16_rn(v - hi);
-                } else out_split[r * 2 * Kp + Kp + off + c] = v - hi;
+                out_split[r * 2 * Kp + Kp + off + c] = v - hi;
             }
         }
         off += s.C;
     }
     if (out_split)
         for (int c = off + threadIdx.x; c < Kp; c += blockDim.x) {
-            out_split[r * 2 * Kp + c] = 0.f;
-            if (mixed) {
-                __nv_bfloat16* h16 = reinterpret_cast<__nv_bfloat16*>(out_split + r * 2 * Kp + Kp);
-                h16[c] = __float2bfloat16_rn(0.f);
-                h16[Kp + c] = __float2bfloat16_rn(0.f);
-            } else out_split[r * 2 * Kp + Kp + c] = 0.f;
+            if (mixed) mixed_store1(reinterpret_cast<uint16_t*>(out_split + r * 2 * Kp), Kp, c, 0.f);
+            else {
+                out_split[r * 2 * Kp + c] = 0.f;
+                out_split[r * 2 * Kp + Kp + c] = 0.f;
+            }
         }
 }
 

@@ -47,15 +47,9 @@ struct EpiDst {
     int rel;
 };
 
-// MIXED operand row: [tf32(x) fp32 x Kp | bf16(x) x Kp | bf16(x - tf32(x)) x Kp]; p = address of the fp32 slot of column rel
+// MIXED operand row (common.cuh); p = address of the fp32 slot `rel` of the row, i.e. row base + rel floats
 __device__ __forceinline__ void store_mixed(float* p, int Kp, int rel, float v) {
-    uint32_t hb;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v));
-    const float hi = __uint_as_float(hb);
-    p[0] = hi;
-    __nv_bfloat16* h16 = reinterpret_cast<__nv_bfloat16*>(p - rel + Kp) + rel;
-    h16[0] = __float2bfloat16_rn(v);
-    h16[Kp] = __float2bfloat16_rn(v - hi);
+    mixed_store1(reinterpret_cast<uint16_t*>(p - rel), Kp, rel, v);
 }
 
 // order-preserving float -> int map for atomicMax (mode 3): signed-int order == float order
@@ -162,22 +156,7 @@ __device__ __forceinline__ void vstore(const VDst& d, int row, float4 v) {
         *reinterpret_cast<float4*>(q) = hi;
         *reinterpret_cast<float4*>(q + d.lo) = lo;
     } else if (d.kind == 4) {
-        float4 hi;
-        uint32_t hb;
-        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v.x)); hi.x = __uint_as_float(hb);
-        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v.y)); hi.y = __uint_as_float(hb);
-        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v.z)); hi.z = __uint_as_float(hb);
-        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v.w)); hi.w = __uint_as_float(hb);
-        float* q = d.p + row * d.rs;
-        *reinterpret_cast<float4*>(q) = hi;
-        __nv_bfloat162 a0 = __floats2bfloat162_rn(v.x, v.y), a1 = __floats2bfloat162_rn(v.z, v.w);
-        __nv_bfloat162 l0 = __floats2bfloat162_rn(v.x - hi.x, v.y - hi.y), l1 = __floats2bfloat162_rn(v.z - hi.z, v.w - hi.w);
-        __nv_bfloat16* h16 = reinterpret_cast<__nv_bfloat16*>(q - d.rel + d.lo) + d.rel;      // 8-byte aligned: rel % 4 == 0
-        uint2 pa, pl;
-        pa.x = *reinterpret_cast<uint32_t*>(&a0); pa.y = *reinterpret_cast<uint32_t*>(&a1);
-        pl.x = *reinterpret_cast<uint32_t*>(&l0); pl.y = *reinterpret_cast<uint32_t*>(&l1);
-        *reinterpret_cast<uint2*>(h16) = pa;
-        *reinterpret_cast<uint2*>(h16 + d.lo) = pl;
+        mixed_store4(reinterpret_cast<uint16_t*>(d.p + row * d.rs - d.rel), d.lo, d.rel, v);
     }
 }
 
@@ -349,21 +328,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const int m0 = (tt / num_n_tiles) * TC_BM, n0 = (tt % num_n_tiles) * BN;
                 const int kb0 = z * kb_per, kb1 = min(kblocks, kb0 + kb_per);
                 if (g.mixed) {
-                    // per 64 columns of K: two TF32 stages (hi.hi, 32 columns each) and two bf16 stages (lo.b, a.lo; 64
-                    // columns = one 128-byte swizzle span each).  Every stage is the same 16 KB + BN*128 B.
+                    // per 64 columns of K three 16-bit stages (64 columns = one 128-byte swizzle span each):
+                    //   fp16(a).fp16(b), lo(a).bf16(b), bf16(a).lo(b).  Every stage is 16 KB + BN*128 B.
                     for (int k64 = 0; k64 < Kp / 64; ++k64) {
-                        for (int u = 0; u < 4; ++u) {
+                        for (int u = 0; u < 3; ++u) {
                             tc_mbar_wait(empty + stage, phase ^ 1);
                             unsigned char* sa = base + stage * STAGE_BYTES;
                             tc_mbar_expect_tx(full + stage, STAGE_BYTES);
-                            if (u < 2) {
-                                tma_load_2d(sa, &tmA, k64 * 64 + u * 32, m0, full + stage);
-                                tma_load_2d(sa + TC_A_BYTES, &tmB, k64 * 64 + u * 32, n0, full + stage);
-                            } else {
-                                // u == 2: lo16(A) . hi16(B);  u == 3: hi16(A) . lo16(B)
-                                tma_load_2d(sa, &tmA16, (u == 2 ? 3 : 2) * Kp + k64 * 64, m0, full + stage);
-                                tma_load_2d(sa + TC_A_BYTES, &tmB16, (u == 2 ? 2 : 3) * Kp + k64 * 64, n0, full + stage);
-                            }
+                            const int a_part = u == 0 ? 0 : (u == 1 ? 2 : 1), b_part = u == 0 ? 0 : (u == 1 ? 1 : 2);
+                            tma_load_2d(sa, &tmA16, a_part * Kp + k64 * 64, m0, full + stage);
+                            tma_load_2d(sa + TC_A_BYTES, &tmB16, b_part * Kp + k64 * 64, n0, full + stage);
                             if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
                         }
                     }
@@ -390,8 +364,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // ===================== MMA issuer =====================
         if (lane == 0) {
             constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
-            // kind::f16 with bf16 operands (format 1), fp32 accumulate
+            // kind::f16, fp32 accumulate: bf16 operands (format 1) for the cross terms, fp16 operands (format 0) for hi.hi
             constexpr uint32_t idesc16 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+            constexpr uint32_t idesc_h = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
@@ -403,17 +378,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const uint32_t d_tmem = tmem_base + acc * BN;
                 uint32_t accum = 0;
                 const int zz = t / tiles_mn;
-                const int nkb = g.mixed ? 4 * (Kp / 64) : 3 * (min(kblocks, zz * kb_per + kb_per) - zz * kb_per);
+                const int nkb = g.mixed ? 3 * (Kp / 64) : 3 * (min(kblocks, zz * kb_per + kb_per) - zz * kb_per);
+                int u3 = 0;
                 for (int kb = 0; kb < nkb; ++kb) {
                     tc_mbar_wait(full + stage, phase);
                     tc_fence_after();
                     const uint32_t sa = s_u32(base + stage * STAGE_BYTES);
                     const uint64_t adesc = make_sw128_desc(sa), bdesc = make_sw128_desc(sa + TC_A_BYTES);
-                    if (g.mixed && (kb & 2)) {
-                        // bf16 stage: 64 columns of K, 16 per instruction = the same +32 B descriptor step
+                    if (g.mixed) {
+                        // 16-bit stage: 64 columns of K, 16 per instruction = the same +32 B descriptor step
+                        const uint32_t id = u3 == 0 ? idesc_h : idesc16;
+                        if (++u3 == 3) u3 = 0;
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
-                            umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc16, accum);
+                            umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), id, accum);
                             accum = 1;
                         }
                     } else {
@@ -567,7 +545,7 @@ __global__ void split_tf32_kernel(const float* __restrict__ src, long rows, int 
     }
 }
 
-// MIXED operand of a row-major (rows, K) matrix: [tf32(x) | bf16(x) | bf16(x - tf32(x))], zero padded to Kp (multiple of 64)
+// MIXED operand of a row-major (rows, K) matrix: [fp16(x) | bf16(x) | bf16(x - fp16(x)) | unused], zero padded to Kp (multiple of 64)
 __global__ void split_mixed_kernel(const float* __restrict__ src, long rows, int K, long ld, int Kp, float* __restrict__ dst) {
     for (long r = blockIdx.x; r < rows; r += gridDim.x) {
         float* d = dst + r * 2 * Kp;

@@ -350,7 +350,7 @@ def mixed_kpad(K):
 
 def split_mixed(x2d):
     """MIXED tensor-core operand of a row-major (rows, K) matrix (include/tgpose_b200.h, tgp_gemm_args.mixed):
-    (rows, 2*mixed_kpad(K)) fp32 slots = [tf32(x) | bf16(x), bf16(x - tf32(x))]."""
+    (rows, 2*mixed_kpad(K)) fp32 slots = 16-bit slots [fp16(x) | bf16(x) | bf16(x - fp16(x)) | unused]."""
     assert x2d.stride(-1) == 1
     rows, K = x2d.shape
     dst = torch.empty((rows, 2 * mixed_kpad(K)), dtype=torch.float32, device=x2d.device)
