@@ -132,49 +132,97 @@ orl_global_kernel(const float* __restrict__ f, const IdxT* __restrict__ idx, int
 
 
 // ORL global feature with the cloud's 32-channel slice staged in shared memory: CTA = (32-channel chunk, cloud).
-// The k-fold gather (20 x the feature map through L2 in the kernel above) becomes conflict-free shared-memory reads
-// (lane = channel = bank); HBM/L2 traffic drops to the compulsory one read of the feature map.  The per-point maxima
-// are summed per warp and the warps are added in a fixed order: deterministic, and independent of the batch.
+// The k-fold gather (20 x the feature map through L2 in the kernel above) becomes shared-memory reads; HBM/L2 traffic
+// drops to the compulsory one read of the feature map.
+//   stage  : the whole slice (N x 128 B) goes out as 16-byte cp.async pieces at once (no per-row load latency chain);
+//   gather : 8 lanes x 4 channels per point, 4 points per warp step; the point's neighbour indices sit 8 per register
+//            across its 8 lanes (the next 8 are prefetched while these are consumed) and reach the lanes by width-8
+//            shuffles; one LDS.128 per neighbour and lane: 1.75 instructions per (neighbour, channel) instead of 4.
+// The per-point maxima are summed per lane, then over the 4 point groups and the warps in a fixed order: deterministic,
+// and independent of the batch.
 constexpr int ORLS_THREADS = 512;
 template <typename IdxT, bool ARG>
 __global__ void __launch_bounds__(ORLS_THREADS)
 orl_smem_kernel(const float* __restrict__ f, const IdxT* __restrict__ idx, int N, int k, int C,
                 float* __restrict__ g, uint8_t* __restrict__ arg) {
     extern __shared__ __align__(16) float orl_tab[];       // [N][32]
-    __shared__ float part[ORLS_THREADS / 32][32];
+    __shared__ __align__(16) float part[ORLS_THREADS / 32][32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int c0 = blockIdx.x * 32, c = c0 + lane;
+    const int c0 = blockIdx.x * 32;
     const long b = blockIdx.y;
     const float* fb = f + b * N * (long)C;
-    for (int n = warp; n < N; n += ORLS_THREADS / 32) orl_tab[n * 32 + lane] = c < C ? __ldg(fb + (long)n * C + c) : 0.f;
-    __syncthreads();
-    float acc = 0.f;
-    for (int n = warp; n < N; n += ORLS_THREADS / 32) {
-        const IdxT* id = idx + (b * N + n) * k;
-        int nb = lane < k ? ld_idx(id, lane) : 0;            // k <= 32: one coalesced index load per point
-        float best = -FLT_MAX;
-        int bj = 0;
-        const int kk = k < 32 ? k : 32;
-#pragma unroll 4
-        for (int j = 0; j < kk; ++j) {
-            const float v = orl_tab[__shfl_sync(0xffffffffu, nb, j) * 32 + lane];
-            if (ARG) { if (v > best) { best = v; bj = j; } }
-            else best = fmaxf(best, v);
+    if (C % 4 == 0 && c0 + 32 <= C && ((uintptr_t)f & 15) == 0) {
+        for (int p = threadIdx.x; p < N * 8; p += ORLS_THREADS) {
+            const int n = p >> 3, q = p & 7;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(orl_tab + n * 32 + q * 4)),
+                         "l"(fb + (long)n * C + c0 + q * 4) : "memory");
         }
-        for (int j = 32; j < k; ++j) {                       // k > 32 (not used by the network)
-            const float v = orl_tab[ld_idx(id, j) * 32 + lane];
-            if (v > best) { best = v; bj = j; }
-        }
-        acc += best;
-        if (ARG && c < C) arg[(b * N + n) * (long)C + c] = (uint8_t)bj;
+        asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+    } else {
+        for (int n = warp; n < N; n += ORLS_THREADS / 32) orl_tab[n * 32 + lane] = c0 + lane < C ? __ldg(fb + (long)n * C + c0 + lane) : 0.f;
     }
-    part[warp][lane] = acc;
     __syncthreads();
-    if (warp == 0 && c < C) {
+    const int grp = lane >> 3, l8 = lane & 7;
+    const float4* tab4 = reinterpret_cast<const float4*>(orl_tab) + l8;     // row r -> tab4[r * 8]
+    constexpr int PSTEP = (ORLS_THREADS / 32) * 4;                            // points per CTA step
+    auto load = [&](int n, int j0) -> int { return (n < N && j0 + l8 < k) ? ld_idx(idx + (b * N + n) * k, j0 + l8) : 0; };
+    int n = warp * 4 + grp, j0 = 0;
+    int cur = load(n, 0);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f), best = make_float4(-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX);
+    int b0 = 0, b1 = 0, b2 = 0, b3 = 0;
+    while (n - grp < N) {                                                     // warp-uniform: the 4 groups advance together
+        int nj0 = j0 + 8, nn = n;
+        if (nj0 >= k) { nj0 = 0; nn = n + PSTEP; }
+        const int nxt = load(nn, nj0);
+        const int cnt = min(8, k - j0);
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {
+            if (jj < cnt) {
+                const int nb = __shfl_sync(0xffffffffu, cur, jj, 8);
+                const float4 v = tab4[nb * 8];
+                if (ARG) {
+                    if (v.x > best.x) { best.x = v.x; b0 = j0 + jj; }
+                    if (v.y > best.y) { best.y = v.y; b1 = j0 + jj; }
+                    if (v.z > best.z) { best.z = v.z; b2 = j0 + jj; }
+                    if (v.w > best.w) { best.w = v.w; b3 = j0 + jj; }
+                } else {
+                    best.x = fmaxf(best.x, v.x); best.y = fmaxf(best.y, v.y);
+                    best.z = fmaxf(best.z, v.z); best.w = fmaxf(best.w, v.w);
+                }
+            }
+        }
+        if (nj0 == 0) {                                                       // point finished
+            if (n < N) {
+                acc.x += best.x; acc.y += best.y; acc.z += best.z; acc.w += best.w;
+                if (ARG) {
+                    uint8_t* ap = arg + (b * N + n) * (long)C + c0 + l8 * 4;
+                    if (c0 + l8 * 4 + 3 < C && (C & 3) == 0) *reinterpret_cast<uchar4*>(ap) = make_uchar4((uint8_t)b0, (uint8_t)b1, (uint8_t)b2, (uint8_t)b3);
+                    else {
+                        if (c0 + l8 * 4 + 0 < C) ap[0] = (uint8_t)b0;
+                        if (c0 + l8 * 4 + 1 < C) ap[1] = (uint8_t)b1;
+                        if (c0 + l8 * 4 + 2 < C) ap[2] = (uint8_t)b2;
+                        if (c0 + l8 * 4 + 3 < C) ap[3] = (uint8_t)b3;
+                    }
+                }
+            }
+            best = make_float4(-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX);
+            b0 = b1 = b2 = b3 = 0;
+        }
+        cur = nxt; j0 = nj0; n = nn;
+    }
+    // fixed-order sums: the 4 point groups of a warp, then the warps
+#pragma unroll
+    for (int o = 8; o <= 16; o <<= 1) {
+        acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o); acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+        acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o); acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
+    }
+    if (lane < 8) *reinterpret_cast<float4*>(&part[warp][lane * 4]) = acc;
+    __syncthreads();
+    if (warp == 0 && c0 + lane < C) {
         float s = 0.f;
 #pragma unroll
         for (int w = 0; w < ORLS_THREADS / 32; ++w) s += part[w][lane];
-        g[b * C + c] = s / (float)N;
+        g[b * C + c0 + lane] = s / (float)N;
     }
 }
 
