@@ -12,7 +12,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-fi
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-graph > $O/${R}_ncu_launches.log 2>&1
 fi
 # (ncu matches the base name, without the tgp:: namespace)
-KERNELS="^(concat_rows|edge_record|gather_max|gather_rows|gemm_naive|gemm_skinny|gemm_simt|gemm_tc|knn_tc|knn_xyz|knn_feat|layer_conv|nearest|orl_|rownorm|select_rows|split_tf32|split_mixed|surface_conv|direction_norm)"
+KERNELS="^(concat_rows|decode_max|edge_record|gather_max|gather_rows|gemm_naive|gemm_skinny|gemm_simt|gemm_tc|knn_tc|knn_xyz|knn_feat|layer_conv|nearest|orl_|rownorm|select_rows|split_tf32|split_mixed|surface_conv|direction_norm)"
 # 2. every library kernel of ONE forward (third forward of the script: warm caches / packs) with the sections the
 #    roofline needs; the report stays on the box (it exceeds the 64 MiB return limit), only its raw CSV page comes back
 python scripts/profile_forward.py > $O/${R}_plain_fwd.log 2>&1 &&

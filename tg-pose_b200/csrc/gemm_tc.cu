@@ -160,6 +160,11 @@ __device__ __forceinline__ void vstore(const VDst& d, int row, float4 v) {
     }
 }
 
+// LEAN (host-checked: no residual, no per-cloud bias, no column-max segment, segments do not overlap): the epilogue of the
+// projection / head GEMMs that only add a bias, optionally apply the BatchNorm affine + activation and write ONE
+// destination per column -- ~4x fewer instructions per chunk than the general path, which matters because only 8 epilogue
+// warps are resident and the K = 128..256 encoder GEMMs are bound by exactly this code.
+template <bool LEAN>
 __device__ __forceinline__ void epi_chunk_vec(const tgp_gemm_args& g, uint32_t stg_addr, const uint32_t (&r)[32], int lane,
                                               long row0, int nrows, int colbase, long grp0, int gb_switch, long zoff) {
     // stage: thread = row writes its 32 columns as 8 float4, slot j ^ (row & 7) of its 128-byte line
@@ -206,18 +211,21 @@ __device__ __forceinline__ void epi_chunk_vec(const tgp_gemm_args& g, uint32_t s
                     d.p = g.seg[s].ptr + zoff + row0 * d.rs + rel;
                     d.lo = g.seg[s].slab_width;
                 }
-                if (!d0.kind) d0 = d; else d1 = d;
+                if (LEAN || !d0.kind) d0 = d; else d1 = d;
             }
         }
-        if (g.group_bias) {
-            gb0 = ldg4s(g.group_bias + grp0 * g.Ncols + col);
-            if (gb_switch < nrows) gb1 = ldg4s(g.group_bias + (grp0 + 1) * g.Ncols + col);
+        if (!LEAN) {
+            if (g.group_bias) {
+                gb0 = ldg4s(g.group_bias + grp0 * g.Ncols + col);
+                if (gb_switch < nrows) gb1 = ldg4s(g.group_bias + (grp0 + 1) * g.Ncols + col);
+            }
+            if (g.res1) r1p = g.res1 + row0 * g.ld_res1 + col;
+            if (g.res2) r2p = g.res2 + row0 * g.ld_res2 + col;
         }
-        if (g.res1) r1p = g.res1 + row0 * g.ld_res1 + col;
-        if (g.res2) r2p = g.res2 + row0 * g.ld_res2 + col;
     }
     float4 mx0 = make_float4(-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F), mx1 = mx0;
-    const bool any_max = d0.kind == 3 || d1.kind == 3;
+    const bool any_max = !LEAN && (d0.kind == 3 || d1.kind == 3);
+    const bool has_act = g.scale != nullptr || g.neg_slope != nullptr || g.relu != 0;       // warp-uniform
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
         float4 a[4];
@@ -226,6 +234,21 @@ __device__ __forceinline__ void epi_chunk_vec(const tgp_gemm_args& g, uint32_t s
             const int row = (half * 4 + u) * 4 + rsub;
             const uint32_t ad = stg_addr + (uint32_t)(row * 128 + ((c4i ^ (row & 7)) << 4));
             asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a[u].x), "=f"(a[u].y), "=f"(a[u].z), "=f"(a[u].w) : "r"(ad));
+        }
+        if (LEAN) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int row = (half * 4 + u) * 4 + rsub;
+                if (live && row < nrows) {
+                    float4 v = f4add(a[u], bias);
+                    if (has_act) {
+                        v.x = act1(v.x, sc.x, sh.x, sl.x); v.y = act1(v.y, sc.y, sh.y, sl.y);
+                        v.z = act1(v.z, sc.z, sh.z, sl.z); v.w = act1(v.w, sc.w, sh.w, sl.w);
+                    }
+                    vstore(d0, row, v);
+                }
+            }
+            continue;
         }
         float4 q1[4], q2[4];
 #pragma unroll
@@ -255,7 +278,7 @@ __device__ __forceinline__ void epi_chunk_vec(const tgp_gemm_args& g, uint32_t s
             }
         }
     }
-    if (__any_sync(0xffffffffu, any_max)) {
+    if (!LEAN && __any_sync(0xffffffffu, any_max)) {
         // combine the 4 row sub-groups (lanes differing in bits 3, 4), then one atomicMax per column and group
 #pragma unroll
         for (int o = 8; o <= 16; o <<= 1) {
@@ -444,8 +467,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 TMEM_LD_32x32(taddr, r);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                 __syncwarp();
+                if (vec_ok == 2 && !(dbg & 1)) {
+                    epi_chunk_vec<true>(g, stg_addr, r, lane, row0, nrows, n0 + c0, grp0, gb_switch, z * zstride);
+                    continue;
+                }
                 if (vec_ok && !gb_slow && !(dbg & 1)) {
-                    epi_chunk_vec(g, stg_addr, r, lane, row0, nrows, n0 + c0, grp0, gb_switch, z * zstride);
+                    epi_chunk_vec<false>(g, stg_addr, r, lane, row0, nrows, n0 + c0, grp0, gb_switch, z * zstride);
                     continue;
                 }
 #pragma unroll
@@ -675,6 +702,17 @@ static int launch_tc(const tgp_gemm_args* a, cudaStream_t st, int ksplit = 1) {
         vec_ok = vec_ok && al16(sg.ptr);
         if (sg.mode == 1) vec_ok = vec_ok && sg.slab_width % 4 == 0;
         else vec_ok = vec_ok && sg.ld % 4 == 0 && ((sg.mode != 2 && sg.mode != 4) || sg.slab_width % 4 == 0);
+    }
+    if (vec_ok && !a->res1 && !a->res2 && !a->group_bias) {
+        // lean epilogue: one destination per column (segments disjoint), no column-max cells
+        bool lean = true;
+        for (int s = 0; s < a->nseg && lean; ++s) {
+            if (a->seg[s].mode == 3) lean = false;
+            for (int t = 0; t < s && lean; ++t)
+                if (a->seg[s].col_begin < a->seg[t].col_end && a->seg[t].col_begin < a->seg[s].col_end) lean = false;
+        }
+        { const char* e = getenv("TGP_TC_NO_LEAN"); if (e && e[0] == '1') lean = false; }
+        if (lean) vec_ok = 2;
     }
     { const char* e = getenv("TGP_TC_SCALAR_EPI"); if (e && e[0] == '1') vec_ok = 0; }
     static int dbg = -1;
