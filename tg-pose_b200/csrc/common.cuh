@@ -79,16 +79,25 @@ __device__ __forceinline__ void mixed_store1(uint16_t* row16, int Kp, int col, f
     row16[Kp + col] = bf16_bits(v);
     row16[2 * Kp + col] = bf16_bits(v - hi);
 }
-// four consecutive values (col % 4 == 0, row 16-byte aligned): three 8-byte stores
+// two values -> packed fp16x2 (saturating; x in the low half) and their fp32 read-back
+__device__ __forceinline__ uint32_t mixed_hi16x2(float x, float y, float& hx, float& hy) {
+    uint32_t d;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(y), "f"(x));
+    asm("{\n\t.reg .b16 l, h;\n\tmov.b32 {l, h}, %2;\n\tcvt.f32.f16 %0, l;\n\tcvt.f32.f16 %1, h;\n\t}" : "=f"(hx), "=f"(hy) : "r"(d));
+    return d;
+}
+__device__ __forceinline__ uint32_t bf16x2_bits(float x, float y) {
+    uint32_t d;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(y), "f"(x));
+    return d;
+}
+// four consecutive values (col % 4 == 0, row 16-byte aligned): three 8-byte stores, packed conversions
 __device__ __forceinline__ void mixed_store4(uint16_t* row16, int Kp, int col, float4 v) {
     float h0, h1, h2, h3;
-    const uint32_t a0 = mixed_hi16(v.x, h0), a1 = mixed_hi16(v.y, h1), a2 = mixed_hi16(v.z, h2), a3 = mixed_hi16(v.w, h3);
-    *reinterpret_cast<uint2*>(row16 + col) = make_uint2(a0 | (a1 << 16), a2 | (a3 << 16));
-    *reinterpret_cast<uint2*>(row16 + Kp + col) =
-        make_uint2((uint32_t)bf16_bits(v.x) | ((uint32_t)bf16_bits(v.y) << 16), (uint32_t)bf16_bits(v.z) | ((uint32_t)bf16_bits(v.w) << 16));
-    *reinterpret_cast<uint2*>(row16 + 2 * Kp + col) =
-        make_uint2((uint32_t)bf16_bits(v.x - h0) | ((uint32_t)bf16_bits(v.y - h1) << 16),
-                   (uint32_t)bf16_bits(v.z - h2) | ((uint32_t)bf16_bits(v.w - h3) << 16));
+    const uint32_t a01 = mixed_hi16x2(v.x, v.y, h0, h1), a23 = mixed_hi16x2(v.z, v.w, h2, h3);
+    *reinterpret_cast<uint2*>(row16 + col) = make_uint2(a01, a23);
+    *reinterpret_cast<uint2*>(row16 + Kp + col) = make_uint2(bf16x2_bits(v.x, v.y), bf16x2_bits(v.z, v.w));
+    *reinterpret_cast<uint2*>(row16 + 2 * Kp + col) = make_uint2(bf16x2_bits(v.x - h0, v.y - h1), bf16x2_bits(v.z - h2, v.w - h3));
 }
 
 #define TGP_DISPATCH_IDX(bits, ...)                                   \
