@@ -232,6 +232,9 @@ layer_conv_kernel(const float4* __restrict__ rec, const float* __restrict__ dire
         __syncwarp();
         rp += rstep;
         if (n + nwarps < n_end && lane < k) nxt = __ldg(rp + lane);
+        // the centre term is only needed after the neighbour loop: fetch it now so its latency hides behind the loop
+        float cen = 0.f;
+        if (lane < 4) cen = __ldg(centre + pt * ld_centre + cg * 4 + lane);
         float m = -FLT_MAX;
         int a = 0;
         if (lane < W) {
@@ -252,8 +255,7 @@ layer_conv_kernel(const float4* __restrict__ rec, const float* __restrict__ dire
         m += __shfl_down_sync(0xffffffffu, m, 16);
         m += __shfl_down_sync(0xffffffffu, m, 8);
         m += __shfl_down_sync(0xffffffffu, m, 4);
-        if (lane < 4)
-            store_out(out, out_split, kp, pt, C, cg * 4 + lane, __ldg(centre + pt * ld_centre + cg * 4 + lane) + m * inv_s);
+        if (lane < 4) store_out(out, out_split, kp, pt, C, cg * 4 + lane, cen + m * inv_s);
     }
 }
 
