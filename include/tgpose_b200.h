@@ -206,6 +206,8 @@ int tgp_split_tf32(const float* src, long rows, int K, long ld, int src_is_kn, f
 /* mixed operand (tgp_gemm_args.mixed): K rounded up to 64, and the split of a row-major (rows, K) matrix (zero padded). */
 int tgp_mixed_kpad(int K);
 int tgp_split_mixed(const float* src, long rows, int K, long ld, float* dst, tgp_stream_t stream);
+/* transposed mixed operand: dst (K, 8*Mp bytes), Mp = tgp_mixed_kpad(rows), row k = column k of src (zero padded). */
+int tgp_split_mixed_t(const float* src, long rows, int K, long ld, float* dst, tgp_stream_t stream);
 
 /* ------------------------------------------------------------------ chamfer (losses/chamfer3D) */
 
@@ -281,14 +283,16 @@ int tgp_surface_conv_bwd(const float* xyz, const void* idx, int idx_bits, const 
 /* weight-gradient contraction out (K1,K2; row stride ldo) = A^T B with A (M,K1), B (M,K2) row-major
  * (dW = x^T dY of `feature_map @ weights`, gcn3d.py:170, and of every 1x1 Conv1d on the path).
  * tgp_gemm_tn: exact fp32 FMA path on the raw operands (small / odd shapes).
- * tgp_gemm_tn_tc: tcgen05 3xTF32 path; operands are the TRANSPOSED splits from tgp_split_tf32(src_is_kn=1):
- *                 At_split (K1, 2*Mp), Bt_split (K2, 2*Mp), Mp = tgp_split_kpad(M); split-K over M. */
+ * tgp_gemm_tn_tc: tcgen05 path; operands are the TRANSPOSED splits: mixed = 0 (3xTF32) from tgp_split_tf32(src_is_kn=1),
+ *                 At_split (K1, 2*Mp), Bt_split (K2, 2*Mp), Mp = tgp_split_kpad(M); mixed = 1 (fp16 + bf16 cross terms,
+ *                 see tgp_gemm_args.mixed) from tgp_split_mixed_t, rows of 8*Mp bytes, Mp = tgp_mixed_kpad(M).
+ *                 Split-K over M, partial sums added in a fixed order (deterministic). */
 size_t tgp_gemm_tn_workspace(long M, int K1, int K2);
 int tgp_gemm_tn(const float* A, long lda, const float* Bm, long ldb, long M, int K1, int K2, float* out, long ldo,
                 void* workspace, size_t workspace_bytes, tgp_stream_t stream);
 size_t tgp_gemm_tn_tc_workspace(long M, int K1, int K2);
 int tgp_gemm_tn_tc(const float* At_split, const float* Bt_split, long M, int K1, int K2, float* out, long ldo,
-                   void* workspace, size_t workspace_bytes, tgp_stream_t stream);
+                   int mixed, void* workspace, size_t workspace_bytes, tgp_stream_t stream);
 
 /* ------------------------------------------------------------------ heads in training
  * Train-mode Conv1d(k=1) + BatchNorm1d + ReLU/LeakyReLU stacks of the heads (PoseR.py:26-33, PoseTs.py:31-38,

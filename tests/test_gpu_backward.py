@@ -54,6 +54,19 @@ def test_gemm_tn(ops, M, K1, K2, tc):
     assert float(dst[:, :4].abs().max()) == 0.0 and float(dst[:, 4 + K2:].abs().max()) == 0.0
 
 
+@pytest.mark.parametrize("M,K1,K2", [(1000, 128, 1152), (40000, 256, 1289), (5001, 70, 48), (33000, 1024, 256)])
+def test_gemm_tn_mixed(ops, M, K1, K2):
+    """weight-gradient contraction of the heads on transposed MIXED operands (fp16 hi.hi + bf16 cross terms, split-K):
+    error at the fp32-summation-noise level of the output scale, deterministic, strided operands accepted."""
+    g = torch.Generator().manual_seed(M + K1 + K2)
+    A = torch.randn(M, K1, generator=g).cuda()
+    B = torch.randn(M, K2 + 3, generator=g).cuda()[:, 3:]
+    out = ops.gemm_tn(A, B, tc=True, mixed=True)
+    ref = A.double().t() @ B.double()
+    assert float((out.double() - ref).abs().max()) <= 1.6e-5 * float(ref.abs().max()) * max(1.0, (M / 4096) ** 0.5)
+    assert torch.equal(out, ops.gemm_tn(A, B, tc=True, mixed=True))
+
+
 def test_gemm_tn_tc_is_deterministic(ops):
     g = torch.Generator().manual_seed(1)
     A = torch.randn(30000, 128, generator=g).cuda()

@@ -71,6 +71,7 @@ SIGNATURES = {
     "tgp_decode_max": (c_int, [c_void_p, c_long, c_void_p, c_void_p]),
     "tgp_mixed_kpad": (c_int, [c_int]),
     "tgp_split_mixed": (c_int, [c_void_p, c_long, c_int, c_long, c_void_p, c_void_p]),
+    "tgp_split_mixed_t": (c_int, [c_void_p, c_long, c_int, c_long, c_void_p, c_void_p]),
     "tgp_dcd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, ctypes.c_float, ctypes.c_float,
                         c_void_p, c_void_p, c_void_p, c_void_p]),
     "tgp_act_bwd": (c_int, [c_void_p, c_long, c_void_p, c_long, c_void_p, c_int, c_long, c_int, c_void_p, c_long,
@@ -97,7 +98,7 @@ SIGNATURES = {
     "tgp_gemm_tn": (c_int, [c_void_p, c_long, c_void_p, c_long, c_long, c_int, c_int, c_void_p, c_long, c_void_p,
                             c_size_t, c_void_p]),
     "tgp_gemm_tn_tc_workspace": (c_size_t, [c_long, c_int, c_int]),
-    "tgp_gemm_tn_tc": (c_int, [c_void_p, c_void_p, c_long, c_int, c_int, c_void_p, c_long, c_void_p, c_size_t,
+    "tgp_gemm_tn_tc": (c_int, [c_void_p, c_void_p, c_long, c_int, c_int, c_void_p, c_long, c_int, c_void_p, c_size_t,
                                c_void_p]),
 }
 

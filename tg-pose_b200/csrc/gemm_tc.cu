@@ -323,7 +323,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
     const tgp_gemm_args& g = P.a;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int kblocks = Kp / TC_BK;
+    const int kblocks = P.a.mixed ? Kp / 64 : Kp / TC_BK;      // K blocks: 64 columns (mixed) or 32 (tf32)
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < TC_STAGES; ++s) { tc_mbar_init(full + s, 1); tc_mbar_init(empty + s, 1); }
@@ -353,7 +353,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (g.mixed) {
                     // per 64 columns of K three 16-bit stages (64 columns = one 128-byte swizzle span each):
                     //   fp16(a).fp16(b), lo(a).bf16(b), bf16(a).lo(b).  Every stage is 16 KB + BN*128 B.
-                    for (int k64 = 0; k64 < Kp / 64; ++k64) {
+                    for (int k64 = kb0; k64 < kb1; ++k64) {
                         for (int u = 0; u < 3; ++u) {
                             tc_mbar_wait(empty + stage, phase ^ 1);
                             unsigned char* sa = base + stage * STAGE_BYTES;
@@ -401,7 +401,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const uint32_t d_tmem = tmem_base + acc * BN;
                 uint32_t accum = 0;
                 const int zz = t / tiles_mn;
-                const int nkb = g.mixed ? 3 * (Kp / 64) : 3 * (min(kblocks, zz * kb_per + kb_per) - zz * kb_per);
+                const int nkb = 3 * (min(kblocks, zz * kb_per + kb_per) - zz * kb_per);
                 int u3 = 0;
                 for (int kb = 0; kb < nkb; ++kb) {
                     tc_mbar_wait(full + stage, phase);
@@ -625,7 +625,47 @@ using namespace tgp;
 
 extern "C" int tgp_split_kpad(int K) { return (K + TC_BK - 1) / TC_BK * TC_BK; }
 
+// transposed MIXED operand of a row-major (rows, K) matrix: dst row k holds column k of src, rows padded to
+// Mp = ceil64(rows) with zeros -- the operand of the weight-gradient contraction x^T . dY (contraction over the rows).
+// Tile = 64 rows x 32 columns through shared memory; a lane packs two consecutive rows per 32-bit store.
+__global__ void __launch_bounds__(256)
+split_mixed_transpose_kernel(const float* __restrict__ src, long rows, int K, long ld, long Mp, float* __restrict__ dst) {
+    __shared__ float tile[64][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const long r0 = (long)blockIdx.y * 64;
+    const int k0 = blockIdx.x * 32;
+#pragma unroll
+    for (int rr = 0; rr < 64; rr += 8) {
+        const long r = r0 + rr + ty;
+        tile[rr + ty][tx] = (r < rows && k0 + tx < K) ? __ldg(src + r * ld + k0 + tx) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < 32; kk += 8) {
+        const int k = k0 + kk + ty;
+        if (k >= K) continue;
+        const float v0 = tile[2 * tx][kk + ty], v1 = tile[2 * tx + 1][kk + ty];
+        float h0, h1;
+        uint32_t* row32 = reinterpret_cast<uint32_t*>(dst + (long)k * 2 * Mp);      // 4*Mp 16-bit slots = 2*Mp words
+        const long w = r0 / 2 + tx;
+        row32[w] = mixed_hi16x2(v0, v1, h0, h1);
+        row32[Mp / 2 + w] = bf16x2_bits(v0, v1);
+        row32[Mp + w] = bf16x2_bits(v0 - h0, v1 - h1);
+    }
+}
+
 extern "C" int tgp_mixed_kpad(int K) { return (K + 63) / 64 * 64; }
+
+extern "C" int tgp_split_mixed_t(const float* src, long rows, int K, long ld, float* dst, tgp_stream_t stream) {
+    if (!src || !dst) return fail(TGP_EINVAL, "tgp_split_mixed_t: null pointer");
+    if (rows <= 0 || rows > 0x7fffffffL - 64 || K <= 0) return fail(TGP_EINVAL, "tgp_split_mixed_t: bad sizes");
+    if ((uintptr_t)dst % 16) return fail(TGP_EINVAL, "tgp_split_mixed_t: dst must be 16-byte aligned");
+    const long Mp = (rows + 63) / 64 * 64;
+    dim3 grid((unsigned)((K + 31) / 32), (unsigned)(Mp / 64));
+    if (grid.y > 65535) return fail(TGP_EINVAL, "tgp_split_mixed_t: too many rows");
+    split_mixed_transpose_kernel<<<grid, 256, 0, as_stream(stream)>>>(src, rows, K, ld, Mp, dst);
+    return check_launch("split_mixed_transpose_kernel");
+}
 
 extern "C" int tgp_split_mixed(const float* src, long rows, int K, long ld, float* dst, tgp_stream_t stream) {
     if (!src || !dst) return fail(TGP_EINVAL, "tgp_split_mixed: null pointer");
@@ -664,7 +704,6 @@ static int launch_tc(const tgp_gemm_args* a, cudaStream_t st, int ksplit = 1) {
     rc = tgp_make_map(&tmB, a->B_split, a->Ncols, Kp, BN);
     if (rc) return rc;
     if (a->mixed) {
-        if (ksplit != 1) return fail(TGP_EINVAL, "tgp_gemm: split-K is not available for mixed operands");
         rc = tgp_make_map_bf16(&tmA16, a->A_split, a->M, Kp, TC_BM);
         if (rc) return rc;
         rc = tgp_make_map_bf16(&tmB16, a->B_split, a->Ncols, Kp, BN);
@@ -678,7 +717,7 @@ static int launch_tc(const tgp_gemm_args* a, cudaStream_t st, int ksplit = 1) {
     const int num_m_tiles = (int)((a->M + TC_BM - 1) / TC_BM);
     const int num_n_tiles = (a->Ncols + BN - 1) / BN;
     const int tiles_mn = num_m_tiles * num_n_tiles;
-    const int kblocks = Kp / TC_BK;
+    const int kblocks = a->mixed ? Kp / 64 : Kp / TC_BK;
     const int kb_per = (kblocks + ksplit - 1) / ksplit;
     ksplit = (kblocks + kb_per - 1) / kb_per;          // no empty slices
     const int num_tiles = tiles_mn * ksplit;
@@ -739,11 +778,11 @@ int tgp_gemm_tc(const tgp_gemm_args* a, cudaStream_t st) {
 // TRANSPOSED splits (tgp_split_tf32 with src_is_kn): At_split (K1, 2*Mp), Bt_split (K2, 2*Mp).  The long
 // contraction is cut into split-K slices (one TMEM accumulator each, partials in `workspace`) that a second
 // kernel adds in a fixed order.
-static int tn_plan(long M, int K1, int K2, int* bn_out) {
+static int tn_plan(long M, int K1, int K2, int* bn_out, int mixed = 0) {
     const long mt = (K1 + TC_BM - 1) / TC_BM;
     int bn = K2 > 128 ? 256 : (K2 > 64 ? 128 : 64);
     const long tiles = mt * ((K2 + bn - 1) / bn);
-    const int kblocks = tgp_split_kpad((int)M) / TC_BK;
+    const int kblocks = mixed ? tgp_mixed_kpad((int)M) / 64 : tgp_split_kpad((int)M) / TC_BK;
     long ks = (2L * TGP_NUM_SMS + tiles - 1) / tiles;
     const long cap = kblocks / 16 > 0 ? kblocks / 16 : 1;     // at least 16 K blocks (x3 passes) per slice
     if (ks > cap) ks = cap;
@@ -758,19 +797,20 @@ static int tn_plan(long M, int K1, int K2, int* bn_out) {
 extern "C" size_t tgp_gemm_tn_tc_workspace(long M, int K1, int K2) {
     if (M <= 0 || K1 <= 0 || K2 <= 0) return 0;
     int bn;
-    const int ks = tn_plan(M, K1, K2, &bn);
-    return (size_t)ks * K1 * K2 * sizeof(float);
+    const int ks = tn_plan(M, K1, K2, &bn), ksm = tn_plan(M, K1, K2, &bn, 1);
+    return (size_t)(ks > ksm ? ks : ksm) * K1 * K2 * sizeof(float);
 }
 
 extern "C" int tgp_gemm_tn_tc(const float* At_split, const float* Bt_split, long M, int K1, int K2, float* out,
-                              long ldo, void* workspace, size_t workspace_bytes, tgp_stream_t stream) {
+                              long ldo, int mixed, void* workspace, size_t workspace_bytes, tgp_stream_t stream) {
     if (!At_split || !Bt_split || !out || !workspace) return fail(TGP_EINVAL, "tgp_gemm_tn_tc: null pointer");
     if (M <= 0 || M > 0x7fffffffL - 64 || K1 <= 0 || K2 <= 0) return fail(TGP_EINVAL, "tgp_gemm_tn_tc: bad sizes");
     if ((uintptr_t)At_split % 16 || (uintptr_t)Bt_split % 16) return fail(TGP_EINVAL, "tgp_gemm_tn_tc: operands must be 16-byte aligned");
     if (workspace_bytes < tgp_gemm_tn_tc_workspace(M, K1, K2)) return fail(TGP_ENOSPACE, "tgp_gemm_tn_tc: workspace too small");
     int bn;
-    const int ks = tn_plan(M, K1, K2, &bn);
+    const int ks = tn_plan(M, K1, K2, &bn, mixed);
     tgp_gemm_args a = {};
+    a.mixed = mixed ? 1 : 0;
     a.A_split = At_split;
     a.B_split = Bt_split;
     a.M = K1;

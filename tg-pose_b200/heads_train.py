@@ -23,8 +23,7 @@ class _ConvBNActFn(torch.autograd.Function):
         cout, cin = weight.shape[0], weight.shape[1]
         w2 = weight.reshape(cout, cin)
         z = torch.empty((M, cout), dtype=torch.float32, device=x2d.device)
-        # forward and dx contractions on MIXED operands (TF32 + bf16 cross terms, see tgp_gemm_args.mixed); the weight
-        # gradient keeps the transposed 3xTF32 operands
+        # forward, dx and weight-gradient contractions on MIXED operands (fp16 + bf16 cross terms, see tgp_gemm_args.mixed)
         xs = x_split if (x_split is not None and x_split.numel()) else ops.split_mixed(x2d)
         ops.gemm(None, w2, True, [(0, cout, z, 0, 0)], bias=bias, K=cin, A_split=xs, B_split=ops.split_mixed(w2.detach()),
                  mixed=True)
@@ -47,7 +46,7 @@ class _ConvBNActFn(torch.autograd.Function):
     def backward(ctx, dy, _ds, _dm, _dv):
         x2d, w2, z, y, mean, invstd, gamma = ctx.saved_tensors
         dz, dbeta, dgamma = ops.bn_bwd(dy, y, z, mean, invstd, gamma, ctx.slope)
-        dw = ops.gemm_tn(dz, x2d).view(ctx.wshape)
+        dw = ops.gemm_tn(dz, x2d, mixed=True).view(ctx.wshape)
         db = ops.colsum(dz).view(-1) if ctx.has_bias else None
         dx = None
         if ctx.needs_input_grad[0]:

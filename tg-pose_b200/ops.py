@@ -499,9 +499,19 @@ def surface_conv_bwd(xyz, idx, directions, arg, grad2d, S, C):
     return dd
 
 
-def gemm_tn(A2d, B2d, out=None, tc=None):
+def split_mixed_t(x2d):
+    """TRANSPOSED mixed operand of a row-major (rows, K) matrix: (K, 2*mixed_kpad(rows)) fp32 slots, row k = column k."""
+    assert x2d.stride(1) == 1
+    rows, K = x2d.shape
+    dst = torch.empty((K, 2 * mixed_kpad(rows)), dtype=torch.float32, device=x2d.device)
+    _run("split_mixed_t", _lib.load().tgp_split_mixed_t, _p(x2d), rows, K, x2d.stride(0), _p(dst), _stream())
+    return dst
+
+
+def gemm_tn(A2d, B2d, out=None, tc=None, mixed=False):
     """A^T B: (M,K1),(M,K2) -> (K1,K2), the weight-gradient contraction.  Large shapes run on the tensor cores
-    (transposed tf32 splits + split-K), small / skinny ones on the exact fp32 FMA kernel."""
+    (transposed splits + split-K; 3xTF32, or the heads' mixed fp16+bf16 operands when mixed), small / skinny ones on the
+    exact fp32 FMA kernel."""
     M, K1 = A2d.shape
     K2 = B2d.shape[1]
     assert B2d.shape[0] == M and A2d.stride(1) == 1 and B2d.stride(1) == 1
@@ -512,12 +522,14 @@ def gemm_tn(A2d, B2d, out=None, tc=None):
     if tc is None:
         tc = TC_ENABLED and M >= 512 and K1 >= 16 and K2 >= 16
     if tc:
-        At = split_tf32(A2d, src_is_kn=True)
+        spl = split_mixed_t if mixed else (lambda t: split_tf32(t, src_is_kn=True))
+        At = spl(A2d)
         Bt = At if (B2d.data_ptr() == A2d.data_ptr() and B2d.shape == A2d.shape and B2d.stride() == A2d.stride()) \
-            else split_tf32(B2d, src_is_kn=True)
+            else spl(B2d)
         nb = lib.tgp_gemm_tn_tc_workspace(M, K1, K2)
         ws = _ws(nb, A2d.device)
-        _run("gemm_tn_tc", lib.tgp_gemm_tn_tc, _p(At), _p(Bt), M, K1, K2, _p(out), out.stride(0), _p(ws), nb, _stream())
+        _run("gemm_tn_tc", lib.tgp_gemm_tn_tc, _p(At), _p(Bt), M, K1, K2, _p(out), out.stride(0), 1 if mixed else 0,
+             _p(ws), nb, _stream())
     else:
         nb = lib.tgp_gemm_tn_workspace(M, K1, K2)
         ws = _ws(nb, A2d.device)
