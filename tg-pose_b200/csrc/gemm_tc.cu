@@ -384,8 +384,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
+        // ===================== MMA issuer (whole warp converged, one elected lane issues: descriptors and loop state
+        // stay in uniform registers -- ~2 instructions per MMA instead of ~8 with a single-lane branch) =====================
+        {
             constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
             // kind::f16, fp32 accumulate: bf16 operands (format 1) for the cross terms, fp16 operands (format 0) for hi.hi
             constexpr uint32_t idesc16 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
@@ -408,27 +409,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     tc_fence_after();
                     const uint32_t sa = s_u32(base + stage * STAGE_BYTES);
                     const uint64_t adesc = make_sw128_desc(sa), bdesc = make_sw128_desc(sa + TC_A_BYTES);
-                    if (g.mixed) {
-                        // 16-bit stage: 64 columns of K, 16 per instruction = the same +32 B descriptor step
-                        const uint32_t id = u3 == 0 ? idesc_h : idesc16;
-                        if (++u3 == 3) u3 = 0;
+                    const uint32_t id = u3 == 0 ? idesc_h : idesc16;
+                    if (++u3 == 3) u3 = 0;
+                    if (tc_elect_one()) {
+                        if (g.mixed) {
+                            // 16-bit stage: 64 columns of K, 16 per instruction = the same +32 B descriptor step
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), id, accum);
-                            accum = 1;
-                        }
-                    } else {
+                            for (int k = 0; k < 4; ++k)
+                                umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), id, k ? 1u : accum);
+                        } else if (!(dbg & 2)) {
 #pragma unroll
-                        for (int k = 0; k < ((dbg & 2) ? 0 : TC_BK / 8); ++k) {
-                            // +32 B along K inside the swizzle span = +2 in the descriptor's 16-byte address units
-                            umma_tf32(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, accum);
-                            accum = 1;
+                            for (int k = 0; k < TC_BK / 8; ++k)
+                                // +32 B along K inside the swizzle span = +2 in the descriptor's 16-byte address units
+                                umma_tf32(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, k ? 1u : accum);
                         }
+                        umma_commit(empty + stage);
                     }
-                    umma_commit(empty + stage);
+                    __syncwarp();
+                    accum = 1;
                     if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(tmem_full + acc);
+                if (tc_elect_one()) umma_commit(tmem_full + acc);
+                __syncwarp();
             }
         }
     } else {

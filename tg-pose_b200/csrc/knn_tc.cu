@@ -329,8 +329,8 @@ knn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
+        // ===================== MMA issuer (whole warp converged; one elected lane issues) =====================
+        {
             constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(KT_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
             int stage = 0;
             uint32_t phase = 0;
@@ -356,17 +356,21 @@ knn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                             const uint32_t sb = s_u32(base + stage * KT_STAGE_BYTES);
                             const uint64_t bhi = make_sw128_desc(sb), blo = make_sw128_desc(sb + TC_A_BYTES);
                             const uint32_t ahi = tmem_base + A_COL + kb * TC_BK, alo = ahi + Kp;
+                            if (tc_elect_one()) {
 #pragma unroll
-                            for (int kk = 0; kk < TC_BK / 8; ++kk) {
-                                umma_tf32_ts(d_tmem, alo + 8 * kk, bhi + (uint64_t)(2 * kk), idesc, accum);
-                                umma_tf32_ts(d_tmem, ahi + 8 * kk, blo + (uint64_t)(2 * kk), idesc, 1);
-                                umma_tf32_ts(d_tmem, ahi + 8 * kk, bhi + (uint64_t)(2 * kk), idesc, 1);
-                                accum = 1;
+                                for (int kk = 0; kk < TC_BK / 8; ++kk) {
+                                    umma_tf32_ts(d_tmem, alo + 8 * kk, bhi + (uint64_t)(2 * kk), idesc, kk ? 1u : accum);
+                                    umma_tf32_ts(d_tmem, ahi + 8 * kk, blo + (uint64_t)(2 * kk), idesc, 1);
+                                    umma_tf32_ts(d_tmem, ahi + 8 * kk, bhi + (uint64_t)(2 * kk), idesc, 1);
+                                }
+                                umma_commit(empty + stage);
                             }
-                            umma_commit(empty + stage);
+                            __syncwarp();
+                            accum = 1;
                             if (++stage == KT_STAGES) { stage = 0; phase ^= 1; }
                         }
-                        umma_commit(tmem_full + acc);
+                        if (tc_elect_one()) umma_commit(tmem_full + acc);
+                        __syncwarp();
                         continue;
                     }
                     for (int kb = 0; kb < 3 * kblocks; ++kb) {
@@ -374,15 +378,18 @@ knn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                         tc_fence_after();
                         const uint32_t sa = s_u32(base + stage * KT_STAGE_BYTES);
                         const uint64_t adesc = make_sw128_desc(sa), bdesc = make_sw128_desc(sa + TC_A_BYTES);
+                        if (tc_elect_one()) {
 #pragma unroll
-                        for (int kk = 0; kk < TC_BK / 8; ++kk) {
-                            umma_tf32(d_tmem, adesc + (uint64_t)(2 * kk), bdesc + (uint64_t)(2 * kk), idesc, accum);
-                            accum = 1;
+                            for (int kk = 0; kk < TC_BK / 8; ++kk)
+                                umma_tf32(d_tmem, adesc + (uint64_t)(2 * kk), bdesc + (uint64_t)(2 * kk), idesc, kk ? 1u : accum);
+                            umma_commit(empty + stage);
                         }
-                        umma_commit(empty + stage);
+                        __syncwarp();
+                        accum = 1;
                         if (++stage == KT_STAGES) { stage = 0; phase ^= 1; }
                     }
-                    umma_commit(tmem_full + acc);
+                    if (tc_elect_one()) umma_commit(tmem_full + acc);
+                    __syncwarp();
                 }
             }
         }
