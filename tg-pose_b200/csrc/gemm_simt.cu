@@ -324,6 +324,39 @@ __global__ void gemm_naive_kernel(const __grid_constant__ GemmDev P, long total)
     epilogue_store(g, m, n, acc);
 }
 
+// tiny-N contraction with K-contiguous weight rows (N <= 8, e.g. the recon head's 128 -> 3): a warp per row, lanes
+// split K with 128-bit loads of the row (read once, coalesced) and of the <= 8 weight rows (L1-resident), then one
+// warp reduction per output.
+__global__ void __launch_bounds__(256)
+gemm_smalln_kernel(const __grid_constant__ GemmDev P) {
+    const tgp_gemm_args& g = P.a;
+    const int lane = threadIdx.x & 31;
+    const long m = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (m >= g.M) return;
+    const bool vecA = (g.lda % 4 == 0) && ((uintptr_t)g.A % 16 == 0);
+    const bool vecB = (g.ldb % 4 == 0) && ((uintptr_t)g.Bmat % 16 == 0);
+    float acc[8];
+#pragma unroll
+    for (int n = 0; n < 8; ++n) acc[n] = 0.f;
+    for (int k0 = lane * 4; k0 < g.K; k0 += 128) {
+        const float4 a = ld4_guard(g.A, m, g.M, g.lda, k0, g.K, vecA);
+#pragma unroll
+        for (int n = 0; n < 8; ++n) {
+            if (n < g.Ncols) {
+                const float4 w = ld4_guard(g.Bmat, n, g.Ncols, g.ldb, k0, g.K, vecB);
+                acc[n] = fmaf(a.x, w.x, fmaf(a.y, w.y, fmaf(a.z, w.z, fmaf(a.w, w.w, acc[n]))));
+            }
+        }
+    }
+#pragma unroll
+    for (int n = 0; n < 8; ++n) {
+        if (n < g.Ncols) {
+            const float v = warp_sum(acc[n]);
+            if (lane == n) epilogue_store(g, m, n, v);
+        }
+    }
+}
+
 __global__ void decode_max_kernel(const int* __restrict__ enc, long n, float* __restrict__ out) {
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) {
@@ -384,6 +417,10 @@ int tgp_gemm_simt(const tgp_gemm_args* a, cudaStream_t st) {
         }
         gemm_skinny_kernel<<<grid, 256, 0, st>>>(P);
         return check_launch("gemm_skinny_kernel");
+    }
+    if (a->Ncols <= 8 && a->b_is_nk && a->K >= 32) {
+        gemm_smalln_kernel<<<(unsigned)((a->M + 7) / 8), 256, 0, st>>>(P);
+        return check_launch("gemm_smalln_kernel");
     }
     if (a->K <= 8 || a->Ncols <= 8) {
         const long total = a->M * a->Ncols;
