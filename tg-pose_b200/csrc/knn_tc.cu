@@ -236,7 +236,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
 // ~7x fewer selection instructions than the insertion lists of knn_tc_kernel at 2x its (cheap) tensor work; no distance
 // tile in shared memory.  A query with more than KT2_CAP survivors (massive ties) or fewer than K (non-finite input)
 // sends its unit to the fix-up list, which knn_tc_kernel redoes right behind this launch.
-constexpr int KT2_CAP = 64;                              // survivor buffer entries per query
+constexpr int KT2_CAP = 80;                              // survivor buffer entries per query (41 +- 4 expected at K = 31)
 constexpr int KT2_GM_LD = 65;                            // pitch of the group-minimum rows (bank-conflict free)
 
 // ATM (D <= 128): the unit's query tile [tf32 | residual] is written ONCE into the 256 tensor-memory columns the
@@ -525,11 +525,11 @@ knn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                 if (n < K || n > KT2_CAP) { bad = true; continue; }
                 uint2* qbuf = buf + ql * KT2_CAP;
 #pragma unroll
-                for (int s = 0; s < KT2_CAP / 32; ++s)
+                for (int s = 0; s < (KT2_CAP + 31) / 32; ++s)
                     if (s * 32 + lane < n) qbuf[s * 32 + lane].x = ordered_key(__uint_as_float(qbuf[s * 32 + lane].x));
                 __syncwarp();
                 const size_t o = ((size_t)b * N + q0 + ql) * k;
-                warp_rank_store<KT2_CAP / 32>(qbuf, n, k, lane, idx64 ? idx64 + o : nullptr, idx32 ? idx32 + o : nullptr);
+                warp_rank_store<(KT2_CAP + 31) / 32>(qbuf, n, k, lane, idx64 ? idx64 + o : nullptr, idx32 ? idx32 + o : nullptr);
             }
             if (bad && lane == 0) atomicOr(unit_flag, 1);
             epi_bar_sync();
