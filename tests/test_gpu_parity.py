@@ -119,6 +119,31 @@ def test_knn_feat_vs_oracle(ops, B, N, D, k):
     assert (srt[..., 1:] != srt[..., :-1]).all()
 
 
+@pytest.mark.parametrize("B,N,D,k", [(3, 1028, 128, 20), (2, 300, 256, 20), (2, 64, 256, 8)])
+def test_knn_feat_duplicate_rows_take_the_fixup_path(ops, B, N, D, k):
+    """More identical feature rows than the survivor buffer holds (zero-padded / dropped-out clouds): the threshold-selection
+    kernel hands those units to the insertion-list fix-up.  Distances between duplicates are exact ties (bit-equal inner
+    products), so the expected neighbours of a duplicated row are the lowest-index duplicates."""
+    g = torch.Generator().manual_seed(N + D + k)
+    x = torch.randn(B, N, D, generator=g) * 0.5
+    ndup = min(N // 2, 150)
+    x[:, N - ndup:] = x[:, :1]                                  # rows N-ndup.. equal row 0
+    mine = nump(ops.knn_feat(x.cuda(), k)[0])
+    ref, dist = orc.knn_feat(x.numpy(), k, return_dist=True)
+    q = (x.numpy().astype(np.float64) ** 2).sum(-1)
+    any_, set_, viol = knn_feat_mismatch(mine, ref, dist, D, q)
+    assert viol == 0
+    assert mine.min() >= 0 and mine.max() < N
+    srt = np.sort(mine, axis=2)
+    assert (srt[..., 1:] != srt[..., :-1]).all()
+    # a duplicated row: rank 0 is dropped positionally, the k reported neighbours are the next lowest-index duplicates
+    dups = np.concatenate([[0], np.arange(N - ndup, N)])
+    for b in range(B):
+        got = mine[b, N - 1]
+        assert set(got.tolist()) <= set(dups.tolist()), got
+        assert (np.diff(got) > 0).all()                         # ties in ascending index order
+
+
 @pytest.mark.parametrize("tag", list("abcd"))
 def test_nearest_golden(ops, tag):
     g = golden("nearest")
