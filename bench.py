@@ -61,7 +61,40 @@ class ClockSampler:
         self.proc = None
         self.gpu = gpu_index
 
+    def _nvml_loop(self, handle, nv):
+        bits = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        mx = nv.nvmlDeviceGetMaxClockInfo(handle, nv.NVML_CLOCK_SM)
+        while not self._stop.is_set():
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(handle, nv.NVML_CLOCK_SM)
+                rs = int(get_reasons(handle))
+                self.nvml_rows.append((float(sm), float(mx), [n for n, b in bits.items() if rs & b]))
+            except Exception:
+                break
+            time.sleep(0.004)
+
     def start(self):
+        # in-process NVML polling every ~4 ms (a step lasts ~3 ms, a default run well under a second: nvidia-smi's
+        # 100 ms loop would deliver one or two samples); nvidia-smi -lms stays as the fallback
+        self._stop = threading.Event()
+        self.nvml_rows = []
+        try:
+            import pynvml as nv
+            import torch
+            nv.nvmlInit()
+            try:
+                uuid = "GPU-" + str(torch.cuda.get_device_properties(self.gpu).uuid)
+                handle = nv.nvmlDeviceGetHandleByUUID(uuid.encode() if hasattr(uuid, "encode") else uuid)
+            except Exception:
+                handle = nv.nvmlDeviceGetHandleByIndex(self.gpu)
+            nv.nvmlDeviceGetClockInfo(handle, nv.NVML_CLOCK_SM)
+            threading.Thread(target=self._nvml_loop, args=(handle, nv), daemon=True).start()
+            self.proc = None
+            self.nvml = True
+            return
+        except Exception:
+            self.nvml = False
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.FIELDS}",
                                           "--format=csv,noheader,nounits", "-lms", "100"],
@@ -75,6 +108,16 @@ class ClockSampler:
             self.rows.append(line.strip())
 
     def stop(self):
+        if getattr(self, "nvml", False):
+            self._stop.set()
+            time.sleep(0.01)
+            rows = list(self.nvml_rows)
+            if not rows:
+                return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+            sm = sorted(r[0] for r in rows)
+            reasons = sorted({n for r in rows for n in r[2]})
+            return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(r[1] for r in rows), "reasons": reasons,
+                    "samples": len(sm), "source": "NVML, 4 ms period, during the timed and end-to-end loops"}
         if self.proc is not None:
             self.proc.terminate()
             try:
