@@ -103,7 +103,8 @@ def test_knn_feat_golden(ops, tag, D):
 
 
 @pytest.mark.parametrize("B,N,D,k", [(4, 1028, 128, 20), (4, 257, 256, 20), (8, 64, 256, 8), (2, 130, 20, 5), (1, 4500, 64, 30),
-                                     (1, 300, 64, 40), (2, 257, 128, 20)])
+                                     (1, 300, 64, 40), (2, 257, 128, 20), (3, 100, 128, 10), (2, 64, 64, 8), (5, 200, 128, 31),
+                                     (40, 257, 64, 20)])
 def test_knn_feat_vs_oracle(ops, B, N, D, k):
     g = torch.Generator().manual_seed(N + D)
     x = torch.randn(B, N, D, generator=g) * 0.5
