@@ -369,6 +369,124 @@ __global__ void affine_act_kernel(const float* __restrict__ z, long ld_z, const 
     }
 }
 
+// 128-bit column reductions (C % 4 == 0, 16-byte aligned rows): a lane owns 4 consecutive columns, a CTA a 128-column
+// chunk; 4 independent 512-byte row segments in flight per warp.  MODE 0: sum x; 1: sum (x - mu)^2; 2: the two sums of the
+// BatchNorm backward (g, g * zhat).  Same partial layout / fixed-order finalize as the scalar kernels.
+template <int MODE>
+__global__ void __launch_bounds__(CS_THREADS)
+colred_vec_kernel(const float* __restrict__ x, long ld, long rows_per_group, int C, const float* __restrict__ mu,
+                  const float* __restrict__ y, long ld_y, const float* __restrict__ z, long ld_z,
+                  const float* __restrict__ invstd, float slope, float* __restrict__ partial) {
+    __shared__ __align__(16) float part[MODE == 2 ? 2 : 1][CS_THREADS / 32][128];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int c = (blockIdx.x * 32 + lane) * 4;
+    const long grp = blockIdx.y;
+    const int nsplit = gridDim.z, sp = blockIdx.z;
+    const long per = (rows_per_group + nsplit - 1) / nsplit;
+    const long r_beg = grp * rows_per_group + sp * per;
+    const long r_end = min((grp + 1) * rows_per_group, r_beg + per);
+    float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
+    constexpr int NW = CS_THREADS / 32;
+    if (c < C) {
+        float4 m = a0, is = a0;
+        if (MODE >= 1) m = __ldg(reinterpret_cast<const float4*>(mu + c));
+        if (MODE == 2) is = __ldg(reinterpret_cast<const float4*>(invstd + c));
+        auto body = [&](long r) {
+            float4 v = __ldg(reinterpret_cast<const float4*>(x + r * ld + c));
+            if (MODE == 0) { a0.x += v.x; a0.y += v.y; a0.z += v.z; a0.w += v.w; }
+            else if (MODE == 1) {
+                v.x -= m.x; v.y -= m.y; v.z -= m.z; v.w -= m.w;
+                a0.x = fmaf(v.x, v.x, a0.x); a0.y = fmaf(v.y, v.y, a0.y); a0.z = fmaf(v.z, v.z, a0.z); a0.w = fmaf(v.w, v.w, a0.w);
+            } else {
+                const float4 yy = __ldg(reinterpret_cast<const float4*>(y + r * ld_y + c));
+                const float4 zz = __ldg(reinterpret_cast<const float4*>(z + r * ld_z + c));
+                if (!(yy.x > 0.f)) v.x *= slope;
+                if (!(yy.y > 0.f)) v.y *= slope;
+                if (!(yy.z > 0.f)) v.z *= slope;
+                if (!(yy.w > 0.f)) v.w *= slope;
+                a0.x += v.x; a0.y += v.y; a0.z += v.z; a0.w += v.w;
+                a1.x = fmaf(v.x, (zz.x - m.x) * is.x, a1.x); a1.y = fmaf(v.y, (zz.y - m.y) * is.y, a1.y);
+                a1.z = fmaf(v.z, (zz.z - m.z) * is.z, a1.z); a1.w = fmaf(v.w, (zz.w - m.w) * is.w, a1.w);
+            }
+        };
+        long r = r_beg + warp;
+        for (; r + 3 * NW < r_end; r += 4 * NW) { body(r); body(r + NW); body(r + 2 * NW); body(r + 3 * NW); }
+        for (; r < r_end; r += NW) body(r);
+    }
+    *reinterpret_cast<float4*>(&part[0][warp][lane * 4]) = a0;
+    if (MODE == 2) *reinterpret_cast<float4*>(&part[MODE == 2 ? 1 : 0][warp][lane * 4]) = a1;
+    __syncthreads();
+    for (int i = threadIdx.x; i < (MODE == 2 ? 256 : 128); i += CS_THREADS) {
+        const int which = i >> 7, cc = blockIdx.x * 128 + (i & 127);
+        if (cc < C) {
+            float s = 0.f;
+#pragma unroll
+            for (int w = 0; w < NW; ++w) s += part[which][w][i & 127];
+            if (MODE == 2) partial[((long)sp * 2 + which) * C + cc] = s;
+            else partial[(grp * nsplit + sp) * C + cc] = s;
+        }
+    }
+}
+
+// 128-bit variants of the two element-wise passes above / below (C % 4 == 0, 16-byte aligned rows): CTA-strided rows,
+// a thread owns 4 consecutive channels, no 64-bit division per element, packed operand stores.
+__global__ void __launch_bounds__(256)
+affine_act_vec_kernel(const float* __restrict__ z, long ld_z, const float* __restrict__ scale, const float* __restrict__ shift,
+                      float slope, long M, int C, float* __restrict__ out, long ld_out, float* __restrict__ out_split, int kp,
+                      int mixed) {
+    for (int c = threadIdx.x * 4; c < C; c += blockDim.x * 4) {
+        const float4 sc = __ldg(reinterpret_cast<const float4*>(scale + c)), sh = __ldg(reinterpret_cast<const float4*>(shift + c));
+        for (long r = blockIdx.x; r < M; r += gridDim.x) {
+            float4 v = __ldg(reinterpret_cast<const float4*>(z + r * ld_z + c));
+            v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y); v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
+            v.x = v.x > 0.f ? v.x : v.x * slope; v.y = v.y > 0.f ? v.y : v.y * slope;
+            v.z = v.z > 0.f ? v.z : v.z * slope; v.w = v.w > 0.f ? v.w : v.w * slope;
+            if (out) *reinterpret_cast<float4*>(out + r * ld_out + c) = v;
+            if (out_split && mixed) {
+                mixed_store4(reinterpret_cast<uint16_t*>(out_split + r * 2 * kp), kp, c, v);
+            } else if (out_split) {
+                float4 hi;
+                uint32_t hb;
+                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v.x)); hi.x = __uint_as_float(hb);
+                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v.y)); hi.y = __uint_as_float(hb);
+                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v.z)); hi.z = __uint_as_float(hb);
+                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v.w)); hi.w = __uint_as_float(hb);
+                float* q = out_split + r * 2 * kp + c;
+                *reinterpret_cast<float4*>(q) = hi;
+                *reinterpret_cast<float4*>(q + kp) = make_float4(v.x - hi.x, v.y - hi.y, v.z - hi.z, v.w - hi.w);
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_vec_kernel(const float* __restrict__ dy, long ld_dy, const float* __restrict__ y, long ld_y,
+                        const float* __restrict__ z, long ld_z, const float* __restrict__ mean,
+                        const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ dbeta,
+                        const float* __restrict__ dgamma, float slope, long M, int C, float* __restrict__ dz, long ld_dz) {
+    const float inv_m = 1.0f / (float)M;
+    for (int c = threadIdx.x * 4; c < C; c += blockDim.x * 4) {
+        const float4 mu = __ldg(reinterpret_cast<const float4*>(mean + c)), is = __ldg(reinterpret_cast<const float4*>(invstd + c));
+        const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma + c));
+        const float4 db = __ldg(reinterpret_cast<const float4*>(dbeta + c)), dg = __ldg(reinterpret_cast<const float4*>(dgamma + c));
+        for (long r = blockIdx.x; r < M; r += gridDim.x) {
+            float4 g = __ldg(reinterpret_cast<const float4*>(dy + r * ld_dy + c));
+            const float4 yy = __ldg(reinterpret_cast<const float4*>(y + r * ld_y + c));
+            const float4 zz = __ldg(reinterpret_cast<const float4*>(z + r * ld_z + c));
+            if (!(yy.x > 0.f)) g.x *= slope;
+            if (!(yy.y > 0.f)) g.y *= slope;
+            if (!(yy.z > 0.f)) g.z *= slope;
+            if (!(yy.w > 0.f)) g.w *= slope;
+            float4 o;
+            o.x = ga.x * is.x * (g.x - db.x * inv_m - (zz.x - mu.x) * is.x * dg.x * inv_m);
+            o.y = ga.y * is.y * (g.y - db.y * inv_m - (zz.y - mu.y) * is.y * dg.y * inv_m);
+            o.z = ga.z * is.z * (g.z - db.z * inv_m - (zz.z - mu.z) * is.z * dg.z * inv_m);
+            o.w = ga.w * is.w * (g.w - db.w * inv_m - (zz.w - mu.w) * is.w * dg.w * inv_m);
+            *reinterpret_cast<float4*>(dz + r * ld_dz + c) = o;
+        }
+    }
+}
+
 // partial[sp][0][c] = sum g, partial[sp][1][c] = sum g * zhat over this split's rows
 __global__ void __launch_bounds__(CS_THREADS)
 bn_bwd_reduce_kernel(const float* __restrict__ dy, long ld_dy, const float* __restrict__ y, long ld_y,
@@ -450,7 +568,7 @@ extern "C" int tgp_act_bwd(const float* grad, long ld_grad, const float* y, long
 
 static int colsum_nsplit(long rows_per_group, long groups, int C) {
     // enough CTAs to fill the machine, at least 64 rows each; depends on the shape only (deterministic)
-    const long chunks = (C + 31) / 32;
+    const long chunks = C % 4 == 0 ? (C + 127) / 128 : (C + 31) / 32;     // CTAs per split (128-bit kernels own 128 columns)
     long want = ((long)TGP_NUM_SMS * 4 + chunks * groups - 1) / (chunks * groups);
     long cap = (rows_per_group + 63) / 64;
     long s = want < cap ? want : cap;
@@ -473,8 +591,16 @@ extern "C" int tgp_colsum(const float* x, long ld, long M, int C, long rows_per_
     const int nsplit = colsum_nsplit(rows_per_group, groups, C);
     cudaStream_t st = as_stream(stream);
     dim3 grid((C + 31) / 32, (unsigned)groups, nsplit);
-    colsum_partial_kernel<<<grid, CS_THREADS, 0, st>>>(x, ld, rows_per_group, C, static_cast<float*>(workspace));
-    int rc = check_launch("colsum_partial_kernel");
+    int rc;
+    if (C % 4 == 0 && ld % 4 == 0 && ((uintptr_t)x & 15) == 0) {
+        grid.x = (C + 127) / 128;
+        colred_vec_kernel<0><<<grid, CS_THREADS, 0, st>>>(x, ld, rows_per_group, C, nullptr, nullptr, 0, nullptr, 0, nullptr, 0.f,
+                                                         static_cast<float*>(workspace));
+        rc = check_launch("colred_vec_kernel<0>");
+    } else {
+        colsum_partial_kernel<<<grid, CS_THREADS, 0, st>>>(x, ld, rows_per_group, C, static_cast<float*>(workspace));
+        rc = check_launch("colsum_partial_kernel");
+    }
     if (rc) return rc;
     const long total = groups * C;
     colsum_finalize_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(static_cast<const float*>(workspace), nsplit, C, total, out);
@@ -602,7 +728,7 @@ extern "C" int tgp_gemm_tn(const float* A, long lda, const float* Bm, long ldb, 
 }
 
 static int rowsplit(long M, int C, int per_row_min) {
-    const long chunks = (C + 31) / 32;
+    const long chunks = C % 4 == 0 ? (C + 127) / 128 : (C + 31) / 32;
     long want = ((long)TGP_NUM_SMS * 4 + chunks - 1) / chunks;
     long cap = (M + per_row_min - 1) / per_row_min;
     long s = want < cap ? want : cap;
@@ -619,8 +745,15 @@ extern "C" int tgp_colsumsq_dev(const float* x, long ld, long M, int C, const fl
     const int nsplit = rowsplit(M, C, 64);
     cudaStream_t st = as_stream(stream);
     dim3 grid((C + 31) / 32, 1, nsplit);
-    colsumsq_partial_kernel<<<grid, CS_THREADS, 0, st>>>(x, ld, M, C, mu, static_cast<float*>(workspace));
-    int rc = check_launch("colsumsq_partial_kernel");
+    int rc;
+    if (C % 4 == 0 && ld % 4 == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)mu & 15) == 0) {
+        grid.x = (C + 127) / 128;
+        colred_vec_kernel<1><<<grid, CS_THREADS, 0, st>>>(x, ld, M, C, mu, nullptr, 0, nullptr, 0, nullptr, 0.f, static_cast<float*>(workspace));
+        rc = check_launch("colred_vec_kernel<1>");
+    } else {
+        colsumsq_partial_kernel<<<grid, CS_THREADS, 0, st>>>(x, ld, M, C, mu, static_cast<float*>(workspace));
+        rc = check_launch("colsumsq_partial_kernel");
+    }
     if (rc) return rc;
     colsum_finalize_kernel<<<(unsigned)((C + 255) / 256), 256, 0, st>>>(static_cast<const float*>(workspace), nsplit, C, C, out);
     return check_launch("colsum_finalize_kernel");
@@ -630,6 +763,14 @@ extern "C" int tgp_affine_act(const float* z, long ld_z, const float* scale, con
                               int C, float* out, long ld_out, float* out_split, int Kp, int mixed, tgp_stream_t stream) {
     if (!z || !scale || !shift || (!out && !out_split)) return fail(TGP_EINVAL, "tgp_affine_act: null pointer");
     if (M <= 0 || C <= 0 || (out_split && Kp < C) || (out_split && mixed && Kp % 64)) return fail(TGP_EINVAL, "tgp_affine_act: bad sizes");
+    auto al16 = [](const void* q) { return ((uintptr_t)q & 15) == 0; };
+    if (C % 4 == 0 && ld_z % 4 == 0 && al16(z) && al16(scale) && al16(shift) && (!out || (ld_out % 4 == 0 && al16(out))) &&
+        (!out_split || (al16(out_split) && Kp % 4 == 0))) {
+        const long nb = M < (long)TGP_NUM_SMS * 16 ? M : (long)TGP_NUM_SMS * 16;
+        affine_act_vec_kernel<<<(unsigned)nb, C >= 1024 ? 256 : (C >= 256 ? 64 : 32), 0, as_stream(stream)>>>(
+            z, ld_z, scale, shift, slope, M, C, out, ld_out, out_split, Kp, mixed);
+        return check_launch("affine_act_vec_kernel");
+    }
     affine_act_kernel<<<grid_for(M * C, 256), 256, 0, as_stream(stream)>>>(z, ld_z, scale, shift, slope, M, C, out, ld_out, out_split, Kp, mixed);
     return check_launch("affine_act_kernel");
 }
@@ -646,12 +787,28 @@ extern "C" int tgp_bn_bwd(const float* dy, long ld_dy, const float* y, long ld_y
     cudaStream_t st = as_stream(stream);
     dim3 grid((C + 31) / 32, 1, nsplit);
     float* part = static_cast<float*>(workspace);
-    bn_bwd_reduce_kernel<<<grid, CS_THREADS, 0, st>>>(dy, ld_dy, y, ld_y, z, ld_z, mean, invstd, slope, M, C, part);
-    int rc = check_launch("bn_bwd_reduce_kernel");
+    int rc;
+    auto a16 = [](const void* q) { return ((uintptr_t)q & 15) == 0; };
+    if (C % 4 == 0 && ld_dy % 4 == 0 && ld_y % 4 == 0 && ld_z % 4 == 0 && a16(dy) && a16(y) && a16(z) && a16(mean) && a16(invstd)) {
+        grid.x = (C + 127) / 128;
+        colred_vec_kernel<2><<<grid, CS_THREADS, 0, st>>>(dy, ld_dy, M, C, mean, y, ld_y, z, ld_z, invstd, slope, part);
+        rc = check_launch("colred_vec_kernel<2>");
+    } else {
+        bn_bwd_reduce_kernel<<<grid, CS_THREADS, 0, st>>>(dy, ld_dy, y, ld_y, z, ld_z, mean, invstd, slope, M, C, part);
+        rc = check_launch("bn_bwd_reduce_kernel");
+    }
     if (rc) return rc;
     bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(part, nsplit, C, dbeta, dgamma);
     rc = check_launch("bn_bwd_finalize_kernel");
     if (rc) return rc;
+    auto al16 = [](const void* q) { return ((uintptr_t)q & 15) == 0; };
+    if (C % 4 == 0 && ld_dy % 4 == 0 && ld_y % 4 == 0 && ld_z % 4 == 0 && ld_dz % 4 == 0 && al16(dy) && al16(y) && al16(z) &&
+        al16(dz) && al16(mean) && al16(invstd) && al16(gamma) && al16(dbeta) && al16(dgamma)) {
+        const long nb = M < (long)TGP_NUM_SMS * 16 ? M : (long)TGP_NUM_SMS * 16;
+        bn_bwd_apply_vec_kernel<<<(unsigned)nb, C >= 1024 ? 256 : (C >= 256 ? 64 : 32), 0, st>>>(
+            dy, ld_dy, y, ld_y, z, ld_z, mean, invstd, gamma, dbeta, dgamma, slope, M, C, dz, ld_dz);
+        return check_launch("bn_bwd_apply_vec_kernel");
+    }
     bn_bwd_apply_kernel<<<grid_for(M * C, 256), 256, 0, st>>>(dy, ld_dy, y, ld_y, z, ld_z, mean, invstd, gamma, dbeta, dgamma, slope, M, C, dz, ld_dz);
     return check_launch("bn_bwd_apply_kernel");
 }
