@@ -311,10 +311,11 @@ int tgp_affine_act(const float* z, long ld_z, const float* scale, const float* s
                    float* out, long ld_out, float* out_split, int Kp, int mixed, tgp_stream_t stream);
 
 /* backward of y = act(BN_train(z)): dbeta[c] = sum g, dgamma[c] = sum g * zhat, g = dy * act'(y),
- * dz = gamma * invstd * (g - dbeta / M - zhat * dgamma / M).  workspace: tgp_bn_workspace(M, C). */
+ * dz = gamma * invstd * (g - dbeta / M - zhat * dgamma / M).  workspace: tgp_bn_workspace(M, C).
+ * dz_mixed (optional): dz also written as the MIXED operand (M, 8*tgp_mixed_kpad(C) bytes) of the dx contraction. */
 int tgp_bn_bwd(const float* dy, long ld_dy, const float* y, long ld_y, const float* z, long ld_z,
                const float* mean, const float* invstd, const float* gamma, float slope, long M, int C,
-               float* dz, long ld_dz, float* dbeta, float* dgamma,
+               float* dz, long ld_dz, float* dz_mixed, float* dbeta, float* dgamma,
                void* workspace, size_t workspace_bytes, tgp_stream_t stream);
 
 #ifdef __cplusplus

@@ -463,8 +463,13 @@ __global__ void __launch_bounds__(256)
 bn_bwd_apply_vec_kernel(const float* __restrict__ dy, long ld_dy, const float* __restrict__ y, long ld_y,
                         const float* __restrict__ z, long ld_z, const float* __restrict__ mean,
                         const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ dbeta,
-                        const float* __restrict__ dgamma, float slope, long M, int C, float* __restrict__ dz, long ld_dz) {
+                        const float* __restrict__ dgamma, float slope, long M, int C, float* __restrict__ dz, long ld_dz,
+                        float* __restrict__ dz_mixed, int kp) {
     const float inv_m = 1.0f / (float)M;
+    if (dz_mixed)      // zero padding of the operand columns past C (Kp = ceil64(C))
+        for (long r = blockIdx.x; r < M; r += gridDim.x)
+            for (int c = C + threadIdx.x * 4; c < kp; c += blockDim.x * 4)
+                mixed_store4(reinterpret_cast<uint16_t*>(dz_mixed + r * 2 * kp), kp, c, make_float4(0.f, 0.f, 0.f, 0.f));
     for (int c = threadIdx.x * 4; c < C; c += blockDim.x * 4) {
         const float4 mu = __ldg(reinterpret_cast<const float4*>(mean + c)), is = __ldg(reinterpret_cast<const float4*>(invstd + c));
         const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma + c));
@@ -483,6 +488,7 @@ bn_bwd_apply_vec_kernel(const float* __restrict__ dy, long ld_dy, const float* _
             o.z = ga.z * is.z * (g.z - db.z * inv_m - (zz.z - mu.z) * is.z * dg.z * inv_m);
             o.w = ga.w * is.w * (g.w - db.w * inv_m - (zz.w - mu.w) * is.w * dg.w * inv_m);
             *reinterpret_cast<float4*>(dz + r * ld_dz + c) = o;
+            if (dz_mixed) mixed_store4(reinterpret_cast<uint16_t*>(dz_mixed + r * 2 * kp), kp, c, o);
         }
     }
 }
@@ -777,8 +783,8 @@ extern "C" int tgp_affine_act(const float* z, long ld_z, const float* scale, con
 
 extern "C" int tgp_bn_bwd(const float* dy, long ld_dy, const float* y, long ld_y, const float* z, long ld_z,
                           const float* mean, const float* invstd, const float* gamma, float slope, long M, int C,
-                          float* dz, long ld_dz, float* dbeta, float* dgamma, void* workspace, size_t workspace_bytes,
-                          tgp_stream_t stream) {
+                          float* dz, long ld_dz, float* dz_mixed, float* dbeta, float* dgamma, void* workspace,
+                          size_t workspace_bytes, tgp_stream_t stream) {
     if (!dy || !y || !z || !mean || !invstd || !gamma || !dz || !dbeta || !dgamma || !workspace)
         return fail(TGP_EINVAL, "tgp_bn_bwd: null pointer");
     if (M <= 0 || C <= 0) return fail(TGP_EINVAL, "tgp_bn_bwd: sizes must be positive");
@@ -805,10 +811,13 @@ extern "C" int tgp_bn_bwd(const float* dy, long ld_dy, const float* y, long ld_y
     if (C % 4 == 0 && ld_dy % 4 == 0 && ld_y % 4 == 0 && ld_z % 4 == 0 && ld_dz % 4 == 0 && al16(dy) && al16(y) && al16(z) &&
         al16(dz) && al16(mean) && al16(invstd) && al16(gamma) && al16(dbeta) && al16(dgamma)) {
         const long nb = M < (long)TGP_NUM_SMS * 16 ? M : (long)TGP_NUM_SMS * 16;
+        if (dz_mixed && !al16(dz_mixed)) return fail(TGP_EINVAL, "tgp_bn_bwd: dz_mixed must be 16-byte aligned");
         bn_bwd_apply_vec_kernel<<<(unsigned)nb, C >= 1024 ? 256 : (C >= 256 ? 64 : 32), 0, st>>>(
-            dy, ld_dy, y, ld_y, z, ld_z, mean, invstd, gamma, dbeta, dgamma, slope, M, C, dz, ld_dz);
+            dy, ld_dy, y, ld_y, z, ld_z, mean, invstd, gamma, dbeta, dgamma, slope, M, C, dz, ld_dz, dz_mixed,
+            tgp_mixed_kpad(C));
         return check_launch("bn_bwd_apply_vec_kernel");
     }
+    if (dz_mixed) return fail(TGP_EINVAL, "tgp_bn_bwd: dz_mixed needs C % 4 == 0 and 16-byte aligned operands");
     bn_bwd_apply_kernel<<<grid_for(M * C, 256), 256, 0, st>>>(dy, ld_dy, y, ld_y, z, ld_z, mean, invstd, gamma, dbeta, dgamma, slope, M, C, dz, ld_dz);
     return check_launch("bn_bwd_apply_kernel");
 }

@@ -45,14 +45,14 @@ class _ConvBNActFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dy, _ds, _dm, _dv):
         x2d, w2, z, y, mean, invstd, gamma = ctx.saved_tensors
-        dz, dbeta, dgamma = ops.bn_bwd(dy, y, z, mean, invstd, gamma, ctx.slope)
+        dz, dbeta, dgamma, dzm = ops.bn_bwd(dy, y, z, mean, invstd, gamma, ctx.slope, want_mixed=ctx.needs_input_grad[0])
         dw = ops.gemm_tn(dz, x2d, mixed=True).view(ctx.wshape)
         db = ops.colsum(dz).view(-1) if ctx.has_bias else None
         dx = None
         if ctx.needs_input_grad[0]:
             cout, cin = w2.shape
             dx = torch.empty((dz.shape[0], cin), dtype=torch.float32, device=dz.device)
-            ops.gemm(None, w2, False, [(0, cin, dx, 0, 0)], K=cout, Ncols=cin, A_split=ops.split_mixed(dz),
+            ops.gemm(None, w2, False, [(0, cin, dx, 0, 0)], K=cout, Ncols=cin, A_split=dzm if dzm is not None else ops.split_mixed(dz),
                      B_split=ops.split_mixed(w2.t().contiguous()), mixed=True)
         return dx, dw, db, dgamma, dbeta, None, None, None, None
 

@@ -572,8 +572,9 @@ def affine_act(z2d, scale, shift, slope, want_raw=True, want_split=False, mixed=
     return raw, spl
 
 
-def bn_bwd(dy2d, y2d, z2d, mean, invstd, gamma, slope):
-    """-> (dz (M,C), dbeta (C,), dgamma (C,)) of y = act(BN_train(z))."""
+def bn_bwd(dy2d, y2d, z2d, mean, invstd, gamma, slope, want_mixed=False):
+    """-> (dz (M,C), dbeta (C,), dgamma (C,)) of y = act(BN_train(z)); with want_mixed also dz as the mixed operand of
+    the dx contraction (4th result; None when the shape does not take the 128-bit kernel)."""
     M, C = z2d.shape
     dy2d = dy2d if dy2d.stride(1) == 1 else dy2d.contiguous()
     lib = _lib.load()
@@ -582,6 +583,11 @@ def bn_bwd(dy2d, y2d, z2d, mean, invstd, gamma, slope):
     dz = torch.empty((M, C), dtype=torch.float32, device=z2d.device)
     dbeta = torch.empty(C, dtype=torch.float32, device=z2d.device)
     dgamma = torch.empty(C, dtype=torch.float32, device=z2d.device)
+    dzm = None
+    if want_mixed and C % 4 == 0 and all(t.stride(0) % 4 == 0 and t.data_ptr() % 16 == 0 for t in (dy2d, y2d, z2d)):
+        dzm = mixed_buf(M, C, z2d.device)
     _run("bn_bwd", lib.tgp_bn_bwd, _p(dy2d), dy2d.stride(0), _p(y2d), y2d.stride(0), _p(z2d), z2d.stride(0), _p(mean),
-         _p(invstd), _p(gamma), float(slope), M, C, _p(dz), C, _p(dbeta), _p(dgamma), _p(ws), nb, _stream())
+         _p(invstd), _p(gamma), float(slope), M, C, _p(dz), C, _p(dzm), _p(dbeta), _p(dgamma), _p(ws), nb, _stream())
+    if want_mixed:
+        return dz, dbeta, dgamma, dzm
     return dz, dbeta, dgamma
