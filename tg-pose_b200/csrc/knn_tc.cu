@@ -16,6 +16,7 @@
 // Padding: rows of a tile that belong to the next cloud / lie past the end are masked through q_j = +inf.
 #include "knn_select.cuh"
 #include "tc_common.cuh"
+#include <stdlib.h>
 
 namespace tgp {
 
@@ -239,6 +240,51 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
 constexpr int KT2_CAP = 80;                              // survivor buffer entries per query (41 +- 4 expected at K = 31)
 constexpr int KT2_GM_LD = 65;                            // pitch of the group-minimum rows (bank-conflict free)
 
+// 32 accumulator columns of one query row -> distances -> pass 0: group minima (groups of GS consecutive candidates, slot =
+// group % 64, exclusive to this thread); pass 1: survivors (d <= T) appended with one predicated shared-memory atomic each
+template <int GS>
+__device__ __forceinline__ void kt2_consume(const uint32_t (&r)[32], const float* wqs, float qi, int pass, int c0, float* gmr,
+                                            float T, uint32_t cnt_addr, uint32_t buf_row) {
+    const float4* qj4 = reinterpret_cast<const float4*>(wqs);
+#pragma unroll
+    for (int h = 0; h < 32; h += 16) {                    // 16 columns at a time: bounded register pressure
+        float d[16];
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) {
+            const float4 qj = qj4[(h + j) >> 2];
+            d[j] = __fadd_rn(__fadd_rn(__fmul_rn(__uint_as_float(r[h + j]), -2.0f), qj.x), qi);
+            d[j + 1] = __fadd_rn(__fadd_rn(__fmul_rn(__uint_as_float(r[h + j + 1]), -2.0f), qj.y), qi);
+            d[j + 2] = __fadd_rn(__fadd_rn(__fmul_rn(__uint_as_float(r[h + j + 2]), -2.0f), qj.z), qi);
+            d[j + 3] = __fadd_rn(__fadd_rn(__fmul_rn(__uint_as_float(r[h + j + 3]), -2.0f), qj.w), qi);
+        }
+        if (pass == 0) {
+#pragma unroll
+            for (int w = 1; w < GS; w <<= 1)
+#pragma unroll
+                for (int j = 0; j < 16; j += 2 * w) d[j] = fminf(d[j], d[j + w]);
+            const int g0 = (c0 + h) / GS;
+#pragma unroll
+            for (int g = 0; g < 16 / GS; ++g) {
+                float* slot = gmr + ((g0 + g) & 63);
+                if (d[g * GS] < *slot) *slot = d[g * GS];  // (+inf padding never writes: GS = 1 shares slots across chunks only for N <= 64)
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                asm volatile(
+                    "{\n\t.reg .pred p, q;\n\t.reg .u32 pos, addr;\n\t"
+                    "setp.le.f32 p, %0, %1;\n\t"
+                    "@p atom.shared.add.u32 pos, [%2], 1;\n\t"
+                    "setp.lt.and.u32 q, pos, %3, p;\n\t"
+                    "mad.lo.u32 addr, pos, 8, %4;\n\t"
+                    "@q st.shared.v2.b32 [addr], {%5, %6};\n\t}"
+                    :: "f"(d[j]), "f"(T), "r"(cnt_addr), "n"(KT2_CAP), "r"(buf_row), "r"(__float_as_uint(d[j])), "r"(c0 + h + j)
+                    : "memory");
+            }
+        }
+    }
+}
+
 // ATM (D <= 128): the unit's query tile [tf32 | residual] is written ONCE into the 256 tensor-memory columns the
 // accumulators leave free and every MMA reads its A operand from there; only candidate tiles stream through shared
 // memory (hi and lo k-blocks of a stage loaded once and used by all three products).  3x less L2 -> SM traffic than
@@ -460,46 +506,7 @@ knn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) tc_mbar_arrive(tmem_empty + acc);      // accumulator is in registers: the next tile may start
-                    const float4* qj4 = reinterpret_cast<const float4*>(wqs);
-#pragma unroll
-                    for (int h = 0; h < 32; h += 16) {                    // 16 columns at a time: bounded register pressure
-                        float d[16];
-#pragma unroll
-                        for (int j = 0; j < 16; j += 4) {
-                            const float4 qj = qj4[(h + j) >> 2];
-                            d[j] = __fadd_rn(__fadd_rn(__fmul_rn(__uint_as_float(r[h + j]), -2.0f), qj.x), qi);
-                            d[j + 1] = __fadd_rn(__fadd_rn(__fmul_rn(__uint_as_float(r[h + j + 1]), -2.0f), qj.y), qi);
-                            d[j + 2] = __fadd_rn(__fadd_rn(__fmul_rn(__uint_as_float(r[h + j + 2]), -2.0f), qj.z), qi);
-                            d[j + 3] = __fadd_rn(__fadd_rn(__fmul_rn(__uint_as_float(r[h + j + 3]), -2.0f), qj.w), qi);
-                        }
-                        if (pass == 0) {
-                            // group minima: groups of GS consecutive candidates, slot = group % 64 (exclusive to this thread)
-#pragma unroll
-                            for (int w = 1; w < GS; w <<= 1)
-#pragma unroll
-                                for (int j = 0; j < 16; j += 2 * w) d[j] = fminf(d[j], d[j + w]);
-                            const int g0 = (c0 + h) / GS;
-#pragma unroll
-                            for (int g = 0; g < 16 / GS; ++g) {
-                                float* slot = gmr + ((g0 + g) & 63);
-                                if (d[g * GS] < *slot) *slot = d[g * GS];  // (+inf padding never writes: GS = 1 shares slots across chunks only for N <= 64)
-                            }
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 16; ++j) {
-                                // survivors: one predicated shared-memory atomic per hit, no divergence
-                                asm volatile(
-                                    "{\n\t.reg .pred p, q;\n\t.reg .u32 pos, addr;\n\t"
-                                    "setp.le.f32 p, %0, %1;\n\t"
-                                    "@p atom.shared.add.u32 pos, [%2], 1;\n\t"
-                                    "setp.lt.and.u32 q, pos, %3, p;\n\t"
-                                    "mad.lo.u32 addr, pos, 8, %4;\n\t"
-                                    "@q st.shared.v2.b32 [addr], {%5, %6};\n\t}"
-                                    :: "f"(d[j]), "f"(T), "r"(cnt_addr), "n"(KT2_CAP), "r"(buf_row), "r"(__float_as_uint(d[j])), "r"(c0 + h + j)
-                                    : "memory");
-                            }
-                        }
-                    }
+                    kt2_consume<GS>(r, wqs, qi, pass, c0, gmr, T, cnt_addr, buf_row);
                 }
                 epi_bar_sync();
                 if (pass == 0) {
