@@ -206,7 +206,10 @@ int tgp_split_tf32(const float* src, long rows, int K, long ld, int src_is_kn, f
 /* mixed operand (tgp_gemm_args.mixed): K rounded up to 64, and the split of a row-major (rows, K) matrix (zero padded). */
 int tgp_mixed_kpad(int K);
 int tgp_split_mixed(const float* src, long rows, int K, long ld, float* dst, tgp_stream_t stream);
-/* transposed mixed operand: dst (K, 8*Mp bytes), Mp = tgp_mixed_kpad(rows), row k = column k of src (zero padded). */
+/* transposed mixed operand, K-blocked: dst = tgp_split_mixed_t_bytes(rows, K) bytes (128-byte aligned), 16-bit slots
+ * [part 0..2][ceil(rows/64)][ceil256(K)][64]: per block of 64 source rows a dense (ceil256(K) x 128 B) matrix for each of
+ * fp16(x), bf16(x), bf16(x - fp16(x)); source rows past `rows` are zero.  Operand of tgp_gemm_tn_tc(mixed = 1). */
+size_t tgp_split_mixed_t_bytes(long rows, int K);
 int tgp_split_mixed_t(const float* src, long rows, int K, long ld, float* dst, tgp_stream_t stream);
 
 /* ------------------------------------------------------------------ chamfer (losses/chamfer3D) */
@@ -285,7 +288,7 @@ int tgp_surface_conv_bwd(const float* xyz, const void* idx, int idx_bits, const 
  * tgp_gemm_tn: exact fp32 FMA path on the raw operands (small / odd shapes).
  * tgp_gemm_tn_tc: tcgen05 path; operands are the TRANSPOSED splits: mixed = 0 (3xTF32) from tgp_split_tf32(src_is_kn=1),
  *                 At_split (K1, 2*Mp), Bt_split (K2, 2*Mp), Mp = tgp_split_kpad(M); mixed = 1 (fp16 + bf16 cross terms,
- *                 see tgp_gemm_args.mixed) from tgp_split_mixed_t, rows of 8*Mp bytes, Mp = tgp_mixed_kpad(M).
+ *                 see tgp_gemm_args.mixed) from tgp_split_mixed_t (K-blocked layout).
  *                 Split-K over M, partial sums added in a fixed order (deterministic). */
 size_t tgp_gemm_tn_workspace(long M, int K1, int K2);
 int tgp_gemm_tn(const float* A, long lda, const float* Bm, long ldb, long M, int K1, int K2, float* out, long ldo,

@@ -359,8 +359,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             unsigned char* sa = base + stage * STAGE_BYTES;
                             tc_mbar_expect_tx(full + stage, STAGE_BYTES);
                             const int a_part = u == 0 ? 0 : (u == 1 ? 2 : 1), b_part = u == 0 ? 0 : (u == 1 ? 1 : 2);
-                            tma_load_2d(sa, &tmA16, a_part * Kp + k64 * 64, m0, full + stage);
-                            tma_load_2d(sa + TC_A_BYTES, &tmB16, b_part * Kp + k64 * 64, n0, full + stage);
+                            if (g.mixed == 2) {
+                                // K-blocked transposed operands (tgp_split_mixed_t): a tile is one contiguous block
+                                const int nblk = Kp / 64;
+                                const long RA = ((long)g.M + 255) / 256 * 256, RB = ((long)g.Ncols + 255) / 256 * 256;
+                                tma_load_2d(sa, &tmA16, 0, (int)(((long)a_part * nblk + k64) * RA + m0), full + stage);
+                                tma_load_2d(sa + TC_A_BYTES, &tmB16, 0, (int)(((long)b_part * nblk + k64) * RB + n0), full + stage);
+                            } else {
+                                tma_load_2d(sa, &tmA16, a_part * Kp + k64 * 64, m0, full + stage);
+                                tma_load_2d(sa + TC_A_BYTES, &tmB16, b_part * Kp + k64 * 64, n0, full + stage);
+                            }
                             if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
                         }
                     }
@@ -639,14 +647,19 @@ using namespace tgp;
 
 extern "C" int tgp_split_kpad(int K) { return (K + TC_BK - 1) / TC_BK * TC_BK; }
 
-// transposed MIXED operand of a row-major (rows, K) matrix: dst row k holds column k of src, rows padded to
-// Mp = ceil64(rows) with zeros -- the operand of the weight-gradient contraction x^T . dY (contraction over the rows).
-// Tile = 64 rows x 32 columns through shared memory; a lane packs two consecutive rows per 32-bit store.
+// TRANSPOSED mixed operand of a row-major (rows, K) matrix, K-BLOCKED: the operand of the weight-gradient contraction
+// x^T . dY (contraction over the rows).  Layout: 16-bit slots [part 0..2][row block of 64][R = ceil256(K)][64], i.e. for every
+// block of 64 source rows a dense (R x 128 B) matrix per part (fp16 hi | bf16 x | bf16 lo).  A TMA tile (128 or 256 operand
+// rows x one 64-wide K block) is then ONE contiguous 16 / 32 KB piece of memory.  (The first version kept each operand row
+// contiguous over all source rows: 2 MB between the rows of a tile -- every 128-byte row segment in its own page -- and
+// ran the contraction at 120 TFLOP/s against 430 for the forward shape; TLB / DRAM-page thrash.)
+// Tile = 64 rows x 32 columns through shared memory; a lane packs two consecutive source rows per 32-bit store, a warp
+// writes one full 128-byte operand row.
 __global__ void __launch_bounds__(256)
-split_mixed_transpose_kernel(const float* __restrict__ src, long rows, int K, long ld, long Mp, float* __restrict__ dst) {
+split_mixed_transpose_kernel(const float* __restrict__ src, long rows, int K, long ld, long nblk, long R, float* __restrict__ dst) {
     __shared__ float tile[64][33];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    const long r0 = (long)blockIdx.y * 64;
+    const long blk = blockIdx.y, r0 = blk * 64;
     const int k0 = blockIdx.x * 32;
 #pragma unroll
     for (int rr = 0; rr < 64; rr += 8) {
@@ -654,18 +667,26 @@ split_mixed_transpose_kernel(const float* __restrict__ src, long rows, int K, lo
         tile[rr + ty][tx] = (r < rows && k0 + tx < K) ? __ldg(src + r * ld + k0 + tx) : 0.f;
     }
     __syncthreads();
+    uint32_t* d32 = reinterpret_cast<uint32_t*>(dst);
 #pragma unroll
     for (int kk = 0; kk < 32; kk += 8) {
         const int k = k0 + kk + ty;
         if (k >= K) continue;
         const float v0 = tile[2 * tx][kk + ty], v1 = tile[2 * tx + 1][kk + ty];
         float h0, h1;
-        uint32_t* row32 = reinterpret_cast<uint32_t*>(dst + (long)k * 2 * Mp);      // 4*Mp 16-bit slots = 2*Mp words
-        const long w = r0 / 2 + tx;
-        row32[w] = mixed_hi16x2(v0, v1, h0, h1);
-        row32[Mp / 2 + w] = bf16x2_bits(v0, v1);
-        row32[Mp + w] = bf16x2_bits(v0 - h0, v1 - h1);
+        const long w = (blk * R + k) * 32 + tx;                   // 32-bit word of (block, operand row k), part 0
+        const long part = nblk * R * 32;
+        d32[w] = mixed_hi16x2(v0, v1, h0, h1);
+        d32[part + w] = bf16x2_bits(v0, v1);
+        d32[2 * part + w] = bf16x2_bits(v0 - h0, v1 - h1);
     }
+}
+
+static long mixed_t_rows(int K) { return ((long)K + 255) / 256 * 256; }
+
+extern "C" size_t tgp_split_mixed_t_bytes(long rows, int K) {
+    if (rows <= 0 || K <= 0) return 0;
+    return (size_t)3 * ((rows + 63) / 64) * mixed_t_rows(K) * 128;
 }
 
 extern "C" int tgp_mixed_kpad(int K) { return (K + 63) / 64 * 64; }
@@ -673,11 +694,12 @@ extern "C" int tgp_mixed_kpad(int K) { return (K + 63) / 64 * 64; }
 extern "C" int tgp_split_mixed_t(const float* src, long rows, int K, long ld, float* dst, tgp_stream_t stream) {
     if (!src || !dst) return fail(TGP_EINVAL, "tgp_split_mixed_t: null pointer");
     if (rows <= 0 || rows > 0x7fffffffL - 64 || K <= 0) return fail(TGP_EINVAL, "tgp_split_mixed_t: bad sizes");
-    if ((uintptr_t)dst % 16) return fail(TGP_EINVAL, "tgp_split_mixed_t: dst must be 16-byte aligned");
-    const long Mp = (rows + 63) / 64 * 64;
-    dim3 grid((unsigned)((K + 31) / 32), (unsigned)(Mp / 64));
+    if ((uintptr_t)dst % 128) return fail(TGP_EINVAL, "tgp_split_mixed_t: dst must be 128-byte aligned");
+    const long nblk = (rows + 63) / 64, R = mixed_t_rows(K);
+    if (3 * nblk * R > 0x7fffffffL) return fail(TGP_EINVAL, "tgp_split_mixed_t: operand too large for one tensor map");
+    dim3 grid((unsigned)((K + 31) / 32), (unsigned)nblk);
     if (grid.y > 65535) return fail(TGP_EINVAL, "tgp_split_mixed_t: too many rows");
-    split_mixed_transpose_kernel<<<grid, 256, 0, as_stream(stream)>>>(src, rows, K, ld, Mp, dst);
+    split_mixed_transpose_kernel<<<grid, 256, 0, as_stream(stream)>>>(src, rows, K, ld, nblk, R, dst);
     return check_launch("split_mixed_transpose_kernel");
 }
 
@@ -717,15 +739,28 @@ template <int BN>
 static int launch_tc(const tgp_gemm_args* a, cudaStream_t st, int ksplit = 1) {
     const int Kp = a->mixed ? tgp_mixed_kpad(a->K) : tgp_split_kpad(a->K);
     CUtensorMap tmA, tmB, tmA16, tmB16;
-    int rc = tgp_make_map(&tmA, a->A_split, a->M, Kp, TC_BM);
-    if (rc) return rc;
-    rc = tgp_make_map(&tmB, a->B_split, a->Ncols, Kp, BN);
-    if (rc) return rc;
+    int rc = 0;
+    if (!a->mixed) {
+        rc = tgp_make_map(&tmA, a->A_split, a->M, Kp, TC_BM);
+        if (rc) return rc;
+        rc = tgp_make_map(&tmB, a->B_split, a->Ncols, Kp, BN);
+        if (rc) return rc;
+    }
     if (a->mixed) {
-        rc = tgp_make_map_bf16(&tmA16, a->A_split, a->M, Kp, TC_BM);
-        if (rc) return rc;
-        rc = tgp_make_map_bf16(&tmB16, a->B_split, a->Ncols, Kp, BN);
-        if (rc) return rc;
+        if (a->mixed == 2) {
+            const long nblk = Kp / 64;
+            rc = tgp_make_map_bf16_blocked(&tmA16, a->A_split, 3 * nblk * (((long)a->M + 255) / 256 * 256), TC_BM);
+            if (rc) return rc;
+            rc = tgp_make_map_bf16_blocked(&tmB16, a->B_split, 3 * nblk * (((long)a->Ncols + 255) / 256 * 256), BN);
+            if (rc) return rc;
+        } else {
+            rc = tgp_make_map_bf16(&tmA16, a->A_split, a->M, Kp, TC_BM);
+            if (rc) return rc;
+            rc = tgp_make_map_bf16(&tmB16, a->B_split, a->Ncols, Kp, BN);
+            if (rc) return rc;
+        }
+        tmA = tmA16;      // (the fp32 maps are not used by mixed launches)
+        tmB = tmB16;
     } else {
         tmA16 = tmA;
         tmB16 = tmB;
@@ -828,7 +863,7 @@ extern "C" int tgp_gemm_tn_tc(const float* At_split, const float* Bt_split, long
     int bn;
     const int ks = tn_plan(M, K1, K2, &bn, mixed);
     tgp_gemm_args a = {};
-    a.mixed = mixed ? 1 : 0;
+    a.mixed = mixed ? 2 : 0;            // 2: K-blocked transposed operands from tgp_split_mixed_t
     a.A_split = At_split;
     a.B_split = Bt_split;
     a.M = K1;

@@ -500,10 +500,12 @@ def surface_conv_bwd(xyz, idx, directions, arg, grad2d, S, C):
 
 
 def split_mixed_t(x2d):
-    """TRANSPOSED mixed operand of a row-major (rows, K) matrix: (K, 2*mixed_kpad(rows)) fp32 slots, row k = column k."""
+    """TRANSPOSED, K-blocked mixed operand of a row-major (rows, K) matrix (include/tgpose_b200.h, tgp_split_mixed_t):
+    a flat buffer of tgp_split_mixed_t_bytes(rows, K) bytes."""
     assert x2d.stride(1) == 1
     rows, K = x2d.shape
-    dst = torch.empty((K, 2 * mixed_kpad(rows)), dtype=torch.float32, device=x2d.device)
+    nbytes = _lib.load().tgp_split_mixed_t_bytes(rows, K)
+    dst = torch.empty(nbytes // 4, dtype=torch.float32, device=x2d.device)
     _run("split_mixed_t", _lib.load().tgp_split_mixed_t, _p(x2d), rows, K, x2d.stride(0), _p(dst), _stream())
     return dst
 
