@@ -210,6 +210,11 @@ int tgp_split_mixed(const float* src, long rows, int K, long ld, float* dst, tgp
  * [part 0..2][ceil(rows/64)][ceil256(K)][64]: per block of 64 source rows a dense (ceil256(K) x 128 B) matrix for each of
  * fp16(x), bf16(x), bf16(x - fp16(x)); source rows past `rows` are zero.  Operand of tgp_gemm_tn_tc(mixed = 1). */
 size_t tgp_split_mixed_t_bytes(long rows, int K);
+/* the same for the 3xTF32 operands of the encoder's weight gradients: src (Kdim, rows) row-major (Kdim = contraction
+ * length), dst = tgp_split_tf32_t_bytes(Kdim, rows) bytes, floats [part hi|lo][ceil(Kdim/32)][ceil256(rows)][32].
+ * Operand of tgp_gemm_tn_tc(mixed = 0). */
+size_t tgp_split_tf32_t_bytes(long Kdim, int rows);
+int tgp_split_tf32_t(const float* src, long Kdim, int rows, long ld, float* dst, tgp_stream_t stream);
 int tgp_split_mixed_t(const float* src, long rows, int K, long ld, float* dst, tgp_stream_t stream);
 
 /* ------------------------------------------------------------------ chamfer (losses/chamfer3D) */
@@ -286,8 +291,8 @@ int tgp_surface_conv_bwd(const float* xyz, const void* idx, int idx_bits, const 
 /* weight-gradient contraction out (K1,K2; row stride ldo) = A^T B with A (M,K1), B (M,K2) row-major
  * (dW = x^T dY of `feature_map @ weights`, gcn3d.py:170, and of every 1x1 Conv1d on the path).
  * tgp_gemm_tn: exact fp32 FMA path on the raw operands (small / odd shapes).
- * tgp_gemm_tn_tc: tcgen05 path; operands are the TRANSPOSED splits: mixed = 0 (3xTF32) from tgp_split_tf32(src_is_kn=1),
- *                 At_split (K1, 2*Mp), Bt_split (K2, 2*Mp), Mp = tgp_split_kpad(M); mixed = 1 (fp16 + bf16 cross terms,
+ * tgp_gemm_tn_tc: tcgen05 path; operands are the K-blocked TRANSPOSED splits: mixed = 0 (3xTF32) from tgp_split_tf32_t;
+ *                 mixed = 1 (fp16 + bf16 cross terms,
  *                 see tgp_gemm_args.mixed) from tgp_split_mixed_t (K-blocked layout).
  *                 Split-K over M, partial sums added in a fixed order (deterministic). */
 size_t tgp_gemm_tn_workspace(long M, int K1, int K2);

@@ -73,6 +73,8 @@ SIGNATURES = {
     "tgp_split_mixed": (c_int, [c_void_p, c_long, c_int, c_long, c_void_p, c_void_p]),
     "tgp_split_mixed_t": (c_int, [c_void_p, c_long, c_int, c_long, c_void_p, c_void_p]),
     "tgp_split_mixed_t_bytes": (c_size_t, [c_long, c_int]),
+    "tgp_split_tf32_t": (c_int, [c_void_p, c_long, c_int, c_long, c_void_p, c_void_p]),
+    "tgp_split_tf32_t_bytes": (c_size_t, [c_long, c_int]),
     "tgp_dcd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, ctypes.c_float, ctypes.c_float,
                         c_void_p, c_void_p, c_void_p, c_void_p]),
     "tgp_act_bwd": (c_int, [c_void_p, c_long, c_void_p, c_long, c_void_p, c_int, c_long, c_int, c_void_p, c_long,

@@ -36,6 +36,7 @@ constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;   // TMA warp + MMA warp + ep
 
 struct GemmDev {
     tgp_gemm_args a;
+    int blocked;       // operands are the K-blocked transposed splits of the weight-gradient contraction (tgp_gemm_tn_tc)
 };
 
 // one output destination of a column: pointer to (row0, col), row stride, and (split mode) the lo-half offset
@@ -359,7 +360,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             unsigned char* sa = base + stage * STAGE_BYTES;
                             tc_mbar_expect_tx(full + stage, STAGE_BYTES);
                             const int a_part = u == 0 ? 0 : (u == 1 ? 2 : 1), b_part = u == 0 ? 0 : (u == 1 ? 1 : 2);
-                            if (g.mixed == 2) {
+                            if (P.blocked) {
                                 // K-blocked transposed operands (tgp_split_mixed_t): a tile is one contiguous block
                                 const int nblk = Kp / 64;
                                 const long RA = ((long)g.M + 255) / 256 * 256, RB = ((long)g.Ncols + 255) / 256 * 256;
@@ -383,8 +384,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         if (dbg & 4) { tc_mbar_arrive(full + stage); }
                         else {
                             tc_mbar_expect_tx(full + stage, STAGE_BYTES);
-                            tma_load_2d(sa, &tmA, a_off + kb * TC_BK, m0, full + stage);
-                            tma_load_2d(sa + TC_A_BYTES, &tmB, b_off + kb * TC_BK, n0, full + stage);
+                            if (P.blocked) {
+                                // K-blocked transposed splits (tgp_split_tf32_t): [part][block of 32][ceil256(rows)][32]
+                                const long RA = ((long)g.M + 255) / 256 * 256, RB = ((long)g.Ncols + 255) / 256 * 256;
+                                tma_load_2d(sa, &tmA, 0, (int)(((long)(a_off ? 1 : 0) * kblocks + kb) * RA + m0), full + stage);
+                                tma_load_2d(sa + TC_A_BYTES, &tmB, 0, (int)(((long)(b_off ? 1 : 0) * kblocks + kb) * RB + n0), full + stage);
+                            } else {
+                                tma_load_2d(sa, &tmA, a_off + kb * TC_BK, m0, full + stage);
+                                tma_load_2d(sa + TC_A_BYTES, &tmB, b_off + kb * TC_BK, n0, full + stage);
+                            }
                         }
                         if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
                     }
@@ -629,6 +637,34 @@ split_tf32_transpose_kernel(const float* __restrict__ src, long rows, long K, lo
     }
 }
 
+// K-BLOCKED transposed [tf32 | residual] split of a row-major (Kdim, rows) matrix -- the 3xTF32 operand of the encoder's
+// weight-gradient contractions: floats [part hi|lo][block of 32 source rows][R = ceil256(rows)][32]; a TMA tile is one
+// contiguous piece (see split_mixed_transpose_kernel for why).
+__global__ void __launch_bounds__(256)
+split_tf32_t_blocked_kernel(const float* __restrict__ src, long Kdim, long rows, long ld, long nblk, long R, float* __restrict__ dst) {
+    __shared__ float tile[32][33];
+    const long kb = blockIdx.x, k0 = kb * 32, r0 = (long)blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = ty; i < 32; i += 8) {
+        const long k = k0 + i, r = r0 + tx;
+        tile[i][tx] = (k < Kdim && r < rows) ? __ldg(src + k * ld + r) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = ty; i < 32; i += 8) {
+        const long r = r0 + i;
+        if (r < rows) {
+            const float v = tile[tx][i];
+            uint32_t hb;
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v));
+            const float hi = __uint_as_float(hb);
+            dst[(kb * R + r) * 32 + tx] = hi;
+            dst[((nblk + kb) * R + r) * 32 + tx] = v - hi;
+        }
+    }
+}
+
 // out[r, c] = sum_z partial[z][r][c]  (fixed order: deterministic)
 __global__ void tc_splitk_reduce_kernel(const float* __restrict__ partial, int nsplit, long rows, int cols,
                                         float* __restrict__ out, long ldo) {
@@ -717,6 +753,23 @@ extern "C" int tgp_split_mixed(const float* src, long rows, int K, long ld, floa
     return check_launch("split_mixed_kernel");
 }
 
+extern "C" size_t tgp_split_tf32_t_bytes(long Kdim, int rows) {
+    if (Kdim <= 0 || rows <= 0) return 0;
+    return (size_t)2 * ((Kdim + 31) / 32) * (((long)rows + 255) / 256 * 256) * 128;
+}
+
+extern "C" int tgp_split_tf32_t(const float* src, long Kdim, int rows, long ld, float* dst, tgp_stream_t stream) {
+    if (!src || !dst) return fail(TGP_EINVAL, "tgp_split_tf32_t: null pointer");
+    if (Kdim <= 0 || Kdim > 0x7fffffffL - 64 || rows <= 0) return fail(TGP_EINVAL, "tgp_split_tf32_t: bad sizes");
+    if ((uintptr_t)dst % 128) return fail(TGP_EINVAL, "tgp_split_tf32_t: dst must be 128-byte aligned");
+    const long nblk = (Kdim + 31) / 32, R = ((long)rows + 255) / 256 * 256;
+    if (2 * nblk * R > 0x7fffffffL) return fail(TGP_EINVAL, "tgp_split_tf32_t: operand too large for one tensor map");
+    dim3 grid((unsigned)nblk, (unsigned)((rows + 31) / 32));
+    if (grid.y > 65535) return fail(TGP_EINVAL, "tgp_split_tf32_t: too many rows");
+    split_tf32_t_blocked_kernel<<<grid, 256, 0, as_stream(stream)>>>(src, Kdim, rows, ld, nblk, R, dst);
+    return check_launch("split_tf32_t_blocked_kernel");
+}
+
 extern "C" int tgp_split_tf32(const float* src, long rows, int K, long ld, int src_is_kn, float* dst,
                               tgp_stream_t stream) {
     if (!src || !dst) return fail(TGP_EINVAL, "tgp_split_tf32: null pointer");
@@ -736,18 +789,24 @@ extern "C" int tgp_split_tf32(const float* src, long rows, int K, long ld, int s
 }
 
 template <int BN>
-static int launch_tc(const tgp_gemm_args* a, cudaStream_t st, int ksplit = 1) {
+static int launch_tc(const tgp_gemm_args* a, cudaStream_t st, int ksplit = 1, int blocked = 0) {
     const int Kp = a->mixed ? tgp_mixed_kpad(a->K) : tgp_split_kpad(a->K);
     CUtensorMap tmA, tmB, tmA16, tmB16;
     int rc = 0;
-    if (!a->mixed) {
+    if (!a->mixed && blocked) {
+        const long nblk = Kp / TC_BK;
+        rc = tgp_make_map_f32_blocked(&tmA, a->A_split, 2 * nblk * (((long)a->M + 255) / 256 * 256), TC_BM);
+        if (rc) return rc;
+        rc = tgp_make_map_f32_blocked(&tmB, a->B_split, 2 * nblk * (((long)a->Ncols + 255) / 256 * 256), BN);
+        if (rc) return rc;
+    } else if (!a->mixed) {
         rc = tgp_make_map(&tmA, a->A_split, a->M, Kp, TC_BM);
         if (rc) return rc;
         rc = tgp_make_map(&tmB, a->B_split, a->Ncols, Kp, BN);
         if (rc) return rc;
     }
     if (a->mixed) {
-        if (a->mixed == 2) {
+        if (blocked) {
             const long nblk = Kp / 64;
             rc = tgp_make_map_bf16_blocked(&tmA16, a->A_split, 3 * nblk * (((long)a->M + 255) / 256 * 256), TC_BM);
             if (rc) return rc;
@@ -767,6 +826,7 @@ static int launch_tc(const tgp_gemm_args* a, cudaStream_t st, int ksplit = 1) {
     }
     GemmDev P;
     P.a = *a;
+    P.blocked = blocked;
     const int num_m_tiles = (int)((a->M + TC_BM - 1) / TC_BM);
     const int num_n_tiles = (a->Ncols + BN - 1) / BN;
     const int tiles_mn = num_m_tiles * num_n_tiles;
@@ -863,7 +923,7 @@ extern "C" int tgp_gemm_tn_tc(const float* At_split, const float* Bt_split, long
     int bn;
     const int ks = tn_plan(M, K1, K2, &bn, mixed);
     tgp_gemm_args a = {};
-    a.mixed = mixed ? 2 : 0;            // 2: K-blocked transposed operands from tgp_split_mixed_t
+    a.mixed = mixed ? 1 : 0;
     a.A_split = At_split;
     a.B_split = Bt_split;
     a.M = K1;
@@ -877,9 +937,9 @@ extern "C" int tgp_gemm_tn_tc(const float* At_split, const float* Bt_split, long
     a.seg[0].ptr = ks > 1 ? static_cast<float*>(workspace) : out;
     cudaStream_t st = as_stream(stream);
     int rc;
-    if (bn == 256) rc = launch_tc<256>(&a, st, ks);
-    else if (bn == 128) rc = launch_tc<128>(&a, st, ks);
-    else rc = launch_tc<64>(&a, st, ks);
+    if (bn == 256) rc = launch_tc<256>(&a, st, ks, 1);
+    else if (bn == 128) rc = launch_tc<128>(&a, st, ks, 1);
+    else rc = launch_tc<64>(&a, st, ks, 1);
     if (rc || ks == 1) return rc;
     const long total = (long)K1 * K2;
     long nb = (total + 255) / 256;

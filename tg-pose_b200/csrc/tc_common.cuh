@@ -185,3 +185,18 @@ static inline int tgp_make_map_bf16_blocked(CUtensorMap* tm, const float* ptr, l
     if (r != CUDA_SUCCESS) return tgp::fail(TGP_EINVAL, "tgp_gemm: cuTensorMapEncodeTiled (blocked bf16) failed");
     return TGP_OK;
 }
+
+// fp32 view of a K-BLOCKED transposed [tf32 | residual] operand (tgp_split_tf32_t): dense rows of 32 floats (128 bytes).
+static inline int tgp_make_map_f32_blocked(CUtensorMap* tm, const float* ptr, long total_rows, int box_rows) {
+    tgp_encode_fn enc = tgp_get_encode();
+    if (!enc) return tgp::fail(TGP_EINVAL, "tgp_gemm: cuTensorMapEncodeTiled unavailable");
+    cuuint64_t gdim[2] = {32u, (cuuint64_t)total_rows};
+    cuuint64_t gstride[1] = {128u};
+    cuuint32_t box[2] = {32u, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), gdim, gstride, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return tgp::fail(TGP_EINVAL, "tgp_gemm: cuTensorMapEncodeTiled (blocked fp32) failed");
+    return TGP_OK;
+}

@@ -510,6 +510,17 @@ def split_mixed_t(x2d):
     return dst
 
 
+def split_tf32_t(x2d):
+    """TRANSPOSED, K-blocked [tf32 | residual] operand of a row-major (rows, K) matrix for the 3xTF32 weight-gradient
+    contraction (include/tgpose_b200.h, tgp_split_tf32_t): flat buffer of tgp_split_tf32_t_bytes(rows, K) bytes."""
+    assert x2d.stride(1) == 1
+    rows, K = x2d.shape
+    nbytes = _lib.load().tgp_split_tf32_t_bytes(rows, K)
+    dst = torch.empty(nbytes // 4, dtype=torch.float32, device=x2d.device)
+    _run("split_tf32_t", _lib.load().tgp_split_tf32_t, _p(x2d), rows, K, x2d.stride(0), _p(dst), _stream())
+    return dst
+
+
 def gemm_tn(A2d, B2d, out=None, tc=None, mixed=False):
     """A^T B: (M,K1),(M,K2) -> (K1,K2), the weight-gradient contraction.  Large shapes run on the tensor cores
     (transposed splits + split-K; 3xTF32, or the heads' mixed fp16+bf16 operands when mixed), small / skinny ones on the
@@ -524,7 +535,7 @@ def gemm_tn(A2d, B2d, out=None, tc=None, mixed=False):
     if tc is None:
         tc = TC_ENABLED and M >= 512 and K1 >= 16 and K2 >= 16
     if tc:
-        spl = split_mixed_t if mixed else (lambda t: split_tf32(t, src_is_kn=True))
+        spl = split_mixed_t if mixed else split_tf32_t
         At = spl(A2d)
         Bt = At if (B2d.data_ptr() == A2d.data_ptr() and B2d.shape == A2d.shape and B2d.stride() == A2d.stride()) \
             else spl(B2d)
