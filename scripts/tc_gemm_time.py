@@ -16,3 +16,7 @@ def t(M, K, N, reps=10):
 t(32896, 1286, 1024)
 t(32896, 128, 1152)
 t(32896, 1024, 256)
+if os.environ.get("TGP_SMALL"):
+    t(32896, 128, 128)
+    t(8224, 256, 256)
+    t(2048, 512, 512)
