@@ -320,9 +320,12 @@ int tgp_affine_act(const float* z, long ld_z, const float* scale, const float* s
 
 /* backward of y = act(BN_train(z)): dbeta[c] = sum g, dgamma[c] = sum g * zhat, g = dy * act'(y),
  * dz = gamma * invstd * (g - dbeta / M - zhat * dgamma / M).  workspace: tgp_bn_workspace(M, C).
- * dz_mixed (optional): dz also written as the MIXED operand (M, 8*tgp_mixed_kpad(C) bytes) of the dx contraction. */
+ * dz_mixed (optional): dz also written as the MIXED operand (M, 8*tgp_mixed_kpad(C) bytes) of the dx contraction.
+ * scale / shift (optional, the forward's tgp_affine_act arguments): the activation mask is recomputed from z
+ * (y = act(fma(z, scale, shift)), bit-identical) instead of being read from y. */
 int tgp_bn_bwd(const float* dy, long ld_dy, const float* y, long ld_y, const float* z, long ld_z,
-               const float* mean, const float* invstd, const float* gamma, float slope, long M, int C,
+               const float* mean, const float* invstd, const float* gamma, const float* scale, const float* shift,
+               float slope, long M, int C,
                float* dz, long ld_dz, float* dz_mixed, float* dbeta, float* dgamma,
                void* workspace, size_t workspace_bytes, tgp_stream_t stream);
 

@@ -95,7 +95,7 @@ SIGNATURES = {
     "tgp_affine_act": (c_int, [c_void_p, c_long, c_void_p, c_void_p, ctypes.c_float, c_long, c_int, c_void_p, c_long,
                                c_void_p, c_int, c_int, c_void_p]),
     "tgp_bn_bwd": (c_int, [c_void_p, c_long, c_void_p, c_long, c_void_p, c_long, c_void_p, c_void_p, c_void_p,
-                           ctypes.c_float, c_long, c_int, c_void_p, c_long, c_void_p, c_void_p, c_void_p, c_void_p,
+                           c_void_p, c_void_p, ctypes.c_float, c_long, c_int, c_void_p, c_long, c_void_p, c_void_p, c_void_p, c_void_p,
                            c_size_t, c_void_p]),
     "tgp_gemm_tn_workspace": (c_size_t, [c_long, c_int, c_int]),
     "tgp_gemm_tn": (c_int, [c_void_p, c_long, c_void_p, c_long, c_long, c_int, c_int, c_void_p, c_long, c_void_p,

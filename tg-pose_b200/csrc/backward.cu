@@ -376,7 +376,8 @@ template <int MODE>
 __global__ void __launch_bounds__(CS_THREADS)
 colred_vec_kernel(const float* __restrict__ x, long ld, long rows_per_group, int C, const float* __restrict__ mu,
                   const float* __restrict__ y, long ld_y, const float* __restrict__ z, long ld_z,
-                  const float* __restrict__ invstd, float slope, float* __restrict__ partial) {
+                  const float* __restrict__ invstd, float slope, float* __restrict__ partial,
+                  const float* __restrict__ scale = nullptr, const float* __restrict__ shift = nullptr) {
     __shared__ __align__(16) float part[MODE == 2 ? 2 : 1][CS_THREADS / 32][128];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int c = (blockIdx.x * 32 + lane) * 4;
@@ -391,6 +392,8 @@ colred_vec_kernel(const float* __restrict__ x, long ld, long rows_per_group, int
         float4 m = a0, is = a0;
         if (MODE >= 1) m = __ldg(reinterpret_cast<const float4*>(mu + c));
         if (MODE == 2) is = __ldg(reinterpret_cast<const float4*>(invstd + c));
+        float4 sc = a0, sh = a0;
+        if (MODE == 2 && scale) { sc = __ldg(reinterpret_cast<const float4*>(scale + c)); sh = __ldg(reinterpret_cast<const float4*>(shift + c)); }
         auto body = [&](long r) {
             float4 v = __ldg(reinterpret_cast<const float4*>(x + r * ld + c));
             if (MODE == 0) { a0.x += v.x; a0.y += v.y; a0.z += v.z; a0.w += v.w; }
@@ -398,8 +401,11 @@ colred_vec_kernel(const float* __restrict__ x, long ld, long rows_per_group, int
                 v.x -= m.x; v.y -= m.y; v.z -= m.z; v.w -= m.w;
                 a0.x = fmaf(v.x, v.x, a0.x); a0.y = fmaf(v.y, v.y, a0.y); a0.z = fmaf(v.z, v.z, a0.z); a0.w = fmaf(v.w, v.w, a0.w);
             } else {
-                const float4 yy = __ldg(reinterpret_cast<const float4*>(y + r * ld_y + c));
                 const float4 zz = __ldg(reinterpret_cast<const float4*>(z + r * ld_z + c));
+                // activation mask: from y, or recomputed bit-identically from z (y = act(fma(z, scale, shift))) -- one read less
+                float4 yy;
+                if (scale) yy = make_float4(fmaf(zz.x, sc.x, sh.x), fmaf(zz.y, sc.y, sh.y), fmaf(zz.z, sc.z, sh.z), fmaf(zz.w, sc.w, sh.w));
+                else yy = __ldg(reinterpret_cast<const float4*>(y + r * ld_y + c));
                 if (!(yy.x > 0.f)) v.x *= slope;
                 if (!(yy.y > 0.f)) v.y *= slope;
                 if (!(yy.z > 0.f)) v.z *= slope;
@@ -464,7 +470,7 @@ bn_bwd_apply_vec_kernel(const float* __restrict__ dy, long ld_dy, const float* _
                         const float* __restrict__ z, long ld_z, const float* __restrict__ mean,
                         const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ dbeta,
                         const float* __restrict__ dgamma, float slope, long M, int C, float* __restrict__ dz, long ld_dz,
-                        float* __restrict__ dz_mixed, int kp) {
+                        float* __restrict__ dz_mixed, int kp, const float* __restrict__ scale, const float* __restrict__ shift) {
     const float inv_m = 1.0f / (float)M;
     if (dz_mixed)      // zero padding of the operand columns past C (Kp = ceil64(C))
         for (long r = blockIdx.x; r < M; r += gridDim.x)
@@ -474,10 +480,14 @@ bn_bwd_apply_vec_kernel(const float* __restrict__ dy, long ld_dy, const float* _
         const float4 mu = __ldg(reinterpret_cast<const float4*>(mean + c)), is = __ldg(reinterpret_cast<const float4*>(invstd + c));
         const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma + c));
         const float4 db = __ldg(reinterpret_cast<const float4*>(dbeta + c)), dg = __ldg(reinterpret_cast<const float4*>(dgamma + c));
+        float4 sc = mu, sh = mu;
+        if (scale) { sc = __ldg(reinterpret_cast<const float4*>(scale + c)); sh = __ldg(reinterpret_cast<const float4*>(shift + c)); }
         for (long r = blockIdx.x; r < M; r += gridDim.x) {
             float4 g = __ldg(reinterpret_cast<const float4*>(dy + r * ld_dy + c));
-            const float4 yy = __ldg(reinterpret_cast<const float4*>(y + r * ld_y + c));
             const float4 zz = __ldg(reinterpret_cast<const float4*>(z + r * ld_z + c));
+            float4 yy;
+            if (scale) yy = make_float4(fmaf(zz.x, sc.x, sh.x), fmaf(zz.y, sc.y, sh.y), fmaf(zz.z, sc.z, sh.z), fmaf(zz.w, sc.w, sh.w));
+            else yy = __ldg(reinterpret_cast<const float4*>(y + r * ld_y + c));
             if (!(yy.x > 0.f)) g.x *= slope;
             if (!(yy.y > 0.f)) g.y *= slope;
             if (!(yy.z > 0.f)) g.z *= slope;
@@ -782,7 +792,8 @@ extern "C" int tgp_affine_act(const float* z, long ld_z, const float* scale, con
 }
 
 extern "C" int tgp_bn_bwd(const float* dy, long ld_dy, const float* y, long ld_y, const float* z, long ld_z,
-                          const float* mean, const float* invstd, const float* gamma, float slope, long M, int C,
+                          const float* mean, const float* invstd, const float* gamma, const float* scale,
+                          const float* shift, float slope, long M, int C,
                           float* dz, long ld_dz, float* dz_mixed, float* dbeta, float* dgamma, void* workspace,
                           size_t workspace_bytes, tgp_stream_t stream) {
     if (!dy || !y || !z || !mean || !invstd || !gamma || !dz || !dbeta || !dgamma || !workspace)
@@ -797,7 +808,9 @@ extern "C" int tgp_bn_bwd(const float* dy, long ld_dy, const float* y, long ld_y
     auto a16 = [](const void* q) { return ((uintptr_t)q & 15) == 0; };
     if (C % 4 == 0 && ld_dy % 4 == 0 && ld_y % 4 == 0 && ld_z % 4 == 0 && a16(dy) && a16(y) && a16(z) && a16(mean) && a16(invstd)) {
         grid.x = (C + 127) / 128;
-        colred_vec_kernel<2><<<grid, CS_THREADS, 0, st>>>(dy, ld_dy, M, C, mean, y, ld_y, z, ld_z, invstd, slope, part);
+        const bool mask_from_z = scale && shift && a16(scale) && a16(shift);
+        colred_vec_kernel<2><<<grid, CS_THREADS, 0, st>>>(dy, ld_dy, M, C, mean, y, ld_y, z, ld_z, invstd, slope, part,
+                                                         mask_from_z ? scale : nullptr, mask_from_z ? shift : nullptr);
         rc = check_launch("colred_vec_kernel<2>");
     } else {
         bn_bwd_reduce_kernel<<<grid, CS_THREADS, 0, st>>>(dy, ld_dy, y, ld_y, z, ld_z, mean, invstd, slope, M, C, part);
@@ -814,7 +827,7 @@ extern "C" int tgp_bn_bwd(const float* dy, long ld_dy, const float* y, long ld_y
         if (dz_mixed && !al16(dz_mixed)) return fail(TGP_EINVAL, "tgp_bn_bwd: dz_mixed must be 16-byte aligned");
         bn_bwd_apply_vec_kernel<<<(unsigned)nb, C >= 1024 ? 256 : (C >= 256 ? 64 : 32), 0, st>>>(
             dy, ld_dy, y, ld_y, z, ld_z, mean, invstd, gamma, dbeta, dgamma, slope, M, C, dz, ld_dz, dz_mixed,
-            tgp_mixed_kpad(C));
+            tgp_mixed_kpad(C), (scale && shift && al16(scale) && al16(shift)) ? scale : nullptr, shift);
         return check_launch("bn_bwd_apply_vec_kernel");
     }
     if (dz_mixed) return fail(TGP_EINVAL, "tgp_bn_bwd: dz_mixed needs C % 4 == 0 and 16-byte aligned operands");

@@ -585,7 +585,7 @@ def affine_act(z2d, scale, shift, slope, want_raw=True, want_split=False, mixed=
     return raw, spl
 
 
-def bn_bwd(dy2d, y2d, z2d, mean, invstd, gamma, slope, want_mixed=False):
+def bn_bwd(dy2d, y2d, z2d, mean, invstd, gamma, slope, want_mixed=False, scale=None, shift=None):
     """-> (dz (M,C), dbeta (C,), dgamma (C,)) of y = act(BN_train(z)); with want_mixed also dz as the mixed operand of
     the dx contraction (4th result; None when the shape does not take the 128-bit kernel)."""
     M, C = z2d.shape
@@ -600,7 +600,8 @@ def bn_bwd(dy2d, y2d, z2d, mean, invstd, gamma, slope, want_mixed=False):
     if want_mixed and C % 4 == 0 and all(t.stride(0) % 4 == 0 and t.data_ptr() % 16 == 0 for t in (dy2d, y2d, z2d)):
         dzm = mixed_buf(M, C, z2d.device)
     _run("bn_bwd", lib.tgp_bn_bwd, _p(dy2d), dy2d.stride(0), _p(y2d), y2d.stride(0), _p(z2d), z2d.stride(0), _p(mean),
-         _p(invstd), _p(gamma), float(slope), M, C, _p(dz), C, _p(dzm), _p(dbeta), _p(dgamma), _p(ws), nb, _stream())
+         _p(invstd), _p(gamma), _p(scale), _p(shift), float(slope), M, C, _p(dz), C, _p(dzm), _p(dbeta), _p(dgamma), _p(ws),
+         nb, _stream())
     if want_mixed:
         return dz, dbeta, dgamma, dzm
     return dz, dbeta, dgamma
