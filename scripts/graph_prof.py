@@ -43,3 +43,11 @@ for e in evs:
     a = agg.setdefault(k, [0, 0.0]); a[0] += 1; a[1] += e.time_range.end - e.time_range.start
 for k, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:32]:
     print(f"{t/1e3:8.3f} ms x{c:3d}  {k}")
+if os.environ.get("TIMELINE"):
+    print("--- timeline: start(us) dur(us) idle-before(us) name  (idle = no kernel on any stream)")
+    busy_end = evs[0].time_range.start
+    for e in evs:
+        s, en = e.time_range.start, e.time_range.end
+        gap = max(0, s - busy_end)
+        print(f"{(s-t0):8.1f} {(en-s):7.1f} {gap:6.1f}  {e.name.split('(')[0][-48:]}")
+        busy_end = max(busy_end, en)

@@ -35,7 +35,7 @@ def _orl_tail_bwd(grad_out, out, post, feature, g, idx_xyz, arg_orl, conv2_w, B,
     dg = ops.matmul_kn(d_gb, w2[:, C:], tc=False)                           # (B, C)
     d_w2 = torch.empty((C, 2 * C), dtype=torch.float32, device=dev)
     ops.gemm_tn(d_gb, g, out=d_w2[:, C:], tc=False)
-    ops.gemm_tn(gz, feature.view(M, C), out=d_w2[:, :C])
+    ops.gemm_tn(gz, feature.view(M, C), out=d_w2[:, :C], mixed=True)      # gradients: fp16+bf16 mixed operands (1.5 passes)
     d_sc = torch.zeros((B, N, C), dtype=torch.float32, device=dev)
     ops.gather_max_bwd(dg, idx_xyz, arg_orl, N, d_sc, per_cloud=True, scale=1.0 / N)
     if df_dst is None:
@@ -69,7 +69,7 @@ def hs_layer_backward(ctx, grad_out):
     d_dir = ops.layer_conv_bwd(rec, directions, slab, arg, dP[:, :C], B, N, S, C, d_support=dP[:, C:C + SC])
     wcat, _bcat, _ws = _pack_layer(weights, bias, ste_w, S, C)    # (cin, (S+2)C)
     d_fm = ops.linear_nk(dP, wcat)                                # dP @ wcat^T
-    d_wcat = ops.gemm_tn(fm.view(M, cin), dP)                     # (cin, (S+2)C)
+    d_wcat = ops.gemm_tn(fm.view(M, cin), dP, mixed=True)         # (cin, (S+2)C); mixed operands like the heads
     d_bcat = ops.colsum(dP[:, :C + SC]).view(-1)
     d_weights = torch.cat([d_wcat[:, :C],
                            d_wcat[:, C:C + SC].reshape(cin, C // 4, S, 4).permute(0, 2, 1, 3).reshape(cin, SC)], dim=1)
