@@ -189,6 +189,13 @@ typedef struct {
      * (fp32-summation-noise level at the heads' K ~ 1e3).  Used for the heads' 1x1 convolutions (PoseR.py, PoseTs.py,
      * FaceRecon.py:89-167), whose outputs feed no neighbour search; the encoder and the kNN keep the 3xTF32 operands. */
     int mixed;
+    /* block-diagonal ("grouped") contraction on mixed operands: when a_group_cols > 0, output columns
+     * [g*a_group_cols, (g+1)*a_group_cols) contract the A columns [g*Kp, (g+1)*Kp) of a WIDER operand of padded width a_kp
+     * (several equally shaped layers that read different column blocks of one activation buffer and would each fill the
+     * machine badly -- the three pose-head conv2 layers: 257 row tiles on 148 SMs -- run as one launch).  a_group_cols must be
+     * a multiple of 256, K a multiple of 64; B_split stacks the layers' (a_group_cols, K) weights.  0: plain contraction. */
+    int a_kp;
+    int a_group_cols;
 } tgp_gemm_args;
 
 /* feature_map @ weights + bias (gcn3d.py:170) and every 1x1 Conv1d on the path. */

@@ -32,11 +32,14 @@ def test_library_exports_every_declared_symbol():
 
 def test_gemm_args_struct_layout_matches_header():
     from tgpose_b200 import _lib
-    # natural alignment of the C structs (LP64): tgp_out_seg 32 B, tgp_gemm_args 152 + 4*32 + 16 + (int mixed, padded to 8)
+    # natural alignment of the C structs (LP64): tgp_out_seg 32 B, tgp_gemm_args 152 + 4*32 + 16 + (int mixed, a_kp,
+    # a_group_cols, padded to 16)
     assert ctypes.sizeof(_lib.OutSeg) == 32
-    assert ctypes.sizeof(_lib.GemmArgs) == 152 + 4 * 32 + 16 + 8
+    assert ctypes.sizeof(_lib.GemmArgs) == 152 + 4 * 32 + 16 + 16
     assert _lib.GemmArgs.seg.offset == 152
     assert _lib.GemmArgs.mixed.offset == 152 + 4 * 32 + 16
+    assert _lib.GemmArgs.a_kp.offset == _lib.GemmArgs.mixed.offset + 4
+    assert _lib.GemmArgs.a_group_cols.offset == _lib.GemmArgs.mixed.offset + 8
     assert ctypes.sizeof(_lib.ConcatSrc) == 40
 
 

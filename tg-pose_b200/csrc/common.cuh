@@ -99,6 +99,18 @@ __device__ __forceinline__ void mixed_store4(uint16_t* row16, int Kp, int col, f
     *reinterpret_cast<uint2*>(row16 + Kp + col) = make_uint2(bf16x2_bits(v.x, v.y), bf16x2_bits(v.z, v.w));
     *reinterpret_cast<uint2*>(row16 + 2 * Kp + col) = make_uint2(bf16x2_bits(v.x - h0, v.y - h1), bf16x2_bits(v.z - h2, v.w - h3));
 }
+// the same with streaming (evict-first) stores: a GEMM epilogue that writes an operand larger than L2 must not push the
+// weight tiles, which every row block re-reads, out of the cache
+__device__ __forceinline__ void st_cs_u2(void* p, uint32_t a, uint32_t b) {
+    asm volatile("st.global.cs.v2.b32 [%0], {%1, %2};" ::"l"(p), "r"(a), "r"(b) : "memory");
+}
+__device__ __forceinline__ void mixed_store4_cs(uint16_t* row16, int Kp, int col, float4 v) {
+    float h0, h1, h2, h3;
+    const uint32_t a01 = mixed_hi16x2(v.x, v.y, h0, h1), a23 = mixed_hi16x2(v.z, v.w, h2, h3);
+    st_cs_u2(row16 + col, a01, a23);
+    st_cs_u2(row16 + Kp + col, bf16x2_bits(v.x, v.y), bf16x2_bits(v.z, v.w));
+    st_cs_u2(row16 + 2 * Kp + col, bf16x2_bits(v.x - h0, v.y - h1), bf16x2_bits(v.z - h2, v.w - h3));
+}
 
 #define TGP_DISPATCH_IDX(bits, ...)                                   \
     do {                                                              \

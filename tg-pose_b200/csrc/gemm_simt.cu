@@ -379,6 +379,7 @@ int tgp_gemm_validate(const tgp_gemm_args* a) {
     if (!a) return fail(TGP_EINVAL, "tgp_gemm: null args");
     if ((!a->A || !a->Bmat) && (!a->A_split || !a->B_split)) return fail(TGP_EINVAL, "tgp_gemm: null operand");
     if (a->M <= 0 || a->K <= 0 || a->Ncols <= 0) return fail(TGP_EINVAL, "tgp_gemm: sizes must be positive");
+    if (a->a_group_cols != 0 && (!a->mixed || !a->A_split || !a->B_split)) return fail(TGP_EINVAL, "tgp_gemm: a grouped contraction needs mixed operands");
     if (a->nseg < 1 || a->nseg > 4) return fail(TGP_EINVAL, "tgp_gemm: nseg must be 1..4");
     if (a->rows_per_group < 0) return fail(TGP_EINVAL, "tgp_gemm: rows_per_group must be >= 0");
     if (a->group_bias && a->rows_per_group <= 0) return fail(TGP_EINVAL, "tgp_gemm: rows_per_group must be positive");

@@ -157,17 +157,17 @@ __device__ __forceinline__ void vstore(const VDst& d, int row, float4 v) {
         *reinterpret_cast<float4*>(q) = hi;
         *reinterpret_cast<float4*>(q + d.lo) = lo;
     } else if (d.kind == 4) {
-        mixed_store4(reinterpret_cast<uint16_t*>(d.p + row * d.rs - d.rel), d.lo, d.rel, v);
+        mixed_store4_cs(reinterpret_cast<uint16_t*>(d.p + row * d.rs - d.rel), d.lo, d.rel, v);
     }
 }
 
-// LEAN (host-checked: no residual, no per-cloud bias, no column-max segment, segments do not overlap): the epilogue of the
+// LEAN (host-checked: no residual, no per-cloud bias, segments do not overlap): the epilogue of the
 // projection / head GEMMs that only add a bias, optionally apply the BatchNorm affine + activation and write ONE
 // destination per column -- ~4x fewer instructions per chunk than the general path, which matters because only 8 epilogue
 // warps are resident and the K = 128..256 encoder GEMMs are bound by exactly this code.
 template <bool LEAN>
 __device__ __forceinline__ void epi_chunk_vec(const tgp_gemm_args& g, uint32_t stg_addr, const uint32_t (&r)[32], int lane,
-                                              long row0, int nrows, int colbase, long grp0, int gb_switch, long zoff) {
+                                              long row0, int nrows, int colbase, long grp0, int gb_switch, long zoff, int dbg = 0) {
     // stage: thread = row writes its 32 columns as 8 float4, slot j ^ (row & 7) of its 128-byte line
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -225,7 +225,7 @@ __device__ __forceinline__ void epi_chunk_vec(const tgp_gemm_args& g, uint32_t s
         }
     }
     float4 mx0 = make_float4(-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F), mx1 = mx0;
-    const bool any_max = !LEAN && (d0.kind == 3 || d1.kind == 3);
+    const bool any_max = d0.kind == 3 || (!LEAN && d1.kind == 3);
     const bool has_act = g.scale != nullptr || g.neg_slope != nullptr || g.relu != 0;       // warp-uniform
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
@@ -246,7 +246,11 @@ __device__ __forceinline__ void epi_chunk_vec(const tgp_gemm_args& g, uint32_t s
                         v.x = act1(v.x, sc.x, sh.x, sl.x); v.y = act1(v.y, sc.y, sh.y, sl.y);
                         v.z = act1(v.z, sc.z, sh.z, sl.z); v.w = act1(v.w, sc.w, sh.w, sl.w);
                     }
-                    vstore(d0, row, v);
+                    if (d0.kind == 3) {            // per-cloud column max: nothing is stored, the running maxima go out below
+                        float4& m = row >= gb_switch ? mx1 : mx0;
+                        m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
+                    } else if (!(dbg & 8)) vstore(d0, row, v);
+                    else if (v.x == 1.2345e33f) d0.p[0] = v.y;       // (profiling switch: keep the arithmetic, drop the stores)
                 }
             }
             continue;
@@ -279,7 +283,7 @@ __device__ __forceinline__ void epi_chunk_vec(const tgp_gemm_args& g, uint32_t s
             }
         }
     }
-    if (!LEAN && __any_sync(0xffffffffu, any_max)) {
+    if (__any_sync(0xffffffffu, any_max)) {
         // combine the 4 row sub-groups (lanes differing in bits 3, 4), then one atomicMax per column and group
 #pragma unroll
         for (int o = 8; o <= 16; o <<= 1) {
@@ -289,7 +293,7 @@ __device__ __forceinline__ void epi_chunk_vec(const tgp_gemm_args& g, uint32_t s
             mx1.z = fmaxf(mx1.z, __shfl_xor_sync(0xffffffffu, mx1.z, o)); mx1.w = fmaxf(mx1.w, __shfl_xor_sync(0xffffffffu, mx1.w, o));
         }
         if (any_max && live && rsub == 0 && nrows > 0) {
-            const VDst& dm = d0.kind == 3 ? d0 : d1;
+            const VDst& dm = (LEAN || d0.kind == 3) ? d0 : d1;
             int* cell = reinterpret_cast<int*>(dm.p);
             atomicMax(cell, enc_ordered(mx0.x)); atomicMax(cell + 1, enc_ordered(mx0.y));
             atomicMax(cell + 2, enc_ordered(mx0.z)); atomicMax(cell + 3, enc_ordered(mx0.w));
@@ -367,7 +371,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                 tma_load_2d(sa, &tmA16, 0, (int)(((long)a_part * nblk + k64) * RA + m0), full + stage);
                                 tma_load_2d(sa + TC_A_BYTES, &tmB16, 0, (int)(((long)b_part * nblk + k64) * RB + n0), full + stage);
                             } else {
-                                tma_load_2d(sa, &tmA16, a_part * Kp + k64 * 64, m0, full + stage);
+                                // (grouped contraction: the n-tile's group selects a Kp-wide column block of a wider A operand)
+                                const int a_col = g.a_group_cols > 0 ? a_part * g.a_kp + (n0 / g.a_group_cols) * Kp : a_part * Kp;
+                                tma_load_2d(sa, &tmA16, a_col + k64 * 64, m0, full + stage);
                                 tma_load_2d(sa + TC_A_BYTES, &tmB16, b_part * Kp + k64 * 64, n0, full + stage);
                             }
                             if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
@@ -486,7 +492,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                 __syncwarp();
                 if (vec_ok == 2 && !(dbg & 1)) {
-                    epi_chunk_vec<true>(g, stg_addr, r, lane, row0, nrows, n0 + c0, grp0, gb_switch, z * zstride);
+                    epi_chunk_vec<true>(g, stg_addr, r, lane, row0, nrows, n0 + c0, grp0, gb_switch, z * zstride, dbg);
                     continue;
                 }
                 if (vec_ok && !gb_slow && !(dbg & 1)) {
@@ -813,7 +819,10 @@ static int launch_tc(const tgp_gemm_args* a, cudaStream_t st, int ksplit = 1, in
             rc = tgp_make_map_bf16_blocked(&tmB16, a->B_split, 3 * nblk * (((long)a->Ncols + 255) / 256 * 256), BN);
             if (rc) return rc;
         } else {
-            rc = tgp_make_map_bf16(&tmA16, a->A_split, a->M, Kp, TC_BM);
+            if (a->a_group_cols > 0 && (a->a_group_cols % 256 || a->a_kp < Kp || a->a_kp % 64 || a->K % 64 ||
+                                        (long)((a->Ncols + a->a_group_cols - 1) / a->a_group_cols) * Kp > a->a_kp || ksplit != 1))
+                return fail(TGP_EINVAL, "tgp_gemm: bad grouped-contraction arguments");
+            rc = tgp_make_map_bf16(&tmA16, a->A_split, a->M, a->a_group_cols > 0 ? a->a_kp : Kp, TC_BM);
             if (rc) return rc;
             rc = tgp_make_map_bf16(&tmB16, a->B_split, a->Ncols, Kp, BN);
             if (rc) return rc;
@@ -856,10 +865,9 @@ static int launch_tc(const tgp_gemm_args* a, cudaStream_t st, int ksplit = 1, in
         else vec_ok = vec_ok && sg.ld % 4 == 0 && ((sg.mode != 2 && sg.mode != 4) || sg.slab_width % 4 == 0);
     }
     if (vec_ok && !a->res1 && !a->res2 && !a->group_bias) {
-        // lean epilogue: one destination per column (segments disjoint), no column-max cells
+        // lean epilogue: one destination per column (segments disjoint; raw / slab / split / mixed / column max)
         bool lean = true;
         for (int s = 0; s < a->nseg && lean; ++s) {
-            if (a->seg[s].mode == 3) lean = false;
             for (int t = 0; t < s && lean; ++t)
                 if (a->seg[s].col_begin < a->seg[t].col_end && a->seg[t].col_begin < a->seg[s].col_end) lean = false;
         }

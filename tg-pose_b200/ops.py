@@ -277,7 +277,7 @@ PARAM_CACHE = ParamCache()
 
 def gemm(A, Bmat, b_is_nk, segs, bias=None, group_bias=None, rows_per_group=0, res1=None, res2=None,
          scale=None, shift=None, relu=False, K=None, Ncols=None, A_split=None, B_split=None, neg_slope=None, tc=None,
-         mixed=False):
+         mixed=False, a_kp=0, a_group_cols=0):
     """C = A @ B (+ epilogue) written to `segs` = [(col_begin, col_end, tensor, mode, slab_width)].
     A: (M,K) with unit column stride; Bmat: (K,Ncols) or, if b_is_nk, (Ncols,K); both may be row-strided views."""
     assert Bmat.stride(-1) == 1
@@ -308,6 +308,7 @@ def gemm(A, Bmat, b_is_nk, segs, bias=None, group_bias=None, rows_per_group=0, r
     if A_split is not None and B_split is not None:
         a.A_split, a.B_split = A_split.data_ptr(), B_split.data_ptr()
     a.mixed = 1 if mixed else 0
+    a.a_kp, a.a_group_cols = int(a_kp), int(a_group_cols)      # block-diagonal contraction (tgp_gemm_args.a_group_cols)
     if mixed:
         assert A_split is not None and B_split is not None, "mixed operands must be supplied (split_mixed / mode-4 epilogue)"
     a.M, a.K, a.Ncols = M, K, Ncols

@@ -314,6 +314,9 @@ class PoseNet9D(nn.Module):
                 b45d, b23d = self._packs["ph_l45"][1].double(), self._packs["ph_l23"][1].double()
                 wf = w1d @ w45d
                 self._packs["ph_fold"] = ((wf @ w23d).float().contiguous(), (wf @ b23d + w1d @ b45d).float().contiguous())
+                # conv2 of the three pose tails as ONE grouped contraction (each alone: 257 row tiles on 148 SMs)
+                self._packs["tails2"] = _Packed([g.conv2.weight, r.conv2.weight, t.conv2.weight],
+                                                [_fold(g.conv2, g.bn2), _fold(r.conv2, r.bn2), _fold(t.conv2, t.bn2)], [0.0, 0.0, 0.0])
                 for name, head in (("green", g), ("red", r), ("ts", t)):
                     sc, sh = _fold(head.conv3, head.bn3)
                     self._packs[name + "3"] = (head.conv3.weight.detach().reshape(256, 256), sc.contiguous(), sh.contiguous())
@@ -322,12 +325,24 @@ class PoseNet9D(nn.Module):
         return self._packs
 
     @staticmethod
-    def _stage(pk, x_split, K, outs, M, rows_per_group=0, **kw):
+    def _stage(pk, x_split, K, outs, M, rows_per_group=0, shared_split=False, **kw):
         """one fused GEMM: column blocks of pk.w go to `outs` = [(n_cols, 'raw'|'split'|'max')]; returns the tensors.
-        'max': per-cloud column max (torch.max over the points) taken in the epilogue, nothing else is written."""
+        'max': per-cloud column max (torch.max over the points) taken in the epilogue, nothing else is written.
+        shared_split: the 'split' outputs (all of one width n) are written side by side into ONE mixed operand of width
+        n_split * n, the A operand of a grouped contraction (tgp_gemm_args.a_group_cols); that operand is returned for each."""
         segs, res, c0 = [], [], 0
         dev = x_split.device
+        shared, n_sh, j_sh = None, sum(1 for _, kd in outs if kd == "split"), 0
         for n, kind in outs:
+            if kind == "split" and shared_split:
+                if shared is None:
+                    shared = ops.mixed_buf(M, n_sh * n, dev)
+                # column block j of the shared operand: 16-bit slot offset j*n = float offset j*n/2; slab width = operand Kp
+                segs.append((c0, c0 + n, shared[:, j_sh * n // 2:], 4, ops.mixed_kpad(n_sh * n)))
+                j_sh += 1
+                res.append(shared)
+                c0 += n
+                continue
             if kind == "raw":
                 t_ = torch.empty((M, n), dtype=torch.float32, device=dev)
                 segs.append((c0, c0 + n, t_, 0, 0))
@@ -359,8 +374,10 @@ class PoseNet9D(nn.Module):
         raw, xs = ops.concat_rows(src, B, N, want_raw=self.train_outputs, want_split=True, mixed=True)
         # stage 1: four 1286/1289 -> 1024 convolutions as one contraction over the shared operand; conv_5's output is
         # only ever max-pooled over the cloud (FaceRecon.py:145-146), so that pooling happens in the epilogue
-        hg, hr, f5max, ht = self._stage(pk["stage1"], xs, kin, [(1024, "split"), (1024, "split"), (1024, "max"),
-                                                                 (1024, "split")], M, rows_per_group=N)
+        # (the three 1024-wide hidden activations of the pose tails land side by side in one operand: their conv2 layers
+        # run as one grouped contraction below)
+        hid, _, f5max, _ = self._stage(pk["stage1"], xs, kin, [(1024, "split"), (1024, "split"), (1024, "max"),
+                                                                (1024, "split")], M, rows_per_group=N, shared_split=True)
         # The three pose tails and the decoder chain are independent after stage 1.  Each of their GEMMs has 257 row tiles
         # for 148 SMs (a 1.7-wave tail), so they are issued on forked streams: the persistent CTAs of one kernel that finish
         # early free their SMs for the next kernel's CTAs.  Under CUDA-graph capture the forks become parallel branches.
@@ -397,28 +414,30 @@ class PoseNet9D(nn.Module):
         last = dec.recon_head[3]
         recon = ops.linear_nk(d4, last.weight.reshape(3, 128), bias=last.bias).view(B, N, 3)
 
-        def tail(name, hidden_split):
-            # conv2 + bn2 + relu, max over the points in the epilogue (PoseR.py:32-33); conv3 + bn3 + relu; conv4
-            (hm,) = self._stage(pk[name + "2"], hidden_split, 1024, [(256, "max")], M, rows_per_group=N)
-            w3, sc3, sh3 = pk[name + "3"]
-            v = ops.linear_nk(ops.decode_max(hm), w3, scale=sc3, shift=sh3, relu=True, tc=False)
-            w4, b4 = pk[name + "4"]
-            return ops.linear_nk(v, w4, bias=b4, tc=False)
+        def tails():
+            # conv2 + bn2 + relu of the three tails with the max over the points in the epilogue (PoseR.py:32-33), one grouped
+            # launch; then per tail conv3 + bn3 + relu and conv4 on the per-cloud skinny kernel
+            Bc = M // N
+            hm = torch.full((Bc, 768), -2 ** 31, dtype=torch.int32, device=hid.device)
+            p2 = pk["tails2"]
+            ops.gemm(None, p2.w, True, [(0, 768, hm, 3, 0)], scale=p2.scale, shift=p2.shift, neg_slope=p2.slope, K=1024,
+                     A_split=hid, B_split=p2.w_split, rows_per_group=N, mixed=True, a_kp=ops.mixed_kpad(3072), a_group_cols=256)
+            pooled3 = ops.decode_max(hm)
+            outs = []
+            for j, name in enumerate(("green", "red", "ts")):
+                w3, sc3, sh3 = pk[name + "3"]
+                v = ops.linear_nk(pooled3[:, 256 * j:256 * (j + 1)], w3, scale=sc3, shift=sh3, relu=True, tc=False)
+                w4, b4 = pk[name + "4"]
+                outs.append(ops.linear_nk(v, w4, bias=b4, tc=False))
+            return outs
 
         self._last_recon = recon          # (tests) the reference computes recon in inference too but only returns it with FLAGS.train
         if side is not None:
             with torch.cuda.stream(side[0]):
-                green_R_vec = tail("green", hg)
-            with torch.cuda.stream(side[1]):
-                red_R_vec = tail("red", hr)
-            with torch.cuda.stream(side[2]):
-                ts_vec = tail("ts", ht)
-            for st in side:
-                main.wait_stream(st)
+                green_R_vec, red_R_vec, ts_vec = tails()
+            main.wait_stream(side[0])
         else:
-            green_R_vec = tail("green", hg)
-            red_R_vec = tail("red", hr)
-            ts_vec = tail("ts", ht)
+            green_R_vec, red_R_vec, ts_vec = tails()
         feat = feat_global = None
         if self.train_outputs:
             feat = raw.view(B, N, kin)[:, :, :FEAT_C]
