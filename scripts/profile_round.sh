@@ -24,8 +24,8 @@ ncu --section SpeedOfLight --section MemoryWorkloadAnalysis --section ComputeWor
 ncu -i /tmp/${R}_forward.ncu-rep --page raw --csv > $O/${R}_forward_raw.csv
 tail -2 $O/${R}_ncu_forward.log
 if [ "${2:-all}" = "fwdonly" ]; then exit 0; fi
-# 3. the dominant kernel (tcgen05 GEMM), full set with source correlation: the 17 launches of one forward
+# 3. the dominant kernel (tcgen05 GEMM), full set with source correlation: the 15 launches of one forward
 python scripts/profile_forward.py > $O/${R}_plain_fwd2.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:"^gemm_tc" -s 34 -c 17 -o $O/${R}_gemm_tc -f \
+ncu --set full --clock-control none --import-source on -k regex:"^gemm_tc" -s 30 -c 15 -o $O/${R}_gemm_tc -f \
     python scripts/profile_forward.py > $O/${R}_ncu_gemm.log 2>&1
 tail -2 $O/${R}_ncu_gemm.log
