@@ -414,30 +414,39 @@ class PoseNet9D(nn.Module):
         last = dec.recon_head[3]
         recon = ops.linear_nk(d4, last.weight.reshape(3, 128), bias=last.bias).view(B, N, 3)
 
-        def tails():
-            # conv2 + bn2 + relu of the three tails with the max over the points in the epilogue (PoseR.py:32-33), one grouped
-            # launch; then per tail conv3 + bn3 + relu and conv4 on the per-cloud skinny kernel
+        def tails_pool():
+            # conv2 + bn2 + relu of the three tails with the max over the points in the epilogue (PoseR.py:32-33): one grouped launch
             Bc = M // N
             hm = torch.full((Bc, 768), -2 ** 31, dtype=torch.int32, device=hid.device)
             p2 = pk["tails2"]
             ops.gemm(None, p2.w, True, [(0, 768, hm, 3, 0)], scale=p2.scale, shift=p2.shift, neg_slope=p2.slope, K=1024,
                      A_split=hid, B_split=p2.w_split, rows_per_group=N, mixed=True, a_kp=ops.mixed_kpad(3072), a_group_cols=256)
-            pooled3 = ops.decode_max(hm)
-            outs = []
-            for j, name in enumerate(("green", "red", "ts")):
-                w3, sc3, sh3 = pk[name + "3"]
-                v = ops.linear_nk(pooled3[:, 256 * j:256 * (j + 1)], w3, scale=sc3, shift=sh3, relu=True, tc=False)
-                w4, b4 = pk[name + "4"]
-                outs.append(ops.linear_nk(v, w4, bias=b4, tc=False))
-            return outs
+            return ops.decode_max(hm)
+
+        def tail_fc(pooled3, j, name):
+            # conv3 + bn3 + relu and conv4 of one tail on the per-cloud skinny kernel
+            w3, sc3, sh3 = pk[name + "3"]
+            v = ops.linear_nk(pooled3[:, 256 * j:256 * (j + 1)], w3, scale=sc3, shift=sh3, relu=True, tc=False)
+            w4, b4 = pk[name + "4"]
+            return ops.linear_nk(v, w4, bias=b4, tc=False)
 
         self._last_recon = recon          # (tests) the reference computes recon in inference too but only returns it with FLAGS.train
+        names = ("green", "red", "ts")
         if side is not None:
             with torch.cuda.stream(side[0]):
-                green_R_vec, red_R_vec, ts_vec = tails()
-            main.wait_stream(side[0])
+                pooled3 = tails_pool()
+            side[1].wait_stream(side[0])
+            side[2].wait_stream(side[0])
+            vecs = []
+            for j, name in enumerate(names):      # the three short per-cloud chains run side by side
+                with torch.cuda.stream(side[j]):
+                    vecs.append(tail_fc(pooled3, j, name))
+            for st in side:
+                main.wait_stream(st)
         else:
-            green_R_vec, red_R_vec, ts_vec = tails()
+            pooled3 = tails_pool()
+            vecs = [tail_fc(pooled3, j, name) for j, name in enumerate(names)]
+        green_R_vec, red_R_vec, ts_vec = vecs
         feat = feat_global = None
         if self.train_outputs:
             feat = raw.view(B, N, kin)[:, :, :FEAT_C]
