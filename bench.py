@@ -367,7 +367,7 @@ def run_train(args):
     B = gb // world
     torch.manual_seed(0)
     net = PoseNet9D(train_outputs=True).to(dev)
-    step = TrainStep(net)
+    step = TrainStep(net, optimizer=args.optimizer)
     sets = []
     for s_ in range(2):
         pts, cat = synth_inputs(B, 4321 + 17 * rank + s_)
@@ -418,7 +418,7 @@ def run_train(args):
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": "RL_TDA training step: PoseNet9D fwd+bwd, chamfer3D/DCD recon loss, gradient "
-                                       "all-reduce, clip, Adam; global batch 256 x 1028 points",
+                                       f"all-reduce, clip, {args.optimizer} step; global batch 256 x 1028 points",
                            "points": N_PTS, "global_batch": gb, "per_gpu_batch": B, "parallelism": f"dp{world}",
                            "l2": "per-step working set (> 1 GB of activations) exceeds the 126 MB L2"},
                 "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": B * (N_PTS * 3 + 1) * 4, "d2h_bytes_per_step": 4},
@@ -627,6 +627,8 @@ def main():
     ap.add_argument("--mode", default="infer", choices=["infer", "train", "micro"],
                     help="infer: BASELINE.json configs[1] (the headline); train: configs[2], a secondary line")
     ap.add_argument("--train-batch", type=int, default=256, help="global batch of the training step")
+    ap.add_argument("--optimizer", default="ranger", choices=["ranger", "adam"],
+                    help="--mode train: the reference's Ranger (fused kernels) or torch's fused Adam")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -240,12 +240,13 @@ int tgp_chamfer_bwd(const float* xyz1, const float* xyz2, const float* graddist1
                     const int32_t* idx1, const int32_t* idx2, int B, int n, int m,
                     float* gradxyz1, float* gradxyz2, tgp_stream_t stream);
 
-/* calc_dcd, losses/TDA_loss_sym_recon.py:411-450 (non_reg=False), on the outputs of tgp_chamfer_fwd:
+/* calc_dcd, losses/TDA_loss_sym_recon.py:411-450, on the outputs of tgp_chamfer_fwd (frac = n/m resp. m/n; non_reg != 0
+ * clamps both to >= 1, :418-420):
  * loss (B) = mean_i(1 - exp(-alpha d1_i) w1_i) + 0.5 mean_j(1 - exp(-alpha d2_j) w2_j) with the bincount weights
  * w = (count[idx]^n_lambda + 1e-6)^-1 * frac built in shared memory (replaces the reference's Python loop over
  * the batch with torch.bincount).  coef1 (B,n) / coef2 (B,m), optional: d loss[b] / d dist (weights detached). */
 int tgp_dcd(const float* dist1, const float* dist2, const int32_t* idx1, const int32_t* idx2, int B, int n, int m,
-            float alpha, float n_lambda, float* loss, float* coef1, float* coef2, tgp_stream_t stream);
+            float alpha, float n_lambda, int non_reg, float* loss, float* coef1, float* coef2, tgp_stream_t stream);
 
 /* ------------------------------------------------------------------ backward (SURVEY 8a', north_star item 5)
  * The reference has no hand-written backward for gcn3d: torch autograd differentiates the graph built by
@@ -335,6 +336,47 @@ int tgp_bn_bwd(const float* dy, long ld_dy, const float* y, long ld_y, const flo
                float slope, long M, int C,
                float* dz, long ld_dz, float* dz_mixed, float* dbeta, float* dgamma,
                void* workspace, size_t workspace_bytes, tgp_stream_t stream);
+
+/* ------------------------------------------------------------------ optimiser step
+ * trainer/RL_TDA.py:223-224: torch.nn.utils.clip_grad_norm_(net1.parameters(), 5); optimizer.step() with
+ * optimizer = Ranger (tools/torch_utils/solver/ranger2020.py:44-235: RAdam + Lookahead + gradient centralisation,
+ * gc_loc = True).  Parameters, gradients, exp_avg, exp_avg_sq and the Lookahead slow copy are five flat fp32 arenas
+ * with identical element offsets; the row table says how they are cut. */
+
+/* `len` consecutive elements from element `off` of every arena, belonging to parameter tensor `tensor`.
+ * gc != 0: the row is a dim-0 slice of a centralised tensor and its mean is removed from the gradient
+ * (centralized_gradient, ranger2020.py:31-41); gc == 0: a piece of a tensor that is not centralised. */
+typedef struct {
+    long long off;
+    int len;
+    int gc;
+    int tensor;
+    int pad_;
+} tgp_ranger_row;
+
+/* per-step scalars, computed by the host as ranger2020.py:179-201 does */
+typedef struct {
+    float beta1, beta2, eps, weight_decay;
+    float one_minus_beta1, one_minus_beta2;   /* rounded from the host's doubles like the `alpha=` / `value=` of :174,177
+                                                 (1.f - beta2 in fp32 would be off by 5e-5 relative) */
+    float neg_step;     /* -(step_size * lr), rounded from double like the `alpha=` of p.add_ (:220) */
+    int rectified;      /* N_sma > N_sma_threshhold (:208): divide by sqrt(exp_avg_sq) + eps */
+    int lookahead;      /* step % k == 0 (:225) */
+    float la_alpha;     /* Lookahead interpolation factor */
+    float max_norm;     /* > 0: gradients are scaled by min(1, max_norm / (total_norm + 1e-6)) as clip_grad_norm_ does */
+} tgp_ranger_hyper;
+
+/* pass 1: row_sum[r] = sum of row r's gradient (all n_rows rows), *sumsq = sum of squares of every active element
+ * (zeroed by the call).  active_dev (optional, int per tensor): 0 = the tensor has no gradient this step. */
+int tgp_ranger_reduce(const float* grads, const tgp_ranger_row* rows_dev, int n_rows, const int* active_dev,
+                      float* row_sum, double* sumsq, tgp_stream_t stream);
+
+/* pass 2 over rows [row_begin, row_end) (one call per parameter group): g' = clip * (g - mean_row); moments; RAdam
+ * step; Lookahead.  sumsq may be NULL when max_norm <= 0; total_norm (optional, device float) = sqrt(*sumsq). */
+int tgp_ranger_update(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, float* slow,
+                      const tgp_ranger_row* rows_dev, int row_begin, int row_end, const int* active_dev,
+                      const float* row_sum, const double* sumsq, const tgp_ranger_hyper* hyper_host,
+                      float* total_norm, tgp_stream_t stream);
 
 #ifdef __cplusplus
 }

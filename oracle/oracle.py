@@ -206,11 +206,13 @@ def calc_cd(d1, d2):
     return cd_p.astype(np.float32), cd_t.astype(np.float32)
 
 
-def calc_dcd(d1, d2, i1, i2, alpha=70.0, n_lambda=0.3):
-    """TDA_loss_sym_recon.py:411-450 (non_reg=False): per-cloud density-aware chamfer loss."""
+def calc_dcd(d1, d2, i1, i2, alpha=70.0, n_lambda=0.3, non_reg=False):
+    """TDA_loss_sym_recon.py:411-450: per-cloud density-aware chamfer loss (non_reg: ratios clamped to >= 1, :418-420)."""
     B, n = d1.shape
     m = d2.shape[1]
     frac_12, frac_21 = n / m, m / n
+    if non_reg:
+        frac_12, frac_21 = max(1, frac_12), max(1, frac_21)
     out = np.empty(B, np.float32)
     for b in range(B):
         c1 = np.bincount(i1[b], minlength=m)
@@ -525,3 +527,59 @@ def hs_layer_backward(p, xyz, fm, k, idx, idx_orl, G):
              "STE_layer.weight": np.einsum("bno,bni->oi", G64, fm64).reshape(C, cin, 1).astype(np.float32),
              "conv2.weight": d_conv2}
     return d_fm.astype(np.float32), grads
+
+
+# ----------------------------------------------------------------------------- optimiser step
+def clip_coef(grads, max_norm):
+    """torch.nn.utils.clip_grad_norm_ (trainer/RL_TDA.py:223): total 2-norm over all tensors, coefficient
+    max_norm / (total + 1e-6) clamped to 1.  Returns (total_norm, coefficient)."""
+    total = np.sqrt(sum(float(np.sum(g.astype(np.float64) ** 2)) for g in grads))
+    return total, min(1.0, max_norm / (total + 1e-6))
+
+
+def radam_scalars(step, beta1, beta2, threshold):
+    """tools/torch_utils/solver/ranger2020.py:183-201 -> (N_sma > threshold, step_size), double arithmetic like the
+    reference's Python floats."""
+    beta2_t = beta2 ** step
+    n_max = 2 / (1 - beta2) - 1
+    n_sma = n_max - 2 * step * beta2_t / (1 - beta2_t)
+    if n_sma > threshold:
+        step_size = np.sqrt((1 - beta2_t) * (n_sma - 4) / (n_max - 4) * (n_sma - 2) / n_sma * n_max / (n_max - 2)) \
+            / (1 - beta1 ** step)
+        return True, float(step_size)
+    return False, 1.0 / (1 - beta1 ** step)
+
+
+def ranger_step(state, grads, lr=1e-3, alpha=0.5, k=6, threshold=5, betas=(0.95, 0.999), eps=1e-5, weight_decay=0.0,
+                use_gc=True, gc_conv_only=False, max_norm=None):
+    """One clip_grad_norm_ + Ranger.step() (ranger2020.py:133-235, gc_loc=True) in float32 numpy.
+    state: {"step": int, "p": [...], "m": [...], "v": [...], "slow": [...]} updated in place; returns the total norm."""
+    f = np.float32
+    total, coef = clip_coef(grads, max_norm) if max_norm else (0.0, 1.0)
+    state["step"] += 1
+    t = state["step"]
+    rect, step_size = radam_scalars(t, betas[0], betas[1], threshold)
+    for i, g in enumerate(grads):
+        g = (g * f(coef)).astype(f) if max_norm else g.astype(f)
+        if use_gc and g.ndim > (3 if gc_conv_only else 1):                       # centralized_gradient :31-41
+            g = g - g.mean(axis=tuple(range(1, g.ndim)), keepdims=True, dtype=f)
+        p, m, v = state["p"][i], state["m"][i], state["v"][i]
+        v *= f(betas[1])
+        v += f(1 - betas[1]) * g * g                                               # :174
+        m *= f(betas[0])
+        m += f(1 - betas[0]) * g                                                   # :177
+        G = m / (np.sqrt(v) + f(eps)) if rect else m                               # :208-212 (`G_grad = exp_avg`: an ALIAS)
+        if weight_decay != 0:
+            G += f(weight_decay) * p        # :214-215, in place: on un-rectified steps this also lands in exp_avg
+        p += f(-step_size * lr) * G                                                # :220
+        if t % k == 0:                                                             # :225-231
+            slow = state["slow"][i]
+            slow += f(alpha) * (p - slow)
+            p[...] = slow
+    return total
+
+
+def ranger_init(params):
+    """state as ranger2020.py:155-165 creates it on the first step."""
+    return {"step": 0, "p": [np.array(p, np.float32) for p in params], "m": [np.zeros_like(p, np.float32) for p in params],
+            "v": [np.zeros_like(p, np.float32) for p in params], "slow": [np.array(p, np.float32) for p in params]}

@@ -421,11 +421,56 @@ def backward_cases():
     save("face_enc_bwd", **o2)
 
 
+def ranger_case():
+    """tools/torch_utils/solver/ranger2020.py (Ranger :44-235: RAdam + Lookahead + gradient centralisation) behind
+    torch.nn.utils.clip_grad_norm_(params, 5) -- the two calls that close a training step (trainer/RL_TDA.py:223-224).
+    Parameter shapes follow the path's modules: Conv1d weights (out, in, 1), HS_layer weights (in, (S+1) out),
+    directions (3, S out), biases / BatchNorm vectors (1-D: no centralisation).  9 steps: both RAdam branches
+    (N_sma crosses the threshold 5 at step 6) and one Lookahead interpolation (k = 6)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location(
+        "ref_ranger2020", os.path.join(REF, "tools", "torch_utils", "solver", "ranger2020.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    g = torch.Generator().manual_seed(77)
+    shapes = [(128, 3, 1), (3, 7 * 16), (16, 8 * 16), (8 * 16,), (32, 37, 1), (32,), (5, 3), (1,), (3, 1030), (2, 3, 5, 1)]
+    steps = 9
+    snaps = (0, 3, 5, 8)                      # parameter snapshots after steps 1, 4, 6, 9
+    out = {"n_tensors": np.int64(len(shapes)), "steps": np.int64(steps), "snaps": np.asarray(snaps, np.int64)}
+    p0 = [torch.randn(*s, generator=g) * 0.3 for s in shapes]
+    # gradient scales chosen so that the clip is active on some steps (total norm > 5) and inactive on others
+    scales = [0.02, 3.0, 0.05, 4.0, 0.01, 0.5, 2.5, 0.03, 0.2]
+    grads = [[torch.randn(*s, generator=g) * scales[t] for s in shapes] for t in range(steps)]
+    for i, t0 in enumerate(p0):
+        out[f"p0_{i}"] = np_(t0)
+    for t in range(steps):
+        for i in range(len(shapes)):
+            out[f"g_{t}_{i}"] = np_(grads[t][i])
+    for tag, kw in (("default", dict(lr=1e-3)),
+                    ("wd_convonly", dict(lr=3e-3, weight_decay=0.01, gc_conv_only=True, betas=(0.9, 0.99), k=4, alpha=0.3)),
+                    ("nogc", dict(lr=1e-2, use_gc=False, eps=1e-8))):
+        params = [torch.nn.Parameter(t0.clone()) for t0 in p0]
+        opt = mod.Ranger(params, **kw)
+        norms = []
+        for t in range(steps):
+            for p_, g_ in zip(params, grads[t]):
+                p_.grad = g_.clone()
+            norms.append(float(torch.nn.utils.clip_grad_norm_(params, 5)))
+            opt.step()
+            if t in snaps:
+                for i, p_ in enumerate(params):
+                    out[f"{tag}_p_{t}_{i}"] = np_(p_).copy()      # np_ aliases the parameter storage
+        out[f"{tag}_norms"] = np.asarray(norms, np.float64)
+        for i, p_ in enumerate(params):
+            st = opt.state[p_]
+            out[f"{tag}_m_{i}"] = np_(st["exp_avg"])
+            out[f"{tag}_v_{i}"] = np_(st["exp_avg_sq"])
+            out[f"{tag}_slow_{i}"] = np_(st["slow_buffer"])
+    save("ranger", **out)
+
+
 if __name__ == "__main__":
-    knn_cases()
-    gather_dir_cases()
-    conv_cases()
-    chamfer_cases()
-    face_enc_case()
-    posenet_case()
-    backward_cases()
+    cases = {"knn": knn_cases, "gather_dir": gather_dir_cases, "conv": conv_cases, "chamfer": chamfer_cases,
+             "face_enc": face_enc_case, "posenet": posenet_case, "backward": backward_cases, "ranger": ranger_case}
+    for name in (sys.argv[1:] or list(cases)):       # python make_golden.py [case ...]
+        cases[name]()

@@ -323,14 +323,29 @@ def test_dcd_vs_oracle(B, n, m):
     assert torch.isfinite(a.grad).all()
 
 
-def test_train_step_runs_and_learns():
+@pytest.mark.parametrize("B,n,m", [(3, 300, 100), (2, 64, 257)])
+def test_dcd_non_reg_vs_oracle(B, n, m):
+    """calc_dcd(non_reg=True): both point-count ratios clamped to >= 1 (TDA_loss_sym_recon.py:418-420)."""
+    from tgpose_b200.dist_chamfer_3D import calc_dcd
+    g = torch.Generator().manual_seed(n * 7 + m)
+    a = (torch.rand(B, n, 3, generator=g) * 0.3).cuda()
+    b = (torch.rand(B, m, 3, generator=g) * 0.3).cuda()
+    loss, d1, d2, i1, i2 = calc_dcd(a, b, alpha=40, n_lambda=0.5, return_raw=True, non_reg=True)
+    ref = orc.calc_dcd(nump(d1), nump(d2), nump(i1), nump(i2), alpha=40.0, n_lambda=0.5, non_reg=True)
+    assert_close(nump(loss), ref, what="calc_dcd non_reg")
+    plain = calc_dcd(a, b, alpha=40, n_lambda=0.5)
+    assert float((plain - loss).abs().max()) > 1e-4        # the clamp changes the result when n != m
+
+
+@pytest.mark.parametrize("optimizer", ["ranger", "adam"])
+def test_train_step_runs_and_learns(optimizer):
     """the synthetic RL_TDA step (train_step.py): finite loss, every trainable parameter that is on the path gets a
     finite gradient, and a few steps on one fixed batch reduce the loss."""
     from tgpose_b200.posenet import PoseNet9D
     from tgpose_b200.train_step import TrainStep, synthetic_targets
     torch.manual_seed(0)
     net = PoseNet9D(train_outputs=True).cuda()
-    step = TrainStep(net, lr=2e-4)
+    step = TrainStep(net, lr=2e-4, optimizer=optimizer)
     gen = torch.Generator().manual_seed(3)
     pts = (torch.rand(4, 256, 3, generator=gen) - 0.5) * 0.3 + torch.tensor([0.1, -0.1, 1.0])
     cat = torch.randint(0, 6, (4, 1), generator=gen).float()

@@ -102,3 +102,59 @@ def test_pool_consumes_cpu_rng_like_reference():
     assert torch.equal(torch.randperm(32), c)
     g = np.load(os.path.join(ROOT, "tests", "golden", "convs.npz"))
     assert np.array_equal(b.numpy().astype(np.int16), g["p_perm"])
+
+
+# ----------------------------------------------------------------------------------------- optimiser host logic
+def test_ranger_struct_layouts_match_header():
+    from tgpose_b200 import _lib, ranger
+    # tgp_ranger_hyper: 7 floats, 2 ints, 2 floats; tgp_ranger_row: long long + 4 ints
+    assert ctypes.sizeof(_lib.RangerHyper) == 44
+    assert _lib.RangerHyper.neg_step.offset == 24 and _lib.RangerHyper.rectified.offset == 28
+    assert _lib.RangerHyper.max_norm.offset == 40
+    rec = ranger._pack_rows(np.asarray([[64, 5, 1, 2]], np.int64))
+    assert rec.dtype.itemsize == 24 and rec.tobytes()[:8] == (64).to_bytes(8, "little")
+    assert int.from_bytes(rec.tobytes()[8:12], "little") == 5 and int.from_bytes(rec.tobytes()[16:20], "little") == 2
+
+
+def test_ranger_row_table():
+    """centralised tensors: one row per dim-0 slice (ranger2020.py:31-41); the rest: <= 4096-element pieces; every
+    tensor starts on a 128-byte boundary; rows are disjoint and cover every element exactly once."""
+    from tgpose_b200.ranger import ALIGN, ROW_PIECE, build_row_table
+    shapes = [(128, 3, 1), (3, 896), (10001,), (), (5,), (2, 3, 5, 1), (0,)]
+    offsets, total, rows = build_row_table(shapes)
+    assert all(o % ALIGN == 0 for o in offsets) and total % ALIGN == 0
+    cover = np.zeros(total, np.int32)
+    for off, ln, gc, t in rows:
+        cover[off:off + ln] += 1
+        numel = int(np.prod(shapes[t])) if shapes[t] else 1
+        assert offsets[t] <= off and off + ln <= offsets[t] + numel
+        assert gc == (1 if len(shapes[t]) > 1 else 0)
+        assert ln == (numel // shapes[t][0] if gc else min(ROW_PIECE, offsets[t] + numel - off))
+    for t, s in enumerate(shapes):
+        numel = int(np.prod(s)) if s else 1
+        assert (cover[offsets[t]:offsets[t] + numel] == 1).all()
+    assert cover.sum() == sum(int(np.prod(s)) if s else 1 for s in shapes)
+    assert (rows[:, 3] == np.sort(rows[:, 3])).all()            # parameter order -> contiguous row range per group
+    # gc_conv_only: only tensors with more than 3 dims are centralised; use_gc=False: none
+    _, _, r2 = build_row_table(shapes, gc_conv_only=True)
+    assert set(r2[r2[:, 2] == 1, 3]) == {5}
+    _, _, r3 = build_row_table(shapes, use_gc=False)
+    assert not r3[:, 2].any()
+
+
+def test_radam_scalars_match_oracle_and_cross_threshold():
+    from oracle import oracle as orc
+    from tgpose_b200.ranger import radam_scalars
+    seen = set()
+    for step in range(1, 40):
+        a, b = radam_scalars(step, 0.95, 0.999, 5), orc.radam_scalars(step, 0.95, 0.999, 5)
+        assert a[0] == b[0] and abs(a[1] - b[1]) <= 1e-12 * abs(b[1])
+        seen.add(a[0])
+    assert seen == {False, True}
+    assert radam_scalars(5, 0.95, 0.999, 5)[0] is False and radam_scalars(6, 0.95, 0.999, 5)[0] is True
+
+
+def test_ranger_has_no_cpu_path():
+    from tgpose_b200.ranger import Ranger
+    with pytest.raises(RuntimeError):
+        Ranger([torch.nn.Parameter(torch.zeros(4, 4))])

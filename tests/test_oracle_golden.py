@@ -196,3 +196,28 @@ def test_backward_oracle_vs_reference_autograd():
     idx4 = orc.knn_xyz(x, 4)
     df = orc.gather_max_backward(g["p_f"], idx4, g["p_G"], rows=perm[:32])
     assert_grad_close(df, g["p_df"], what="pool d_f")
+
+
+# ----------------------------------------------------------------------------------------- optimiser step
+RANGER_CONFIGS = {"default": dict(lr=1e-3),
+                  "wd_convonly": dict(lr=3e-3, weight_decay=0.01, gc_conv_only=True, betas=(0.9, 0.99), k=4, alpha=0.3),
+                  "nogc": dict(lr=1e-2, use_gc=False, eps=1e-8)}
+
+
+@pytest.mark.parametrize("tag", list(RANGER_CONFIGS))
+def test_ranger_oracle_vs_reference(tag):
+    """oracle.ranger_step against clip_grad_norm_(5) + the reference's Ranger.step() (ranger2020.py), 9 steps: both RAdam
+    branches, Lookahead, weight decay incl. the reference's exp_avg alias, gc_conv_only, no centralisation."""
+    z = golden("ranger")
+    n, steps = int(z["n_tensors"]), int(z["steps"])
+    st = orc.ranger_init([z[f"p0_{i}"] for i in range(n)])
+    for t in range(steps):
+        tot = orc.ranger_step(st, [z[f"g_{t}_{i}"] for i in range(n)], max_norm=5, **RANGER_CONFIGS[tag])
+        assert abs(tot - z[f"{tag}_norms"][t]) <= 1e-5 * tot
+        if t in z["snaps"]:
+            for i in range(n):
+                assert np.abs(st["p"][i] - z[f"{tag}_p_{t}_{i}"]).max() <= 2e-7, (tag, t, i)
+    for name in ("m", "v", "slow"):
+        for i in range(n):
+            ref = z[f"{tag}_{name}_{i}"]
+            assert np.abs(st[name][i] - ref).max() <= 2e-6 * (np.abs(ref).max() + 1e-30), (tag, name, i)

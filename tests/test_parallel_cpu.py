@@ -31,7 +31,9 @@ def _worker(rank, world, port, q):
     x = torch.full((2, 4), float(rank + 1))
     lin(x).sum().backward()
     nb = parallel.allreduce_gradients(lin.parameters(), world)
-    q.put((rank, lo, hi, perm[:8].tolist(), lin.weight.grad.clone(), lin.bias.grad.clone(), nb))
+    flat = torch.arange(10, dtype=torch.float32) * (rank + 1)          # a flat gradient arena (ranger.Ranger.flat_grads)
+    nflat = parallel.allreduce_flat(flat, world, bucket_bytes=16)       # 4-element slices -> 3 collectives
+    q.put((rank, lo, hi, perm[:8].tolist(), lin.weight.grad.clone(), lin.bias.grad.clone(), nb, flat, nflat))
     dist.destroy_process_group()
 
 
@@ -46,7 +48,8 @@ def test_two_rank_sharding_and_grad_allreduce():
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    (r0, lo0, hi0, perm0, gw0, gb0, nb0), (r1, lo1, hi1, perm1, gw1, gb1, nb1) = res
+    (r0, lo0, hi0, perm0, gw0, gb0, nb0, f0, nf0), (r1, lo1, hi1, perm1, gw1, gb1, nb1, f1, nf1) = res
+    assert nf0 == nf1 == 3 and torch.equal(f0, f1) and torch.allclose(f0, torch.arange(10, dtype=torch.float32) * 1.5)
     assert (lo0, hi0, lo1, hi1) == (0, 17, 17, 33)           # contiguous, disjoint, covering
     assert perm0 == perm1                                     # same Pool permutation on every rank
     # rank r: d/dW sum(lin(x)) = 2*(r+1) per entry; average over ranks = 3

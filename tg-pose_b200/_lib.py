@@ -36,6 +36,14 @@ class GemmArgs(ctypes.Structure):
                 ("A_split", c_void_p), ("B_split", c_void_p), ("mixed", c_int), ("a_kp", c_int), ("a_group_cols", c_int)]
 
 
+class RangerHyper(ctypes.Structure):
+    """tgp_ranger_hyper"""
+    _fields_ = [("beta1", ctypes.c_float), ("beta2", ctypes.c_float), ("eps", ctypes.c_float),
+                ("weight_decay", ctypes.c_float), ("one_minus_beta1", ctypes.c_float),
+                ("one_minus_beta2", ctypes.c_float), ("neg_step", ctypes.c_float), ("rectified", c_int),
+                ("lookahead", c_int), ("la_alpha", ctypes.c_float), ("max_norm", ctypes.c_float)]
+
+
 # name -> (restype, argtypes); must list every symbol include/tgpose_b200.h declares
 SIGNATURES = {
     "tgp_version": (c_int, []),
@@ -76,7 +84,7 @@ SIGNATURES = {
     "tgp_split_tf32_t": (c_int, [c_void_p, c_long, c_int, c_long, c_void_p, c_void_p]),
     "tgp_split_tf32_t_bytes": (c_size_t, [c_long, c_int]),
     "tgp_dcd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, ctypes.c_float, ctypes.c_float,
-                        c_void_p, c_void_p, c_void_p, c_void_p]),
+                        c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "tgp_act_bwd": (c_int, [c_void_p, c_long, c_void_p, c_long, c_void_p, c_int, c_long, c_int, c_void_p, c_long,
                             c_void_p]),
     "tgp_colsum_workspace": (c_size_t, [c_long, c_int, c_long]),
@@ -101,6 +109,9 @@ SIGNATURES = {
     "tgp_gemm_tn": (c_int, [c_void_p, c_long, c_void_p, c_long, c_long, c_int, c_int, c_void_p, c_long, c_void_p,
                             c_size_t, c_void_p]),
     "tgp_gemm_tn_tc_workspace": (c_size_t, [c_long, c_int, c_int]),
+    "tgp_ranger_reduce": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "tgp_ranger_update": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p,
+                                  c_void_p, c_void_p, ctypes.POINTER(RangerHyper), c_void_p, c_void_p]),
     "tgp_gemm_tn_tc": (c_int, [c_void_p, c_void_p, c_long, c_int, c_int, c_void_p, c_long, c_int, c_void_p, c_size_t,
                                c_void_p]),
 }

@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libtgpose_b200.so")
-SOURCES = ["capi.cu", "knn.cu", "gather.cu", "graph_conv.cu", "gemm_simt.cu", "gemm_tc.cu", "chamfer.cu", "backward.cu", "knn_tc.cu"]
+SOURCES = ["capi.cu", "knn.cu", "gather.cu", "graph_conv.cu", "gemm_simt.cu", "gemm_tc.cu", "chamfer.cu", "backward.cu", "knn_tc.cu", "optim.cu"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v"]
 

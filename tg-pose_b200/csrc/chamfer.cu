@@ -130,7 +130,7 @@ __global__ void chamfer_bwd_scatter_kernel(const float* __restrict__ xyz1, const
 constexpr int DCD_THREADS = 256;
 __global__ void __launch_bounds__(DCD_THREADS)
 dcd_kernel(const float* __restrict__ dist1, const float* __restrict__ dist2, const int32_t* __restrict__ idx1,
-           const int32_t* __restrict__ idx2, int n, int m, float alpha, float lambda, float* __restrict__ loss,
+           const int32_t* __restrict__ idx2, int n, int m, float alpha, float lambda, int non_reg, float* __restrict__ loss,
            float* __restrict__ coef1, float* __restrict__ coef2) {
     extern __shared__ int hist[];            // [m] counts of idx1 values, then [n] counts of idx2 values
     __shared__ float red[2][DCD_THREADS / 32];
@@ -142,7 +142,8 @@ dcd_kernel(const float* __restrict__ dist1, const float* __restrict__ dist2, con
     for (int i = threadIdx.x; i < n; i += DCD_THREADS) atomicAdd(c1 + __ldg(idx1 + b * n + i), 1);
     for (int j = threadIdx.x; j < m; j += DCD_THREADS) atomicAdd(c2 + __ldg(idx2 + b * m + j), 1);
     __syncthreads();
-    const float frac_12 = (float)n / (float)m, frac_21 = (float)m / (float)n;
+    float frac_12 = (float)n / (float)m, frac_21 = (float)m / (float)n;
+    if (non_reg) { frac_12 = fmaxf(1.f, frac_12); frac_21 = fmaxf(1.f, frac_21); }   // TDA_loss_sym_recon.py:418-420
     float s1 = 0.f, s2 = 0.f;
     for (int i = threadIdx.x; i < n; i += DCD_THREADS) {
         const float w = frac_21 / (powf((float)c1[__ldg(idx1 + b * n + i)], lambda) + 1e-6f);
@@ -200,8 +201,8 @@ extern "C" int tgp_chamfer_bwd(const float* xyz1, const float* xyz2, const float
 }
 
 extern "C" int tgp_dcd(const float* dist1, const float* dist2, const int32_t* idx1, const int32_t* idx2, int B, int n,
-                       int m, float alpha, float n_lambda, float* loss, float* coef1, float* coef2,
-                       tgp_stream_t stream) {
+                       int m, float alpha, float n_lambda, int non_reg, float* loss, float* coef1,
+                       float* coef2, tgp_stream_t stream) {
     if (!dist1 || !dist2 || !idx1 || !idx2 || !loss) return fail(TGP_EINVAL, "tgp_dcd: null pointer");
     if (B <= 0 || n <= 0 || m <= 0) return fail(TGP_EINVAL, "tgp_dcd: sizes must be positive");
     const size_t smem = (size_t)(n + m) * sizeof(int);
@@ -211,6 +212,6 @@ extern "C" int tgp_dcd(const float* dist1, const float* dist2, const int32_t* id
         cudaFuncSetAttribute(dcd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         attr = true;
     }
-    dcd_kernel<<<B, DCD_THREADS, smem, as_stream(stream)>>>(dist1, dist2, idx1, idx2, n, m, alpha, n_lambda, loss, coef1, coef2);
+    dcd_kernel<<<B, DCD_THREADS, smem, as_stream(stream)>>>(dist1, dist2, idx1, idx2, n, m, alpha, n_lambda, non_reg, loss, coef1, coef2);
     return check_launch("dcd_kernel");
 }

@@ -70,9 +70,10 @@ class _DcdTail(torch.autograd.Function):
     reference, TDA_loss_sym_recon.py:433,438, so only d loss / d dist flows back)."""
 
     @staticmethod
-    def forward(ctx, dist1, dist2, idx1, idx2, alpha, n_lambda):
+    def forward(ctx, dist1, dist2, idx1, idx2, alpha, n_lambda, non_reg=False):
         need = any(ctx.needs_input_grad)
-        loss, c1, c2 = ops.dcd(dist1.contiguous(), dist2.contiguous(), idx1, idx2, alpha, n_lambda, want_coef=need)
+        loss, c1, c2 = ops.dcd(dist1.contiguous(), dist2.contiguous(), idx1, idx2, alpha, n_lambda, want_coef=need,
+                                non_reg=non_reg)
         if need:
             ctx.save_for_backward(c1, c2)
         return loss
@@ -81,19 +82,17 @@ class _DcdTail(torch.autograd.Function):
     def backward(ctx, gloss):
         c1, c2 = ctx.saved_tensors
         g = gloss.contiguous().unsqueeze(1)
-        return c1 * g, c2 * g, None, None, None, None
+        return c1 * g, c2 * g, None, None, None, None, None
 
 
 def calc_dcd(pred_recon, cate_gt, alpha=0.1, n_lambda=0.3, return_raw=False, non_reg=False):
-    """losses/TDA_loss_sym_recon.py:411-450 -> per-cloud loss (B,).  non_reg=True (never used by the reference's
-    callers, :338) is not implemented."""
-    if non_reg:
-        raise NotImplementedError("calc_dcd(non_reg=True)")
+    """losses/TDA_loss_sym_recon.py:411-450 -> per-cloud loss (B,); non_reg clamps the two point-count ratios to >= 1
+    (:418-420)."""
     pred_recon = pred_recon.float()
     cate_gt = cate_gt.float()
     assert pred_recon.shape[0] == cate_gt.shape[0]
     dist1, dist2, idx1, idx2 = chamfer_3DDist()(pred_recon, cate_gt)
-    loss = _DcdTail.apply(dist1, dist2, idx1, idx2, alpha, n_lambda)
+    loss = _DcdTail.apply(dist1, dist2, idx1, idx2, alpha, n_lambda, bool(non_reg))
     if return_raw:
         return [loss, dist1, dist2, idx1, idx2]
     return loss

@@ -396,7 +396,7 @@ def chamfer_forward(xyz1, xyz2, dist1, dist2, idx1, idx2, sums=None):
                                            _p(sums), _stream())
 
 
-def dcd(dist1, dist2, idx1, idx2, alpha, n_lambda, want_coef=True):
+def dcd(dist1, dist2, idx1, idx2, alpha, n_lambda, want_coef=True, non_reg=False):
     """calc_dcd tail (TDA_loss_sym_recon.py:411-450) -> loss (B), [d loss / d dist1 (B,n), d loss / d dist2 (B,m)]."""
     B, n = dist1.shape
     m = dist2.shape[1]
@@ -404,7 +404,7 @@ def dcd(dist1, dist2, idx1, idx2, alpha, n_lambda, want_coef=True):
     c1 = torch.empty_like(dist1) if want_coef else None
     c2 = torch.empty_like(dist2) if want_coef else None
     _run("dcd", _lib.load().tgp_dcd, _p(dist1), _p(dist2), _p(idx1), _p(idx2), B, n, m, float(alpha), float(n_lambda),
-         _p(loss), _p(c1), _p(c2), _stream())
+         1 if non_reg else 0, _p(loss), _p(c1), _p(c2), _stream())
     return loss, c1, c2
 
 

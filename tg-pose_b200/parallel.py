@@ -59,6 +59,22 @@ def allreduce_gradients(params, world=None, bucket_bytes=32 << 20):
     return n_buckets
 
 
+def allreduce_flat(flat, world=None, bucket_bytes=32 << 20):
+    """average a flat gradient arena (ranger.Ranger.flat_grads) over all ranks in place: one all_reduce per ~32 MB
+    slice, no flatten / unflatten copies."""
+    if not dist.is_initialized():
+        return 0
+    world = world or dist.get_world_size()
+    step = max(1, bucket_bytes // flat.element_size())
+    n_buckets = 0
+    for lo in range(0, flat.numel(), step):
+        piece = flat[lo:lo + step]
+        dist.all_reduce(piece, op=dist.ReduceOp.SUM)
+        piece.div_(world)
+        n_buckets += 1
+    return n_buckets
+
+
 @torch.no_grad()
 def sharded_inference(net, points, cat_id, seed=7, gather=True):
     """run `net` on this rank's slice of (points, cat_id); optionally all_gather the small pose outputs."""

@@ -13,13 +13,16 @@ the step that exercise the hot path and states the rest as simple stand-ins:
   pose terms                             smooth-L1 of the rotation axes / T / s against synthetic ground truth
   total.backward()                       chamfer backward + the backward kernels of SURVEY 8a' + torch heads
   all-reduce                             NCCL gradient averaging (parallel.allreduce_gradients); world 1: no-op
-  clip_grad_norm_(5); optimizer.step()   RL_TDA.py:222-224 (reference: Ranger; here torch Adam, fused)
+  clip_grad_norm_(5); optimizer.step()   RL_TDA.py:222-224 with the reference's optimiser, Ranger
+                                         (config.py:126 optimizer_type = 'Ranger'): ranger.Ranger, two kernels per
+                                         step over flat arenas; optimizer="adam" keeps torch's fused Adam
 """
 import torch
 import torch.nn.functional as F
 
 from . import parallel
 from .dist_chamfer_3D import calc_cd, calc_dcd
+from .ranger import Ranger
 
 
 def synthetic_targets(batch, seed, device):
@@ -46,10 +49,16 @@ def losses(out, pts, tgt):
 class TrainStep:
     """one optimisation step: forward, loss, backward, gradient all-reduce, clip, optimizer step."""
 
-    def __init__(self, net, lr=1e-4, seed=7):
+    def __init__(self, net, lr=1e-4, seed=7, optimizer="ranger"):
         self.net = net
         self.params = [p for p in net.parameters() if p.requires_grad]
-        self.opt = torch.optim.Adam(self.params, lr=lr, fused=self.params[0].is_cuda)
+        self.ranger = optimizer == "ranger"
+        if self.ranger:
+            self.opt = Ranger(self.params, lr=lr)
+        elif optimizer == "adam":
+            self.opt = torch.optim.Adam(self.params, lr=lr, fused=self.params[0].is_cuda)
+        else:
+            raise ValueError(f"TrainStep: unknown optimizer {optimizer!r}")
         self.seed = seed
         self.buckets = 0
 
@@ -59,6 +68,13 @@ class TrainStep:
         out = self.net(pts, cat)
         ls = losses(out, pts, tgt)
         total = 0.1 * ls["recon"] + 0.9 * ls["R_DCD"] + 0.1 * ls["pose"]        # weights as RL_TDA.py:214
+        if self.ranger:
+            self.opt.zero_grad()
+            total.backward()
+            self.buckets = parallel.allreduce_flat(self.opt.flat_grads)
+            self.opt.clip_grad_norm_(5.0)
+            self.opt.step()
+            return total.detach()
         self.opt.zero_grad(set_to_none=True)
         total.backward()
         self.buckets = parallel.allreduce_gradients(self.params)
