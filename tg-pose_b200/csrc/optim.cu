@@ -1,14 +1,16 @@
 // optim.cu -- the two calls that close a training step of the reference (trainer/RL_TDA.py:223-224):
 //   torch.nn.utils.clip_grad_norm_(net1.parameters(), 5); optimizer.step()   with optimizer = Ranger
 //   (tools/torch_utils/solver/ranger2020.py:44-235: RAdam + Lookahead + gradient centralisation).
-// The reference walks ~200 parameter tensors in Python, ~15 ATen launches each.  Here parameters, gradients, both
+// The reference walks the ~100 parameter tensors in Python, ~15 ATen launches each.  Here parameters, gradients, both
 // moments and the Lookahead copy live in five flat fp32 arenas with identical offsets, described by one ROW TABLE
 // (a row = dim-0 slice of a centralised tensor, or a <= 4096-element piece of a 1-D tensor), and a step is two
 // HBM-bound passes:
 //   tgp_ranger_reduce  reads the gradients once: per-row sums (the centralisation means) + the global sum of squares
 //                      (the clip norm)                                                      4 B / element
 //   tgp_ranger_update  g' = clip * (g - mean_row); moments; RAdam step; Lookahead          28 B / element (+8 on Lookahead steps)
-// A warp owns a row (lanes stride it, 128-bit accesses when the row is 16-byte aligned), so the mean is a register.
+// A warp owns a row, so the mean is a register; lanes stride the row with 128-bit accesses between a scalar head (up to
+// the first 16-byte boundary -- the arenas share offsets and are all 256-byte aligned, so one split serves all five) and
+// a scalar tail: rows of 1286 = 1024 + 256 + 6 columns, the heads' usual width, are never 16-byte aligned as a whole.
 #include "common.cuh"
 
 namespace tgp {
@@ -16,7 +18,15 @@ namespace tgp {
 constexpr int OPT_THREADS = 256;
 constexpr int OPT_WARPS = OPT_THREADS / 32;
 
-__device__ __forceinline__ bool row_vec4(const tgp_ranger_row& r) { return ((r.off | (long long)r.len) & 3) == 0; }
+// row = [head scalars | n4 float4 | tail scalars]
+struct RowSplit { int head, n4, tail; };
+__device__ __forceinline__ RowSplit split_row(const tgp_ranger_row& r) {
+    RowSplit s;
+    s.head = min(r.len, (int)((4 - (r.off & 3)) & 3));
+    s.n4 = (r.len - s.head) >> 2;
+    s.tail = r.len - s.head - 4 * s.n4;
+    return s;
+}
 
 __global__ void __launch_bounds__(OPT_THREADS)
 ranger_reduce_kernel(const float* __restrict__ grads, const tgp_ranger_row* __restrict__ rows, int n_rows,
@@ -29,22 +39,20 @@ ranger_reduce_kernel(const float* __restrict__ grads, const tgp_ranger_row* __re
         const tgp_ranger_row row = rows[r];
         if (!active || active[row.tensor]) {
             const float* g = grads + row.off;
-            if (row_vec4(row)) {
-                const float4* g4 = reinterpret_cast<const float4*>(g);
-                const int n4 = row.len >> 2;
+            const RowSplit sp = split_row(row);
+            const float4* g4 = reinterpret_cast<const float4*>(g + sp.head);
 #pragma unroll 4
-                for (int i = lane; i < n4; i += 32) {
-                    const float4 v = __ldg(g4 + i);
-                    s += (v.x + v.y) + (v.z + v.w);
-                    q = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, q))));
-                }
-            } else {
-#pragma unroll 4
-                for (int i = lane; i < row.len; i += 32) {
-                    const float v = __ldg(g + i);
-                    s += v;
-                    q = fmaf(v, v, q);
-                }
+            for (int i = lane; i < sp.n4; i += 32) {
+                const float4 v = __ldg(g4 + i);
+                s += (v.x + v.y) + (v.z + v.w);
+                q = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, q))));
+            }
+            // head (< 4) and tail (< 4) elements: lanes 0..2 and 4..6
+            const int e = lane < sp.head ? lane : (lane >= 4 && lane - 4 < sp.tail ? sp.head + 4 * sp.n4 + lane - 4 : -1);
+            if (e >= 0) {
+                const float v = __ldg(g + e);
+                s += v;
+                q = fmaf(v, v, q);
             }
         }
         s = warp_sum(s);
@@ -82,7 +90,7 @@ __device__ __forceinline__ void ranger_elem(const ElemCoef& c, float mean, float
     }
 }
 
-__global__ void __launch_bounds__(OPT_THREADS)
+__global__ void __launch_bounds__(OPT_THREADS, 4)
 ranger_update_kernel(float* __restrict__ params, const float* __restrict__ grads, float* __restrict__ exp_avg,
                      float* __restrict__ exp_avg_sq, float* __restrict__ slow, const tgp_ranger_row* __restrict__ rows,
                      int row_begin, int row_end, const int* __restrict__ active, const float* __restrict__ row_sum,
@@ -105,31 +113,36 @@ ranger_update_kernel(float* __restrict__ params, const float* __restrict__ grads
     float* m = exp_avg + row.off;
     float* v = exp_avg_sq + row.off;
     float* s = slow + row.off;
-    if (row_vec4(row)) {
-        const int n4 = row.len >> 2;
+    const RowSplit sp = split_row(row);
+    {
+        float4* pv = reinterpret_cast<float4*>(p + sp.head);
+        float4* mv = reinterpret_cast<float4*>(m + sp.head);
+        float4* vv = reinterpret_cast<float4*>(v + sp.head);
+        float4* sv = reinterpret_cast<float4*>(s + sp.head);
+        const float4* gv = reinterpret_cast<const float4*>(g + sp.head);
 #pragma unroll 2
-        for (int i = lane; i < n4; i += 32) {
-            const float4 g4 = __ldg(reinterpret_cast<const float4*>(g) + i);
-            float4 p4 = reinterpret_cast<float4*>(p)[i], m4 = reinterpret_cast<float4*>(m)[i], v4 = reinterpret_cast<float4*>(v)[i];
+        for (int i = lane; i < sp.n4; i += 32) {
+            const float4 g4 = __ldg(gv + i);
+            float4 p4 = pv[i], m4 = mv[i], v4 = vv[i];
             float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (c.lookahead) s4 = reinterpret_cast<float4*>(s)[i];
+            if (c.lookahead) s4 = sv[i];
             ranger_elem(c, mean, g4.x, p4.x, m4.x, v4.x, s4.x);
             ranger_elem(c, mean, g4.y, p4.y, m4.y, v4.y, s4.y);
             ranger_elem(c, mean, g4.z, p4.z, m4.z, v4.z, s4.z);
             ranger_elem(c, mean, g4.w, p4.w, m4.w, v4.w, s4.w);
-            reinterpret_cast<float4*>(p)[i] = p4;
-            reinterpret_cast<float4*>(m)[i] = m4;
-            reinterpret_cast<float4*>(v)[i] = v4;
-            if (c.lookahead) reinterpret_cast<float4*>(s)[i] = s4;
+            pv[i] = p4;
+            mv[i] = m4;
+            vv[i] = v4;
+            if (c.lookahead) sv[i] = s4;
         }
-    } else {
-#pragma unroll 2
-        for (int i = lane; i < row.len; i += 32) {
-            float pi = p[i], mi = m[i], vi = v[i], si = c.lookahead ? s[i] : 0.f;
-            ranger_elem(c, mean, __ldg(g + i), pi, mi, vi, si);
-            p[i] = pi; m[i] = mi; v[i] = vi;
-            if (c.lookahead) s[i] = si;
-        }
+    }
+    // head (< 4) and tail (< 4) elements: lanes 0..2 and 4..6
+    const int i = lane < sp.head ? lane : (lane >= 4 && lane - 4 < sp.tail ? sp.head + 4 * sp.n4 + lane - 4 : -1);
+    if (i >= 0) {
+        float pi = p[i], mi = m[i], vi = v[i], si = c.lookahead ? s[i] : 0.f;
+        ranger_elem(c, mean, __ldg(g + i), pi, mi, vi, si);
+        p[i] = pi; m[i] = mi; v[i] = vi;
+        if (c.lookahead) s[i] = si;
     }
 }
 
