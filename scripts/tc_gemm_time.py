@@ -13,6 +13,10 @@ def t(M, K, N, reps=10):
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
     print(f"dbg={os.environ.get('TGP_TC_DEBUG','0')} {M}x{K}x{N}: {ms:.3f} ms  {6*M*K*N/ms/1e9:.1f} TF32 TFLOP/s", flush=True)
+if os.environ.get("TGP_SHAPES"):          # e.g. TGP_SHAPES=32896x128x1024,8224x256x2048
+    for spec in os.environ["TGP_SHAPES"].split(","):
+        t(*[int(v) for v in spec.split("x")])
+    sys.exit(0)
 t(32896, 1286, 1024)
 t(32896, 128, 1152)
 t(32896, 1024, 256)
