@@ -364,6 +364,8 @@ typedef struct {
     int lookahead;      /* step % k == 0 (:225) */
     float la_alpha;     /* Lookahead interpolation factor */
     float max_norm;     /* > 0: gradients are scaled by min(1, max_norm / (total_norm + 1e-6)) as clip_grad_norm_ does */
+    int gc_on_update;   /* 0: gc_loc = True, rows with gc != 0 lose the mean of the GRADIENT (:170-171, the default);
+                           1: gc_loc = False, they lose the mean of the update G_grad (:217-218) */
 } tgp_ranger_hyper;
 
 /* pass 1: row_sum[r] = sum of row r's gradient (all n_rows rows), *sumsq = sum of squares of every active element

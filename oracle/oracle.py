@@ -551,8 +551,10 @@ def radam_scalars(step, beta1, beta2, threshold):
 
 
 def ranger_step(state, grads, lr=1e-3, alpha=0.5, k=6, threshold=5, betas=(0.95, 0.999), eps=1e-5, weight_decay=0.0,
-                use_gc=True, gc_conv_only=False, max_norm=None):
-    """One clip_grad_norm_ + Ranger.step() (ranger2020.py:133-235, gc_loc=True) in float32 numpy.
+                use_gc=True, gc_conv_only=False, max_norm=None, gc_loc=True):
+    """One clip_grad_norm_ + Ranger.step() (ranger2020.py:133-235) in float32 numpy.  gc_loc=True centralises the
+    gradient (:170-171), gc_loc=False the update G_grad (:217-218; in place, so on un-rectified steps -- where G_grad
+    IS exp_avg -- the moment is centralised too).
     state: {"step": int, "p": [...], "m": [...], "v": [...], "slow": [...]} updated in place; returns the total norm."""
     f = np.float32
     total, coef = clip_coef(grads, max_norm) if max_norm else (0.0, 1.0)
@@ -561,7 +563,8 @@ def ranger_step(state, grads, lr=1e-3, alpha=0.5, k=6, threshold=5, betas=(0.95,
     rect, step_size = radam_scalars(t, betas[0], betas[1], threshold)
     for i, g in enumerate(grads):
         g = (g * f(coef)).astype(f) if max_norm else g.astype(f)
-        if use_gc and g.ndim > (3 if gc_conv_only else 1):                       # centralized_gradient :31-41
+        gc = use_gc and g.ndim > (3 if gc_conv_only else 1)                       # centralized_gradient :31-41
+        if gc and gc_loc:
             g = g - g.mean(axis=tuple(range(1, g.ndim)), keepdims=True, dtype=f)
         p, m, v = state["p"][i], state["m"][i], state["v"][i]
         v *= f(betas[1])
@@ -571,6 +574,8 @@ def ranger_step(state, grads, lr=1e-3, alpha=0.5, k=6, threshold=5, betas=(0.95,
         G = m / (np.sqrt(v) + f(eps)) if rect else m                               # :208-212 (`G_grad = exp_avg`: an ALIAS)
         if weight_decay != 0:
             G += f(weight_decay) * p        # :214-215, in place: on un-rectified steps this also lands in exp_avg
+        if gc and not gc_loc:
+            G -= G.mean(axis=tuple(range(1, G.ndim)), keepdims=True, dtype=f)      # :217-218, in place as well
         p += f(-step_size * lr) * G                                                # :220
         if t % k == 0:                                                             # :225-231
             slow = state["slow"][i]

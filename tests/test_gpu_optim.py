@@ -12,7 +12,8 @@ pytestmark = pytest.mark.gpu
 
 CONFIGS = {"default": dict(lr=1e-3),
            "wd_convonly": dict(lr=3e-3, weight_decay=0.01, gc_conv_only=True, betas=(0.9, 0.99), k=4, alpha=0.3),
-           "nogc": dict(lr=1e-2, use_gc=False, eps=1e-8)}
+           "nogc": dict(lr=1e-2, use_gc=False, eps=1e-8),
+           "gc_update": dict(lr=2e-3, gc_loc=False, weight_decay=0.005)}
 
 
 def nump(t):
@@ -122,12 +123,13 @@ def test_ranger_picks_up_reallocated_gradients():
     close_update(nump(lin.weight), st["p"][0].astype(np.float64), nump(w0), "weight after one step")
 
 
-def test_ranger_rejects_cpu_parameters_and_gc_loc():
+def test_ranger_rejects_cpu_parameters_and_bad_arguments():
     from tgpose_b200.ranger import Ranger
     with pytest.raises(RuntimeError):
         Ranger([torch.nn.Parameter(torch.zeros(3))])
-    with pytest.raises(NotImplementedError):
-        Ranger([torch.nn.Parameter(torch.zeros(3, device="cuda"))], gc_loc=False)
+    for bad in (dict(alpha=1.5), dict(k=0), dict(lr=0.0), dict(eps=0.0)):      # ranger2020.py:80-88
+        with pytest.raises(ValueError):
+            Ranger([torch.nn.Parameter(torch.zeros(3, device="cuda"))], **bad)
 
 
 def test_ranger_state_dict_round_trip():

@@ -108,7 +108,7 @@ def test_pool_consumes_cpu_rng_like_reference():
 def test_ranger_struct_layouts_match_header():
     from tgpose_b200 import _lib, ranger
     # tgp_ranger_hyper: 7 floats, 2 ints, 2 floats; tgp_ranger_row: long long + 4 ints
-    assert ctypes.sizeof(_lib.RangerHyper) == 44
+    assert ctypes.sizeof(_lib.RangerHyper) == 48 and _lib.RangerHyper.gc_on_update.offset == 44
     assert _lib.RangerHyper.neg_step.offset == 24 and _lib.RangerHyper.rectified.offset == 28
     assert _lib.RangerHyper.max_norm.offset == 40
     rec = ranger._pack_rows(np.asarray([[64, 5, 1, 2]], np.int64))

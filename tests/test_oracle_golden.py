@@ -201,7 +201,8 @@ def test_backward_oracle_vs_reference_autograd():
 # ----------------------------------------------------------------------------------------- optimiser step
 RANGER_CONFIGS = {"default": dict(lr=1e-3),
                   "wd_convonly": dict(lr=3e-3, weight_decay=0.01, gc_conv_only=True, betas=(0.9, 0.99), k=4, alpha=0.3),
-                  "nogc": dict(lr=1e-2, use_gc=False, eps=1e-8)}
+                  "nogc": dict(lr=1e-2, use_gc=False, eps=1e-8),
+                  "gc_update": dict(lr=2e-3, gc_loc=False, weight_decay=0.005)}
 
 
 @pytest.mark.parametrize("tag", list(RANGER_CONFIGS))

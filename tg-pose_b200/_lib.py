@@ -41,7 +41,7 @@ class RangerHyper(ctypes.Structure):
     _fields_ = [("beta1", ctypes.c_float), ("beta2", ctypes.c_float), ("eps", ctypes.c_float),
                 ("weight_decay", ctypes.c_float), ("one_minus_beta1", ctypes.c_float),
                 ("one_minus_beta2", ctypes.c_float), ("neg_step", ctypes.c_float), ("rectified", c_int),
-                ("lookahead", c_int), ("la_alpha", ctypes.c_float), ("max_norm", ctypes.c_float)]
+                ("lookahead", c_int), ("la_alpha", ctypes.c_float), ("max_norm", ctypes.c_float), ("gc_on_update", c_int)]
 
 
 # name -> (restype, argtypes); must list every symbol include/tgpose_b200.h declares

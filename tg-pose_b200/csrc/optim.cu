@@ -146,6 +146,69 @@ ranger_update_kernel(float* __restrict__ params, const float* __restrict__ grads
     }
 }
 
+// gc_loc = False (ranger2020.py:217-218): the UPDATE G_grad is centralised instead of the gradient.  The mean of a row of
+// G only exists once the whole row's moments are updated, so the warp walks its row twice: pass 1 updates the moments,
+// forms G (Adam quotient or exp_avg, plus weight decay) and sums it; pass 2 re-forms G from the moments just written
+// (L1/L2-resident: a row is <= a few thousand elements), removes the mean and steps.  On un-rectified steps G_grad IS
+// exp_avg in the reference (an alias, :212), so weight decay and the centralisation land in exp_avg as well; kept.
+// Not the reference's default and not on the benchmark path: scalar accesses.
+__global__ void __launch_bounds__(OPT_THREADS)
+ranger_update_gcu_kernel(float* __restrict__ params, const float* __restrict__ grads, float* __restrict__ exp_avg,
+                         float* __restrict__ exp_avg_sq, float* __restrict__ slow, const tgp_ranger_row* __restrict__ rows,
+                         int row_begin, int row_end, const int* __restrict__ active, const double* __restrict__ sumsq,
+                         tgp_ranger_hyper h, float* __restrict__ total_norm) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int r = row_begin + blockIdx.x * OPT_WARPS + warp;
+    const float norm = sumsq ? (float)sqrt(*sumsq) : 0.f;
+    if (total_norm && blockIdx.x == 0 && threadIdx.x == 0) *total_norm = norm;
+    if (r >= row_end) return;
+    const tgp_ranger_row row = rows[r];
+    if (active && !active[row.tensor]) return;
+    const float clip = (h.max_norm > 0.f && sumsq) ? fminf(1.f, h.max_norm / (norm + 1e-6f)) : 1.f;
+    float* p = params + row.off;
+    const float* g = grads + row.off;
+    float* m = exp_avg + row.off;
+    float* v = exp_avg_sq + row.off;
+    float* s = slow + row.off;
+    float sum = 0.f;
+    for (int i = lane; i < row.len; i += 32) {
+        const float gc = __ldg(g + i) * clip;
+        const float vi = fmaf(h.one_minus_beta2 * gc, gc, v[i] * h.beta2);
+        float mi = fmaf(h.one_minus_beta1, gc, m[i] * h.beta1);
+        float G = h.rectified ? mi / (sqrtf(vi) + h.eps) : mi;
+        if (h.weight_decay != 0.f) {
+            G = fmaf(h.weight_decay, p[i], G);
+            if (!h.rectified) mi = G;
+        }
+        v[i] = vi;
+        m[i] = mi;
+        sum += G;
+    }
+    sum = warp_sum(sum);
+    const float mean = row.gc ? sum / (float)row.len : 0.f;
+    __syncwarp();
+    for (int i = lane; i < row.len; i += 32) {      // each lane re-reads only what it wrote itself
+        const float mi = m[i];
+        float pi = p[i];
+        float G;
+        if (h.rectified) {
+            G = mi / (sqrtf(v[i]) + h.eps);
+            if (h.weight_decay != 0.f) G = fmaf(h.weight_decay, pi, G);
+            G -= mean;
+        } else {
+            G = mi - mean;                            // exp_avg already carries the weight-decay term (alias)
+            m[i] = G;
+        }
+        pi = fmaf(h.neg_step, G, pi);
+        if (h.lookahead) {
+            const float si = fmaf(h.la_alpha, pi - s[i], s[i]);
+            s[i] = si;
+            pi = si;
+        }
+        p[i] = pi;
+    }
+}
+
 }  // namespace tgp
 
 using namespace tgp;
@@ -176,6 +239,12 @@ extern "C" int tgp_ranger_update(float* params, const float* grads, float* exp_a
         return fail(TGP_EINVAL, "tgp_ranger_update: Lookahead alpha must be in [0, 1]");   // ranger2020.py:81-82
     if (h.max_norm > 0.f && !sumsq) return fail(TGP_EINVAL, "tgp_ranger_update: clipping needs the sumsq of tgp_ranger_reduce");
     const int blocks = (row_end - row_begin + OPT_WARPS - 1) / OPT_WARPS;
+    if (h.gc_on_update) {
+        ranger_update_gcu_kernel<<<blocks, OPT_THREADS, 0, as_stream(stream)>>>(params, grads, exp_avg, exp_avg_sq, slow,
+                                                                               rows_dev, row_begin, row_end, active_dev,
+                                                                               sumsq, h, total_norm);
+        return check_launch("ranger_update_gcu_kernel");
+    }
     ranger_update_kernel<<<blocks, OPT_THREADS, 0, as_stream(stream)>>>(params, grads, exp_avg, exp_avg_sq, slow, rows_dev,
                                                                        row_begin, row_end, active_dev, row_sum, sumsq, h,
                                                                        total_norm);

@@ -20,7 +20,8 @@ Differences from the reference, all stated:
     A gradient that autograd re-allocated elsewhere is copied back into the arena by step().
   * a parameter whose .grad is None is skipped like ranger2020.py:146-147 does, but the step counter is the
     optimiser's, not the parameter's (they coincide whenever every parameter gets a gradient on every step).
-  * gc_loc=False (centralising the update instead of the gradient) is not implemented: raises.
+  * gc_loc=False (centralising the update instead of the gradient, ranger2020.py:217-218) runs a second, scalar
+    update kernel in which a warp walks its row twice; the default gc_loc=True is the tuned path.
 There is no CPU path: parameters must be CUDA tensors and the shared object must be built.
 """
 import ctypes
@@ -87,8 +88,6 @@ class Ranger(Optimizer):
             raise ValueError(f"Invalid Learning Rate: {lr}")
         if not eps > 0:
             raise ValueError(f"Invalid eps: {eps}")
-        if not gc_loc:
-            raise NotImplementedError("Ranger(gc_loc=False) is not implemented on the fused path")
         defaults = dict(lr=lr, alpha=alpha, k=k, step_counter=0, betas=betas, N_sma_threshhold=N_sma_threshhold,
                         eps=eps, weight_decay=weight_decay)
         super().__init__(params, defaults)
@@ -210,7 +209,8 @@ class Ranger(Optimizer):
             rect, step_size = radam_scalars(self.steps, beta1, beta2, self.N_sma_threshhold)
             h = _lib.RangerHyper(beta1, beta2, group["eps"], group["weight_decay"], 1 - beta1, 1 - beta2,
                                  -step_size * group["lr"],
-                                 1 if rect else 0, 1 if self.steps % group["k"] == 0 else 0, self.alpha, self._max_norm)
+                                 1 if rect else 0, 1 if self.steps % group["k"] == 0 else 0, self.alpha, self._max_norm,
+                                 0 if self.gc_loc else 1)
             _lib.check(self._lib.tgp_ranger_update(
                 self.flat_params.data_ptr(), self.flat_grads.data_ptr(), self.flat_exp_avg.data_ptr(),
                 self.flat_exp_avg_sq.data_ptr(), self.flat_slow.data_ptr(), self._rows_dev.data_ptr(), r0, r1, a,
