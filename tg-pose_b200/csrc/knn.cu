@@ -164,7 +164,6 @@ knn_xyz_sel_kernel(const float* __restrict__ xyz, int N, int k, int tile, int sl
     // ---- pass 2: every lane appends its survivors (d <= T) to a private list: no ballots in the scan
     // (the write cursor of each list is a byte offset that advances by one 256-byte row per survivor; predicated, no branch)
     uint32_t cur[KS_QPW];
-#pragma unroll
     const uint32_t wsm_s = (uint32_t)__cvta_generic_to_shared(wsm);
 #pragma unroll
     for (int q = 0; q < KS_QPW; ++q) cur[q] = wsm_s + (uint32_t)(q * qstride + lane * 8);
