@@ -122,8 +122,9 @@ int tgp_surface_conv_fwd(const float* xyz, const void* idx, int idx_bits, const 
                          int B, int N, int k, int S, int C, float* out, uint8_t* arg, float* out_split,
                          tgp_stream_t stream);
 
-/* Edge records for the layer convolution: rec[b,n,j] = (dx,dy,dz, bitcast<float>(int idx[b,n,j]))
- * with (dx,dy,dz) = get_neighbor_direction_norm (gcn3d.py:48-58).  rec: (B,N,k,4) fp32, 16-byte aligned. */
+/* Edge records for the layer convolution: rec[b,j,n] = (dx,dy,dz, bitcast<float>(int idx[b,n,j]))
+ * with (dx,dy,dz) = get_neighbor_direction_norm (gcn3d.py:48-58).  rec: (B,k,N,4) fp32 -- NEIGHBOUR-major, so that
+ * consecutive points read consecutive records -- 16-byte aligned. */
 int tgp_edge_records(const float* xyz, const void* idx, int idx_bits, int B, int N, int k,
                      float* rec, tgp_stream_t stream);
 

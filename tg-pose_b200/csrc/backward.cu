@@ -151,7 +151,7 @@ layer_conv_bwd_kernel(const float4* __restrict__ rec, const float* __restrict__ 
             const long pt = b * N + n;
             const float gsc = __ldg(G + pt * ld_g + cg * 4 + c4) * inv_s;
             const int j = arg_slab[((long)cg * M + pt) * W + lane];
-            const float4 d = __ldg(rec + pt * k + j);
+            const float4 d = __ldg(rec + (b * k + j) * N + n);      // neighbour-major records (tgp_edge_records)
             const int nb = __float_as_int(d.w);
             const float sup = __ldg(slab + ((long)cg * M + b * N + nb) * W + lane);
             const float th = fmaxf(fmaf(d.z, sz, fmaf(d.y, sy, d.x * sx)), 0.f);

@@ -13,6 +13,7 @@
 // is a conflict-free 112-byte shared-memory row read by lanes 0..27 of a warp.
 #include "common.cuh"
 #include <float.h>
+#include <stdlib.h>
 
 namespace tgp {
 
@@ -64,7 +65,7 @@ __device__ __forceinline__ void store_out(float* __restrict__ out, float* __rest
 }
 
 // ------------------------------------------------------------------------------------------
-// edge records: (dx,dy,dz, idx) per (b,n,j)
+// edge records: (dx,dy,dz, idx) per (b,j,n) -- NEIGHBOUR-major, so the points of a warp's quad read contiguous bytes
 template <typename IdxT>
 __global__ void edge_record_kernel(const float* __restrict__ xyz, const IdxT* __restrict__ idx, long total, int N,
                                    int k, float4* __restrict__ rec) {
@@ -77,7 +78,8 @@ __global__ void edge_record_kernel(const float* __restrict__ xyz, const IdxT* __
     const float* c = xyz + pt * 3;
     float x = __ldg(p) - __ldg(c), y = __ldg(p + 1) - __ldg(c + 1), z = __ldg(p + 2) - __ldg(c + 2);
     normalize3(x, y, z);
-    rec[e] = make_float4(x, y, z, __int_as_float(nb));
+    const long n = pt - b * N;
+    rec[(b * k + (e - pt * k)) * N + n] = make_float4(x, y, z, __int_as_float(nb));
 }
 
 // ------------------------------------------------------------------------------------------
@@ -168,11 +170,52 @@ surface_conv_kernel(const float* __restrict__ xyz, const IdxT* __restrict__ idx,
 }
 
 // ------------------------------------------------------------------------------------------
-// layer conv.  CTA = (4-channel group cg, cloud b).  lane = s*4 + c4 (< S*4 <= 32).
-// TAB: the (cloud, channel-group) support table is staged in shared memory (N*S*16 B <= ~215 KB, i.e. N <= ~1960 at
-// S = 7); otherwise (the N = 2048..16384 microbenchmark clouds) the 112-byte rows are gathered through L2.
+// packed fp32 pairs (FFMA2 / FMUL2 on sm_100a): two channels per instruction -- same .rn arithmetic as the scalar
+// forms, half the issue slots.  A pair built from one scalar twice is encoded by ptxas as a broadcast operand.
+__device__ __forceinline__ unsigned long long f2_pack(float lo, float hi) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void f2_unpack(unsigned long long v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long f2_mul(unsigned long long a, unsigned long long b) {
+    unsigned long long d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ unsigned long long f2_fma(unsigned long long a, unsigned long long b, unsigned long long c) {
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+
+// 16-byte asynchronous global -> shared copy (LDGSTS, L1 bypassed) and its group bookkeeping
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N_>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N_) : "memory"); }
+
+// ------------------------------------------------------------------------------------------
+// layer conv.  CTA = (4-channel group cg, cloud b[, point split z]).
+// A warp works on FOUR points at a time: lane = p*8 + s (point p of the quad, support s < S); a lane owns the 4 channels
+// of its (point, support) -- one 16-byte chunk of a slab row.  Per neighbour a lane issues ONE 16-byte record load
+// (direction + neighbour index, from a per-warp shared-memory ring that cp.async fills one quad ahead; the records are
+// neighbour-major in HBM, so a quad's k x 64 bytes are k contiguous pieces), ONE 16-byte gather of its chunk of the
+// neighbour's slab row (the 8 lanes of a quarter-warp read one contiguous 112-byte row: conflict-free) and 16 arithmetic
+// instructions for its 4 (neighbour, support, channel) elements (cosine as packed FMUL2/FFMA2, ReLU, packed multiply,
+// max).  What bounded the round-1 mapping (lane = (support, channel), one point per warp) was the shared-memory pipe:
+// one broadcast record load (2 cycles) + one 4-byte gather (1 cycle) per 28 elements = 0.107 cycles per element; this
+// one spends 4 (gather) + ~3.2 (record) cycles per 112 elements = 0.064 (profiles/r02_layer_conv.md; ncu: LSU data pipe
+// 81 % busy, i.e. the kernel now sits on that roof).  Loading the records straight from global memory into registers
+// (prefetch distance 4) was 1.9x slower: ptxas sinks the loads next to their uses under the 64-register cap.
+// TAB: the (cloud, channel-group) support table is staged in shared memory by TMA bulk copies (N*S*16 B <= ~227 KB,
+// i.e. N <= ~2070 at S = 7); otherwise (the N = 2048..16384 microbenchmark clouds) the rows are gathered through L2.
 template <bool ARG, int KT, bool TAB>
-__global__ void __launch_bounds__(1024)
+__global__ void __launch_bounds__(ARG ? 512 : 1024, 1)    // the arg-max slots of the training variant need the registers
 layer_conv_kernel(const float4* __restrict__ rec, const float* __restrict__ directions,
                   const float* __restrict__ centre, long ld_centre, const float* __restrict__ slab,
                   long M, int N, int k_rt, int S, int C, float* __restrict__ out, uint8_t* __restrict__ arg_slab,
@@ -182,7 +225,8 @@ layer_conv_kernel(const float4* __restrict__ rec, const float* __restrict__ dire
     const int W = S * 4;                                   // slab row width in floats
     float* tab = reinterpret_cast<float*>(smem_raw);       // [N][W]
     const size_t tab_bytes = TAB ? (size_t)N * W * sizeof(float) : 0;
-    float4* recs = reinterpret_cast<float4*>(smem_raw + ((tab_bytes + 15) & ~(size_t)15));  // [warps][k]
+    // per-warp record ring: [2 quads][k neighbours][4 points] float4, filled by cp.async one quad ahead
+    const uint32_t ring_base = smem_u32(smem_raw) + (uint32_t)((tab_bytes + 127) & ~(size_t)127);
     __shared__ __align__(8) uint64_t bar;
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
@@ -205,57 +249,123 @@ layer_conv_kernel(const float4* __restrict__ rec, const float* __restrict__ dire
             bulk_g2s(smem_raw + off, reinterpret_cast<const unsigned char*>(src) + off, nbytes, &bar);
         }
     }
-    // this lane's support direction while the table is in flight
-    float sx = 0.f, sy = 0.f, sz = 0.f;
-    const int s_l = lane >> 2, c4 = lane & 3;
-    if (lane < W) load_sd(directions, SC, s_l * C + cg * 4 + c4, sx, sy, sz);
+    // this lane's four support directions (channels cg*4 .. cg*4+3 of support s) while the table is in flight
+    const int p = lane >> 3, s = lane & 7;
+    const bool act = s < S;
+    unsigned long long sx01 = 0, sx23 = 0, sy01 = 0, sy23 = 0, sz01 = 0, sz23 = 0;
+    if (act) {
+        float x[4], y[4], z[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) load_sd(directions, SC, s * C + cg * 4 + c, x[c], y[c], z[c]);
+        sx01 = f2_pack(x[0], x[1]); sx23 = f2_pack(x[2], x[3]);
+        sy01 = f2_pack(y[0], y[1]); sy23 = f2_pack(y[2], y[3]);
+        sz01 = f2_pack(z[0], z[1]); sz23 = f2_pack(z[2], z[3]);
+    }
+    const int s_c = act ? s : 0;                           // idle lanes (s >= S) shadow support 0; nothing of theirs is stored
+    const uint32_t tab_lane = smem_u32(tab) + (uint32_t)s_c * 16u;
+    const uint32_t row_bytes = (uint32_t)W * 4u;
+    const float4* src4 = reinterpret_cast<const float4*>(src) + s_c;
+    const float inv_s = 1.0f / (float)S;
+    // gridDim.z splits the quads of the cloud when (clouds x channel groups) alone cannot fill the machine
+    const int quads = (N + 3) >> 2;
+    const int per = (quads + gridDim.z - 1) / gridDim.z;
+    const int q_beg = blockIdx.z * per, q_end = min(quads, q_beg + per);
+    const float4* recb = rec + b * (long)k * N;
+    const uint32_t quad_bytes = (uint32_t)k * 64u;
+    const uint32_t ring = ring_base + (uint32_t)warp * 2u * quad_bytes;
+    // the records of one quad = k rows of 64 contiguous bytes: chunk c = j*4 + p  ->  rec[b][j][4q + p]
+    auto fetch_quad = [&](int q, uint32_t dst) {
+        for (int c = lane; c < k * 4; c += 32) {
+            const int j = c >> 2, n = min(q * 4 + (c & 3), N - 1);
+            cp_async16(dst + (uint32_t)c * 16u, recb + (long)j * N + n);
+        }
+        cp_async_commit();
+    };
+    int q = q_beg + warp;
+    if (q < q_end) fetch_quad(q, ring);
     if (TAB) mbar_wait(&bar, 0);
 
-    float4* my = recs + warp * k;
-    const float inv_s = 1.0f / (float)S;
-    // byte address of this lane's column in table row 0; a neighbour's row is one integer add away
-    const uint32_t tab_lane = smem_u32(tab) + (uint32_t)(lane < W ? lane : 0) * 4u;
-    const uint32_t row_bytes = (uint32_t)W * 4u;
-    // the k edge records of the warp's next point are fetched while the current point is being reduced
-    // gridDim.z splits the points of the cloud when (clouds x channel groups) alone cannot fill the machine
-    const int per = (N + gridDim.z - 1) / gridDim.z;
-    const int n_beg = blockIdx.z * per, n_end = min(N, n_beg + per);
-    const float4* rp = rec + (b * N + n_beg + warp) * (long)k;
-    const long rstep = (long)nwarps * k;
-    float4 nxt = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (n_beg + warp < n_end && lane < k) nxt = __ldg(rp + lane);
-    for (int n = n_beg + warp; n < n_end; n += nwarps) {
-        const long pt = b * N + n;
+    for (uint32_t buf = 0; q < q_end; q += nwarps, buf ^= 1u) {
+        const int n = q * 4 + p;
+        const bool valid = n < N;
+        const int n_ld = valid ? n : N - 1;
+        const long pt = b * N + n_ld;
+        if (q + nwarps < q_end) { fetch_quad(q + nwarps, ring + (buf ^ 1u) * quad_bytes); cp_async_wait<1>(); }
+        else cp_async_wait<0>();
         __syncwarp();
-        if (lane < k) my[lane] = nxt;
-        for (int j = lane + 32; j < k; j += 32) my[j] = __ldg(rp + j);
-        __syncwarp();
-        rp += rstep;
-        if (n + nwarps < n_end && lane < k) nxt = __ldg(rp + lane);
-        // the centre term is only needed after the neighbour loop: fetch it now so its latency hides behind the loop
-        float cen = 0.f;
-        if (lane < 4) cen = __ldg(centre + pt * ld_centre + cg * 4 + lane);
-        float m = -FLT_MAX;
-        int a = 0;
-        if (lane < W) {
-#pragma unroll (KT > 0 ? KT : 4)
-            for (int j = 0; j < k; ++j) {
-                const float4 d = my[j];
-                float sup;
-                if (TAB) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(sup) : "r"(tab_lane + (uint32_t)__float_as_int(d.w) * row_bytes));
-                else sup = __ldg(src + (long)__float_as_int(d.w) * W + (lane < W ? lane : 0));
-                const float th = fmaxf(fmaf(d.z, sz, fmaf(d.y, sy, d.x * sx)), 0.f);
-                const float v = th * sup;
-                if (ARG) { if (v > m) { m = v; a = j; } }
-                else m = fmaxf(m, v);
+        const uint32_t rq = ring + buf * quad_bytes + (uint32_t)p * 16u;
+        float m0 = -FLT_MAX, m1 = -FLT_MAX, m2 = -FLT_MAX, m3 = -FLT_MAX;
+        int a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+        // one neighbour: record (broadcast within the point's 8 lanes), gather, 16 arithmetic instructions for the
+        // lane's 4 (neighbour, support, channel) elements
+        auto step = [&](const int j) {
+            float4 d;
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                         : "=f"(d.x), "=f"(d.y), "=f"(d.z), "=f"(d.w) : "r"(rq + (uint32_t)j * 64u));
+            float4 sup;
+            if (TAB) {
+                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                             : "=f"(sup.x), "=f"(sup.y), "=f"(sup.z), "=f"(sup.w)
+                             : "r"(tab_lane + (uint32_t)__float_as_int(d.w) * row_bytes));
+            } else {
+                sup = __ldg(src4 + (long)__float_as_int(d.w) * S);
             }
-            if (ARG) arg_slab[((long)cg * M + pt) * W + lane] = (uint8_t)a;
-        } else m = 0.f;
-        // sum over supports: lanes with equal c4 (stride 4)
-        m += __shfl_down_sync(0xffffffffu, m, 16);
-        m += __shfl_down_sync(0xffffffffu, m, 8);
-        m += __shfl_down_sync(0xffffffffu, m, 4);
-        if (lane < 4) store_out(out, out_split, kp, pt, C, cg * 4 + lane, cen + m * inv_s);
+            const unsigned long long dx = f2_pack(d.x, d.x), dy = f2_pack(d.y, d.y), dz = f2_pack(d.z, d.z);
+            float t0, t1, t2, t3;
+            f2_unpack(f2_fma(dz, sz01, f2_fma(dy, sy01, f2_mul(dx, sx01))), t0, t1);
+            f2_unpack(f2_fma(dz, sz23, f2_fma(dy, sy23, f2_mul(dx, sx23))), t2, t3);
+            float v0, v1, v2, v3;
+            f2_unpack(f2_mul(f2_pack(fmaxf(t0, 0.f), fmaxf(t1, 0.f)), f2_pack(sup.x, sup.y)), v0, v1);
+            f2_unpack(f2_mul(f2_pack(fmaxf(t2, 0.f), fmaxf(t3, 0.f)), f2_pack(sup.z, sup.w)), v2, v3);
+            if (ARG) {
+                if (v0 > m0) { m0 = v0; a0 = j; }
+                if (v1 > m1) { m1 = v1; a1 = j; }
+                if (v2 > m2) { m2 = v2; a2 = j; }
+                if (v3 > m3) { m3 = v3; a3 = j; }
+            } else {
+                m0 = fmaxf(m0, v0); m1 = fmaxf(m1, v1); m2 = fmaxf(m2, v2); m3 = fmaxf(m3, v3);
+            }
+        };
+        if (KT > 0) {
+#pragma unroll
+            for (int j = 0; j < KT; ++j) step(j);
+        } else {
+#pragma unroll 4
+            for (int j = 0; j < k; ++j) step(j);
+        }
+        __syncwarp();                                      // every lane is done with this buffer before it is refilled
+        float4 cen = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (s == 0) {
+            const float* cp = centre + pt * ld_centre + cg * 4;
+            cen = make_float4(__ldg(cp), __ldg(cp + 1), __ldg(cp + 2), __ldg(cp + 3));
+        }
+        if (ARG && act && valid) {
+            const uint32_t packed = (uint32_t)a0 | ((uint32_t)a1 << 8) | ((uint32_t)a2 << 16) | ((uint32_t)a3 << 24);
+            *reinterpret_cast<uint32_t*>(arg_slab + ((long)cg * M + pt) * W + s * 4) = packed;
+        }
+        if (!act) { m0 = 0.f; m1 = 0.f; m2 = 0.f; m3 = 0.f; }
+        // sum over the supports of a point: butterfly over the 8 lanes of its group (fixed order)
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) {
+            m0 += __shfl_xor_sync(0xffffffffu, m0, o);
+            m1 += __shfl_xor_sync(0xffffffffu, m1, o);
+            m2 += __shfl_xor_sync(0xffffffffu, m2, o);
+            m3 += __shfl_xor_sync(0xffffffffu, m3, o);
+        }
+        if (s == 0 && valid) {
+            const float4 r = make_float4(cen.x + m0 * inv_s, cen.y + m1 * inv_s, cen.z + m2 * inv_s, cen.w + m3 * inv_s);
+            *reinterpret_cast<float4*>(out + pt * C + cg * 4) = r;
+            if (out_split) {
+                float4 hi, lo;
+                uint32_t hb;
+                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(r.x)); hi.x = __uint_as_float(hb); lo.x = r.x - hi.x;
+                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(r.y)); hi.y = __uint_as_float(hb); lo.y = r.y - hi.y;
+                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(r.z)); hi.z = __uint_as_float(hb); lo.z = r.z - hi.z;
+                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(r.w)); hi.w = __uint_as_float(hb); lo.w = r.w - hi.w;
+                *reinterpret_cast<float4*>(out_split + pt * 2 * kp + cg * 4) = hi;
+                *reinterpret_cast<float4*>(out_split + pt * 2 * kp + kp + cg * 4) = lo;
+            }
+        }
     }
 }
 
@@ -320,18 +430,33 @@ extern "C" int tgp_layer_conv_fwd(const float* edge_rec, const float* directions
     if ((uintptr_t)support_slab % 16 || (uintptr_t)edge_rec % 16) return fail(TGP_EINVAL, "tgp_layer_conv_fwd: slab / edge_rec must be 16-byte aligned");
     const int W = S * 4;
     const size_t tab_bytes = (size_t)N * W * sizeof(float);
-    // enough warps to hide the gather latency, few enough that several CTAs share an SM when the table is small
-    int threads = N >= 512 ? 1024 : (N >= 128 ? 256 : 128);
-    size_t smem = ((tab_bytes + 15) & ~(size_t)15) + sizeof(float4) * (threads / 32) * k;
-    const bool tab = smem <= 227 * 1024;        // else: gather the support rows through L2 instead of a shared-memory table
-    if (!tab) smem = sizeof(float4) * (threads / 32) * k;
-    if (smem > 227 * 1024) return fail(TGP_EINVAL, "tgp_layer_conv_fwd: k too large");
-    // point splits: aim at >= 2 CTAs per SM; depends on the shapes only.  (Each split re-stages the table when TAB.)
-    int zs = (2 * TGP_NUM_SMS + (C / 4) * B - 1) / ((C / 4) * B);
-    const int zcap = (N + 255) / 256;
+    const size_t ring_per_warp = (size_t)2 * k * 64;          // two quads of k records x 4 points x 16 B
+    const size_t tab_al = (tab_bytes + 127) & ~(size_t)127;
+    const bool tab = tab_al + 4 * ring_per_warp <= 227 * 1024;   // else: gather the support rows through L2
+    if (4 * ring_per_warp > 227 * 1024) return fail(TGP_EINVAL, "tgp_layer_conv_fwd: k too large");
+    // point splits (each split re-stages the table when TAB): only when (channel groups x clouds) is under ~4 waves.
+    const int quads = (N + 3) / 4;
+    int wmax = arg_slab ? 16 : 32;
+    {
+        const size_t room = 227 * 1024 - (tab ? tab_al : 0);
+        if ((size_t)wmax * ring_per_warp > room) wmax = (int)(room / ring_per_warp);
+    }
+    int zs = (4 * TGP_NUM_SMS + (C / 4) * B - 1) / ((C / 4) * B);
+    const int zcap = (quads + wmax - 1) / wmax;
     if (zs > zcap) zs = zcap;
     if (zs < 1) zs = 1;
     if (zs > 64) zs = 64;
+    if (const char* e = getenv("TGP_LC_ZS")) { const int v = atoi(e); if (v > 0 && v <= 64) zs = v; }   // tuning hook
+    // warps per CTA (a warp works on one quad of points at a time)
+    const int qcta = (quads + zs - 1) / zs;
+    // ~8 quads per warp (measured best at N = 1028 / 257 / 64: 32 / 8 / 4 warps): small clouds run as several small
+    // resident CTAs per SM so that table loads, set-up and tails of one overlap the neighbour loops of the others
+    int nw = (qcta + 7) / 8;
+    if (nw > wmax) nw = wmax;
+    if (nw < 2) nw = 2;
+    if (const char* e = getenv("TGP_LC_WARPS")) { const int v = atoi(e); if (v > 0 && v <= wmax) nw = v; }   // tuning hook
+    const int threads = nw * 32;
+    const size_t smem = (tab ? tab_al : 0) + (size_t)nw * ring_per_warp;
     dim3 grid(C / 4, B, zs);
     cudaStream_t st = as_stream(stream);
     const long M = (long)B * N;

@@ -212,15 +212,15 @@ def edge_records(xyz, idx):
     xyz = _f32c(xyz, "edge_records")
     idx, bits = _idx(idx, "edge_records")
     B, N, k = idx.shape
-    rec = torch.empty((B, N, k, 4), dtype=torch.float32, device=xyz.device)
+    rec = torch.empty((B, k, N, 4), dtype=torch.float32, device=xyz.device)     # neighbour-major
     _run("edge_records", _lib.load().tgp_edge_records, _p(xyz), _p(idx), bits, B, N, k, _p(rec), _stream())
     return rec
 
 
 def layer_conv(rec, directions, centre, support_slab, B, N, S, C, want_arg=False, want_split=False, full=False):
     """HS_layer.graph_conv after the projection, gcn3d.py:157-180 -> (B,N,C).
-    centre: (B*N, C) view (any row stride); support_slab: [C/4][B*N][S*4]."""
-    k = rec.shape[2]
+    centre: (B*N, C) view (any row stride); support_slab: [C/4][B*N][S*4]; rec (B,k,N,4) from edge_records."""
+    k = rec.shape[1]
     directions = _f32c(directions, "layer_conv")
     out = torch.empty((B, N, C), dtype=torch.float32, device=rec.device)
     arg = torch.empty((C // 4, B * N, S * 4), dtype=torch.uint8, device=rec.device) if want_arg else None
@@ -472,7 +472,7 @@ def scatter_add_rows(grad, index, N):
 
 def layer_conv_bwd(rec, directions, support_slab, arg_slab, grad2d, B, N, S, C, d_support):
     """-> d_directions (3,S*C); d_support: a (B*N, S*C) row-strided view that is overwritten (slab column order)."""
-    k = rec.shape[2]
+    k = rec.shape[1]
     directions = _f32c(directions, "layer_conv_bwd")
     lib = _lib.load()
     nb = lib.tgp_layer_conv_bwd_workspace(B, S, C)
