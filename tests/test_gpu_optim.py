@@ -61,6 +61,35 @@ def test_ranger_vs_reference_golden(tag):
         close_rel(nump(st["slow_buffer"]), z[f"{tag}_slow_{i}"], f"{tag} slow_buffer {i}", rel=2e-6)
 
 
+def test_ranger_weights_loaded_after_construction_follow_reference_trajectory():
+    """the reference workflow: build the optimiser on the random-init net, THEN load pretrained weights without optimiser
+    state (engine/train.py:52-55).  ranger2020.py:158-168 snapshots slow_buffer at a parameter's first step(), i.e. from
+    the loaded weights -- so the golden trajectory (recorded from p0) must be reproduced when p0 arrives after Ranger()."""
+    from tgpose_b200.ranger import Ranger
+    z = golden("ranger")
+    tag = "default"
+    n, steps, snaps = int(z["n_tensors"]), int(z["steps"]), set(int(s) for s in z["snaps"])
+    torch.manual_seed(3)
+    params = [torch.nn.Parameter(torch.randn(*z[f"p0_{i}"].shape).cuda()) for i in range(n)]       # "random init"
+    opt = Ranger(params, **CONFIGS[tag])
+    with torch.no_grad():
+        for i, p in enumerate(params):                                                             # load_state_dict does copy_()
+            p.copy_(torch.from_numpy(z[f"p0_{i}"]))
+    for t in range(steps):
+        opt.zero_grad()
+        for i, p in enumerate(params):
+            p.grad.copy_(torch.from_numpy(z[f"g_{t}_{i}"]))
+        opt.clip_grad_norm_(5)
+        opt.step()
+        if t in snaps:                                     # the Lookahead pull-back at step k = 6 is inside the snapshots
+            for i, p in enumerate(params):
+                close_update(nump(p), z[f"{tag}_p_{t}_{i}"], z[f"p0_{i}"], f"late-load step {t + 1} tensor {i}")
+    for i, p in enumerate(params):
+        close_rel(nump(opt.state[p]["slow_buffer"]), z[f"{tag}_slow_{i}"], f"late-load slow_buffer {i}", rel=2e-6)
+    with pytest.raises(RuntimeError):
+        opt.add_param_group({"params": [torch.nn.Parameter(torch.zeros(3).cuda())]})
+
+
 def test_ranger_groups_inactive_and_ragged_rows_vs_oracle():
     """two parameter groups with their own lr / weight decay, a tensor without a gradient (skipped like
     ranger2020.py:146-147), rows that are not 16-byte aligned, a 1-D tensor longer than one row piece, no clipping on

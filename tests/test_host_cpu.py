@@ -51,6 +51,19 @@ def test_no_cpu_fallback():
     layer = gcn3d.HS_layer(8, 8, 7)
     with pytest.raises(RuntimeError):
         layer(x, torch.rand(1, 16, 8), 4)
+    # the heads have no eager torch branch either: train and eval mode both refuse CPU tensors
+    from tgpose_b200 import posenet
+    dec = posenet.FaceRecon_decoder(16) if hasattr(posenet, "FaceRecon_decoder") else None
+    net = posenet.PoseNet9D()
+    for mode in (True, False):
+        net.train(mode)
+        with pytest.raises(RuntimeError):
+            net(torch.rand(2, 32, 3), torch.zeros(2, 1))
+    for name in ("rot_green", "rot_red"):
+        head = getattr(net, name)
+        with pytest.raises(RuntimeError):
+            head.train()(torch.rand(2, posenet.FEAT_C, 32))
+    del dec
 
 
 def test_state_dict_names_and_shapes():

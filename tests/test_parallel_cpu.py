@@ -16,7 +16,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, done):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
                       LOCAL_RANK=str(rank))
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -33,21 +33,26 @@ def _worker(rank, world, port, q):
     nb = parallel.allreduce_gradients(lin.parameters(), world)
     flat = torch.arange(10, dtype=torch.float32) * (rank + 1)          # a flat gradient arena (ranger.Ranger.flat_grads)
     nflat = parallel.allreduce_flat(flat, world, bucket_bytes=16)       # 4-element slices -> 3 collectives
-    q.put((rank, lo, hi, perm[:8].tolist(), lin.weight.grad.clone(), lin.bias.grad.clone(), nb, flat, nflat))
+    # plain lists, not tensors: a tensor travels as a shared-memory handle that dies with its producer
+    q.put((rank, lo, hi, perm[:8].tolist(), lin.weight.grad.tolist(), lin.bias.grad.tolist(), nb, flat.tolist(), nflat))
     dist.destroy_process_group()
+    done.wait(timeout=120)          # stay alive until the parent has drained the queue
 
 
 def test_two_rank_sharding_and_grad_allreduce():
     world, port = 2, _free_port()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    done = ctx.Event()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q, done)) for r in range(world)]
     for p in procs:
         p.start()
     res = sorted([q.get(timeout=120) for _ in range(world)], key=lambda t: t[0])
+    done.set()
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
+    res = [tuple(torch.tensor(v) if isinstance(v, list) and i in (4, 5, 7) else v for i, v in enumerate(t)) for t in res]
     (r0, lo0, hi0, perm0, gw0, gb0, nb0, f0, nf0), (r1, lo1, hi1, perm1, gw1, gb1, nb1, f1, nf1) = res
     assert nf0 == nf1 == 3 and torch.equal(f0, f1) and torch.allclose(f0, torch.arange(10, dtype=torch.float32) * 1.5)
     assert (lo0, hi0, lo1, hi1) == (0, 17, 17, 33)           # contiguous, disjoint, covering

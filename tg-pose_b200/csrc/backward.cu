@@ -667,10 +667,9 @@ extern "C" int tgp_layer_conv_bwd(const float* edge_rec, const float* directions
     if (smem + 13 * 1024 > 227 * 1024) return fail(TGP_EINVAL, "tgp_layer_conv_bwd: N*S too large for the shared-memory gradient table");
     const int threads = N >= 512 ? 1024 : (N >= 128 ? 256 : 128);
     cudaStream_t st = as_stream(stream);
-    static bool attr = false;
-    if (!attr) {
+    static std::atomic<unsigned long long> attr{0};   // one bit per device: function attributes are per device
+    if (first_on_device(attr)) {
         cudaFuncSetAttribute(layer_conv_bwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 13 * 1024);
-        attr = true;
     }
     dim3 grid(C / 4, B);
     float* part = static_cast<float*>(workspace);

@@ -207,10 +207,9 @@ extern "C" int tgp_dcd(const float* dist1, const float* dist2, const int32_t* id
     if (B <= 0 || n <= 0 || m <= 0) return fail(TGP_EINVAL, "tgp_dcd: sizes must be positive");
     const size_t smem = (size_t)(n + m) * sizeof(int);
     if (smem > 200 * 1024) return fail(TGP_EINVAL, "tgp_dcd: n + m too large for the shared-memory histograms");
-    static bool attr = false;
-    if (!attr) {
+    static std::atomic<unsigned long long> attr{0};   // one bit per device: function attributes are per device
+    if (first_on_device(attr)) {
         cudaFuncSetAttribute(dcd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        attr = true;
     }
     dcd_kernel<<<B, DCD_THREADS, smem, as_stream(stream)>>>(dist1, dist2, idx1, idx2, n, m, alpha, n_lambda, non_reg, loss, coef1, coef2);
     return check_launch("dcd_kernel");

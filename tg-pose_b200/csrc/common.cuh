@@ -33,6 +33,14 @@ inline int check_launch(const char* what) {
 
 inline cudaStream_t as_stream(tgp_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 
+// true the first time it is called with the current device for this guard (cudaFuncSetAttribute is per device)
+inline bool first_on_device(std::atomic<unsigned long long>& seen) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const unsigned long long bit = 1ull << (dev & 63);
+    return (seen.fetch_or(bit, std::memory_order_relaxed) & bit) == 0;
+}
+
 // index tensors arrive as int64 (torch.topk, gcn3d.py:21) or int32 (internal)
 template <typename IdxT>
 __device__ __forceinline__ int ld_idx(const IdxT* p, size_t i) {

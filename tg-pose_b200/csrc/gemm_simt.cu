@@ -408,10 +408,9 @@ int tgp_gemm_simt(const tgp_gemm_args* a, cudaStream_t st) {
         // (the summation order over k is the same in both kernels: the choice only depends on operand alignment)
         if (a->lda % 4 == 0 && a->ldb % 4 == 0 && (uintptr_t)a->A % 16 == 0 && (uintptr_t)a->Bmat % 16 == 0) {
             const size_t smem = (size_t)SKP_STAGES * SKP_STAGE_FLOATS * sizeof(float);
-            static bool attr_set = false;
-            if (!attr_set) {
+            static std::atomic<unsigned long long> attr_set{0};   // one bit per device: function attributes are per device
+            if (first_on_device(attr_set)) {
                 cudaFuncSetAttribute(gemm_skinny_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-                attr_set = true;
             }
             gemm_skinny_pipe_kernel<<<grid, 256, smem, st>>>(P);
             return check_launch("gemm_skinny_pipe_kernel");

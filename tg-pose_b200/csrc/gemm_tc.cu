@@ -845,10 +845,9 @@ static int launch_tc(const tgp_gemm_args* a, cudaStream_t st, int ksplit = 1, in
     const int num_tiles = tiles_mn * ksplit;
     const long zstride = ksplit > 1 ? a->M * (long)a->seg[0].ld : 0;
     const size_t smem = (size_t)TcStages<BN>::value * (TC_A_BYTES + BN * TC_BK * 4) + 1024 + 256 + TC_EPI_WARPS * 32 * 33 * sizeof(float);
-    static bool attr_set = false;
-    if (!attr_set) {
+    static std::atomic<unsigned long long> attr_set{0};   // one bit per device: function attributes are per device
+    if (first_on_device(attr_set)) {
         cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        attr_set = true;
     }
     const int grid = num_tiles < TGP_NUM_SMS ? num_tiles : TGP_NUM_SMS;
     // 128-bit epilogue: every width / boundary / leading dimension a multiple of 4 floats, every pointer 16-byte aligned

@@ -476,11 +476,10 @@ extern "C" int tgp_knn_xyz(const float* xyz, int B, int N, int k, int64_t* idx64
         // threshold selection; the whole cloud stays resident when it fits, otherwise both passes walk 8192-point tiles
         const int tile = N <= KS_TILE_MAX ? ((N + 63) & ~63) : KS_TILE_MAX;
         const size_t smem = (size_t)tile * sizeof(float4) + (size_t)(KS_THREADS / 32) * ks_warp_smem(k);
-        static bool attr_set = false;
-        if (!attr_set) {
+        static std::atomic<unsigned long long> attr_set{0};   // one bit per device: function attributes are per device
+        if (first_on_device(attr_set)) {
             cudaFuncSetAttribute(knn_xyz_sel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)(KS_TILE_MAX * sizeof(float4) + (KS_THREADS / 32) * ks_warp_smem(63)));
-            attr_set = true;
         }
         dim3 grid((N + KS_QPC - 1) / KS_QPC, B);
         knn_xyz_sel_kernel<<<grid, KS_THREADS, smem, st>>>(xyz, N, k, tile, ks_slots(k), idx64, idx32);

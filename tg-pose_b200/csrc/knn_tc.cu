@@ -585,8 +585,8 @@ int tgp_knn_tc(const float* x_split, const float* qn, int B, int N, int D, int k
     const int num_units = B * q_tiles;
     const size_t smem = (size_t)KT_STAGES * KT_STAGE_BYTES + 1024 + 256 + sizeof(float) * (TC_BM * KT_LDD + 2 * KT_BN);
     const size_t smem2 = (size_t)KT_STAGES * KT_STAGE_BYTES + 1024 + 256 + (size_t)TC_BM * KT2_CAP * 8 + TC_BM * 8 + KT_EPI_WARPS * 32 * 4;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static std::atomic<unsigned long long> attr_set{0};   // one bit per device: function attributes are per device
+    if (first_on_device(attr_set)) {
         cudaFuncSetAttribute(knn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         cudaFuncSetAttribute(knn_tc2_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         cudaFuncSetAttribute(knn_tc2_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -594,7 +594,6 @@ int tgp_knn_tc(const float* x_split, const float* qn, int B, int N, int D, int k
         cudaFuncSetAttribute(knn_tc2_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         cudaFuncSetAttribute(knn_tc2_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         cudaFuncSetAttribute(knn_tc2_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        attr_set = true;
     }
     if (smem > 227 * 1024 || smem2 > 227 * 1024) return fail(TGP_EINVAL, "tgp_knn_feat: shared memory budget exceeded");
     const int grid = num_units < TGP_NUM_SMS ? num_units : TGP_NUM_SMS;

@@ -26,8 +26,12 @@ class GraphedPoseNet:
         self.cat = torch.zeros(batch, 1, device=dev)
         self.perm1 = torch.zeros(self.p1, dtype=torch.int64, device=dev)
         self.perm2 = torch.zeros(self.p2, dtype=torch.int64, device=dev)
-        self.h_perm1 = torch.zeros(self.p1, dtype=torch.int64).pin_memory()
-        self.h_perm2 = torch.zeros(self.p2, dtype=torch.int64).pin_memory()
+        # pinned staging, double-buffered: the H2D copy of draw i may still be queued behind replay i-1 when the host
+        # writes draw i+1, so each buffer is reused only after the event recorded behind its last copy has completed
+        self.h_perm = [(torch.zeros(self.p1, dtype=torch.int64).pin_memory(),
+                        torch.zeros(self.p2, dtype=torch.int64).pin_memory()) for _ in range(2)]
+        self._copied = [None, None]
+        self._slot = 0
         self._draw()
         # a valid input for the warm-up / capture passes (the values are overwritten before every replay)
         self.pts.copy_(torch.rand(batch, n_points, 3, device=dev) - 0.5)
@@ -49,10 +53,18 @@ class GraphedPoseNet:
 
     def _draw(self):
         """the two CPU-generator draws of Pool_layer.forward, in the reference's order (gcn3d.py:241-243)."""
-        self.h_perm1.copy_(torch.randperm(self.n0)[:self.p1])
-        self.h_perm2.copy_(torch.randperm(self.n1)[:self.p2])
-        self.perm1.copy_(self.h_perm1, non_blocking=True)
-        self.perm2.copy_(self.h_perm2, non_blocking=True)
+        i = self._slot
+        self._slot ^= 1
+        if self._copied[i] is not None:
+            self._copied[i].synchronize()
+        h1, h2 = self.h_perm[i]
+        h1.copy_(torch.randperm(self.n0)[:self.p1])
+        h2.copy_(torch.randperm(self.n1)[:self.p2])
+        self.perm1.copy_(h1, non_blocking=True)
+        self.perm2.copy_(h2, non_blocking=True)
+        ev = self._copied[i] or torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.perm1.device))
+        self._copied[i] = ev
 
     def __call__(self, points, obj_id):
         """points (B,N,3), obj_id (B,1): host (pinned) or device tensors.  Returns the static output dict (valid

@@ -19,8 +19,17 @@ TC_ENABLED = True
 EVENT_LOG = None
 
 
+# device of the op being assembled: set by _f32c / _idx from the op's own tensors, so that the stream handed to the
+# C-ABI and the launch itself belong to the tensors' device, not to whatever device happens to be current
+_DEV = None
+
+
 def _run(name, cfn, *args):
     log = EVENT_LOG
+    if _DEV is not None and _DEV.index is not None and _DEV.index != torch.cuda.current_device():
+        with torch.cuda.device(_DEV):
+            _lib.check(cfn(*args), "tgp_" + name)
+        return
     if log is None:
         _lib.check(cfn(*args), "tgp_" + name)
         return
@@ -37,12 +46,14 @@ def _p(t):
 
 
 def _stream():
-    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    return ctypes.c_void_p(torch.cuda.current_stream(_DEV).cuda_stream)
 
 
 def _f32c(t, name):
+    global _DEV
     if not t.is_cuda:
         raise RuntimeError(f"{name}: expected a CUDA tensor (tg-pose_b200 has no CPU path)")
+    _DEV = t.device
     if t.dtype != torch.float32:
         t = t.float()
     return t.contiguous()

@@ -36,6 +36,12 @@ def _fold(conv, bn):
     return scale, shift
 
 
+
+def _require_cuda(t, what):
+    """the heads run on the library kernels only: there is no CPU / eager fallback (north_star)."""
+    if not t.is_cuda:
+        raise RuntimeError(f"{what}: CUDA tensor required -- tg-pose_b200 has no CPU path")
+
 class _Packed:
     """weights of one fused 1x1-conv stage: (Ncols, K) matrix, its tensor-core split, affine and activation."""
 
@@ -85,10 +91,9 @@ class Face_Dec(nn.Module):
 
     def forward(self, x):
         """x (B, C, N) -> recon (B, N, 3)."""
-        if self.training and x.is_cuda:
-            return self.forward_rows(x.permute(0, 2, 1).contiguous())
+        _require_cuda(x, "FaceRecon decoder")
         if self.training:
-            return self.recon_head(self.conv1d_block(x)).permute(0, 2, 1)
+            return self.forward_rows(x.permute(0, 2, 1).contiguous())
         h = x.permute(0, 2, 1).contiguous()
         b = self.conv1d_block
         h = pointwise(h, b[0], b[1], "relu")
@@ -144,12 +149,10 @@ class PH_Predictor(nn.Module):
     def forward(self, feat):
         """feat (B,N,1286) -> (feat + pi1 + pi2 as (B,1286,N), h1, h2)."""
         bs = feat.shape[0]
-        if self.training and feat.is_cuda:
+        _require_cuda(feat, "PH_Predictor")
+        if self.training:
             f = _train_chain(feat.reshape(-1, feat.shape[2]), [(self.conv_5[0], self.conv_5[1], 0.2)])
             pooled = f.view(bs, feat.shape[1], -1).max(dim=1)[0]
-        elif self.training:
-            f = self.conv_5(feat.permute(0, 2, 1))
-            pooled = F.adaptive_max_pool1d(f, 1).view(bs, -1)
         else:
             f = pointwise(feat, self.conv_5[0], self.conv_5[1], "leaky")
             pooled = f.max(dim=1)[0]
@@ -205,14 +208,11 @@ class _PointHead(nn.Module):
 
     def trunk(self, x):
         """x (B, f, N) -> (B, k)."""
-        if self.training and x.is_cuda:
+        _require_cuda(x, "pose head trunk")
+        if self.training:
             B, C, N = x.shape
             h = _train_chain(x.permute(0, 2, 1).reshape(B * N, C), [(self.conv1, self.bn1, 0.0), (self.conv2, self.bn2, 0.0)])
             x = h.view(B, N, -1).max(dim=1)[0].unsqueeze(2)
-        elif self.training:
-            x = F.relu(self.bn1(self.conv1(x)))
-            x = F.relu(self.bn2(self.conv2(x)))
-            x = torch.max(x, 2, keepdim=True)[0]
         else:
             h = pointwise(x.permute(0, 2, 1).contiguous(), self.conv1, self.bn1, "relu")
             h = pointwise(h, self.conv2, self.bn2, "relu")
@@ -463,7 +463,11 @@ class PoseNet9D(nn.Module):
         return out
 
     def forward(self, points, obj_id, enable_proj=False):
-        if not self.training and not self.only_encoder and points.is_cuda:
+        _require_cuda(points, "PoseNet9D")
+        # the fused inference pipeline bypasses autograd and the optional projection layer: take it only when nothing
+        # can ask for a gradient and enable_proj is off (FaceRecon.py:83-84); otherwise the module-by-module path runs
+        if (not self.training and not self.only_encoder and not enable_proj
+                and not (torch.is_grad_enabled() and (points.requires_grad or any(p.requires_grad for p in self.parameters())))):
             return self._forward_fused_eval(points, obj_id, enable_proj)
         mean = points.mean(dim=1, keepdim=True)
         centred = points - mean

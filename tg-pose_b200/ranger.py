@@ -129,7 +129,11 @@ class Ranger(Optimizer):
                     gview.copy_(old_grad)
                 p.grad = gview
                 self._views.append(gview)
-        self.flat_slow = self.flat_params.clone()     # state["slow_buffer"].copy_(p.data), ranger2020.py:163-165
+        # state["slow_buffer"].copy_(p.data) happens LAZILY, at a parameter's first step() (ranger2020.py:158-168), not
+        # here: the reference workflow builds the optimiser first and loads the pretrained weights afterwards
+        # (engine/train.py:52-55), so the snapshot must see the loaded weights.
+        self.flat_slow = torch.zeros_like(self.flat_params)
+        self._slow_ready = False
         for p, off in zip(plist, offsets):
             self.state[p] = {"step": 0, **self._state_views(p, off)}
         # row ranges per parameter group (rows are emitted in parameter order)
@@ -199,6 +203,9 @@ class Ranger(Optimizer):
         loss = None                                   # the reference ignores the closure too (ranger2020.py:134-140)
         if not getattr(self, "_reduced", False):
             self._reduce()
+        if not self._slow_ready:                      # first step without a loaded state: slow_buffer <- p.data as it is NOW
+            self.flat_slow.copy_(self.flat_params)
+            self._slow_ready = True
         self.steps += 1
         st = torch.cuda.current_stream(self.flat_params.device).cuda_stream
         a = self._active_dev.data_ptr() if self._active_dev is not None else None
@@ -250,6 +257,14 @@ class Ranger(Optimizer):
             steps = max(steps, step)
             self.state[p] = {"step": step, **views}
         self.steps = steps
+        self._slow_ready = steps > 0                  # a resumed run keeps the checkpoint's slow buffers
+
+    def add_param_group(self, param_group):
+        """parameters are fixed once the arenas are laid out (the constructor's own calls come before that)."""
+        if hasattr(self, "_plist"):
+            raise RuntimeError("Ranger.add_param_group: the flat arenas are already laid out; pass every parameter "
+                               "group to the constructor")
+        super().add_param_group(param_group)
 
     @property
     def total_norm(self):

@@ -59,12 +59,15 @@ class TrainStep:
             self.opt = torch.optim.Adam(self.params, lr=lr, fused=self.params[0].is_cuda)
         else:
             raise ValueError(f"TrainStep: unknown optimizer {optimizer!r}")
+        # the reference seeds ONCE at start-up (engine/train.py seed_init_fn): every rank starts from the same CPU-RNG
+        # state and consumes it identically (Pool_layer's randperm draws), so the ranks stay in lock-step while the
+        # subsample -- and every dropout mask -- changes from step to step.
         self.seed = seed
+        parallel.seed_for_forward(seed)
         self.buckets = 0
 
     def __call__(self, pts, cat, tgt):
         self.net.train()
-        parallel.seed_for_forward(self.seed)
         out = self.net(pts, cat)
         ls = losses(out, pts, tgt)
         total = 0.1 * ls["recon"] + 0.9 * ls["R_DCD"] + 0.1 * ls["pose"]        # weights as RL_TDA.py:214
