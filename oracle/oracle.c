@@ -375,8 +375,11 @@ void orc_orl_global(const float* f, const int64_t* idx, int B, int N, int k, int
  * and tools/pyTorchChamferDistance/chamfer_distance.cpp:59-87 nnsearch:
  *   d = dx*dx + dy*dy + dz*dz with dx = x2 - x1 (exact difference form), strict '<'
  *   so the lowest index wins ties.
- * contract != 0 reproduces what nvcc's default -fmad=true makes of the CUDA source
- * (fma(dz,dz, fma(dy,dy, dx*dx))); contract == 0 is the plain C++ rounding of nnsearch.
+ * contract != 0 reproduces what nvcc 12.9 (default -fmad=true) makes of the CUDA source's
+ * `x2*x2+y2*y2+z2*z2` for sm_100a -- fma(dz,dz, fma(dx,dx, dy*dy)): FMUL on y, FFMA on x, FFMA on z, read off the
+ * SASS of oracle/_ref/chamfer3D (built from the reference's own chamfer3D.cu by oracle/build_ref.py) and checked
+ * bit for bit against that kernel on the GPU (tests/test_gpu_ref_chamfer.py);
+ * contract == 0 is the plain C++ rounding of nnsearch.
  */
 void orc_chamfer_nn(const float* a, const float* b2, int B, int n, int m, int contract, float* dist, int32_t* idx) {
 #pragma omp parallel for schedule(static)
@@ -388,7 +391,7 @@ void orc_chamfer_nn(const float* a, const float* b2, int B, int n, int m, int co
         for (int j = 0; j < m; ++j) {
             float dx = qb[j * 3] - p[0], dy = qb[j * 3 + 1] - p[1], dz = qb[j * 3 + 2] - p[2];
             float d;
-            if (contract) d = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+            if (contract) d = fmaf(dz, dz, fmaf(dx, dx, dy * dy));
             else { d = dx * dx; d = d + dy * dy; d = d + dz * dz; }
             if (j == 0 || d < best) { best = d; bj = j; }
         }

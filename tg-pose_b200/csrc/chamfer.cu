@@ -2,60 +2,165 @@
 //
 // Replaces NmDistanceKernel / NmDistanceGradKernel (reference losses/chamfer3D/chamfer3D.cu:12-195).
 // The reference launches dim3(32,16)x512 twice, re-stages the target cloud in every y-block
-// (13 of 16 idle at n ~ 1k) and keeps the running minimum in global memory; here both directions
-// are one launch, a CTA owns 128 queries of one (cloud, direction), the running (min, argmin)
-// stays in registers and the per-cloud sums calc_cd needs (TDA_loss_sym_recon.py:495-509) are
-// reduced in the same kernel.
+// (13 of 16 idle at n ~ 1k), tracks (min, argmin) with a compare + two selects per pair and keeps
+// the running minimum in global memory.  Here both directions are one launch; a thread owns FOUR
+// queries (every candidate fetched from shared memory feeds 4 distance evaluations); candidates are
+// staged as PAIRS (x0,x1,y0,y1 | z0,z1) so that the 6 arithmetic operations of a distance run as
+// packed FADD2 / FMUL2 / FFMA2 on two candidates at once; and the inner loop tracks only the running
+// MINIMUM (one 3-input FMNMX per query and candidate pair, on the ALU pipe, beside the FMA pipe)
+// plus, per 32-candidate chunk, which chunk last lowered it.  The arg-min is recovered afterwards
+// by re-evaluating that one chunk (bit-identical arithmetic) and taking the first candidate whose
+// distance equals the minimum -- the lowest index on ties, like the reference's strict '<'.
+// The per-cloud sums calc_cd needs (TDA_loss_sym_recon.py:495-509) are reduced in the same kernel.
 //
-// Arithmetic: d = fma(dz,dz, fma(dy,dy, dx*dx)) with dx = x2 - x1 -- what nvcc's default
-// -fmad=true makes of chamfer3D.cu:32-35 -- and strict '<', so the lowest index wins ties.
+// Arithmetic: d = fma(dz,dz, fma(dx,dx, dy*dy)) with dx = x2 - x1 -- what nvcc 12.9's default
+// -fmad=true makes of chamfer3D.cu:32-35 for sm_100a (FMUL on y, FFMA on x, FFMA on z in the SASS of
+// oracle/_ref/chamfer3D); tests/test_gpu_ref_chamfer.py holds this kernel bit-equal to that build.
 #include "common.cuh"
 #include <math_constants.h>
+#include <stdlib.h>
 
 namespace tgp {
 
-constexpr int CH_THREADS = 128;
-constexpr int CH_TILE = 2048;
+constexpr int CH_Q = 4;            // queries per thread
+constexpr int CH_CHUNK = 8;        // candidates per arg-min chunk (4 pairs)
+constexpr int CH_PPC = CH_CHUNK / 2;
+constexpr int CH_XY_STRIDE = CH_PPC + 1;   // float4 slots per chunk: one pad slot rotates the banks from chunk to chunk, so the
+constexpr int CH_Z_STRIDE = CH_PPC + 2;    // arg-min pass (every lane in a different chunk) spreads over the banks; z: 16-byte aligned
+constexpr int CH_TILE = 1152;      // candidates staged per pass (18 KB: the 1024 / 1028-point clouds of the path in one pass)
+constexpr int CH_NCHUNK = CH_TILE / CH_CHUNK;
+constexpr int CH_MAX_THREADS = 128;
 
-__global__ void __launch_bounds__(CH_THREADS)
+__device__ __forceinline__ unsigned long long ch_pack(float lo, float hi) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void ch_unpack(unsigned long long v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long ch_add2(unsigned long long a, unsigned long long b) {
+    unsigned long long d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ unsigned long long ch_mul2(unsigned long long a, unsigned long long b) {
+    unsigned long long d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ unsigned long long ch_fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ float ch_min3(float a, float b, float c) {
+    float d;
+    asm("min.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
+
+__global__ void __launch_bounds__(CH_MAX_THREADS)
 chamfer_fwd_kernel(const float* __restrict__ xyz1, const float* __restrict__ xyz2, int n, int m,
                    float* __restrict__ dist1, float* __restrict__ dist2, int32_t* __restrict__ idx1,
                    int32_t* __restrict__ idx2, float* __restrict__ sums) {
-    __shared__ float4 cand[CH_TILE];
+    __shared__ __align__(16) float4 cxy[CH_NCHUNK * CH_XY_STRIDE];     // (x0, x1, y0, y1) of candidate pair p
+    __shared__ __align__(16) float2 cz[CH_NCHUNK * CH_Z_STRIDE];       // (z0, z1)
     const int dir = blockIdx.z;
     const long b = blockIdx.y;
     const int nq = dir == 0 ? n : m, nc = dir == 0 ? m : n;
-    if ((int)blockIdx.x * CH_THREADS >= nq) return;  // uniform per CTA
+    const int qbase = blockIdx.x * (blockDim.x * CH_Q);
+    if (qbase >= nq) return;  // uniform per CTA
     const float* q = (dir == 0 ? xyz1 : xyz2) + b * nq * 3;
     const float* c = (dir == 0 ? xyz2 : xyz1) + b * nc * 3;
     float* dist = (dir == 0 ? dist1 : dist2) + b * nq;
     int32_t* idx = (dir == 0 ? idx1 : idx2) + b * nq;
 
-    const int i = blockIdx.x * CH_THREADS + threadIdx.x;
-    float x1 = 0.f, y1 = 0.f, z1 = 0.f;
-    if (i < nq) { x1 = __ldg(q + i * 3); y1 = __ldg(q + i * 3 + 1); z1 = __ldg(q + i * 3 + 2); }
-    float best = CUDART_INF_F;
-    int bi = 0;
+    // query u of this thread: qbase + u * blockDim.x + threadIdx.x (coalesced result stores); x2 - x1 is one packed add
+    // of the broadcast (-x1)
+    float qx[CH_Q], qy[CH_Q], qz[CH_Q];
+    float best[CH_Q], cm[CH_Q];
+    int bchunk[CH_Q], bi[CH_Q];
+#pragma unroll
+    for (int u = 0; u < CH_Q; ++u) {
+        const int i = min(qbase + u * (int)blockDim.x + (int)threadIdx.x, nq - 1);
+        qx[u] = __ldg(q + i * 3); qy[u] = __ldg(q + i * 3 + 1); qz[u] = __ldg(q + i * 3 + 2);
+        best[u] = CUDART_INF_F; cm[u] = CUDART_INF_F; bchunk[u] = -1; bi[u] = 0;
+    }
     for (int t0 = 0; t0 < nc; t0 += CH_TILE) {
         const int nt = min(CH_TILE, nc - t0);
+        const int nchunk = (nt + CH_CHUNK - 1) / CH_CHUNK;
         __syncthreads();
-        for (int j = threadIdx.x; j < nt; j += CH_THREADS)
-            cand[j] = make_float4(__ldg(c + (t0 + j) * 3), __ldg(c + (t0 + j) * 3 + 1), __ldg(c + (t0 + j) * 3 + 2), 0.f);
+        // candidates past the end are +inf: their distance is +inf and never lowers a minimum
+        for (int p = threadIdx.x; p < nchunk * CH_PPC; p += blockDim.x) {
+            float x0 = CUDART_INF_F, y0 = CUDART_INF_F, z0 = CUDART_INF_F, x1 = CUDART_INF_F, y1 = CUDART_INF_F, z1 = CUDART_INF_F;
+            if (2 * p < nt) {
+                const float* s = c + (long)(t0 + 2 * p) * 3;
+                x0 = __ldg(s); y0 = __ldg(s + 1); z0 = __ldg(s + 2);
+                if (2 * p + 1 < nt) { x1 = __ldg(s + 3); y1 = __ldg(s + 4); z1 = __ldg(s + 5); }
+            }
+            const int ch = p / CH_PPC, pp = p - ch * CH_PPC;
+            cxy[ch * CH_XY_STRIDE + pp] = make_float4(x0, x1, y0, y1);
+            cz[ch * CH_Z_STRIDE + pp] = make_float2(z0, z1);
+        }
         __syncthreads();
-#pragma unroll 8
-        for (int j = 0; j < nt; ++j) {
-            const float4 p = cand[j];
-            const float dx = p.x - x1, dy = p.y - y1, dz = p.z - z1;
-            const float d = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
-            if (d < best) { best = d; bi = t0 + j; }
+        unsigned long long nqx[CH_Q], nqy[CH_Q], nqz[CH_Q];
+#pragma unroll
+        for (int u = 0; u < CH_Q; ++u) {
+            nqx[u] = ch_pack(-qx[u], -qx[u]); nqy[u] = ch_pack(-qy[u], -qy[u]); nqz[u] = ch_pack(-qz[u], -qz[u]);
+        }
+#pragma unroll 2
+        for (int ch = 0; ch < nchunk; ++ch) {
+#pragma unroll
+            for (int pp = 0; pp < CH_PPC; ++pp) {
+                const float4 a = cxy[ch * CH_XY_STRIDE + pp];
+                const float2 zz = cz[ch * CH_Z_STRIDE + pp];
+                const unsigned long long ax = ch_pack(a.x, a.y), ay = ch_pack(a.z, a.w), az = ch_pack(zz.x, zz.y);
+#pragma unroll
+                for (int u = 0; u < CH_Q; ++u) {
+                    const unsigned long long dx = ch_add2(ax, nqx[u]), dy = ch_add2(ay, nqy[u]), dz = ch_add2(az, nqz[u]);
+                    float d0, d1;
+                    ch_unpack(ch_fma2(dz, dz, ch_fma2(dx, dx, ch_mul2(dy, dy))), d0, d1);
+                    cm[u] = ch_min3(cm[u], d0, d1);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < CH_Q; ++u) {
+                if (cm[u] < best[u]) { best[u] = cm[u]; bchunk[u] = ch; }     // strict: the earliest chunk keeps a tie
+                cm[u] = CUDART_INF_F;
+            }
+        }
+        // arg-min of the queries whose minimum fell inside this tile: first candidate of the winning chunk whose
+        // (bit-identically recomputed) distance equals the minimum; the chunk is still in shared memory
+#pragma unroll
+        for (int u = 0; u < CH_Q; ++u) {
+            if (bchunk[u] < 0) continue;
+            const int ch = bchunk[u];
+            int w = CH_CHUNK - 1;
+#pragma unroll
+            for (int pp = CH_PPC - 1; pp >= 0; --pp) {
+                const float4 a = cxy[ch * CH_XY_STRIDE + pp];
+                const float2 zz = cz[ch * CH_Z_STRIDE + pp];
+                const float dx1 = __fadd_rn(a.y, -qx[u]), dy1 = __fadd_rn(a.w, -qy[u]), dz1 = __fadd_rn(zz.y, -qz[u]);
+                const float dx0 = __fadd_rn(a.x, -qx[u]), dy0 = __fadd_rn(a.z, -qy[u]), dz0 = __fadd_rn(zz.x, -qz[u]);
+                if (__fmaf_rn(dz1, dz1, __fmaf_rn(dx1, dx1, __fmul_rn(dy1, dy1))) == best[u]) w = 2 * pp + 1;
+                if (__fmaf_rn(dz0, dz0, __fmaf_rn(dx0, dx0, __fmul_rn(dy0, dy0))) == best[u]) w = 2 * pp;
+            }
+            bi[u] = t0 + ch * CH_CHUNK + w;
+            bchunk[u] = -1;
         }
     }
     float s_d = 0.f, s_r = 0.f;
-    if (i < nq) {
-        dist[i] = best;
-        idx[i] = bi;
-        s_d = best;
-        s_r = sqrtf(best);
+#pragma unroll
+    for (int u = 0; u < CH_Q; ++u) {
+        const int i = qbase + u * (int)blockDim.x + (int)threadIdx.x;
+        if (i < nq) {
+            // every distance +inf / NaN (no chunk ever lowered the minimum): the reference takes candidate 0 (chamfer3D.cu:36)
+            dist[i] = best[u];
+            idx[i] = bi[u];
+            s_d += best[u];
+            s_r += sqrtf(best[u]);
+        }
     }
     if (sums) {
         s_d = warp_sum(s_d);
@@ -177,9 +282,22 @@ extern "C" int tgp_chamfer_fwd(const float* xyz1, const float* xyz2, int B, int 
     if (!xyz1 || !xyz2 || !dist1 || !dist2 || !idx1 || !idx2) return fail(TGP_EINVAL, "tgp_chamfer_fwd: null pointer");
     if (B <= 0 || n <= 0 || m <= 0) return fail(TGP_EINVAL, "tgp_chamfer_fwd: sizes must be positive");
     if (B > 65535) return fail(TGP_EINVAL, "tgp_chamfer_fwd: B > 65535");
+    // threads per CTA: 4 queries each; chosen so that the CTAs of a cloud come out evenly filled (1028 queries ->
+    // 3 CTAs of 96 threads rather than 2 full + 1 nearly empty CTA of 128)
     const int nmax = n > m ? n : m;
-    dim3 grid((nmax + CH_THREADS - 1) / CH_THREADS, B, 2);
-    chamfer_fwd_kernel<<<grid, CH_THREADS, 0, as_stream(stream)>>>(xyz1, xyz2, n, m, dist1, dist2, idx1, idx2, sums);
+    int threads = CH_MAX_THREADS;
+    {
+        double best = -1.0;
+        for (int t = CH_MAX_THREADS; t >= 32; t -= 32) {
+            const int g = (nmax + t * CH_Q - 1) / (t * CH_Q);
+            double eff = (double)nmax / ((double)g * t * CH_Q);
+            if ((long)g * B * 2 < 2 * TGP_NUM_SMS) eff *= 0.8;      // too few CTAs to fill the machine: prefer smaller ones
+            if (eff > best + 0.03) { best = eff; threads = t; }
+        }
+    }
+    if (const char* e = getenv("TGP_CH_THREADS")) { const int v = atoi(e); if (v >= 32 && v <= CH_MAX_THREADS && v % 32 == 0) threads = v; }   // tuning hook
+    dim3 grid((nmax + threads * CH_Q - 1) / (threads * CH_Q), B, 2);
+    chamfer_fwd_kernel<<<grid, threads, 0, as_stream(stream)>>>(xyz1, xyz2, n, m, dist1, dist2, idx1, idx2, sums);
     return check_launch("chamfer_fwd_kernel");
 }
 
