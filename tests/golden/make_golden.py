@@ -315,6 +315,97 @@ def posenet_case():
     save("posenet", **out)
 
 
+def _ref_functions(relpath, names):
+    """source of top-level functions of a reference file that cannot be IMPORTED (losses/TDA_loss_sym_recon.py needs
+    tools.geom_utils, whose source is absent from the reference): the function bodies are cut out of the file with `ast`
+    and executed here unchanged -- nothing is copied into the repo."""
+    import ast
+    src = open(os.path.join(REF, relpath)).read()
+    tree = ast.parse(src)
+    out = {}
+    for node in tree.body:
+        if isinstance(node, ast.FunctionDef) and node.name in names:
+            out[node.name] = ast.get_source_segment(src, node)
+    assert set(out) == set(names), (relpath, names, list(out))
+    return out
+
+
+def dcd_case():
+    """calc_dcd / calc_cd of losses/TDA_loss_sym_recon.py (:411-450, :495-509), executed from the reference source with
+    the reference's own pure-torch chamfer (losses/metrics/CD/chamfer_python.py:18-39, the oracle of its unit test) in
+    place of the CUDA extension; alpha = 70, n_lambda = 0.3 as at the call site (:338), and a non_reg case."""
+    fns = _ref_functions("losses/TDA_loss_sym_recon.py", ["calc_dcd", "calc_cd"])
+
+    class _Cham:                                   # stands in for dist_chamfer_3D.chamfer_3DDist()
+        def __call__(self, a, b):
+            return chamfer_python.distChamfer(a, b)
+
+    class _Mod:
+        chamfer_3DDist = _Cham
+
+    ns = {"torch": torch, "dist_chamfer_3D": _Mod}
+    exec(fns["calc_cd"], ns)
+    exec(fns["calc_dcd"], ns)
+    g = torch.Generator().manual_seed(606)
+    out = {}
+    for tag, B, n, m, kw in [("a", 3, 257, 200, dict(alpha=70, n_lambda=0.3)),
+                             ("b", 2, 1028, 1024, dict(alpha=70, n_lambda=0.3)),
+                             ("c", 2, 150, 400, dict(alpha=40, n_lambda=0.5, non_reg=True)),
+                             ("d", 1, 64, 64, dict())]:
+        # clustered prediction against a uniform target: many predictions share a nearest target point (count > 1)
+        pred = (torch.rand(B, n, 3, generator=g) * 0.25 + 0.1).requires_grad_(True)
+        gt = torch.rand(B, m, 3, generator=g) * 0.5
+        with torch.enable_grad():
+            loss = ns["calc_dcd"](pred, gt, **kw)
+            cd_p, cd_t = ns["calc_cd"](pred, gt)
+            (loss.sum() + 0.25 * cd_t.sum()).backward()
+        out[f"{tag}_pred"], out[f"{tag}_gt"] = np_(pred), np_(gt)
+        out[f"{tag}_loss"], out[f"{tag}_cd_p"], out[f"{tag}_cd_t"] = np_(loss), np_(cd_p), np_(cd_t)
+        out[f"{tag}_grad"] = np_(pred.grad)
+        out[f"{tag}_kw"] = np.array([kw.get("alpha", 0.1), kw.get("n_lambda", 0.3), 1.0 if kw.get("non_reg") else 0.0])
+    save("dcd", **out)
+
+
+def posenet_1028_case():
+    """full PoseNet9D (eval) at 4 x 1028 points -- the benchmarked cloud size, where every level has >= 256 rows and the
+    new path runs tcgen05 everywhere -- with the 14 recorded index tensors.  `feat` is kept on 24 rows per cloud."""
+    from network.fs_net_repo.PoseNet9D import PoseNet9D
+    torch.manual_seed(0)
+    net = PoseNet9D().eval()
+    g = torch.Generator().manual_seed(1028)
+    B, N = 4, 1028
+    pts = nocs_cloud(g, B, N)
+    cat_id = torch.randint(0, 6, (B, 1), generator=g).float()
+    calls = []
+    orig_knn, orig_nn = gcn3d.get_neighbor_index, gcn3d.get_nearest_index
+
+    def rec_knn(v, k):
+        r = orig_knn(v, k)
+        calls.append(np_(r).astype(np.int16))
+        return r
+
+    def rec_nn(t, s_):
+        r = orig_nn(t, s_)
+        calls.append(np_(r).astype(np.int16))
+        return r
+
+    gcn3d.get_neighbor_index, gcn3d.get_nearest_index = rec_knn, rec_nn
+    try:
+        with torch.no_grad():
+            torch.manual_seed(7)
+            res = net(pts, cat_id)
+    finally:
+        gcn3d.get_neighbor_index, gcn3d.get_nearest_index = orig_knn, orig_nn
+    assert len(calls) == 14
+    rows = torch.randperm(N, generator=g)[:24].sort()[0]
+    out = {"pts": np_(pts), "cat_id": np_(cat_id), "feat_rows": np_(rows).astype(np.int16)}
+    for k_, v in res.items():
+        out["out_" + k_] = np_(v[:, rows]) if k_ == "feat" else np_(v)
+    for i, c in enumerate(calls):
+        out[f"idx_{i:02d}"] = c
+    save("posenet_1028", **out)
+
+
 def _patched(knn_list):
     """replay recorded index tensors into the reference (it resolves get_neighbor_index through module globals)."""
     it = iter(knn_list)
@@ -472,6 +563,7 @@ def ranger_case():
 
 if __name__ == "__main__":
     cases = {"knn": knn_cases, "gather_dir": gather_dir_cases, "conv": conv_cases, "chamfer": chamfer_cases,
-             "face_enc": face_enc_case, "posenet": posenet_case, "backward": backward_cases, "ranger": ranger_case}
+             "face_enc": face_enc_case, "posenet": posenet_case, "backward": backward_cases, "ranger": ranger_case,
+             "dcd": dcd_case, "posenet_1028": posenet_1028_case}
     for name in (sys.argv[1:] or list(cases)):       # python make_golden.py [case ...]
         cases[name]()

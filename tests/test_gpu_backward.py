@@ -323,6 +323,26 @@ def test_dcd_vs_oracle(B, n, m):
     assert torch.isfinite(a.grad).all()
 
 
+@pytest.mark.parametrize("tag", list("abcd"))
+def test_dcd_vs_reference_golden(tag):
+    """calc_dcd / calc_cd and their gradient w.r.t. the prediction against the REFERENCE'S OWN functions
+    (losses/TDA_loss_sym_recon.py:411-450, :495-509 executed from source by make_golden.py with the reference's pure-torch
+    chamfer): loss rel 1e-4, gradient by the gradient rule of tests/util.py."""
+    from tgpose_b200.dist_chamfer_3D import calc_cd, calc_dcd
+    from util import golden
+    g = golden("dcd")
+    alpha, lam, non_reg = float(g[f"{tag}_kw"][0]), float(g[f"{tag}_kw"][1]), bool(g[f"{tag}_kw"][2])
+    pred = torch.from_numpy(g[f"{tag}_pred"]).cuda().requires_grad_(True)
+    gt = torch.from_numpy(g[f"{tag}_gt"]).cuda()
+    loss = calc_dcd(pred, gt, alpha=alpha, n_lambda=lam, non_reg=non_reg)
+    cd_p, cd_t = calc_cd(pred, gt)
+    assert_close(nump(loss), g[f"{tag}_loss"], what=f"calc_dcd {tag}")
+    assert_close(nump(cd_p), g[f"{tag}_cd_p"], what="cd_p")
+    assert_close(nump(cd_t), g[f"{tag}_cd_t"], what="cd_t")
+    (loss.sum() + 0.25 * cd_t.sum()).backward()
+    assert_grad_close(nump(pred.grad), g[f"{tag}_grad"], what=f"d (dcd + cd_t) / d pred {tag}")
+
+
 @pytest.mark.parametrize("B,n,m", [(3, 300, 100), (2, 64, 257)])
 def test_dcd_non_reg_vs_oracle(B, n, m):
     """calc_dcd(non_reg=True): both point-count ratios clamped to >= 1 (TDA_loss_sym_recon.py:418-420)."""

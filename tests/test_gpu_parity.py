@@ -398,8 +398,9 @@ def test_face_enc_injected_and_free():
         feat_free, fg = enc(pts, cat)
     assert feat.shape == (2, 128, 1286) and fg.shape == (2, 1286, 128)
     assert_close(nump(feat), g["feat"], what="Face_Enc feat with reference indices (T2)")
-    # xyz-space index tensors of the free run are bit-exact vs the reference (slots 0,1,3,4,6,8,9,11,12,13)
-    for slot in (0, 1, 3, 4, 12):
+    # xyz-space index tensors of the free run are bit-exact vs the reference -- all ten of them (the pooled levels see
+    # the same points because Pool_layer's permutation comes from the same CPU seed)
+    for slot in (0, 1, 3, 4, 6, 8, 9, 11, 12, 13):
         assert np.array_equal(nump(enc._record[slot]).astype(np.int64), g[f"idx_{slot:02d}"].astype(np.int64)), slot
     frac = frac_close(nump(feat_free), g["feat"])
     print(f"T3 free-running in-tolerance fraction: {frac:.4f}")
@@ -507,6 +508,72 @@ def test_posenet_golden():
         assert np.degrees(np.arccos(cosang)).max() < 0.25, k
     for k in ("Pred_T", "Pred_s"):
         assert np.abs(nump(out[k]) - g["out_" + k]).max() < 1e-4, k
+
+
+def _axis_angle_deg(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    cosang = np.clip((a * b).sum(1) / (np.linalg.norm(a, axis=1) * np.linalg.norm(b, axis=1)), -1, 1)
+    return float(np.degrees(np.arccos(cosang)).max())
+
+
+def test_posenet_1028_golden_tensor_core_path():
+    """T2 at the BENCHMARKED cloud size: 4 x 1028 points, so every level has >= 256 rows and every contraction of the
+    encoder runs on tcgen05 (3xTF32), the heads on mixed operands -- against the reference's own PoseNet9D output with its
+    14 index tensors replayed (tests/golden/posenet_1028.npz).  T3: the free-running fraction is printed."""
+    from tgpose_b200.posenet import PoseNet9D
+    g = golden("posenet_1028")
+    torch.manual_seed(0)
+    net = PoseNet9D(train_outputs=True).cuda().eval()
+    enc = net.face_all.encoder
+    pts, cat = cu(g["pts"]), cu(g["cat_id"])
+    rows = g["feat_rows"].astype(np.int64)
+    with torch.no_grad():
+        enc._inject = [cu(g[f"idx_{i:02d}"].astype(np.int32)) for i in range(14)]
+        torch.manual_seed(7)
+        out = {k: v.clone() for k, v in net(pts, cat).items()}
+        enc._inject = None
+        enc._record = []
+        torch.manual_seed(7)
+        free = {k: v.clone() for k, v in net(pts, cat).items()}
+        rec = [nump(t).astype(np.int64) for t in enc._record]
+        enc._record = None
+    assert_close(nump(out["feat"])[:, rows], g["out_feat"], what="feat (T2, 4 x 1028, tcgen05 path)")
+    for k in ("recon", "f_green_R", "f_red_R", "h1", "h2", "feat_global"):
+        assert_close(nump(out[k]), g["out_" + k], rel=2e-4, floor=2e-6, what=k)
+    ang = {k: _axis_angle_deg(nump(out[k]), g["out_" + k]) for k in ("p_green_R", "p_red_R")}
+    dts = {k: float(np.abs(nump(out[k]) - g["out_" + k]).max()) for k in ("Pred_T", "Pred_s")}
+    print(f"T2 4x1028 pose error vs reference: axes {ang} deg, T/s abs {dts}")
+    # poses at rel 1e-4 (north_star): unit axes within 1e-4 rad = 0.0057 deg, T / s (|.| ~ 0.1 .. 1) within 1e-5 absolute
+    # (measured on B200: 1.2e-4 / 1.2e-3 deg, 2.4e-7 / 4.2e-7)
+    assert max(ang.values()) < 0.0057 and max(dts.values()) < 1e-5
+    # every xyz-space index tensor of the free run is bit-exact vs the reference (call order: SURVEY 8a a1):
+    # 0 conv_0 RF-P, 1 conv_0 ORL, 3 conv_1 ORL, 4 pool_1, 6 conv_2 ORL, 8 conv_3 ORL, 9 pool_2, 11 conv_4 ORL, 12/13 nearest
+    for slot in (0, 1, 3, 4, 6, 8, 9, 11, 12, 13):
+        assert np.array_equal(rec[slot], g[f"idx_{slot:02d}"].astype(np.int64)), f"xyz index slot {slot}"
+    # feature-space slots (2, 5, 7, 10): rows whose neighbour SET differs from the reference's (ill-conditioned, SURVEY 8c')
+    for slot in (2, 5, 7, 10):
+        a, b = np.sort(rec[slot], axis=-1), np.sort(g[f"idx_{slot:02d}"].astype(np.int64), axis=-1)
+        print(f"T3 slot {slot}: {float((a != b).any(-1).mean()):.4f} of rows with a different neighbour set")
+    frac = frac_close(nump(free["feat"])[:, rows], g["out_feat"])
+    print(f"T3 free-running in-tolerance fraction at 4 x 1028: {frac:.4f}")
+    # T3 is reported, not gated on (SURVEY 8c'): feature-space kNN is ill-conditioned, a flipped neighbour moves a
+    # max-over-k, the ORL cloud mean carries it to every row and seeds more flips downstream (measured here: 0.9 % /
+    # 3.9 % / 6.7 % / 10.2 % of rows with a different neighbour SET at the four RF-F calls, 62 % of feat elements inside
+    # rel 1e-4).  The gate is the other direction of T2: OUR free-running indices replayed into the CPU oracle must
+    # reproduce OUR outputs within rel 1e-4 -- i.e. every difference from the reference is an index flip inside the
+    # rounding bound of the reference's own formula (rule 3, tested at op level), never arithmetic.
+    assert frac > 0.5
+    sd = {k: v.detach().cpu().numpy() for k, v in net.state_dict().items()}
+    torch.manual_seed(7)
+    perm1, perm2 = torch.randperm(1028).numpy(), torch.randperm(257).numpy()
+    orc.USE_BLAS = True
+    try:
+        ref = orc.posenet_forward(sd, g["pts"], g["cat_id"], perm1, perm2, inject=rec)
+    finally:
+        orc.USE_BLAS = False
+    assert_close(nump(free["feat"]), ref["feat"], what="free-running feat vs oracle with OUR indices replayed")
+    for k in ("recon", "h1", "h2", "feat_global", "Pred_T", "Pred_s"):
+        assert_close(nump(free[k]), ref[k], rel=2e-4, floor=2e-6, what=f"free-running {k} vs oracle replay")
 
 
 def test_cuda_graph_replay_equals_eager():

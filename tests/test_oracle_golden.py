@@ -173,6 +173,43 @@ def test_posenet_injected_indices():
         assert_close(out[k], g["out_" + k], rel=2e-4, floor=2e-6, what=k)
 
 
+# ----------------------------------------------------------------------------------------- DCD loss tail
+@pytest.mark.parametrize("tag", list("abcd"))
+def test_calc_dcd_oracle_vs_reference(tag):
+    """oracle.calc_dcd / calc_cd pinned to the reference's own calc_dcd / calc_cd (losses/TDA_loss_sym_recon.py:411-450,
+    :495-509, executed from the reference source by make_golden.py: dcd_case with chamfer_python.distChamfer)."""
+    g = golden("dcd")
+    alpha, lam, non_reg = float(g[f"{tag}_kw"][0]), float(g[f"{tag}_kw"][1]), bool(g[f"{tag}_kw"][2])
+    d1, d2, i1, i2 = orc.chamfer_forward(g[f"{tag}_pred"], g[f"{tag}_gt"])
+    loss = orc.calc_dcd(d1, d2, i1, i2, alpha=alpha, n_lambda=lam, non_reg=non_reg)
+    assert_close(loss, g[f"{tag}_loss"], what=f"calc_dcd {tag}")
+    cd_p, cd_t = orc.calc_cd(d1, d2)
+    assert_close(cd_p, g[f"{tag}_cd_p"], what="cd_p")
+    assert_close(cd_t, g[f"{tag}_cd_t"], what="cd_t")
+
+
+def test_posenet_1028_injected_indices():
+    """the oracle at the BENCHMARKED cloud size (4 x 1028) against the reference's PoseNet9D with its indices replayed."""
+    torch = pytest.importorskip("torch")
+    from tgpose_b200.posenet import PoseNet9D
+    g = golden("posenet_1028")
+    torch.manual_seed(0)
+    net = PoseNet9D(train_outputs=True).eval()
+    sd = {k: v.detach().numpy() for k, v in net.state_dict().items()}
+    torch.manual_seed(7)
+    perm1, perm2 = torch.randperm(1028).numpy(), torch.randperm(257).numpy()
+    inject = [g[f"idx_{i:02d}"].astype(np.int64) for i in range(14)]
+    orc.USE_BLAS = True
+    try:
+        out = orc.posenet_forward(sd, g["pts"], g["cat_id"], perm1, perm2, inject=inject)
+    finally:
+        orc.USE_BLAS = False
+    rows = g["feat_rows"].astype(np.int64)
+    assert_close(out["feat"][:, rows], g["out_feat"], what="feat rows")
+    for k in ("recon", "f_green_R", "f_red_R", "Pred_T", "Pred_s", "h1", "h2", "feat_global"):
+        assert_close(out[k], g["out_" + k], rel=2e-4, floor=2e-6, what=k)
+
+
 # ----------------------------------------------------------------------------------------- backward oracle
 def _bparams(g, prefix):
     return {k[len(prefix):]: g[k] for k in g.files if k.startswith(prefix)}

@@ -13,7 +13,9 @@ from . import ops
 class GraphedPoseNet:
     """net: a PoseNet9D in eval mode on a CUDA device; fixed (batch, n_points)."""
 
-    def __init__(self, net, batch, n_points, warmup=2):
+    def __init__(self, net, batch, n_points, warmup=2, encoder_only=False):
+        """encoder_only: capture Face_Enc.forward alone (SURVEY 8d asks for encoder-only clouds/s beside the full network);
+        the static output is then the (feat, feat_global) pair of FaceRecon.py:86."""
         assert not net.training, "graph replay is for inference"
         self.net = net
         dev = next(net.parameters()).device
@@ -41,13 +43,14 @@ class GraphedPoseNet:
             side = torch.cuda.Stream(device=dev)
             side.wait_stream(torch.cuda.current_stream(dev))
             with torch.cuda.stream(side), torch.no_grad():
+                fwd = self.enc if encoder_only else net
                 for _ in range(warmup):           # weight packs / split caches are built here, outside the capture
-                    net(self.pts, self.cat)
+                    fwd(self.pts, self.cat)
             torch.cuda.current_stream(dev).wait_stream(side)
             torch.cuda.synchronize(dev)
             self.graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph), torch.no_grad():
-                self.out = net(self.pts, self.cat)
+                self.out = fwd(self.pts, self.cat)
         finally:
             self.enc._static_perms = None
 

@@ -65,6 +65,7 @@ class TrainStep:
         self.seed = seed
         parallel.seed_for_forward(seed)
         self.buckets = 0
+        self.ar_events = None          # bench.py sets this to a list to time the collective with CUDA events
 
     def __call__(self, pts, cat, tgt):
         self.net.train()
@@ -74,7 +75,14 @@ class TrainStep:
         if self.ranger:
             self.opt.zero_grad()
             total.backward()
+            ev = None
+            if self.ar_events is not None:
+                ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+                ev[0].record()
             self.buckets = parallel.allreduce_flat(self.opt.flat_grads)
+            if ev is not None:
+                ev[1].record()
+                self.ar_events.append(ev)
             self.opt.clip_grad_norm_(5.0)
             self.opt.step()
             return total.detach()
