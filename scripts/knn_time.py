@@ -1,11 +1,11 @@
-"""Times the xyz / feature kNN kernels (CUDA events, L2 flush between iterations)."""
+"""xyz / feature kNN timing over k (CUDA events, L2 flush): python scripts/knn_time.py [N ...]"""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from tgpose_b200 import _lib, ops
 _lib.load()
 flush = torch.empty(256 * 1024 * 1024 // 4, device="cuda")
-def timed(fn, iters=20):
+def timed(fn, iters=10):
     for _ in range(3): fn()
     ts = []
     for _ in range(iters):
@@ -16,11 +16,12 @@ def timed(fn, iters=20):
     ts.sort()
     return ts[len(ts) // 2]
 g = torch.Generator().manual_seed(0)
-for B, N, k in [(32, 1028, 20), (32, 1028, 4), (32, 257, 20), (32, 64, 8), (32, 1028, 30), (8, 4096, 20), (2, 16384, 20)]:
-    x = torch.rand(B, N, 3, generator=g).cuda()
-    t = timed(lambda: ops.knn_xyz(x, k, want64=False, want32=True))
-    print(f"xyz  B={B} N={N} k={k}: {t*1e3:.1f} us  {B*N*N/t/1e6:.0f} Gpairs/s")
-for B, N, D, k in [(32, 1028, 128, 20), (32, 257, 128, 20), (32, 257, 256, 20), (32, 64, 256, 8), (32, 1028, 128, 30), (8, 4096, 128, 20)]:
-    x = (torch.randn(B, N, D, generator=g) * 0.5).cuda()
-    t = timed(lambda: ops.knn_feat(x, k, want64=False, want32=True))
-    print(f"feat B={B} N={N} D={D} k={k}: {t*1e3:.1f} us  {B*N*N/t/1e6:.0f} Gpairs/s")
+Ns = [int(v) for v in sys.argv[1:]] or [1028, 4096]
+for N in Ns:
+    B = max(1, 32 * 1028 // N)
+    xyz = torch.rand(B, N, 3, generator=g).cuda()
+    feat = (torch.randn(B, N, 128, generator=g) * 0.3).cuda()
+    for k in (10, 20, 30, 40, 50, 63):
+        tx = timed(lambda: ops.knn_xyz(xyz, k, want64=False, want32=True))
+        tf = timed(lambda: ops.knn_feat(feat, k, want64=False, want32=True))
+        print(f"N={N} B={B} k={k}: xyz {tx*1e3:.1f} us  feat(D=128) {tf*1e3:.1f} us")

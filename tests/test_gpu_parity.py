@@ -52,7 +52,9 @@ def test_knn_xyz_duplicates(ops):
 
 @pytest.mark.parametrize("B,N,k", [(8, 1028, 20), (3, 257, 20), (5, 64, 8), (2, 1028, 4), (2, 333, 50), (1, 5000, 10),
                                    (2, 40, 39), (1, 2, 1), (3, 1028, 31), (2, 40, 31), (1, 33, 31), (1, 9000, 20),
-                                   (1, 16500, 31), (2, 1028, 1), (2, 65, 30)])
+                                   (1, 16500, 31), (2, 1028, 1), (2, 65, 30),
+                                   # k = 32..63 on the threshold path (128 group minima)
+                                   (4, 1028, 50), (2, 1028, 40), (2, 257, 63), (1, 9000, 50), (2, 64, 63), (3, 52, 50), (2, 1028, 32)])
 def test_knn_xyz_vs_oracle(ops, B, N, k):
     g = torch.Generator().manual_seed(B * 1000 + N + k)
     x = torch.rand(B, N, 3, generator=g)
@@ -81,6 +83,8 @@ def test_knn_xyz_multi_tile_with_duplicates(ops):
     x[1, :] = x[1, 0]
     mine = nump(ops.knn_xyz(x.cuda(), 20)[0])
     assert np.array_equal(mine, orc.knn_xyz(x.numpy(), 20))
+    mine = nump(ops.knn_xyz(x.cuda(), 45)[0])            # k > 31: the two-register insertion lists of the slow path
+    assert np.array_equal(mine, orc.knn_xyz(x.numpy(), 45))
 
 
 def test_knn_errors(ops):
@@ -104,7 +108,10 @@ def test_knn_feat_golden(ops, tag, D):
 
 @pytest.mark.parametrize("B,N,D,k", [(4, 1028, 128, 20), (4, 257, 256, 20), (8, 64, 256, 8), (2, 130, 20, 5), (1, 4500, 64, 30),
                                      (1, 300, 64, 40), (2, 257, 128, 20), (3, 100, 128, 10), (2, 64, 64, 8), (5, 200, 128, 31),
-                                     (40, 257, 64, 20)])
+                                     (40, 257, 64, 20),
+                                     # k = 32..63: tensor-core kernel with 128 group minima (BASELINE configs[3] sweeps k to 50)
+                                     (3, 1028, 128, 50), (2, 1028, 128, 40), (2, 257, 256, 63), (1, 2048, 128, 50), (2, 70, 64, 50),
+                                     (2, 600, 128, 32)])
 def test_knn_feat_vs_oracle(ops, B, N, D, k):
     g = torch.Generator().manual_seed(N + D)
     x = torch.randn(B, N, D, generator=g) * 0.5
@@ -120,7 +127,8 @@ def test_knn_feat_vs_oracle(ops, B, N, D, k):
     assert (srt[..., 1:] != srt[..., :-1]).all()
 
 
-@pytest.mark.parametrize("B,N,D,k", [(3, 1028, 128, 20), (2, 300, 256, 20), (2, 64, 256, 8)])
+@pytest.mark.parametrize("B,N,D,k", [(3, 1028, 128, 20), (2, 300, 256, 20), (2, 64, 256, 8),
+                                     (2, 1028, 128, 50), (2, 300, 64, 40)])      # k > 31: fix-up through the fp32 tile kernel
 def test_knn_feat_duplicate_rows_take_the_fixup_path(ops, B, N, D, k):
     """More identical feature rows than the survivor buffer holds (zero-padded / dropped-out clouds): the threshold-selection
     kernel hands those units to the insertion-list fix-up.  Distances between duplicates are exact ties (bit-equal inner

@@ -118,6 +118,9 @@ __device__ __forceinline__ void stage_xyz_tile(float4* pts, const float* cloud, 
     }
 }
 
+// G4 (k + 1 in 33..64): 128 group minima (four per lane) instead of 64 -- the K-th smallest of them still bounds the
+// K-th distance, and ~ -128 ln(1 - K/128) candidates (65 at K = 51, 89 at K = 64) survive it
+template <bool G4>
 __global__ void __launch_bounds__(KS_THREADS)
 knn_xyz_sel_kernel(const float* __restrict__ xyz, int N, int k, int tile, int slots, int64_t* __restrict__ idx64,
                    int32_t* __restrict__ idx32) {
@@ -134,13 +137,13 @@ knn_xyz_sel_kernel(const float* __restrict__ xyz, int N, int k, int tile, int sl
     const int qbase = blockIdx.x * KS_QPC + warp * KS_QPW;
     const bool single = N <= tile;
 
-    float a0[KS_QPW], a1[KS_QPW], a2[KS_QPW], qq[KS_QPW], m0[KS_QPW], m1[KS_QPW];
+    float a0[KS_QPW], a1[KS_QPW], a2[KS_QPW], qq[KS_QPW], m0[KS_QPW], m1[KS_QPW], m2[KS_QPW], m3[KS_QPW];
 #pragma unroll
     for (int q = 0; q < KS_QPW; ++q) {
         const int qi = min(qbase + q, N - 1);              // clamped: idle warps still walk the barriers
         a0[q] = __ldg(cloud + qi * 3); a1[q] = __ldg(cloud + qi * 3 + 1); a2[q] = __ldg(cloud + qi * 3 + 2);
         qq[q] = __fadd_rn(__fadd_rn(__fmul_rn(a0[q], a0[q]), __fmul_rn(a1[q], a1[q])), __fmul_rn(a2[q], a2[q]));
-        m0[q] = CUDART_INF_F; m1[q] = CUDART_INF_F;
+        m0[q] = CUDART_INF_F; m1[q] = CUDART_INF_F; m2[q] = CUDART_INF_F; m3[q] = CUDART_INF_F;
     }
     // ---- pass 1: 64 strided group minima per query
     for (int t0 = 0; t0 < N; t0 += tile) {
@@ -151,16 +154,19 @@ knn_xyz_sel_kernel(const float* __restrict__ xyz, int N, int k, int tile, int sl
 #pragma unroll 2
         for (int j0 = 0; j0 < ntp; j0 += 64) {
             const float4 p = pts[j0 + lane], r = pts[j0 + 32 + lane];
+            const bool odd = G4 && (j0 & 64);              // G4: blocks of 64 alternate between the minima pairs (0,1) and (2,3)
 #pragma unroll
             for (int q = 0; q < KS_QPW; ++q) {
-                m0[q] = fminf(m0[q], xyz_dist(a0[q], a1[q], a2[q], qq[q], p));
-                m1[q] = fminf(m1[q], xyz_dist(a0[q], a1[q], a2[q], qq[q], r));
+                const float dp = xyz_dist(a0[q], a1[q], a2[q], qq[q], p), dr = xyz_dist(a0[q], a1[q], a2[q], qq[q], r);
+                if (odd) { m2[q] = fminf(m2[q], dp); m3[q] = fminf(m3[q], dr); }
+                else { m0[q] = fminf(m0[q], dp); m1[q] = fminf(m1[q], dr); }
             }
         }
     }
     float T[KS_QPW];
 #pragma unroll
-    for (int q = 0; q < KS_QPW; ++q) T[q] = fminf(warp_kth_of_64(m0[q], m1[q], K, lane), 3.0e38f);
+    for (int q = 0; q < KS_QPW; ++q)
+        T[q] = fminf(G4 ? warp_kth_of_128(m0[q], m1[q], m2[q], m3[q], K, lane) : warp_kth_of_64(m0[q], m1[q], K, lane), 3.0e38f);
     // ---- pass 2: every lane appends its survivors (d <= T) to a private list: no ballots in the scan
     // (the write cursor of each list is a byte offset that advances by one 256-byte row per survivor; predicated, no branch)
     uint32_t cur[KS_QPW];
@@ -236,24 +242,35 @@ knn_xyz_sel_kernel(const float* __restrict__ xyz, int N, int k, int tile, int sl
             for (int q = 0; q < KS_QPW; ++q) {
                 const int qi = qbase + q;
                 if (!redo[q]) continue;
-                WarpTopList<1> top;
+                constexpr int TS = G4 ? 2 : 1;
+                WarpTopList<TS> top;
                 float* sd = reinterpret_cast<float*>(wsm + q * qstride);            // list parked between tiles
-                int* si = reinterpret_cast<int*>(sd + 32);
+                int* si = reinterpret_cast<int*>(sd + 32 * TS);
                 if (t0 == 0) top.init();
-                else { top.d[0] = sd[lane]; top.i[0] = si[lane]; }
+                else {
+#pragma unroll
+                    for (int s_ = 0; s_ < TS; ++s_) { top.d[s_] = sd[s_ * 32 + lane]; top.i[s_] = si[s_ * 32 + lane]; }
+                }
                 // nothing above T can be among the K nearest: admission is capped just above it from the start
                 const float cap = T[q] < 3.0e38f ? nextafterf(T[q], CUDART_INF_F) : CUDART_INF_F;
                 float th = fminf(top.thresh(K), cap);
                 for (int j0 = 0; j0 < ntp; j0 += 32)
                     top.admit(xyz_dist(a0[q], a1[q], a2[q], qq[q], pts[j0 + lane]), t0 + j0, lane, th, K, cap);
                 if (t0 + nt >= N) {
-                    if (lane >= 1 && lane <= k) {
-                        const size_t o = ((size_t)b * N + qi) * k + lane - 1;
-                        const int v = top.i[0] < 0 ? 0 : top.i[0];            // unfilled rank (NaN input): a valid index
-                        if (idx64) idx64[o] = v;
-                        if (idx32) idx32[o] = v;
+#pragma unroll
+                    for (int s_ = 0; s_ < TS; ++s_) {
+                        const int rank = s_ * 32 + lane;
+                        if (rank >= 1 && rank <= k) {
+                            const size_t o = ((size_t)b * N + qi) * k + rank - 1;
+                            const int v = top.i[s_] < 0 ? 0 : top.i[s_];      // unfilled rank (NaN input): a valid index
+                            if (idx64) idx64[o] = v;
+                            if (idx32) idx32[o] = v;
+                        }
                     }
-                } else { sd[lane] = top.d[0]; si[lane] = top.i[0]; }
+                } else {
+#pragma unroll
+                    for (int s_ = 0; s_ < TS; ++s_) { sd[s_ * 32 + lane] = top.d[s_]; si[s_ * 32 + lane] = top.i[s_]; }
+                }
                 __syncwarp();
             }
         }
@@ -326,7 +343,21 @@ __global__ void rownorm_kernel(const float* __restrict__ x, long rows, int D, fl
 template <int SLOTS>
 __global__ void __launch_bounds__(KF_THREADS)
 knn_feat_kernel(const float* __restrict__ x, const float* __restrict__ qn, int N, int D, int k,
-                int64_t* __restrict__ idx64, int32_t* __restrict__ idx32) {
+                int64_t* __restrict__ idx64, int32_t* __restrict__ idx32,
+                const int* __restrict__ unit_list, int q_tiles, int q_step) {
+    // unit_list != nullptr: fix-up launch behind the tensor-core kernel for k > 31 -- only query tiles that overlap a
+    // listed unit ([0] = count; unit = cloud * q_tiles + tile of q_step queries) are redone (normally none)
+    if (unit_list) {
+        const int cntu = unit_list[0];
+        const int qa = blockIdx.x * KF_BM, qe = qa + KF_BM;
+        bool hit = false;
+        for (int i = 0; i < cntu; ++i) {
+            const int u = unit_list[1 + i];
+            const int u0 = (u % q_tiles) * q_step;
+            hit |= (u / q_tiles == (int)blockIdx.y) && u0 < qe && u0 + q_step > qa;
+        }
+        if (!hit) return;
+    }
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* As = reinterpret_cast<float*>(smem_raw);              // [KF_BK][KF_LDA]
     float* Bs = As + KF_BK * KF_LDA;                             // [KF_BK][KF_LDB]
@@ -472,17 +503,20 @@ extern "C" int tgp_knn_xyz(const float* xyz, int B, int N, int k, int64_t* idx64
     cudaStream_t st = as_stream(stream);
     static int legacy = -1;
     if (legacy < 0) { const char* e = getenv("TGP_KNN_LEGACY"); legacy = (e && e[0] == '1') ? 1 : 0; }
-    if (k + 1 <= 32 && !legacy) {
+    if (k + 1 <= 64 && !legacy) {
         // threshold selection; the whole cloud stays resident when it fits, otherwise both passes walk 8192-point tiles
         const int tile = N <= KS_TILE_MAX ? ((N + 63) & ~63) : KS_TILE_MAX;
         const size_t smem = (size_t)tile * sizeof(float4) + (size_t)(KS_THREADS / 32) * ks_warp_smem(k);
         static std::atomic<unsigned long long> attr_set{0};   // one bit per device: function attributes are per device
         if (first_on_device(attr_set)) {
-            cudaFuncSetAttribute(knn_xyz_sel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+            cudaFuncSetAttribute(knn_xyz_sel_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)(KS_TILE_MAX * sizeof(float4) + (KS_THREADS / 32) * ks_warp_smem(63)));
+            cudaFuncSetAttribute(knn_xyz_sel_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)(KS_TILE_MAX * sizeof(float4) + (KS_THREADS / 32) * ks_warp_smem(63)));
         }
         dim3 grid((N + KS_QPC - 1) / KS_QPC, B);
-        knn_xyz_sel_kernel<<<grid, KS_THREADS, smem, st>>>(xyz, N, k, tile, ks_slots(k), idx64, idx32);
+        if (k + 1 <= 32) knn_xyz_sel_kernel<false><<<grid, KS_THREADS, smem, st>>>(xyz, N, k, tile, ks_slots(k), idx64, idx32);
+        else knn_xyz_sel_kernel<true><<<grid, KS_THREADS, smem, st>>>(xyz, N, k, tile, ks_slots(k), idx64, idx32);
         return check_launch("knn_xyz_sel_kernel");
     }
     const int tile = N < KNN_TILE_MAX ? N : KNN_TILE_MAX;
@@ -541,18 +575,28 @@ extern "C" int tgp_knn_feat(const float* x, const float* x_split, int B, int N, 
         }
         static int legacy = -1;
         if (legacy < 0) { const char* e = getenv("TGP_KNN_LEGACY"); legacy = (e && e[0] == '1') ? 1 : 0; }
-        return tgp_knn_tc(x_split, qn, B, N, D, k, idx64, idx32,
-                          legacy ? nullptr : reinterpret_cast<int*>(ws + knn_qn_bytes(B, N)), st);
+        int* fix = reinterpret_cast<int*>(ws + knn_qn_bytes(B, N));
+        if (k + 1 <= 32) return tgp_knn_tc(x_split, qn, B, N, D, k, idx64, idx32, legacy ? nullptr : fix, st);
+        // k = 32..63: threshold selection on 128 group minima; units it could not finish (massive ties, non-finite input)
+        // are redone by the fp32 tile kernel below, which returns at once when the list is empty
+        rc = tgp_knn_tc(x_split, qn, B, N, D, k, idx64, idx32, fix, st);
+        if (rc) return rc;
+        const int q_tiles = (N + 127) / 128, q_step = (N + q_tiles - 1) / q_tiles;      // unit geometry of tgp_knn_tc
+        const size_t smem = sizeof(float) * (KF_BK * KF_LDA + KF_BK * KF_LDB + KF_BM * KF_LDD) + (size_t)KF_BM * 32 * 2 * 8;
+        cudaFuncSetAttribute(knn_feat_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        dim3 grid((N + KF_BM - 1) / KF_BM, B);
+        knn_feat_kernel<2><<<grid, KF_THREADS, smem, st>>>(x, qn, N, D, k, idx64, idx32, fix, q_tiles, q_step);
+        return check_launch("knn_feat_kernel (fix-up)");
     }
     const int slots = (k + 1 > 32) ? 2 : 1;
     const size_t smem = sizeof(float) * (KF_BK * KF_LDA + KF_BK * KF_LDB + KF_BM * KF_LDD) + (size_t)KF_BM * 32 * slots * 8;
     dim3 grid((N + KF_BM - 1) / KF_BM, B);
     if (slots == 1) {
         cudaFuncSetAttribute(knn_feat_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        knn_feat_kernel<1><<<grid, KF_THREADS, smem, st>>>(x, qn, N, D, k, idx64, idx32);
+        knn_feat_kernel<1><<<grid, KF_THREADS, smem, st>>>(x, qn, N, D, k, idx64, idx32, nullptr, 0, 0);
     } else {
         cudaFuncSetAttribute(knn_feat_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        knn_feat_kernel<2><<<grid, KF_THREADS, smem, st>>>(x, qn, N, D, k, idx64, idx32);
+        knn_feat_kernel<2><<<grid, KF_THREADS, smem, st>>>(x, qn, N, D, k, idx64, idx32, nullptr, 0, 0);
     }
     return check_launch("knn_feat_kernel");
 }

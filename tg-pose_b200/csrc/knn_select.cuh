@@ -141,6 +141,48 @@ __device__ __forceinline__ float warp_kth_of_64(float v0, float v1, int K, int l
     return v;
 }
 
+// K-th smallest (1-based, K <= 128) of the 128 values held four per lane (element e = 32 r + lane): a full bitonic sort
+// (28 compare-exchange steps, across lanes for strides < 32 and across the four registers above) -- ~250 instructions,
+// once per query
+__device__ __forceinline__ float warp_kth_of_128(float v0, float v1, float v2, float v3, int K, int lane) {
+    float v[4] = {v0, v1, v2, v3};
+#pragma unroll
+    for (int k = 2; k <= 128; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            if (j >= 32) {
+                const int dr = j >> 5;                      // partner register: r ^ dr, same lane
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    if ((r & dr) == 0) {
+                        const int e = 32 * r + lane;
+                        const bool asc = (e & k) == 0;      // (k = 128: always ascending)
+                        const float lo = fminf(v[r], v[r | dr]), hi = fmaxf(v[r], v[r | dr]);
+                        v[r] = asc ? lo : hi;
+                        v[r | dr] = asc ? hi : lo;
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    const int e = 32 * r + lane;
+                    const float o = __shfl_xor_sync(FULL, v[r], j);
+                    const bool keep_min = ((e & k) == 0) == ((e & j) == 0);
+                    v[r] = keep_min ? fminf(v[r], o) : fmaxf(v[r], o);
+                }
+            }
+        }
+    }
+    const int e = K - 1;
+    float out = 0.f;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const float c = __shfl_sync(FULL, v[r], e & 31);
+        if ((e >> 5) == r) out = c;
+    }
+    return out;
+}
+
 // monotone map float -> uint32 (a < b <=> key(a) < key(b) for non-NaN values)
 __device__ __forceinline__ uint32_t ordered_key(float d) {
     const uint32_t u = __float_as_uint(d);

@@ -237,12 +237,19 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
 // ~7x fewer selection instructions than the insertion lists of knn_tc_kernel at 2x its (cheap) tensor work; no distance
 // tile in shared memory.  A query with more than KT2_CAP survivors (massive ties) or fewer than K (non-finite input)
 // sends its unit to the fix-up list, which knn_tc_kernel redoes right behind this launch.
-constexpr int KT2_CAP = 80;                              // survivor buffer entries per query (41 +- 4 expected at K = 31)
-constexpr int KT2_GM_LD = 65;                            // pitch of the group-minimum rows (bank-conflict free)
+// NS group-minimum slots per query: 64 for K = k + 1 <= 32, 128 for K <= 64 (expected survivors -NS ln(1 - K/NS):
+// 42 at K = 31 / NS = 64; 65 at K = 51, 89 at K = 64 / NS = 128).  The bigger survivor buffers of NS = 128 are paid for
+// with a 2-stage operand ring instead of 4 (the selection, not the feed, bounds this kernel).
+template <int NS> struct Kt2 {
+    static constexpr int CAP = NS == 64 ? 80 : 144;      // survivor buffer entries per query
+    static constexpr int GM_LD = NS + 1;                 // pitch of the group-minimum rows (bank-conflict free)
+    static constexpr int STAGES = NS == 64 ? KT_STAGES : 2;
+    static constexpr int RANK_SLOTS = (CAP + 31) / 32;
+};
 
 // 32 accumulator columns of one query row -> distances -> pass 0: group minima (groups of GS consecutive candidates, slot =
 // group % 64, exclusive to this thread); pass 1: survivors (d <= T) appended with one predicated shared-memory atomic each
-template <int GS>
+template <int GS, int NS>
 __device__ __forceinline__ void kt2_consume(const uint32_t (&r)[32], const float* wqs, float qi, int pass, int c0, float* gmr,
                                             float T, uint32_t cnt_addr, uint32_t buf_row) {
     const float4* qj4 = reinterpret_cast<const float4*>(wqs);
@@ -265,7 +272,7 @@ __device__ __forceinline__ void kt2_consume(const uint32_t (&r)[32], const float
             const int g0 = (c0 + h) / GS;
 #pragma unroll
             for (int g = 0; g < 16 / GS; ++g) {
-                float* slot = gmr + ((g0 + g) & 63);
+                float* slot = gmr + ((g0 + g) & (NS - 1));
                 if (d[g * GS] < *slot) *slot = d[g * GS];  // (+inf padding never writes: GS = 1 shares slots across chunks only for N <= 64)
             }
         } else {
@@ -278,7 +285,7 @@ __device__ __forceinline__ void kt2_consume(const uint32_t (&r)[32], const float
                     "setp.lt.and.u32 q, pos, %3, p;\n\t"
                     "mad.lo.u32 addr, pos, 8, %4;\n\t"
                     "@q st.shared.v2.b32 [addr], {%5, %6};\n\t}"
-                    :: "f"(d[j]), "f"(T), "r"(cnt_addr), "n"(KT2_CAP), "r"(buf_row), "r"(__float_as_uint(d[j])), "r"(c0 + h + j)
+                    :: "f"(d[j]), "f"(T), "r"(cnt_addr), "n"(Kt2<NS>::CAP), "r"(buf_row), "r"(__float_as_uint(d[j])), "r"(c0 + h + j)
                     : "memory");
             }
         }
@@ -290,24 +297,25 @@ __device__ __forceinline__ void kt2_consume(const uint32_t (&r)[32], const float
 // memory (hi and lo k-blocks of a stage loaded once and used by all three products).  3x less L2 -> SM traffic than
 // re-fetching the query tile for every candidate tile and segment -- that traffic, not the tensor pipe, bounded the
 // streaming variant (ncu: tensor pipe 34 % busy, long-scoreboard stalls).
-template <int GS, bool ATM>
+template <int GS, bool ATM, int NS>
 __global__ void __launch_bounds__(KT_THREADS, 1)
 knn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmC,
                const float* __restrict__ x_split, const float* __restrict__ qn, int N, int Kp, int k, int q_tiles,
                int q_step, int num_units, int* __restrict__ fix_list, int64_t* __restrict__ idx64,
                int32_t* __restrict__ idx32) {
     extern __shared__ __align__(1024) unsigned char kt_smem[];
+    constexpr int KT2_CAP = Kt2<NS>::CAP, KT2_GM_LD = Kt2<NS>::GM_LD, STG = Kt2<NS>::STAGES;
     unsigned char* base = reinterpret_cast<unsigned char*>(((uintptr_t)kt_smem + 1023) & ~(uintptr_t)1023);
-    uint64_t* full = reinterpret_cast<uint64_t*>(base + KT_STAGES * KT_STAGE_BYTES);
-    uint64_t* empty = full + KT_STAGES;
-    uint64_t* tmem_full = empty + KT_STAGES;
+    uint64_t* full = reinterpret_cast<uint64_t*>(base + STG * KT_STAGE_BYTES);
+    uint64_t* empty = full + STG;
+    uint64_t* tmem_full = empty + STG;
     uint64_t* tmem_empty = tmem_full + 2;
     uint64_t* a_ready = tmem_empty + 2;
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(a_ready + 1);
     int* unit_flag = reinterpret_cast<int*>(tmem_ptr + 1);
     constexpr int TMEM_COLS = ATM ? 512 : 256;
     constexpr uint32_t A_COL = 256;                                                 // first tensor-memory column of the query tile
-    unsigned char* sel = base + KT_STAGES * KT_STAGE_BYTES + 256;
+    unsigned char* sel = base + STG * KT_STAGE_BYTES + 256;
     uint2* buf = reinterpret_cast<uint2*>(sel);                                     // [128][KT2_CAP] survivors (pass 2)
     float* gm = reinterpret_cast<float*>(sel);                                      // [128][KT2_GM_LD] group minima (pass 1), same bytes
     int* cnt = reinterpret_cast<int*>(sel + TC_BM * KT2_CAP * 8);                   // [128]
@@ -320,7 +328,7 @@ knn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     const int K = k + 1;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < KT_STAGES; ++s) { tc_mbar_init(full + s, 1); tc_mbar_init(empty + s, 1); }
+        for (int s = 0; s < STG; ++s) { tc_mbar_init(full + s, 1); tc_mbar_init(empty + s, 1); }
         for (int s = 0; s < 2; ++s) { tc_mbar_init(tmem_full + s, 1); tc_mbar_init(tmem_empty + s, KT_EPI_WARPS); }
         tc_mbar_init(a_ready, KT_EPI_WARPS);
         *unit_flag = 0;
@@ -356,7 +364,7 @@ knn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                             tc_mbar_expect_tx(full + stage, KT_STAGE_BYTES);
                             tma_load_2d(sa, &tmC, kb * TC_BK, crow, full + stage);
                             tma_load_2d(sa + TC_A_BYTES, &tmC, Kp + kb * TC_BK, crow, full + stage);
-                            if (++stage == KT_STAGES) { stage = 0; phase ^= 1; }
+                            if (++stage == STG) { stage = 0; phase ^= 1; }
                         }
                         continue;
                     }
@@ -368,7 +376,7 @@ knn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                             tc_mbar_expect_tx(full + stage, KT_STAGE_BYTES);
                             tma_load_2d(sa, &tmQ, a_off + kb * TC_BK, qrow, full + stage);
                             tma_load_2d(sa + TC_A_BYTES, &tmC, b_off + kb * TC_BK, crow, full + stage);
-                            if (++stage == KT_STAGES) { stage = 0; phase ^= 1; }
+                            if (++stage == STG) { stage = 0; phase ^= 1; }
                         }
                     }
                 }
@@ -413,7 +421,7 @@ knn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                             }
                             __syncwarp();
                             accum = 1;
-                            if (++stage == KT_STAGES) { stage = 0; phase ^= 1; }
+                            if (++stage == STG) { stage = 0; phase ^= 1; }
                         }
                         if (tc_elect_one()) umma_commit(tmem_full + acc);
                         __syncwarp();
@@ -432,7 +440,7 @@ knn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                         }
                         __syncwarp();
                         accum = 1;
-                        if (++stage == KT_STAGES) { stage = 0; phase ^= 1; }
+                        if (++stage == STG) { stage = 0; phase ^= 1; }
                     }
                     if (tc_elect_one()) umma_commit(tmem_full + acc);
                     __syncwarp();
@@ -483,7 +491,7 @@ knn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                 __syncwarp();
                 if (lane == 0) tc_mbar_arrive(a_ready);
             }
-            for (int i = et; i < TC_BM * 64; i += 32 * KT_EPI_WARPS) gm[(i >> 6) * KT2_GM_LD + (i & 63)] = CUDART_INF_F;
+            for (int i = et; i < TC_BM * NS; i += 32 * KT_EPI_WARPS) gm[(i / NS) * KT2_GM_LD + (i % NS)] = CUDART_INF_F;
             const float qi = my_row < nq ? __ldg(qb + q0 + my_row) : 0.f;
             epi_bar_sync();
             float T = 0.f;
@@ -506,15 +514,17 @@ knn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) tc_mbar_arrive(tmem_empty + acc);      // accumulator is in registers: the next tile may start
-                    kt2_consume<GS>(r, wqs, qi, pass, c0, gmr, T, cnt_addr, buf_row);
+                    kt2_consume<GS, NS>(r, wqs, qi, pass, c0, gmr, T, cnt_addr, buf_row);
                 }
                 epi_bar_sync();
                 if (pass == 0) {
-                    // thresholds: K-th smallest of the 64 group minima of each query
+                    // thresholds: K-th smallest of the NS group minima of each query
 #pragma unroll 2
                     for (int i = 0; i < KT_QPW; ++i) {
                         const int ql = e + KT_EPI_WARPS * i;
-                        const float t = warp_kth_of_64(gm[ql * KT2_GM_LD + lane], gm[ql * KT2_GM_LD + 32 + lane], K, lane);
+                        const float* gq = gm + ql * KT2_GM_LD;
+                        const float t = NS == 64 ? warp_kth_of_64(gq[lane], gq[32 + lane], K, lane)
+                                                 : warp_kth_of_128(gq[lane], gq[32 + lane], gq[(64 + lane) % NS], gq[(96 + lane) % NS], K, lane);
                         if (lane == 0) Ts[ql] = fminf(t, 3.0e38f);
                     }
                     epi_bar_sync();                                        // group minima are dead: the survivor buffers take their place
@@ -562,7 +572,7 @@ using namespace tgp;
 // (must not depend on B: a cloud's result may not change with the batch it sits in)
 bool tgp_knn_tc_eligible(int B, int N, int D, int k) {
     (void)B;
-    return k + 1 <= 32 && N >= 64 && D >= 16;
+    return k + 1 <= 64 && N >= 64 && D >= 16;
 }
 
 size_t tgp_knn_tc_fix_bytes(int B, int N) {
@@ -584,35 +594,42 @@ int tgp_knn_tc(const float* x_split, const float* qn, int B, int N, int D, int k
     const int q_step = (N + q_tiles - 1) / q_tiles;          // balanced query tiles (1028 -> 9 x 115, not 8 x 128 + 4)
     const int num_units = B * q_tiles;
     const size_t smem = (size_t)KT_STAGES * KT_STAGE_BYTES + 1024 + 256 + sizeof(float) * (TC_BM * KT_LDD + 2 * KT_BN);
-    const size_t smem2 = (size_t)KT_STAGES * KT_STAGE_BYTES + 1024 + 256 + (size_t)TC_BM * KT2_CAP * 8 + TC_BM * 8 + KT_EPI_WARPS * 32 * 4;
+    const bool big = k + 1 > 32;                             // 128 group minima, bigger survivor buffers, 2-stage ring
+    const size_t smem2 = (size_t)(big ? Kt2<128>::STAGES : Kt2<64>::STAGES) * KT_STAGE_BYTES + 1024 + 256 +
+                         (size_t)TC_BM * (big ? Kt2<128>::CAP : Kt2<64>::CAP) * 8 + TC_BM * 8 + KT_EPI_WARPS * 32 * 4;
     static std::atomic<unsigned long long> attr_set{0};   // one bit per device: function attributes are per device
     if (first_on_device(attr_set)) {
         cudaFuncSetAttribute(knn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        cudaFuncSetAttribute(knn_tc2_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        cudaFuncSetAttribute(knn_tc2_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        cudaFuncSetAttribute(knn_tc2_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        cudaFuncSetAttribute(knn_tc2_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        cudaFuncSetAttribute(knn_tc2_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        cudaFuncSetAttribute(knn_tc2_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+#define KT2_ATTR(GS, ATM, NS) cudaFuncSetAttribute(knn_tc2_kernel<GS, ATM, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)
+        KT2_ATTR(1, false, 64); KT2_ATTR(2, false, 64); KT2_ATTR(4, false, 64);
+        KT2_ATTR(1, true, 64); KT2_ATTR(2, true, 64); KT2_ATTR(4, true, 64);
+        KT2_ATTR(1, false, 128); KT2_ATTR(2, false, 128); KT2_ATTR(4, false, 128);
+        KT2_ATTR(1, true, 128); KT2_ATTR(2, true, 128); KT2_ATTR(4, true, 128);
+#undef KT2_ATTR
     }
     if (smem > 227 * 1024 || smem2 > 227 * 1024) return fail(TGP_EINVAL, "tgp_knn_feat: shared memory budget exceeded");
     const int grid = num_units < TGP_NUM_SMS ? num_units : TGP_NUM_SMS;
     if (!fix_list) {
+        if (big) return fail(TGP_EINVAL, "tgp_knn_feat: the insertion-list kernel covers k <= 31 only");
         knn_tc_kernel<<<grid, KT_THREADS, smem, st>>>(tmQ, tmC, qn, N, Kp, k, q_tiles, q_step, num_units, nullptr, idx64, idx32);
         return check_launch("knn_tc_kernel");
     }
     cudaMemsetAsync(fix_list, 0, sizeof(int), st);
     // query tile in tensor memory when [tf32 | residual] fits the 256 free columns in whole 32-column stores per chunk
     const bool atm = Kp <= 128 && Kp % 64 == 0;
-#define KT2_LAUNCH(GS, ATM) knn_tc2_kernel<GS, ATM><<<grid, KT_THREADS, smem2, st>>>(tmQ, tmC, x_split, qn, N, Kp, k, q_tiles, q_step, num_units, fix_list, idx64, idx32)
-    if (atm) {
-        if (N <= 64) KT2_LAUNCH(1, true); else if (N < 256) KT2_LAUNCH(2, true); else KT2_LAUNCH(4, true);
+#define KT2_LAUNCH(GS, ATM, NS) knn_tc2_kernel<GS, ATM, NS><<<grid, KT_THREADS, smem2, st>>>(tmQ, tmC, x_split, qn, N, Kp, k, q_tiles, q_step, num_units, fix_list, idx64, idx32)
+    // group size: the slots (group % NS) must hold at least K finite minima -> groups of 1 / 2 / 4 consecutive candidates
+    if (!big) {
+        if (atm) { if (N <= 64) KT2_LAUNCH(1, true, 64); else if (N < 256) KT2_LAUNCH(2, true, 64); else KT2_LAUNCH(4, true, 64); }
+        else { if (N <= 64) KT2_LAUNCH(1, false, 64); else if (N < 256) KT2_LAUNCH(2, false, 64); else KT2_LAUNCH(4, false, 64); }
     } else {
-        if (N <= 64) KT2_LAUNCH(1, false); else if (N < 256) KT2_LAUNCH(2, false); else KT2_LAUNCH(4, false);
+        if (atm) { if (N < 256) KT2_LAUNCH(1, true, 128); else if (N < 512) KT2_LAUNCH(2, true, 128); else KT2_LAUNCH(4, true, 128); }
+        else { if (N < 256) KT2_LAUNCH(1, false, 128); else if (N < 512) KT2_LAUNCH(2, false, 128); else KT2_LAUNCH(4, false, 128); }
     }
 #undef KT2_LAUNCH
     rc = check_launch("knn_tc2_kernel");
     if (rc) return rc;
+    if (big) return TGP_OK;      // k > 31: the caller redoes the listed units with the fp32 tile kernel (knn.cu)
     // fix-up: the units knn_tc2_kernel listed (normally none: the launch returns at once)
     const int fgrid = grid < 32 ? grid : 32;
     knn_tc_kernel<<<fgrid, KT_THREADS, smem, st>>>(tmQ, tmC, qn, N, Kp, k, q_tiles, q_step, num_units, fix_list, idx64, idx32);
