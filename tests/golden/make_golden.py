@@ -406,6 +406,62 @@ def posenet_1028_case():
     save("posenet_1028", **out)
 
 
+def train_glue_case():
+    """the loss glue of the RL_TDA step outside the hot path, from the reference's own code: feat_consistency_loss /
+    prop_sym_matching_loss (losses/consistency_loss.py:11-45, importable) and the lr factors of flat_and_anneal_lr_scheduler
+    (tools/torch_utils/solver/lr_scheduler.py:177-279, cut out with `ast`: the module imports the missing tools.logger)
+    with the flags' defaults (config.py:123-130: cosine anneal from 0.72, linear warm-up 1000 iters from 0.001)."""
+    import importlib
+    cl = importlib.import_module("losses.consistency_loss")
+    g = torch.Generator().manual_seed(31)
+    B, N = 6, 257
+    x1 = torch.randn(B, 1286, generator=g).requires_grad_(True)
+    x2 = torch.randn(B, 1286, generator=g)
+    pc = torch.rand(B, N, 3, generator=g) - 0.5
+    pc_re = (pc + 0.02 * torch.randn(B, N, 3, generator=g)).requires_grad_(True)
+    q = torch.linalg.qr(torch.randn(B, 3, 3, generator=g))[0]
+    gt_R = q * torch.sign(torch.linalg.det(q)).view(B, 1, 1)
+    gt_t = torch.rand(B, 3, generator=g)
+    # one cloud per symmetry class of consistency_loss.py:41-79 (+ repeats): (1,0,0,0) zeroed, (1,1,..) y-reflection,
+    # (0,1,..) yx-reflection, (0,0,..) none
+    sym = torch.tensor([[1, 0, 0, 0], [1, 1, 0, 0], [0, 1, 0, 0], [0, 0, 0, 0], [1, 0, 1, 0], [0, 1, 1, 1]])
+    with torch.enable_grad():
+        l1 = cl.feat_consistency_loss(x1, x2)
+        l2 = cl.prop_sym_matching_loss(pc, pc_re, gt_R, gt_t, sym)
+        (l1 + l2).backward()
+    out = {"x1": np_(x1), "x2": np_(x2), "pc": np_(pc), "pc_re": np_(pc_re), "gt_R": np_(gt_R), "gt_t": np_(gt_t),
+           "sym": np_(sym), "feat_loss": np_(l1), "sym_loss": np_(l2), "g_x1": np_(x1.grad), "g_pc_re": np_(pc_re.grad),
+           "feat_consist_w": np.float32(flags.FLAGS.feat_consist_w)}
+    fn = _ref_functions("tools/torch_utils/solver/lr_scheduler.py", ["flat_and_anneal_lr_scheduler"])
+    import math
+    from bisect import bisect_right
+
+    class _Log:
+        def warning(self, *a, **k):
+            pass
+
+    ns = {"torch": torch, "cos": math.cos, "pi": math.pi, "bisect_right": bisect_right, "logger": _Log()}
+    exec(fn["flat_and_anneal_lr_scheduler"], ns)
+    total = 20000
+    opt = torch.optim.SGD([torch.nn.Parameter(torch.zeros(1))], lr=1.0)
+    sch = ns["flat_and_anneal_lr_scheduler"](opt, total_iters=total, warmup_iters=flags.FLAGS.warmup_iters,
+                                             warmup_factor=flags.FLAGS.warmup_factor, warmup_method=flags.FLAGS.warmup_method,
+                                             anneal_point=flags.FLAGS.anneal_point, anneal_method=flags.FLAGS.anneal_method,
+                                             target_lr_factor=0)
+    its = [0, 1, 10, 500, 999, 1000, 1001, 5000, 14399, 14400, 14401, 16000, 18000, 19999]
+    fac = {}
+    for it in range(total):
+        if it in its:
+            fac[it] = opt.param_groups[0]["lr"]
+        opt.step()
+        sch.step()
+    out["lr_total"] = np.int64(total)
+    out["lr_iters"] = np.array(its, np.int64)
+    out["lr_factor"] = np.array([fac[i] for i in its], np.float64)
+    out["lr_args"] = np.array([flags.FLAGS.warmup_iters, flags.FLAGS.warmup_factor, flags.FLAGS.anneal_point], np.float64)
+    save("train_glue", **out)
+
+
 def _patched(knn_list):
     """replay recorded index tensors into the reference (it resolves get_neighbor_index through module globals)."""
     it = iter(knn_list)
@@ -564,6 +620,6 @@ def ranger_case():
 if __name__ == "__main__":
     cases = {"knn": knn_cases, "gather_dir": gather_dir_cases, "conv": conv_cases, "chamfer": chamfer_cases,
              "face_enc": face_enc_case, "posenet": posenet_case, "backward": backward_cases, "ranger": ranger_case,
-             "dcd": dcd_case, "posenet_1028": posenet_1028_case}
+             "dcd": dcd_case, "posenet_1028": posenet_1028_case, "train_glue": train_glue_case}
     for name in (sys.argv[1:] or list(cases)):       # python make_golden.py [case ...]
         cases[name]()

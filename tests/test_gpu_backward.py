@@ -362,22 +362,31 @@ def test_train_step_runs_and_learns(optimizer):
     """the synthetic RL_TDA step (train_step.py): finite loss, every trainable parameter that is on the path gets a
     finite gradient, and a few steps on one fixed batch reduce the loss."""
     from tgpose_b200.posenet import PoseNet9D
-    from tgpose_b200.train_step import TrainStep, synthetic_targets
+    from tgpose_b200.train_step import TrainStep, augment, synthetic_targets
     torch.manual_seed(0)
     net = PoseNet9D(train_outputs=True).cuda()
-    step = TrainStep(net, lr=2e-4, optimizer=optimizer)
+    net2 = PoseNet9D(only_encoder=True).cuda()                     # RL_TDA.py:20: frozen encoder on the augmented cloud
+    step = TrainStep(net, lr=2e-4, optimizer=optimizer, net2=net2, total_iters=100)
+    step.sched.kw.update(warmup_iters=0)                           # (the flags' 1000-iteration warm-up would freeze 13 steps)
+    step.sched._apply()
     gen = torch.Generator().manual_seed(3)
     pts = (torch.rand(4, 256, 3, generator=gen) - 0.5) * 0.3 + torch.tensor([0.1, -0.1, 1.0])
     cat = torch.randint(0, 6, (4, 1), generator=gen).float()
     tgt = synthetic_targets(4, 5, "cuda")
-    first = float(step(pts.cuda(), cat.cuda(), tgt))
+    aug = augment(pts, 9).cuda()
+    w2 = {n: p.detach().clone() for n, p in net2.named_parameters()}
+    first = float(step(pts.cuda(), cat.cuda(), tgt, aug))
+    assert set(step.last_losses) >= {"RL_loss", "recon_1_loss", "recon_consistency_loss", "R_DCD", "recon", "pose"}
+    assert all(torch.isfinite(v).all() for v in step.last_losses.values())
+    assert all(p.grad is None for p in net2.parameters())           # net2 runs under no_grad and is never stepped
+    assert all(torch.equal(w2[n], p.detach()) for n, p in net2.named_parameters())
     for n, p in net.named_parameters():
         if "proj_layer" in n:
             continue
         assert p.grad is not None and torch.isfinite(p.grad).all(), n
     hist = [first]
     for _ in range(12):
-        hist.append(float(step(pts.cuda(), cat.cuda(), tgt)))
+        hist.append(float(step(pts.cuda(), cat.cuda(), tgt, aug)))
     print("train-step losses:", " ".join(f"{v:.4f}" for v in hist))
     assert all(np.isfinite(v) for v in hist)
     # dropout (p = 0.5 / 0.2), 4-cloud BatchNorm statistics and fp32 atomics make the trajectory noisy: the check is that

@@ -171,3 +171,32 @@ def test_ranger_has_no_cpu_path():
     from tgpose_b200.ranger import Ranger
     with pytest.raises(RuntimeError):
         Ranger([torch.nn.Parameter(torch.zeros(4, 4))])
+
+
+def test_training_glue_matches_reference():
+    """the RL_TDA loss glue and lr schedule restated in train_step.py against the reference's own functions
+    (losses/consistency_loss.py, tools/torch_utils/solver/lr_scheduler.py; tests/golden/train_glue.npz)."""
+    from tgpose_b200 import train_step as ts
+    from util import golden
+    g = golden("train_glue")
+    x1 = torch.from_numpy(g["x1"]).requires_grad_(True)
+    pc_re = torch.from_numpy(g["pc_re"]).requires_grad_(True)
+    l1 = ts.feat_consistency_loss(x1, torch.from_numpy(g["x2"]), float(g["feat_consist_w"]))
+    l2 = ts.prop_sym_matching_loss(torch.from_numpy(g["pc"]), pc_re, torch.from_numpy(g["gt_R"]), torch.from_numpy(g["gt_t"]),
+                                   torch.from_numpy(g["sym"]))
+    (l1 + l2).backward()
+    assert abs(float(l1) - float(g["feat_loss"])) <= 1e-5 * abs(float(g["feat_loss"]))
+    assert abs(float(l2) - float(g["sym_loss"])) <= 1e-5 * abs(float(g["sym_loss"]))
+    assert np.allclose(x1.grad.numpy(), g["g_x1"], rtol=1e-4, atol=1e-8)
+    assert np.allclose(pc_re.grad.numpy(), g["g_pc_re"], rtol=1e-4, atol=1e-9)
+    wi, wf, ap = g["lr_args"]
+    for it, f in zip(g["lr_iters"], g["lr_factor"]):
+        mine = ts.flat_and_anneal_factor(int(it), int(g["lr_total"]), warmup_iters=int(wi), warmup_factor=float(wf), anneal_point=float(ap))
+        assert abs(mine - f) <= 1e-12 + 1e-9 * abs(f), (it, mine, f)
+    # the scheduler object applies the factor of iteration `it` after `it` step() calls, like LambdaLR
+    opt = torch.optim.SGD([torch.nn.Parameter(torch.zeros(1))], lr=2.0)
+    sch = ts.FlatAndAnneal(opt, int(g["lr_total"]), warmup_iters=int(wi), warmup_factor=float(wf), anneal_point=float(ap))
+    assert abs(opt.param_groups[0]["lr"] - 2.0 * g["lr_factor"][0]) < 1e-12
+    for _ in range(10):
+        sch.step()
+    assert abs(opt.param_groups[0]["lr"] - 2.0 * g["lr_factor"][list(g["lr_iters"]).index(10)]) < 1e-12

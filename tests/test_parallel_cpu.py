@@ -33,8 +33,20 @@ def _worker(rank, world, port, q, done):
     nb = parallel.allreduce_gradients(lin.parameters(), world)
     flat = torch.arange(10, dtype=torch.float32) * (rank + 1)          # a flat gradient arena (ranger.Ranger.flat_grads)
     nflat = parallel.allreduce_flat(flat, world, bucket_bytes=16)       # 4-element slices -> 3 collectives
+    # overlapped all-reduce over a flat arena: three parameters whose gradients are views of one buffer, 2 slices
+    # (16 bytes = 4 elements each would give 3; use 6-element slices -> 2), one parameter WITHOUT a gradient this step
+    ps = [torch.nn.Parameter(torch.full((4,), 1.0)), torch.nn.Parameter(torch.full((3,), 2.0)), torch.nn.Parameter(torch.full((5,), 3.0))]
+    arena = torch.zeros(12)
+    offs = [0, 4, 7]
+    for p_, o in zip(ps, offs):
+        p_.grad = arena[o:o + p_.numel()].view(p_.shape)
+    ov = parallel.OverlappedAllReduce(arena, ps, offs, bucket_bytes=24, world=world)
+    ov.begin()
+    ((ps[0] * (rank + 1)).sum() + (ps[1] * 10 * (rank + 1)).sum()).backward()       # ps[2] gets no gradient
+    n_slices = ov.finish()
+    ov_res = (arena.tolist(), n_slices, ov.launched_early, all(p_.grad.data_ptr() == arena[o:].data_ptr() for p_, o in zip(ps, offs)))
     # plain lists, not tensors: a tensor travels as a shared-memory handle that dies with its producer
-    q.put((rank, lo, hi, perm[:8].tolist(), lin.weight.grad.tolist(), lin.bias.grad.tolist(), nb, flat.tolist(), nflat))
+    q.put((rank, lo, hi, perm[:8].tolist(), lin.weight.grad.tolist(), lin.bias.grad.tolist(), nb, flat.tolist(), nflat, ov_res))
     dist.destroy_process_group()
     done.wait(timeout=120)          # stay alive until the parent has drained the queue
 
@@ -53,6 +65,14 @@ def test_two_rank_sharding_and_grad_allreduce():
         p.join(timeout=60)
         assert p.exitcode == 0
     res = [tuple(torch.tensor(v) if isinstance(v, list) and i in (4, 5, 7) else v for i, v in enumerate(t)) for t in res]
+    ov0, ov1 = res[0][9], res[1][9]
+    res = [t[:9] for t in res]
+    # averaged over the two ranks: d/dp0 = (1 + 2) / 2, d/dp1 = 10 * 1.5, p2 untouched (0); gradients stayed arena views
+    assert ov0[0] == ov1[0] == [1.5] * 4 + [15.0] * 3 + [0.0] * 5
+    assert ov0[1] == 2 and ov0[3] and ov1[3]
+    # slice 0 = elements 0..5 (p0, head of p1) went out from the hooks during backward; slice 1 (tail of p1, p2) waits for
+    # p2, which got no gradient, and is launched by finish()
+    assert ov0[2] == ov1[2] == 1
     (r0, lo0, hi0, perm0, gw0, gb0, nb0, f0, nf0), (r1, lo1, hi1, perm1, gw1, gb1, nb1, f1, nf1) = res
     assert nf0 == nf1 == 3 and torch.equal(f0, f1) and torch.allclose(f0, torch.arange(10, dtype=torch.float32) * 1.5)
     assert (lo0, hi0, lo1, hi1) == (0, 17, 17, 33)           # contiguous, disjoint, covering

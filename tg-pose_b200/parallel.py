@@ -75,6 +75,71 @@ def allreduce_flat(flat, world=None, bucket_bytes=32 << 20):
     return n_buckets
 
 
+class OverlappedAllReduce:
+    """DDP-style overlap of the gradient all-reduce with backward over a FLAT gradient arena (ranger.Ranger.flat_grads).
+
+    The arena is cut into ~bucket_bytes slices.  Every parameter whose gradient view lies (partly) in a slice holds one
+    count of it; a post-accumulate-grad hook releases the count, and the slice whose count reaches zero is all-reduced
+    at once with async_op=True -- NCCL orders the collective behind the kernels already queued on the compute stream and
+    runs it on its own stream while backward keeps launching.  finish() launches whatever is left (parameters that got no
+    gradient this step), waits, and divides by the world size.  Slices are launched in a fixed order per rank only if the
+    hooks fire in the same order on every rank, which holds for identical replicas (same autograd graph)."""
+
+    def __init__(self, flat, params, offsets, bucket_bytes=32 << 20, world=None):
+        self.flat = flat
+        self.world = world or dist.get_world_size()
+        step = max(1, bucket_bytes // flat.element_size())
+        self.bounds = [(lo, min(lo + step, flat.numel())) for lo in range(0, flat.numel(), step)]
+        self.members = [0] * len(self.bounds)
+        self.param_slices = []
+        for p, off in zip(params, offsets):
+            first, last = off // step, (off + max(p.numel(), 1) - 1) // step
+            sl = list(range(first, min(last, len(self.bounds) - 1) + 1))
+            self.param_slices.append(sl)
+            for i in sl:
+                self.members[i] += 1
+        self.handles = []
+        self.left = list(self.members)
+        self.launched = [False] * len(self.bounds)
+        self.active = False
+        for p, sl in zip(params, self.param_slices):
+            p.register_post_accumulate_grad_hook(self._make_hook(sl))
+
+    def _make_hook(self, sl):
+        def hook(_p):
+            if not self.active:
+                return
+            for i in sl:
+                self.left[i] -= 1
+                if self.left[i] == 0:
+                    self._launch(i)
+        return hook
+
+    def _launch(self, i):
+        if self.launched[i]:
+            return
+        lo, hi = self.bounds[i]
+        self.handles.append(dist.all_reduce(self.flat[lo:hi], op=dist.ReduceOp.SUM, async_op=True))
+        self.launched[i] = True
+
+    def begin(self):
+        self.left = list(self.members)
+        self.launched = [False] * len(self.bounds)
+        self.handles = []
+        self.active = True
+
+    def finish(self):
+        self.active = False
+        early = sum(self.launched)
+        for i in range(len(self.bounds)):
+            self._launch(i)
+        for h in self.handles:
+            h.wait()
+        self.flat.div_(self.world)
+        self.launched_early = early
+        return len(self.bounds)
+
+
 @torch.no_grad()
 def sharded_inference(net, points, cat_id, seed=7, gather=True):
     """run `net` on this rank's slice of (points, cat_id); optionally all_gather the small pose outputs."""
