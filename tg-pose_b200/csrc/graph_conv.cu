@@ -212,6 +212,10 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // one spends 4 (gather) + ~3.2 (record) cycles per 112 elements = 0.064 (profiles/r02_layer_conv.md; ncu: LSU data pipe
 // 81 % busy, i.e. the kernel now sits on that roof).  Loading the records straight from global memory into registers
 // (prefetch distance 4) was 1.9x slower: ptxas sinks the loads next to their uses under the 64-register cap.
+// Also tried and dropped (round 2): a lane owning HALF a 128-byte-padded row (4 rotated chunks, 16 points per warp, one
+// record load per 448 elements: 0.042 pipe cycles per element on paper).  Its 48 direction constants + 16 running maxima
+// need ~128 registers, i.e. 13 warps per SM: 322 us against this kernel's 207 us at 32 x 1028 x 128 (ncu: 18 % of the warp
+// slots occupied, every warp waiting on its own fixed-latency chain).
 // TAB: the (cloud, channel-group) support table is staged in shared memory by TMA bulk copies (N*S*16 B <= ~227 KB,
 // i.e. N <= ~2070 at S = 7); otherwise (the N = 2048..16384 microbenchmark clouds) the rows are gathered through L2.
 template <bool ARG, int KT, bool TAB>
@@ -428,6 +432,9 @@ extern "C" int tgp_layer_conv_fwd(const float* edge_rec, const float* directions
     if (S * 4 > 32) return fail(TGP_EINVAL, "tgp_layer_conv_fwd: S > 8 unsupported");
     if (k > 255 || B > 65535) return fail(TGP_EINVAL, "tgp_layer_conv_fwd: k > 255 or B > 65535");
     if ((uintptr_t)support_slab % 16 || (uintptr_t)edge_rec % 16) return fail(TGP_EINVAL, "tgp_layer_conv_fwd: slab / edge_rec must be 16-byte aligned");
+    cudaStream_t st = as_stream(stream);
+    const long M = (long)B * N;
+    const int kp = (C + 31) / 32 * 32;
     const int W = S * 4;
     const size_t tab_bytes = (size_t)N * W * sizeof(float);
     const size_t ring_per_warp = (size_t)2 * k * 64;          // two quads of k records x 4 points x 16 B
@@ -458,9 +465,6 @@ extern "C" int tgp_layer_conv_fwd(const float* edge_rec, const float* directions
     const int threads = nw * 32;
     const size_t smem = (tab ? tab_al : 0) + (size_t)nw * ring_per_warp;
     dim3 grid(C / 4, B, zs);
-    cudaStream_t st = as_stream(stream);
-    const long M = (long)B * N;
-    const int kp = (C + 31) / 32 * 32;
 #define TGP_LAUNCH_LC(ARGV, KTV, TABV)                                                                                   \
     do {                                                                                                                \
         cudaFuncSetAttribute(layer_conv_kernel<ARGV, KTV, TABV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
