@@ -92,11 +92,12 @@ def test_pack_layer_column_order():
     ste = torch.arange(C * cin, dtype=torch.float32).reshape(C, cin, 1) + 1000
     wcat, bcat, _ = _pack_layer(w, b, ste, S, C)
     assert wcat.shape == (cin, (S + 2) * C) and bcat.shape == ((S + 2) * C,)
-    assert torch.equal(wcat[:, :C], w[:, :C])
+    SC = S * C                                                     # packed order: [slab | centre | STE]
+    assert torch.equal(wcat[:, SC:SC + C], w[:, :C]) and torch.equal(bcat[SC:SC + C], b[:C])
     for cg in range(C // 4):
         for s in range(S):
             for c4 in range(4):
-                col = C + cg * S * 4 + s * 4 + c4
+                col = cg * S * 4 + s * 4 + c4
                 assert torch.equal(wcat[:, col], w[:, C + s * C + cg * 4 + c4])
                 assert bcat[col] == b[C + s * C + cg * 4 + c4]
     assert torch.equal(wcat[:, (S + 1) * C:], ste[:, :, 0].t())

@@ -2,7 +2,7 @@
 
 Forward pipelines (each step one C-ABI launch):
   HSSurfaceFn : gcn3d.py:78-112   STE gemm | xyz kNN | surface conv | ORL gather-max-mean | ORL gemm
-  HSLayerFn   : gcn3d.py:142-186  fused projection+STE gemm (centre | support slab | f_STE) |
+  HSLayerFn   : gcn3d.py:142-186  fused projection+STE gemm (support slab | centre | f_STE) |
                                   feature kNN | edge records | layer conv | xyz kNN | ORL | ORL gemm
   PoolFn      : gcn3d.py:225-245  xyz kNN | gather-max on the sampled rows | row select
 The backward contract is SURVEY 8(a'); see backward.py for the kernels' host side.
@@ -12,17 +12,19 @@ import torch
 from . import ops
 
 def _pack_layer(weights, bias, ste_w, S, C):
-    """[centre | support in slab column order (cgroup, s, c4) | STE^T] as one (in, (S+2)*C) operand, its bias and
-    its tensor-core split.  Cached per parameter object/version (weights are constants in inference)."""
+    """[support in slab column order (cgroup, s, c4) | centre | STE^T] as one (in, (S+2)*C) operand, its bias and
+    its tensor-core split.  The slab columns come FIRST: at S = 7 a channel group is 28 columns and S*C is a multiple of
+    224, so the projection runs on 224-column tiles that each hold 8 whole channel groups and stores every (group, 32 rows)
+    block with one bulk copy (csrc/gemm_tc.cu).  Cached per parameter object/version (weights are constants in inference)."""
 
     def build():
         cin = weights.shape[0]
         with torch.no_grad():
             w = weights.detach()
             sup = w[:, C:].reshape(cin, S, C // 4, 4).permute(0, 2, 1, 3).reshape(cin, S * C)
-            wcat = torch.cat([w[:, :C], sup, ste_w.detach().reshape(C, cin).t()], dim=1).contiguous()
+            wcat = torch.cat([sup, w[:, :C], ste_w.detach().reshape(C, cin).t()], dim=1).contiguous()
             b = bias.detach()
-            bcat = torch.cat([b[:C], b[C:].reshape(S, C // 4, 4).permute(1, 0, 2).reshape(-1),
+            bcat = torch.cat([b[C:].reshape(S, C // 4, 4).permute(1, 0, 2).reshape(-1), b[:C],
                               torch.zeros(C, device=b.device, dtype=b.dtype)]).contiguous()
             wsplit = ops.split_tf32(wcat, src_is_kn=True) if wcat.is_cuda else None
         return wcat, bcat, wsplit
@@ -102,7 +104,7 @@ class HSLayerFn(torch.autograd.Function):
         f_ste = torch.empty((M, C), dtype=torch.float32, device=dev)
         tc = ops.tc_eligible(M, C, C)
         ops.gemm(fm.view(M, cin), wcat, False,
-                 [(0, C, centre, 0, 0), (C, C + S * C, slab, 1, S * 4), (C + S * C, (S + 2) * C, f_ste, 0, 0)],
+                 [(0, S * C, slab, 1, S * 4), (S * C, S * C + C, centre, 0, 0), (S * C + C, (S + 2) * C, f_ste, 0, 0)],
                  bias=bcat, A_split=fm_split if (fm_split is not None and fm_split.numel()) else None,
                  B_split=wcat_split)
         if idx_feat is None:

@@ -10,7 +10,7 @@ uint8 arg-max slots saved in the forward:
       dg   = d_gb W2b, dW2b = d_gb^T g, dW2a = gz^T f         tgp_gemm / tgp_gemm_tn(_tc)
       d_f  = gz W2a + gz + scatter_argmax(dg / N)             tgp_gather_max_bwd + tgp_gemm (residual epilogue)
   layer conv (SURVEY 8a' bullets 1-2)                         tgp_layer_conv_bwd  -> d_support, d_directions
-  projection fm @ [Wc | Wsup | W_STE^T] + b                   tgp_gemm (dfm), tgp_gemm_tn_tc (dW), tgp_colsum (db)
+  projection fm @ [Wsup | Wc | W_STE^T] + b                   tgp_gemm (dfm), tgp_gemm_tn_tc (dW), tgp_colsum (db)
   surface conv                                                tgp_surface_conv_bwd -> d_directions
   Pool / upsample                                             tgp_gather_max_bwd / tgp_scatter_add_rows
 """
@@ -62,11 +62,11 @@ def hs_layer_backward(ctx, grad_out):
     B, N, cin = fm.shape
     M = B * N
     SC = S * C
-    # gradient operand of the packed projection, columns [d_centre | d_support (slab order) | d_f_STE]
+    # gradient operand of the packed projection, columns [d_support (slab order) | d_centre | d_f_STE] (autograd._pack_layer)
     dP = torch.empty((M, (S + 2) * C), dtype=torch.float32, device=fm.device)
     _, _, d_conv2 = _orl_tail_bwd(grad_out, out, post, feature, g, idx_xyz, arg_orl, conv2_w, B, N, C,
-                                  gz_dst=dP[:, C + SC:], df_dst=dP[:, :C])
-    d_dir = ops.layer_conv_bwd(rec, directions, slab, arg, dP[:, :C], B, N, S, C, d_support=dP[:, C:C + SC])
+                                  gz_dst=dP[:, C + SC:], df_dst=dP[:, SC:SC + C])
+    d_dir = ops.layer_conv_bwd(rec, directions, slab, arg, dP[:, SC:SC + C], B, N, S, C, d_support=dP[:, :SC])
     wcat, _bcat, _ws = _pack_layer(weights, bias, ste_w, S, C)    # (cin, (S+2)C)
     # dP @ wcat^T on mixed operands (gradients feed no neighbour search: fp16+bf16 accuracy is enough, 1.5 instead of 3 passes)
     d_fm = torch.empty((M, cin), dtype=torch.float32, device=fm.device)
@@ -74,9 +74,9 @@ def hs_layer_backward(ctx, grad_out):
              B_split=ops.split_mixed(wcat), mixed=True)
     d_wcat = ops.gemm_tn(fm.view(M, cin), dP, mixed=True)         # (cin, (S+2)C); mixed operands like the heads
     d_bcat = ops.colsum(dP[:, :C + SC]).view(-1)
-    d_weights = torch.cat([d_wcat[:, :C],
-                           d_wcat[:, C:C + SC].reshape(cin, C // 4, S, 4).permute(0, 2, 1, 3).reshape(cin, SC)], dim=1)
-    d_bias = torch.cat([d_bcat[:C], d_bcat[C:].reshape(C // 4, S, 4).permute(1, 0, 2).reshape(SC)])
+    d_weights = torch.cat([d_wcat[:, SC:SC + C],
+                           d_wcat[:, :SC].reshape(cin, C // 4, S, 4).permute(0, 2, 1, 3).reshape(cin, SC)], dim=1)
+    d_bias = torch.cat([d_bcat[SC:], d_bcat[:SC].reshape(C // 4, S, 4).permute(1, 0, 2).reshape(SC)])
     d_ste = d_wcat[:, C + SC:].t().reshape(C, cin, 1)
     return (None, d_fm.view(B, N, cin), d_weights, d_bias, d_dir, d_ste, d_conv2,
             None, None, None, None, None, None, None, None, None)
