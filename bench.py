@@ -702,11 +702,11 @@ def run_micro(args):
                          "knn_xyz": {"ms": t_xyz * 1e3, "gpairs_s": B * N * N / t_xyz / 1e9, "fp32_frac": f_xyz / t_xyz / 1e12 / FP32_PEAK_TFLOPS},
                          "knn_feat_D128": {"ms": t_feat * 1e3, "gpairs_s": B * N * N / t_feat / 1e9, "tflops": f_feat / t_feat / 1e12,
                                            "fp32_frac": f_feat / t_feat / 1e12 / FP32_PEAK_TFLOPS,
-                                           "path": "tcgen05 3xTF32 + warp select" if k <= 31 else "fp32 FMA tile + warp select"},
+                                           "path": "tcgen05 3xTF32 + threshold select (64 group minima)" if k <= 31 else "tcgen05 3xTF32 + threshold select (128 group minima)"},
                          "surface_conv": {"ms": t_surf * 1e3, "tflops": f_surf / t_surf / 1e12, "fp32_frac": f_surf / t_surf / 1e12 / FP32_PEAK_TFLOPS},
                          "layer_conv": {"ms": t_lay * 1e3, "tflops": f_lay / t_lay / 1e12, "fp32_frac": f_lay / t_lay / 1e12 / FP32_PEAK_TFLOPS,
                                         "hbm_gbs": b_lay / t_lay / 1e9, "hbm_frac": b_lay / t_lay / 1e9 / peaks["hbm_gbs"],
-                                        "table": "smem" if N * S * 16 <= 215 * 1024 else "L2 gather"}})
+                                        "table": "smem" if N * S * 16 + 4 * 2 * k * 64 <= 227 * 1024 else "L2 gather"}})
     print(json.dumps({"metric": "kNN + Conv_surface/Conv_layer microbench sweep", "S": S, "C": C, "D": D,
                       "fp32_peak_tflops": FP32_PEAK_TFLOPS, "hbm_peak_gbs": peaks["hbm_gbs"], "peak_source": peaks["source"],
                       "timing": "median of CUDA-event times, 256 MB L2 flush before each iteration", "rows": rows}), flush=True)

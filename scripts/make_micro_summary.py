@@ -12,7 +12,7 @@ with open(os.path.join(ROOT, "profiles", f"{R}_microbench.md"), "w") as f:
             f"Roofs: FP32 {d['fp32_peak_tflops']:.1f} TFLOP/s (148 SM x 128 lanes x 2 x 1.965 GHz, derived), HBM {d['hbm_peak_gbs']:.0f} GB/s ({d['peak_source']}).\n"
             "Fractions are ALGORITHMIC work (SURVEY 8d) / time / roof: kNN `N^2(2D+3)+N^2` flops, surface conv `N k S C 8 + N S C`, "
             "layer conv `N k S C 9 + N S C` flops and its compulsory bytes.  The feature-space kNN computes its inner products on the "
-            "tensor cores for k <= 31, so its fraction of the FP32 (CUDA-core) roof can exceed 100 %; k = 40, 50 run the fp32 FMA tile kernel.\n\n"
+            "tensor cores (k <= 63 since round 2), so its fraction of the FP32 (CUDA-core) roof can exceed 100 %.\n\n"
             "| N | B | k | kNN xyz ms | Gpairs/s | % FP32 | kNN feat ms | Gpairs/s | % FP32 | path | surface conv ms | % FP32 | layer conv ms | % FP32 | % HBM | table |\n"
             "|---:|---:|---:|---:|---:|---:|---:|---:|---:|---|---:|---:|---:|---:|---:|---|\n")
     for r in d["rows"]:

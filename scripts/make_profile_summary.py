@@ -9,6 +9,8 @@ import csv, gzip, json, os, re, subprocess, sys
 from collections import OrderedDict, defaultdict
 
 R = sys.argv[1] if len(sys.argv) > 1 else "r01"
+# optional: what was captured (default: one inference forward); e.g. "the backward / loss / optimiser kernels of ..."
+WHAT = sys.argv[2] if len(sys.argv) > 2 else None
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GO, PR = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
 
@@ -43,10 +45,10 @@ def launches():
     with gzip.open(os.path.join(PR, f"{R}_launches.csv.gz"), "wt") as f:
         f.write(raw)
     with open(os.path.join(PR, f"{R}_launches_summary.md"), "w") as f:
-        f.write(f"# {R} -- ncu launch list of `python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-graph`\n\n"
+        f.write(f"# {R} -- ncu launch list of `python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-graph --no-train`\n\n"
                 "Command (under gpurun, directly after the same command exited 0 without ncu; scripts/profile_round.sh):\n\n"
                 f"    ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/{R}_launches.csv \\\n"
-                "        python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-graph\n\n"
+                "        python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-graph --no-train\n\n"
                 f"{n} launches, {total / 1000.0:.2f} ms of kernel time in total (3 warm-up + 2 per-kernel-table + 2 timed + 2 end-to-end "
                 "forward passes of 32 x 1028 clouds, plus the L2 flush fills).  Per-launch times are cold-cache and serialised: compare SHARES with "
                 "bench.py's `kernels` table, not absolutes.  `--no-graph` so that every kernel is its own launch row "
@@ -116,10 +118,16 @@ def forward():
     json.dump({"source": f"ncu --set full --clock-control none, one forward of 32 x 1028 clouds (scripts/profile_round.sh {R})",
                "per_kernel": per, "launches": launches_}, open(os.path.join(PR, f"{R}_kernels.json"), "w"), indent=1)
     with open(os.path.join(PR, f"{R}_kernels.md"), "w") as f:
-        f.write(f"# {R} -- `ncu --set full` of every library kernel in one forward (32 x 1028 clouds, eval, eager launches)\n\n"
+        if WHAT:
+            f.write(f"# {R} -- ncu sections of {WHAT}\n\nCommand: `scripts/profile_train.sh {R}`.  Times are under the profiler (cold caches, "
+                    "serialised) -- use them for shares and per-kernel diagnosis, never as benchmark values.  dram = `dram__bytes_read.sum + "
+                    "dram__bytes_write.sum`.\n\n")
+        else:
+            f.write(f"# {R} -- `ncu --set full` of every library kernel in one forward (32 x 1028 clouds, eval, eager launches)\n\n"
                 "Command: `scripts/profile_round.sh` step 2 (`-k regex:<library kernel names> -s <launches of the two warm-up forwards> -c <launches of "
                 "one forward>`, i.e. the third forward of `scripts/profile_forward.py`).  Times are under the profiler (cold caches, serialised) -- use them for "
-                "shares and per-kernel diagnosis, never as benchmark values.  dram = `dram__bytes_read.sum + dram__bytes_write.sum`.\n\n"
+                "shares and per-kernel diagnosis, never as benchmark values.  dram = `dram__bytes_read.sum + dram__bytes_write.sum`.\n\n")
+        f.write(
                 "## Per kernel (summed over its launches in the forward)\n\n"
                 "| kernel | launches | us | share | DRAM MB | tensor pipe % | FMA pipe % | IPC |\n|---|---:|---:|---:|---:|---:|---:|---:|\n")
         tot = sum(a["us"] for a in per.values())

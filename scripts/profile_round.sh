@@ -7,9 +7,9 @@ O=gpurun_out
 mkdir -p $O
 if [ "${2:-all}" = "all" ]; then
 # 1. launch list of the benchmark command (eager launches: one row per kernel; cold-cache, serialised)
-python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-graph > $O/${R}_plain_bench.log 2>&1 &&
+python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-graph --no-train > $O/${R}_plain_bench.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file $O/${R}_launches.csv \
-    python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-graph > $O/${R}_ncu_launches.log 2>&1
+    python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-graph --no-train > $O/${R}_ncu_launches.log 2>&1
 fi
 # (ncu matches the base name, without the tgp:: namespace)
 KERNELS="^(concat_rows|decode_max|edge_record|gather_max|gather_rows|gemm_naive|gemm_skinny|gemm_simt|gemm_tc|knn_tc|knn_xyz|knn_feat|layer_conv|nearest|orl_|rownorm|select_rows|split_tf32|split_mixed|surface_conv|direction_norm)"
