@@ -79,7 +79,10 @@ class Face_Enc(nn.Module):
         """the five graph-conv feature maps and the two nearest-upsampling index tensors (FaceRecon.py:55-70):
         -> dict(fm_0 (B,N0,128), fm_1 (B,N0,128), fm_2, fm_3 (B,N1,256), fm_4 (B,N2,512), nn1, nn2 (B,N0,1) int32)."""
         k = self.neighbor_num
-        fold = not self.training
+        # eval BatchNorm + ReLU folded into the GEMM epilogue only when nothing can ask for a gradient through it
+        # (the folded constants are detached: an eval-mode forward with grad enabled takes the module path instead)
+        fold = not self.training and not (torch.is_grad_enabled() and any(
+            p.requires_grad for bn in (self.bn1, self.bn2, self.bn3) for p in bn.parameters()))
         self._slot = 0
         share = self._inject is None
 
