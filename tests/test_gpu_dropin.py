@@ -24,5 +24,5 @@ def test_reference_face_enc_runs_unchanged_on_our_gcn3d():
     assert r["same_init"] and r["state_keys_equal_golden"]        # same constructor order / parameter names as the reference
     # the reference's call sequence on the plain API and our fused encoder run the same kernels: they agree up to the
     # BatchNorm folding of the fused path (and the index flips that can seed); the reference golden is the T3 comparison
-    assert r["frac_vs_fused"] > 0.98
+    assert r["frac_vs_fused"] > 0.99
     assert r["frac_vs_reference_golden"] > 0.90
