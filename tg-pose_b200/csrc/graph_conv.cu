@@ -215,7 +215,9 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // Also tried and dropped (round 2): a lane owning HALF a 128-byte-padded row (4 rotated chunks, 16 points per warp, one
 // record load per 448 elements: 0.042 pipe cycles per element on paper).  Its 48 direction constants + 16 running maxima
 // need ~128 registers, i.e. 13 warps per SM: 322 us against this kernel's 207 us at 32 x 1028 x 128 (ncu: 18 % of the warp
-// slots occupied, every warp waiting on its own fixed-latency chain).
+// slots occupied, every warp waiting on its own fixed-latency chain).  A support PAIR per lane (8 points per warp, 72
+// registers, 26 warps) ran correctly at 262 us: it executes MORE instructions per element than this kernel (0.29 vs 0.23:
+// its per-group ring bookkeeping and register-pair moves outweigh the shared record load) at 61 % pipe utilisation.
 // TAB: the (cloud, channel-group) support table is staged in shared memory by TMA bulk copies (N*S*16 B <= ~227 KB,
 // i.e. N <= ~2070 at S = 7); otherwise (the N = 2048..16384 microbenchmark clouds) the rows are gathered through L2.
 template <bool ARG, int KT, bool TAB>
