@@ -714,17 +714,18 @@ def run_micro(args):
 
 def profile_traffic(kernel_substr):
     """DRAM bytes per forward of the kernels whose name contains `kernel_substr`, from the newest committed
-    profiles/*_kernels.json (written by scripts/make_profile_summary.py from an `ncu --set full` capture); None if absent."""
+    profiles/*_kernels.json that captured such a kernel (written by scripts/make_profile_summary.py from an ncu capture of one
+    inference forward; the training-step captures do not contain the forward kernels); None if absent."""
     import glob
-    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_kernels.json")))
-    if not files:
-        return None
-    try:
-        per = json.load(open(files[-1]))["per_kernel"]
-        tot = sum(v["dram_bytes"] for k, v in per.items() if kernel_substr in k)
-        return tot if tot > 0 else None
-    except Exception:
-        return None
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "*_kernels.json")), reverse=True):
+        try:
+            per = json.load(open(path))["per_kernel"]
+            tot = sum(v["dram_bytes"] for k, v in per.items() if kernel_substr in k)
+            if tot > 0:
+                return tot
+        except Exception:
+            continue
+    return None
 
 
 def kernel_report(event_log, steps, B, peaks):
