@@ -7,6 +7,7 @@
 #include "common.cuh"
 #include <cuda_bf16.h>
 #include <float.h>
+#include <stdlib.h>
 
 namespace tgp {
 
@@ -140,7 +141,7 @@ orl_global_kernel(const float* __restrict__ f, const IdxT* __restrict__ idx, int
 //            shuffles; one LDS.128 per neighbour and lane: 1.75 instructions per (neighbour, channel) instead of 4.
 // The per-point maxima are summed per lane, then over the 4 point groups and the warps in a fixed order: deterministic,
 // and independent of the batch.
-constexpr int ORLS_THREADS = 512;
+constexpr int ORLS_THREADS = 1024;                          // upper bound; the launch picks 512 or 1024 (tgp_orl_global)
 template <typename IdxT, bool ARG>
 __global__ void __launch_bounds__(ORLS_THREADS)
 orl_smem_kernel(const float* __restrict__ f, const IdxT* __restrict__ idx, int N, int k, int C,
@@ -152,19 +153,19 @@ orl_smem_kernel(const float* __restrict__ f, const IdxT* __restrict__ idx, int N
     const long b = blockIdx.y;
     const float* fb = f + b * N * (long)C;
     if (C % 4 == 0 && c0 + 32 <= C && ((uintptr_t)f & 15) == 0) {
-        for (int p = threadIdx.x; p < N * 8; p += ORLS_THREADS) {
+        for (int p = threadIdx.x; p < N * 8; p += blockDim.x) {
             const int n = p >> 3, q = p & 7;
             asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(orl_tab + n * 32 + q * 4)),
                          "l"(fb + (long)n * C + c0 + q * 4) : "memory");
         }
         asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
     } else {
-        for (int n = warp; n < N; n += ORLS_THREADS / 32) orl_tab[n * 32 + lane] = c0 + lane < C ? __ldg(fb + (long)n * C + c0 + lane) : 0.f;
+        for (int n = warp; n < N; n += blockDim.x / 32) orl_tab[n * 32 + lane] = c0 + lane < C ? __ldg(fb + (long)n * C + c0 + lane) : 0.f;
     }
     __syncthreads();
     const int grp = lane >> 3, l8 = lane & 7;
     const float4* tab4 = reinterpret_cast<const float4*>(orl_tab) + l8;     // row r -> tab4[r * 8]
-    constexpr int PSTEP = (ORLS_THREADS / 32) * 4;                            // points per CTA step
+    const int PSTEP = (blockDim.x / 32) * 4;                                  // points per CTA step
     auto load = [&](int n, int j0) -> int { return (n < N && j0 + l8 < k) ? ld_idx(idx + (b * N + n) * k, j0 + l8) : 0; };
     int n = warp * 4 + grp, j0 = 0;
     int cur = load(n, 0);
@@ -220,8 +221,7 @@ orl_smem_kernel(const float* __restrict__ f, const IdxT* __restrict__ idx, int N
     __syncthreads();
     if (warp == 0 && c0 + lane < C) {
         float s = 0.f;
-#pragma unroll
-        for (int w = 0; w < ORLS_THREADS / 32; ++w) s += part[w][lane];
+        for (int w = 0; w < (int)(blockDim.x / 32); ++w) s += part[w][lane];
         g[b * C + c0 + lane] = s / (float)N;
     }
 }
@@ -399,13 +399,17 @@ extern "C" int tgp_orl_global(const float* f, const void* idx, int idx_bits, int
     if (tab_bytes <= 200 * 1024) {
         // the cloud's channel slice fits in shared memory (N <= 1600): one pass, no partial sums
         dim3 grid(chunks, B);
+        // warps: the gather is a chain of dependent shared-memory reads -- a large table (one CTA per SM) gets all 32 warps;
+        // depends on N only, so a cloud's result does not change with the batch it sits in
+        int threads = N >= 512 ? 1024 : 512;
+        if (const char* e = getenv("TGP_ORL_THREADS")) { const int v = atoi(e); if (v >= 128 && v <= 1024 && v % 32 == 0) threads = v; }   // tuning hook
         TGP_DISPATCH_IDX(idx_bits, {
             if (arg) {
                 cudaFuncSetAttribute(orl_smem_kernel<IdxT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-                orl_smem_kernel<IdxT, true><<<grid, ORLS_THREADS, tab_bytes, st>>>(f, (const IdxT*)idx, N, k, C, g, arg);
+                orl_smem_kernel<IdxT, true><<<grid, threads, tab_bytes, st>>>(f, (const IdxT*)idx, N, k, C, g, arg);
             } else {
                 cudaFuncSetAttribute(orl_smem_kernel<IdxT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-                orl_smem_kernel<IdxT, false><<<grid, ORLS_THREADS, tab_bytes, st>>>(f, (const IdxT*)idx, N, k, C, g, arg);
+                orl_smem_kernel<IdxT, false><<<grid, threads, tab_bytes, st>>>(f, (const IdxT*)idx, N, k, C, g, arg);
             }
         });
         return check_launch("orl_smem_kernel");
