@@ -65,6 +65,28 @@ __device__ __forceinline__ void store_out(float* __restrict__ out, float* __rest
 }
 
 // ------------------------------------------------------------------------------------------
+// packed fp32 pairs (FFMA2 / FMUL2 on sm_100a): two channels per instruction -- same .rn arithmetic as the scalar
+// forms, half the issue slots.  A pair built from one scalar twice is encoded by ptxas as a broadcast operand.
+__device__ __forceinline__ unsigned long long f2_pack(float lo, float hi) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void f2_unpack(unsigned long long v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long f2_mul(unsigned long long a, unsigned long long b) {
+    unsigned long long d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ unsigned long long f2_fma(unsigned long long a, unsigned long long b, unsigned long long c) {
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+
+// ------------------------------------------------------------------------------------------
 // edge records: (dx,dy,dz, idx) per (b,j,n) -- NEIGHBOUR-major, so the points of a warp's quad read contiguous bytes
 template <typename IdxT>
 __global__ void edge_record_kernel(const float* __restrict__ xyz, const IdxT* __restrict__ idx, long total, int N,
@@ -123,6 +145,39 @@ surface_conv_kernel(const float* __restrict__ xyz, const IdxT* __restrict__ idx,
             my[j] = make_float4(x, y, z, 0.f);
         }
         __syncwarp();
+        // two channels (c, c + 32) per lane and iteration as one packed pair: the cosine of a neighbour against a support is
+        // FMUL2 + 2 FFMA2 for both channels -- 5 instead of 8 issue slots per 2 elements (the scalar loop ran at IPC 2.8 with the
+        // FMA pipe 47 % busy: issue-bound)
+        if (S_T > 0 && !ARG && (C & 63) == 0) {
+            for (int c = lane; c < C; c += 64) {
+                unsigned long long sx[S_T > 0 ? S_T : 1], sy[S_T > 0 ? S_T : 1], sz[S_T > 0 ? S_T : 1];
+                float ma[S_T > 0 ? S_T : 1], mb[S_T > 0 ? S_T : 1];
+#pragma unroll
+                for (int s = 0; s < S_T; ++s) {
+                    sx[s] = f2_pack(sd[s * C + c], sd[s * C + c + 32]);
+                    sy[s] = f2_pack(sd[SC + s * C + c], sd[SC + s * C + c + 32]);
+                    sz[s] = f2_pack(sd[2 * SC + s * C + c], sd[2 * SC + s * C + c + 32]);
+                    ma[s] = 0.f; mb[s] = 0.f;
+                }
+#pragma unroll 2
+                for (int j = 0; j < k; ++j) {
+                    const float4 d = my[j];
+                    const unsigned long long dx = f2_pack(d.x, d.x), dy = f2_pack(d.y, d.y), dz = f2_pack(d.z, d.z);
+#pragma unroll
+                    for (int s = 0; s < S_T; ++s) {
+                        float ta, tb;
+                        f2_unpack(f2_fma(dz, sz[s], f2_fma(dy, sy[s], f2_mul(dx, sx[s]))), ta, tb);
+                        ma[s] = fmaxf(ma[s], ta); mb[s] = fmaxf(mb[s], tb);
+                    }
+                }
+                float acca = 0.f, accb = 0.f;
+#pragma unroll
+                for (int s = 0; s < S_T; ++s) { acca += ma[s]; accb += mb[s]; }
+                store_out(out, out_split, kp, pt, C, c, acca * inv_s);
+                store_out(out, out_split, kp, pt, C, c + 32, accb * inv_s);
+            }
+            continue;
+        }
         for (int c = lane; c < C; c += 32) {
             if (S_T > 0) {
                 float sx[S_T > 0 ? S_T : 1], sy[S_T > 0 ? S_T : 1], sz[S_T > 0 ? S_T : 1], m[S_T > 0 ? S_T : 1];
@@ -167,28 +222,6 @@ surface_conv_kernel(const float* __restrict__ xyz, const IdxT* __restrict__ idx,
             }
         }
     }
-}
-
-// ------------------------------------------------------------------------------------------
-// packed fp32 pairs (FFMA2 / FMUL2 on sm_100a): two channels per instruction -- same .rn arithmetic as the scalar
-// forms, half the issue slots.  A pair built from one scalar twice is encoded by ptxas as a broadcast operand.
-__device__ __forceinline__ unsigned long long f2_pack(float lo, float hi) {
-    unsigned long long r;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-    return r;
-}
-__device__ __forceinline__ void f2_unpack(unsigned long long v, float& lo, float& hi) {
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
-}
-__device__ __forceinline__ unsigned long long f2_mul(unsigned long long a, unsigned long long b) {
-    unsigned long long d;
-    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-    return d;
-}
-__device__ __forceinline__ unsigned long long f2_fma(unsigned long long a, unsigned long long b, unsigned long long c) {
-    unsigned long long d;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-    return d;
 }
 
 // 16-byte asynchronous global -> shared copy (LDGSTS, L1 bypassed) and its group bookkeeping
