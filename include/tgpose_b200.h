@@ -310,6 +310,12 @@ int tgp_gemm_tn(const float* A, long lda, const float* Bm, long ldb, long M, int
 size_t tgp_gemm_tn_tc_workspace(long M, int K1, int K2);
 int tgp_gemm_tn_tc(const float* At_split, const float* Bt_split, long M, int K1, int K2, float* out, long ldo,
                    int mixed, void* workspace, size_t workspace_bytes, tgp_stream_t stream);
+/* tgp_gemm_tn_tc_rm: the same contraction on ROW-MAJOR mixed operands read in place (no transposing split): A_mixed (M rows,
+ *                 4*kp_a 16-bit slots per row) and B_mixed (M rows, 4*kp_b slots) as written by tgp_split_mixed, tgp_gemm
+ *                 mode 4 or tgp_affine_act(mixed); they enter the MMA as MN-major operands.  kp_a >= K1, kp_b >= K2,
+ *                 multiples of 64.  Workspace: tgp_gemm_tn_tc_workspace(M, K1, K2). */
+int tgp_gemm_tn_tc_rm(const float* A_mixed, int kp_a, const float* B_mixed, int kp_b, long M, int K1, int K2,
+                      float* out, long ldo, void* workspace, size_t workspace_bytes, tgp_stream_t stream);
 
 /* ------------------------------------------------------------------ heads in training
  * Train-mode Conv1d(k=1) + BatchNorm1d + ReLU/LeakyReLU stacks of the heads (PoseR.py:26-33, PoseTs.py:31-38,

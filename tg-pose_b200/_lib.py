@@ -114,6 +114,8 @@ SIGNATURES = {
                                   c_void_p, c_void_p, ctypes.POINTER(RangerHyper), c_void_p, c_void_p]),
     "tgp_gemm_tn_tc": (c_int, [c_void_p, c_void_p, c_long, c_int, c_int, c_void_p, c_long, c_int, c_void_p, c_size_t,
                                c_void_p]),
+    "tgp_gemm_tn_tc_rm": (c_int, [c_void_p, c_int, c_void_p, c_int, c_long, c_int, c_int, c_void_p, c_long, c_void_p, c_size_t,
+                          c_void_p]),
 }
 
 _lib = None

@@ -70,9 +70,10 @@ def hs_layer_backward(ctx, grad_out):
     wcat, _bcat, _ws = _pack_layer(weights, bias, ste_w, S, C)    # (cin, (S+2)C)
     # dP @ wcat^T on mixed operands (gradients feed no neighbour search: fp16+bf16 accuracy is enough, 1.5 instead of 3 passes)
     d_fm = torch.empty((M, cin), dtype=torch.float32, device=fm.device)
-    ops.gemm(None, wcat, True, [(0, cin, d_fm, 0, 0)], K=dP.shape[1], A_split=ops.split_mixed(dP),
+    dPm = ops.split_mixed(dP)                                     # one mixed split of dP serves both contractions
+    ops.gemm(None, wcat, True, [(0, cin, d_fm, 0, 0)], K=dP.shape[1], A_split=dPm,
              B_split=ops.split_mixed(wcat), mixed=True)
-    d_wcat = ops.gemm_tn(fm.view(M, cin), dP, mixed=True)         # (cin, (S+2)C); mixed operands like the heads
+    d_wcat = ops.gemm_tn(fm.view(M, cin), dP, mixed=True, B_mixed=dPm)   # (cin, (S+2)C); row-major operands read in place
     d_bcat = ops.colsum(dP[:, :C + SC]).view(-1)
     d_weights = torch.cat([d_wcat[:, SC:SC + C],
                            d_wcat[:, :SC].reshape(cin, C // 4, S, 4).permute(0, 2, 1, 3).reshape(cin, SC)], dim=1)

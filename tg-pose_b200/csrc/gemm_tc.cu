@@ -36,7 +36,9 @@ constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;   // TMA warp + MMA warp + ep
 
 struct GemmDev {
     tgp_gemm_args a;
-    int blocked;       // operands are the K-blocked transposed splits of the weight-gradient contraction (tgp_gemm_tn_tc)
+    int blocked;       // 1: operands are the K-blocked transposed splits of the weight-gradient contraction (tgp_gemm_tn_tc)
+                       // 2: row-major mixed operands read in place as MN-major tiles (tgp_gemm_tn_tc_rm)
+    int kp_a, kp_b;    // blocked == 2: 16-bit slots per part of the A / B operand rows
 };
 
 // one output destination of a column: pointer to (row0, col), row stride, and (split mode) the lo-half offset
@@ -364,7 +366,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             unsigned char* sa = base + stage * STAGE_BYTES;
                             tc_mbar_expect_tx(full + stage, STAGE_BYTES);
                             const int a_part = u == 0 ? 0 : (u == 1 ? 2 : 1), b_part = u == 0 ? 0 : (u == 1 ? 1 : 2);
-                            if (P.blocked) {
+                            if (P.blocked == 2) {
+                                // ROW-MAJOR mixed operands read in place as MN-major tiles (tgp_gemm_tn_tc_rm): the contraction
+                                // runs over the ROWS; a stage = 64 rows x (128 | BN) columns of one 16-bit part, fetched as
+                                // 64-column boxes that land 8 KB apart (the descriptors' leading byte offset)
+                                for (int h = 0; h < TC_BM / 64; ++h)
+                                    tma_load_2d(sa + h * 8192, &tmA16, a_part * P.kp_a + m0 + h * 64, k64 * 64, full + stage);
+                                for (int h = 0; h < BN / 64; ++h)
+                                    tma_load_2d(sa + TC_A_BYTES + h * 8192, &tmB16, b_part * P.kp_b + n0 + h * 64, k64 * 64, full + stage);
+                            } else if (P.blocked) {
                                 // K-blocked transposed operands (tgp_split_mixed_t): a tile is one contiguous block
                                 const int nblk = Kp / 64;
                                 const long RA = ((long)g.M + 255) / 256 * 256, RB = ((long)g.Ncols + 255) / 256 * 256;
@@ -433,6 +443,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     const uint64_t adesc = make_sw128_desc(sa), bdesc = make_sw128_desc(sa + TC_A_BYTES);
                     const uint32_t id = u3 == 0 ? idesc_h : idesc16;
                     if (++u3 == 3) u3 = 0;
+                    if (g.mixed && P.blocked == 2) {
+                        // MN-major A and B (instruction-descriptor bits 15 / 16); 64 contraction rows per stage = 4 x K16,
+                        // each K16 step = two 8-row swizzle atoms = 2048 B further
+                        const uint64_t ad = make_sw128_mn_desc(sa, 8192), bd = make_sw128_mn_desc(sa + TC_A_BYTES, 8192);
+                        if (tc_elect_one()) {
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                umma_bf16(d_tmem, ad + (uint64_t)(128 * k), bd + (uint64_t)(128 * k), id | (1u << 15) | (1u << 16), k ? 1u : accum);
+                            umma_commit(empty + stage);
+                        }
+                        __syncwarp();
+                        accum = 1;
+                        if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+                        continue;
+                    }
                     if (tc_elect_one()) {
                         if (g.mixed) {
                             // 16-bit stage: 64 columns of K, 16 per instruction = the same +32 B descriptor step
@@ -795,7 +820,7 @@ extern "C" int tgp_split_tf32(const float* src, long rows, int K, long ld, int s
 }
 
 template <int BN>
-static int launch_tc(const tgp_gemm_args* a, cudaStream_t st, int ksplit = 1, int blocked = 0) {
+static int launch_tc(const tgp_gemm_args* a, cudaStream_t st, int ksplit = 1, int blocked = 0, int kp_a = 0, int kp_b = 0) {
     const int Kp = a->mixed ? tgp_mixed_kpad(a->K) : tgp_split_kpad(a->K);
     CUtensorMap tmA, tmB, tmA16, tmB16;
     int rc = 0;
@@ -812,7 +837,13 @@ static int launch_tc(const tgp_gemm_args* a, cudaStream_t st, int ksplit = 1, in
         if (rc) return rc;
     }
     if (a->mixed) {
-        if (blocked) {
+        if (blocked == 2) {
+            // row-major mixed operands (rows = contraction index a->K, 4*kp 16-bit slots per row), boxes of 64 rows x 64 slots
+            rc = tgp_make_map_bf16(&tmA16, a->A_split, a->K, kp_a, 64);
+            if (rc) return rc;
+            rc = tgp_make_map_bf16(&tmB16, a->B_split, a->K, kp_b, 64);
+            if (rc) return rc;
+        } else if (blocked) {
             const long nblk = Kp / 64;
             rc = tgp_make_map_bf16_blocked(&tmA16, a->A_split, 3 * nblk * (((long)a->M + 255) / 256 * 256), TC_BM);
             if (rc) return rc;
@@ -836,6 +867,8 @@ static int launch_tc(const tgp_gemm_args* a, cudaStream_t st, int ksplit = 1, in
     GemmDev P;
     P.a = *a;
     P.blocked = blocked;
+    P.kp_a = kp_a;
+    P.kp_b = kp_b;
     const int num_m_tiles = (int)((a->M + TC_BM - 1) / TC_BM);
     const int num_n_tiles = (a->Ncols + BN - 1) / BN;
     const int tiles_mn = num_m_tiles * num_n_tiles;
@@ -947,6 +980,45 @@ extern "C" int tgp_gemm_tn_tc(const float* At_split, const float* Bt_split, long
     if (bn == 256) rc = launch_tc<256>(&a, st, ks, 1);
     else if (bn == 128) rc = launch_tc<128>(&a, st, ks, 1);
     else rc = launch_tc<64>(&a, st, ks, 1);
+    if (rc || ks == 1) return rc;
+    const long total = (long)K1 * K2;
+    long nb = (total + 255) / 256;
+    if (nb > TGP_NUM_SMS * 8) nb = TGP_NUM_SMS * 8;
+    tc_splitk_reduce_kernel<<<(unsigned)nb, 256, 0, st>>>(static_cast<const float*>(workspace), ks, K1, K2, out, ldo);
+    return check_launch("tc_splitk_reduce_kernel");
+}
+
+// The same contraction on ROW-MAJOR mixed operands (tgp_split_mixed / epilogue mode 4 / tgp_affine_act(mixed)), read in place:
+// A (M, K1) and B (M, K2) both have the contraction index M as their slow dimension, i.e. they are MN-major operands of the
+// MMA (tcgen05 instruction-descriptor bits a_major / b_major).  No transposing split: the forward pass's operand of x and the
+// backward pass's operand of dY (which the dX contraction needs anyway) are all this launch reads.
+extern "C" int tgp_gemm_tn_tc_rm(const float* A_mixed, int kp_a, const float* B_mixed, int kp_b, long M, int K1, int K2,
+                                 float* out, long ldo, void* workspace, size_t workspace_bytes, tgp_stream_t stream) {
+    if (!A_mixed || !B_mixed || !out || !workspace) return fail(TGP_EINVAL, "tgp_gemm_tn_tc_rm: null pointer");
+    if (M <= 0 || M > 0x7fffffffL - 64 || K1 <= 0 || K2 <= 0) return fail(TGP_EINVAL, "tgp_gemm_tn_tc_rm: bad sizes");
+    if (kp_a < K1 || kp_b < K2 || kp_a % 64 || kp_b % 64) return fail(TGP_EINVAL, "tgp_gemm_tn_tc_rm: kp must be a multiple of 64 and >= the operand width");
+    if ((uintptr_t)A_mixed % 16 || (uintptr_t)B_mixed % 16) return fail(TGP_EINVAL, "tgp_gemm_tn_tc_rm: operands must be 16-byte aligned");
+    if (workspace_bytes < tgp_gemm_tn_tc_workspace(M, K1, K2)) return fail(TGP_ENOSPACE, "tgp_gemm_tn_tc_rm: workspace too small");
+    int bn;
+    const int ks = tn_plan(M, K1, K2, &bn, 1);
+    tgp_gemm_args a = {};
+    a.mixed = 1;
+    a.A_split = A_mixed;
+    a.B_split = B_mixed;
+    a.M = K1;
+    a.K = (int)M;
+    a.Ncols = K2;
+    a.nseg = 1;
+    a.seg[0].col_begin = 0;
+    a.seg[0].col_end = K2;
+    a.seg[0].mode = 0;
+    a.seg[0].ld = ks > 1 ? K2 : ldo;
+    a.seg[0].ptr = ks > 1 ? static_cast<float*>(workspace) : out;
+    cudaStream_t st = as_stream(stream);
+    int rc;
+    if (bn == 256) rc = launch_tc<256>(&a, st, ks, 2, kp_a, kp_b);
+    else if (bn == 128) rc = launch_tc<128>(&a, st, ks, 2, kp_a, kp_b);
+    else rc = launch_tc<64>(&a, st, ks, 2, kp_a, kp_b);
     if (rc || ks == 1) return rc;
     const long total = (long)K1 * K2;
     long nb = (total + 255) / 256;

@@ -76,6 +76,20 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
     return d;
 }
 
+// MN-major, 128B-swizzled operand tile (the contraction index is the SLOW one: a row-major (rows = contraction, cols = M or N)
+// matrix read in place): rows of 128 B = 64 consecutive 16-bit M/N elements for ONE contraction index; 8 consecutive
+// contraction indices form a 1024-byte swizzle atom; the next group of 8 lies SBO = 1024 B further, the next 64 M/N
+// elements LBO bytes further (canonical layout ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units).
+__device__ __forceinline__ uint64_t make_sw128_mn_desc(uint32_t smem_addr, uint32_t lbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;   // leading byte offset: between 64-element blocks along M/N
+    d |= (uint64_t)(1024 >> 4) << 32;                   // stride byte offset: between groups of 8 contraction indices
+    d |= (uint64_t)1 << 46;                             // version
+    d |= (uint64_t)2 << 61;                             // SWIZZLE_128B
+    return d;
+}
+
 __device__ __forceinline__ float lds_f32(uint32_t addr) {
     float v;
     asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));

@@ -33,7 +33,7 @@ class _ConvBNActFn(torch.autograd.Function):
         scale = gamma * invstd
         shift = beta - mean * scale
         y, y_split = ops.affine_act(z, scale, shift, slope, want_raw=True, want_split=want_split, mixed=True)
-        ctx.save_for_backward(x2d, w2, z, y, mean, invstd, gamma, scale, shift)
+        ctx.save_for_backward(x2d, w2, z, y, mean, invstd, gamma, scale, shift, xs)     # xs: the weight gradient reads it in place
         ctx.slope = slope
         ctx.has_bias = bias is not None
         ctx.wshape = weight.shape
@@ -44,10 +44,12 @@ class _ConvBNActFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dy, _ds, _dm, _dv):
-        x2d, w2, z, y, mean, invstd, gamma, scale, shift = ctx.saved_tensors
-        dz, dbeta, dgamma, dzm = ops.bn_bwd(dy, y, z, mean, invstd, gamma, ctx.slope, want_mixed=ctx.needs_input_grad[0],
+        x2d, w2, z, y, mean, invstd, gamma, scale, shift, xs = ctx.saved_tensors
+        # dz also as a mixed operand: the dX contraction AND the weight gradient (row-major operands read in place as
+        # MN-major MMA operands, tgp_gemm_tn_tc_rm) consume it -- no transposing split of dz or x
+        dz, dbeta, dgamma, dzm = ops.bn_bwd(dy, y, z, mean, invstd, gamma, ctx.slope, want_mixed=True,
                                              scale=scale, shift=shift)
-        dw = ops.gemm_tn(dz, x2d, mixed=True).view(ctx.wshape)
+        dw = ops.gemm_tn(dz, x2d, mixed=True, A_mixed=dzm, B_mixed=xs).view(ctx.wshape)
         db = ops.colsum(dz).view(-1) if ctx.has_bias else None
         dx = None
         if ctx.needs_input_grad[0]:

@@ -533,10 +533,14 @@ def split_tf32_t(x2d):
     return dst
 
 
-def gemm_tn(A2d, B2d, out=None, tc=None, mixed=False):
+GEMM_TN_ROWMAJOR = True     # mixed weight gradients read the row-major operands in place (MN-major MMA operands)
+
+
+def gemm_tn(A2d, B2d, out=None, tc=None, mixed=False, A_mixed=None, B_mixed=None):
     """A^T B: (M,K1),(M,K2) -> (K1,K2), the weight-gradient contraction.  Large shapes run on the tensor cores
-    (transposed splits + split-K; 3xTF32, or the heads' mixed fp16+bf16 operands when mixed), small / skinny ones on the
-    exact fp32 FMA kernel."""
+    (split-K over M; 3xTF32 on transposed splits, or -- mixed -- fp16+bf16 operands read IN PLACE from the row-major mixed
+    splits, which the forward / dX contractions have usually produced already: pass them as A_mixed / B_mixed), small /
+    skinny ones on the exact fp32 FMA kernel."""
     M, K1 = A2d.shape
     K2 = B2d.shape[1]
     assert B2d.shape[0] == M and A2d.stride(1) == 1 and B2d.stride(1) == 1
@@ -546,7 +550,16 @@ def gemm_tn(A2d, B2d, out=None, tc=None, mixed=False):
     lib = _lib.load()
     if tc is None:
         tc = TC_ENABLED and M >= 512 and K1 >= 16 and K2 >= 16
-    if tc:
+    if tc and mixed and GEMM_TN_ROWMAJOR:
+        Am = A_mixed if (A_mixed is not None and A_mixed.numel()) else split_mixed(A2d)
+        same = B2d.data_ptr() == A2d.data_ptr() and B2d.shape == A2d.shape and B2d.stride() == A2d.stride()
+        Bm = B_mixed if (B_mixed is not None and B_mixed.numel()) else (Am if same else split_mixed(B2d))
+        kpa, kpb = Am.shape[1] // 2, Bm.shape[1] // 2          # a mixed row is 2*Kp fp32 slots = 4*Kp 16-bit slots
+        assert Am.shape[0] == M and Bm.shape[0] == M and kpa >= K1 and kpb >= K2
+        nb = lib.tgp_gemm_tn_tc_workspace(M, K1, K2)
+        ws = _ws(nb, A2d.device)
+        _run("gemm_tn_tc", lib.tgp_gemm_tn_tc_rm, _p(Am), kpa, _p(Bm), kpb, M, K1, K2, _p(out), out.stride(0), _p(ws), nb, _stream())
+    elif tc:
         spl = split_mixed_t if mixed else split_tf32_t
         At = spl(A2d)
         Bt = At if (B2d.data_ptr() == A2d.data_ptr() and B2d.shape == A2d.shape and B2d.stride() == A2d.stride()) \
