@@ -167,17 +167,19 @@ __device__ __forceinline__ void vstore(const VDst& d, int row, float4 v) {
 // projection / head GEMMs that only add a bias, optionally apply the BatchNorm affine + activation and write ONE
 // destination per column -- ~4x fewer instructions per chunk than the general path, which matters because only 8 epilogue
 // warps are resident and the K = 128..256 encoder GEMMs are bound by exactly this code.
-template <bool LEAN>
-__device__ __forceinline__ void epi_chunk_vec(const tgp_gemm_args& g, uint32_t stg_addr, const uint32_t (&r)[32], int lane,
-                                              long row0, int nrows, int colbase, long grp0, int gb_switch, long zoff, int dbg = 0) {
-    // stage: thread = row writes its 32 columns as 8 float4, slot j ^ (row & 7) of its 128-byte line
+// stage one chunk: thread = row writes its 32 columns as 8 float4, slot j ^ (row & 7) of its 128-byte line
+__device__ __forceinline__ void epi_stage_vec(uint32_t stg_addr, const uint32_t (&r)[32], int lane) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         const uint32_t ad = stg_addr + (uint32_t)(lane * 128 + ((j ^ (lane & 7)) << 4));
         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(ad), "r"(r[4 * j]), "r"(r[4 * j + 1]),
                      "r"(r[4 * j + 2]), "r"(r[4 * j + 3]) : "memory");
     }
-    __syncwarp();
+}
+
+template <bool LEAN>
+__device__ __forceinline__ void epi_chunk_vec(const tgp_gemm_args& g, uint32_t stg_addr, int lane,
+                                              long row0, int nrows, int colbase, long grp0, int gb_switch, long zoff, int dbg = 0) {
     const int c4i = lane & 7, rsub = lane >> 3;
     const int col = colbase + c4i * 4;
     const bool live = col < g.Ncols && nrows > 0;     // row blocks past M must not touch group_bias / residual rows
@@ -307,6 +309,93 @@ __device__ __forceinline__ void epi_chunk_vec(const tgp_gemm_args& g, uint32_t s
         }
     }
     __syncwarp();
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// FAST lean chunk (vec_ok == 3: lean + 16-byte aligned parameter vectors; all 32 rows live; the chunk's 32 columns lie in
+// ONE segment of kind raw / slab / split / mixed).  The 8 epilogue warps are latency-bound, not issue-bound (halving them
+// takes 90 -> 141 us on the level-0 projection), so what counts is the length of the per-chunk dependency chain: the
+// destination of a lane is computed ONCE per tile (before the accumulator wait) and fetched by shuffles, parameters come as
+// 128-bit loads, shared-memory addresses are loop invariants, all eight LDS.128 are issued before the first store, and the
+// kind / activation switches are compile-time.
+struct FastDst {
+    float* p;      // (row0, this lane's first column)
+    int rs;        // row stride in floats
+    int kind;      // 0 none, 1 raw / slab, 2 split, 3 column max (-> general lean path), 4 mixed operand
+    int lo;        // split: offset of the residual half; mixed: Kp
+    int rel;       // column inside the segment
+};
+
+__device__ __forceinline__ FastDst fast_entry(const tgp_gemm_args& g, int col, long row0, long zoff) {
+    FastDst d = {nullptr, 0, 0, 0, 0};
+    if (col >= g.Ncols) return d;
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+        if (s < g.nseg && col >= g.seg[s].col_begin && col < g.seg[s].col_end) {
+            const int rel = col - g.seg[s].col_begin;
+            d.rel = rel;
+            if (g.seg[s].mode == 3) {
+                d.kind = 3;
+            } else if (g.seg[s].mode == 1) {
+                const int w = g.seg[s].slab_width;
+                const int cg = rel / w, rr = rel - cg * w;
+                d.kind = 1;
+                d.rs = w;
+                d.p = g.seg[s].ptr + ((long)cg * g.M + row0) * w + rr;
+            } else {
+                d.kind = g.seg[s].mode == 2 ? 2 : (g.seg[s].mode == 4 ? 4 : 1);
+                d.rs = (int)g.seg[s].ld;
+                d.p = g.seg[s].ptr + zoff + row0 * g.seg[s].ld + rel;
+                d.lo = g.seg[s].slab_width;
+            }
+        }
+    }
+    return d;
+}
+
+__device__ __forceinline__ float4 ldg128(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+template <bool ACT, int KIND>
+__device__ __forceinline__ void epi_fast_rows(uint32_t ld_even, uint32_t ld_odd, float* p_r, int rs, int lo, int rel,
+                                              float4 bias, float4 sc, float4 sh, float4 sl) {
+    float4 a[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+        const uint32_t ad = ((u & 1) ? ld_odd : ld_even) + (uint32_t)(u * 512);
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a[u].x), "=f"(a[u].y), "=f"(a[u].z), "=f"(a[u].w) : "r"(ad));
+    }
+    const long step = 4L * rs;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+        float4 v = f4add(a[u], bias);
+        if (ACT) {
+            v.x = act1(v.x, sc.x, sh.x, sl.x); v.y = act1(v.y, sc.y, sh.y, sl.y);
+            v.z = act1(v.z, sc.z, sh.z, sl.z); v.w = act1(v.w, sc.w, sh.w, sl.w);
+        }
+        float* q = p_r + u * step;
+        if (KIND == 1) {
+            *reinterpret_cast<float4*>(q) = v;
+        } else if (KIND == 2) {
+            float4 hi, lw;
+            uint32_t hb;
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v.x)); hi.x = __uint_as_float(hb); lw.x = v.x - hi.x;
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v.y)); hi.y = __uint_as_float(hb); lw.y = v.y - hi.y;
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v.z)); hi.z = __uint_as_float(hb); lw.z = v.z - hi.z;
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v.w)); hi.w = __uint_as_float(hb); lw.w = v.w - hi.w;
+            *reinterpret_cast<float4*>(q) = hi;
+            *reinterpret_cast<float4*>(q + lo) = lw;
+        } else {
+            mixed_store4_cs(reinterpret_cast<uint16_t*>(q - rel), lo, rel, v);
+        }
+    }
+}
+
+template <bool ACT>
+__device__ __forceinline__ void epi_fast_kind(int kind, uint32_t ld_even, uint32_t ld_odd, float* p_r, int rs, int lo, int rel,
+                                              float4 bias, float4 sc, float4 sh, float4 sl) {
+    if (kind == 1) epi_fast_rows<ACT, 1>(ld_even, ld_odd, p_r, rs, lo, rel, bias, sc, sh, sl);
+    else if (kind == 2) epi_fast_rows<ACT, 2>(ld_even, ld_odd, p_r, rs, lo, rel, bias, sc, sh, sl);
+    else epi_fast_rows<ACT, 4>(ld_even, ld_odd, p_r, rs, lo, rel, bias, sc, sh, sl);
 }
 
 template <int BN>
@@ -485,15 +574,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int quarter = warp & 3;
         const int half = (warp - 2) >> 2;            // which interleaved set of 32-column chunks
         float* stg = stage_all + (warp - 2) * (32 * 33);
+        const uint32_t stg_addr = s_u32(stg);
+        const int c4i = lane & 7, rsub = lane >> 3;
+        // loop-invariant staging read addresses of the fast path: row = 4 u + rsub, slot c4i ^ (row & 7)
+        const uint32_t ld_even = stg_addr + (uint32_t)(rsub * 128 + ((c4i ^ rsub) << 4));
+        const uint32_t ld_odd = stg_addr + (uint32_t)(rsub * 128 + ((c4i ^ (4 + rsub)) << 4));
+        const bool gb_slow = g.group_bias && g.rows_per_group > 0 && g.rows_per_group < 32;
+        const int path = (dbg & 1) ? 0 : (vec_ok >= 2 ? 2 : ((vec_ok && !gb_slow) ? 1 : 0));   // 2 lean, 1 vector, 0 scalar
+        const bool fast_ok = vec_ok == 3 && !(dbg & 9);
+        const bool has_act = g.scale != nullptr || g.neg_slope != nullptr || g.relu != 0;
         int it = 0;
         for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
             const int z = t / tiles_mn, tt = t - z * tiles_mn;
             const int m0 = (tt / num_n_tiles) * TC_BM, n0 = (tt % num_n_tiles) * BN;
-            tc_mbar_wait(tmem_full + acc, acc_phase);
-            tc_fence_after();
-            // TMEM gives each thread one ROW (32 consecutive columns per load); a padded shared-memory
+            // TMEM gives each thread one ROW (32 consecutive columns per load); a shared-memory
             // transpose turns that into lane = COLUMN so that every global access of the epilogue
             // (residual loads, output stores) is a full, coalesced 128-byte row segment.
             const long row0 = (long)m0 + quarter * 32;
@@ -501,97 +597,137 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             // per-cloud bias: at most one group boundary inside these 32 rows when rows_per_group >= 32
             long grp0 = 0;
             int gb_switch = 64;
-            bool gb_slow = false;
             if (g.group_bias || g.rows_per_group > 0) {
                 grp0 = row0 / g.rows_per_group;
                 const long nxt = (grp0 + 1) * g.rows_per_group - row0;
                 gb_switch = nxt < 64 ? (int)nxt : 64;
-                gb_slow = g.group_bias && g.rows_per_group < 32;
             }
-            const uint32_t stg_addr = s_u32(stg);
+            // fast path: lane L owns the destination of (chunk L / 8 of this warp, column quad L % 8), computed while the
+            // mainloop of this tile is still running
+            FastDst fd = {nullptr, 0, 0, 0, 0};
+            if (fast_ok) {
+                const int fc0 = half * 32 + 64 * (lane >> 3);
+                if (fc0 < BN) fd = fast_entry(g, n0 + fc0 + c4i * 4, row0, z * zstride);
+            }
+            tc_mbar_wait(tmem_full + acc, acc_phase);
+            tc_fence_after();
+            const uint32_t taddr0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN);
+            uint32_t r[32];
+            TMEM_LD_32x32(taddr0 + (uint32_t)(half * 32), r);
+            int ci = 0;
 #pragma unroll 1
-            for (int c0 = half * 32; c0 < BN; c0 += 64) {
-                uint32_t r[32];
-                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + c0);
-                TMEM_LD_32x32(taddr, r);
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                __syncwarp();
-                if (vec_ok == 2 && !(dbg & 1)) {
-                    epi_chunk_vec<true>(g, stg_addr, r, lane, row0, nrows, n0 + c0, grp0, gb_switch, z * zstride, dbg);
-                    continue;
-                }
-                if (vec_ok && !gb_slow && !(dbg & 1)) {
-                    epi_chunk_vec<false>(g, stg_addr, r, lane, row0, nrows, n0 + c0, grp0, gb_switch, z * zstride);
-                    continue;
-                }
+            for (int c0 = half * 32; c0 < BN; c0 += 64, ++ci) {
+                TMEM_WAIT_LD(r);
+                if (path) {
+                    epi_stage_vec(stg_addr, r, lane);
+                } else {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) sts_f32(stg_addr + (uint32_t)((lane * 33 + j) * 4), __uint_as_float(r[j]));
+                    for (int j = 0; j < 32; ++j) sts_f32(stg_addr + (uint32_t)((lane * 33 + j) * 4), __uint_as_float(r[j]));
+                }
                 __syncwarp();
-                const int col = n0 + c0 + lane;
-                const bool live = col < g.Ncols && nrows > 0 && !(dbg & 1);
-                // per-column constants of this lane
-                float bias = 0.f, sc = 1.f, sh = 0.f, slope = g.relu ? 0.f : 1.f, gbv0 = 0.f, gbv1 = 0.f;
-                EpiDst d0 = {nullptr, 0, 0, 0, 0}, d1 = {nullptr, 0, 0, 0, 0};
-                const float* r1p = nullptr;
-                const float* r2p = nullptr;
-                if (live) {
-                    if (g.bias) bias = __ldg(g.bias + col);
-                    if (g.scale) { sc = __ldg(g.scale + col); sh = __ldg(g.shift + col); }
-                    if (g.neg_slope) slope = __ldg(g.neg_slope + col);
-#pragma unroll
-                    for (int s = 0; s < 4; ++s) {
-                        if (s < g.nseg && col >= g.seg[s].col_begin && col < g.seg[s].col_end) {
-                            const int rel = col - g.seg[s].col_begin;
-                            EpiDst d;
-                            d.mix = 0; d.rel = 0;
-                            if (g.seg[s].mode == 3) {
-                                // per-group column max: rows_per_group >= 32, so a 32-row block touches <= 2 groups
-                                d.rs = g.seg[s].col_end - g.seg[s].col_begin;
-                                d.lo = -1;
-                                d.p = g.seg[s].ptr + grp0 * d.rs + rel;
-                            } else if (g.seg[s].mode == 1) {
-                                const int w = g.seg[s].slab_width;
-                                const int cg = rel / w, rr = rel - cg * w;
-                                d.rs = w; d.lo = 0;
-                                d.p = g.seg[s].ptr + ((long)cg * g.M + row0) * w + rr;
-                            } else {
-                                d.rs = g.seg[s].ld;
-                                d.p = g.seg[s].ptr + z * zstride + row0 * d.rs + rel;
-                                d.lo = g.seg[s].mode == 2 ? g.seg[s].slab_width : 0;
-                                if (g.seg[s].mode == 4) { d.mix = g.seg[s].slab_width; d.rel = rel; }
+                // the chunk is in shared memory: fetch the next one while this one is processed, or hand the accumulator
+                // stage back to the MMA warp right away
+                if (c0 + 64 < BN) {
+                    TMEM_LD_32x32(taddr0 + (uint32_t)(c0 + 64), r);
+                } else {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) tc_mbar_arrive(tmem_empty + acc);
+                }
+                bool done = false;
+                if (fast_ok) {
+                    const int src = ci * 8 + c4i;
+                    const unsigned long long pp = __shfl_sync(0xffffffffu, (unsigned long long)(uintptr_t)fd.p, src);
+                    const int rs = __shfl_sync(0xffffffffu, fd.rs, src), kind = __shfl_sync(0xffffffffu, fd.kind, src);
+                    const int lo = __shfl_sync(0xffffffffu, fd.lo, src), rel = __shfl_sync(0xffffffffu, fd.rel, src);
+                    const int k0 = __shfl_sync(0xffffffffu, kind, 0);
+                    if (nrows == 32 && (k0 == 1 || k0 == 2 || k0 == 4) && __all_sync(0xffffffffu, kind == k0)) {
+                        const int col = n0 + c0 + c4i * 4;
+                        float* p_r = reinterpret_cast<float*>((uintptr_t)pp) + (long)rsub * rs;
+                        const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                        const float4 bias = g.bias ? ldg128(g.bias + col) : zero4;
+                        if (has_act) {
+                            const float s0 = g.relu ? 0.f : 1.f;
+                            const float4 sc = g.scale ? ldg128(g.scale + col) : make_float4(1.f, 1.f, 1.f, 1.f);
+                            const float4 sh = g.scale ? ldg128(g.shift + col) : zero4;
+                            const float4 sl = g.neg_slope ? ldg128(g.neg_slope + col) : make_float4(s0, s0, s0, s0);
+                            epi_fast_kind<true>(k0, ld_even, ld_odd, p_r, rs, lo, rel, bias, sc, sh, sl);
+                        } else {
+                            epi_fast_kind<false>(k0, ld_even, ld_odd, p_r, rs, lo, rel, bias, zero4, zero4, zero4);
+                        }
+                        done = true;
+                    }
+                }
+                if (done) {
+                } else if (path == 2) {
+                    epi_chunk_vec<true>(g, stg_addr, lane, row0, nrows, n0 + c0, grp0, gb_switch, z * zstride, dbg);
+                } else if (path == 1) {
+                    epi_chunk_vec<false>(g, stg_addr, lane, row0, nrows, n0 + c0, grp0, gb_switch, z * zstride);
+                } else {
+                    const int col = n0 + c0 + lane;
+                    const bool live = col < g.Ncols && nrows > 0 && !(dbg & 1);
+                    // per-column constants of this lane
+                    float bias = 0.f, sc = 1.f, sh = 0.f, slope = g.relu ? 0.f : 1.f, gbv0 = 0.f, gbv1 = 0.f;
+                    EpiDst d0 = {nullptr, 0, 0, 0, 0}, d1 = {nullptr, 0, 0, 0, 0};
+                    const float* r1p = nullptr;
+                    const float* r2p = nullptr;
+                    if (live) {
+                        if (g.bias) bias = __ldg(g.bias + col);
+                        if (g.scale) { sc = __ldg(g.scale + col); sh = __ldg(g.shift + col); }
+                        if (g.neg_slope) slope = __ldg(g.neg_slope + col);
+    #pragma unroll
+                        for (int s = 0; s < 4; ++s) {
+                            if (s < g.nseg && col >= g.seg[s].col_begin && col < g.seg[s].col_end) {
+                                const int rel = col - g.seg[s].col_begin;
+                                EpiDst d;
+                                d.mix = 0; d.rel = 0;
+                                if (g.seg[s].mode == 3) {
+                                    // per-group column max: rows_per_group >= 32, so a 32-row block touches <= 2 groups
+                                    d.rs = g.seg[s].col_end - g.seg[s].col_begin;
+                                    d.lo = -1;
+                                    d.p = g.seg[s].ptr + grp0 * d.rs + rel;
+                                } else if (g.seg[s].mode == 1) {
+                                    const int w = g.seg[s].slab_width;
+                                    const int cg = rel / w, rr = rel - cg * w;
+                                    d.rs = w; d.lo = 0;
+                                    d.p = g.seg[s].ptr + ((long)cg * g.M + row0) * w + rr;
+                                } else {
+                                    d.rs = g.seg[s].ld;
+                                    d.p = g.seg[s].ptr + z * zstride + row0 * d.rs + rel;
+                                    d.lo = g.seg[s].mode == 2 ? g.seg[s].slab_width : 0;
+                                    if (g.seg[s].mode == 4) { d.mix = g.seg[s].slab_width; d.rel = rel; }
+                                }
+                                if (!d0.p) d0 = d; else d1 = d;     // at most two destinations per column (raw + split)
                             }
-                            if (!d0.p) d0 = d; else d1 = d;     // at most two destinations per column (raw + split)
                         }
-                    }
-                    if (g.group_bias && !gb_slow) {
-                        gbv0 = __ldg(g.group_bias + grp0 * g.Ncols + col);
-                        if (gb_switch < nrows) gbv1 = __ldg(g.group_bias + (grp0 + 1) * g.Ncols + col);
-                    }
-                    if (g.res1) r1p = g.res1 + row0 * g.ld_res1 + col;
-                    if (g.res2) r2p = g.res2 + row0 * g.ld_res2 + col;
-                }
-                if (gb_slow) {
-                    // tiny groups (< 32 rows per cloud): fold the per-row group bias into the staged values first
-                    if (live)
-                        for (int rr = 0; rr < nrows; ++rr) {
-                            const uint32_t ad = stg_addr + (uint32_t)((rr * 33 + lane) * 4);
-                            sts_f32(ad, lds_f32(ad) + __ldg(g.group_bias + ((row0 + rr) / g.rows_per_group) * g.Ncols + col));
+                        if (g.group_bias && !gb_slow) {
+                            gbv0 = __ldg(g.group_bias + grp0 * g.Ncols + col);
+                            if (gb_switch < nrows) gbv1 = __ldg(g.group_bias + (grp0 + 1) * g.Ncols + col);
                         }
+                        if (g.res1) r1p = g.res1 + row0 * g.ld_res1 + col;
+                        if (g.res2) r2p = g.res2 + row0 * g.ld_res2 + col;
+                    }
+                    if (gb_slow) {
+                        // tiny groups (< 32 rows per cloud): fold the per-row group bias into the staged values first
+                        if (live)
+                            for (int rr = 0; rr < nrows; ++rr) {
+                                const uint32_t ad = stg_addr + (uint32_t)((rr * 33 + lane) * 4);
+                                sts_f32(ad, lds_f32(ad) + __ldg(g.group_bias + ((row0 + rr) / g.rows_per_group) * g.Ncols + col));
+                            }
+                    }
+                    const int nr = live ? nrows : 0;
+                    if (__any_sync(0xffffffffu, d0.p != nullptr && d0.lo < 0))
+                        epi_rows<true, true>(stg_addr, lane, nr, bias, sc, sh, slope, gbv0, gbv1, gb_switch, r1p, g.ld_res1, r2p,
+                                             g.ld_res2, d0, d1);
+                    else if (__any_sync(0xffffffffu, d1.p != nullptr))
+                        epi_rows<true, false>(stg_addr, lane, nr, bias, sc, sh, slope, gbv0, gbv1, gb_switch, r1p, g.ld_res1, r2p,
+                                       g.ld_res2, d0, d1);
+                    else
+                        epi_rows<false, false>(stg_addr, lane, nr, bias, sc, sh, slope, gbv0, gbv1, gb_switch, r1p, g.ld_res1, r2p,
+                                        g.ld_res2, d0, d1);
                 }
-                const int nr = live ? nrows : 0;
-                if (__any_sync(0xffffffffu, d0.p != nullptr && d0.lo < 0))
-                    epi_rows<true, true>(stg_addr, lane, nr, bias, sc, sh, slope, gbv0, gbv1, gb_switch, r1p, g.ld_res1, r2p,
-                                         g.ld_res2, d0, d1);
-                else if (__any_sync(0xffffffffu, d1.p != nullptr))
-                    epi_rows<true, false>(stg_addr, lane, nr, bias, sc, sh, slope, gbv0, gbv1, gb_switch, r1p, g.ld_res1, r2p,
-                                   g.ld_res2, d0, d1);
-                else
-                    epi_rows<false, false>(stg_addr, lane, nr, bias, sc, sh, slope, gbv0, gbv1, gb_switch, r1p, g.ld_res1, r2p,
-                                    g.ld_res2, d0, d1);
+                __syncwarp();
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) tc_mbar_arrive(tmem_empty + acc);
         }
     }
     tc_fence_before();
@@ -904,7 +1040,16 @@ static int launch_tc(const tgp_gemm_args* a, cudaStream_t st, int ksplit = 1, in
                 if (a->seg[s].col_begin < a->seg[t].col_end && a->seg[t].col_begin < a->seg[s].col_end) lean = false;
         }
         { const char* e = getenv("TGP_TC_NO_LEAN"); if (e && e[0] == '1') lean = false; }
-        if (lean) vec_ok = 2;
+        if (lean) {
+            vec_ok = 2;
+            // fast lean path: the per-column parameter vectors are read with 128-bit loads
+            if ((!a->bias || al16(a->bias)) && (!a->scale || (al16(a->scale) && al16(a->shift))) && (!a->neg_slope || al16(a->neg_slope))) {
+                bool small = true;
+                for (int s = 0; s < a->nseg; ++s) small = small && a->seg[s].ld < (1L << 31);
+                const char* e = getenv("TGP_TC_NO_FAST");
+                if (small && !(e && e[0] == '1')) vec_ok = 3;
+            }
+        }
     }
     { const char* e = getenv("TGP_TC_SCALAR_EPI"); if (e && e[0] == '1') vec_ok = 0; }
     static int dbg = -1;
@@ -912,6 +1057,7 @@ static int launch_tc(const tgp_gemm_args* a, cudaStream_t st, int ksplit = 1, in
     gemm_tc_kernel<BN><<<grid, TC_THREADS, smem, st>>>(tmA, tmB, tmA16, tmB16, P, Kp, num_n_tiles, num_tiles, dbg, tiles_mn, kb_per, zstride, vec_ok);
     return check_launch("gemm_tc_kernel");
 }
+
 
 // tensor-core path: both operands pre-split ([hi | lo], tgp_split_tf32)
 int tgp_gemm_tc(const tgp_gemm_args* a, cudaStream_t st) {

@@ -112,6 +112,17 @@ __device__ __forceinline__ void sts_f32(uint32_t addr, float v) {
           "=r"(r[29]), "=r"(r[30]), "=r"(r[31])                                                             \
         : "r"(taddr))
 
+// wait for the outstanding tcgen05.ld of `r`: the registers are in-out operands, so no value read before the wait can be
+// used after it (the loads complete asynchronously; other work may be scheduled between the load and this wait)
+#define TMEM_WAIT_LD(r)                                                                                 \
+    asm volatile("tcgen05.wait::ld.sync.aligned;"                                                       \
+        : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),   \
+          "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]),          \
+          "+r"(r[15]), "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]),        \
+          "+r"(r[22]), "+r"(r[23]), "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]),        \
+          "+r"(r[29]), "+r"(r[30]), "+r"(r[31])                                                             \
+        :: "memory")
+
 #define TMEM_ST_32x32(taddr, r)                                                                         \
     asm volatile(                                                                                       \
         "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "                                                 \
