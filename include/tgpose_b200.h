@@ -197,6 +197,13 @@ typedef struct {
      * a multiple of 256, K a multiple of 64; B_split stacks the layers' (a_group_cols, K) weights.  0: plain contraction. */
     int a_kp;
     int a_group_cols;
+    /* GATHERED residuals (tensor-core path only): when res1_idx / res2_idx is non-NULL, output row m adds row
+     * res1_idx[m] / res2_idx[m] of res1 / res2 instead of row m.  A 1x1 convolution over a concatenation whose column blocks
+     * are nearest-neighbour upsamplings of coarser levels (FaceRecon.py:69-81 feeding PoseR.py:26, PoseTs.py:24,
+     * FaceRecon.py:100,133) is W.[x | up(y)] = W_x.x + up(W_y.y): the W_y.y products are computed once per COARSE point
+     * and gathered here, instead of once per fine point. */
+    const int32_t* res1_idx;
+    const int32_t* res2_idx;
 } tgp_gemm_args;
 
 /* feature_map @ weights + bias (gcn3d.py:170) and every 1x1 Conv1d on the path. */

@@ -632,6 +632,81 @@ def test_gemm_mixed_operands(ops, M, K, N):
     assert float((out2.double() - ref2).abs().max()) <= 1.6e-5 * float(ref2.abs().max())
 
 
+@pytest.mark.parametrize("M,K,N,npg,ncoarse", [(4112, 265, 512, 1028, 257), (1028, 128, 256, 257, 64), (300, 64, 128, 100, 7),
+                                                (2056, 320, 384, 1028, 257)])
+def test_gemm_gathered_residuals(ops, M, K, N, npg, ncoarse):
+    """tgp_gemm_args.res1_idx / res2_idx: output row m adds row idx[m] of the residual matrices before the affine / activation.
+    Checked against an fp64 product for every destination kind (raw, split, mixed, per-cloud column max) together with a
+    per-cloud bias, on shapes with full 32-row blocks (fast chunk) and ragged last blocks, for mixed and 3xTF32 operands."""
+    g = torch.Generator().manual_seed(M + K + N)
+    B = M // npg
+    A = torch.randn(M, K, generator=g).cuda()
+    W = (torch.randn(N, K, generator=g) * 0.05).cuda()
+    R1 = torch.randn(B * ncoarse, N + 8, generator=g).cuda()[:, 4:4 + N]      # row-strided views (ld = N + 8)
+    R2 = torch.randn(B * 5, N, generator=g).cuda()
+    i1 = (torch.randint(0, ncoarse, (B, npg), generator=g) + torch.arange(B).view(B, 1) * ncoarse).int().cuda().reshape(-1)
+    i2 = (torch.randint(0, 5, (B, npg), generator=g) + torch.arange(B).view(B, 1) * 5).int().cuda().reshape(-1)
+    gb = torch.randn(B, N, generator=g).cuda()
+    scale, shift = (torch.rand(N, generator=g) + 0.5).cuda(), torch.randn(N, generator=g).cuda()
+    slope = torch.full((N,), 0.2).cuda()
+    pre = A.double() @ W.double().t() + R1.double()[i1.long()] + R2.double()[i2.long()] + gb.double().repeat_interleave(npg, 0)
+    v = pre * scale.double() + shift.double()
+    ref = torch.where(v > 0, v, 0.2 * v)
+    tol = 1.6e-5 * float(pre.abs().max()) * float(scale.max())
+    h = N // 4
+    for mixed in (True, False):
+        a_split = ops.split_mixed(A) if mixed else ops.split_tf32(A)
+        w_split = ops.split_mixed(W) if mixed else ops.split_tf32(W)
+        raw = torch.empty(M, h, device="cuda")
+        spl = ops._split_buf(M, h, "cuda")
+        mix = ops.mixed_buf(M, h, "cuda")
+        mx = torch.full((B, h), -2 ** 31, dtype=torch.int32, device="cuda")
+        segs = [(0, h, raw, 0, 0), (h, 2 * h, spl, 2, ops.kpad(h)), (2 * h, 3 * h, mix, 4, ops.mixed_kpad(h)), (3 * h, N, mx, 3, 0)]
+        ops.gemm(None, W, True, segs, K=K, A_split=a_split, B_split=w_split, mixed=mixed, group_bias=gb, rows_per_group=npg,
+                 res1=R1, res2=R2, res1_idx=i1, res2_idx=i2, scale=scale, shift=shift, neg_slope=slope)
+        assert float((raw.double() - ref[:, :h]).abs().max()) <= tol
+        got_spl = spl[:, :h].double() + spl[:, ops.kpad(h):ops.kpad(h) + h].double()
+        assert float((got_spl - ref[:, h:2 * h]).abs().max()) <= tol
+        # the mixed destination: fp16 slot + residual slot reproduce the value to ~2^-19
+        m16 = mix.view(torch.int16)
+        kp = ops.mixed_kpad(h)
+        hi = m16[:, :h].view(torch.float16).double()
+        lo = m16[:, 2 * kp:2 * kp + h].view(torch.bfloat16).double()
+        assert float((hi + lo - ref[:, 2 * h:3 * h]).abs().max()) <= tol + 4e-6 * float(ref.abs().max())
+        got_mx = ops.decode_max(mx).double()
+        assert float((got_mx - ref[:, 3 * h:].view(B, npg, -1).amax(1)).abs().max()) <= tol
+    # the exact-fp32 kernel takes the same arguments
+    out = torch.empty(M, N, device="cuda")
+    ops.gemm(A, W, True, [(0, N, out, 0, 0)], group_bias=gb, rows_per_group=npg, res1=R1, res2=R2, res1_idx=i1, res2_idx=i2,
+             scale=scale, shift=shift, neg_slope=slope, tc=False)
+    assert float((out.double() - ref).abs().max()) <= tol
+
+
+def test_posenet_factored_heads_equal_unfactored():
+    """The heads' first layers with the upsampled channels contracted per coarse point (W.[x | up(y)] = W_x.x + up(W_y.y),
+    posenet.py) against the same layers over the materialised concatenation: same outputs to fp32 summation noise."""
+    from tgpose_b200.posenet import PoseNet9D
+    g = golden("posenet_1028")
+    torch.manual_seed(0)
+    net = PoseNet9D(train_outputs=True).cuda().eval()
+    pts, cat = cu(g["pts"]), cu(g["cat_id"])
+    outs = {}
+    with torch.no_grad():
+        for fac in (True, False):
+            net.factored_heads = fac
+            net.face_all.encoder._record = []
+            torch.manual_seed(7)
+            outs[fac] = {k: v.clone() for k, v in net(pts, cat).items()}
+            if fac:
+                net.face_all.encoder._inject = [t.clone() for t in net.face_all.encoder._record]   # same neighbourhoods in both runs
+    for k in outs[True]:
+        a, b = nump(outs[True][k]), nump(outs[False][k])
+        if k in ("feat", "feat_global"):
+            assert np.array_equal(a, b), k
+        else:
+            assert_close(a, b, rel=1e-4, floor=2e-6, what=f"factored heads: {k}")
+
+
 def test_gemm_mixed_operands_range(ops):
     """fp16(x) saturates instead of overflowing (the bf16 residual carries the remainder) and tiny values keep their relative
     accuracy through the residual: rows scaled by 1e5 / 1e-6 stay finite and accurate."""

@@ -33,9 +33,11 @@ def test_library_exports_every_declared_symbol():
 def test_gemm_args_struct_layout_matches_header():
     from tgpose_b200 import _lib
     # natural alignment of the C structs (LP64): tgp_out_seg 32 B, tgp_gemm_args 152 + 4*32 + 16 + (int mixed, a_kp,
-    # a_group_cols, padded to 16)
+    # a_group_cols, padded to 16) + the two gathered-residual index pointers
     assert ctypes.sizeof(_lib.OutSeg) == 32
-    assert ctypes.sizeof(_lib.GemmArgs) == 152 + 4 * 32 + 16 + 16
+    assert ctypes.sizeof(_lib.GemmArgs) == 152 + 4 * 32 + 16 + 16 + 16
+    assert _lib.GemmArgs.res1_idx.offset == 152 + 4 * 32 + 16 + 16
+    assert _lib.GemmArgs.res2_idx.offset == _lib.GemmArgs.res1_idx.offset + 8
     assert _lib.GemmArgs.seg.offset == 152
     assert _lib.GemmArgs.mixed.offset == 152 + 4 * 32 + 16
     assert _lib.GemmArgs.a_kp.offset == _lib.GemmArgs.mixed.offset + 4

@@ -33,7 +33,8 @@ class GemmArgs(ctypes.Structure):
                 ("res2", c_void_p), ("ld_res2", c_long),
                 ("scale", c_void_p), ("shift", c_void_p),
                 ("relu", c_int), ("neg_slope", c_void_p), ("nseg", c_int), ("seg", OutSeg * 4),
-                ("A_split", c_void_p), ("B_split", c_void_p), ("mixed", c_int), ("a_kp", c_int), ("a_group_cols", c_int)]
+                ("A_split", c_void_p), ("B_split", c_void_p), ("mixed", c_int), ("a_kp", c_int), ("a_group_cols", c_int),
+                ("res1_idx", c_void_p), ("res2_idx", c_void_p)]
 
 
 class RangerHyper(ctypes.Structure):

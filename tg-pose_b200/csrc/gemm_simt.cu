@@ -38,8 +38,8 @@ __device__ __forceinline__ float4 ld4_guard(const float* base, long row, long nr
 __device__ __forceinline__ void epilogue_store(const tgp_gemm_args& g, long row, int col, float v) {
     if (g.bias) v += __ldg(g.bias + col);
     if (g.group_bias) v += __ldg(g.group_bias + (row / g.rows_per_group) * g.Ncols + col);
-    if (g.res1) v += __ldg(g.res1 + row * g.ld_res1 + col);
-    if (g.res2) v += __ldg(g.res2 + row * g.ld_res2 + col);
+    if (g.res1) v += __ldg(g.res1 + (g.res1_idx ? (long)__ldg(g.res1_idx + row) : row) * g.ld_res1 + col);
+    if (g.res2) v += __ldg(g.res2 + (g.res2_idx ? (long)__ldg(g.res2_idx + row) : row) * g.ld_res2 + col);
     if (g.scale) v = fmaf(v, __ldg(g.scale + col), __ldg(g.shift + col));
     if (g.neg_slope) v = v > 0.f ? v : v * __ldg(g.neg_slope + col);
     else if (g.relu) v = fmaxf(v, 0.f);

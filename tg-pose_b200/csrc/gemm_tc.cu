@@ -179,7 +179,8 @@ __device__ __forceinline__ void epi_stage_vec(uint32_t stg_addr, const uint32_t 
 
 template <bool LEAN>
 __device__ __forceinline__ void epi_chunk_vec(const tgp_gemm_args& g, uint32_t stg_addr, int lane,
-                                              long row0, int nrows, int colbase, long grp0, int gb_switch, long zoff, int dbg = 0) {
+                                              long row0, int nrows, int colbase, long grp0, int gb_switch, long zoff, int dbg = 0,
+                                              int ri1 = 0, int ri2 = 0) {
     const int c4i = lane & 7, rsub = lane >> 3;
     const int col = colbase + c4i * 4;
     const bool live = col < g.Ncols && nrows > 0;     // row blocks past M must not touch group_bias / residual rows
@@ -224,8 +225,10 @@ __device__ __forceinline__ void epi_chunk_vec(const tgp_gemm_args& g, uint32_t s
                 gb0 = ldg4s(g.group_bias + grp0 * g.Ncols + col);
                 if (gb_switch < nrows) gb1 = ldg4s(g.group_bias + (grp0 + 1) * g.Ncols + col);
             }
-            if (g.res1) r1p = g.res1 + row0 * g.ld_res1 + col;
-            if (g.res2) r2p = g.res2 + row0 * g.ld_res2 + col;
+            // residual rows: lane L of the warp holds the residual row of output row row0 + L (ri1 / ri2: the row itself, or
+            // res*_idx[row] for GATHERED residuals)
+            if (g.res1) r1p = g.res1 + col;
+            if (g.res2) r2p = g.res2 + col;
         }
     }
     float4 mx0 = make_float4(-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F), mx1 = mx0;
@@ -265,9 +268,10 @@ __device__ __forceinline__ void epi_chunk_vec(const tgp_gemm_args& g, uint32_t s
             const int row = (half * 4 + u) * 4 + rsub;
             q1[u] = make_float4(0.f, 0.f, 0.f, 0.f);
             q2[u] = q1[u];
+            const int i1 = __shfl_sync(0xffffffffu, ri1, row), i2 = __shfl_sync(0xffffffffu, ri2, row);
             if (row < nrows) {
-                if (r1p) q1[u] = __ldg(reinterpret_cast<const float4*>(r1p + (long)row * g.ld_res1));
-                if (r2p) q2[u] = __ldg(reinterpret_cast<const float4*>(r2p + (long)row * g.ld_res2));
+                if (r1p) q1[u] = __ldg(reinterpret_cast<const float4*>(r1p + (long)i1 * g.ld_res1));
+                if (r2p) q2[u] = __ldg(reinterpret_cast<const float4*>(r2p + (long)i2 * g.ld_res2));
             }
         }
 #pragma unroll
@@ -326,7 +330,7 @@ struct FastDst {
     int rel;       // column inside the segment
 };
 
-__device__ __forceinline__ FastDst fast_entry(const tgp_gemm_args& g, int col, long row0, long zoff) {
+__device__ __forceinline__ FastDst fast_entry(const tgp_gemm_args& g, int col, long row0, long zoff, long grp0) {
     FastDst d = {nullptr, 0, 0, 0, 0};
     if (col >= g.Ncols) return d;
 #pragma unroll
@@ -335,7 +339,9 @@ __device__ __forceinline__ FastDst fast_entry(const tgp_gemm_args& g, int col, l
             const int rel = col - g.seg[s].col_begin;
             d.rel = rel;
             if (g.seg[s].mode == 3) {
-                d.kind = 3;
+                d.kind = 3;      // (the lean fast path leaves column maxima to the general lean chunk; the residual one uses p / rs)
+                d.rs = g.seg[s].col_end - g.seg[s].col_begin;
+                d.p = g.seg[s].ptr + grp0 * d.rs + rel;
             } else if (g.seg[s].mode == 1) {
                 const int w = g.seg[s].slab_width;
                 const int cg = rel / w, rr = rel - cg * w;
@@ -396,6 +402,87 @@ __device__ __forceinline__ void epi_fast_kind(int kind, uint32_t ld_even, uint32
     if (kind == 1) epi_fast_rows<ACT, 1>(ld_even, ld_odd, p_r, rs, lo, rel, bias, sc, sh, sl);
     else if (kind == 2) epi_fast_rows<ACT, 2>(ld_even, ld_odd, p_r, rs, lo, rel, bias, sc, sh, sl);
     else epi_fast_rows<ACT, 4>(ld_even, ld_odd, p_r, rs, lo, rel, bias, sc, sh, sl);
+}
+
+
+// FAST chunk WITH residuals / per-cloud bias (vec_ok == 4: one destination per column, 16-byte aligned parameter vectors, all 32
+// rows live): the ORL contractions (conv2(cat[f, g]) + f + f_STE, gcn3d.py:110-112,184-186: two residuals + the per-cloud term)
+// and the heads' first layers with GATHERED residuals (tgp_gemm_args.res1_idx).  Same structure as the lean fast chunk; the
+// residual rows of the 32 output rows sit one per lane (ri1 / ri2) and are fetched by shuffles; 4 rows (a 128-bit staging
+// read + two 128-bit residual loads each) are in flight before the first store.
+template <int KIND>
+__device__ __forceinline__ void epi_fast_res_rows(uint32_t ld_even, uint32_t ld_odd, float* p_r, int rs, int lo, int rel, int rsub,
+                                                  float4 bias, float4 sc, float4 sh, float4 sl, const float* r1c, long ld1, int ri1,
+                                                  const float* r2c, long ld2, int ri2, float4 gb0, float4 gb1, int gb_switch) {
+    float4 mx0 = make_float4(-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F), mx1 = mx0;
+    const long step = 4L * rs;
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        float4 a[4], q1[4], q2[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int uu = h * 4 + u;
+            const uint32_t ad = ((uu & 1) ? ld_odd : ld_even) + (uint32_t)(uu * 512);
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a[u].x), "=f"(a[u].y), "=f"(a[u].z), "=f"(a[u].w) : "r"(ad));
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int row = 4 * (h * 4 + u) + rsub;
+            const int i1 = __shfl_sync(0xffffffffu, ri1, row), i2 = __shfl_sync(0xffffffffu, ri2, row);
+            q1[u] = r1c ? ldg128(r1c + (long)i1 * ld1) : zero4;
+            q2[u] = r2c ? ldg128(r2c + (long)i2 * ld2) : zero4;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int uu = h * 4 + u, row = 4 * uu + rsub;
+            const bool second = row >= gb_switch;
+            float4 v = f4add(f4add(f4add(a[u], bias), f4add(q1[u], q2[u])), second ? gb1 : gb0);
+            v.x = act1(v.x, sc.x, sh.x, sl.x); v.y = act1(v.y, sc.y, sh.y, sl.y);
+            v.z = act1(v.z, sc.z, sh.z, sl.z); v.w = act1(v.w, sc.w, sh.w, sl.w);
+            float* q = p_r + uu * step;
+            if (KIND == 1) {
+                *reinterpret_cast<float4*>(q) = v;
+            } else if (KIND == 2) {
+                float4 hi, lw;
+                uint32_t hb;
+                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v.x)); hi.x = __uint_as_float(hb); lw.x = v.x - hi.x;
+                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v.y)); hi.y = __uint_as_float(hb); lw.y = v.y - hi.y;
+                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v.z)); hi.z = __uint_as_float(hb); lw.z = v.z - hi.z;
+                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v.w)); hi.w = __uint_as_float(hb); lw.w = v.w - hi.w;
+                *reinterpret_cast<float4*>(q) = hi;
+                *reinterpret_cast<float4*>(q + lo) = lw;
+            } else if (KIND == 4) {
+                mixed_store4_cs(reinterpret_cast<uint16_t*>(q - rel), lo, rel, v);
+            } else {
+                float4& m = second ? mx1 : mx0;
+                m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
+            }
+        }
+    }
+    if (KIND == 3) {
+        // per-cloud column max: combine the 4 row sub-groups (lane bits 3, 4), one atomicMax per column and cloud
+#pragma unroll
+        for (int o = 8; o <= 16; o <<= 1) {
+            mx0.x = fmaxf(mx0.x, __shfl_xor_sync(0xffffffffu, mx0.x, o)); mx0.y = fmaxf(mx0.y, __shfl_xor_sync(0xffffffffu, mx0.y, o));
+            mx0.z = fmaxf(mx0.z, __shfl_xor_sync(0xffffffffu, mx0.z, o)); mx0.w = fmaxf(mx0.w, __shfl_xor_sync(0xffffffffu, mx0.w, o));
+            mx1.x = fmaxf(mx1.x, __shfl_xor_sync(0xffffffffu, mx1.x, o)); mx1.y = fmaxf(mx1.y, __shfl_xor_sync(0xffffffffu, mx1.y, o));
+            mx1.z = fmaxf(mx1.z, __shfl_xor_sync(0xffffffffu, mx1.z, o)); mx1.w = fmaxf(mx1.w, __shfl_xor_sync(0xffffffffu, mx1.w, o));
+        }
+        if (rsub == 0) {
+            // p_r = cell of (first cloud of the block, this lane's first column) for rsub == 0; rs = cells per cloud
+            int* cell = reinterpret_cast<int*>(p_r);
+            if (gb_switch > 0) {
+                atomicMax(cell, enc_ordered(mx0.x)); atomicMax(cell + 1, enc_ordered(mx0.y));
+                atomicMax(cell + 2, enc_ordered(mx0.z)); atomicMax(cell + 3, enc_ordered(mx0.w));
+            }
+            if (gb_switch < 32) {
+                cell += rs;
+                atomicMax(cell, enc_ordered(mx1.x)); atomicMax(cell + 1, enc_ordered(mx1.y));
+                atomicMax(cell + 2, enc_ordered(mx1.z)); atomicMax(cell + 3, enc_ordered(mx1.w));
+            }
+        }
+    }
 }
 
 template <int BN>
@@ -580,8 +667,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint32_t ld_even = stg_addr + (uint32_t)(rsub * 128 + ((c4i ^ rsub) << 4));
         const uint32_t ld_odd = stg_addr + (uint32_t)(rsub * 128 + ((c4i ^ (4 + rsub)) << 4));
         const bool gb_slow = g.group_bias && g.rows_per_group > 0 && g.rows_per_group < 32;
-        const int path = (dbg & 1) ? 0 : (vec_ok >= 2 ? 2 : ((vec_ok && !gb_slow) ? 1 : 0));   // 2 lean, 1 vector, 0 scalar
-        const bool fast_ok = vec_ok == 3 && !(dbg & 9);
+        const int path = (dbg & 1) ? 0 : ((vec_ok == 2 || vec_ok == 3) ? 2 : ((vec_ok && !gb_slow) ? 1 : 0));   // 2 lean, 1 vector, 0 scalar
+        const bool fast_ok = (vec_ok == 3 || vec_ok == 4) && !(dbg & 9);
+        const bool fast_res = vec_ok == 4;            // residuals / per-cloud bias on the fast chunk
         const bool has_act = g.scale != nullptr || g.neg_slope != nullptr || g.relu != 0;
         int it = 0;
         for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
@@ -607,7 +695,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             FastDst fd = {nullptr, 0, 0, 0, 0};
             if (fast_ok) {
                 const int fc0 = half * 32 + 64 * (lane >> 3);
-                if (fc0 < BN) fd = fast_entry(g, n0 + fc0 + c4i * 4, row0, z * zstride);
+                if (fc0 < BN) fd = fast_entry(g, n0 + fc0 + c4i * 4, row0, z * zstride, grp0);
+            }
+            // residual row of output row row0 + lane (the row itself, or the gathered one)
+            int ri1 = 0, ri2 = 0;
+            if (row0 + lane < g.M) {
+                if (g.res1) ri1 = g.res1_idx ? __ldg(g.res1_idx + row0 + lane) : (int)(row0 + lane);
+                if (g.res2) ri2 = g.res2_idx ? __ldg(g.res2_idx + row0 + lane) : (int)(row0 + lane);
             }
             tc_mbar_wait(tmem_full + acc, acc_phase);
             tc_fence_after();
@@ -641,7 +735,33 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     const int rs = __shfl_sync(0xffffffffu, fd.rs, src), kind = __shfl_sync(0xffffffffu, fd.kind, src);
                     const int lo = __shfl_sync(0xffffffffu, fd.lo, src), rel = __shfl_sync(0xffffffffu, fd.rel, src);
                     const int k0 = __shfl_sync(0xffffffffu, kind, 0);
-                    if (nrows == 32 && (k0 == 1 || k0 == 2 || k0 == 4) && __all_sync(0xffffffffu, kind == k0)) {
+                    if (fast_res) {
+                        if (nrows == 32 && k0 >= 1 && k0 <= 4 && __all_sync(0xffffffffu, kind == k0)) {
+                            const int col = n0 + c0 + c4i * 4;
+                            float* p_r = reinterpret_cast<float*>((uintptr_t)pp) + (k0 == 3 ? 0L : (long)rsub * rs);
+                            const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                            const float s0 = g.relu ? 0.f : 1.f;
+                            const float4 bias = g.bias ? ldg128(g.bias + col) : zero4;
+                            const float4 sc = g.scale ? ldg128(g.scale + col) : make_float4(1.f, 1.f, 1.f, 1.f);
+                            const float4 sh = g.scale ? ldg128(g.shift + col) : zero4;
+                            const float4 sl = g.neg_slope ? ldg128(g.neg_slope + col) : make_float4(s0, s0, s0, s0);
+                            float4 gb0 = zero4, gb1 = zero4;
+                            if (g.group_bias) {
+                                gb0 = ldg128(g.group_bias + grp0 * g.Ncols + col);
+                                if (gb_switch < 32) gb1 = ldg128(g.group_bias + (grp0 + 1) * g.Ncols + col);
+                            }
+                            const float* r1c = g.res1 ? g.res1 + col : nullptr;
+                            const float* r2c = g.res2 ? g.res2 + col : nullptr;
+#define TGP_FAST_RES(KD) epi_fast_res_rows<KD>(ld_even, ld_odd, p_r, rs, lo, rel, rsub, bias, sc, sh, sl, r1c, g.ld_res1, ri1, r2c, \
+                                               g.ld_res2, ri2, gb0, gb1, gb_switch)
+                            if (k0 == 1) TGP_FAST_RES(1);
+                            else if (k0 == 2) TGP_FAST_RES(2);
+                            else if (k0 == 3) TGP_FAST_RES(3);
+                            else TGP_FAST_RES(4);
+#undef TGP_FAST_RES
+                            done = true;
+                        }
+                    } else if (nrows == 32 && (k0 == 1 || k0 == 2 || k0 == 4) && __all_sync(0xffffffffu, kind == k0)) {
                         const int col = n0 + c0 + c4i * 4;
                         float* p_r = reinterpret_cast<float*>((uintptr_t)pp) + (long)rsub * rs;
                         const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -662,7 +782,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 } else if (path == 2) {
                     epi_chunk_vec<true>(g, stg_addr, lane, row0, nrows, n0 + c0, grp0, gb_switch, z * zstride, dbg);
                 } else if (path == 1) {
-                    epi_chunk_vec<false>(g, stg_addr, lane, row0, nrows, n0 + c0, grp0, gb_switch, z * zstride);
+                    epi_chunk_vec<false>(g, stg_addr, lane, row0, nrows, n0 + c0, grp0, gb_switch, z * zstride, 0, ri1, ri2);
                 } else {
                     const int col = n0 + c0 + lane;
                     const bool live = col < g.Ncols && nrows > 0 && !(dbg & 1);
@@ -1051,6 +1171,21 @@ static int launch_tc(const tgp_gemm_args* a, cudaStream_t st, int ksplit = 1, in
             }
         }
     }
+    if (vec_ok == 1) {
+        // fast chunk with residuals / per-cloud bias: one destination per column, aligned parameter vectors, groups >= 32 rows
+        bool ok = (a->rows_per_group == 0 || a->rows_per_group >= 32) && (!a->group_bias || al16(a->group_bias));
+        ok = ok && (!a->bias || al16(a->bias)) && (!a->scale || (al16(a->scale) && al16(a->shift))) && (!a->neg_slope || al16(a->neg_slope));
+        for (int s = 0; s < a->nseg && ok; ++s) {
+            ok = ok && a->seg[s].ld < (1L << 31);
+            for (int t = 0; t < s && ok; ++t)
+                if (a->seg[s].col_begin < a->seg[t].col_end && a->seg[t].col_begin < a->seg[s].col_end) ok = false;
+        }
+        const char* e = getenv("TGP_TC_NO_FAST");
+        if (ok && !(e && e[0] == '1')) vec_ok = 4;
+    }
+    if ((a->res1_idx || a->res2_idx) && (!vec_ok || (a->rows_per_group > 0 && a->rows_per_group < 32 && a->group_bias)))
+        return fail(TGP_EINVAL, "tgp_gemm: gathered residuals need the 128-bit epilogue (widths / leading dimensions multiples of 4, 16-byte aligned pointers)");
+    if ((a->res1_idx && !a->res1) || (a->res2_idx && !a->res2)) return fail(TGP_EINVAL, "tgp_gemm: res*_idx without res*");
     { const char* e = getenv("TGP_TC_SCALAR_EPI"); if (e && e[0] == '1') vec_ok = 0; }
     static int dbg = -1;
     if (dbg < 0) { const char* e = getenv("TGP_TC_DEBUG"); dbg = e ? atoi(e) : 0; }

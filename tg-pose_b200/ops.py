@@ -288,7 +288,7 @@ PARAM_CACHE = ParamCache()
 
 def gemm(A, Bmat, b_is_nk, segs, bias=None, group_bias=None, rows_per_group=0, res1=None, res2=None,
          scale=None, shift=None, relu=False, K=None, Ncols=None, A_split=None, B_split=None, neg_slope=None, tc=None,
-         mixed=False, a_kp=0, a_group_cols=0):
+         mixed=False, a_kp=0, a_group_cols=0, res1_idx=None, res2_idx=None, algo_flops=None):
     """C = A @ B (+ epilogue) written to `segs` = [(col_begin, col_end, tensor, mode, slab_width)].
     A: (M,K) with unit column stride; Bmat: (K,Ncols) or, if b_is_nk, (Ncols,K); both may be row-strided views."""
     assert Bmat.stride(-1) == 1
@@ -332,6 +332,10 @@ def gemm(A, Bmat, b_is_nk, segs, bias=None, group_bias=None, rows_per_group=0, r
     if res2 is not None:
         assert res2.stride(-1) == 1
         a.res2, a.ld_res2 = res2.data_ptr(), res2.stride(0)
+    for nm, ix, rs_ in (("res1_idx", res1_idx, res1), ("res2_idx", res2_idx, res2)):
+        if ix is not None:      # gathered residual: output row m adds row ix[m] of the residual matrix
+            assert rs_ is not None and ix.dtype == torch.int32 and ix.is_contiguous() and ix.numel() == M
+            setattr(a, nm, ix.data_ptr())
     a.scale = scale.data_ptr() if scale is not None else None
     a.shift = shift.data_ptr() if shift is not None else None
     a.relu = 1 if relu else 0
@@ -341,7 +345,8 @@ def gemm(A, Bmat, b_is_nk, segs, bias=None, group_bias=None, rows_per_group=0, r
         a.seg[i] = OutSeg(c0, c1, mode, sw, t.stride(0) if mode in (0, 2, 4) else 0, t.data_ptr())
     name = "gemm_tc" if A_split is not None and B_split is not None else "gemm"
     if EVENT_LOG is not None:
-        EVENT_LOG.setdefault("__gemm_shapes__", []).append((name, M, K, Ncols, bool(mixed)))
+        # algo_flops: flops of the REFERENCE's contraction this launch stands for, when the launch is a factored piece of it
+        EVENT_LOG.setdefault("__gemm_shapes__", []).append((name, M, K, Ncols, bool(mixed), algo_flops))
     _run(name, _lib.load().tgp_gemm, ctypes.byref(a), _stream())
 
 

@@ -61,6 +61,23 @@ class _Packed:
         # three at ~2^-19 relative error per product; nothing downstream of the heads is a neighbour search
         self.w_split = ops.split_mixed(self.w)
 
+    @classmethod
+    def from_matrix(cls, w, scale=None, shift=None, slope=None):
+        """a pack from an already assembled (Ncols, K) matrix (column subsets of a layer's weight)."""
+        pk = cls.__new__(cls)
+        pk.w = w.detach().contiguous()
+        pk.scale = scale.contiguous() if scale is not None else None
+        pk.shift = shift.contiguous() if shift is not None else None
+        pk.slope = slope.contiguous() if slope is not None else None
+        pk.w_split = ops.split_mixed(pk.w)
+        return pk
+
+
+# column blocks of `feat` (FaceRecon.py:81) [fm_0 | fm_1 | up(fm_2) | up(fm_3) | up(fm_4) | one-hot] (+ xyz for Pose_Ts)
+_FINE_COLS = list(range(0, 256)) + list(range(1280, FEAT_C + 3))      # per-point blocks: fm_0, fm_1, one-hot, xyz
+_L1_COLS = slice(256, 768)                                             # fm_2 | fm_3: level-1 points, upsampled by nn1
+_L2_COLS = slice(768, 1280)                                            # fm_4: level-2 points, upsampled by nn2
+
 
 def pointwise(x_cl, conv, bn=None, act=None, slope=0.2):
     """1x1 Conv1d (+ eval BatchNorm + activation) on a channel-last (B,N,Cin) tensor -> (B,N,Cout): one GEMM
@@ -259,6 +276,7 @@ class PoseNet9D(nn.Module):
         self.only_encoder = only_encoder
         self.train_outputs = train_outputs
         self.overlap_heads = True      # inference: pose tails on forked streams next to the decoder chain
+        self.factored_heads = True     # inference: upsampled input channels of the first layers contracted per COARSE point
         self._side = None
         if not only_encoder:
             self.face_all = FaceNet(**enc_kwargs)
@@ -317,6 +335,18 @@ class PoseNet9D(nn.Module):
                 # conv2 of the three pose tails as ONE grouped contraction (each alone: 257 row tiles on 148 SMs)
                 self._packs["tails2"] = _Packed([g.conv2.weight, r.conv2.weight, t.conv2.weight],
                                                 [_fold(g.conv2, g.bn2), _fold(r.conv2, r.bn2), _fold(t.conv2, t.bn2)], [0.0, 0.0, 0.0])
+                # FACTORED first layers.  `feat` is a concatenation whose blocks fm_2 | fm_3 and fm_4 are nearest-neighbour
+                # upsamplings of the 257 / 64 coarse points (FaceRecon.py:69-81), and a 1x1 convolution commutes with a
+                # gather of rows:  W.[x | up(y)] = W_x.x + up(W_y.y).  So the 1024 upsampled input channels of the five
+                # first-layer convolutions (the four of stage 1 + decoder conv1) are contracted ONCE PER COARSE POINT
+                # (K = 512 at 257 and at 64 points per cloud instead of K = 1024 at 1028 points: 3.0x fewer flops for these
+                # layers, which were 70 % of the network's), and the per-point contraction keeps K = 265 and adds the two
+                # coarse products as gathered residuals in its epilogue (tgp_gemm_args.res1_idx / res2_idx).
+                s1, d1 = self._packs["stage1"], self._packs["dec1"]
+                self._packs["stage1f"] = _Packed.from_matrix(s1.w[:, _FINE_COLS], s1.scale, s1.shift, s1.slope)
+                self._packs["dec1f"] = _Packed.from_matrix(d1.w[:, _FINE_COLS], d1.scale, d1.shift, d1.slope)
+                self._packs["coarse1"] = _Packed.from_matrix(torch.cat([s1.w[:, _L1_COLS], d1.w[:, _L1_COLS]], 0))
+                self._packs["coarse2"] = _Packed.from_matrix(torch.cat([s1.w[:, _L2_COLS], d1.w[:, _L2_COLS]], 0))
                 for name, head in (("green", g), ("red", r), ("ts", t)):
                     sc, sh = _fold(head.conv3, head.bn3)
                     self._packs[name + "3"] = (head.conv3.weight.detach().reshape(256, 256), sc.contiguous(), sh.contiguous())
@@ -370,14 +400,47 @@ class PoseNet9D(nn.Module):
         kin = FEAT_C + 3
         # [feat | xyz] (Pose_Ts input, PoseNet9D.py:63) assembled straight into the tensor-core operand: upsampling
         # gathers, one-hot broadcast and both torch.cat of the reference in one launch
-        src = enc.concat_sources(parts, enc.one_hot(obj_id, B), extra=[(centred.reshape(M, 3), None, 1)])
-        raw, xs = ops.concat_rows(src, B, N, want_raw=self.train_outputs, want_split=True, mixed=True)
+        one_hot = enc.one_hot(obj_id, B)
+        flat = lambda t_: t_.reshape(-1, t_.shape[-1])
+        raw = None
+        if self.train_outputs:      # the (B, N, 1286) `feat` output itself (returned only with FLAGS.train, PoseNet9D.py:68-80)
+            raw = ops.concat_rows(enc.concat_sources(parts, one_hot), B, N)[0]
+        factored = self.factored_heads and parts["fm_2"].shape[1] * B >= 256 and parts["fm_4"].shape[1] * B >= 256
+        if factored:
+            # per-point operand [fm_0 | fm_1 | one-hot | xyz] (K = 265) and the two coarse operands, as mixed tensor-core operands
+            N1, N2 = parts["fm_2"].shape[1], parts["fm_4"].shape[1]
+            xs = ops.concat_rows([(flat(parts["fm_0"]), None, 1), (flat(parts["fm_1"]), None, 1), (one_hot, None, 0),
+                                  (centred.reshape(M, 3), None, 1)], B, N, want_raw=False, want_split=True, mixed=True)[1]
+            xs1 = ops.concat_rows([(flat(parts["fm_2"]), None, 1), (flat(parts["fm_3"]), None, 1)], B, N1, want_raw=False,
+                                  want_split=True, mixed=True)[1]
+            xs2 = ops.split_mixed(flat(parts["fm_4"]))
+            # coarse products of all five first layers at once: (B*N1, 4608) and (B*N2, 4608), no bias / activation
+            c1, c2 = pk["coarse1"], pk["coarse2"]
+            nc = c1.w.shape[0]
+            P1 = torch.empty((B * N1, nc), dtype=torch.float32, device=xs.device)
+            P2 = torch.empty((B * N2, nc), dtype=torch.float32, device=xs.device)
+            ops.gemm(None, c1.w, True, [(0, nc, P1, 0, 0)], K=512, A_split=xs1, B_split=c1.w_split, mixed=True, algo_flops=0)
+            ops.gemm(None, c2.w, True, [(0, nc, P2, 0, 0)], K=512, A_split=xs2, B_split=c2.w_split, mixed=True, algo_flops=0)
+            # rows of P1 / P2 that each level-0 point adds: its nearest coarse point (FaceRecon.py:69-73), as global row numbers
+            cloud = torch.arange(B, device=xs.device, dtype=torch.int32).view(B, 1)
+            gi1 = (parts["nn1"].view(B, N) + cloud * N1).contiguous()
+            gi2 = (parts["nn2"].view(B, N) + cloud * N2).contiguous()
+            k1 = len(_FINE_COLS)
+            res_s1 = dict(res1=P1[:, :4096], res2=P2[:, :4096], res1_idx=gi1, res2_idx=gi2, algo_flops=2 * M * kin * 4096)
+            res_d1 = dict(res1=P1[:, 4096:], res2=P2[:, 4096:], res1_idx=gi1, res2_idx=gi2, algo_flops=2 * M * kin * 512)
+            pk_s1, pk_d1 = pk["stage1f"], pk["dec1f"]
+        else:
+            # [feat | xyz] (Pose_Ts input, PoseNet9D.py:63) assembled straight into the tensor-core operand: upsampling
+            # gathers, one-hot broadcast and both torch.cat of the reference in one launch
+            src = enc.concat_sources(parts, one_hot, extra=[(centred.reshape(M, 3), None, 1)])
+            xs = ops.concat_rows(src, B, N, want_raw=False, want_split=True, mixed=True)[1]
+            k1, res_s1, res_d1, pk_s1, pk_d1 = kin, {}, {}, pk["stage1"], pk["dec1"]
         # stage 1: four 1286/1289 -> 1024 convolutions as one contraction over the shared operand; conv_5's output is
         # only ever max-pooled over the cloud (FaceRecon.py:145-146), so that pooling happens in the epilogue
         # (the three 1024-wide hidden activations of the pose tails land side by side in one operand: their conv2 layers
         # run as one grouped contraction below)
-        hid, _, f5max, _ = self._stage(pk["stage1"], xs, kin, [(1024, "split"), (1024, "split"), (1024, "max"),
-                                                                (1024, "split")], M, rows_per_group=N, shared_split=True)
+        hid, _, f5max, _ = self._stage(pk_s1, xs, k1, [(1024, "split"), (1024, "split"), (1024, "max"),
+                                                       (1024, "split")], M, rows_per_group=N, shared_split=True, **res_s1)
         # The three pose tails and the decoder chain are independent after stage 1.  Each of their GEMMs has 257 row tiles
         # for 148 SMs (a 1.7-wave tail), so they are issued on forked streams: the persistent CTAs of one kernel that finish
         # early free their SMs for the next kernel's CTAs.  Under CUDA-graph capture the forks become parallel branches.
@@ -407,7 +470,7 @@ class PoseNet9D(nn.Module):
         else:
             wfold, bfold = pk["ph_fold"]
             gb = ops.linear_nk(feat_all, wfold, bias=bfold, tc=False)
-        (d1,) = self._stage(pk["dec1"], xs, kin, [(512, "split")], M, group_bias=gb, rows_per_group=N)
+        (d1,) = self._stage(pk_d1, xs, k1, [(512, "split")], M, group_bias=gb, rows_per_group=N, **res_d1)
         (d2,) = self._stage(pk["dec2"], d1, 512, [(512, "split")], M)
         (d3,) = self._stage(pk["dec3"], d2, 512, [(256, "split")], M)
         (d4,) = self._stage(pk["dec4"], d3, 256, [(128, "raw")], M)
@@ -449,7 +512,7 @@ class PoseNet9D(nn.Module):
         green_R_vec, red_R_vec, ts_vec = vecs
         feat = feat_global = None
         if self.train_outputs:
-            feat = raw.view(B, N, kin)[:, :, :FEAT_C]
+            feat = raw.view(B, N, FEAT_C)
             feat_global = feat.max(dim=1)[0]
         return self._assemble(green_R_vec, red_R_vec, ts_vec[:, 0:3], ts_vec[:, 3:6], mean, recon, h1, h2, feat, feat_global)
 
