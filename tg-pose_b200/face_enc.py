@@ -49,6 +49,10 @@ class Face_Enc(nn.Module):
         self._record = None
         # CUDA-graph replay (graph.py): device tensors holding the two Pool_layer draws of this forward
         self._static_perms = None
+        # inference: everything that depends on the coordinates only (level-1 / level-2 xyz kNN, both nearest-upsampling index
+        # tensors) runs on a forked stream beside conv_0 / conv_1 instead of in the chain
+        self.xyz_ahead = True
+        self._xyz_stream = None
 
     # -- helpers -------------------------------------------------------------------------
     def _next_idx(self, compute):
@@ -74,6 +78,36 @@ class Face_Enc(nn.Module):
     def _bn_relu(self, bn, x):
         return F.relu(bn(x.transpose(1, 2)).transpose(1, 2))
 
+    def _xyz_side_work(self, vertices, k):
+        """The coordinate-only part of the forward on a forked stream.  Pool_layer's sample does not depend on the features
+        (gcn3d.py:241-244: one torch.randperm per level), so the pooled clouds, their xyz kNN (conv_2 / conv_3 / conv_4 ORL,
+        pool_2) and the two nearest-upsampling searches (FaceRecon.py:69-70) are known as soon as the input is.  Both draws are
+        made here, in the reference's order.  Returns a dict; the caller waits for the stream before the first use."""
+        dev = vertices.device
+        n0 = vertices.shape[1]
+        p1 = int(n0 / self.pool_1.pooling_rate)
+        p2 = int(p1 / self.pool_2.pooling_rate)
+        sp = self._static_perms
+        if sp is not None:
+            perm1, perm2 = sp
+        else:
+            perm1 = torch.randperm(n0)[:p1].to(dev, non_blocking=True)
+            perm2 = torch.randperm(p1)[:p2].to(dev, non_blocking=True)
+        if self._xyz_stream is None or self._xyz_stream.device != dev:
+            self._xyz_stream = torch.cuda.Stream(device=dev)
+        side, main = self._xyz_stream, torch.cuda.current_stream(dev)
+        side.wait_stream(main)
+        k1, k2 = min(k, p1 // 8), min(k, p2 // 8)
+        with torch.cuda.stream(side):
+            v1 = ops.select_rows(vertices, perm1)
+            i_l1 = ops.knn_xyz(v1, k1, want64=False, want32=True)[1]
+            v2 = ops.select_rows(v1, perm2)
+            i_l2 = ops.knn_xyz(v2, k2, want64=False, want32=True)[1]
+            nn1 = ops.nearest(vertices, v1, want64=False, want32=True)[1]
+            nn2 = ops.nearest(vertices, v2, want64=False, want32=True)[1]
+        return {"perm1": perm1, "perm2": perm2, "i_l1": i_l1, "i_l2": i_l2, "nn1": nn1, "nn2": nn2, "stream": side,
+                "keep": (v1, v2)}
+
     # -- forward -------------------------------------------------------------------------
     def encode(self, vertices):
         """the five graph-conv feature maps and the two nearest-upsampling index tensors (FaceRecon.py:55-70):
@@ -85,6 +119,9 @@ class Face_Enc(nn.Module):
             p.requires_grad for bn in (self.bn1, self.bn2, self.bn3) for p in bn.parameters()))
         self._slot = 0
         share = self._inject is None
+        ahead = None
+        if share and self.xyz_ahead and vertices.is_cuda and not torch.is_grad_enabled() and vertices.shape[1] >= 128:
+            ahead = self._xyz_side_work(vertices.contiguous().float(), k)
 
         def xyz_knn(v, kk):
             return ops.knn_xyz(v, kk, want64=False, want32=True)[1]
@@ -106,12 +143,15 @@ class Face_Enc(nn.Module):
             fm_1 = self._bn_relu(self.bn1, self.conv_1(vertices, fm_0, k, idx_feat=i1, idx_xyz=i1_orl, fm_split=fm_0s))
         ip1 = self._next_idx(lambda: i0[:, :, :4].contiguous() if share else xyz_knn(vertices, 4))
         sp = self._static_perms
+        if ahead is not None:
+            sp = (ahead["perm1"], ahead["perm2"])
+            torch.cuda.current_stream(vertices.device).wait_stream(ahead["stream"])
         v_pool_1, fm_pool_1 = self.pool_1(vertices, fm_1, idx_xyz=ip1, sample_idx=sp[0] if sp else None)
 
         # level 1
         k1 = min(k, v_pool_1.shape[1] // 8)
         i2 = self._next_idx(lambda: feat_knn(fm_pool_1, k1))
-        i2_orl = self._next_idx(lambda: xyz_knn(v_pool_1, k1))
+        i2_orl = self._next_idx(lambda: ahead["i_l1"] if ahead is not None else xyz_knn(v_pool_1, k1))
         if fold:
             fm_2, fm_2s = self.conv_2(v_pool_1, fm_pool_1, k1, idx_feat=i2, idx_xyz=i2_orl,
                                       post=self._bn_post(self.bn2), want_split=True)
@@ -131,12 +171,12 @@ class Face_Enc(nn.Module):
         # level 2
         k2 = min(k, v_pool_2.shape[1] // 8)
         i4 = self._next_idx(lambda: feat_knn(fm_pool_2, k2))
-        i4_orl = self._next_idx(lambda: xyz_knn(v_pool_2, k2))
+        i4_orl = self._next_idx(lambda: ahead["i_l2"] if ahead is not None else xyz_knn(v_pool_2, k2))
         fm_4 = self.conv_4(v_pool_2, fm_pool_2, k2, idx_feat=i4, idx_xyz=i4_orl)
 
         # nearest-neighbour upsampling indices back to level 0 (FaceRecon.py:69-70)
-        nn1 = self._next_idx(lambda: ops.nearest(vertices, v_pool_1, want64=False, want32=True)[1])
-        nn2 = self._next_idx(lambda: ops.nearest(vertices, v_pool_2, want64=False, want32=True)[1])
+        nn1 = self._next_idx(lambda: ahead["nn1"] if ahead is not None else ops.nearest(vertices, v_pool_1, want64=False, want32=True)[1])
+        nn2 = self._next_idx(lambda: ahead["nn2"] if ahead is not None else ops.nearest(vertices, v_pool_2, want64=False, want32=True)[1])
         return {"fm_0": fm_0, "fm_1": fm_1, "fm_2": fm_2, "fm_3": fm_3, "fm_4": fm_4, "nn1": nn1, "nn2": nn2}
 
     def one_hot(self, cat_id, bs):
