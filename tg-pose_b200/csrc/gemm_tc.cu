@@ -410,10 +410,32 @@ __device__ __forceinline__ void epi_fast_kind(int kind, uint32_t ld_even, uint32
 // and the heads' first layers with GATHERED residuals (tgp_gemm_args.res1_idx).  Same structure as the lean fast chunk; the
 // residual rows of the 32 output rows sit one per lane (ri1 / ri2) and are fetched by shuffles; 4 rows (a 128-bit staging
 // read + two 128-bit residual loads each) are in flight before the first store.
-template <int KIND>
+// RESIDUAL PREFETCH (vec_ok == 5: the fast residual chunk of a 256-column-tile launch).  ncu / K sweep: the two residual loads
+// of a row cost the chunk two exposed L2 round trips (~1500 cycles each, 170 of the 436 us of the heads' first layer) and the
+// register budget (168 with 10 warps) has no room to keep more of them in flight.  These launches are epilogue-bound, so
+// they run their operand ring two stages deep and the freed 96 KB hold, per epilogue warp, the residual pieces of ONE chunk
+// ([half][residual][row quad][lane] x 16 B = 8 KB), fetched by cp.async one half-chunk ahead: every lane copies exactly the
+// 16 bytes it will add, so no barrier is involved -- only its own cp.async groups (one per half-chunk, in order).
+__device__ __forceinline__ void cp_async16_g2s(uint32_t dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void res_prefetch_half(uint32_t rb_lane, int h, const float* r1c, long ld1, int ri1, const float* r2c,
+                                                  long ld2, int ri2, int rsub, bool on) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const int row = 4 * (h * 4 + u) + rsub;
+        const int i1 = __shfl_sync(0xffffffffu, ri1, row), i2 = __shfl_sync(0xffffffffu, ri2, row);
+        if (on && r1c) cp_async16_g2s(rb_lane + (uint32_t)(((h * 2 + 0) * 4 + u) * 512), r1c + (long)i1 * ld1);
+        if (on && r2c) cp_async16_g2s(rb_lane + (uint32_t)(((h * 2 + 1) * 4 + u) * 512), r2c + (long)i2 * ld2);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");      // (an empty group when nothing was issued: the counts stay uniform)
+}
+
+template <int KIND, bool BUF>
 __device__ __forceinline__ void epi_fast_res_rows(uint32_t ld_even, uint32_t ld_odd, float* p_r, int rs, int lo, int rel, int rsub,
                                                   float4 bias, float4 sc, float4 sh, float4 sl, const float* r1c, long ld1, int ri1,
-                                                  const float* r2c, long ld2, int ri2, float4 gb0, float4 gb1, int gb_switch) {
+                                                  const float* r2c, long ld2, int ri2, float4 gb0, float4 gb1, int gb_switch,
+                                                  uint32_t rb_lane = 0, bool has_next = false) {
     float4 mx0 = make_float4(-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F), mx1 = mx0;
     const long step = 4L * rs;
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -426,12 +448,25 @@ __device__ __forceinline__ void epi_fast_res_rows(uint32_t ld_even, uint32_t ld_
             const uint32_t ad = ((uu & 1) ? ld_odd : ld_even) + (uint32_t)(uu * 512);
             asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a[u].x), "=f"(a[u].y), "=f"(a[u].z), "=f"(a[u].w) : "r"(ad));
         }
+        if (BUF) {
+            // this half's pieces were requested one half-chunk ago; at most the following half's group may still be pending
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int row = 4 * (h * 4 + u) + rsub;
-            const int i1 = __shfl_sync(0xffffffffu, ri1, row), i2 = __shfl_sync(0xffffffffu, ri2, row);
-            q1[u] = r1c ? ldg128(r1c + (long)i1 * ld1) : zero4;
-            q2[u] = r2c ? ldg128(r2c + (long)i2 * ld2) : zero4;
+            for (int u = 0; u < 4; ++u) {
+                q1[u] = zero4; q2[u] = zero4;
+                if (r1c) { const uint32_t ad = rb_lane + (uint32_t)(((h * 2 + 0) * 4 + u) * 512);
+                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(q1[u].x), "=f"(q1[u].y), "=f"(q1[u].z), "=f"(q1[u].w) : "r"(ad)); }
+                if (r2c) { const uint32_t ad = rb_lane + (uint32_t)(((h * 2 + 1) * 4 + u) * 512);
+                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(q2[u].x), "=f"(q2[u].y), "=f"(q2[u].z), "=f"(q2[u].w) : "r"(ad)); }
+            }
+        } else {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int row = 4 * (h * 4 + u) + rsub;
+                const int i1 = __shfl_sync(0xffffffffu, ri1, row), i2 = __shfl_sync(0xffffffffu, ri2, row);
+                q1[u] = r1c ? ldg128(r1c + (long)i1 * ld1) : zero4;
+                q2[u] = r2c ? ldg128(r2c + (long)i2 * ld2) : zero4;
+            }
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
@@ -459,6 +494,8 @@ __device__ __forceinline__ void epi_fast_res_rows(uint32_t ld_even, uint32_t ld_
                 m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
             }
         }
+        // the values of this half are consumed: its buffer takes the same half of the NEXT chunk (64 columns further)
+        if (BUF) res_prefetch_half(rb_lane, h, r1c ? r1c + 64 : nullptr, ld1, ri1, r2c ? r2c + 64 : nullptr, ld2, ri2, rsub, has_next);
     }
     if (KIND == 3) {
         // per-cloud column max: combine the 4 row sub-groups (lane bits 3, 4), one atomicMax per column and cloud
@@ -490,7 +527,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmA16, const __grid_constant__ CUtensorMap tmB16,
                const __grid_constant__ GemmDev P, int Kp, int num_n_tiles, int num_tiles, int dbg,
-               int tiles_mn, int kb_per, long zstride, int vec_ok) {
+               int tiles_mn, int kb_per, long zstride, int vec_ok, int nst) {
     extern __shared__ __align__(1024) unsigned char tc_smem[];
     constexpr int B_BYTES = BN * TC_BK * 4;
     constexpr int TC_STAGES = TcStages<BN>::value;
@@ -562,7 +599,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                 tma_load_2d(sa, &tmA16, a_col + k64 * 64, m0, full + stage);
                                 tma_load_2d(sa + TC_A_BYTES, &tmB16, b_part * Kp + k64 * 64, n0, full + stage);
                             }
-                            if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+                            if (++stage == nst) { stage = 0; phase ^= 1; }
                         }
                     }
                     continue;
@@ -586,7 +623,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                 tma_load_2d(sa + TC_A_BYTES, &tmB, b_off + kb * TC_BK, n0, full + stage);
                             }
                         }
-                        if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+                        if (++stage == nst) { stage = 0; phase ^= 1; }
                     }
                 }
             }
@@ -631,7 +668,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         }
                         __syncwarp();
                         accum = 1;
-                        if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+                        if (++stage == nst) { stage = 0; phase ^= 1; }
                         continue;
                     }
                     if (tc_elect_one()) {
@@ -650,7 +687,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     }
                     __syncwarp();
                     accum = 1;
-                    if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+                    if (++stage == nst) { stage = 0; phase ^= 1; }
                 }
                 if (tc_elect_one()) umma_commit(tmem_full + acc);
                 __syncwarp();
@@ -668,8 +705,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint32_t ld_odd = stg_addr + (uint32_t)(rsub * 128 + ((c4i ^ (4 + rsub)) << 4));
         const bool gb_slow = g.group_bias && g.rows_per_group > 0 && g.rows_per_group < 32;
         const int path = (dbg & 1) ? 0 : ((vec_ok == 2 || vec_ok == 3) ? 2 : ((vec_ok && !gb_slow) ? 1 : 0));   // 2 lean, 1 vector, 0 scalar
-        const bool fast_ok = (vec_ok == 3 || vec_ok == 4) && !(dbg & 9);
-        const bool fast_res = vec_ok == 4;            // residuals / per-cloud bias on the fast chunk
+        const bool fast_ok = (vec_ok >= 3 && vec_ok <= 5) && !(dbg & 9);
+        const bool fast_res = vec_ok == 4 || vec_ok == 5;            // residuals / per-cloud bias on the fast chunk
+        const bool res_buf = vec_ok == 5;             // ... with the residual pieces prefetched into shared memory (2-stage ring)
+        const uint32_t rb_lane = s_u32(base + 2 * STAGE_BYTES) + (uint32_t)((warp - 2) * 8192 + lane * 16);
         const bool has_act = g.scale != nullptr || g.neg_slope != nullptr || g.relu != 0;
         int it = 0;
         for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
@@ -702,6 +741,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (row0 + lane < g.M) {
                 if (g.res1) ri1 = g.res1_idx ? __ldg(g.res1_idx + row0 + lane) : (int)(row0 + lane);
                 if (g.res2) ri2 = g.res2_idx ? __ldg(g.res2_idx + row0 + lane) : (int)(row0 + lane);
+            }
+            int pf = -1;          // chunk of this tile whose residual pieces are in flight / in the buffer
+            if (res_buf) {
+                // first chunk of the tile: requested before the accumulator wait
+                const int col = n0 + half * 32 + c4i * 4;
+                const bool on = col < g.Ncols;
+                const float* r1c = g.res1 ? g.res1 + col : nullptr;
+                const float* r2c = g.res2 ? g.res2 + col : nullptr;
+                res_prefetch_half(rb_lane, 0, r1c, g.ld_res1, ri1, r2c, g.ld_res2, ri2, rsub, on);
+                res_prefetch_half(rb_lane, 1, r1c, g.ld_res1, ri1, r2c, g.ld_res2, ri2, rsub, on);
+                pf = 0;
             }
             tc_mbar_wait(tmem_full + acc, acc_phase);
             tc_fence_after();
@@ -752,12 +802,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             }
                             const float* r1c = g.res1 ? g.res1 + col : nullptr;
                             const float* r2c = g.res2 ? g.res2 + col : nullptr;
-#define TGP_FAST_RES(KD) epi_fast_res_rows<KD>(ld_even, ld_odd, p_r, rs, lo, rel, rsub, bias, sc, sh, sl, r1c, g.ld_res1, ri1, r2c, \
-                                               g.ld_res2, ri2, gb0, gb1, gb_switch)
-                            if (k0 == 1) TGP_FAST_RES(1);
-                            else if (k0 == 2) TGP_FAST_RES(2);
-                            else if (k0 == 3) TGP_FAST_RES(3);
-                            else TGP_FAST_RES(4);
+#define TGP_FAST_RES(KD, BF, ...) epi_fast_res_rows<KD, BF>(ld_even, ld_odd, p_r, rs, lo, rel, rsub, bias, sc, sh, sl, r1c, g.ld_res1, ri1, \
+                                                            r2c, g.ld_res2, ri2, gb0, gb1, gb_switch, ##__VA_ARGS__)
+                            if (res_buf) {
+                                if (pf != ci) {      // (the chunk before this one did not take the fast path: request now)
+                                    res_prefetch_half(rb_lane, 0, r1c, g.ld_res1, ri1, r2c, g.ld_res2, ri2, rsub, true);
+                                    res_prefetch_half(rb_lane, 1, r1c, g.ld_res1, ri1, r2c, g.ld_res2, ri2, rsub, true);
+                                }
+                                const bool has_next = c0 + 64 < BN && col + 64 < g.Ncols;
+                                if (k0 == 1) TGP_FAST_RES(1, true, rb_lane, has_next);
+                                else if (k0 == 2) TGP_FAST_RES(2, true, rb_lane, has_next);
+                                else if (k0 == 3) TGP_FAST_RES(3, true, rb_lane, has_next);
+                                else TGP_FAST_RES(4, true, rb_lane, has_next);
+                                pf = has_next ? ci + 1 : -1;
+                            }
+                            else if (k0 == 1) TGP_FAST_RES(1, false);
+                            else if (k0 == 2) TGP_FAST_RES(2, false);
+                            else if (k0 == 3) TGP_FAST_RES(3, false);
+                            else TGP_FAST_RES(4, false);
 #undef TGP_FAST_RES
                             done = true;
                         }
@@ -1181,7 +1243,12 @@ static int launch_tc(const tgp_gemm_args* a, cudaStream_t st, int ksplit = 1, in
                 if (a->seg[s].col_begin < a->seg[t].col_end && a->seg[t].col_begin < a->seg[s].col_end) ok = false;
         }
         const char* e = getenv("TGP_TC_NO_FAST");
-        if (ok && !(e && e[0] == '1')) vec_ok = 4;
+        if (ok && !(e && e[0] == '1')) {
+            vec_ok = 4;
+            // 256-column tiles: residual pieces prefetched into the shared memory of ring stages 2..3 (the ring runs 2 deep)
+            const char* e2 = getenv("TGP_TC_NO_RESBUF");
+            if (BN == 256 && (a->res1 || a->res2) && TcStages<BN>::value >= 4 && !(e2 && e2[0] == '1')) vec_ok = 5;
+        }
     }
     if ((a->res1_idx || a->res2_idx) && (!vec_ok || (a->rows_per_group > 0 && a->rows_per_group < 32 && a->group_bias)))
         return fail(TGP_EINVAL, "tgp_gemm: gathered residuals need the 128-bit epilogue (widths / leading dimensions multiples of 4, 16-byte aligned pointers)");
@@ -1189,7 +1256,10 @@ static int launch_tc(const tgp_gemm_args* a, cudaStream_t st, int ksplit = 1, in
     { const char* e = getenv("TGP_TC_SCALAR_EPI"); if (e && e[0] == '1') vec_ok = 0; }
     static int dbg = -1;
     if (dbg < 0) { const char* e = getenv("TGP_TC_DEBUG"); dbg = e ? atoi(e) : 0; }
-    gemm_tc_kernel<BN><<<grid, TC_THREADS, smem, st>>>(tmA, tmB, tmA16, tmB16, P, Kp, num_n_tiles, num_tiles, dbg, tiles_mn, kb_per, zstride, vec_ok);
+    int nst = TcStages<BN>::value;      // operand ring depth in use (<= the depth the shared memory is carved for)
+    { const char* e = getenv("TGP_TC_NST"); if (e && atoi(e) >= 2 && atoi(e) < nst) nst = atoi(e); }
+    if (vec_ok == 5) nst = 2;
+    gemm_tc_kernel<BN><<<grid, TC_THREADS, smem, st>>>(tmA, tmB, tmA16, tmB16, P, Kp, num_n_tiles, num_tiles, dbg, tiles_mn, kb_per, zstride, vec_ok, nst);
     return check_launch("gemm_tc_kernel");
 }
 
