@@ -823,7 +823,10 @@ def kernel_report(event_log, steps, B, peaks):
         kr["orl_global"] = {"bound": "hbm", "achieved_gbs": by / ms("orl_global") / 1e9,
                             "frac_hbm": by / ms("orl_global") / 1e9 / peaks["hbm_gbs"]}
     if ms("concat_rows"):
-        by = B * N0 * (4 * 1289 + 6 * 1344)
+        # bytes moved by the two operand-assembly launches of the factored heads (posenet.py): per level-0 point the
+        # [fm_0 | fm_1 | one-hot | xyz] row (265 floats read, 3 x 320 16-bit slots written), per level-1 point [fm_2 | fm_3]
+        # (512 floats read, 3 x 512 slots written); the level-2 operand goes through split_mixed
+        by = B * (N0 * (4 * 265 + 6 * 320) + N1 * (4 * 512 + 6 * 512))
         kr["concat_rows"] = {"bound": "hbm", "achieved_gbs": by / ms("concat_rows") / 1e9,
                              "frac_hbm": by / ms("concat_rows") / 1e9 / peaks["hbm_gbs"]}
     out["kernel_rooflines"] = {kk_: {a: (round(b, 4) if isinstance(b, float) else b) for a, b in v.items()} for kk_, v in kr.items()}

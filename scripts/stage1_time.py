@@ -15,11 +15,12 @@ flush = torch.empty(256 * 1024 * 1024 // 4, device="cuda")
 fine = torch.randn(M, 265, generator=g).cuda()
 c1 = torch.randn(B * N1, 512, generator=g).cuda()
 c2 = torch.randn(B * N2, 512, generator=g).cuda()
-# rows in the order the heads use (Face_Enc.upsample_order): sorted by the nearest level-1 point; the nearest level-2 point of
-# neighbouring rows mostly coincides (here: a fixed map level-1 -> level-2 plus 10 % strays); STAGE1_RANDOM=1: arbitrary order
+# the points of a cloud come in no particular order, so neither do their nearest coarse points.  STAGE1_SORTED=1: rows sorted by
+# their level-1 point, level-2 point mostly shared by neighbouring rows (an ordering that was tried for the heads and dropped:
+# it is slower, DESIGN.md 3a')
 nn1 = torch.randint(0, N1, (B, N), generator=g)
 nn2 = torch.randint(0, N2, (B, N), generator=g)
-if os.environ.get("STAGE1_RANDOM", "0") != "1":
+if os.environ.get("STAGE1_SORTED", "0") == "1":
     nn1 = nn1.sort(dim=1).values
     nn2 = torch.where(torch.rand(B, N, generator=g) < 0.1, nn2, (nn1 * 7) % N2)
 nn1, nn2 = nn1.cuda(), nn2.cuda()
