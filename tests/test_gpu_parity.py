@@ -708,6 +708,29 @@ def test_posenet_factored_heads_equal_unfactored():
             assert_close(a, b, rel=1e-4, floor=2e-6, what=f"factored heads: {k}")
 
 
+def test_face_enc_coordinate_work_ahead_is_bit_equal():
+    """Face_Enc inference with the coordinate-only work (pooled clouds, level-1 / level-2 xyz kNN, nearest upsampling) on the
+    forked stream equals the in-chain order bit for bit, draws the same two permutations from the CPU generator, and leaves
+    the generator in the same state (gcn3d.py:241-244)."""
+    from tgpose_b200.face_enc import Face_Enc
+    torch.manual_seed(0)
+    enc = Face_Enc().cuda().eval()
+    g = torch.Generator().manual_seed(5)
+    pts = torch.rand(4, 1028, 3, generator=g).cuda()
+    cat = torch.randint(0, 6, (4, 1), generator=g).float().cuda()
+    outs, states = [], []
+    with torch.no_grad():
+        for ahead in (True, False, True):
+            enc.xyz_ahead = ahead
+            torch.manual_seed(11)
+            feat, _ = enc(pts, cat)
+            torch.cuda.synchronize()
+            outs.append(feat.clone())
+            states.append(torch.get_rng_state().clone())
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+    assert torch.equal(states[0], states[1])
+
+
 def test_gemm_mixed_operands_range(ops):
     """fp16(x) saturates instead of overflowing (the bf16 residual carries the remainder) and tiny values keep their relative
     accuracy through the residual: rows scaled by 1e5 / 1e-6 stay finite and accurate."""
