@@ -197,9 +197,10 @@ typedef struct {
      * a multiple of 256, K a multiple of 64; B_split stacks the layers' (a_group_cols, K) weights.  0: plain contraction. */
     int a_kp;
     int a_group_cols;
-    /* GATHERED residuals (tensor-core path only): when res1_idx / res2_idx is non-NULL, output row m adds row
-     * res1_idx[m] / res2_idx[m] of res1 / res2 instead of row m.  A 1x1 convolution over a concatenation whose column blocks
-     * are nearest-neighbour upsamplings of coarser levels (FaceRecon.py:69-81 feeding PoseR.py:26, PoseTs.py:24,
+    /* GATHERED residuals: when res1_idx / res2_idx is non-NULL (int32, M entries), output row m adds row
+     * res1_idx[m] / res2_idx[m] of res1 / res2 instead of row m (both the fp32 FMA and the tensor-core path; the latter needs
+     * every width / leading dimension a multiple of 4 floats and 16-byte aligned pointers, else TGP_EINVAL).
+     * A 1x1 convolution over a concatenation whose column blocks are nearest-neighbour upsamplings of coarser levels (FaceRecon.py:69-81 feeding PoseR.py:26, PoseTs.py:24,
      * FaceRecon.py:100,133) is W.[x | up(y)] = W_x.x + up(W_y.y): the W_y.y products are computed once per COARSE point
      * and gathered here, instead of once per fine point. */
     const int32_t* res1_idx;
