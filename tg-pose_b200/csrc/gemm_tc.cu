@@ -333,28 +333,31 @@ struct FastDst {
 __device__ __forceinline__ FastDst fast_entry(const tgp_gemm_args& g, int col, long row0, long zoff, long grp0) {
     FastDst d = {nullptr, 0, 0, 0, 0};
     if (col >= g.Ncols) return d;
+    // pick the segment first (cheap compares; segments are disjoint on the fast paths), then do the arithmetic for it alone:
+    // this runs once per tile and epilogue warp, in front of the accumulator wait, and short-K launches feel its length
+    int sidx = -1;
 #pragma unroll
-    for (int s = 0; s < 4; ++s) {
-        if (s < g.nseg && col >= g.seg[s].col_begin && col < g.seg[s].col_end) {
-            const int rel = col - g.seg[s].col_begin;
-            d.rel = rel;
-            if (g.seg[s].mode == 3) {
-                d.kind = 3;      // (the lean fast path leaves column maxima to the general lean chunk; the residual one uses p / rs)
-                d.rs = g.seg[s].col_end - g.seg[s].col_begin;
-                d.p = g.seg[s].ptr + grp0 * d.rs + rel;
-            } else if (g.seg[s].mode == 1) {
-                const int w = g.seg[s].slab_width;
-                const int cg = rel / w, rr = rel - cg * w;
-                d.kind = 1;
-                d.rs = w;
-                d.p = g.seg[s].ptr + ((long)cg * g.M + row0) * w + rr;
-            } else {
-                d.kind = g.seg[s].mode == 2 ? 2 : (g.seg[s].mode == 4 ? 4 : 1);
-                d.rs = (int)g.seg[s].ld;
-                d.p = g.seg[s].ptr + zoff + row0 * g.seg[s].ld + rel;
-                d.lo = g.seg[s].slab_width;
-            }
-        }
+    for (int s = 0; s < 4; ++s)
+        if (s < g.nseg && col >= g.seg[s].col_begin && col < g.seg[s].col_end) sidx = s;
+    if (sidx < 0) return d;
+    const tgp_out_seg& sg = g.seg[sidx];
+    const int rel = col - sg.col_begin;
+    d.rel = rel;
+    if (sg.mode == 3) {
+        d.kind = 3;      // (the lean fast path leaves column maxima to the general lean chunk; the residual one uses p / rs)
+        d.rs = sg.col_end - sg.col_begin;
+        d.p = sg.ptr + grp0 * d.rs + rel;
+    } else if (sg.mode == 1) {
+        const unsigned w = (unsigned)sg.slab_width;
+        const unsigned cg = (unsigned)rel / w, rr = (unsigned)rel - cg * w;
+        d.kind = 1;
+        d.rs = (int)w;
+        d.p = sg.ptr + ((long)cg * g.M + row0) * w + rr;
+    } else {
+        d.kind = sg.mode == 2 ? 2 : (sg.mode == 4 ? 4 : 1);
+        d.rs = (int)sg.ld;
+        d.p = sg.ptr + zoff + row0 * sg.ld + rel;
+        d.lo = sg.slab_width;
     }
     return d;
 }
@@ -431,7 +434,9 @@ __device__ __forceinline__ void res_prefetch_half(uint32_t rb_lane, int h, const
     asm volatile("cp.async.commit_group;" ::: "memory");      // (an empty group when nothing was issued: the counts stay uniform)
 }
 
-template <int KIND, bool BUF>
+// BG: the launch has a bias or a per-cloud bias (false: both adds and the per-row group select drop out of the chunk -- the heads'
+// factored first layers carry their bias in the BatchNorm shift)
+template <int KIND, bool BUF, bool BG>
 __device__ __forceinline__ void epi_fast_res_rows(uint32_t ld_even, uint32_t ld_odd, float* p_r, int rs, int lo, int rel, int rsub,
                                                   float4 bias, float4 sc, float4 sh, float4 sl, const float* r1c, long ld1, int ri1,
                                                   const float* r2c, long ld2, int ri2, float4 gb0, float4 gb1, int gb_switch,
@@ -472,7 +477,8 @@ __device__ __forceinline__ void epi_fast_res_rows(uint32_t ld_even, uint32_t ld_
         for (int u = 0; u < 4; ++u) {
             const int uu = h * 4 + u, row = 4 * uu + rsub;
             const bool second = row >= gb_switch;
-            float4 v = f4add(f4add(f4add(a[u], bias), f4add(q1[u], q2[u])), second ? gb1 : gb0);
+            float4 v = BG ? f4add(f4add(f4add(a[u], bias), f4add(q1[u], q2[u])), second ? gb1 : gb0)
+                          : f4add(a[u], f4add(q1[u], q2[u]));
             v.x = act1(v.x, sc.x, sh.x, sl.x); v.y = act1(v.y, sc.y, sh.y, sl.y);
             v.z = act1(v.z, sc.z, sh.z, sl.z); v.w = act1(v.w, sc.w, sh.w, sl.w);
             float* q = p_r + uu * step;
@@ -719,15 +725,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             // TMEM gives each thread one ROW (32 consecutive columns per load); a shared-memory
             // transpose turns that into lane = COLUMN so that every global access of the epilogue
             // (residual loads, output stores) is a full, coalesced 128-byte row segment.
-            const long row0 = (long)m0 + quarter * 32;
-            const int nrows = (int)max((long)0, min((long)32, g.M - row0));
+            const int row0 = m0 + quarter * 32;          // (32-bit: the row count fits the TMA's int coordinates)
+            const int nrows = max(0, min(32, (int)g.M - row0));
             // per-cloud bias: at most one group boundary inside these 32 rows when rows_per_group >= 32
-            long grp0 = 0;
+            int grp0 = 0;
             int gb_switch = 64;
-            if (g.group_bias || g.rows_per_group > 0) {
-                grp0 = row0 / g.rows_per_group;
-                const long nxt = (grp0 + 1) * g.rows_per_group - row0;
-                gb_switch = nxt < 64 ? (int)nxt : 64;
+            if (g.rows_per_group > 0) {
+                grp0 = (int)((unsigned)row0 / (unsigned)g.rows_per_group);
+                const int nxt = (grp0 + 1) * g.rows_per_group - row0;
+                gb_switch = nxt < 64 ? nxt : 64;
             }
             // fast path: lane L owns the destination of (chunk L / 8 of this warp, column quad L % 8), computed while the
             // mainloop of this tile is still running
@@ -802,24 +808,31 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             }
                             const float* r1c = g.res1 ? g.res1 + col : nullptr;
                             const float* r2c = g.res2 ? g.res2 + col : nullptr;
-#define TGP_FAST_RES(KD, BF, ...) epi_fast_res_rows<KD, BF>(ld_even, ld_odd, p_r, rs, lo, rel, rsub, bias, sc, sh, sl, r1c, g.ld_res1, ri1, \
-                                                            r2c, g.ld_res2, ri2, gb0, gb1, gb_switch, ##__VA_ARGS__)
+#define TGP_FAST_RES(KD, BF, BGF, ...) epi_fast_res_rows<KD, BF, BGF>(ld_even, ld_odd, p_r, rs, lo, rel, rsub, bias, sc, sh, sl, r1c, g.ld_res1, \
+                                                                      ri1, r2c, g.ld_res2, ri2, gb0, gb1, gb_switch, ##__VA_ARGS__)
                             if (res_buf) {
                                 if (pf != ci) {      // (the chunk before this one did not take the fast path: request now)
                                     res_prefetch_half(rb_lane, 0, r1c, g.ld_res1, ri1, r2c, g.ld_res2, ri2, rsub, true);
                                     res_prefetch_half(rb_lane, 1, r1c, g.ld_res1, ri1, r2c, g.ld_res2, ri2, rsub, true);
                                 }
                                 const bool has_next = c0 + 64 < BN && col + 64 < g.Ncols;
-                                if (k0 == 1) TGP_FAST_RES(1, true, rb_lane, has_next);
-                                else if (k0 == 2) TGP_FAST_RES(2, true, rb_lane, has_next);
-                                else if (k0 == 3) TGP_FAST_RES(3, true, rb_lane, has_next);
-                                else TGP_FAST_RES(4, true, rb_lane, has_next);
+                                if (g.bias || g.group_bias) {
+                                    if (k0 == 1) TGP_FAST_RES(1, true, true, rb_lane, has_next);
+                                    else if (k0 == 2) TGP_FAST_RES(2, true, true, rb_lane, has_next);
+                                    else if (k0 == 3) TGP_FAST_RES(3, true, true, rb_lane, has_next);
+                                    else TGP_FAST_RES(4, true, true, rb_lane, has_next);
+                                } else {
+                                    if (k0 == 1) TGP_FAST_RES(1, true, false, rb_lane, has_next);
+                                    else if (k0 == 2) TGP_FAST_RES(2, true, false, rb_lane, has_next);
+                                    else if (k0 == 3) TGP_FAST_RES(3, true, false, rb_lane, has_next);
+                                    else TGP_FAST_RES(4, true, false, rb_lane, has_next);
+                                }
                                 pf = has_next ? ci + 1 : -1;
                             }
-                            else if (k0 == 1) TGP_FAST_RES(1, false);
-                            else if (k0 == 2) TGP_FAST_RES(2, false);
-                            else if (k0 == 3) TGP_FAST_RES(3, false);
-                            else TGP_FAST_RES(4, false);
+                            else if (k0 == 1) TGP_FAST_RES(1, false, true);
+                            else if (k0 == 2) TGP_FAST_RES(2, false, true);
+                            else if (k0 == 3) TGP_FAST_RES(3, false, true);
+                            else TGP_FAST_RES(4, false, true);
 #undef TGP_FAST_RES
                             done = true;
                         }
@@ -1268,6 +1281,7 @@ static int launch_tc(const tgp_gemm_args* a, cudaStream_t st, int ksplit = 1, in
 int tgp_gemm_tc(const tgp_gemm_args* a, cudaStream_t st) {
     if ((uintptr_t)a->A_split % 16 || (uintptr_t)a->B_split % 16)
         return fail(TGP_EINVAL, "tgp_gemm: split operands must be 16-byte aligned");
+    if (a->M > 0x7fffffffL - 256) return fail(TGP_EINVAL, "tgp_gemm: M exceeds the tensor-core path's 32-bit row coordinates");
     // widest column block that still gives every SM a tile (small problems: more, narrower tiles)
     const long mt = (a->M + TC_BM - 1) / TC_BM;
     int bn = a->Ncols > 128 ? 256 : (a->Ncols > 64 ? 128 : 64);
