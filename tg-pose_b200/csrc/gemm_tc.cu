@@ -717,11 +717,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint32_t rb_lane = s_u32(base + 2 * STAGE_BYTES) + (uint32_t)((warp - 2) * 8192 + lane * 16);
         const bool has_act = g.scale != nullptr || g.neg_slope != nullptr || g.relu != 0;
         int it = 0;
-        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+        // tile coordinates (split-K slice, row tile, column tile) advanced incrementally: three integer divisions per tile sat
+        // in front of every tile's epilogue
+        const int num_m_tiles = tiles_mn / num_n_tiles;
+        int z = (int)blockIdx.x / tiles_mn, tm, tn;
+        { const int tt0 = (int)blockIdx.x - z * tiles_mn; tm = tt0 / num_n_tiles; tn = tt0 - tm * num_n_tiles; }
+        const int dz = (int)gridDim.x / tiles_mn, dr = (int)gridDim.x - dz * tiles_mn;
+        const int dm = dr / num_n_tiles, dn = dr - dm * num_n_tiles;
+        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it,
+                 tn += dn, tm += dm + (tn >= num_n_tiles), tn -= (tn >= num_n_tiles) ? num_n_tiles : 0,
+                 z += dz + (tm >= num_m_tiles), tm -= (tm >= num_m_tiles) ? num_m_tiles : 0) {
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
-            const int z = t / tiles_mn, tt = t - z * tiles_mn;
-            const int m0 = (tt / num_n_tiles) * TC_BM, n0 = (tt % num_n_tiles) * BN;
+            const int m0 = tm * TC_BM, n0 = tn * BN;
             // TMEM gives each thread one ROW (32 consecutive columns per load); a shared-memory
             // transpose turns that into lane = COLUMN so that every global access of the epilogue
             // (residual loads, output stores) is a full, coalesced 128-byte row segment.
