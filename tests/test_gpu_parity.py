@@ -633,12 +633,15 @@ def test_gemm_mixed_operands(ops, M, K, N):
 
 
 @pytest.mark.parametrize("M,K,N,npg,ncoarse", [(4112, 265, 512, 1028, 257), (1028, 128, 256, 257, 64), (300, 64, 128, 100, 7),
-                                                (2056, 320, 384, 1028, 257), (8224, 265, 1024, 1028, 257)])
+                                                (2056, 320, 384, 1028, 257), (8224, 265, 1024, 1028, 257),
+                                                (8224, 64, 576, 1028, 257)])
 def test_gemm_gathered_residuals(ops, M, K, N, npg, ncoarse):
     """tgp_gemm_args.res1_idx / res2_idx: output row m adds row idx[m] of the residual matrices before the affine / activation.
     Checked against an fp64 product for every destination kind (raw, split, mixed, per-cloud column max) together with a
     per-cloud bias, on shapes with full 32-row blocks (fast chunk) and ragged last blocks, for mixed and 3xTF32 operands; the
-    last shape runs 256-column tiles, i.e. the residual pieces prefetched into shared memory (gemm_tc.cu, vec_ok == 5)."""
+    last two shapes run 256-column tiles, i.e. the residual pieces prefetched into shared memory (gemm_tc.cu, vec_ok == 5) --
+    the very last one with 144-column segments, so that fast and general chunks alternate inside a tile and the last column
+    tile is ragged."""
     g = torch.Generator().manual_seed(M + K + N)
     B = M // npg
     A = torch.randn(M, K, generator=g).cuda()
