@@ -105,8 +105,18 @@ class Face_Enc(nn.Module):
             i_l2 = ops.knn_xyz(v2, k2, want64=False, want32=True)[1]
             nn1 = ops.nearest(vertices, v1, want64=False, want32=True)[1]
             nn2 = ops.nearest(vertices, v2, want64=False, want32=True)[1]
+            up_rows = self.upsample_rows(nn1, nn2, p1, p2)
         return {"perm1": perm1, "perm2": perm2, "i_l1": i_l1, "i_l2": i_l2, "nn1": nn1, "nn2": nn2, "stream": side,
-                "keep": (v1, v2)}
+                "keep": (v1, v2), "up_rows": up_rows}
+
+    @staticmethod
+    def upsample_rows(nn1, nn2, n1, n2):
+        """the rows of the level-1 / level-2 feature maps that every level-0 point upsamples from (FaceRecon.py:69-73) as GLOBAL
+        row numbers (B*N,) int32 -- what the heads' factored first layers gather their coarse products by (posenet.py)."""
+        B, N = nn1.shape[0], nn1.shape[1]
+        cloud = torch.arange(B, device=nn1.device, dtype=torch.int32).view(B, 1)
+        return ((nn1.reshape(B, N) + cloud * n1).reshape(-1).contiguous(),
+                (nn2.reshape(B, N) + cloud * n2).reshape(-1).contiguous())
 
     # -- forward -------------------------------------------------------------------------
     def encode(self, vertices):
@@ -177,7 +187,8 @@ class Face_Enc(nn.Module):
         # nearest-neighbour upsampling indices back to level 0 (FaceRecon.py:69-70)
         nn1 = self._next_idx(lambda: ahead["nn1"] if ahead is not None else ops.nearest(vertices, v_pool_1, want64=False, want32=True)[1])
         nn2 = self._next_idx(lambda: ahead["nn2"] if ahead is not None else ops.nearest(vertices, v_pool_2, want64=False, want32=True)[1])
-        return {"fm_0": fm_0, "fm_1": fm_1, "fm_2": fm_2, "fm_3": fm_3, "fm_4": fm_4, "nn1": nn1, "nn2": nn2}
+        return {"fm_0": fm_0, "fm_1": fm_1, "fm_2": fm_2, "fm_3": fm_3, "fm_4": fm_4, "nn1": nn1, "nn2": nn2,
+                "up_rows": ahead["up_rows"] if ahead is not None else None}
 
     def one_hot(self, cat_id, bs):
         obj_idh = cat_id.view(-1, 1)

@@ -422,9 +422,7 @@ class PoseNet9D(nn.Module):
             ops.gemm(None, c1.w, True, [(0, nc, P1, 0, 0)], K=512, A_split=xs1, B_split=c1.w_split, mixed=True, algo_flops=0)
             ops.gemm(None, c2.w, True, [(0, nc, P2, 0, 0)], K=512, A_split=xs2, B_split=c2.w_split, mixed=True, algo_flops=0)
             # rows of P1 / P2 that each level-0 point adds: its nearest coarse point (FaceRecon.py:69-73), as global row numbers
-            cloud = torch.arange(B, device=xs.device, dtype=torch.int32).view(B, 1)
-            gi1 = (parts["nn1"].view(B, N) + cloud * N1).contiguous()
-            gi2 = (parts["nn2"].view(B, N) + cloud * N2).contiguous()
+            gi1, gi2 = parts.get("up_rows") or enc.upsample_rows(parts["nn1"], parts["nn2"], N1, N2)
             k1 = len(_FINE_COLS)
             res_s1 = dict(res1=P1[:, :4096], res2=P2[:, :4096], res1_idx=gi1, res2_idx=gi2, algo_flops=2 * M * kin * 4096)
             res_d1 = dict(res1=P1[:, 4096:], res2=P2[:, 4096:], res1_idx=gi1, res2_idx=gi2, algo_flops=2 * M * kin * 512)
