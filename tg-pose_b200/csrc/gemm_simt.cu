@@ -384,6 +384,7 @@ int tgp_gemm_validate(const tgp_gemm_args* a) {
     if (a->rows_per_group < 0) return fail(TGP_EINVAL, "tgp_gemm: rows_per_group must be >= 0");
     if (a->group_bias && a->rows_per_group <= 0) return fail(TGP_EINVAL, "tgp_gemm: rows_per_group must be positive");
     if ((a->scale == nullptr) != (a->shift == nullptr)) return fail(TGP_EINVAL, "tgp_gemm: scale and shift go together");
+    if ((a->res1_idx && !a->res1) || (a->res2_idx && !a->res2)) return fail(TGP_EINVAL, "tgp_gemm: res*_idx without res*");
     for (int s = 0; s < a->nseg; ++s) {
         const tgp_out_seg& sg = a->seg[s];
         if (!sg.ptr || sg.col_begin < 0 || sg.col_end > a->Ncols || sg.col_begin >= sg.col_end)

@@ -419,14 +419,15 @@ class PoseNet9D(nn.Module):
             nc = c1.w.shape[0]
             P1 = torch.empty((B * N1, nc), dtype=torch.float32, device=xs.device)
             P2 = torch.empty((B * N2, nc), dtype=torch.float32, device=xs.device)
-            ops.gemm(None, c1.w, True, [(0, nc, P1, 0, 0)], K=512, A_split=xs1, B_split=c1.w_split, mixed=True, algo_flops=0)
-            ops.gemm(None, c2.w, True, [(0, nc, P2, 0, 0)], K=512, A_split=xs2, B_split=c2.w_split, mixed=True, algo_flops=0)
+            ops.gemm(None, c1.w, True, [(0, nc, P1, 0, 0)], K=c1.w.shape[1], A_split=xs1, B_split=c1.w_split, mixed=True, algo_flops=0)
+            ops.gemm(None, c2.w, True, [(0, nc, P2, 0, 0)], K=c2.w.shape[1], A_split=xs2, B_split=c2.w_split, mixed=True, algo_flops=0)
             # rows of P1 / P2 that each level-0 point adds: its nearest coarse point (FaceRecon.py:69-73), as global row numbers
             gi1, gi2 = parts.get("up_rows") or enc.upsample_rows(parts["nn1"], parts["nn2"], N1, N2)
             k1 = len(_FINE_COLS)
-            res_s1 = dict(res1=P1[:, :4096], res2=P2[:, :4096], res1_idx=gi1, res2_idx=gi2, algo_flops=2 * M * kin * 4096)
-            res_d1 = dict(res1=P1[:, 4096:], res2=P2[:, 4096:], res1_idx=gi1, res2_idx=gi2, algo_flops=2 * M * kin * 512)
             pk_s1, pk_d1 = pk["stage1f"], pk["dec1f"]
+            n_s1, n_d1 = pk_s1.w.shape[0], pk_d1.w.shape[0]          # 4096 stage-1 columns, then the decoder's 512
+            res_s1 = dict(res1=P1[:, :n_s1], res2=P2[:, :n_s1], res1_idx=gi1, res2_idx=gi2, algo_flops=2 * M * kin * n_s1)
+            res_d1 = dict(res1=P1[:, n_s1:], res2=P2[:, n_s1:], res1_idx=gi1, res2_idx=gi2, algo_flops=2 * M * kin * n_d1)
         else:
             # [feat | xyz] (Pose_Ts input, PoseNet9D.py:63) assembled straight into the tensor-core operand: upsampling
             # gathers, one-hot broadcast and both torch.cat of the reference in one launch
