@@ -149,6 +149,8 @@ int tgp_layer_conv_fwd(const float* edge_rec, const float* directions,
  *         tf32(v) at out[m*ld + rel] and v - tf32(v) at out[m*ld + slab_width + rel] (slab_width = Kp).
  * mode 4: MIXED, the value is written as a mixed tensor-core operand (see tgp_gemm_args.mixed): ptr = operand base,
  *         ld = 2*Kp (fp32 slots per row), slab_width = Kp = tgp_mixed_kpad(width); col_begin maps to operand column 0.
+ * mode 5: as mode 4 without the bf16(x) slot (left unwritten): the operand of a mixed = 2 contraction, which never reads it --
+ *         one conversion and one store per four values less.  Modes 4 and 5 cannot be combined in one launch.
  * mode 3: COLUMN MAX per group of rows_per_group rows (torch.max over the points of a cloud, PoseR.py:33,
  *         FaceRecon.py:146): ptr is an int32 (M / rows_per_group, col_end - col_begin) buffer pre-filled with
  *         INT_MIN that receives atomicMax of the order-preserving encoding e(v) = bits(v) >= 0 ? bits(v) :
@@ -188,7 +190,9 @@ typedef struct {
      * fp16(a).fp16(b) + lo(a).bf16(b) + bf16(a).lo(b), three 16-bit tensor-core passes at twice the TF32 rate into one
      * fp32 accumulator = 1.5 TF32-pass equivalents instead of the three of 3xTF32, relative error ~2^-19 per product
      * (fp32-summation-noise level at the heads' K ~ 1e3).  Used for the heads' 1x1 convolutions (PoseR.py, PoseTs.py,
-     * FaceRecon.py:89-167), whose outputs feed no neighbour search; the encoder and the kNN keep the 3xTF32 operands. */
+     * FaceRecon.py:89-167), whose outputs feed no neighbour search; the encoder and the kNN keep the 3xTF32 operands.
+     * mixed = 2: B_split is a tgp_split_mixed_w16 operand (residual slot in fp16) and the third pass is fp16(a).lo16(b): the
+     * bf16(x) slot of A_split is never read, so producers may leave it out (output mode 5).  Same ~2^-19 per product. */
     int mixed;
     /* block-diagonal ("grouped") contraction on mixed operands: when a_group_cols > 0, output columns
      * [g*a_group_cols, (g+1)*a_group_cols) contract the A columns [g*Kp, (g+1)*Kp) of a WIDER operand of padded width a_kp
@@ -222,6 +226,10 @@ int tgp_split_tf32(const float* src, long rows, int K, long ld, int src_is_kn, f
 /* mixed operand (tgp_gemm_args.mixed): K rounded up to 64, and the split of a row-major (rows, K) matrix (zero padded). */
 int tgp_mixed_kpad(int K);
 int tgp_split_mixed(const float* src, long rows, int K, long ld, float* dst, tgp_stream_t stream);
+/* the WEIGHT operand of a tgp_gemm_args.mixed = 2 contraction: same layout, the residual slot in fp16:
+ * [fp16(w) | bf16(w) | fp16(w - fp16(w)) | unused] (the weights of the heads' 1x1 convolutions, PoseR.py / PoseTs.py /
+ * FaceRecon.py:89-167, folded and packed once). */
+int tgp_split_mixed_w16(const float* src, long rows, int K, long ld, float* dst, tgp_stream_t stream);
 /* transposed mixed operand, K-blocked: dst = tgp_split_mixed_t_bytes(rows, K) bytes (128-byte aligned), 16-bit slots
  * [part 0..2][ceil(rows/64)][ceil256(K)][64]: per block of 64 source rows a dense (ceil256(K) x 128 B) matrix for each of
  * fp16(x), bf16(x), bf16(x - fp16(x)); source rows past `rows` are zero.  Operand of tgp_gemm_tn_tc(mixed = 1). */

@@ -734,6 +734,46 @@ def test_face_enc_coordinate_work_ahead_is_bit_equal():
     assert torch.equal(states[0], states[1])
 
 
+@pytest.mark.parametrize("M,K,N", [(1028, 1289, 512), (4112, 1024, 256), (300, 64, 128)])
+def test_gemm_mixed_w16_operands(ops, M, K, N):
+    """mixed = 2: the weight operand carries its residual in fp16 (tgp_split_mixed_w16), the third pass is fp16(a).lo16(b), and
+    producers may leave the bf16(x) slot of the activation operand out (output mode 5).  Same error bound as mixed = 1 against
+    an fp64 product; a mode-5 operand (its bf16 slot pre-filled with NaN patterns, never written, never read) feeds a second
+    contraction."""
+    g = torch.Generator().manual_seed(M + K + N + 1)
+    A = torch.randn(M, K, generator=g).cuda()
+    W = (torch.randn(N, K, generator=g) * 0.05).cuda()
+    bias = torch.randn(N, generator=g).cuda()
+    ref = A.double() @ W.double().t() + bias.double()
+    out = torch.empty(M, N, device="cuda")
+    ops.gemm(None, W, True, [(0, N, out, 0, 0)], bias=bias, K=K, A_split=ops.split_mixed(A), B_split=ops.split_mixed(W, w16=True),
+             mixed=2)
+    scale = float(ref.abs().max())
+    assert float((out.double() - ref).abs().max()) <= 1.6e-5 * scale
+    kp = ops.mixed_kpad(N)
+    mix = torch.full((M, 2 * kp), float("nan"), device="cuda")
+    ops.gemm(None, W, True, [(0, N, mix, 5, kp)], bias=bias, K=K, A_split=ops.split_mixed(A), B_split=ops.split_mixed(W, w16=True),
+             mixed=2)
+    m16 = mix.view(torch.int16)
+    full = ops.split_mixed(out).view(torch.int16)
+    assert torch.equal(m16[:, :N], full[:, :N]) and torch.equal(m16[:, 2 * kp:2 * kp + N], full[:, 2 * kp:2 * kp + N])
+    fill = torch.full((1, 2 * kp), float("nan"), device="cuda").view(torch.int16)
+    assert torch.equal(m16[:, kp:kp + N], fill[:, kp:kp + N].expand(M, -1))                # the bf16(x) slot was left alone
+    if kp != N:
+        mix.view(torch.int16)[:, N:kp] = 0
+        mix.view(torch.int16)[:, 2 * kp + N:3 * kp] = 0                                     # (padding columns of the operand)
+    W2 = (torch.randn(64, N, generator=g) * 0.1).cuda()
+    out2 = torch.empty(M, 64, device="cuda")
+    ops.gemm(None, W2, True, [(0, 64, out2, 0, 0)], K=N, A_split=mix, B_split=ops.split_mixed(W2, w16=True), mixed=2)
+    ref2 = out.double() @ W2.double().t()
+    assert bool(torch.isfinite(out2).all())
+    assert float((out2.double() - ref2).abs().max()) <= 1.6e-5 * float(ref2.abs().max())
+    # modes 4 and 5 do not mix in one launch
+    with pytest.raises(RuntimeError):
+        ops.gemm(None, W, True, [(0, N // 2, mix, 5, kp), (N // 2, N, mix[:, N // 4:], 4, kp)], K=K, A_split=ops.split_mixed(A),
+                 B_split=ops.split_mixed(W, w16=True), mixed=2)
+
+
 def test_gemm_mixed_operands_range(ops):
     """fp16(x) saturates instead of overflowing (the bf16 residual carries the remainder) and tiny values keep their relative
     accuracy through the residual: rows scaled by 1e5 / 1e-6 stay finite and accurate."""

@@ -80,6 +80,7 @@ SIGNATURES = {
     "tgp_decode_max": (c_int, [c_void_p, c_long, c_void_p, c_void_p]),
     "tgp_mixed_kpad": (c_int, [c_int]),
     "tgp_split_mixed": (c_int, [c_void_p, c_long, c_int, c_long, c_void_p, c_void_p]),
+    "tgp_split_mixed_w16": (c_int, [c_void_p, c_long, c_int, c_long, c_void_p, c_void_p]),
     "tgp_split_mixed_t": (c_int, [c_void_p, c_long, c_int, c_long, c_void_p, c_void_p]),
     "tgp_split_mixed_t_bytes": (c_size_t, [c_long, c_int]),
     "tgp_split_tf32_t": (c_int, [c_void_p, c_long, c_int, c_long, c_void_p, c_void_p]),

@@ -81,10 +81,12 @@ __device__ __forceinline__ uint16_t bf16_bits(float v) {
     return h;
 }
 // one value -> slot `col` of the row starting at `row16`
-__device__ __forceinline__ void mixed_store1(uint16_t* row16, int Kp, int col, float v) {
+// nb: leave the bf16(x) slot unwritten -- the operand of a contraction whose WEIGHTS carry their residual in fp16
+// (tgp_gemm_args.mixed == 2: the third pass is fp16(a).fp16lo(b) and never reads bf16(a))
+__device__ __forceinline__ void mixed_store1(uint16_t* row16, int Kp, int col, float v, bool nb = false) {
     float hi;
     row16[col] = mixed_hi16(v, hi);
-    row16[Kp + col] = bf16_bits(v);
+    if (!nb) row16[Kp + col] = bf16_bits(v);
     row16[2 * Kp + col] = bf16_bits(v - hi);
 }
 // two values -> packed fp16x2 (saturating; x in the low half) and their fp32 read-back
@@ -92,6 +94,11 @@ __device__ __forceinline__ uint32_t mixed_hi16x2(float x, float y, float& hx, fl
     uint32_t d;
     asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(y), "f"(x));
     asm("{\n\t.reg .b16 l, h;\n\tmov.b32 {l, h}, %2;\n\tcvt.f32.f16 %0, l;\n\tcvt.f32.f16 %1, h;\n\t}" : "=f"(hx), "=f"(hy) : "r"(d));
+    return d;
+}
+__device__ __forceinline__ uint32_t f16x2_bits(float x, float y) {
+    uint32_t d;
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(y), "f"(x));
     return d;
 }
 __device__ __forceinline__ uint32_t bf16x2_bits(float x, float y) {
@@ -112,11 +119,11 @@ __device__ __forceinline__ void mixed_store4(uint16_t* row16, int Kp, int col, f
 __device__ __forceinline__ void st_cs_u2(void* p, uint32_t a, uint32_t b) {
     asm volatile("st.global.cs.v2.b32 [%0], {%1, %2};" ::"l"(p), "r"(a), "r"(b) : "memory");
 }
-__device__ __forceinline__ void mixed_store4_cs(uint16_t* row16, int Kp, int col, float4 v) {
+__device__ __forceinline__ void mixed_store4_cs(uint16_t* row16, int Kp, int col, float4 v, bool nb = false) {
     float h0, h1, h2, h3;
     const uint32_t a01 = mixed_hi16x2(v.x, v.y, h0, h1), a23 = mixed_hi16x2(v.z, v.w, h2, h3);
     st_cs_u2(row16 + col, a01, a23);
-    st_cs_u2(row16 + Kp + col, bf16x2_bits(v.x, v.y), bf16x2_bits(v.z, v.w));
+    if (!nb) st_cs_u2(row16 + Kp + col, bf16x2_bits(v.x, v.y), bf16x2_bits(v.z, v.w));
     st_cs_u2(row16 + 2 * Kp + col, bf16x2_bits(v.x - h0, v.y - h1), bf16x2_bits(v.z - h2, v.w - h3));
 }
 

@@ -391,10 +391,10 @@ int tgp_gemm_validate(const tgp_gemm_args* a) {
             return fail(TGP_EINVAL, "tgp_gemm: bad output segment");
         if (sg.mode == 1 && (sg.slab_width <= 0 || (sg.col_end - sg.col_begin) % sg.slab_width))
             return fail(TGP_EINVAL, "tgp_gemm: slab segment must be a multiple of slab_width");
-        if (sg.mode < 0 || sg.mode > 4) return fail(TGP_EINVAL, "tgp_gemm: bad segment mode");
-        if (sg.mode == 4 && (sg.slab_width % 64 || sg.slab_width < sg.col_end - sg.col_begin || sg.ld != 2L * sg.slab_width))
+        if (sg.mode < 0 || sg.mode > 5) return fail(TGP_EINVAL, "tgp_gemm: bad segment mode");
+        if (sg.mode >= 4 && (sg.slab_width % 64 || sg.slab_width < sg.col_end - sg.col_begin || sg.ld != 2L * sg.slab_width))
             return fail(TGP_EINVAL, "tgp_gemm: mixed segment needs slab_width = tgp_mixed_kpad(width) and ld = 2*slab_width");
-        if (sg.mode == 4 && !(a->A_split && a->B_split)) return fail(TGP_EINVAL, "tgp_gemm: mixed output is written by the tensor-core path only");
+        if (sg.mode >= 4 && !(a->A_split && a->B_split)) return fail(TGP_EINVAL, "tgp_gemm: mixed output is written by the tensor-core path only");
         if (sg.mode == 3 && a->rows_per_group < 32) return fail(TGP_EINVAL, "tgp_gemm: column-max segment needs rows_per_group >= 32");
         if (sg.mode == 2 && sg.slab_width < sg.col_end - sg.col_begin) return fail(TGP_EINVAL, "tgp_gemm: split segment wider than Kp");
     }

@@ -51,8 +51,8 @@ struct EpiDst {
 };
 
 // MIXED operand row (common.cuh); p = address of the fp32 slot `rel` of the row, i.e. row base + rel floats
-__device__ __forceinline__ void store_mixed(float* p, int Kp, int rel, float v) {
-    mixed_store1(reinterpret_cast<uint16_t*>(p - rel), Kp, rel, v);
+__device__ __forceinline__ void store_mixed(float* p, int Kp, int rel, float v, bool nb = false) {
+    mixed_store1(reinterpret_cast<uint16_t*>(p - rel), Kp, rel, v, nb);
 }
 
 // order-preserving float -> int map for atomicMax (mode 3): signed-int order == float order
@@ -61,10 +61,10 @@ __device__ __forceinline__ int enc_ordered(float v) {
     return i >= 0 ? i : i ^ 0x7fffffff;
 }
 
-__device__ __forceinline__ void epi_store(EpiDst& d, float v) {
+__device__ __forceinline__ void epi_store(EpiDst& d, float v, bool nb) {
     if (d.p) {
         if (d.mix) {
-            store_mixed(d.p, d.mix, d.rel, v);
+            store_mixed(d.p, d.mix, d.rel, v, nb);
         } else if (d.lo) {
             uint32_t hb;
             asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v));
@@ -82,7 +82,7 @@ __device__ __forceinline__ void epi_store(EpiDst& d, float v) {
 template <bool D1, bool MX>
 __device__ __forceinline__ void epi_rows(uint32_t stg_addr, int lane, int nrows, float bias, float sc, float sh,
                                          float slope, float gbv0, float gbv1, int gb_switch, const float* r1p,
-                                         long ld1, const float* r2p, long ld2, EpiDst d0, EpiDst d1) {
+                                         long ld1, const float* r2p, long ld2, EpiDst d0, EpiDst d1, bool nb) {
     float mx0 = -CUDART_INF_F, mx1 = -CUDART_INF_F;
     const bool is_max = MX && d0.lo < 0;
 #pragma unroll 1
@@ -109,8 +109,8 @@ __device__ __forceinline__ void epi_rows(uint32_t stg_addr, int lane, int nrows,
                 if (MX && is_max) {
                     if ((rr0 + u) >= gb_switch) mx1 = fmaxf(mx1, v); else mx0 = fmaxf(mx0, v);
                 } else {
-                    epi_store(d0, v);
-                    if (D1) epi_store(d1, v);
+                    epi_store(d0, v, nb);
+                    if (D1) epi_store(d1, v, nb);
                 }
             }
         }
@@ -145,7 +145,7 @@ __device__ __forceinline__ float act1(float v, float sc, float sh, float sl) {
     v = fmaf(v, sc, sh);
     return v > 0.f ? v : v * sl;
 }
-__device__ __forceinline__ void vstore(const VDst& d, int row, float4 v) {
+__device__ __forceinline__ void vstore(const VDst& d, int row, float4 v, bool nb) {
     if (d.kind == 1) {
         *reinterpret_cast<float4*>(d.p + row * d.rs) = v;
     } else if (d.kind == 2) {
@@ -159,7 +159,7 @@ __device__ __forceinline__ void vstore(const VDst& d, int row, float4 v) {
         *reinterpret_cast<float4*>(q) = hi;
         *reinterpret_cast<float4*>(q + d.lo) = lo;
     } else if (d.kind == 4) {
-        mixed_store4_cs(reinterpret_cast<uint16_t*>(d.p + row * d.rs - d.rel), d.lo, d.rel, v);
+        mixed_store4_cs(reinterpret_cast<uint16_t*>(d.p + row * d.rs - d.rel), d.lo, d.rel, v, nb);
     }
 }
 
@@ -180,7 +180,7 @@ __device__ __forceinline__ void epi_stage_vec(uint32_t stg_addr, const uint32_t 
 template <bool LEAN>
 __device__ __forceinline__ void epi_chunk_vec(const tgp_gemm_args& g, uint32_t stg_addr, int lane,
                                               long row0, int nrows, int colbase, long grp0, int gb_switch, long zoff, int dbg = 0,
-                                              int ri1 = 0, int ri2 = 0) {
+                                              int ri1 = 0, int ri2 = 0, bool nb = false) {
     const int c4i = lane & 7, rsub = lane >> 3;
     const int col = colbase + c4i * 4;
     const bool live = col < g.Ncols && nrows > 0;     // row blocks past M must not touch group_bias / residual rows
@@ -212,7 +212,7 @@ __device__ __forceinline__ void epi_chunk_vec(const tgp_gemm_args& g, uint32_t s
                     d.rs = w;
                     d.p = g.seg[s].ptr + ((long)cg * g.M + row0) * w + rr;
                 } else {
-                    d.kind = g.seg[s].mode == 2 ? 2 : (g.seg[s].mode == 4 ? 4 : 1);
+                    d.kind = g.seg[s].mode == 2 ? 2 : (g.seg[s].mode >= 4 ? 4 : 1);
                     d.rs = g.seg[s].ld;
                     d.p = g.seg[s].ptr + zoff + row0 * d.rs + rel;
                     d.lo = g.seg[s].slab_width;
@@ -256,7 +256,7 @@ __device__ __forceinline__ void epi_chunk_vec(const tgp_gemm_args& g, uint32_t s
                     if (d0.kind == 3) {            // per-cloud column max: nothing is stored, the running maxima go out below
                         float4& m = row >= gb_switch ? mx1 : mx0;
                         m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
-                    } else if (!(dbg & 8)) vstore(d0, row, v);
+                    } else if (!(dbg & 8)) vstore(d0, row, v, nb);
                     else if (v.x == 1.2345e33f) d0.p[0] = v.y;       // (profiling switch: keep the arithmetic, drop the stores)
                 }
             }
@@ -282,8 +282,8 @@ __device__ __forceinline__ void epi_chunk_vec(const tgp_gemm_args& g, uint32_t s
                 float4 v = f4add(f4add(f4add(a[u], bias), f4add(q1[u], q2[u])), second ? gb1 : gb0);
                 v.x = act1(v.x, sc.x, sh.x, sl.x); v.y = act1(v.y, sc.y, sh.y, sl.y);
                 v.z = act1(v.z, sc.z, sh.z, sl.z); v.w = act1(v.w, sc.w, sh.w, sl.w);
-                vstore(d0, row, v);
-                vstore(d1, row, v);
+                vstore(d0, row, v, nb);
+                vstore(d1, row, v, nb);
                 if (any_max) {
                     float4& m = second ? mx1 : mx0;
                     m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
@@ -354,7 +354,7 @@ __device__ __forceinline__ FastDst fast_entry(const tgp_gemm_args& g, int col, l
         d.rs = (int)w;
         d.p = sg.ptr + ((long)cg * g.M + row0) * w + rr;
     } else {
-        d.kind = sg.mode == 2 ? 2 : (sg.mode == 4 ? 4 : 1);
+        d.kind = sg.mode == 2 ? 2 : (sg.mode >= 4 ? 4 : 1);
         d.rs = (int)sg.ld;
         d.p = sg.ptr + zoff + row0 * sg.ld + rel;
         d.lo = sg.slab_width;
@@ -366,7 +366,7 @@ __device__ __forceinline__ float4 ldg128(const float* p) { return __ldg(reinterp
 
 template <bool ACT, int KIND>
 __device__ __forceinline__ void epi_fast_rows(uint32_t ld_even, uint32_t ld_odd, float* p_r, int rs, int lo, int rel,
-                                              float4 bias, float4 sc, float4 sh, float4 sl) {
+                                              float4 bias, float4 sc, float4 sh, float4 sl, bool nb) {
     float4 a[8];
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
@@ -394,17 +394,17 @@ __device__ __forceinline__ void epi_fast_rows(uint32_t ld_even, uint32_t ld_odd,
             *reinterpret_cast<float4*>(q) = hi;
             *reinterpret_cast<float4*>(q + lo) = lw;
         } else {
-            mixed_store4_cs(reinterpret_cast<uint16_t*>(q - rel), lo, rel, v);
+            mixed_store4_cs(reinterpret_cast<uint16_t*>(q - rel), lo, rel, v, nb);
         }
     }
 }
 
 template <bool ACT>
 __device__ __forceinline__ void epi_fast_kind(int kind, uint32_t ld_even, uint32_t ld_odd, float* p_r, int rs, int lo, int rel,
-                                              float4 bias, float4 sc, float4 sh, float4 sl) {
-    if (kind == 1) epi_fast_rows<ACT, 1>(ld_even, ld_odd, p_r, rs, lo, rel, bias, sc, sh, sl);
-    else if (kind == 2) epi_fast_rows<ACT, 2>(ld_even, ld_odd, p_r, rs, lo, rel, bias, sc, sh, sl);
-    else epi_fast_rows<ACT, 4>(ld_even, ld_odd, p_r, rs, lo, rel, bias, sc, sh, sl);
+                                              float4 bias, float4 sc, float4 sh, float4 sl, bool nb) {
+    if (kind == 1) epi_fast_rows<ACT, 1>(ld_even, ld_odd, p_r, rs, lo, rel, bias, sc, sh, sl, nb);
+    else if (kind == 2) epi_fast_rows<ACT, 2>(ld_even, ld_odd, p_r, rs, lo, rel, bias, sc, sh, sl, nb);
+    else epi_fast_rows<ACT, 4>(ld_even, ld_odd, p_r, rs, lo, rel, bias, sc, sh, sl, nb);
 }
 
 
@@ -440,7 +440,7 @@ template <int KIND, bool BUF, bool BG>
 __device__ __forceinline__ void epi_fast_res_rows(uint32_t ld_even, uint32_t ld_odd, float* p_r, int rs, int lo, int rel, int rsub,
                                                   float4 bias, float4 sc, float4 sh, float4 sl, const float* r1c, long ld1, int ri1,
                                                   const float* r2c, long ld2, int ri2, float4 gb0, float4 gb1, int gb_switch,
-                                                  uint32_t rb_lane = 0, bool has_next = false) {
+                                                  bool nb, uint32_t rb_lane = 0, bool has_next = false) {
     float4 mx0 = make_float4(-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F), mx1 = mx0;
     const long step = 4L * rs;
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -494,7 +494,7 @@ __device__ __forceinline__ void epi_fast_res_rows(uint32_t ld_even, uint32_t ld_
                 *reinterpret_cast<float4*>(q) = hi;
                 *reinterpret_cast<float4*>(q + lo) = lw;
             } else if (KIND == 4) {
-                mixed_store4_cs(reinterpret_cast<uint16_t*>(q - rel), lo, rel, v);
+                mixed_store4_cs(reinterpret_cast<uint16_t*>(q - rel), lo, rel, v, nb);
             } else {
                 float4& m = second ? mx1 : mx0;
                 m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
@@ -528,7 +528,8 @@ __device__ __forceinline__ void epi_fast_res_rows(uint32_t ld_even, uint32_t ld_
     }
 }
 
-template <int BN>
+// NB: the launch's mixed destinations leave out the bf16(x) slot (output mode 5; see tgp_gemm_args.mixed == 2)
+template <int BN, bool NB>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmA16, const __grid_constant__ CUtensorMap tmB16,
@@ -584,7 +585,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             tc_mbar_wait(empty + stage, phase ^ 1);
                             unsigned char* sa = base + stage * STAGE_BYTES;
                             tc_mbar_expect_tx(full + stage, STAGE_BYTES);
-                            const int a_part = u == 0 ? 0 : (u == 1 ? 2 : 1), b_part = u == 0 ? 0 : (u == 1 ? 1 : 2);
+                            // (mixed == 2: the weights' residual slot is fp16, so the third pass pairs it with fp16(a) again)
+                            const int a_part = u == 0 ? 0 : (u == 1 ? 2 : (g.mixed == 2 ? 0 : 1)), b_part = u == 0 ? 0 : (u == 1 ? 1 : 2);
                             if (P.blocked == 2) {
                                 // ROW-MAJOR mixed operands read in place as MN-major tiles (tgp_gemm_tn_tc_rm): the contraction
                                 // runs over the ROWS; a stage = 64 rows x (128 | BN) columns of one 16-bit part, fetched as
@@ -660,7 +662,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     tc_fence_after();
                     const uint32_t sa = s_u32(base + stage * STAGE_BYTES);
                     const uint64_t adesc = make_sw128_desc(sa), bdesc = make_sw128_desc(sa + TC_A_BYTES);
-                    const uint32_t id = u3 == 0 ? idesc_h : idesc16;
+                    const uint32_t id = (u3 == 0 || (u3 == 2 && g.mixed == 2)) ? idesc_h : idesc16;
                     if (++u3 == 3) u3 = 0;
                     if (g.mixed && P.blocked == 2) {
                         // MN-major A and B (instruction-descriptor bits 15 / 16); 64 contraction rows per stage = 4 x K16,
@@ -817,7 +819,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             const float* r1c = g.res1 ? g.res1 + col : nullptr;
                             const float* r2c = g.res2 ? g.res2 + col : nullptr;
 #define TGP_FAST_RES(KD, BF, BGF, ...) epi_fast_res_rows<KD, BF, BGF>(ld_even, ld_odd, p_r, rs, lo, rel, rsub, bias, sc, sh, sl, r1c, g.ld_res1, \
-                                                                      ri1, r2c, g.ld_res2, ri2, gb0, gb1, gb_switch, ##__VA_ARGS__)
+                                                                      ri1, r2c, g.ld_res2, ri2, gb0, gb1, gb_switch, NB, ##__VA_ARGS__)
                             if (res_buf) {
                                 if (pf != ci) {      // (the chunk before this one did not take the fast path: request now)
                                     res_prefetch_half(rb_lane, 0, r1c, g.ld_res1, ri1, r2c, g.ld_res2, ri2, rsub, true);
@@ -854,18 +856,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             const float4 sc = g.scale ? ldg128(g.scale + col) : make_float4(1.f, 1.f, 1.f, 1.f);
                             const float4 sh = g.scale ? ldg128(g.shift + col) : zero4;
                             const float4 sl = g.neg_slope ? ldg128(g.neg_slope + col) : make_float4(s0, s0, s0, s0);
-                            epi_fast_kind<true>(k0, ld_even, ld_odd, p_r, rs, lo, rel, bias, sc, sh, sl);
+                            epi_fast_kind<true>(k0, ld_even, ld_odd, p_r, rs, lo, rel, bias, sc, sh, sl, NB);
                         } else {
-                            epi_fast_kind<false>(k0, ld_even, ld_odd, p_r, rs, lo, rel, bias, zero4, zero4, zero4);
+                            epi_fast_kind<false>(k0, ld_even, ld_odd, p_r, rs, lo, rel, bias, zero4, zero4, zero4, NB);
                         }
                         done = true;
                     }
                 }
                 if (done) {
                 } else if (path == 2) {
-                    epi_chunk_vec<true>(g, stg_addr, lane, row0, nrows, n0 + c0, grp0, gb_switch, z * zstride, dbg);
+                    epi_chunk_vec<true>(g, stg_addr, lane, row0, nrows, n0 + c0, grp0, gb_switch, z * zstride, dbg, 0, 0, NB);
                 } else if (path == 1) {
-                    epi_chunk_vec<false>(g, stg_addr, lane, row0, nrows, n0 + c0, grp0, gb_switch, z * zstride, 0, ri1, ri2);
+                    epi_chunk_vec<false>(g, stg_addr, lane, row0, nrows, n0 + c0, grp0, gb_switch, z * zstride, 0, ri1, ri2, NB);
                 } else {
                     const int col = n0 + c0 + lane;
                     const bool live = col < g.Ncols && nrows > 0 && !(dbg & 1);
@@ -898,7 +900,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                     d.rs = g.seg[s].ld;
                                     d.p = g.seg[s].ptr + z * zstride + row0 * d.rs + rel;
                                     d.lo = g.seg[s].mode == 2 ? g.seg[s].slab_width : 0;
-                                    if (g.seg[s].mode == 4) { d.mix = g.seg[s].slab_width; d.rel = rel; }
+                                    if (g.seg[s].mode >= 4) { d.mix = g.seg[s].slab_width; d.rel = rel; }
                                 }
                                 if (!d0.p) d0 = d; else d1 = d;     // at most two destinations per column (raw + split)
                             }
@@ -921,13 +923,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     const int nr = live ? nrows : 0;
                     if (__any_sync(0xffffffffu, d0.p != nullptr && d0.lo < 0))
                         epi_rows<true, true>(stg_addr, lane, nr, bias, sc, sh, slope, gbv0, gbv1, gb_switch, r1p, g.ld_res1, r2p,
-                                             g.ld_res2, d0, d1);
+                                             g.ld_res2, d0, d1, NB);
                     else if (__any_sync(0xffffffffu, d1.p != nullptr))
                         epi_rows<true, false>(stg_addr, lane, nr, bias, sc, sh, slope, gbv0, gbv1, gb_switch, r1p, g.ld_res1, r2p,
-                                       g.ld_res2, d0, d1);
+                                       g.ld_res2, d0, d1, NB);
                     else
                         epi_rows<false, false>(stg_addr, lane, nr, bias, sc, sh, slope, gbv0, gbv1, gb_switch, r1p, g.ld_res1, r2p,
-                                        g.ld_res2, d0, d1);
+                                        g.ld_res2, d0, d1, NB);
                 }
                 __syncwarp();
             }
@@ -1088,6 +1090,33 @@ split_mixed_transpose_kernel(const float* __restrict__ src, long rows, int K, lo
     }
 }
 
+// WEIGHT operand of a mixed == 2 contraction: [fp16(w) | bf16(w) | fp16(w - fp16(w)) | unused] -- the residual in fp16 (fp16
+// subnormals keep |w - hi - lo| <= 2^-25, i.e. ~2^-20 of a weight of size 0.03), so that the third pass can pair it with the
+// activations' fp16 slot and the activations need no bf16(x) slot at all
+__global__ void __launch_bounds__(256)
+split_mixed_w16_kernel(const float* __restrict__ src, long rows, int K, long ld, int Kp, float* __restrict__ dst) {
+    for (long r = blockIdx.x; r < rows; r += gridDim.x) {
+        uint16_t* d = reinterpret_cast<uint16_t*>(dst + r * 2 * Kp);
+        for (int k = threadIdx.x * 2; k < Kp; k += blockDim.x * 2) {
+            const float x = k < K ? __ldg(src + r * ld + k) : 0.f, y = k + 1 < K ? __ldg(src + r * ld + k + 1) : 0.f;
+            float hx, hy;
+            *reinterpret_cast<uint32_t*>(d + k) = mixed_hi16x2(x, y, hx, hy);
+            *reinterpret_cast<uint32_t*>(d + Kp + k) = bf16x2_bits(x, y);
+            *reinterpret_cast<uint32_t*>(d + 2 * Kp + k) = f16x2_bits(x - hx, y - hy);
+        }
+    }
+}
+
+extern "C" int tgp_split_mixed_w16(const float* src, long rows, int K, long ld, float* dst, tgp_stream_t stream) {
+    if (!src || !dst) return fail(TGP_EINVAL, "tgp_split_mixed_w16: null pointer");
+    if (rows <= 0 || K <= 0) return fail(TGP_EINVAL, "tgp_split_mixed_w16: sizes must be positive");
+    if ((uintptr_t)dst % 16) return fail(TGP_EINVAL, "tgp_split_mixed_w16: dst must be 16-byte aligned");
+    const int Kp = (K + 63) / 64 * 64;
+    long nb = rows < (long)TGP_NUM_SMS * 64 ? rows : (long)TGP_NUM_SMS * 64;
+    split_mixed_w16_kernel<<<(unsigned)nb, 256, 0, as_stream(stream)>>>(src, rows, K, ld, Kp, dst);
+    return check_launch("split_mixed_w16_kernel");
+}
+
 static long mixed_t_rows(int K) { return ((long)K + 255) / 256 * 256; }
 
 extern "C" size_t tgp_split_mixed_t_bytes(long rows, int K) {
@@ -1217,9 +1246,14 @@ static int launch_tc(const tgp_gemm_args* a, cudaStream_t st, int ksplit = 1, in
     const int num_tiles = tiles_mn * ksplit;
     const long zstride = ksplit > 1 ? a->M * (long)a->seg[0].ld : 0;
     const size_t smem = (size_t)TcStages<BN>::value * (TC_A_BYTES + BN * TC_BK * 4) + 1024 + 256 + TC_EPI_WARPS * 32 * 33 * sizeof(float);
-    static std::atomic<unsigned long long> attr_set{0};   // one bit per device: function attributes are per device
-    if (first_on_device(attr_set)) {
-        cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    // mixed destinations without the bf16(x) slot (mode 5) select the NB instantiation; the two kinds do not mix in one launch
+    bool nb = false, m4 = false;
+    for (int s = 0; s < a->nseg; ++s) { nb = nb || a->seg[s].mode == 5; m4 = m4 || a->seg[s].mode == 4; }
+    if (nb && m4) return fail(TGP_EINVAL, "tgp_gemm: output modes 4 and 5 cannot be combined in one launch");
+    static std::atomic<unsigned long long> attr_set[2];   // one bit per device: function attributes are per device
+    if (first_on_device(attr_set[nb ? 1 : 0])) {
+        if (nb) cudaFuncSetAttribute(gemm_tc_kernel<BN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        else cudaFuncSetAttribute(gemm_tc_kernel<BN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     }
     const int grid = num_tiles < TGP_NUM_SMS ? num_tiles : TGP_NUM_SMS;
     // 128-bit epilogue: every width / boundary / leading dimension a multiple of 4 floats, every pointer 16-byte aligned
@@ -1233,7 +1267,7 @@ static int launch_tc(const tgp_gemm_args* a, cudaStream_t st, int ksplit = 1, in
         if (sg.mode == 3) continue;
         vec_ok = vec_ok && al16(sg.ptr);
         if (sg.mode == 1) vec_ok = vec_ok && sg.slab_width % 4 == 0;
-        else vec_ok = vec_ok && sg.ld % 4 == 0 && ((sg.mode != 2 && sg.mode != 4) || sg.slab_width % 4 == 0);
+        else vec_ok = vec_ok && sg.ld % 4 == 0 && ((sg.mode != 2 && sg.mode < 4) || sg.slab_width % 4 == 0);
     }
     if (vec_ok && !a->res1 && !a->res2 && !a->group_bias) {
         // lean epilogue: one destination per column (segments disjoint; raw / slab / split / mixed / column max)
@@ -1280,7 +1314,8 @@ static int launch_tc(const tgp_gemm_args* a, cudaStream_t st, int ksplit = 1, in
     int nst = TcStages<BN>::value;      // operand ring depth in use (<= the depth the shared memory is carved for)
     { const char* e = getenv("TGP_TC_NST"); if (e && atoi(e) >= 2 && atoi(e) < nst) nst = atoi(e); }
     if (vec_ok == 5) nst = 2;
-    gemm_tc_kernel<BN><<<grid, TC_THREADS, smem, st>>>(tmA, tmB, tmA16, tmB16, P, Kp, num_n_tiles, num_tiles, dbg, tiles_mn, kb_per, zstride, vec_ok, nst);
+    if (nb) gemm_tc_kernel<BN, true><<<grid, TC_THREADS, smem, st>>>(tmA, tmB, tmA16, tmB16, P, Kp, num_n_tiles, num_tiles, dbg, tiles_mn, kb_per, zstride, vec_ok, nst);
+    else gemm_tc_kernel<BN, false><<<grid, TC_THREADS, smem, st>>>(tmA, tmB, tmA16, tmB16, P, Kp, num_n_tiles, num_tiles, dbg, tiles_mn, kb_per, zstride, vec_ok, nst);
     return check_launch("gemm_tc_kernel");
 }
 

@@ -318,7 +318,7 @@ def gemm(A, Bmat, b_is_nk, segs, bias=None, group_bias=None, rows_per_group=0, r
     a.Bmat, a.ldb, a.b_is_nk = Bmat.data_ptr(), Bmat.stride(0), 1 if b_is_nk else 0
     if A_split is not None and B_split is not None:
         a.A_split, a.B_split = A_split.data_ptr(), B_split.data_ptr()
-    a.mixed = 1 if mixed else 0
+    a.mixed = int(mixed)          # 0: 3xTF32 operands, 1: mixed, 2: mixed with a w16 weight operand (third pass fp16(a).lo16(b))
     a.a_kp, a.a_group_cols = int(a_kp), int(a_group_cols)      # block-diagonal contraction (tgp_gemm_args.a_group_cols)
     if mixed:
         assert A_split is not None and B_split is not None, "mixed operands must be supplied (split_mixed / mode-4 epilogue)"
@@ -342,7 +342,7 @@ def gemm(A, Bmat, b_is_nk, segs, bias=None, group_bias=None, rows_per_group=0, r
     a.neg_slope = neg_slope.data_ptr() if neg_slope is not None else None
     a.nseg = len(segs)
     for i, (c0, c1, t, mode, sw) in enumerate(segs):
-        a.seg[i] = OutSeg(c0, c1, mode, sw, t.stride(0) if mode in (0, 2, 4) else 0, t.data_ptr())
+        a.seg[i] = OutSeg(c0, c1, mode, sw, t.stride(0) if mode in (0, 2, 4, 5) else 0, t.data_ptr())
     name = "gemm_tc" if A_split is not None and B_split is not None else "gemm"
     if EVENT_LOG is not None:
         # algo_flops: flops of the REFERENCE's contraction this launch stands for, when the launch is a factored piece of it
@@ -365,13 +365,15 @@ def mixed_kpad(K):
     return _lib.load().tgp_mixed_kpad(K)
 
 
-def split_mixed(x2d):
+def split_mixed(x2d, w16=False):
     """MIXED tensor-core operand of a row-major (rows, K) matrix (include/tgpose_b200.h, tgp_gemm_args.mixed):
-    (rows, 2*mixed_kpad(K)) fp32 slots = 16-bit slots [fp16(x) | bf16(x) | bf16(x - fp16(x)) | unused]."""
+    (rows, 2*mixed_kpad(K)) fp32 slots = 16-bit slots [fp16(x) | bf16(x) | bf16(x - fp16(x)) | unused].
+    w16: the weight operand of a mixed = 2 contraction (residual slot in fp16, tgp_split_mixed_w16)."""
     assert x2d.stride(-1) == 1
     rows, K = x2d.shape
     dst = torch.empty((rows, 2 * mixed_kpad(K)), dtype=torch.float32, device=x2d.device)
-    _run("split_mixed", _lib.load().tgp_split_mixed, _p(x2d), rows, K, x2d.stride(0), _p(dst), _stream())
+    lib = _lib.load()
+    _run("split_mixed", lib.tgp_split_mixed_w16 if w16 else lib.tgp_split_mixed, _p(x2d), rows, K, x2d.stride(0), _p(dst), _stream())
     return dst
 
 

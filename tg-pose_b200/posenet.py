@@ -59,7 +59,8 @@ class _Packed:
                                 for m, sl in zip(mats, slopes)]).contiguous()
         # the heads' contractions run on MIXED operands (TF32 + bf16 cross terms): two TF32-pass equivalents instead of
         # three at ~2^-19 relative error per product; nothing downstream of the heads is a neighbour search
-        self.w_split = ops.split_mixed(self.w)
+        # (weight operand of a mixed = 2 contraction: residual slot in fp16, so the activations need no bf16(x) slot)
+        self.w_split = ops.split_mixed(self.w, w16=True)
 
     @classmethod
     def from_matrix(cls, w, scale=None, shift=None, slope=None):
@@ -69,7 +70,7 @@ class _Packed:
         pk.scale = scale.contiguous() if scale is not None else None
         pk.shift = shift.contiguous() if shift is not None else None
         pk.slope = slope.contiguous() if slope is not None else None
-        pk.w_split = ops.split_mixed(pk.w)
+        pk.w_split = ops.split_mixed(pk.w, w16=True)
         return pk
 
 
@@ -368,7 +369,7 @@ class PoseNet9D(nn.Module):
                 if shared is None:
                     shared = ops.mixed_buf(M, n_sh * n, dev)
                 # column block j of the shared operand: 16-bit slot offset j*n = float offset j*n/2; slab width = operand Kp
-                segs.append((c0, c0 + n, shared[:, j_sh * n // 2:], 4, ops.mixed_kpad(n_sh * n)))
+                segs.append((c0, c0 + n, shared[:, j_sh * n // 2:], 5, ops.mixed_kpad(n_sh * n)))
                 j_sh += 1
                 res.append(shared)
                 c0 += n
@@ -381,11 +382,11 @@ class PoseNet9D(nn.Module):
                 segs.append((c0, c0 + n, t_, 3, 0))
             else:
                 t_ = ops.mixed_buf(M, n, dev)
-                segs.append((c0, c0 + n, t_, 4, ops.mixed_kpad(n)))
+                segs.append((c0, c0 + n, t_, 5, ops.mixed_kpad(n)))      # mode 5: mixed operand without the bf16(x) slot
             res.append(t_)
             c0 += n
         ops.gemm(None, pk.w, True, segs, scale=pk.scale, shift=pk.shift, neg_slope=pk.slope, K=K,
-                 A_split=x_split, B_split=pk.w_split, rows_per_group=rows_per_group, mixed=True, **kw)
+                 A_split=x_split, B_split=pk.w_split, rows_per_group=rows_per_group, mixed=2, **kw)
         return res
 
     def _forward_fused_eval(self, points, obj_id, enable_proj=False):
@@ -419,8 +420,8 @@ class PoseNet9D(nn.Module):
             nc = c1.w.shape[0]
             P1 = torch.empty((B * N1, nc), dtype=torch.float32, device=xs.device)
             P2 = torch.empty((B * N2, nc), dtype=torch.float32, device=xs.device)
-            ops.gemm(None, c1.w, True, [(0, nc, P1, 0, 0)], K=c1.w.shape[1], A_split=xs1, B_split=c1.w_split, mixed=True, algo_flops=0)
-            ops.gemm(None, c2.w, True, [(0, nc, P2, 0, 0)], K=c2.w.shape[1], A_split=xs2, B_split=c2.w_split, mixed=True, algo_flops=0)
+            ops.gemm(None, c1.w, True, [(0, nc, P1, 0, 0)], K=c1.w.shape[1], A_split=xs1, B_split=c1.w_split, mixed=2, algo_flops=0)
+            ops.gemm(None, c2.w, True, [(0, nc, P2, 0, 0)], K=c2.w.shape[1], A_split=xs2, B_split=c2.w_split, mixed=2, algo_flops=0)
             # rows of P1 / P2 that each level-0 point adds: its nearest coarse point (FaceRecon.py:69-73), as global row numbers
             gi1, gi2 = parts.get("up_rows") or enc.upsample_rows(parts["nn1"], parts["nn2"], N1, N2)
             k1 = len(_FINE_COLS)
@@ -482,7 +483,7 @@ class PoseNet9D(nn.Module):
             hm = torch.full((Bc, 768), -2 ** 31, dtype=torch.int32, device=hid.device)
             p2 = pk["tails2"]
             ops.gemm(None, p2.w, True, [(0, 768, hm, 3, 0)], scale=p2.scale, shift=p2.shift, neg_slope=p2.slope, K=1024,
-                     A_split=hid, B_split=p2.w_split, rows_per_group=N, mixed=True, a_kp=ops.mixed_kpad(3072), a_group_cols=256)
+                     A_split=hid, B_split=p2.w_split, rows_per_group=N, mixed=2, a_kp=ops.mixed_kpad(3072), a_group_cols=256)
             return ops.decode_max(hm)
 
         def tail_fc(pooled3, j, name):
